@@ -1,0 +1,240 @@
+"""Known-answer tests that pin the oracle's operators, restating the reference's own tests.
+
+Reference tests followed (paths relative to /root/reference/tests):
+  test_vlasov1d/test_multispecies_pushers.py:16-140   spectral pushers vs exact characteristic shift
+  test_vlasov1d/test_velocity_cubic_spline.py:20-46   cubic stencil (interpax rule, bit-exact integer shifts)
+  test_base/test_chang_cooper.py:21-74                chang_cooper_delta limits
+  test_vlasov1d/test_fp_momentum_conservation.py:44-83 Dougherty conservation with n(x) != 1
+  test_vlasov1d/test_absorbing_wave.py:33-72          WaveSolver absorbing boundaries
+  test_vlasov1d/test_landau_damping.py:35-88          damping rate / frequency vs analytic root
+"""
+
+from pathlib import Path
+
+import numpy as np
+import pytest
+import scipy.special
+import yaml
+from scipy import optimize
+from scipy.interpolate import CubicHermiteSpline
+
+from oracle import vlasov1d as O
+
+GOLD = Path(__file__).parent / "golden"
+
+
+def test_space_exponential_exact_shift():
+    Lx = 2 * np.pi
+    v = np.array([0.5])
+    for nx in [16, 32]:
+        dx = Lx / nx
+        x = np.linspace(0, Lx - dx, nx)
+        kxr = np.fft.rfftfreq(nx, d=dx) * 2 * np.pi
+        f = np.sin(2 * x)[:, None]
+        out = O.space_exponential(f, kxr, v, 0.01)
+        exact = np.sin(2 * x - 2 * v[0] * 0.01)[:, None]
+        assert np.sqrt(np.mean((out - exact) ** 2)) < 1e-12
+
+
+def test_velocity_exponential_exact_shift_per_species():
+    vmax = 2 * np.pi
+    e = np.array([0.5])
+    dt = 0.01
+    for nv in [16, 32]:
+        dv = 2.0 * vmax / nv
+        v = np.linspace(-vmax + dv / 2, vmax - dv / 2, nv)
+        kvr = np.fft.rfftfreq(nv, d=dv) * 2.0 * np.pi
+        k = np.pi / vmax
+        f = np.sin(k * v)[None, :]
+        for q, m in [(-1.0, 1.0), (1.0, 1836.0)]:
+            out = O.velocity_exponential(f, kvr, e, np.zeros_like(e), dt, q, m)
+            exact = np.sin(k * (v - (q / m) * e[0] * dt))[None, :]
+            assert np.sqrt(np.mean((out - exact) ** 2)) < 1e-12
+
+
+def _interpax_local_cubic(f, shift, v):
+    """Independent restatement of interpax.interp1d(method='cubic', extrap=1e-30) on a uniform grid:
+    cubic Hermite with centred secant-average slopes inside, one-sided slopes at the ends."""
+    out = np.empty_like(f)
+    dv = v[1] - v[0]
+    for i in range(f.shape[0]):
+        d = np.empty_like(v)
+        d[1:-1] = (f[i, 2:] - f[i, :-2]) / (2 * dv)
+        d[0] = (f[i, 1] - f[i, 0]) / dv
+        d[-1] = (f[i, -1] - f[i, -2]) / dv
+        xq = v - shift[i]
+        val = CubicHermiteSpline(v, f[i], d)(xq)
+        out[i] = np.where((xq < v[0]) | (xq > v[-1]), 1e-30, val)
+    return out
+
+
+@pytest.mark.parametrize("vmin, vmax", [(-6.4, 6.4), (-4.0, 8.0)])
+def test_uniform_cubic_interp_matches_local_cubic_rule(vmin, vmax):
+    nx, nv = 8, 64
+    dv = (vmax - vmin) / nv
+    v = np.linspace(vmin + dv / 2.0, vmax - dv / 2.0, nv)
+    f = np.random.default_rng(42).standard_normal((nx, nv))
+    shift = dv * np.array([-70.0, -2.17, -0.37, 0.0, 0.25, 1.13, 3.4, 70.0])
+    np.testing.assert_allclose(O.uniform_cubic_interp(f, shift, dv), _interpax_local_cubic(f, shift, v),
+                               rtol=2e-12, atol=2e-12)
+
+
+def test_uniform_cubic_interp_integer_shifts_bit_exact():
+    nx, nv, dv = 3, 16, 0.25
+    f = np.arange(nx * nv, dtype=np.float64).reshape(nx, nv)
+    actual = O.uniform_cubic_interp(f, dv * np.array([1.0, -1.0, 0.0]), dv)
+    expected = np.empty((nx, nv))
+    expected[0] = np.concatenate(([1.0e-30], f[0, :-1]))
+    expected[1] = np.concatenate((f[1, 1:], [1.0e-30]))
+    expected[2] = f[2]
+    np.testing.assert_array_equal(actual, expected)
+
+
+def test_chang_cooper_delta_limits():
+    w = np.array([1e-10, 1e-9, 1e-8])
+    d = O.chang_cooper_delta(w)
+    e = 0.5 - w / 12.0
+    np.testing.assert_allclose(d[0], e[0], rtol=1e-12)
+    np.testing.assert_allclose(d[1], e[1], rtol=1e-9)
+    np.testing.assert_allclose(d[2], e[2], rtol=1e-7)
+    np.testing.assert_allclose(O.chang_cooper_delta(np.array([0.0])), 0.5, rtol=1e-14)
+    w = np.array([10.0, 100.0, 1000.0])
+    d = O.chang_cooper_delta(w)
+    np.testing.assert_allclose(d[1], 1 / w[1], rtol=1e-6)
+    np.testing.assert_allclose(d[2], 1 / w[2], rtol=1e-12)
+    w = np.array([0.1, 0.5, 1.0, 2.0, -0.1, -0.5, -1.0, -2.0])
+    np.testing.assert_allclose(O.chang_cooper_delta(w), 1.0 / w - 1.0 / np.expm1(w), rtol=1e-14)
+    d = O.chang_cooper_delta(np.linspace(-5, 5, 100))
+    assert np.all(d >= 0) and np.all(d <= 1)
+
+
+def _fp_cfg(nx, nv, vmax, fp_type):
+    dv = 2.0 * vmax / nv
+    v = np.linspace(-vmax + dv / 2.0, vmax - dv / 2.0, nv)
+    return {
+        "grid": {
+            "species_grids": {"electron": {"v": v, "dv": dv, "nv": nv, "vmax": vmax}},
+            "species_params": {"electron": {"charge": -1.0, "mass": 1.0, "charge_to_mass": -1.0, "T0": 1.0}},
+        },
+        "terms": {"fokker_planck": {"is_on": True, "type": fp_type}, "krook": {"is_on": False}},
+    }
+
+
+@pytest.mark.parametrize("fp_type,energy_rtol", [("dougherty", 5e-3), ("chang_cooper_dougherty", 1e-5)])
+def test_dougherty_conservation_with_density_perturbation(fp_type, energy_rtol):
+    nx, nv, vmax = 16, 512, 6.4
+    cfg = _fp_cfg(nx, nv, vmax, fp_type)
+    v = cfg["grid"]["species_grids"]["electron"]["v"]
+    dv = cfg["grid"]["species_grids"]["electron"]["dv"]
+    x = np.linspace(0, 2 * np.pi, nx, endpoint=False)
+    n_prof = 1.0 + 0.5 * np.sin(x)
+    u0 = 0.5
+    f = n_prof[:, None] * np.exp(-((v[None, :] - u0) ** 2) / 2.0)
+    f = f / (np.sum(np.exp(-((v - u0) ** 2) / 2.0)) * dv)
+    coll = O.Collisions(cfg)
+    out = f
+    for _ in range(50):
+        out = coll(np.ones(nx), None, out, 0.1)
+    n0, n1 = np.sum(f, 1) * dv, np.sum(out, 1) * dv
+    p0, p1 = np.sum(f * v, 1) * dv, np.sum(out * v, 1) * dv
+    e0, e1 = np.sum(f * v**2, 1) * dv, np.sum(out * v**2, 1) * dv
+    np.testing.assert_allclose(n1, n0, rtol=1e-10)
+    np.testing.assert_allclose(p1, p0, rtol=1e-6)
+    np.testing.assert_allclose(e1, e0, rtol=energy_rtol)
+    np.testing.assert_allclose(p1 / n1, u0, atol=1e-6)
+
+
+@pytest.mark.parametrize("fp_type", ["lenard_bernstein", "chang_cooper", "dougherty_nodrag", "super_gaussian"])
+def test_other_fp_types_conserve_density(fp_type):
+    nx, nv, vmax = 4, 256, 6.4
+    cfg = _fp_cfg(nx, nv, vmax, fp_type)
+    v = cfg["grid"]["species_grids"]["electron"]["v"]
+    dv = cfg["grid"]["species_grids"]["electron"]["dv"]
+    f = np.exp(-(v[None, :] ** 2) / 2.0) * (1 + 0.1 * np.arange(nx)[:, None])
+    f = f / (np.sum(np.exp(-(v**2) / 2.0)) * dv)
+    out = f
+    coll = O.Collisions(cfg)
+    # nodrag is only O((nu dt)^2)-stationary (implicit diffusion minus explicit Maxwellian diffusion)
+    nu = 0.01 if fp_type == "dougherty_nodrag" else 1.0
+    for _ in range(10):
+        out = coll(nu * np.ones(nx), None, out, 0.1)
+    np.testing.assert_allclose(np.sum(out, 1) * dv, np.sum(f, 1) * dv, rtol=1e-10)
+    # Maxwellian at T=1 is (near) stationary
+    assert np.max(np.abs(out - f)) < 5e-3 * np.max(f)
+
+
+def test_krook_relaxes_to_maxwellian_and_conserves_density():
+    nx, nv, vmax = 4, 128, 6.4
+    cfg = _fp_cfg(nx, nv, vmax, "dougherty")
+    cfg["terms"]["fokker_planck"]["is_on"] = False
+    cfg["terms"]["krook"]["is_on"] = True
+    v = cfg["grid"]["species_grids"]["electron"]["v"]
+    dv = cfg["grid"]["species_grids"]["electron"]["dv"]
+    f = np.exp(-((v[None, :] - 1.0) ** 2) / 0.5) * np.ones((nx, 1))
+    coll = O.Collisions(cfg)
+    out = coll(None, 1e3 * np.ones(nx), f, 1.0)
+    n = np.sum(f, 1) * dv
+    np.testing.assert_allclose(np.sum(out, 1) * dv, n, rtol=1e-12)
+    np.testing.assert_allclose(out, n[:, None] * coll.f_mx, rtol=1e-12, atol=1e-300)
+
+
+def test_absorbing_wave():
+    xmax, xmin, nx, tmax, c = 1000, 0, 1024, 200, 11.3
+    dx = (xmax - xmin) / nx
+    dt = 0.95 * dx / c
+    nt = int(tmax / dt)
+    xax = np.linspace(xmin - dx / 2.0, xmax + dx / 2.0, nx + 2)
+    env = O.SpaceTimeEnvelope(O.Envelope(40.0, 30.0, 5.0), O.Envelope(800.0, 50.0, 10.0))
+    drv = [O.EMDriver(1.0e-4, -1.4, 15.82, 0.0, env)]
+    a, aold = np.zeros_like(xax), np.zeros_like(xax)
+    peak = 0.0
+    # diffrax takes nt+1 steps of dt up to t1=tmax (the last one clipped); the pulse is long gone by then
+    for n in range(nt + 1):
+        djy = O.ey_driver_source(drv, xax, n * dt, 0.0)
+        r = O.wave_solver(a, aold, djy, 0.0, c, dx, dt)
+        a, aold = r["a"], r["prev_a"]
+        peak = max(peak, np.sum(a**2))
+    assert peak > 1e-6  # the pulse did exist
+    np.testing.assert_almost_equal(np.sum(np.square(a)), 0.0, decimal=8)
+
+
+def _dispersion_root(k0):
+    """adept/electrostatic.py:59-122 restated (wp=vth=1, maxwellian_convention_factor=2)."""
+    def Z(x):
+        return scipy.special.wofz(x) * np.sqrt(np.pi) * 1j
+
+    def Zp(x):
+        return -2.0 * (1.0 + x * Z(x))
+
+    chi = (1.0 / k0) ** 2 / 2.0
+    root = optimize.newton(lambda x: 1.0 - chi * Zp(x), np.sqrt(1.0 + 3 * k0**2))
+    return root * k0 * np.sqrt(2.0)
+
+
+@pytest.mark.parametrize("time,field,edfdv", [
+    ("leapfrog", "poisson", "exponential"),
+    ("sixth", "poisson", "cubic-spline"),
+    ("leapfrog", "ampere", "exponential"),
+    ("leapfrog", "hampere", "cubic-spline"),
+])
+def test_landau_damping_rate_matches_analytic_root(time, field, edfdv):
+    with open(GOLD / "resonance.yaml") as fh:
+        deck = yaml.safe_load(fh)
+    k0 = 0.32
+    root = _dispersion_root(k0)
+    deck["terms"].update(time=time, field=field, edfdv=edfdv)
+    if field == "ampere":
+        deck["grid"]["dt"] = 0.025
+    deck["drivers"]["ex"]["0"]["params"]["k0"] = k0
+    deck["drivers"]["ex"]["0"]["params"]["w0"] = float(np.real(root))
+    deck["grid"]["xmax"] = float(2 * np.pi / k0)
+    deck["grid"]["tmax"] = 300.0 if field != "ampere" else 200.0
+    cfg = O.build_cfg(deck)
+    ts = O.save_axis({"nt": 601}, cfg["grid"])
+    _, saved = O.run(cfg, save={"e": (ts, lambda c, y: y["e"].copy())})
+    efs = np.array(saved["e"])
+    ek1 = np.abs(2.0 / cfg["grid"]["nx"] * np.fft.fft(efs, axis=1)[:, 1])
+    dts = ts[1] - ts[0]
+    sl = slice(-100, -50)
+    gamma = np.mean(np.gradient(ek1[sl], dts) / ek1[sl])
+    np.testing.assert_almost_equal(gamma, np.imag(root), decimal=2)
