@@ -1,0 +1,65 @@
+"""ctypes binding of libadept_b200.so (the C ABI declared in include/adept_b200.h).
+
+There is no CPU fallback: if the shared library has not been built (``python -m adept_b200.build`` or
+``__graft_entry__.build()``) or a call fails, a :class:`AdeptB200Error` is raised.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libadept_b200.so"
+
+c_dp = C.c_void_p  # device pointers travel as integers
+c_i, c_d, c_ll = C.c_int, C.c_double, C.c_longlong
+
+# name -> argtypes; mirrors include/adept_b200.h one to one (checked by tests/test_abi.py)
+SIGNATURES = {
+    "adept_b200_version": [],
+    "adept_b200_last_error": [],
+    "adept_b200_prepare": [c_i],
+    "adept_b200_vdfdx_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_d, c_d, c_dp, c_dp],
+    "adept_b200_edfdv_exp_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_dp, c_dp, c_d, c_d, c_d, c_d, c_dp],
+    "adept_b200_edfdv_spline_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_dp, c_dp, c_d, c_d, c_d, c_d, c_dp],
+    "adept_b200_moments_f64": [c_dp, c_i, c_i, c_i, c_dp, c_d, C.POINTER(c_dp), C.POINTER(c_dp), C.POINTER(c_d), c_dp],
+    "adept_b200_poisson_f64": [c_dp, c_dp, c_ll, c_dp, c_i, c_i, c_i, c_d, c_d, c_dp],
+    "adept_b200_axpy_f64": [c_dp, c_dp, c_d, c_dp, c_ll, c_dp],
+    "adept_b200_ponderomotive_f64": [c_dp, c_dp, c_i, c_i, c_d, c_dp],
+    "adept_b200_wave_step_f64": [c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_i, c_i, c_d, c_d, c_d, c_dp],
+    "adept_b200_collide_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_d, c_d, c_dp, c_dp, c_dp, c_i, c_i, c_i, c_d, c_d,
+                               c_dp, c_dp],
+}
+
+
+class AdeptB200Error(RuntimeError):
+    """Raised when libadept_b200.so is missing or an entry point returns a negative error code."""
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load (once) and return the shared library, with argtypes/restype set for every exported symbol."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise AdeptB200Error(
+            f"{LIB_PATH} not found: build the CUDA extension first (python -m adept_b200.build). "
+            "adept_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here means the .so and the header disagree
+        fn.argtypes = argtypes
+        fn.restype = C.c_char_p if name == "adept_b200_last_error" else c_i
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().adept_b200_last_error()
+        raise AdeptB200Error(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")

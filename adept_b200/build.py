@@ -1,0 +1,80 @@
+"""Build libadept_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m adept_b200.build [--verbose] [--force]
+
+The shared library lands next to this file (adept_b200/libadept_b200.so); objects go to adept_b200/csrc/build/.
+"""
+
+from __future__ import annotations
+
+import argparse
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+CSRC = HERE / "csrc"
+LIB = HERE / "libadept_b200.so"
+SOURCES = ["api.cu", "push.cu", "rowops.cu", "field.cu", "collide.cu"]
+NVCC_FLAGS = [
+    "-O3",
+    "-std=c++17",
+    "-gencode",
+    "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    "-Xcompiler",
+    "-fPIC",
+    "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _stale(target: Path, deps) -> bool:
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(Path(d).stat().st_mtime > t for d in deps)
+
+
+def build(verbose: bool = False, force: bool = False) -> Path:
+    nvcc = _nvcc()
+    objdir = CSRC / "build"
+    objdir.mkdir(exist_ok=True)
+    headers = list(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "adept_b200.h"]
+    extra = ["-Xptxas", "-v"] if verbose else []
+
+    def compile_one(src: str):
+        obj = objdir / (src.replace(".cu", ".o"))
+        if force or _stale(obj, [CSRC / src, *headers]):
+            cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", str(CSRC / src), "-o", str(obj)]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                raise RuntimeError(f"nvcc failed for {src}:\n{res.stdout}\n{res.stderr}")
+            if verbose:
+                sys.stderr.write(res.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    if force or _stale(LIB, objs):
+        cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-lcudart"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--force", action="store_true")
+    a = ap.parse_args()
+    print(build(a.verbose, a.force))

@@ -1,0 +1,198 @@
+// extern "C" boundary of libadept_b200.so (see include/adept_b200.h), twiddle-table cache, error reporting.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <mutex>
+#include <vector>
+
+#include "../../include/adept_b200.h"
+#include "common.cuh"
+
+namespace adept {
+
+static thread_local char g_err[512] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    set_last_error("%s: %s", what, cudaGetErrorString(err));
+    return ADEPT_ERR_CUDA;
+  }
+  return ADEPT_OK;
+}
+
+// ---- twiddle tables ------------------------------------------------------------------------------------------
+// Layout must match FftCfg<LOGN> in fft_core.cuh: radix-16 passes then one radix 2^(logn%4) pass (n < 16: one pass);
+// pass p >= 1 stores tw[off_p + (r-1)*Ns + k] = exp(-2 pi i k r / (Ns R)), k < Ns, r = 1..R-1.
+static std::mutex g_tw_mutex;
+static cplx* g_tw[64][16] = {};
+
+static std::vector<int> radices_of(int logn) {
+  std::vector<int> r;
+  const int n = 1 << logn;
+  if (n < 16) {
+    r.push_back(n);
+    return r;
+  }
+  for (int i = 0; i < logn / 4; i++) r.push_back(16);
+  if (logn % 4) r.push_back(1 << (logn % 4));
+  return r;
+}
+
+const cplx* get_twiddles(int logn) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || logn < 1 || logn > 13) {
+    set_last_error("get_twiddles: no CUDA device or unsupported log2(n)=%d", logn);
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  std::lock_guard<std::mutex> lock(g_tw_mutex);
+  if (g_tw[dev][logn]) return g_tw[dev][logn];
+  const std::vector<int> rad = radices_of(logn);
+  std::vector<cplx> host;
+  int ns = rad[0];
+  const long double two_pi = 6.283185307179586476925286766559005768L;
+  for (size_t p = 1; p < rad.size(); p++) {
+    const int R = rad[p];
+    for (int r = 1; r < R; r++)
+      for (int k = 0; k < ns; k++) {
+        const long double ang = two_pi * (long double)((long long)k * r) / (long double)((long long)ns * R);
+        cplx w;
+        w.x = (double)cosl(ang);
+        w.y = (double)(-sinl(ang));
+        host.push_back(w);
+      }
+    ns *= R;
+  }
+  if (host.empty()) host.push_back(make_double2(1.0, 0.0));  // single-pass transforms never read the table
+  cplx* d = nullptr;
+  cudaError_t err = cudaMalloc(&d, host.size() * sizeof(cplx));
+  if (err == cudaSuccess) err = cudaMemcpy(d, host.data(), host.size() * sizeof(cplx), cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) {
+    set_last_error("get_twiddles(2^%d): %s", logn, cudaGetErrorString(err));
+    (void)cudaGetLastError();
+    if (d) cudaFree(d);
+    return nullptr;
+  }
+  g_tw[dev][logn] = d;
+  return d;
+}
+
+// implemented in push.cu / rowops.cu / field.cu / collide.cu
+int vdfdx_f64(const double*, double*, int, int, int, const double*, double, const double*, double, cudaStream_t);
+int edfdv_exp_f64(const double*, double*, int, int, int, const double*, const double*, const double*, double, double,
+                  double, double, cudaStream_t);
+int edfdv_spline_f64(const double*, double*, int, int, int, const double*, const double*, const double*, double,
+                     double, double, double, cudaStream_t);
+int moments_f64(const double*, int, int, int, const double*, double, const double* const*, double* const*,
+                const double*, cudaStream_t);
+int axpy_f64(const double*, const double*, double, double*, long long, cudaStream_t);
+int poisson_dispatch_f64(const double*, const double*, long long, double*, int, int, int, double, double,
+                         cudaStream_t);
+int ponderomotive_f64(const double*, double*, int, int, double, cudaStream_t);
+int wave_step_f64(const double*, const double*, const double*, const double*, const double*, double*, int, int,
+                  double, double, double, cudaStream_t);
+int collide_f64(const double*, double*, int, int, int, const double*, double, double, const double*, const double*,
+                const double*, int, int, int, double, double, double*, cudaStream_t);
+
+}  // namespace adept
+
+using namespace adept;
+
+#define ADEPT_REQUIRE(ptr, name)                           \
+  if (!(ptr)) {                                            \
+    set_last_error("%s: null pointer for %s", __func__, name); \
+    return ADEPT_ERR_BAD_ARG;                              \
+  }
+
+extern "C" {
+
+int adept_b200_version(void) { return 100; }
+
+const char* adept_b200_last_error(void) { return g_err; }
+
+int adept_b200_prepare(int n) {
+  int logn = 0;
+  if (n < 2 || (n & (n - 1))) {
+    set_last_error("prepare: n=%d is not a power of two", n);
+    return ADEPT_ERR_UNSUPPORTED;
+  }
+  while ((1 << logn) < n) logn++;
+  if (logn > 13) {
+    set_last_error("prepare: n=%d exceeds 8192", n);
+    return ADEPT_ERR_UNSUPPORTED;
+  }
+  return get_twiddles(logn) ? ADEPT_OK : ADEPT_ERR_CUDA;
+}
+
+int adept_b200_vdfdx_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* v, double dt,
+                         double k1x, const double* k1x_batch, void* stream) {
+  ADEPT_REQUIRE(f_in, "f_in") ADEPT_REQUIRE(f_out, "f_out") ADEPT_REQUIRE(v, "v")
+  return vdfdx_f64(f_in, f_out, batch, nx, nv, v, dt, k1x_batch, k1x, (cudaStream_t)stream);
+}
+
+int adept_b200_edfdv_exp_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* e,
+                             const double* dex, const double* pond, double charge, double mass, double dt, double k1v,
+                             void* stream) {
+  ADEPT_REQUIRE(f_in, "f_in") ADEPT_REQUIRE(f_out, "f_out") ADEPT_REQUIRE(e, "e")
+  return edfdv_exp_f64(f_in, f_out, batch, nx, nv, e, dex, pond, charge, mass, dt, k1v, (cudaStream_t)stream);
+}
+
+int adept_b200_edfdv_spline_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* e,
+                                const double* dex, const double* pond, double charge, double mass, double dt,
+                                double dv, void* stream) {
+  ADEPT_REQUIRE(f_in, "f_in") ADEPT_REQUIRE(f_out, "f_out") ADEPT_REQUIRE(e, "e")
+  return edfdv_spline_f64(f_in, f_out, batch, nx, nv, e, dex, pond, charge, mass, dt, dv, (cudaStream_t)stream);
+}
+
+int adept_b200_moments_f64(const double* f, int batch, int nx, int nv, const double* v, double scale_a,
+                           const double* const* base_host, double* const* out_host, const double* scale_b_host,
+                           void* stream) {
+  ADEPT_REQUIRE(f, "f") ADEPT_REQUIRE(out_host, "out_host")
+  return moments_f64(f, batch, nx, nv, v, scale_a, base_host, out_host, scale_b_host, (cudaStream_t)stream);
+}
+
+int adept_b200_poisson_f64(const double* rho, const double* kmul, long long kmul_stride, double* e, int batch, int nx,
+                           int mode, double Te, double lambda_De, void* stream) {
+  ADEPT_REQUIRE(rho, "rho") ADEPT_REQUIRE(kmul, "kmul") ADEPT_REQUIRE(e, "e")
+  if (mode != 0 && mode != 1) {
+    set_last_error("poisson: unknown mode %d", mode);
+    return ADEPT_ERR_BAD_ARG;
+  }
+  return poisson_dispatch_f64(rho, kmul, kmul_stride, e, batch, nx, mode, Te, lambda_De, (cudaStream_t)stream);
+}
+
+int adept_b200_axpy_f64(const double* a, const double* b, double s, double* out, long long n, void* stream) {
+  ADEPT_REQUIRE(a, "a") ADEPT_REQUIRE(b, "b") ADEPT_REQUIRE(out, "out")
+  return axpy_f64(a, b, s, out, n, (cudaStream_t)stream);
+}
+
+int adept_b200_ponderomotive_f64(const double* a, double* pond, int batch, int nx, double dx, void* stream) {
+  ADEPT_REQUIRE(a, "a") ADEPT_REQUIRE(pond, "pond")
+  return ponderomotive_f64(a, pond, batch, nx, dx, (cudaStream_t)stream);
+}
+
+int adept_b200_wave_step_f64(const double* a, const double* aold, const double* djy, const double* ne_n,
+                             const double* ne_np1, double* a_new, int batch, int nx, double c, double dx, double dt,
+                             void* stream) {
+  ADEPT_REQUIRE(a, "a") ADEPT_REQUIRE(aold, "aold") ADEPT_REQUIRE(djy, "djy") ADEPT_REQUIRE(a_new, "a_new")
+  return wave_step_f64(a, aold, djy, ne_n, ne_np1, a_new, batch, nx, c, dx, dt, (cudaStream_t)stream);
+}
+
+int adept_b200_collide_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* v, double dv,
+                           double dt, const double* nu_fp, const double* nu_K, const double* f_mx, int model,
+                           int scheme, int nodrag, double sg_m, double sg_ratio, double* n_out, void* stream) {
+  ADEPT_REQUIRE(f_in, "f_in") ADEPT_REQUIRE(f_out, "f_out") ADEPT_REQUIRE(v, "v")
+  return collide_f64(f_in, f_out, batch, nx, nv, v, dv, dt, nu_fp, nu_K, f_mx, model, scheme, nodrag, sg_m, sg_ratio,
+                     n_out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

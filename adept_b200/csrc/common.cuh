@@ -1,0 +1,48 @@
+// Shared helpers for the adept_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace adept {
+
+typedef double2 cplx;
+
+__device__ __forceinline__ cplx cmake(double x, double y) { return make_double2(x, y); }
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ cplx cconj(cplx a) { return make_double2(a.x, -a.y); }
+// a * (-i)
+__device__ __forceinline__ cplx cmul_mi(cplx a) { return make_double2(a.y, -a.x); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// accel = (q*e + (q^2/m)*pond)/m with the reference's rounding sequence (no FMA contraction):
+// adept/_vlasov1d/solvers/pushers/vlasov.py:83-84
+__device__ __forceinline__ double accel_of(double e, double pond, double q, double q2m, double m) {
+  const double force = __dadd_rn(__dmul_rn(q, e), __dmul_rn(q2m, pond));
+  return __ddiv_rn(force, m);
+}
+
+// error codes returned across the C ABI (include/adept_b200.h)
+enum {
+  ADEPT_OK = 0,
+  ADEPT_ERR_BAD_SHAPE = -1,
+  ADEPT_ERR_UNSUPPORTED = -2,
+  ADEPT_ERR_CUDA = -3,
+  ADEPT_ERR_BAD_ARG = -4,
+};
+
+void set_last_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+// twiddle-table cache (api.cu): per-pass Stockham tables for a complex FFT of length 2^logn on the current device
+const cplx* get_twiddles(int logn);
+
+}  // namespace adept

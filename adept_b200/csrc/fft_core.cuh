@@ -1,0 +1,176 @@
+// In-shared-memory Stockham autosort complex FFT, length N = 2^LOGN (2 <= N <= 8192), fp64.
+//
+// One FFT is computed by T = N/E threads (E = min(16, N) points per thread per pass).  Passes are
+// radix-16 (as many as fit) followed by one radix-2/4/8 pass.  In every pass thread t holds the
+// points e = t + T*m (m = 0..E-1) in registers x[m]; a radix-R butterfly q (q = 0..E/R-1) combines
+// x[q + r*E/R].  Between passes points are exchanged through a padded shared-memory buffer
+// (pad(e) = e + e/16 keeps 16-byte accesses conflict-free for the stride-16 scatter).  The first
+// pass takes its inputs from registers (the caller loads them from global memory), the last pass
+// leaves its outputs in registers in the same e = t + T*m order, so callers read and write global
+// memory coalesced with no extra staging pass.
+//
+// Twiddles: per-pass tables tw[off_p + (r-1)*Ns + k] = exp(-2*pi*i*k*r/(Ns*R)), k < Ns, so that the
+// T threads of a pass read consecutive entries (built on the host in long double; api.cu).
+#pragma once
+#include "common.cuh"
+
+namespace adept {
+
+template <int LOGN>
+struct FftCfg {
+  static constexpr int N = 1 << LOGN;
+  static constexpr int E = N < 16 ? N : 16;
+  static constexpr int T = N / E;
+  static constexpr int NP16 = N < 16 ? 0 : LOGN / 4;
+  static constexpr int REM = N < 16 ? LOGN : LOGN % 4;
+  static constexpr int NPASS = NP16 + (REM ? 1 : 0);
+  static constexpr int BUF = N + N / 16;  // padded buffer length in cplx
+  __host__ __device__ static constexpr int radix(int p) { return p < NP16 ? 16 : (1 << REM); }
+  __host__ __device__ static constexpr int ns(int p) {  // product of radices before pass p
+    int v = 1;
+    for (int i = 0; i < p; i++) v *= radix(i);
+    return v;
+  }
+  __host__ __device__ static constexpr int tw_off(int p) {  // table offset of pass p
+    int v = 0;
+    for (int i = 1; i < p; i++) v += (radix(i) - 1) * ns(i);
+    return v;
+  }
+  static constexpr int TW_TOTAL = tw_off(NPASS);
+};
+
+__device__ __forceinline__ int fft_pad(int e) { return e + (e >> 4); }
+
+// ---- small DFTs, forward sign (W = exp(-2 pi i / R)), natural-order in and out -----------------
+
+__device__ __forceinline__ void dft2(cplx& a, cplx& b) {
+  cplx t = a;
+  a = cadd(t, b);
+  b = csub(t, b);
+}
+
+__device__ __forceinline__ void dft4(cplx& x0, cplx& x1, cplx& x2, cplx& x3) {
+  cplx t0 = cadd(x0, x2), t1 = csub(x0, x2), t2 = cadd(x1, x3), t3 = cmul_mi(csub(x1, x3));
+  x0 = cadd(t0, t2);
+  x1 = cadd(t1, t3);
+  x2 = csub(t0, t2);
+  x3 = csub(t1, t3);
+}
+
+#define ADEPT_SQRT1_2 0.70710678118654752440
+#define ADEPT_COS_PI_8 0.92387953251128675613
+#define ADEPT_SIN_PI_8 0.38268343236508977173
+
+__device__ __forceinline__ void dft8(cplx* v) {  // v[0..7]
+  // even / odd DIT
+  cplx e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
+  cplx o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
+  dft4(e0, e1, e2, e3);
+  dft4(o0, o1, o2, o3);
+  // W8^1 = (1 - i)/sqrt2, W8^2 = -i, W8^3 = (-1 - i)/sqrt2
+  o1 = cmake((o1.x + o1.y) * ADEPT_SQRT1_2, (o1.y - o1.x) * ADEPT_SQRT1_2);
+  o2 = cmul_mi(o2);
+  o3 = cmake((o3.y - o3.x) * ADEPT_SQRT1_2, -(o3.x + o3.y) * ADEPT_SQRT1_2);
+  v[0] = cadd(e0, o0);
+  v[4] = csub(e0, o0);
+  v[1] = cadd(e1, o1);
+  v[5] = csub(e1, o1);
+  v[2] = cadd(e2, o2);
+  v[6] = csub(e2, o2);
+  v[3] = cadd(e3, o3);
+  v[7] = csub(e3, o3);
+}
+
+__device__ __forceinline__ void dft16(cplx* v) {  // v[0..15]
+  // n = c + 4d, k = k1 + 4 k2:  y[k1+4k2] = sum_c W4^{c k2} W16^{c k1} sum_d x[c+4d] W4^{d k1}
+#pragma unroll
+  for (int c = 0; c < 4; c++) dft4(v[c], v[c + 4], v[c + 8], v[c + 12]);  // -> v[c + 4 k1]
+  const cplx w1 = cmake(ADEPT_COS_PI_8, -ADEPT_SIN_PI_8);
+  const cplx w3 = cmake(ADEPT_SIN_PI_8, -ADEPT_COS_PI_8);
+  // k1 = 1: c = 1,2,3 -> W16^1, W16^2, W16^3
+  v[5] = cmul(v[5], w1);
+  v[6] = cmake((v[6].x + v[6].y) * ADEPT_SQRT1_2, (v[6].y - v[6].x) * ADEPT_SQRT1_2);
+  v[7] = cmul(v[7], w3);
+  // k1 = 2: W16^2, W16^4, W16^6
+  v[9] = cmake((v[9].x + v[9].y) * ADEPT_SQRT1_2, (v[9].y - v[9].x) * ADEPT_SQRT1_2);
+  v[10] = cmul_mi(v[10]);
+  v[11] = cmake((v[11].y - v[11].x) * ADEPT_SQRT1_2, -(v[11].x + v[11].y) * ADEPT_SQRT1_2);
+  // k1 = 3: W16^3, W16^6, W16^9 = -W16^1
+  v[13] = cmul(v[13], w3);
+  v[14] = cmake((v[14].y - v[14].x) * ADEPT_SQRT1_2, -(v[14].x + v[14].y) * ADEPT_SQRT1_2);
+  v[15] = cmul(v[15], cmake(-ADEPT_COS_PI_8, ADEPT_SIN_PI_8));
+#pragma unroll
+  for (int k1 = 0; k1 < 4; k1++) dft4(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);  // -> v[4k1 + k2]
+  // transpose register names so that v[k] = y[k]
+#pragma unroll
+  for (int k1 = 0; k1 < 4; k1++)
+#pragma unroll
+    for (int k2 = k1 + 1; k2 < 4; k2++) {
+      cplx t = v[4 * k1 + k2];
+      v[4 * k1 + k2] = v[4 * k2 + k1];
+      v[4 * k2 + k1] = t;
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void dft_r(cplx* v) {
+  if constexpr (R == 2) dft2(v[0], v[1]);
+  if constexpr (R == 4) dft4(v[0], v[1], v[2], v[3]);
+  if constexpr (R == 8) dft8(v);
+  if constexpr (R == 16) dft16(v);
+}
+
+// ---- Stockham passes -------------------------------------------------------------------------
+
+template <int LOGN, int P>
+struct FftPass {
+  using C = FftCfg<LOGN>;
+  static __device__ __forceinline__ void run(cplx (&x)[C::E], cplx* __restrict__ buf, const cplx* __restrict__ tw,
+                                             int t) {
+    constexpr int R = C::radix(P);
+    constexpr int NS = C::ns(P);
+    constexpr int Q = C::E / R;
+    constexpr int T = C::T;
+    if constexpr (P > 0) {
+#pragma unroll
+      for (int m = 0; m < C::E; m++) x[m] = buf[fft_pad(t + T * m)];
+    }
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+      const int k = (t + T * q) & (NS - 1);
+      cplx v[R];
+#pragma unroll
+      for (int r = 0; r < R; r++) v[r] = x[q + r * Q];
+      if constexpr (NS > 1) {
+        const cplx* twp = tw + C::tw_off(P) + k;
+#pragma unroll
+        for (int r = 1; r < R; r++) v[r] = cmul(v[r], __ldg(twp + (r - 1) * NS));
+      }
+      dft_r<R>(v);
+#pragma unroll
+      for (int r = 0; r < R; r++) x[q + r * Q] = v[r];
+    }
+    if constexpr (P < C::NPASS - 1) {
+      __syncthreads();  // all reads of buf for this pass (and any earlier use) are done
+#pragma unroll
+      for (int q = 0; q < Q; q++) {
+        const int b = t + T * q;
+        const int k = b & (NS - 1);
+        const int j0 = (b - k) * R + k;
+#pragma unroll
+        for (int r = 0; r < R; r++) buf[fft_pad(j0 + r * NS)] = x[q + r * Q];
+      }
+      __syncthreads();
+      FftPass<LOGN, P + 1>::run(x, buf, tw, t);
+    }
+  }
+};
+
+// Forward complex FFT of the N points held as x[m] = z[t + T*m]; result X[t + T*m] in x[m].
+// All threads of the CTA must call this together (it uses __syncthreads()).
+template <int LOGN>
+__device__ __forceinline__ void fft_forward(cplx (&x)[FftCfg<LOGN>::E], cplx* buf, const cplx* tw, int t) {
+  FftPass<LOGN, 0>::run(x, buf, tw, t);
+}
+
+}  // namespace adept

@@ -1,0 +1,267 @@
+// O(nx) field kernels: spectral Poisson / Boltzmann-Poisson solve, ponderomotive force, wave-equation step.
+// Reference semantics (file:line relative to /root/reference):
+//   Poisson            adept/_vlasov1d/solvers/pushers/field.py:210-224  E = Re ifft(-i (1/kx) fft(rho))
+//   Boltzmann-Poisson  adept/_vlasov1d/solvers/pushers/field.py:282-298
+//   ponderomotive      adept/_vlasov1d/solvers/pushers/field.py:495      -0.5 * gradient(a^2, dx)[1:-1]
+//   wave equation      adept/_vlasov1d/solvers/pushers/field.py:109-157  (WaveSolver + 2nd-order ABC)
+#include "fft_core.cuh"
+
+namespace adept {
+
+struct PoissonArgs {
+  const double* rho;     // [batch, nx]
+  const double* kmul;    // POISSON: one_over_kx[nx]; BOLTZMANN: kx[nx]   (per batch member if kmul_stride != 0)
+  long long kmul_stride;
+  double* e;             // [batch, nx]
+  int mode;              // 0 poisson, 1 boltzmann
+  double Te, lambda_De;  // boltzmann: lambda_De < 0 -> sqrt(Te / rho_0)
+  const cplx* tw;
+};
+
+template <int LOGN>
+__global__ void __launch_bounds__(FftCfg<LOGN>::T) poisson_kernel(PoissonArgs p) {
+  using C = FftCfg<LOGN>;
+  constexpr int N = C::N, E = C::E, T = C::T;
+  __shared__ __align__(16) cplx buf[C::BUF];
+  __shared__ double rho0_s;
+  const int t = threadIdx.x, tt = threadIdx.x;
+  const double* rho = p.rho + (long long)blockIdx.x * N;
+  const double* kmul = p.kmul + (long long)blockIdx.x * p.kmul_stride;
+  double* eo = p.e + (long long)blockIdx.x * N;
+
+  cplx x[E];
+#pragma unroll
+  for (int m = 0; m < E; m++) x[m] = cmake(rho[tt + T * m], 0.0);
+  fft_forward<LOGN>(x, buf, p.tw, tt);
+  if (t == 0) rho0_s = x[0].x / (double)N;  // mean(rho) = DC / N
+  __syncthreads();
+  const double rho0 = rho0_s;
+#pragma unroll
+  for (int m = 0; m < E; m++) {
+    const int k = tt + T * m;
+    double mult;
+    if (p.mode == 0) {
+      mult = kmul[k];
+    } else {
+      const double kx = kmul[k];
+      const double lam_sq = p.lambda_De < 0.0 ? p.Te / rho0 : p.lambda_De * p.lambda_De;
+      mult = kx * (p.Te / rho0) / (1.0 + lam_sq * kx * kx);
+    }
+    // Y = -i * mult * X = (mult*Xi, -mult*Xr); store swapped for inverse-by-forward
+    const cplx y = cmake(mult * x[m].y, -(mult * x[m].x));
+    x[m] = cmake(y.y, y.x);
+  }
+  if (C::NPASS > 1) __syncthreads();
+  fft_forward<LOGN>(x, buf, p.tw, tt);
+#pragma unroll
+  for (int m = 0; m < E; m++) eo[t + T * m] = x[m].y / (double)N;  // Re(ifft) = Im of swapped result
+}
+
+static int ilog2_exact(int n) {
+  if (n < 2 || (n & (n - 1))) return -1;
+  int l = 0;
+  while ((1 << l) < n) l++;
+  return l;
+}
+
+int poisson_f64(const double* rho, const double* kmul, long long kmul_stride, double* e, int batch, int nx, int mode,
+                double Te, double lambda_De, cudaStream_t stream) {
+  const int logn = ilog2_exact(nx);
+  if (batch < 1 || logn < 1 || logn > 13) {
+    set_last_error("poisson: nx=%d must be a power of two in [2, 8192] (batch=%d)", nx, batch);
+    return logn < 1 || logn > 13 ? ADEPT_ERR_UNSUPPORTED : ADEPT_ERR_BAD_SHAPE;
+  }
+  PoissonArgs p = {rho, kmul, kmul_stride, e, mode, Te, lambda_De, get_twiddles(logn)};
+  if (!p.tw) return ADEPT_ERR_CUDA;
+  switch (logn) {
+#define ADEPT_CASE(L)                                                                              \
+  case L:                                                                                          \
+    poisson_kernel<L><<<batch, FftCfg<L>::T, 0, stream>>>(p); \
+    break;
+    ADEPT_CASE(1)
+    ADEPT_CASE(2)
+    ADEPT_CASE(3)
+    ADEPT_CASE(4)
+    ADEPT_CASE(5)
+    ADEPT_CASE(6)
+    ADEPT_CASE(7)
+    ADEPT_CASE(8)
+    ADEPT_CASE(9)
+    ADEPT_CASE(10)
+    ADEPT_CASE(11)
+#undef ADEPT_CASE
+    default:
+      // static shared memory is limited to 48 KiB: nx >= 4096 uses the dynamic-smem variant below
+      return ADEPT_ERR_UNSUPPORTED;
+  }
+  return check_launch("poisson_kernel");
+}
+
+// nx = 4096 / 8192: same kernel body but with dynamic shared memory (> 48 KiB)
+template <int LOGN>
+__global__ void __launch_bounds__(FftCfg<LOGN>::T) poisson_kernel_big(PoissonArgs p) {
+  using C = FftCfg<LOGN>;
+  constexpr int N = C::N, E = C::E, T = C::T;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* buf = reinterpret_cast<cplx*>(smem_raw);
+  __shared__ double rho0_s;
+  const int t = threadIdx.x;
+  const double* rho = p.rho + (long long)blockIdx.x * N;
+  const double* kmul = p.kmul + (long long)blockIdx.x * p.kmul_stride;
+  double* eo = p.e + (long long)blockIdx.x * N;
+  cplx x[E];
+#pragma unroll
+  for (int m = 0; m < E; m++) x[m] = cmake(rho[t + T * m], 0.0);
+  fft_forward<LOGN>(x, buf, p.tw, t);
+  if (t == 0) rho0_s = x[0].x / (double)N;
+  __syncthreads();
+  const double rho0 = rho0_s;
+#pragma unroll
+  for (int m = 0; m < E; m++) {
+    const int k = t + T * m;
+    double mult;
+    if (p.mode == 0) {
+      mult = kmul[k];
+    } else {
+      const double kx = kmul[k];
+      const double lam_sq = p.lambda_De < 0.0 ? p.Te / rho0 : p.lambda_De * p.lambda_De;
+      mult = kx * (p.Te / rho0) / (1.0 + lam_sq * kx * kx);
+    }
+    const cplx y = cmake(mult * x[m].y, -(mult * x[m].x));
+    x[m] = cmake(y.y, y.x);
+  }
+  __syncthreads();
+  fft_forward<LOGN>(x, buf, p.tw, t);
+#pragma unroll
+  for (int m = 0; m < E; m++) eo[t + T * m] = x[m].y / (double)N;
+}
+
+template <int LOGN>
+static int launch_poisson_big(const PoissonArgs& p, int batch, cudaStream_t stream) {
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const size_t smem = FftCfg<LOGN>::BUF * sizeof(cplx);
+  if (dev < 64 && !configured[dev]) {
+    cudaError_t err =
+        cudaFuncSetAttribute(poisson_kernel_big<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) {
+      set_last_error("cudaFuncSetAttribute(poisson): %s", cudaGetErrorString(err));
+      return ADEPT_ERR_CUDA;
+    }
+    configured[dev] = true;
+  }
+  poisson_kernel_big<LOGN><<<batch, FftCfg<LOGN>::T, smem, stream>>>(p);
+  return check_launch("poisson_kernel_big");
+}
+
+int poisson_dispatch_f64(const double* rho, const double* kmul, long long kmul_stride, double* e, int batch, int nx,
+                         int mode, double Te, double lambda_De, cudaStream_t stream) {
+  const int logn = ilog2_exact(nx);
+  if (logn == 12 || logn == 13) {
+    PoissonArgs p = {rho, kmul, kmul_stride, e, mode, Te, lambda_De, get_twiddles(logn)};
+    if (!p.tw) return ADEPT_ERR_CUDA;
+    return logn == 12 ? launch_poisson_big<12>(p, batch, stream) : launch_poisson_big<13>(p, batch, stream);
+  }
+  return poisson_f64(rho, kmul, kmul_stride, e, batch, nx, mode, Te, lambda_De, stream);
+}
+
+// ---- ponderomotive force: pond_i = -0.5 * (a_{i+2}^2 - a_i^2) / (2 dx), a has nx+2 cells -----------------------
+__global__ void pond_kernel(const double* __restrict__ a, double* __restrict__ pond, int nx, double dx,
+                            long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long b = idx / nx;
+  const int i = (int)(idx % nx);
+  const double* ab = a + b * (nx + 2);
+  const double lo = __dmul_rn(ab[i], ab[i]), hi = __dmul_rn(ab[i + 2], ab[i + 2]);
+  pond[idx] = __dmul_rn(-0.5, __ddiv_rn(__dsub_rn(hi, lo), __dmul_rn(2.0, dx)));
+}
+
+int ponderomotive_f64(const double* a, double* pond, int batch, int nx, double dx, cudaStream_t stream) {
+  if (batch < 1 || nx < 1) {
+    set_last_error("ponderomotive: bad shape batch=%d nx=%d", batch, nx);
+    return ADEPT_ERR_BAD_SHAPE;
+  }
+  const long long total = (long long)batch * nx;
+  pond_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a, pond, nx, dx, total);
+  return check_launch("pond_kernel");
+}
+
+// ---- wave equation step ----------------------------------------------------------------------------------
+struct WaveArgs {
+  const double* a;      // [batch, nx+2]
+  const double* aold;   // [batch, nx+2]
+  const double* djy;    // [batch, nx+2]
+  const double* ne_n;   // [batch, nx] electron charge density at t_n       (nullable -> 0)
+  const double* ne_np1; // [batch, nx] electron charge density at t_{n+1}   (nullable -> 0)
+  double* a_new;        // [batch, nx+2]
+  int nx;
+  double c, dx, dt;
+};
+
+__device__ __forceinline__ double wave_interior(const WaveArgs& p, const double* a, const double* aold,
+                                                const double* djy, const double* n0, const double* n1, int i) {
+  // i in [0, nx): anew[i] of field.py:146-153 (a index i+1)
+  const double d2dx2 = (a[i] - 2.0 * a[i + 1] + a[i + 2]) / (p.dx * p.dx);
+  double ed = 0.0;
+  if (n0 && n1) ed = -0.5 * (n0[i] + n1[i]);  // vector_field.py:346
+  return 2.0 * a[i + 1] - aold[i + 1] + (p.dt * p.dt) * ((p.c * p.c) * d2dx2 - ed * a[i + 1] + djy[i + 1]);
+}
+
+__global__ void wave_kernel(WaveArgs p) {
+  const int nx = p.nx;
+  const long long b = blockIdx.y;
+  const double* a = p.a + b * (nx + 2);
+  const double* aold = p.aold + b * (nx + 2);
+  const double* djy = p.djy + b * (nx + 2);
+  const double* n0 = p.ne_n ? p.ne_n + b * nx : nullptr;
+  const double* n1 = p.ne_np1 ? p.ne_np1 + b * nx : nullptr;
+  double* out = p.a_new + b * (nx + 2);
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;  // index into a_new, 0..nx+1
+  if (j > nx + 1) return;
+  if (j >= 1 && j <= nx) {
+    out[j] = wave_interior(p, a, aold, djy, n0, n1, j - 1);
+    return;
+  }
+  const double c_over_dx = p.c / p.dx;
+  const double cst = c_over_dx * p.dt;
+  const double ooc = 1.0 / p.dt / c_over_dx;
+  const double coeff = -1.0 / (ooc + 2.0 + cst);
+  if (j == 0) {
+    const double an0 = wave_interior(p, a, aold, djy, n0, n1, 0), an1 = wave_interior(p, a, aold, djy, n0, n1, 1);
+    double al = (ooc - 2.0 + cst) * (an1 + aold[0]);
+    al += 2.0 * (cst - ooc) * (a[0] + a[2] - an0 - aold[1]);
+    al -= 4.0 * (ooc + cst) * a[1];
+    al *= coeff;
+    al -= aold[2];
+    out[0] = al;
+  } else {
+    const double anm1 = wave_interior(p, a, aold, djy, n0, n1, nx - 1),
+                 anm2 = wave_interior(p, a, aold, djy, n0, n1, nx - 2);
+    double ar = (ooc - 2.0 + cst) * (anm2 + aold[nx + 1]);
+    ar += 2.0 * (cst - ooc) * (a[nx + 1] + a[nx - 1] - anm1 - aold[nx]);
+    ar -= 4.0 * (ooc + cst) * a[nx];
+    ar *= coeff;
+    ar -= aold[nx - 1];
+    out[nx + 1] = ar;
+  }
+}
+
+int wave_step_f64(const double* a, const double* aold, const double* djy, const double* ne_n, const double* ne_np1,
+                  double* a_new, int batch, int nx, double c, double dx, double dt, cudaStream_t stream) {
+  if (batch < 1 || nx < 2) {
+    set_last_error("wave_step: bad shape batch=%d nx=%d", batch, nx);
+    return ADEPT_ERR_BAD_SHAPE;
+  }
+  if (a_new == a || a_new == aold) {
+    set_last_error("wave_step: a_new must not alias a or aold");
+    return ADEPT_ERR_BAD_ARG;
+  }
+  WaveArgs p = {a, aold, djy, ne_n, ne_np1, a_new, nx, c, dx, dt};
+  dim3 grid((nx + 2 + 255) / 256, batch);
+  wave_kernel<<<grid, 256, 0, stream>>>(p);
+  return check_launch("wave_kernel");
+}
+
+}  // namespace adept

@@ -1,0 +1,307 @@
+// Spectral advection pushers: f <- irfft( exp(-i * m * alpha_seq) * rfft(f) ) along x (strided axis) or
+// along v (contiguous axis), one fused kernel: one HBM read + one HBM write of f per call.
+//
+// Reference semantics (file:line relative to /root/reference):
+//   x-advection  adept/_vlasov1d/solvers/pushers/vlasov.py:234-251  (SpaceExponential.push / __call__)
+//   v-advection  adept/_vlasov1d/solvers/pushers/vlasov.py:74-91    (VelocityExponential.push)
+//
+// Two real sequences (two neighbouring v-columns, or two neighbouring x-rows) are transformed as one
+// complex FFT z = a + i b.  The spectra are separated with the k <-> N-k symmetry, multiplied by their own
+// phase factors (Im of DC/Nyquist dropped exactly like irfft does), recombined, and transformed back with the
+// same forward kernel (swap trick).  Phase factors exp(-i m alpha) are built from two small per-sequence tables
+// (m = 64*hi + lo) so no sincos is evaluated per element.
+#include "fft_core.cuh"
+
+namespace adept {
+
+enum { AXIS_X = 0, AXIS_V = 1 };
+
+template <int LOGN>
+struct PhaseCfg {
+  static constexpr int N = 1 << LOGN;
+  static constexpr int LOB = LOGN > 6 ? 6 : LOGN;
+  static constexpr int LO = 1 << LOB;
+  static constexpr int HI = ((N / 2) >> LOB) + 1;
+  static constexpr int PER_SEQ = HI + LO;
+};
+
+template <int LOGN, int AXIS>
+struct PushCfg {
+  static constexpr int T = FftCfg<LOGN>::T;
+  // x-axis at N=4096: two column pairs per CTA so that the 16-byte column-pair loads of both groups fall in the
+  // same 32-byte sectors at the same time (L1 merges them).
+  static constexpr int THREADS_ = (T >= 512) ? T : ((AXIS == AXIS_X && T == 256) ? 512 : (16 * T > 256 ? 256 : 16 * T));
+  static constexpr int THREADS = THREADS_ < 32 ? 32 : THREADS_;
+  static constexpr int F = THREADS / T;  // FFT groups (sequence pairs) per CTA
+  static constexpr size_t SMEM = (size_t)F * (FftCfg<LOGN>::BUF + 2 * PhaseCfg<LOGN>::PER_SEQ) * sizeof(cplx);
+};
+
+struct PushArgs {
+  const double* fin;
+  double* fout;
+  int batch, nx, nv;
+  long long npairs;  // total sequence pairs over the batch
+  // AXIS_X: alpha_j = k1[b] * (v[j] * dt)
+  const double* v;
+  const double* k1_batch;  // nullable -> k1
+  double k1;
+  double dt;
+  // AXIS_V: accel_i = (q*(e_i+dex_i) + (q*q/m)*pond_i)/m ; alpha_i = k1 * (dt * accel_i)
+  const double* e;
+  const double* dex;   // nullable
+  const double* pond;  // nullable
+  double q, m;
+  const cplx* tw;
+};
+
+template <int LOGN, int AXIS>
+__global__ void __launch_bounds__(PushCfg<LOGN, AXIS>::THREADS, (PushCfg<LOGN, AXIS>::THREADS <= 256 ? 2 : 1))
+    spectral_push_kernel(PushArgs p) {
+  using C = FftCfg<LOGN>;
+  using PC = PhaseCfg<LOGN>;
+  using K = PushCfg<LOGN, AXIS>;
+  constexpr int N = C::N, E = C::E, T = C::T;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* smem = reinterpret_cast<cplx*>(smem_raw);
+
+  const int g = threadIdx.x / T;  // FFT group in this CTA
+  const int t = threadIdx.x % T;
+  cplx* buf = smem + (size_t)g * C::BUF;
+  cplx* ph = smem + (size_t)K::F * C::BUF + (size_t)g * 2 * PC::PER_SEQ;  // [seq][hi.. lo..]
+
+  const long long G = (long long)blockIdx.x * K::F + g;
+  const bool active = G < p.npairs;
+
+  // ---- addressing + per-sequence phase increments ------------------------------------------------------
+  const double* src = p.fin;
+  double* dst = p.fout;
+  long long stride = 1;  // element stride along the transformed axis
+  double alpha_a = 0.0, alpha_b = 0.0;
+  if (active) {
+    if (AXIS == AXIS_V) {
+      const long long row0 = 2 * G;  // global row over [batch, nx]
+      src += row0 * p.nv;
+      dst += row0 * p.nv;
+      const int b = (int)(row0 / p.nx);
+      const double k1 = p.k1_batch ? p.k1_batch[b] : p.k1;
+      const double q2m = p.q * p.q / p.m;
+      double acc[2];
+#pragma unroll
+      for (int s = 0; s < 2; s++) {
+        double ee = p.e[row0 + s];
+        if (p.dex) ee = __dadd_rn(ee, p.dex[row0 + s]);
+        const double pd = p.pond ? p.pond[row0 + s] : 0.0;
+        acc[s] = accel_of(ee, pd, p.q, q2m, p.m);
+      }
+      alpha_a = k1 * (p.dt * acc[0]);
+      alpha_b = k1 * (p.dt * acc[1]);
+    } else {
+      const int half = p.nv / 2;
+      const int b = (int)(G / half);
+      const int cp = (int)(G % half);
+      src += (long long)b * p.nx * p.nv + 2 * cp;
+      dst += (long long)b * p.nx * p.nv + 2 * cp;
+      stride = p.nv;
+      const double k1 = p.k1_batch ? p.k1_batch[b] : p.k1;
+      alpha_a = k1 * (p.v[2 * cp] * p.dt);
+      alpha_b = k1 * (p.v[2 * cp + 1] * p.dt);
+    }
+  }
+
+  // ---- phase tables: ph[s][h] = exp(-i (h<<LOB) alpha_s), ph[s][HI + l] = exp(-i l alpha_s) / (2N) -----------
+  for (int i = t; i < 2 * PC::PER_SEQ; i += T) {
+    const int s = i / PC::PER_SEQ, j = i % PC::PER_SEQ;
+    const double al = s ? alpha_b : alpha_a;
+    double sn, cs;
+    if (j < PC::HI) {
+      sincos((double)(j << PC::LOB) * al, &sn, &cs);
+      ph[i] = cmake(cs, -sn);
+    } else {
+      sincos((double)(j - PC::HI) * al, &sn, &cs);
+      const double sc = 0.5 / (double)N;
+      ph[i] = cmake(cs * sc, -sn * sc);
+    }
+  }
+
+  // ---- load: x[m] = a[e] + i b[e], e = t + T m -----------------------------------------------------------
+  cplx x[E];
+  if (active) {
+    if (AXIS == AXIS_V) {
+      const double* a = src;
+      const double* bq = src + p.nv;
+#pragma unroll
+      for (int m = 0; m < E; m++) {
+        const int e = t + T * m;
+        x[m] = cmake(a[e], bq[e]);
+      }
+    } else {
+#pragma unroll
+      for (int m = 0; m < E; m++) {
+        const long long e = t + T * m;
+        x[m] = *reinterpret_cast<const double2*>(src + e * stride);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int m = 0; m < E; m++) x[m] = cmake(0.0, 0.0);
+  }
+
+  fft_forward<LOGN>(x, buf, p.tw, t);
+
+  // ---- publish Z in natural order ----------------------------------------------------------------------
+  __syncthreads();
+#pragma unroll
+  for (int m = 0; m < E; m++) buf[fft_pad(t + T * m)] = x[m];
+  __syncthreads();
+
+  // ---- separate / phase multiply / recombine, fused into the load of the inverse transform ---------------
+  const cplx* hi_a = ph;
+  const cplx* lo_a = ph + PC::HI;
+  const cplx* hi_b = ph + PC::PER_SEQ;
+  const cplx* lo_b = hi_b + PC::HI;
+#pragma unroll
+  for (int m = 0; m < E; m++) {
+    const int e = t + T * m;
+    const int ep = (N - e) & (N - 1);
+    const cplx zk = buf[fft_pad(e)];
+    const cplx zq = buf[fft_pad(ep)];
+    const bool neg = e > N / 2;
+    const int mm = neg ? N - e : e;
+    cplx pa = cmul(hi_a[mm >> PC::LOB], lo_a[mm & (PC::LO - 1)]);
+    cplx pb = cmul(hi_b[mm >> PC::LOB], lo_b[mm & (PC::LO - 1)]);
+    if (neg) {
+      pa.y = -pa.y;
+      pb.y = -pb.y;
+    }
+    if (e == N / 2) {  // irfft ignores Im of the Nyquist mode
+      pa.y = 0.0;
+      pb.y = 0.0;
+    }
+    const cplx A = cmake(zk.x + zq.x, zk.y - zq.y);  // 2 * spectrum of a
+    const cplx B = cmake(zk.y + zq.y, zq.x - zk.x);  // 2 * spectrum of b
+    const cplx Ap = cmul(A, pa), Bp = cmul(B, pb);
+    // Z' = A' + i B', stored swapped (im, re): inverse FFT = swap . forward FFT . swap
+    x[m] = cmake(Ap.y + Bp.x, Ap.x - Bp.y);
+  }
+
+  fft_forward<LOGN>(x, buf, p.tw, t);
+
+  // ---- store: a'[e] = Im, b'[e] = Re of the swapped result ---------------------------------------------
+  if (active) {
+    if (AXIS == AXIS_V) {
+      double* a = dst;
+      double* bq = dst + p.nv;
+#pragma unroll
+      for (int m = 0; m < E; m++) {
+        const int e = t + T * m;
+        a[e] = x[m].y;
+        bq[e] = x[m].x;
+      }
+    } else {
+#pragma unroll
+      for (int m = 0; m < E; m++) {
+        const long long e = t + T * m;
+        *reinterpret_cast<double2*>(dst + e * stride) = make_double2(x[m].y, x[m].x);
+      }
+    }
+  }
+}
+
+template <int LOGN, int AXIS>
+static int launch_push(const PushArgs& p, cudaStream_t stream) {
+  using K = PushCfg<LOGN, AXIS>;
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto kern = spectral_push_kernel<LOGN, AXIS>;
+  if (dev < 64 && !configured[dev]) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
+    if (err != cudaSuccess) {
+      set_last_error("cudaFuncSetAttribute(push, smem=%zu): %s", K::SMEM, cudaGetErrorString(err));
+      return ADEPT_ERR_CUDA;
+    }
+    configured[dev] = true;
+  }
+  const long long blocks = (p.npairs + K::F - 1) / K::F;
+  kern<<<(unsigned)blocks, K::THREADS, K::SMEM, stream>>>(p);
+  return check_launch("spectral_push_kernel");
+}
+
+template <int AXIS>
+static int dispatch_push(int logn, const PushArgs& p, cudaStream_t stream) {
+  switch (logn) {
+#define ADEPT_CASE(L) \
+  case L:             \
+    return launch_push<L, AXIS>(p, stream);
+    ADEPT_CASE(1)
+    ADEPT_CASE(2)
+    ADEPT_CASE(3)
+    ADEPT_CASE(4)
+    ADEPT_CASE(5)
+    ADEPT_CASE(6)
+    ADEPT_CASE(7)
+    ADEPT_CASE(8)
+    ADEPT_CASE(9)
+    ADEPT_CASE(10)
+    ADEPT_CASE(11)
+    ADEPT_CASE(12)
+    ADEPT_CASE(13)
+#undef ADEPT_CASE
+    default:
+      set_last_error("spectral push: unsupported transform length 2^%d", logn);
+      return ADEPT_ERR_UNSUPPORTED;
+  }
+}
+
+static int ilog2_exact(int n) {
+  if (n < 2 || (n & (n - 1))) return -1;
+  int l = 0;
+  while ((1 << l) < n) l++;
+  return l;
+}
+
+int vdfdx_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* v, double dt,
+              const double* k1_batch, double k1, cudaStream_t stream) {
+  if (batch < 1 || nx < 2 || nv < 2 || (nv & 1)) {
+    set_last_error("vdfdx: bad shape batch=%d nx=%d nv=%d (nv must be even)", batch, nx, nv);
+    return ADEPT_ERR_BAD_SHAPE;
+  }
+  const int logn = ilog2_exact(nx);
+  if (logn < 1 || logn > 13) {
+    set_last_error("vdfdx: nx=%d is not a power of two in [2, 8192]", nx);
+    return ADEPT_ERR_UNSUPPORTED;
+  }
+  if ((reinterpret_cast<uintptr_t>(fin) | reinterpret_cast<uintptr_t>(fout)) & 15) {
+    set_last_error("vdfdx: f buffers must be 16-byte aligned");
+    return ADEPT_ERR_BAD_ARG;
+  }
+  PushArgs p = {};
+  p.fin = fin, p.fout = fout, p.batch = batch, p.nx = nx, p.nv = nv;
+  p.npairs = (long long)batch * (nv / 2);
+  p.v = v, p.k1_batch = k1_batch, p.k1 = k1, p.dt = dt;
+  p.tw = get_twiddles(logn);
+  if (!p.tw) return ADEPT_ERR_CUDA;
+  return dispatch_push<AXIS_X>(logn, p, stream);
+}
+
+int edfdv_exp_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* e, const double* dex,
+                  const double* pond, double q, double m, double dt, double k1, cudaStream_t stream) {
+  if (batch < 1 || nx < 2 || nv < 2 || (nx & 1)) {
+    set_last_error("edfdv_exp: bad shape batch=%d nx=%d nv=%d (nx must be even)", batch, nx, nv);
+    return ADEPT_ERR_BAD_SHAPE;
+  }
+  const int logn = ilog2_exact(nv);
+  if (logn < 1 || logn > 13) {
+    set_last_error("edfdv_exp: nv=%d is not a power of two in [2, 8192]", nv);
+    return ADEPT_ERR_UNSUPPORTED;
+  }
+  PushArgs p = {};
+  p.fin = fin, p.fout = fout, p.batch = batch, p.nx = nx, p.nv = nv;
+  p.npairs = (long long)batch * (nx / 2);
+  p.e = e, p.dex = dex, p.pond = pond, p.q = q, p.m = m, p.dt = dt, p.k1 = k1;
+  p.tw = get_twiddles(logn);
+  if (!p.tw) return ADEPT_ERR_CUDA;
+  return dispatch_push<AXIS_V>(logn, p, stream);
+}
+
+}  // namespace adept

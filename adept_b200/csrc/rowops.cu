@@ -1,0 +1,152 @@
+// Row-wise (v-contiguous) kernels that are not FFTs: cubic-spline v-advection, velocity moments, Krook-free
+// helpers.  Reference semantics (file:line relative to /root/reference):
+//   cubic v-advection   adept/_vlasov1d/solvers/pushers/vlasov.py:106-148 (_uniform_cubic_interp), :162-172
+//   charge density      adept/_vlasov1d/solvers/pushers/field.py:186-208
+//   current density     adept/_vlasov1d/solvers/pushers/field.py:319-340
+#include "common.cuh"
+
+namespace adept {
+
+// ---- cubic-spline (semi-Lagrangian) velocity push ------------------------------------------------------------
+// one CTA per x-row; out-of-place (taps of neighbouring threads are read through L1).
+__global__ void __launch_bounds__(256) spline_push_kernel(const double* __restrict__ fin, double* __restrict__ fout,
+                                                          int nv, const double* __restrict__ e,
+                                                          const double* __restrict__ dex,
+                                                          const double* __restrict__ pond, double q, double m,
+                                                          double dt, double dv) {
+  const long long row = blockIdx.x;
+  const double* fr = fin + row * nv;
+  double* out = fout + row * nv;
+  double ee = e[row];
+  if (dex) ee = __dadd_rn(ee, dex[row]);
+  const double pd = pond ? pond[row] : 0.0;
+  const double shift = __dmul_rn(accel_of(ee, pd, q, q * q / m, m), dt);
+  const double scaled = __ddiv_rn(shift, dv);
+  const int row_offset = (int)floor(-scaled);
+  for (int j = threadIdx.x; j < nv; j += blockDim.x) {
+    int left = j + row_offset;
+    left = left < 0 ? 0 : (left > nv - 2 ? nv - 2 : left);
+    const double query = __dsub_rn((double)j, scaled);
+    double t = __dsub_rn(query, (double)left);
+    t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t);
+    const int im1 = left - 1 < 0 ? 0 : left - 1;
+    const int ip2 = left + 2 > nv - 1 ? nv - 1 : left + 2;
+    const double fm1 = __ldg(fr + im1), f0 = __ldg(fr + left), f1 = __ldg(fr + left + 1), f2 = __ldg(fr + ip2);
+    const double m0 = (left == 0) ? (f1 - f0) : 0.5 * (f1 - fm1);
+    const double m1 = (left == nv - 2) ? (f1 - f0) : 0.5 * (f2 - f0);
+    const double t2 = t * t, t3 = t2 * t;
+    double val = (2.0 * t3 - 3.0 * t2 + 1.0) * f0 + (t3 - 2.0 * t2 + t) * m0 + (-2.0 * t3 + 3.0 * t2) * f1 +
+                 (t3 - t2) * m1;
+    if (query < 0.0 || query > (double)(nv - 1)) val = 1.0e-30;
+    out[j] = val;
+  }
+}
+
+int edfdv_spline_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* e, const double* dex,
+                     const double* pond, double q, double m, double dt, double dv, cudaStream_t stream) {
+  if (batch < 1 || nx < 1 || nv < 2) {
+    set_last_error("edfdv_spline: bad shape batch=%d nx=%d nv=%d (cubic interpolation needs nv >= 2)", batch, nx, nv);
+    return ADEPT_ERR_BAD_SHAPE;
+  }
+  if (fin == fout) {
+    set_last_error("edfdv_spline: in-place operation is not supported (f_in == f_out)");
+    return ADEPT_ERR_BAD_ARG;
+  }
+  spline_push_kernel<<<(unsigned)((long long)batch * nx), 256, 0, stream>>>(fin, fout, nv, e, dex, pond, q, m, dt, dv);
+  return check_launch("spline_push_kernel");
+}
+
+// ---- velocity moments ----------------------------------------------------------------------------------------
+// one warp per row: s_k = sum_j f[row, j] * v[j]^k, k = 0..2; out_k[row] = base_k[row] + scale_b_k * (s_k * scale_a)
+struct MomentArgs {
+  const double* f;
+  const double* v;
+  long long rows;
+  int nv;
+  double scale_a;  // dv
+  const double* base[3];
+  double* out[3];
+  double scale_b[3];
+};
+
+__global__ void __launch_bounds__(256) moments_kernel(MomentArgs p) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  const double* fr = p.f + row * p.nv;
+  const bool need1 = p.out[1] != nullptr, need2 = p.out[2] != nullptr;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  if ((p.nv & 1) == 0 && ((reinterpret_cast<uintptr_t>(fr) & 15) == 0)) {
+    const double2* f2 = reinterpret_cast<const double2*>(fr);
+    const int n2 = p.nv >> 1;
+    for (int j = lane; j < n2; j += 32) {
+      const double2 x = f2[j];
+      s0 += x.x + x.y;
+      if (need1 || need2) {
+        const double v0 = __ldg(p.v + 2 * j), v1 = __ldg(p.v + 2 * j + 1);
+        s1 += x.x * v0 + x.y * v1;
+        if (need2) s2 += x.x * v0 * v0 + x.y * v1 * v1;
+      }
+    }
+  } else {
+    for (int j = lane; j < p.nv; j += 32) {
+      const double x = fr[j];
+      s0 += x;
+      if (need1 || need2) {
+        const double vv = __ldg(p.v + j);
+        s1 += x * vv;
+        if (need2) s2 += x * vv * vv;
+      }
+    }
+  }
+  s0 = warp_sum(s0);
+  if (need1) s1 = warp_sum(s1);
+  if (need2) s2 = warp_sum(s2);
+  if (lane == 0) {
+    const double s[3] = {s0, s1, s2};
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+      if (p.out[k]) {
+        const double term = __dmul_rn(p.scale_b[k], __dmul_rn(s[k], p.scale_a));
+        p.out[k][row] = p.base[k] ? __dadd_rn(p.base[k][row], term) : term;
+      }
+  }
+}
+
+int moments_f64(const double* f, int batch, int nx, int nv, const double* v, double scale_a, const double* const* base,
+                double* const* out, const double* scale_b, cudaStream_t stream) {
+  if (batch < 1 || nx < 1 || nv < 1) {
+    set_last_error("moments: bad shape batch=%d nx=%d nv=%d", batch, nx, nv);
+    return ADEPT_ERR_BAD_SHAPE;
+  }
+  MomentArgs p = {};
+  p.f = f, p.v = v, p.rows = (long long)batch * nx, p.nv = nv, p.scale_a = scale_a;
+  for (int k = 0; k < 3; k++) {
+    p.base[k] = base ? base[k] : nullptr;
+    p.out[k] = out[k];
+    p.scale_b[k] = scale_b ? scale_b[k] : 1.0;
+  }
+  if ((p.out[1] || p.out[2]) && !v) {
+    set_last_error("moments: v grid required for first/second moments");
+    return ADEPT_ERR_BAD_ARG;
+  }
+  const int wpb = 8;
+  const long long blocks = (p.rows + wpb - 1) / wpb;
+  moments_kernel<<<(unsigned)blocks, wpb * 32, 0, stream>>>(p);
+  return check_launch("moments_kernel");
+}
+
+// ---- tiny elementwise: out = a + s * b  (Ampere: E = E_prev - dt * j, field.py:354) ----------------------------
+__global__ void axpy_kernel(const double* __restrict__ a, const double* __restrict__ b, double s,
+                            double* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __dadd_rn(a[i], __dmul_rn(s, b[i]));
+}
+
+int axpy_f64(const double* a, const double* b, double s, double* out, long long n, cudaStream_t stream) {
+  if (n < 1) return ADEPT_OK;
+  axpy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(a, b, s, out, n);
+  return check_launch("axpy_kernel");
+}
+
+}  // namespace adept

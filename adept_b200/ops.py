@@ -1,0 +1,172 @@
+"""Thin torch-tensor front end of the C ABI: one function per entry point of include/adept_b200.h.
+
+torch is used for device memory and streams only; every function enqueues exactly one hand-written CUDA kernel
+on the current torch stream.  Inputs must be float64 CUDA tensors (no CPU path exists; a CPU tensor raises).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import AdeptB200Error
+
+LAUNCHES = 0  # number of adept_b200 kernels enqueued by this process (bench.py reports it)
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t, name, allow_none=False):
+    if t is None:
+        if allow_none:
+            return None
+        raise AdeptB200Error(f"{name}: tensor required")
+    if not isinstance(t, torch.Tensor):
+        raise AdeptB200Error(f"{name}: expected a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise AdeptB200Error(f"{name}: adept_b200 has no CPU path; tensor must live on a CUDA device")
+    if t.dtype != torch.float64:
+        raise AdeptB200Error(f"{name}: expected float64, got {t.dtype}")
+    if not t.is_contiguous():
+        raise AdeptB200Error(f"{name}: tensor must be contiguous")
+    return C.c_void_p(t.data_ptr())
+
+
+def _shape3(f):
+    if f.dim() == 2:
+        return 1, f.shape[0], f.shape[1]
+    if f.dim() == 3:
+        return f.shape[0], f.shape[1], f.shape[2]
+    raise AdeptB200Error(f"f must be [nx, nv] or [batch, nx, nv], got {tuple(f.shape)}")
+
+
+def prepare(n: int) -> None:
+    """Build the twiddle tables for transform length n on the current device (needed before graph capture)."""
+    _lib.check(_lib.load().adept_b200_prepare(int(n)), "prepare")
+
+
+def vdfdx(f, v, dt, k1x, out=None, k1x_batch=None):
+    """x-advection (SpaceExponential, vlasov.py:234-251)."""
+    b, nx, nv = _shape3(f)
+    out = torch.empty_like(f) if out is None else out
+    rc = _lib.load().adept_b200_vdfdx_f64(
+        _ptr(f, "f"), _ptr(out, "out"), b, nx, nv, _ptr(v, "v"), float(dt), float(k1x),
+        _ptr(k1x_batch, "k1x_batch", True), _stream(),
+    )
+    _lib.check(rc, "vdfdx")
+    _count()
+    return out
+
+
+def edfdv_exp(f, e, pond, q, m, dt, k1v, dex=None, out=None):
+    """Spectral v-advection (VelocityExponential, vlasov.py:74-91); e := e + dex inside the kernel."""
+    b, nx, nv = _shape3(f)
+    out = torch.empty_like(f) if out is None else out
+    rc = _lib.load().adept_b200_edfdv_exp_f64(
+        _ptr(f, "f"), _ptr(out, "out"), b, nx, nv, _ptr(e, "e"), _ptr(dex, "dex", True), _ptr(pond, "pond", True),
+        float(q), float(m), float(dt), float(k1v), _stream(),
+    )
+    _lib.check(rc, "edfdv_exp")
+    _count()
+    return out
+
+
+def edfdv_spline(f, e, pond, q, m, dt, dv, dex=None, out=None):
+    """Cubic-spline v-advection (VelocityCubicSpline, vlasov.py:106-172); out-of-place."""
+    b, nx, nv = _shape3(f)
+    out = torch.empty_like(f) if out is None else out
+    rc = _lib.load().adept_b200_edfdv_spline_f64(
+        _ptr(f, "f"), _ptr(out, "out"), b, nx, nv, _ptr(e, "e"), _ptr(dex, "dex", True), _ptr(pond, "pond", True),
+        float(q), float(m), float(dt), float(dv), _stream(),
+    )
+    _lib.check(rc, "edfdv_spline")
+    _count()
+    return out
+
+
+def moments(f, v, scale_a, outs, bases=(None, None, None), scale_b=(1.0, 1.0, 1.0)):
+    """out_k = base_k + scale_b[k] * (sum_j f v^k * scale_a) for each non-None out_k (k = 0, 1, 2)."""
+    b, nx, nv = _shape3(f)
+    PA = C.c_void_p * 3
+    out_arr = PA(*[(_ptr(o, f"out{k}", True)) for k, o in enumerate(outs)])
+    base_arr = PA(*[(_ptr(o, f"base{k}", True)) for k, o in enumerate(bases)])
+    sb = (C.c_double * 3)(*[float(s) for s in scale_b])
+    rc = _lib.load().adept_b200_moments_f64(
+        _ptr(f, "f"), b, nx, nv, _ptr(v, "v", True), float(scale_a), base_arr, out_arr, sb, _stream()
+    )
+    _lib.check(rc, "moments")
+    _count()
+    return outs
+
+
+def poisson(rho, kmul, mode=0, Te=1.0, lambda_De=-1.0, out=None):
+    """Spectral field solve (field.py:210-224 / 282-298).  rho [nx] or [batch, nx]; kmul [nx] or [batch, nx]."""
+    nx = rho.shape[-1]
+    batch = rho.numel() // nx
+    stride = nx if (kmul.dim() == 2 and kmul.shape[0] == batch and batch > 1) else 0
+    out = torch.empty_like(rho) if out is None else out
+    rc = _lib.load().adept_b200_poisson_f64(
+        _ptr(rho, "rho"), _ptr(kmul, "kmul"), stride, _ptr(out, "out"), batch, nx, int(mode), float(Te),
+        float(lambda_De), _stream(),
+    )
+    _lib.check(rc, "poisson")
+    _count()
+    return out
+
+
+def axpy(a, b, s, out=None):
+    """out = a + s*b (Ampere update, field.py:354)."""
+    out = torch.empty_like(a) if out is None else out
+    rc = _lib.load().adept_b200_axpy_f64(_ptr(a, "a"), _ptr(b, "b"), float(s), _ptr(out, "out"), a.numel(), _stream())
+    _lib.check(rc, "axpy")
+    _count()
+    return out
+
+
+def ponderomotive(a, dx, out=None):
+    """pond = -0.5 gradient(a^2, dx)[1:-1] (field.py:495); a is [nx+2] or [batch, nx+2]."""
+    nx = a.shape[-1] - 2
+    batch = a.numel() // (nx + 2)
+    out = a.new_empty(a.shape[:-1] + (nx,)) if out is None else out
+    rc = _lib.load().adept_b200_ponderomotive_f64(_ptr(a, "a"), _ptr(out, "out"), batch, nx, float(dx), _stream())
+    _lib.check(rc, "ponderomotive")
+    _count()
+    return out
+
+
+def wave_step(a, aold, djy, ne_n, ne_np1, c, dx, dt, out=None):
+    """One wave-equation step (WaveSolver, field.py:109-157); returns the new a."""
+    nx = a.shape[-1] - 2
+    batch = a.numel() // (nx + 2)
+    out = torch.empty_like(a) if out is None else out
+    rc = _lib.load().adept_b200_wave_step_f64(
+        _ptr(a, "a"), _ptr(aold, "aold"), _ptr(djy, "djy"), _ptr(ne_n, "ne_n", True), _ptr(ne_np1, "ne_np1", True),
+        _ptr(out, "out"), batch, nx, float(c), float(dx), float(dt), _stream(),
+    )
+    _lib.check(rc, "wave_step")
+    _count()
+    return out
+
+
+def collide(f, v, dv, dt, nu_fp=None, nu_K=None, f_mx=None, model=1, scheme=0, nodrag=False, sg_m=2.0, sg_ratio=0.5,
+            n_out=None, out=None):
+    """Fokker-Planck (delta-form implicit) + Krook (fokker_planck.py:368-484)."""
+    b, nx, nv = _shape3(f)
+    out = torch.empty_like(f) if out is None else out
+    rc = _lib.load().adept_b200_collide_f64(
+        _ptr(f, "f"), _ptr(out, "out"), b, nx, nv, _ptr(v, "v"), float(dv), float(dt), _ptr(nu_fp, "nu_fp", True),
+        _ptr(nu_K, "nu_K", True), _ptr(f_mx, "f_mx", True), int(model), int(scheme), int(bool(nodrag)), float(sg_m),
+        float(sg_ratio), _ptr(n_out, "n_out", True), _stream(),
+    )
+    _lib.check(rc, "collide")
+    _count()
+    return out

@@ -1,0 +1,109 @@
+/* adept_b200 -- C ABI of libadept_b200.so: the B200-native `vlasov-1d` time-step operators of ergodicio/adept.
+ *
+ * Drop-in boundary.  The reference is Python/JAX; the binding a maintainer adds is a `jax.ffi` custom call (or,
+ * without jax, the ctypes stub in adept_b200/_lib.py) whose target forwards to the entry points below.  Each
+ * entry point replaces one reference operator (file:line relative to the reference tree):
+ *
+ *   adept_b200_vdfdx_f64         SpaceExponential.push/__call__      adept/_vlasov1d/solvers/pushers/vlasov.py:234-251
+ *   adept_b200_edfdv_exp_f64     VelocityExponential.push            adept/_vlasov1d/solvers/pushers/vlasov.py:74-91
+ *   adept_b200_edfdv_spline_f64  VelocityCubicSpline.push            adept/_vlasov1d/solvers/pushers/vlasov.py:106-172
+ *   adept_b200_moments_f64       compute_charge/current_density      adept/_vlasov1d/solvers/pushers/field.py:186-208,319-340
+ *   adept_b200_poisson_f64       SpectralPoisson / BoltzmannPoisson  adept/_vlasov1d/solvers/pushers/field.py:210-224,282-298
+ *   adept_b200_axpy_f64          AmpereSolver.__call__               adept/_vlasov1d/solvers/pushers/field.py:342-354
+ *   adept_b200_ponderomotive_f64 ElectricFieldSolver (pond)          adept/_vlasov1d/solvers/pushers/field.py:495
+ *   adept_b200_wave_step_f64     WaveSolver.__call__                 adept/_vlasov1d/solvers/pushers/field.py:109-157
+ *   adept_b200_collide_f64       Collisions._apply_collisions+Krook  adept/_vlasov1d/solvers/pushers/fokker_planck.py:368-484
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers (cudaMalloc / XLA buffers) unless the name ends in `_host`.
+ *   - f is [batch, nx, nv] in C order (v contiguous), fp64; `batch` independent ensemble members.
+ *   - Every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*); nothing synchronises, nothing is
+ *     allocated except the per-(device, n) twiddle tables on first use -- call adept_b200_prepare() before CUDA-graph
+ *     capture.  Callers own every buffer; nothing is retained after return.
+ *   - Return value: 0 on success, negative error code otherwise; adept_b200_last_error() gives the message
+ *     (thread-local).  No CPU fallback exists: without a CUDA device every compute entry point fails with
+ *     ADEPT_B200_ERR_CUDA.
+ */
+#ifndef ADEPT_B200_H
+#define ADEPT_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADEPT_B200_OK 0
+#define ADEPT_B200_ERR_BAD_SHAPE (-1)
+#define ADEPT_B200_ERR_UNSUPPORTED (-2)
+#define ADEPT_B200_ERR_CUDA (-3)
+#define ADEPT_B200_ERR_BAD_ARG (-4)
+
+/* Fokker-Planck model / differencing scheme selectors (fokker_planck.py:314-342) */
+#define ADEPT_B200_FP_LENARD_BERNSTEIN 0
+#define ADEPT_B200_FP_DOUGHERTY 1
+#define ADEPT_B200_FP_SUPER_GAUSSIAN 2
+#define ADEPT_B200_FP_CENTRAL 0
+#define ADEPT_B200_FP_CHANG_COOPER 1
+
+int adept_b200_version(void);
+const char* adept_b200_last_error(void);
+
+/* Build (once per device) the twiddle tables for a transform length n = 2^k, 2 <= n <= 8192. */
+int adept_b200_prepare(int n);
+
+/* x-advection: f_out = irfft(exp(-i kx_m v_j dt) rfft(f_in, axis=x), axis=x).
+ * v[nv] velocity grid; k1x = kx_real[1] = 2 pi / (nx dx); k1x_batch[batch] (nullable) overrides it per member.
+ * nx power of two (<= 8192), nv even.  In-place (f_out == f_in) allowed. */
+int adept_b200_vdfdx_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* v, double dt,
+                         double k1x, const double* k1x_batch, void* stream);
+
+/* v-advection (spectral): accel_i = (q (e_i + dex_i) + (q^2/m) pond_i)/m;
+ * f_out = irfft(exp(-i kv_n dt accel_i) rfft(f_in, axis=v), axis=v).  e, dex, pond are [batch, nx]
+ * (dex, pond nullable); k1v = kv_real[1] = 2 pi / (nv dv).  nv power of two (<= 8192), nx even.  In-place allowed. */
+int adept_b200_edfdv_exp_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* e,
+                             const double* dex, const double* pond, double charge, double mass, double dt, double k1v,
+                             void* stream);
+
+/* v-advection (semi-Lagrangian, local cubic Hermite; out-of-range queries -> 1e-30).  Out-of-place only. */
+int adept_b200_edfdv_spline_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* e,
+                                const double* dex, const double* pond, double charge, double mass, double dt,
+                                double dv, void* stream);
+
+/* Velocity moments per x-row: s_k = sum_j f[., j] v_j^k (k = 0, 1, 2).  For each non-null out_k:
+ *   out_k[row] = (base_k ? base_k[row] : 0) + scale_b[k] * (s_k * scale_a)
+ * e.g. charge density: scale_a = dv, scale_b[0] = q, base_0 = ion background.  out/base: host arrays of 3 device
+ * pointers; scale_b host array of 3 doubles (nullable -> 1). */
+int adept_b200_moments_f64(const double* f, int batch, int nx, int nv, const double* v, double scale_a,
+                           const double* const* base_host, double* const* out_host, const double* scale_b_host,
+                           void* stream);
+
+/* Field solve, one FFT of length nx per member.  mode 0: E = Re ifft(-i kmul fft(rho)), kmul = one_over_kx[nx].
+ * mode 1 (Boltzmann electrons): kmul = kx[nx], kernel kx (Te/rho0) / (1 + lambda^2 kx^2), rho0 = mean(rho),
+ * lambda_De < 0 selects lambda^2 = Te/rho0.  kmul_stride = 0 shares kmul between members, nx = per-member tables. */
+int adept_b200_poisson_f64(const double* rho, const double* kmul, long long kmul_stride, double* e, int batch, int nx,
+                           int mode, double Te, double lambda_De, void* stream);
+
+/* out[i] = a[i] + s * b[i]  (Ampere: E = E_prev - dt j). */
+int adept_b200_axpy_f64(const double* a, const double* b, double s, double* out, long long n, void* stream);
+
+/* pond[b, i] = -0.5 (a[b, i+2]^2 - a[b, i]^2) / (2 dx); a is [batch, nx+2]. */
+int adept_b200_ponderomotive_f64(const double* a, double* pond, int batch, int nx, double dx, void* stream);
+
+/* One leap-frog step of the transverse wave equation with 2nd-order absorbing boundaries.  a, aold, djy, a_new are
+ * [batch, nx+2]; ne_n / ne_np1 [batch, nx] are the electron charge densities before / after the step (nullable = 0).
+ * The caller sets prev_a := a afterwards. */
+int adept_b200_wave_step_f64(const double* a, const double* aold, const double* djy, const double* ne_n,
+                             const double* ne_np1, double* a_new, int batch, int nx, double c, double dx, double dt,
+                             void* stream);
+
+/* Collisions on every x-row: implicit Fokker-Planck (delta form) then Krook.
+ * nu_fp / nu_K: [batch, nx] collision frequencies; null disables the operator.  f_mx[nv]: Krook target (unit
+ * density Maxwellian, fokker_planck.py:463-464).  n_out (nullable) receives sum_j f_out dv.  In-place allowed.
+ * nv % 8 == 0 and nv <= 16384 (small even nv also accepted). */
+int adept_b200_collide_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* v, double dv,
+                           double dt, const double* nu_fp, const double* nu_K, const double* f_mx, int model,
+                           int scheme, int nodrag, double sg_m, double sg_ratio, double* n_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADEPT_B200_H */

@@ -1,0 +1,337 @@
+"""GPU parity tests: every C-ABI operator of libadept_b200.so against the numpy oracle on the same inputs.
+
+Tolerance (BASELINE.json north_star): per-application relative L2 <= 1e-12 in fp64; the cubic stencil's
+integer-cell shifts are bit-exact (reference test_velocity_cubic_spline.py:35-46).
+"""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vlasov1d as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from adept_b200 import ops as _ops
+
+    return _ops
+
+
+def dev(x):
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float64, device="cuda")
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def make_f(nx, nv, vmax=6.4, seed=0, noise=0.0, xmax=20.94):
+    rng = np.random.default_rng(seed)
+    dv = 2 * vmax / nv
+    v = np.linspace(-vmax + dv / 2, vmax - dv / 2, nv)
+    dx = xmax / nx
+    x = np.linspace(dx / 2, xmax - dx / 2, nx)
+    k0 = 2 * np.pi / xmax
+    f = (1 + 0.3 * np.cos(k0 * x) + 0.1 * np.sin(3 * k0 * x))[:, None] * np.exp(-((v - 0.3) ** 2) / 2)[None, :]
+    f = f / (np.sum(np.exp(-(v**2) / 2)) * dv)
+    if noise:
+        f = f + noise * rng.standard_normal((nx, nv))
+    return f, x, v, dx, dv
+
+
+# ---------------------------------------------------------------------------------------------------- x-advection
+@pytest.mark.parametrize("nx,nv", [(2, 8), (4, 16), (8, 1024), (16, 64), (32, 256), (64, 512), (128, 32), (256, 64),
+                                   (512, 32), (1024, 64), (2048, 16), (4096, 64), (8192, 8)])
+@pytest.mark.parametrize("noise", [0.0, 0.05])
+def test_vdfdx_matches_oracle(ops, nx, nv, noise):
+    f, x, v, dx, dv = make_f(nx, nv, seed=nx + nv, noise=noise)
+    kxr = np.fft.rfftfreq(nx, d=dx) * 2 * np.pi
+    dt = 0.1
+    ref = O.space_exponential(f, kxr, v, dt)
+    out = host(ops.vdfdx(dev(f), dev(v), dt, kxr[1]))
+    assert rel_l2(out, ref) <= RTOL
+
+
+def test_vdfdx_inplace_negative_dt_and_batch(ops):
+    nx, nv, B = 64, 128, 3
+    fs, k1s, refs = [], [], []
+    for b in range(B):
+        f, x, v, dx, dv = make_f(nx, nv, seed=b, noise=0.01, xmax=20.0 + 3 * b)
+        kxr = np.fft.rfftfreq(nx, d=dx) * 2 * np.pi
+        fs.append(f)
+        k1s.append(kxr[1])
+        refs.append(O.space_exponential(f, kxr, v, -0.37))
+    fd = dev(np.stack(fs))
+    ops.vdfdx(fd, dev(v), -0.37, 0.0, out=fd, k1x_batch=dev(np.array(k1s)))
+    assert rel_l2(host(fd), np.stack(refs)) <= RTOL
+
+
+def test_vdfdx_exact_characteristic_shift(ops):
+    """reference test_multispecies_pushers.py:16-64 (sinusoid, nv=2 instead of 1: nv must be even)."""
+    Lx = 2 * np.pi
+    for nx in [16, 32]:
+        dx = Lx / nx
+        x = np.linspace(0, Lx - dx, nx)
+        v = np.array([0.5, -0.25])
+        f = np.sin(2 * x)[:, None] * np.ones((1, 2))
+        out = host(ops.vdfdx(dev(f), dev(v), 0.01, 2 * np.pi / (nx * dx)))
+        exact = np.sin(2 * x[:, None] - 2 * v[None, :] * 0.01)
+        assert np.sqrt(np.mean((out - exact) ** 2)) < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------------- v-advection
+@pytest.mark.parametrize("nx,nv", [(2, 2), (4, 8), (32, 16), (32, 256), (64, 512), (8, 1024), (16, 2048), (8, 4096),
+                                   (4, 8192), (6, 64)])
+@pytest.mark.parametrize("noise", [0.0, 0.05])
+def test_edfdv_exp_matches_oracle(ops, nx, nv, noise):
+    f, x, v, dx, dv = make_f(nx, nv, seed=nx * 3 + nv, noise=noise)
+    rng = np.random.default_rng(nx)
+    e, dex, pond = 0.3 * rng.standard_normal(nx), 0.01 * rng.standard_normal(nx), 0.02 * rng.standard_normal(nx)
+    kvr = np.fft.rfftfreq(nv, d=dv) * 2 * np.pi
+    q, m, dt = -1.0, 1.0, 0.1
+    ref = O.velocity_exponential(f, kvr, e + dex, pond, dt, q, m)
+    out = host(ops.edfdv_exp(dev(f), dev(e), dev(pond), q, m, dt, kvr[1], dex=dev(dex)))
+    assert rel_l2(out, ref) <= RTOL
+    # ion-like species, no pond / dex
+    q, m = 10.0, 18360.0
+    ref = O.velocity_exponential(f, kvr, e, np.zeros(nx), dt, q, m)
+    out = host(ops.edfdv_exp(dev(f), dev(e), None, q, m, dt, kvr[1]))
+    assert rel_l2(out, ref) <= RTOL
+
+
+def test_edfdv_exp_exact_characteristic_shift(ops):
+    """reference test_multispecies_pushers.py:67-140."""
+    vmax = 2 * np.pi
+    for nv in [16, 32]:
+        dv = 2.0 * vmax / nv
+        v = np.linspace(-vmax + dv / 2, vmax - dv / 2, nv)
+        k = np.pi / vmax
+        f = np.sin(k * v)[None, :] * np.ones((2, 1))
+        e = np.array([0.5, 0.5])
+        for q, m in [(-1.0, 1.0), (1.0, 1836.0)]:
+            out = host(ops.edfdv_exp(dev(f), dev(e), None, q, m, 0.01, 2 * np.pi / (nv * dv)))
+            exact = np.sin(k * (v - (q / m) * 0.5 * 0.01))[None, :]
+            assert np.sqrt(np.mean((out - exact) ** 2)) < 1e-12
+
+
+@pytest.mark.parametrize("nx,nv,vmin,vmax", [(8, 64, -6.4, 6.4), (8, 64, -4.0, 8.0), (32, 256, -6.4, 6.4),
+                                             (64, 4096, -6.4, 6.4), (5, 40, -0.5, 1.0)])
+def test_edfdv_spline_matches_oracle(ops, nx, nv, vmin, vmax):
+    rng = np.random.default_rng(nv)
+    dv = (vmax - vmin) / nv
+    f = rng.standard_normal((nx, nv))
+    base = np.array([-70.0, -2.17, -0.37, 0.0, 0.25, 1.13, 3.4, 70.0])
+    shift_cells = np.resize(base, nx) + 0.01 * rng.standard_normal(nx) * (np.resize(base, nx) != 0)
+    q, m, dt = -1.0, 1.0, 0.17
+    e = shift_cells * dv / dt * m / q
+    pond = np.zeros(nx)
+    ref = O.velocity_cubic_spline(f, dv, e, pond, dt, q, m)
+    out = host(ops.edfdv_spline(dev(f), dev(e), None, q, m, dt, dv))
+    np.testing.assert_allclose(out, ref, rtol=2e-12, atol=2e-12)
+    # with pond + dex and a different species
+    q, m = 1.0, 4.0
+    e2, dex, pond = rng.standard_normal(nx), 0.1 * rng.standard_normal(nx), 0.05 * rng.standard_normal(nx)
+    ref = O.velocity_cubic_spline(f, dv, e2 + dex, pond, dt, q, m)
+    out = host(ops.edfdv_spline(dev(f), dev(e2), dev(pond), q, m, dt, dv, dex=dev(dex)))
+    np.testing.assert_allclose(out, ref, rtol=2e-12, atol=2e-12)
+
+
+def test_edfdv_spline_integer_shifts_bit_exact(ops):
+    """reference test_velocity_cubic_spline.py:35-46."""
+    nx, nv, dv = 3, 16, 0.25
+    f = np.arange(nx * nv, dtype=np.float64).reshape(nx, nv)
+    shift = dv * np.array([1.0, -1.0, 0.0])
+    out = host(ops.edfdv_spline(dev(f), dev(shift), None, 1.0, 1.0, 1.0, dv))  # accel*dt = e
+    expected = np.empty((nx, nv))
+    expected[0] = np.concatenate(([1.0e-30], f[0, :-1]))
+    expected[1] = np.concatenate((f[1, 1:], [1.0e-30]))
+    expected[2] = f[2]
+    np.testing.assert_array_equal(out, expected)
+
+
+# ---------------------------------------------------------------------------------------------------- moments / fields
+@pytest.mark.parametrize("nx,nv", [(32, 256), (7, 33), (64, 4096)])
+def test_moments_match_numpy(ops, nx, nv):
+    f, x, v, dx, dv = make_f(nx, nv, seed=5, noise=0.01)
+    ion = np.linspace(0.9, 1.1, nx)
+    fd, vd = dev(f), dev(v)
+    rho, j, p2 = (torch.empty(nx, dtype=torch.float64, device="cuda") for _ in range(3))
+    ops.moments(fd, vd, dv, (rho, j, p2), bases=(dev(ion), None, None), scale_b=(-1.0, -1.0, 1.0))
+    np.testing.assert_allclose(host(rho), -1.0 * (np.sum(f, 1) * dv) + ion, rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(host(j), -1.0 * (np.sum(f * v, 1) * dv), rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(host(p2), np.sum(f * v * v, 1) * dv, rtol=1e-13)
+
+
+@pytest.mark.parametrize("nx", [2, 8, 32, 64, 256, 2048, 4096, 8192])
+def test_poisson_matches_oracle(ops, nx):
+    rng = np.random.default_rng(nx)
+    dx = 20.94 / nx
+    kx = np.fft.fftfreq(nx, d=dx) * 2 * np.pi
+    ook = np.zeros(nx)
+    ook[1:] = 1.0 / kx[1:]
+    rho = 1e-2 * rng.standard_normal(nx)
+    e = host(ops.poisson(dev(rho), dev(ook)))
+    assert rel_l2(e, O.poisson(rho, ook)) <= RTOL
+    rho_i = 1.0 + 1e-2 * rng.standard_normal(nx)
+    for lam in [None, 0.0, 0.7]:
+        e = host(ops.poisson(dev(rho_i), dev(kx), mode=1, Te=2.0, lambda_De=-1.0 if lam is None else lam))
+        assert rel_l2(e, O.boltzmann_poisson(rho_i, kx, 2.0, lam)) <= RTOL
+
+
+def test_poisson_batched(ops):
+    nx, B = 64, 5
+    rng = np.random.default_rng(0)
+    rho = rng.standard_normal((B, nx))
+    ooks = []
+    for b in range(B):
+        kx = np.fft.fftfreq(nx, d=(20.0 + b) / nx) * 2 * np.pi
+        ook = np.zeros(nx)
+        ook[1:] = 1.0 / kx[1:]
+        ooks.append(ook)
+    ooks = np.stack(ooks)
+    e = host(ops.poisson(dev(rho), dev(ooks)))
+    ref = np.stack([O.poisson(rho[b], ooks[b]) for b in range(B)])
+    assert rel_l2(e, ref) <= RTOL
+    e = host(ops.poisson(dev(rho), dev(ooks[0])))
+    ref = np.stack([O.poisson(rho[b], ooks[0]) for b in range(B)])
+    assert rel_l2(e, ref) <= RTOL
+
+
+def test_ponderomotive_axpy_wave(ops):
+    nx = 300
+    rng = np.random.default_rng(1)
+    a, aold, djy = (1e-2 * rng.standard_normal(nx + 2) for _ in range(3))
+    dx, dt, c = 0.3, 0.02, 11.3
+    np.testing.assert_allclose(host(ops.ponderomotive(dev(a), dx)), O.ponderomotive(a, dx), rtol=1e-14, atol=1e-300)
+    n0, n1 = -1.0 + 0.01 * rng.standard_normal(nx), -1.0 + 0.01 * rng.standard_normal(nx)
+    ref = O.wave_solver(a, aold, djy, -0.5 * (n0 + n1), c, dx, dt)["a"]
+    out = host(ops.wave_step(dev(a), dev(aold), dev(djy), dev(n0), dev(n1), c, dx, dt))
+    np.testing.assert_allclose(out, ref, rtol=1e-12, atol=1e-16)
+    ref = O.wave_solver(a, aold, djy, 0.0, c, dx, dt)["a"]
+    out = host(ops.wave_step(dev(a), dev(aold), dev(djy), None, None, c, dx, dt))
+    np.testing.assert_allclose(out, ref, rtol=1e-12, atol=1e-16)
+    e, j = rng.standard_normal(nx), rng.standard_normal(nx)
+    np.testing.assert_array_equal(host(ops.axpy(dev(e), dev(j), -dt)), e - dt * j)
+
+
+# ---------------------------------------------------------------------------------------------------- collisions
+def _fp_cfg(nv, vmax, fp_type, krook=False, T0=1.0, m=2.0):
+    dv = 2.0 * vmax / nv
+    v = np.linspace(-vmax + dv / 2.0, vmax - dv / 2.0, nv)
+    return {
+        "grid": {
+            "species_grids": {"electron": {"v": v, "dv": dv, "nv": nv, "vmax": vmax}},
+            "species_params": {"electron": {"charge": -1.0, "mass": 1.0, "charge_to_mass": -1.0, "T0": T0}},
+        },
+        "terms": {"fokker_planck": {"is_on": True, "type": fp_type, "m": m}, "krook": {"is_on": krook}},
+    }
+
+
+MODEL = {"lb": 0, "dougherty": 1, "sg": 2}
+SCHEME = {"central": 0, "cc": 1}
+
+
+def _gpu_collide(ops, coll, f, nu_fp, nu_K, dt, n_out=None):
+    from scipy.special import gammaln
+
+    m = coll.m
+    ratio = float(np.exp(gammaln(3.0 / m) - gammaln(1.0 / m)))
+    return ops.collide(
+        dev(f), dev(coll.v), coll.dv, dt,
+        nu_fp=None if nu_fp is None else dev(nu_fp), nu_K=None if nu_K is None else dev(nu_K),
+        f_mx=dev(coll.f_mx[0]), model=MODEL[coll.model], scheme=SCHEME[coll.scheme], nodrag=coll.nodrag,
+        sg_m=m, sg_ratio=ratio, n_out=n_out,
+    )
+
+
+@pytest.mark.parametrize("fp_type", ["lenard_bernstein", "chang_cooper", "dougherty", "chang_cooper_dougherty",
+                                     "dougherty_nodrag", "super_gaussian"])
+@pytest.mark.parametrize("nx,nv", [(16, 512), (8, 1024), (32, 256), (3, 64), (4, 4096), (2, 6144), (5, 96)])
+def test_collide_matches_oracle(ops, fp_type, nx, nv):
+    cfg = _fp_cfg(nv, 6.4, fp_type, m=3.0 if fp_type == "super_gaussian" else 2.0)
+    coll = O.Collisions(cfg)
+    f, x, v, dx, dv = make_f(nx, nv, seed=nv, noise=0.0)
+    f = f * (1 + 0.05 * np.sin(7 * v))[None, :]
+    nu = np.linspace(0.2, 1.0, nx)
+    dt = 0.1
+    ref = coll(nu, None, f, dt)
+    out = host(_gpu_collide(ops, coll, f, nu, None, dt))
+    assert rel_l2(out, ref) <= RTOL
+    # weakly collisional production regime
+    nu2 = 1e-5 * np.ones(nx)
+    ref = coll(nu2, None, f, dt)
+    out = host(_gpu_collide(ops, coll, f, nu2, None, dt))
+    assert rel_l2(out, ref) <= RTOL
+
+
+def test_collide_strongly_collisional(ops):
+    nx, nv = 8, 512
+    coll = O.Collisions(_fp_cfg(nv, 6.4, "dougherty"))
+    f, *_ = make_f(nx, nv, seed=3)
+    nu = 200.0 * np.ones(nx)
+    ref = coll(nu, None, f, 0.5)
+    out = host(_gpu_collide(ops, coll, f, nu, None, 0.5))
+    assert rel_l2(out, ref) <= 1e-11  # ill-conditioned limit (nu dt D/dv^2 ~ 1.6e5): allow 10x
+
+
+@pytest.mark.parametrize("fp_on", [True, False])
+def test_collide_krook_and_density_output(ops, fp_on):
+    nx, nv = 12, 256
+    cfg = _fp_cfg(nv, 6.4, "dougherty", krook=True, T0=1.3)
+    cfg["terms"]["fokker_planck"]["is_on"] = fp_on
+    coll = O.Collisions(cfg)
+    f, *_ = make_f(nx, nv, seed=9, noise=0.0)
+    nu_fp = np.linspace(0.1, 0.5, nx)
+    nu_K = np.linspace(0.0, 2.0, nx)
+    ref = coll(nu_fp if fp_on else None, nu_K, f, 0.1)
+    n_out = torch.empty(nx, dtype=torch.float64, device="cuda")
+    out = host(_gpu_collide(ops, coll, f, nu_fp if fp_on else None, nu_K, 0.1, n_out=n_out))
+    assert rel_l2(out, ref) <= RTOL
+    np.testing.assert_allclose(host(n_out), np.sum(ref, 1) * coll.dv, rtol=1e-13)
+
+
+def test_collide_conservation_50_steps(ops):
+    """reference test_fp_momentum_conservation.py:44-83 through the CUDA kernel."""
+    for fp_type, energy_rtol in [("dougherty", 5e-3), ("chang_cooper_dougherty", 1e-5)]:
+        nx, nv, vmax = 16, 512, 6.4
+        coll = O.Collisions(_fp_cfg(nv, vmax, fp_type))
+        v, dv = coll.v, coll.dv
+        xx = np.linspace(0, 2 * np.pi, nx, endpoint=False)
+        f = (1.0 + 0.5 * np.sin(xx))[:, None] * np.exp(-((v[None, :] - 0.5) ** 2) / 2.0)
+        f = f / (np.sum(np.exp(-((v - 0.5) ** 2) / 2.0)) * dv)
+        fd, vd, nu = dev(f), dev(v), dev(np.ones(nx))
+        for _ in range(50):
+            fd = ops.collide(fd, vd, dv, 0.1, nu_fp=nu, model=1, scheme=SCHEME[coll.scheme])
+        out = host(fd)
+        np.testing.assert_allclose(np.sum(out, 1) * dv, np.sum(f, 1) * dv, rtol=1e-10)
+        np.testing.assert_allclose(np.sum(out * v, 1) * dv, np.sum(f * v, 1) * dv, rtol=1e-6)
+        np.testing.assert_allclose(np.sum(out * v**2, 1) * dv, np.sum(f * v**2, 1) * dv, rtol=energy_rtol)
+
+
+# ---------------------------------------------------------------------------------------------------- error behaviour
+def test_errors_are_loud(ops):
+    from adept_b200._lib import AdeptB200Error
+
+    f = torch.zeros(12, 16, dtype=torch.float64, device="cuda")
+    v = torch.zeros(16, dtype=torch.float64, device="cuda")
+    with pytest.raises(AdeptB200Error, match="power of two"):
+        ops.vdfdx(f, v, 0.1, 1.0)  # nx = 12
+    with pytest.raises(AdeptB200Error, match="no CPU path"):
+        ops.vdfdx(f.cpu(), v, 0.1, 1.0)
+    with pytest.raises(AdeptB200Error, match="float64"):
+        ops.vdfdx(f.float(), v, 0.1, 1.0)
+    g = torch.zeros(16, 16, dtype=torch.float64, device="cuda")
+    with pytest.raises(AdeptB200Error, match="in-place"):
+        ops.edfdv_spline(g, v, None, 1.0, 1.0, 0.1, 0.1, out=g)
