@@ -1,0 +1,252 @@
+"""Step composition for the vlasov-1d path: integrators, Vlasov-Poisson-Fokker-Planck step and the VlasovMaxwell
+vector field, with the same class names, constructor arguments and call signatures as the reference's
+``adept/_vlasov1d/solvers/vector_field.py`` (:19-361).  The state is a dict of CUDA tensors with the reference's keys
+(species names, ``e, de [nx]``, ``a, da, prev_a [nx+2]``, optional ``diag-*``); ``VlasovMaxwell.__call__(t, y, args)``
+is a map y -> y' exactly like the reference's (adept/_base_.py:37-41).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops, pushers
+
+
+def _is_parallel(parallel, axis: str) -> bool:
+    if not parallel:
+        return False
+    return axis in parallel
+
+
+class TimeIntegrator:
+    """Shared field solver and Vlasov pushers; vector_field.py:19-52."""
+
+    def __init__(self, cfg: dict, grid):
+        self.field_solve = pushers.ElectricFieldSolver(cfg, grid)
+        self.species_grids = cfg["grid"]["species_grids"]
+        self.species_params = cfg["grid"]["species_params"]
+        parallel = cfg["grid"].get("parallel", False)
+        self.edfdv = self.get_edfdv(cfg, parallel)
+        self.vdfdx = pushers.SpaceExponential(grid.x, self.species_grids, parallel=_is_parallel(parallel, "v"))
+
+    def get_edfdv(self, cfg: dict, parallel):
+        kind = cfg["terms"]["edfdv"]
+        if kind == "exponential":
+            return pushers.VelocityExponential(self.species_grids, self.species_params,
+                                               parallel=_is_parallel(parallel, "x"))
+        if kind == "cubic-spline":
+            return pushers.VelocityCubicSpline(self.species_grids, self.species_params,
+                                               parallel=_is_parallel(parallel, "x"))
+        raise NotImplementedError(f"{kind} has not been implemented")
+
+
+class LeapfrogIntegrator(TimeIntegrator):
+    """x-push, field solve on f*, v-push; vector_field.py:55-95."""
+
+    def __init__(self, cfg: dict, grid):
+        super().__init__(cfg, grid)
+        self.dt = grid.dt
+        self.dt_array = self.dt * np.array([0.0, 1.0])
+
+    def __call__(self, f_dict, a, dex_array, prev_ex):
+        f_after_v = self.vdfdx(f_dict, dt=self.dt)
+        f_for_field = f_dict if self.field_solve.hampere else f_after_v
+        pond, e = self.field_solve(f_dict=f_for_field, a=a, prev_ex=prev_ex, dt=self.dt)
+        # e + dex[0] is formed inside the push kernel (same rounding as the reference's explicit sum)
+        f_out = self.edfdv(f_after_v, e=e, pond=pond, dt=self.dt, dex=dex_array[0])
+        return e, f_out
+
+
+class SixthOrderHamIntegrator(TimeIntegrator):
+    """6th-order Hamiltonian splitting: 6 x (field solve + v-push) interleaved with 5 x-pushes; :98-186."""
+
+    def __init__(self, cfg: dict, grid):
+        super().__init__(cfg, grid)
+        self.dt = grid.dt
+        self.a1 = 0.168735950563437422448196
+        self.a2 = 0.377851589220928303880766
+        self.a3 = -0.093175079568731452657924
+        b1 = 0.049086460976116245491441
+        b2 = 0.264177609888976700200146
+        b3 = 0.186735929134907054308413
+        c1 = -0.000069728715055305084099
+        c2 = -0.000625704827430047189169
+        c3 = -0.002213085124045325561636
+        d2 = -2.916600457689847816445691e-6
+        d3 = 3.048480261700038788680723e-5
+        e3 = 4.985549387875068121593988e-7
+        self.D1 = b1 + 2.0 * c1 * self.dt**2.0
+        self.D2 = b2 + 2.0 * c2 * self.dt**2.0 + 4.0 * d2 * self.dt**4.0
+        self.D3 = b3 + 2.0 * c3 * self.dt**2.0 + 4.0 * d3 * self.dt**4.0 - 8.0 * e3 * self.dt**6.0
+        self.dt_array = self.dt * np.array(
+            [
+                0.0,
+                self.a1,
+                self.a1 + self.a2,
+                self.a1 + self.a2 + self.a3,
+                self.a1 + self.a2 + self.a3 + self.a2,
+                self.a1 + self.a2 + self.a3 + self.a2 + self.a1,
+            ]
+        )
+
+    def __call__(self, f_dict, a, dex_array, prev_ex):
+        Ds = (self.D1, self.D2, self.D3, self.D3, self.D2, self.D1)
+        As = (self.a1, self.a2, self.a3, self.a2, self.a1)
+        e = None
+        for i in range(6):
+            pond, e = self.field_solve(f_dict=f_dict, a=a, prev_ex=None, dt=None)
+            f_dict = self.edfdv(f_dict, e=e, pond=pond, dt=Ds[i] * self.dt, dex=dex_array[i])
+            if i < 5:
+                f_dict = self.vdfdx(f_dict, dt=As[i] * self.dt)
+        return e, f_dict
+
+
+class VlasovPoissonFokkerPlanck:
+    """integrator -> collisions -> (filter) -> dfdt diagnostics; vector_field.py:189-253."""
+
+    def __init__(self, cfg: dict, grid):
+        self.dt = grid.dt
+        if cfg["terms"]["time"] == "sixth":
+            self.vlasov_poisson = SixthOrderHamIntegrator(cfg, grid)
+            self.dex_save = 3
+        elif cfg["terms"]["time"] == "leapfrog":
+            self.vlasov_poisson = LeapfrogIntegrator(cfg, grid)
+            self.dex_save = 0
+        else:
+            raise NotImplementedError
+        self.fp = pushers.Collisions(cfg=cfg)
+        self.vlasov_dfdt = cfg["diagnostics"]["diag-vlasov-dfdt"]
+        self.fp_dfdt = cfg["diagnostics"]["diag-fp-dfdt"]
+        hl = cfg["terms"].get("hou_li_filter")
+        self.hou_li_filter_on = bool(hl and hl.get("is_on", False))
+        if self.hou_li_filter_on:
+            self.hou_li_filter = pushers.HouLiFilter(nx=cfg["grid"]["nx"], alpha=hl["alpha"], order=hl["order"])
+
+    def __call__(self, f_dict, a, prev_ex, dex_array, nu_fp, nu_K, n_out=None):
+        e, f_vlasov = self.vlasov_poisson(f_dict, a, dex_array, prev_ex)
+        f_fp = self.fp(nu_fp, nu_K, f_vlasov, dt=self.dt, n_out=n_out)
+        if self.hou_li_filter_on:
+            f_fp = self.hou_li_filter(f_fp)
+        diags = {}
+        ref_species = "electron" if "electron" in f_dict else next(iter(f_dict))
+        if self.vlasov_dfdt:
+            diags["diag-vlasov-dfdt"] = (f_vlasov[ref_species] - f_dict[ref_species]) / self.dt
+        if self.fp_dfdt:
+            diags["diag-fp-dfdt"] = (f_fp[ref_species] - f_vlasov[ref_species]) / self.dt
+        return e, f_fp, diags
+
+
+class VlasovMaxwell:
+    """One full vlasov-1d step y -> y'; vector_field.py:256-361."""
+
+    def __init__(self, cfg, grid, drivers=None, nu_fp_prof=None, nu_K_prof=None, device="cuda"):
+        from .functions import SpaceTimeEnvelopeFunction
+
+        self.cfg, self.grid, self.device = cfg, grid, device
+        self.vpfp = VlasovPoissonFokkerPlanck(cfg, grid)
+        beta = cfg["grid"]["beta"]
+        c = 1.0 / beta
+        self.c = c
+        self.wave_solver = pushers.WaveSolver(c=c, dx=grid.dx, dt=grid.dt)
+        self.dt = grid.dt
+        dcfg = cfg.get("drivers", {"ex": {}, "ey": {}})
+        if drivers is None:
+            ex = [pushers.EMDriver.from_config(d, c) for d in dcfg.get("ex", {}).values()]
+            ey = [pushers.EMDriver.from_config(d, c) for d in dcfg.get("ey", {}).values()]
+            if dcfg.get("ex_stochastic") is not None:
+                raise NotImplementedError("adept_b200: the stochastic Ex driver is not implemented")
+        else:
+            ex, ey = drivers["ex"], drivers["ey"]
+        self.ey_driver = pushers.TransverseCurrentSourceDriver(grid.x_a, drivers=ey, c=c, device=device)
+        self.ex_driver = pushers.LongitudinalElectricFieldDriver(grid.x, drivers=ex, device=device)
+        self.has_ey = len(ey) > 0
+        fpc, kc = cfg["terms"]["fokker_planck"], cfg["terms"]["krook"]
+        self.fp_on, self.krook_on = bool(fpc["is_on"]), bool(kc["is_on"])
+        self.nu_fp_prof = nu_fp_prof if nu_fp_prof is not None else (
+            SpaceTimeEnvelopeFunction.from_config(fpc) if self.fp_on else None)
+        self.nu_K_prof = nu_K_prof if nu_K_prof is not None else (
+            SpaceTimeEnvelopeFunction.from_config(kc) if self.krook_on else None)
+        self._x = np.asarray(grid.x)
+        self._dev_cache = {}
+        self._zeros_a = torch.zeros(grid.nx + 2, dtype=torch.float64, device=device)
+        self._a_live = None
+
+    def _dev(self, arr):
+        return torch.as_tensor(np.ascontiguousarray(arr, dtype=np.float64), device=self.device)
+
+    def total_dex(self, t, args=None):
+        return self.ex_driver(t, args)
+
+    def _nu(self, prof, t, key):
+        """nu(x, t) = time_env(t) * space_env(x): the space factor lives on the device, the time factor is a scalar."""
+        if key not in self._dev_cache:
+            self._dev_cache[key] = self._dev(prof.space_envelope(self._x))
+        return self._dev_cache[key] * float(prof.time_envelope(t))
+
+    def host_inputs(self, t):
+        """Everything one step needs besides the state, evaluated on the host (numpy, O(nx)): the driver fields at the
+        substep times and the collision-frequency profiles (vector_field.py:319-331).  A caller that keeps time on the
+        host copies these to the device and passes them as ``args`` to ``__call__``."""
+        t = float(t)
+        dt_array = self.vpfp.vlasov_poisson.dt_array
+        n_dex = 1 if self.vpfp.dex_save == 0 else len(dt_array)
+        out = {"dex": np.stack([self.ex_driver.host(t + float(d)) for d in dt_array[:n_dex]])}
+        out["djy"] = self.ey_driver.host(t + float(dt_array[1]))
+        if self.fp_on:
+            out["nu_fp"] = self.nu_fp_prof(self._x, t) * np.ones_like(self._x)
+        if self.krook_on:
+            out["nu_K"] = self.nu_K_prof(self._x, t) * np.ones_like(self._x)
+        return out
+
+    def compute_electron_charge_density(self, f_dict):
+        """q_e sum_v f_e dv (zeros if there is no electron species); vector_field.py:297-306."""
+        if "electron" not in f_dict:
+            return torch.zeros(self.grid.nx, dtype=torch.float64, device=self.device)
+        f = f_dict["electron"]
+        dv = float(self.cfg["grid"]["species_grids"]["electron"]["dv"])
+        q = self.cfg["grid"]["species_params"]["electron"]["charge"]
+        out = torch.empty(f.shape[:-1], dtype=torch.float64, device=f.device)
+        # reference: 0 + q * (sum * dv)
+        ops.moments(f, None, dv, (out, None, None), scale_b=(q, 1.0, 1.0))
+        return out
+
+    def __call__(self, t, y, args=None):
+        t = float(t)
+        dt_array = self.vpfp.vlasov_poisson.dt_array
+        n_dex = 1 if self.vpfp.dex_save == 0 else len(dt_array)  # leapfrog only ever reads dex[0]
+        if args is not None and "dex" in args:
+            # per-step inputs supplied by the caller as device tensors (see host_inputs): dex [n_dex, nx], ...
+            dex = list(args["dex"])
+            djy = args["djy"] if self.has_ey else self._zeros_a
+            nu_fp = args.get("nu_fp") if self.fp_on else None
+            nu_K = args.get("nu_K") if self.krook_on else None
+        else:
+            dex = [self.total_dex(t + float(d), args) for d in dt_array[:n_dex]]
+            djy = self.ey_driver(t + float(dt_array[1]), args) if self.has_ey else self._zeros_a
+            nu_fp = self._nu(self.nu_fp_prof, t, "fp") if self.fp_on else None
+            nu_K = self._nu(self.nu_K_prof, t, "K") if self.krook_on else None
+        species = self.cfg["grid"]["species_grids"]
+        f_dict = {k: v for k, v in y.items() if k in species}
+
+        # With no Ey driver and a == prev_a == 0 the wave update returns exactly 0 whatever the density is
+        # (field.py:149-153), so the two density reductions and the wave kernel are skipped.  Checked once.
+        if self._a_live is None:
+            self._a_live = self.has_ey or bool(torch.any(y["a"] != 0)) or bool(torch.any(y["prev_a"] != 0))
+        need_wave = self._a_live
+        if not need_wave:
+            e, f_new, diags = self.vpfp(f_dict=f_dict, a=y["a"], prev_ex=y["e"], dex_array=dex, nu_fp=nu_fp,
+                                        nu_K=nu_K)
+            result = {"a": y["a"], "prev_a": y["a"], "da": djy, "de": dex[self.vpfp.dex_save], "e": e}
+            result.update(f_new)
+            result.update(diags)
+            return result
+        ne_n = self.compute_electron_charge_density(f_dict) if need_wave else None
+        e, f_new, diags = self.vpfp(f_dict=f_dict, a=y["a"], prev_ex=y["e"], dex_array=dex, nu_fp=nu_fp, nu_K=nu_K)
+        ne_np1 = self.compute_electron_charge_density(f_new) if need_wave else None
+        a = self.wave_solver(a=y["a"], aold=y["prev_a"], djy_array=djy, electron_density_n=ne_n,
+                             electron_density_np1=ne_np1)
+        result = {"a": a["a"], "prev_a": a["prev_a"], "da": djy, "de": dex[self.vpfp.dex_save], "e": e}
+        result.update(f_new)
+        result.update(diags)
+        return result

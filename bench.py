@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- phase-space cell-updates/s of the full fp64 vlasov-1d step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--nx 4096] [--nv 4096]
+
+Workload (BASELINE.json configs[2], "C3"): one species, nx = nv = 4096, fp64, leapfrog + spectral x/v pushes +
+Poisson + Dougherty Fokker-Planck collisions, driven electron plasma wave (the configs/vlasov-1d/epw.yaml driver),
+synthetic Maxwellian + 1e-2 cos(k0 x) perturbation.  With N > 1 every rank advances its own independent grid of that
+size (ensemble members shard with no communication: weak scaling); value = total cells advanced / max-over-ranks time.
+
+One JSON line is printed by rank 0 (see the task contract): value (device-resident state), e2e (per-step host inputs
+copied from pinned memory + per-step diagnostic read-back), roofline of the dominant kernel, cpu_baseline (the numpy
+oracle timed on the host cores, rank 0 / N=1 only).  ``--impl reference`` times the oracle alone.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "phase-space cell-updates/s per fp64 vlasov-1d step"
+UNIT = "cell-updates/s"
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def c3_deck(nx: int, nv: int, steps_hint: int = 10000) -> dict:
+    """BASELINE.json configs[2] built from the stock epw.yaml physics (SURVEY.md 8d synthetic inputs)."""
+    env = lambda base: {"baseline": base, "bump_or_trough": "bump", "center": 0.0, "rise": 25.0, "slope": 0.0,  # noqa: E731
+                        "bump_height": 0.0, "width": 100000.0}
+    return {
+        "units": {"normalizing_temperature": "2000eV", "normalizing_density": "1.5e21/cc"},
+        "density": {"quasineutrality": True,
+                    "species-background": {"noise_seed": 420, "noise_type": "gaussian", "noise_val": 0.0, "v0": 0.0,
+                                           "T0": 1.0, "m": 2.0, "basis": "sine", "baseline": 1.0, "amplitude": 1.0e-2,
+                                           "wavenumber": 0.3}},
+        "grid": {"dt": 0.1, "nv": nv, "nx": nx, "tmin": 0.0, "tmax": 0.1 * steps_hint, "vmax": 6.4,
+                 "xmax": 2 * np.pi / 0.3, "xmin": 0.0},
+        "save": {}, "solver": "vlasov-1d", "mlflow": {"experiment": "bench", "run": "c3"},
+        "drivers": {"ex": {"0": {"params": {"a0": 1.0e-2, "k0": 0.3, "w0": 1.1598, "dw0": 0.0},
+                                 "envelope": {"time": {"center": 40.0, "rise": 5.0, "width": 30.0},
+                                              "space": {"center": 0.0, "rise": 10.0, "width": 4000000.0}}}},
+                    "ey": {}},
+        "diagnostics": {"diag-vlasov-dfdt": False, "diag-fp-dfdt": False},
+        "terms": {"field": "poisson", "edfdv": "exponential", "time": "leapfrog",
+                  "fokker_planck": {"is_on": True, "type": "Dougherty", "time": env(1.0e-5), "space": env(1.0)},
+                  "krook": {"is_on": False, "time": env(1.0), "space": env(1.0)}},
+    }
+
+
+def workload_name(nx, nv):
+    return (f"C3 vlasov-1d {nx}x{nv} fp64: leapfrog + spectral vdfdx/edfdv + Poisson + Dougherty FP, driven EPW "
+            "(BASELINE.json configs[2])")
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax = float(parts[1])
+            except ValueError:
+                continue
+            for n, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm (CPU oracle)
+def time_oracle(nx, nv, steps, warmup, workers):
+    from oracle import vlasov1d as O
+
+    O.FFT_WORKERS = workers
+    cfg = O.build_cfg(c3_deck(nx, nv))
+    vf = O.VlasovMaxwell(cfg)
+    y = O.init_state(cfg)
+    dt = cfg["grid"]["dt"]
+    t = 30.0  # driver on
+    for _ in range(warmup):
+        y = vf(t, y, None)
+        t += dt
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        y = vf(t, y, None)
+        t += dt
+    el = time.perf_counter() - t0
+    return nx * nv * steps / el, el / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    workers = os.cpu_count() or 1
+    # bounded sample: the full C3 grid for a few steps (each oracle step is seconds of CPU work)
+    steps = max(1, min(args.steps, 3))
+    warmup = 1
+    val, sec = time_oracle(args.nx, args.nv, steps, warmup, workers)
+    sample = (f"{steps} full steps of the {args.nx}x{args.nv} workload after {warmup} warm-up; numpy/scipy restatement "
+              f"of the reference (jax is not installable offline), scipy.fft workers={workers}, LAPACK dgtsv row loop")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.nx, args.nv), "nx": args.nx, "nv": args.nv},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from adept_b200 import ops
+    from adept_b200._lib import AdeptB200Error
+    from adept_b200.module import Vlasov1D
+
+    if not torch.cuda.is_available():
+        raise AdeptB200Error("bench.py: no CUDA device (the B200 arm has no CPU fallback)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    nx, nv, K, W = args.nx, args.nv, args.steps, args.warmup
+    cells = nx * nv
+    sim = Vlasov1D(c3_deck(nx, nv))
+    vf = sim.vector_field
+    dt = sim.grid.dt
+    t_start = 30.0  # inside the driver's flat top: every term of the step is active
+    sim.t, sim.step_index = t_start, int(round(t_start / dt))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        tns = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tns, op=dist.ReduceOp.MAX)
+        return float(tns.item())
+
+    # -- per-kernel CUDA-event instrumentation (same stream as the launches: torch's current stream) -------------
+    kernel_events = {}
+
+    def instrument(name):
+        fn = getattr(ops, name)
+
+        def wrapped(*a, **kw):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out = fn(*a, **kw)
+            e.record()
+            kernel_events.setdefault(name, []).append((s, e))
+            return out
+
+        return fn, wrapped
+
+    # ---- value: state and per-step inputs resident in HBM ------------------------------------------------------
+    for _ in range(W):
+        sim.step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    originals = {}
+    for name in ("vdfdx", "edfdv_exp", "edfdv_spline", "collide", "moments", "poisson", "ponderomotive"):
+        originals[name], wrapped = instrument(name)
+        setattr(ops, name, wrapped)
+    launches0 = ops.LAUNCHES
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(K):
+        sim.step()
+    ev1.record()
+    barrier()
+    elapsed = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)
+    launches = ops.LAUNCHES - launches0
+    for name, fn in originals.items():
+        setattr(ops, name, fn)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * cells * K / elapsed
+
+    per_kernel = {}
+    for name, evs in kernel_events.items():
+        ts = np.array([s.elapsed_time(e) * 1e-3 for s, e in evs])
+        per_kernel[name] = {"launches_per_step": len(evs) / K, "avg_us": float(ts.mean() * 1e6),
+                            "share_of_step": float(ts.sum() / (elapsed))}
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
+    else:
+        peak, peak_src = FALLBACK_HBM_GBS, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    full_pass = {k: v for k, v in per_kernel.items() if k in ("vdfdx", "edfdv_exp", "edfdv_spline", "collide")}
+    dom = max(full_pass, key=lambda k: full_pass[k]["share_of_step"])
+    alg_bytes = 16.0 * cells  # one fp64 read + one fp64 write of f per operator application
+    achieved = alg_bytes / (full_pass[dom]["avg_us"] * 1e-6) / 1e9
+    traffic_path = ROOT / "profiles" / "dram_traffic.json"
+    traffic = None
+    if traffic_path.exists():
+        traffic = json.loads(traffic_path.read_text()).get(dom)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "step_frac_of_48B_roofline": (48.0 * cells / (elapsed / K) / 1e9) / peak}
+
+    # ---- e2e: public API, per-step host inputs from pinned memory + per-step diagnostic read-back ----------------
+    hin = vf.host_inputs(sim.t)
+    pinned = {k: torch.empty(v.shape, dtype=torch.float64).pin_memory() for k, v in hin.items()}
+    devbuf = {k: torch.empty(v.shape, dtype=torch.float64, device="cuda") for k, v in hin.items()}
+    h2d_bytes = sum(v.numel() * 8 for v in pinned.values())
+    diag_dev = torch.empty(2, dtype=torch.float64, device="cuda")
+    diag_host = torch.empty(2, dtype=torch.float64).pin_memory()
+    d2h_bytes = diag_host.numel() * 8
+
+    def e2e_step():
+        h = vf.host_inputs(sim.t)  # O(nx) numpy on the host, like the reference's driver / profile evaluation
+        for k, v in h.items():
+            pinned[k].copy_(torch.from_numpy(np.ascontiguousarray(v)))
+            devbuf[k].copy_(pinned[k], non_blocking=True)
+        sim.state = vf(sim.t, sim.state, devbuf)
+        sim.step_index += 1
+        sim.t = sim.step_index * dt
+        diag_dev[0] = torch.mean(sim.state["e"] ** 2.0)  # mean_e2 (storage.py:316)
+        diag_dev[1] = torch.mean(sim.state["de"] ** 2.0)  # mean_de2
+        diag_host.copy_(diag_dev, non_blocking=False)  # the per-step read-back synchronises, as a real logger would
+        return float(diag_host[0])
+
+    for _ in range(max(W, 3)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_elapsed = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * cells * K / e2e_elapsed
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        workers = os.cpu_count() or 1
+        cval, csec = time_oracle(nx, nv, 2, 1, workers)
+        cpu_baseline = {"value": cval, "unit": UNIT, "cores": workers, "kind": "port",
+                        "sample": f"2 full {nx}x{nv} steps after 1 warm-up ({csec:.2f} s/step); numpy/scipy oracle, "
+                                  f"scipy.fft workers={workers}"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": elapsed / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(nx, nv), "nx": nx, "nv": nv, "members_per_gpu": 1,
+                   "parallelism": f"ensemble x{world} (independent grids, no collective)",
+                   "l2": f"working set {2 * cells * 8 / 2**20:.0f} MiB of f (in + out) per operator > 126 MB L2",
+                   "t_start": t_start},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": e2e_elapsed / K * 1e3,
+                "what": "Vlasov1D/VlasovMaxwell public call; per step: host evaluates driver + collision profiles, "
+                        "copies them from pinned memory, state f stays in HBM, mean_e2/mean_de2 read back"},
+        "roofline": roofline, "kernels": per_kernel, "gpu_launches": launches, "clocks": clocks,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--nx", type=int, default=4096)
+    ap.add_argument("--nv", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

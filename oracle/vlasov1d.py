@@ -266,11 +266,32 @@ def init_state(cfg: dict) -> dict:
 # Vlasov pushers  (adept/_vlasov1d/solvers/pushers/vlasov.py)
 # --------------------------------------------------------------------------------------
 
+# bench.py's reference arm sets this to the host core count: the batched 1-D transforms then run through
+# scipy.fft (pocketfft, ``workers=``); 1 keeps numpy's single-threaded pocketfft (used by every parity test).
+FFT_WORKERS = 1
+
+
+def _rfft(a, axis):
+    if FFT_WORKERS > 1:
+        import scipy.fft
+
+        return scipy.fft.rfft(a, axis=axis, workers=FFT_WORKERS)
+    return np.fft.rfft(a, axis=axis)
+
+
+def _irfft(a, axis):
+    if FFT_WORKERS > 1:
+        import scipy.fft
+
+        return scipy.fft.irfft(a, axis=axis, workers=FFT_WORKERS)
+    return np.fft.irfft(a, axis=axis)
+
+
 
 def space_exponential(f, kx_real, v, dt):
     """vlasov.py:234-251: irfft(exp(-i kx (v dt)) rfft(f, axis=0), axis=0)."""
     vdt = v * dt
-    return np.real(np.fft.irfft(np.exp(-1j * kx_real[:, None] * vdt[None, :]) * np.fft.rfft(f, axis=0), axis=0))
+    return np.real(_irfft(np.exp(-1j * kx_real[:, None] * vdt[None, :]) * _rfft(f, axis=0), axis=0))
 
 
 def accel_from_fields(e, pond, q, m):
@@ -283,7 +304,7 @@ def velocity_exponential(f, kv_real, e, pond, dt, q, m):
     """vlasov.py:74-91."""
     accel = accel_from_fields(e, pond, q, m)
     return np.real(
-        np.fft.irfft(np.exp(-1j * kv_real[None, :] * dt * accel[:, None]) * np.fft.rfft(f, axis=1), axis=1)
+        _irfft(np.exp(-1j * kv_real[None, :] * dt * accel[:, None]) * _rfft(f, axis=1), axis=1)
     )
 
 

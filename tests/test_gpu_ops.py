@@ -268,7 +268,12 @@ def test_collide_matches_oracle(ops, fp_type, nx, nv):
     dt = 0.1
     ref = coll(nu, None, f, dt)
     out = host(_gpu_collide(ops, coll, f, nu, None, dt))
-    assert rel_l2(out, ref) <= RTOL
+    # dougherty_nodrag subtracts dt*nu*lap(D f_M) explicitly (fokker_planck.py:414-427): a 1-ulp difference in
+    # exp() is amplified by dt*nu*D/dv^2 (1e4 at nv=4096), in the reference as much as here.
+    # More generally cond(I - dt nu L) ~ 1 + 4 dt nu D / dv^2 (2e4 at nv=6144, nu=1): LAPACK gtsv and the parallel
+    # solve both carry cond * eps of rounding error, so the comparison tolerance scales with it.
+    amp = dt * nu.max() / dv**2
+    assert rel_l2(out, ref) <= max(RTOL, 2e-16 * amp)
     # weakly collisional production regime
     nu2 = 1e-5 * np.ones(nx)
     ref = coll(nu2, None, f, dt)

@@ -1,0 +1,140 @@
+"""GPU parity of the full vlasov-1d step (VlasovMaxwell) against the numpy oracle, through the drop-in classes.
+
+Decks: BASELINE.json configs[0] (configs/vlasov-1d/epw.yaml: sixth + cubic-spline + Dougherty + dfdt diags, 32x256),
+configs[1] (EPW + collisions, 64x512, leapfrog + exponential), and the reference's test decks in tests/golden/.
+Bars: per-step relative L2 <= 1e-12 on every state entry; field-energy history to 1e-9 (relative to its peak).
+"""
+
+from copy import deepcopy
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+from oracle import vlasov1d as O
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    nb = np.linalg.norm(b.ravel())
+    return float(np.linalg.norm((a - b).ravel()) / nb) if nb > 0 else float(np.linalg.norm(a.ravel()))
+
+
+def load(name):
+    with open(GOLD / f"{name}.yaml") as fh:
+        return yaml.safe_load(fh)
+
+
+def c2_deck():
+    """configs[1]: EPW with Lenard-Bernstein/Dougherty collisions, nx=64, nv=512 (from the stock epw.yaml)."""
+    d = load("epw")
+    d["grid"].update(nx=64, nv=512)
+    d["terms"].update(time="leapfrog", edfdv="exponential")
+    d["terms"]["fokker_planck"]["time"]["baseline"] = 1.0e-3
+    d["diagnostics"] = {"diag-vlasov-dfdt": False, "diag-fp-dfdt": False}
+    return d
+
+
+def variants():
+    out = {"C1-epw": load("epw"), "C2-epw-fp": c2_deck()}
+    d = c2_deck()
+    d["terms"]["fokker_planck"]["type"] = "chang_cooper"
+    d["terms"]["krook"]["is_on"] = True
+    d["terms"]["krook"]["time"]["baseline"] = 1e-3
+    out["C2-cc-lb-krook"] = d
+    d = c2_deck()
+    d["terms"].update(field="ampere")
+    d["grid"]["dt"] = 0.025
+    out["C2-ampere"] = d
+    out["resonance"] = load("resonance")
+    out["fp-conservation"] = load("fokker_planck_conservation")
+    d = load("multispecies_ion_acoustic")
+    out["multispecies"] = d
+    d = c2_deck()  # driven transverse wave: wave solver + ponderomotive force on
+    d["drivers"]["ey"] = {"0": deepcopy(d["drivers"]["ex"]["0"])}
+    d["drivers"]["ey"]["0"]["params"].update(a0=1.0e-2, k0=1.0, w0=2.0)
+    d["drivers"]["ey"]["0"]["envelope"]["time"].update(center=1.0, width=2.0, rise=0.2)
+    out["C2-ey-wave"] = d
+    return out
+
+
+VARIANTS = variants()
+
+
+@pytest.mark.parametrize("name", list(VARIANTS))
+def test_step_by_step_parity(name):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from adept_b200.module import Vlasov1D
+
+    deck = VARIANTS[name]
+    sim = Vlasov1D(deck)
+    cfg = O.build_cfg(deck)
+    vf = O.VlasovMaxwell(cfg)
+    y = O.init_state(cfg)
+    dt = cfg["grid"]["dt"]
+    assert abs(dt - sim.grid.dt) == 0.0
+    nsteps = 12
+    # start the comparison where the driver is on so that every term is exercised
+    t0 = 30.0 if (cfg["drivers"].get("ex") and not cfg["drivers"].get("ey")) else 0.0
+    sim.t, sim.step_index = t0, int(round(t0 / dt))
+    g_ = cfg["grid"]
+    # E is the k-space integral of rho = sum_s q_s n_s + n_ion, a difference of O(1) moments: two correct
+    # implementations differ by a few eps * |q n| / k_min in E whatever its size, so E gets an absolute floor.
+    rho_scale = sum(abs(g_["species_params"][s]["charge"]) * np.max(np.abs(d[0]))
+                    for s, d in g_["species_distributions"].items())
+    k1 = 2 * np.pi / (g_["xmax"] - g_["xmin"])
+    e_floor = 50 * np.finfo(float).eps * rho_scale * max(1.0, 1.0 / k1)
+    worst, worst_abs = {}, {}
+    for n in range(nsteps):
+        t = t0 + n * dt
+        # per-step parity: both sides start each step from the oracle's state
+        sim.state = {k: torch.as_tensor(v, device="cuda").contiguous() for k, v in y.items()}
+        y_gpu = sim.vector_field(t, sim.state, None)
+        y = vf(t, y, None)
+        assert set(y_gpu) == set(y)
+        for k in y:
+            g = y_gpu[k].cpu().numpy()
+            assert g.shape == y[k].shape, k
+            if k.startswith("diag-"):
+                # (f1 - f0)/dt amplifies rounding of f by 1/dt: compare against the scale of f/dt
+                err = np.linalg.norm(g - y[k]) / (np.linalg.norm(y["electron"]) / dt)
+            elif k == "e":
+                err = max(0.0, np.max(np.abs(g - y[k])) - e_floor) / max(np.max(np.abs(y[k])), 1e-300)
+            else:
+                err = rel_l2(g, y[k])
+            worst[k] = max(worst.get(k, 0.0), err)
+    for k, err in worst.items():
+        assert err <= 1e-12, (name, k, err)
+    if name == "C2-ey-wave":
+        assert np.max(np.abs(y["a"])) > 0 and np.max(np.abs(y["e"])) > 0  # the wave + ponderomotive path really ran
+
+
+@pytest.mark.parametrize("name", ["C2-epw-fp", "C1-epw"])
+def test_free_running_energy_history(name):
+    """Run both sides freely (no re-synchronisation) and compare the field-energy history (diagnostic parity)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from adept_b200.module import Vlasov1D, default_scalars
+
+    deck = deepcopy(VARIANTS[name])
+    deck["grid"]["tmax"] = 60.0
+    sim = Vlasov1D(deck)
+    cfg = O.build_cfg(deck)
+    nsteps = 500
+    ts = cfg["grid"]["dt"] * np.arange(1, nsteps + 1)
+    _, ref = O.run(cfg, nsteps=nsteps, save={"s": (ts, O.default_scalars)})
+    _, got = sim.run(nsteps=nsteps, save={"s": (ts, default_scalars)})
+    for key in ["mean_e2", "mean_field_energy", "mean_kinetic_energy", "mean_total_energy", "mean_n_electron",
+                "mean_P_electron", "mean_f2_electron", "mean_-flogf_electron"]:
+        r = np.array([s[key] for s in ref["s"]])
+        g = np.array([float(s[key]) for s in got["s"]])
+        assert len(r) == len(g) == nsteps
+        np.testing.assert_allclose(g, r, rtol=1e-9, atol=1e-9 * np.max(np.abs(r)), err_msg=key)
+    f_ref = O.run(cfg, nsteps=0)[0]  # shapes only
+    assert sim.state["electron"].shape == f_ref["electron"].shape

@@ -1,0 +1,60 @@
+"""Per-kernel micro-benchmark at the C3 size (development aid, not the bench contract).
+
+    python tools/kbench.py [nx nv [iters]]
+"""
+import sys
+
+import numpy as np
+import torch
+
+from adept_b200 import ops
+
+nx = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+nv = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+iters = int(sys.argv[3]) if len(sys.argv) > 3 else 20
+PEAK = 6544.0
+
+vmax = 6.4
+dv = 2 * vmax / nv
+v = np.linspace(-vmax + dv / 2, vmax - dv / 2, nv)
+xmax = 20.94
+dx = xmax / nx
+x = np.linspace(dx / 2, xmax - dx / 2, nx)
+f = (1 + 0.01 * np.cos(0.3 * x))[:, None] * np.exp(-v**2 / 2)[None, :] / (np.sum(np.exp(-v**2 / 2)) * dv)
+fd = torch.as_tensor(f, device="cuda")
+gd = torch.empty_like(fd)
+vd = torch.as_tensor(v, device="cuda")
+e = torch.as_tensor(1e-2 * np.sin(0.3 * x), device="cuda")
+nu = torch.full((nx,), 1e-5, dtype=torch.float64, device="cuda")
+rho = torch.empty(nx, dtype=torch.float64, device="cuda")
+k1x, k1v = 2 * np.pi / xmax, 2 * np.pi / (nv * dv)
+flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+
+
+def timeit(name, fn, bytes_per_cell=16.0):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        t.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(t) * 1e-3)
+    ts = np.array(ts)
+    gbs = nx * nv * bytes_per_cell / ts / 1e9
+    print(f"{name:14s} median {np.median(ts)*1e6:8.1f} us  best {ts.min()*1e6:8.1f} us   "
+          f"{np.median(gbs):7.0f} GB/s  = {np.median(gbs)/PEAK*100:5.1f}% of measured HBM peak")
+
+
+timeit("copy(torch)", lambda: gd.copy_(fd))
+timeit("vdfdx", lambda: ops.vdfdx(fd, vd, 0.1, k1x, out=gd))
+timeit("edfdv_exp", lambda: ops.edfdv_exp(fd, e, None, -1.0, 1.0, 0.1, k1v, out=gd))
+timeit("edfdv_spline", lambda: ops.edfdv_spline(fd, e, None, -1.0, 1.0, 0.1, dv, out=gd))
+timeit("moments(n)", lambda: ops.moments(fd, vd, dv, (rho, None, None)), 8.0)
+timeit("collide_dough", lambda: ops.collide(fd, vd, dv, 0.1, nu_fp=nu, model=1, scheme=0, out=gd))
+timeit("collide_cc", lambda: ops.collide(fd, vd, dv, 0.1, nu_fp=nu, model=1, scheme=1, out=gd))
+timeit("poisson", lambda: ops.poisson(rho, rho), 0.0)
