@@ -18,7 +18,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -65,46 +64,48 @@ def workload_name(nx, nv):
 
 # ------------------------------------------------------------------------------------------------ clocks sampler
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons through NVML (nvidia-ml-py) every 50 ms on a host thread while the timed
+    region runs (nvidia-smi -lms block-buffers its pipe, so short runs would see no samples)."""
+
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
 
     def __init__(self, index: int):
-        self.index, self.samples, self.proc = index, [], None
+        self.index, self.sm, self.mask, self.smax = index, [], 0, None
+        self._stop = threading.Event()
+        self._thread = None
+        self.err = None
+
+    def _run(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            while not self._stop.is_set():
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                try:
+                    self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:  # older bindings
+                    self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self._stop.wait(0.05)
+        except Exception as exc:  # no NVML: report it, never fail the bench
+            self.err = repr(exc)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append(line.strip())
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, smax, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            parts = [p.strip() for p in s.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                smax = float(parts[1])
-            except ValueError:
-                continue
-            for n, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2.0)
+        if self.err or not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.smax, "reasons": [f"nvml unavailable: {self.err}"], "samples": 0}
+        reasons = [n for n, bit in self.REASONS if self.mask & bit]
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.smax, "reasons": reasons,
+                "samples": len(self.sm)}
 
 
 # ------------------------------------------------------------------------------------------------ reference arm (CPU oracle)
