@@ -10,10 +10,18 @@
 //   chang_cooper_delta                                     adept/driftdiffusion.py:77-103
 //   Krook                                                  fokker_planck.py:446-484
 //
-// Parallel solve: T = nv/E threads per x-row, each owning E contiguous velocity cells in registers.  Every
-// thread eliminates its chunk (modified Thomas with a left "spike"), the T chunk-last unknowns form a reduced
-// tridiagonal system solved with parallel cyclic reduction in shared memory, then chunks back-substitute.
-// The matrix is strictly diagonally dominant (I - dt nu L, zero-flux L), so no pivoting is needed; the reference's
+// Formulation.  With U_e = dt nu bare_upper_e and L_e = dt nu bare_lower_e on edge e (between cells e and e+1) the
+// operator A = I - dt nu L of both differencing schemes has  a_i = -L_{i-1},  c_i = -U_i,  b_i = 1 + L_i + U_{i-1}
+// (zero column sums = zero-flux boundaries), and the delta-form right-hand side  f - A f  is the flux difference
+// G_i - G_{i-1},  G_e = U_e f_{e+1} - L_e f_e.  For central differencing U_e, L_e are LINEAR in the edge index
+// (C_e = 2 beta D (v_e - vbar)), so the fast path needs no division and no table per cell.
+//
+// Parallel solve: T = nv/E threads per x-row, each owning E contiguous velocity cells.  A thread eliminates its chunk
+// downwards carrying the "spike" towards the previous chunk's last unknown (rows normalised to unit diagonal with a
+// MUFU.RCP64H + 2 Newton steps reciprocal), an upward sweep expresses the chunk's first unknown through the two
+// neighbouring chunk-last unknowns, the T chunk-last unknowns form a reduced tridiagonal system solved with parallel
+// cyclic reduction in shared memory (unit-diagonal form: one reciprocal per step), then chunks back-substitute
+// directly for f + delta.  The matrix is strictly diagonally dominant, so no pivoting is needed; the reference's
 // LAPACK gtsv agrees to rounding.
 #include "common.cuh"
 
@@ -35,310 +43,379 @@ struct CollideArgs {
   int model, scheme, nodrag;
   double sg_m, sg_ratio;  // super-Gaussian exponent m and Gamma(3/m)/Gamma(1/m)
   double* n_out;          // [rows] or null: sum_j f_out dv
+  int rows_per_cta;       // R: x-rows handled by one CTA (set by the launcher)
 };
+
+// 1/x for |x| in the normal range: MUFU.RCP64H seed (about 20 bits) + two Newton steps -> rounding-level accuracy.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
 
 __device__ __forceinline__ double cc_delta(double w) {  // driftdiffusion.py:96-103
   if (fabs(w) < 1.0e-8) return 0.5 - w / 12.0 + w * w * w / 720.0;
   return 1.0 / w - 1.0 / expm1(w);
 }
 
-struct Edge {
-  double bu, bl, X, Y;  // bare upper / lower entries of this edge; its contributions to bd_i and bd_{i+1}
-};
-
-__device__ __forceinline__ Edge make_edge(double C, double D, double dv, int scheme) {
-  Edge g;
+// bare upper / lower entries of one edge, reference formulas (generic path)
+__device__ __forceinline__ void bare_edge(double C, double D, double dv, int scheme, double& bu, double& bl) {
   if (scheme == FP_CENTRAL) {  // driftdiffusion.py:585-590
-    g.X = (C / 2.0 - D / dv) / dv;
-    g.Y = -(C / 2.0 + D / dv) / dv;
-    g.bu = (C / 2.0 + D / dv) / dv;
-    g.bl = (-C / 2.0 + D / dv) / dv;
+    bu = (C / 2.0 + D / dv) / dv;
+    bl = (-C / 2.0 + D / dv) / dv;
   } else {  // driftdiffusion.py:637-648
     const double sD = fmax(D, 1.0e-30);
     const double w = C * dv / sD;
     const double dl = cc_delta(w);
     const double alpha = -C * dl + sD / dv;
     const double beta = -C * (1.0 - dl) - sD / dv;
-    g.X = -alpha / dv;
-    g.Y = beta / dv;
-    g.bu = -beta / dv;
-    g.bl = alpha / dv;
+    bu = -beta / dv;
+    bl = alpha / dv;
   }
-  return g;
 }
 
-// Sum two values over the T threads of a row; every thread of the CTA must call it.
-//   mode 0: T % 32 == 0 (warps do not straddle rows); mode 1: T < 32, power of two; mode 2: generic tree.
-__device__ __forceinline__ void row_sum2(double& a, double& b, double* red, double* tree, int& parity, int r, int t,
-                                         int T, int mode, unsigned amask) {
-  if (mode == 1) {
-    for (int o = T >> 1; o > 0; o >>= 1) {
-      a += __shfl_xor_sync(amask, a, o);
-      b += __shfl_xor_sync(amask, b, o);
-    }
-    return;
-  }
-  if (mode == 0) {
-    a = warp_sum(a);
-    b = warp_sum(b);
+// Sum NVAL values over the T threads of row r; every thread of the CTA must call it.  warp_mode: T % 32 == 0 (warps do
+// not straddle rows).  `red` is a scratch area of 2 * max(R*T, 32) * NVAL doubles used with alternating halves.
+template <int NVAL>
+__device__ __forceinline__ void row_reduce(double (&val)[NVAL], double* red, int& parity, int r, int t, int T, int RT,
+                                           bool warp_mode, bool live) {
+  double* base = red + (size_t)parity * (RT > 32 ? RT : 32) * NVAL;
+  parity ^= 1;
+  if (warp_mode) {
+#pragma unroll
+    for (int i = 0; i < NVAL; i++) val[i] = warp_sum(val[i]);
     const int nw = T >> 5, w = t >> 5;
-    double* slot = red + parity * 64 + r * nw * 2;  // R*T <= 1024 -> at most 32 warps per CTA
+    double* slot = base + (size_t)r * nw * NVAL;
     if ((t & 31) == 0) {
-      slot[2 * w] = a;
-      slot[2 * w + 1] = b;
+#pragma unroll
+      for (int i = 0; i < NVAL; i++) slot[w * NVAL + i] = val[i];
     }
     __syncthreads();
-    a = 0.0;
-    b = 0.0;
-    for (int i = 0; i < nw; i++) {
-      a += slot[2 * i];
-      b += slot[2 * i + 1];
+#pragma unroll
+    for (int i = 0; i < NVAL; i++) val[i] = 0.0;
+    for (int j = 0; j < nw; j++) {
+#pragma unroll
+      for (int i = 0; i < NVAL; i++) val[i] += slot[j * NVAL + i];
     }
-    parity ^= 1;
-    return;
-  }
-  double* ta = tree + (size_t)r * T * 2;
-  __syncthreads();
-  ta[2 * t] = a;
-  ta[2 * t + 1] = b;
-  __syncthreads();
-  int s = 1;
-  while (s < T) s <<= 1;
-  for (s >>= 1; s > 0; s >>= 1) {
-    if (t < s && t + s < T) {
-      ta[2 * t] += ta[2 * (t + s)];
-      ta[2 * t + 1] += ta[2 * (t + s) + 1];
+  } else {
+    double* slot = base + (size_t)r * T * NVAL;
+    if (live) {
+#pragma unroll
+      for (int i = 0; i < NVAL; i++) slot[t * NVAL + i] = val[i];
     }
     __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NVAL; i++) val[i] = 0.0;
+    for (int j = 0; j < T; j++) {
+#pragma unroll
+      for (int i = 0; i < NVAL; i++) val[i] += slot[j * NVAL + i];
+    }
   }
-  a = ta[0];
-  b = ta[1];
 }
 
-template <int E, int MAXT>
-__global__ void __launch_bounds__(MAXT) collide_kernel(CollideArgs p) {
+template <int E>
+struct CollideSmem {
+  // doubles per CTA for R rows of nv cells handled by RT = R*T threads
+  static __host__ __device__ size_t doubles(int R, int nv, int RT) {
+    const int red = 2 * (RT > 32 ? RT : 32) * 3;
+    return (size_t)R * (nv + nv / E) + (size_t)R * nv + red + 6 * (size_t)RT;
+  }
+};
+
+// FAST: central differencing, LB / Dougherty, no `nodrag` -- the production path.
+template <int E, int MAXT, int MINB, bool FAST>
+__global__ void __launch_bounds__(MAXT, MINB) collide_kernel(CollideArgs p) {
   extern __shared__ __align__(16) double sm[];
   const int nv = p.nv;
   const int T = nv / E;
-  const int R = blockDim.x / T;
-  const int r = threadIdx.x / T, t = threadIdx.x % T;
-  const int nvp = nv + nv / E;
-  double* rowbuf = sm + (size_t)r * nvp;
-  double* red = sm + (size_t)R * nvp;  // 2 parities * 32 warps * 2 values
-  double* pcr = red + 128;              // 2 buffers * 4 arrays * R*T doubles
-  const unsigned amask = __activemask();
+  const int R = p.rows_per_cta;
   const int RT = R * T;
-  const int mode = (T % 32 == 0) ? 0 : ((T < 32 && (T & (T - 1)) == 0) ? 1 : 2);
+  const int nvp = nv + T;  // one pad double per chunk: chunk stride E+1 (odd) -> conflict-free 8-byte accesses
+  const int r = threadIdx.x / T, t = threadIdx.x - r * T;
+  const bool live = r < R;  // blockDim.x may exceed R*T when T does not divide it; spare threads only hit barriers
+  double* rowbuf = sm + (size_t)(live ? r : 0) * nvp;
+  double* apbuf = sm + (size_t)R * nvp + (size_t)(live ? r : 0) * nv;  // [E][T]: spike of the downward sweep
+  double* red = sm + (size_t)R * nvp + (size_t)R * nv;
+  double* pcr = red + 2 * (RT > 32 ? RT : 32) * 3;  // 2 buffers x 3 arrays x RT
+  const bool warp_mode = (T & 31) == 0;
   int parity = 0;
 
   const long long row_raw = (long long)blockIdx.x * R + r;
-  const bool active = row_raw < p.rows;
+  const bool active = live && row_raw < p.rows;
   const long long row = active ? row_raw : p.rows - 1;
-  const double* fin = p.fin + row * nv;
-
-  // ---- 1. row -> shared (coalesced), chunk -> registers ---------------------------------------------------
-  for (int i = t; i < nv; i += T) rowbuf[i + i / E] = fin[i];
-  __syncthreads();
-  const int i0 = E * t;
-  double f[E], vv[E];
-#pragma unroll
-  for (int l = 0; l < E; l++) {
-    f[l] = rowbuf[i0 + l + t];
-    vv[l] = __ldg(p.v + i0 + l);
-  }
-  const double f_left = t > 0 ? rowbuf[i0 - 1 + (t - 1)] : 0.0;
-  const double f_right = t < T - 1 ? rowbuf[i0 + E + (t + 1)] : 0.0;
-  const double v_left = t > 0 ? __ldg(p.v + i0 - 1) : 0.0;
-  const double v_right = t < T - 1 ? __ldg(p.v + i0 + E) : 0.0;
+  const int tt = live ? t : 0;
+  const int me = (live ? r : 0) * T + tt;
   const double dv = p.dv, dt = p.dt;
 
-  double fo[E];  // result of the Fokker-Planck stage
+  // ---- 1. row -> shared (coalesced 16-byte loads when aligned) ---------------------------------------------------
+  {
+    const double* fin = p.fin + row * nv;
+    if (live) {
+      if ((nv & 1) == 0 && ((reinterpret_cast<uintptr_t>(fin) & 15) == 0)) {
+        const double2* f2 = reinterpret_cast<const double2*>(fin);
+        for (int i = t; i < (nv >> 1); i += T) {
+          const double2 x = f2[i];
+          const int j = 2 * i;
+          rowbuf[j + j / E] = x.x;
+          rowbuf[j + 1 + (j + 1) / E] = x.y;
+        }
+      } else {
+        for (int i = t; i < nv; i += T) rowbuf[i + i / E] = fin[i];
+      }
+    }
+  }
+  __syncthreads();
+  const int i0 = E * tt;
+  const double* chunk = rowbuf + i0 + tt;  // chunk[l] = f[i0 + l]
+  const double vc = __ldg(p.v + i0);        // v of the chunk's first cell; v[i0 + l] = vc + l dv (uniform grid)
+
   if (p.nu_fp) {
     const double nu = p.nu_fp[row];
-    // ---- 2. moments: vbar, T (or the super-Gaussian beta closure) -----------------------------------------
-    double s0 = 0.0, s1 = 0.0;
+    // ---- 2. moments in chunk-local index space: sum f, sum f l, sum f l^2 ------------------------------------------
+    double mom[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int l = 0; l < E; l++) {
-      s0 += f[l];
-      s1 += f[l] * vv[l];
+      const double fl = chunk[l];
+      mom[0] += fl;
+      mom[1] = fma(fl, (double)l, mom[1]);
+      mom[2] = fma(fl, (double)(l * l), mom[2]);
     }
-    row_sum2(s0, s1, red, pcr, parity, r, t, T, mode, amask);
+    if (FAST) {
+      // sum f v = vc m0 + dv m1 ; sum f v^2 = vc^2 m0 + 2 vc dv m1 + dv^2 m2
+      const double m0 = mom[0], m1 = mom[1] * dv, m2 = mom[2] * (dv * dv);
+      mom[1] = fma(vc, m0, m1);
+      mom[2] = fma(vc * vc, m0, fma(2.0 * vc, m1, m2));
+    } else {  // generic path: the reference's own summation (fokker_planck.py:88, driftdiffusion.py:125-137)
+      mom[1] = 0.0;
+#pragma unroll
+      for (int l = 0; l < E; l++) mom[1] += chunk[l] * __ldg(p.v + i0 + l);
+    }
+    if (!live) mom[0] = mom[1] = mom[2] = 0.0;
+    row_reduce<3>(mom, red, parity, live ? r : 0, tt, T, RT, warp_mode, live);
+    const double s0 = mom[0], s1 = mom[1], s2 = mom[2];
     const double vbar = (p.model == FP_LB) ? 0.0 : s1 / s0;
     double beta, D;
-    if (p.model == FP_SUPERGAUSSIAN) {
-      double sp = 0.0, dummy = 0.0;
+    if (!FAST && p.model == FP_SUPERGAUSSIAN) {
+      double sp[1] = {0.0};
 #pragma unroll
-      for (int l = 0; l < E; l++) sp += f[l] * pow(fabs(vv[l] - vbar), p.sg_m);
-      row_sum2(sp, dummy, red, pcr, parity, r, t, T, mode, amask);
-      beta = s0 / (p.sg_m * sp);
+      for (int l = 0; l < E; l++) sp[0] += chunk[l] * pow(fabs(__ldg(p.v + i0 + l) - vbar), p.sg_m);
+      if (!live) sp[0] = 0.0;
+      row_reduce<1>(sp, red, parity, live ? r : 0, tt, T, RT, warp_mode, live);
+      beta = s0 / (p.sg_m * sp[0]);
       D = pow(beta, -2.0 / p.sg_m) * p.sg_ratio;
     } else {
-      double v2 = 0.0, nrm = 0.0;
+      double Temp;
+      if (FAST) {
+        // T = sum f (v - vbar)^2 / sum f  (driftdiffusion.py:125-137; dv cancels)
+        Temp = (s2 - 2.0 * vbar * s1 + vbar * vbar * s0) / s0;
+      } else {
+        double tm[2] = {0.0, 0.0};
 #pragma unroll
-      for (int l = 0; l < E; l++) {
-        const double vs = vv[l] - vbar;
-        v2 += f[l] * (vs * vs) * dv;
-        nrm += f[l] * dv;
+        for (int l = 0; l < E; l++) {
+          const double vs = __ldg(p.v + i0 + l) - vbar;
+          tm[0] += chunk[l] * (vs * vs) * dv;
+          tm[1] += chunk[l] * dv;
+        }
+        if (!live) tm[0] = tm[1] = 0.0;
+        row_reduce<2>(tm, red, parity, live ? r : 0, tt, T, RT, warp_mode, live);
+        Temp = tm[0] / tm[1];
       }
-      row_sum2(v2, nrm, red, pcr, parity, r, t, T, mode, amask);
-      const double Temp = v2 / nrm;
       beta = 1.0 / (2.0 * Temp);
       D = 1.0 / (2.0 * beta);
     }
+    const double dtnu = dt * nu;
 
-    // ---- 3. edges i0-1 .. i0+E-1 and the tridiagonal rows of this chunk ------------------------------------
-    const double c2 = 2.0 * beta * D;
-    const double mdtnu = -dt * nu, dtnu = dt * nu;
-    double a[E], bdiag[E], c[E], rhs[E];
-    {
-      Edge prev;  // edge (i0 - 1), between cells i0-1 and i0
-      prev.bu = prev.bl = prev.X = prev.Y = 0.0;
-      if (t > 0) {
+    // ---- 3. edge coefficients U_l, L_l of edge (i0 + l) for l = -1 .. E-1 ------------------------------------------
+    // FAST: U = pD + q (v_e - vbar), L = pD - q (v_e - vbar), v_e = vc + (l + 1/2) dv
+    const double pD = dtnu * D / (dv * dv);
+    const double q = dtnu * (2.0 * beta * D) / (2.0 * dv);
+    const double w0 = q * (vc + 0.5 * dv - vbar), dq = q * dv;
+    auto edge = [&](int l, double& U, double& L) {
+      const int e = i0 + l;  // global edge index, valid for 0 <= e <= nv-2
+      if (e < 0 || e > nv - 2) {
+        U = 0.0;
+        L = 0.0;
+        return;
+      }
+      if (FAST) {
+        const double wq = fma((double)l, dq, w0);
+        U = pD + wq;
+        L = pD - wq;
+      } else {
         double C;
+        const double va = __ldg(p.v + e), vb = __ldg(p.v + e + 1);
         if (p.nodrag) {
           C = 0.0;
         } else if (p.model == FP_SUPERGAUSSIAN) {
-          const double ph0 = beta * pow(fabs(v_left - vbar), p.sg_m), ph1 = beta * pow(fabs(vv[0] - vbar), p.sg_m);
+          const double ph0 = beta * pow(fabs(va - vbar), p.sg_m), ph1 = beta * pow(fabs(vb - vbar), p.sg_m);
           C = D * (ph1 - ph0) / dv;
         } else {
-          C = c2 * (0.5 * (vv[0] + v_left) - vbar);
+          C = (2.0 * beta * D) * (0.5 * (vb + va) - vbar);
         }
-        prev = make_edge(C, D, dv, p.scheme);
+        double bu, bl;
+        bare_edge(C, D, dv, p.scheme, bu, bl);
+        U = dtnu * bu;
+        L = dtnu * bl;
       }
+    };
+
+    // ---- 4. downward elimination, rows normalised to unit diagonal ---------------------------------------------------
+    //   apn_l s_left + x_l + cpn_l x_{l+1} = rpn_l ;  y-form for f + x:  ypn_l = f_l + rpn_l + cpn_l f_{l+1}
+    double cpn[E], ypn[E];
+    double rpn_last, apn_last;
+    {
+      double Um, Lm;  // edge l-1
+      edge(-1, Um, Lm);
+      double f_m = (tt > 0) ? rowbuf[i0 - 1 + (tt - 1)] : 0.0;
+      double f_c = chunk[0];
+      double G_m = Um * f_c - Lm * f_m;  // flux through edge l-1
+      double cp_prev = 0.0, ap_prev = 0.0, rp_prev = 0.0;
 #pragma unroll
       for (int l = 0; l < E; l++) {
-        const int i = i0 + l;
-        const bool has_lo = i >= 1, has_up = i <= nv - 2;
-        Edge cur;
-        cur.bu = cur.bl = cur.X = cur.Y = 0.0;
-        if (has_up) {
-          const double vn = (l < E - 1) ? vv[l < E - 1 ? l + 1 : l] : v_right;
-          double C;
-          if (p.nodrag) {
-            C = 0.0;
-          } else if (p.model == FP_SUPERGAUSSIAN) {
-            const double ph0 = beta * pow(fabs(vv[l] - vbar), p.sg_m), ph1 = beta * pow(fabs(vn - vbar), p.sg_m);
-            C = D * (ph1 - ph0) / dv;
-          } else {
-            C = c2 * (0.5 * (vn + vv[l]) - vbar);
-          }
-          cur = make_edge(C, D, dv, p.scheme);
+        double Uc, Lc;
+        edge(l, Uc, Lc);
+        const double f_p = (l < E - 1) ? chunk[l + 1] : ((tt < T - 1) ? rowbuf[i0 + E + (tt + 1)] : 0.0);
+        const double G_c = Uc * f_p - Lc * f_c;
+        const double rhs = G_c - G_m;
+        const double a = -Lm;
+        const double b = (1.0 + Lc) + Um;
+        double bp, apv, rpv;
+        if (l == 0) {
+          bp = b;
+          apv = a;
+          rpv = rhs;
+        } else {
+          bp = fma(-a, cp_prev, b);
+          apv = -a * ap_prev;
+          rpv = fma(-a, rp_prev, rhs);
         }
-        a[l] = has_lo ? mdtnu * prev.bl : 0.0;
-        c[l] = has_up ? mdtnu * cur.bu : 0.0;
-        const double bd = (has_up ? cur.X : 0.0) + (has_lo ? prev.Y : 0.0);
-        bdiag[l] = 1.0 - dtnu * bd;
-        const double fl = (l == 0) ? f_left : f[l > 0 ? l - 1 : 0];
-        const double fr = (l == E - 1) ? f_right : f[l < E - 1 ? l + 1 : l];
-        rhs[l] = f[l] - ((bdiag[l] * f[l] + c[l] * fr) + a[l] * fl);  // delta form: fokker_planck.py:374
-        prev = cur;
+        const double inv = fast_rcp(bp);
+        const double cp = -Uc * inv, ap = apv * inv, rp = rpv * inv;
+        cpn[l] = cp;
+        if (live) apbuf[l * T + tt] = ap;
+        ypn[l] = (l < E - 1) ? fma(cp, f_p, f_c + rp) : f_c;  // the last row is solved by the reduced system
+        if (l == E - 1) {
+          rpn_last = rp;
+          apn_last = ap;
+        }
+        cp_prev = cp, ap_prev = ap, rp_prev = rp;
+        Um = Uc, Lm = Lc, G_m = G_c, f_m = f_c, f_c = f_p;
       }
     }
 
-    // ---- 4. chunk elimination (spike toward the previous chunk's last unknown) -------------------------------
-    double inv[E], ap[E], rp[E];
-    inv[0] = 1.0 / bdiag[0];
-    ap[0] = a[0];
-    rp[0] = rhs[0];
-    double bp_last = bdiag[0];
+    // ---- 5. upward sweep: x_first = R0 - A0 s_left - C0 s_me --------------------------------------------------------
+    double A0 = 0.0, C0 = 0.0, R0 = 0.0;
+    if (E >= 2) {
+      double RY = ypn[E - 2], A = apbuf[(E - 2) * T + tt], Cc = cpn[E - 2];
 #pragma unroll
-    for (int l = 1; l < E; l++) {
-      const double m = a[l] * inv[l - 1];
-      bp_last = bdiag[l] - m * c[l - 1];
-      ap[l] = -m * ap[l - 1];
-      rp[l] = rhs[l] - m * rp[l - 1];
-      inv[l] = 1.0 / bp_last;
+      for (int l = E - 3; l >= 0; l--) {
+        const double cp = cpn[l];
+        RY = fma(-cp, RY, ypn[l]);
+        A = fma(-cp, A, apbuf[l * T + tt]);
+        Cc = -cp * Cc;
+      }
+      A0 = A, C0 = Cc;
+      R0 = RY - chunk[0] - Cc * chunk[E - 1];  // back from y-form: y = f + x
     }
-    double A0 = ap[E - 2], C0 = c[E - 2], R0 = rp[E - 2];
-#pragma unroll
-    for (int l = E - 3; l >= 0; l--) {
-      const double m = c[l] * inv[l + 1];
-      A0 = ap[l] - m * A0;
-      C0 = -m * C0;
-      R0 = rp[l] - m * R0;
+    double* xb = pcr + 3 * RT;  // second PCR buffer doubles as the exchange area
+    if (live) {
+      xb[me] = A0;
+      xb[RT + me] = C0;
+      xb[2 * RT + me] = R0;
     }
-    // publish (A0, C0, R0, inv0) for the chunk on the left
-    double* xb = pcr + 4 * RT;  // buffer 1 doubles as the exchange area
-    const int me = r * T + t;
-    __syncthreads();  // (mode 2 reductions used pcr as tree scratch)
-    xb[me] = A0;
-    xb[RT + me] = C0;
-    xb[2 * RT + me] = R0;
-    xb[3 * RT + me] = inv[0];
     __syncthreads();
-    double al = ap[E - 1], be = bp_last, ga = 0.0, rh = rp[E - 1];
-    if (t < T - 1) {
-      const double k = c[E - 1] * xb[3 * RT + me + 1];
-      be = bp_last - k * xb[me + 1];
-      ga = -k * xb[RT + me + 1];
-      rh = rp[E - 1] - k * xb[2 * RT + me + 1];
+    // reduced row of this chunk's last unknown: al s_{t-1} + s_t + ga s_{t+1} = rh
+    double al, ga, rh;
+    {
+      double be = 1.0;
+      al = apn_last, ga = 0.0, rh = rpn_last;
+      if (E >= 2 && tt < T - 1) {
+        const double k = cpn[E - 1];
+        be = fma(-k, xb[me + 1], 1.0);
+        ga = -k * xb[RT + me + 1];
+        rh = fma(-k, xb[2 * RT + me + 1], rpn_last);
+      } else if (E == 1 && tt < T - 1) {
+        ga = cpn[0];
+      }
+      const double ib = fast_rcp(be);
+      al *= ib, ga *= ib, rh *= ib;
     }
-    // ---- 5. parallel cyclic reduction on the T chunk-last unknowns ------------------------------------------
+    // ---- 6. parallel cyclic reduction (unit diagonal) on the T chunk-last unknowns ----------------------------------
     double* cur = pcr;
-    double* nxt = pcr + 4 * RT;
-    cur[me] = al;
-    cur[RT + me] = be;
-    cur[2 * RT + me] = ga;
-    cur[3 * RT + me] = rh;
+    double* nxt = pcr + 3 * RT;
+    __syncthreads();  // exchange area (= nxt) fully consumed
+    if (live) {
+      cur[me] = al;
+      cur[RT + me] = ga;
+      cur[2 * RT + me] = rh;
+    }
     __syncthreads();
     for (int s = 1; s < T; s <<= 1) {
-      double al2 = 0.0, ga2 = 0.0, be2 = be, rh2 = rh;
-      if (t - s >= 0) {
-        const int j = me - s;
-        const double k1 = al / cur[RT + j];
-        al2 = -k1 * cur[j];
-        be2 -= k1 * cur[2 * RT + j];
-        rh2 -= k1 * cur[3 * RT + j];
+      double alj = 0.0, gaj = 0.0, rhj = 0.0, alk = 0.0, gak = 0.0, rhk = 0.0;
+      if (tt - s >= 0) {
+        alj = cur[me - s];
+        gaj = cur[RT + me - s];
+        rhj = cur[2 * RT + me - s];
       }
-      if (t + s < T) {
-        const int j = me + s;
-        const double k2 = ga / cur[RT + j];
-        ga2 = -k2 * cur[2 * RT + j];
-        be2 -= k2 * cur[j];
-        rh2 -= k2 * cur[3 * RT + j];
+      if (tt + s < T) {
+        alk = cur[me + s];
+        gak = cur[RT + me + s];
+        rhk = cur[2 * RT + me + s];
       }
-      al = al2, be = be2, ga = ga2, rh = rh2;
-      nxt[me] = al;
-      nxt[RT + me] = be;
-      nxt[2 * RT + me] = ga;
-      nxt[3 * RT + me] = rh;
+      const double be = fma(-al, gaj, fma(-ga, alk, 1.0));
+      const double ib = fast_rcp(be);
+      rh = fma(-al, rhj, fma(-ga, rhk, rh)) * ib;
+      al = -al * alj * ib;
+      ga = -ga * gak * ib;
+      if (live) {
+        nxt[me] = al;
+        nxt[RT + me] = ga;
+        nxt[2 * RT + me] = rh;
+      }
       __syncthreads();
       double* tmp = cur;
       cur = nxt;
       nxt = tmp;
     }
-    const double s_me = rh / be;
-    nxt[me] = s_me;
-    __syncthreads();
-    const double s_left = t > 0 ? nxt[me - 1] : 0.0;
+    const double s_me = rh;  // = x at the chunk's last cell
+    const double s_left = (tt > 0) ? cur[2 * RT + me - 1] : 0.0;
 
-    // ---- 6. back substitution; f + delta ----------------------------------------------------------------------
-    double xi = s_me;
-    fo[E - 1] = f[E - 1] + xi;
+    // ---- 7. back substitution straight into f + delta, written over the row buffer -----------------------------------
+    {
+      double y = ypn[E - 1] + s_me;
+      double* outc = rowbuf + i0 + tt;
+      if (live) outc[E - 1] = y;
 #pragma unroll
-    for (int l = E - 2; l >= 0; l--) {
-      xi = (rp[l] - ap[l] * s_left - c[l] * xi) * inv[l];
-      fo[l] = f[l] + xi;
+      for (int l = E - 2; l >= 0; l--) {
+        y = fma(-cpn[l], y, fma(-apbuf[l * T + tt], s_left, ypn[l]));
+        if (live) outc[l] = y;
+      }
     }
 
-    if (p.nodrag) {
+    if (!FAST && p.nodrag) {
       // fokker_planck.py:414-427: subtract dt nu lap(D f_M) with the same zero-flux stencil
-      double sm0 = 0.0, dummy = 0.0;
+      double sm0[1] = {0.0};
       double fm[E];
 #pragma unroll
       for (int l = 0; l < E; l++) {
-        const double d = vv[l] - vbar;
+        const double d = __ldg(p.v + i0 + l) - vbar;
         fm[l] = exp(-beta * (d * d));
-        sm0 += fm[l];
+        sm0[0] += fm[l];
       }
-      row_sum2(sm0, dummy, red, pcr, parity, r, t, T, mode, amask);
+      if (!live) sm0[0] = 0.0;
+      row_reduce<1>(sm0, red, parity, live ? r : 0, tt, T, RT, warp_mode, live);
       const double nprof = s0 * dv;
-      const double sc = nprof / (sm0 * dv);
-      const double dl = v_left - vbar, dr = v_right - vbar;
-      const double fm_left = t > 0 ? D * (exp(-beta * (dl * dl)) * sc) : 0.0;
-      const double fm_right = t < T - 1 ? D * (exp(-beta * (dr * dr)) * sc) : 0.0;
+      const double sc = nprof / (sm0[0] * dv);
+      const double dl = (tt > 0 ? __ldg(p.v + i0 - 1) : 0.0) - vbar, dr = (tt < T - 1 ? __ldg(p.v + i0 + E) : 0.0) - vbar;
+      const double fm_left = tt > 0 ? D * (exp(-beta * (dl * dl)) * sc) : 0.0;
+      const double fm_right = tt < T - 1 ? D * (exp(-beta * (dr * dr)) * sc) : 0.0;
 #pragma unroll
       for (int l = 0; l < E; l++) fm[l] = D * (fm[l] * sc);
+      double* outc = rowbuf + i0 + tt;
 #pragma unroll
       for (int l = 0; l < E; l++) {
         const int i = i0 + l;
@@ -351,59 +428,72 @@ __global__ void __launch_bounds__(MAXT) collide_kernel(CollideArgs p) {
           lap = (m_ - fm[l]) / (dv * dv);
         else
           lap = (p_ - 2.0 * fm[l] + m_) / (dv * dv);
-        fo[l] = fo[l] - dt * nu * lap;
+        if (live) outc[l] = outc[l] - dt * nu * lap;
       }
     }
-  } else {
-#pragma unroll
-    for (int l = 0; l < E; l++) fo[l] = f[l];
   }
 
-  // ---- 7. Krook: f e^{-nu_K dt} + n f_mx (1 - e^{-nu_K dt}) ---------------------------------------------------
-  if (p.nu_K) {
-    double sn = 0.0, dummy = 0.0;
+  // ---- 8. Krook: f e^{-nu_K dt} + n f_mx (1 - e^{-nu_K dt}); density of the result ------------------------------------
+  if (p.nu_K || p.n_out) {
+    double* outc = rowbuf + i0 + tt;  // own chunk only: no barrier needed after step 7
+    double sn[1] = {0.0};
 #pragma unroll
-    for (int l = 0; l < E; l++) sn += fo[l];
-    row_sum2(sn, dummy, red, pcr, parity, r, t, T, mode, amask);
-    const double nprof = sn * dv;
-    const double ex = exp(-(dt * p.nu_K[row]));
+    for (int l = 0; l < E; l++) sn[0] += outc[l];
+    if (!live) sn[0] = 0.0;
+    row_reduce<1>(sn, red, parity, live ? r : 0, tt, T, RT, warp_mode, live);
+    if (p.nu_K) {
+      const double nprof = sn[0] * dv;
+      const double ex = exp(-(dt * p.nu_K[row]));
+      double s2[1] = {0.0};
 #pragma unroll
-    for (int l = 0; l < E; l++) fo[l] = fo[l] * ex + nprof * __ldg(p.f_mx + i0 + l) * (1.0 - ex);
+      for (int l = 0; l < E; l++) {
+        const double val = outc[l] * ex + nprof * __ldg(p.f_mx + i0 + l) * (1.0 - ex);
+        if (live) outc[l] = val;
+        s2[0] += val;
+      }
+      if (p.n_out) {
+        if (!live) s2[0] = 0.0;
+        row_reduce<1>(s2, red, parity, live ? r : 0, tt, T, RT, warp_mode, live);
+        sn[0] = s2[0];
+      }
+    }
+    if (p.n_out && tt == 0 && active) p.n_out[row] = sn[0] * dv;
   }
 
-  // ---- 8. density of the result -------------------------------------------------------------------------------
-  if (p.n_out) {
-    double sn = 0.0, dummy = 0.0;
-#pragma unroll
-    for (int l = 0; l < E; l++) sn += fo[l];
-    row_sum2(sn, dummy, red, pcr, parity, r, t, T, mode, amask);
-    if (t == 0 && active) p.n_out[row] = sn * dv;
-  }
-
-  // ---- 9. registers -> shared -> global (coalesced) -----------------------------------------------------------
-  __syncthreads();
-#pragma unroll
-  for (int l = 0; l < E; l++) rowbuf[i0 + l + t] = fo[l];
+  // ---- 9. shared -> global (coalesced) --------------------------------------------------------------------------------
   __syncthreads();
   if (active) {
     double* out = p.fout + row * nv;
-    for (int i = t; i < nv; i += T) out[i] = rowbuf[i + i / E];
+    if ((nv & 1) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+      double2* o2 = reinterpret_cast<double2*>(out);
+      for (int i = t; i < (nv >> 1); i += T) {
+        const int j = 2 * i;
+        o2[i] = make_double2(rowbuf[j + j / E], rowbuf[j + 1 + (j + 1) / E]);
+      }
+    } else {
+      for (int i = t; i < nv; i += T) out[i] = rowbuf[i + i / E];
+    }
   }
 }
 
-template <int E, int MAXT>
-static int launch_collide(const CollideArgs& p, cudaStream_t stream) {
+template <int E, int MAXT, int MINB, bool FAST>
+static int launch_collide_t(CollideArgs p, cudaStream_t stream) {
   const int T = p.nv / E;
   int R = MAXT / T;
   if (R < 1) R = 1;
   if ((long long)R > p.rows) R = (int)p.rows;
-  const int threads = R * T;
-  const int nvp = p.nv + p.nv / E;
-  const size_t smem = ((size_t)R * nvp + 128 + 8 * (size_t)R * T) * sizeof(double);
+  p.rows_per_cta = R;
+  const int RT = R * T;
+  const int threads = ((RT + 31) / 32) * 32;  // whole warps; spare threads only take part in barriers
+  const size_t smem = CollideSmem<E>::doubles(R, p.nv, RT) * sizeof(double);
+  if (threads > MAXT || smem > 227 * 1024) {
+    set_last_error("collide: nv=%d does not fit (threads=%d, smem=%zu)", p.nv, threads, smem);
+    return ADEPT_ERR_UNSUPPORTED;
+  }
   static size_t configured[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
-  auto kern = collide_kernel<E, MAXT>;
+  auto kern = collide_kernel<E, MAXT, MINB, FAST>;
   if (dev < 64 && configured[dev] < smem) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) {
@@ -415,6 +505,11 @@ static int launch_collide(const CollideArgs& p, cudaStream_t stream) {
   const long long blocks = (p.rows + R - 1) / R;
   kern<<<(unsigned)blocks, threads, smem, stream>>>(p);
   return check_launch("collide_kernel");
+}
+
+template <int E, int MAXT, int MINB>
+static int launch_collide(const CollideArgs& p, bool fast, cudaStream_t stream) {
+  return fast ? launch_collide_t<E, MAXT, MINB, true>(p, stream) : launch_collide_t<E, MAXT, MINB, false>(p, stream);
 }
 
 int collide_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* v, double dv, double dt,
@@ -433,14 +528,15 @@ int collide_f64(const double* fin, double* fout, int batch, int nx, int nv, cons
     return ADEPT_ERR_BAD_ARG;
   }
   CollideArgs p = {fin, fout, (long long)batch * nx, nv, v, dv, dt, nu_fp, nu_K, f_mx,
-                   model, scheme, nodrag, sg_m, sg_ratio, n_out};
-  if (nv % 8 == 0 && nv / 8 <= 256) return launch_collide<8, 256>(p, stream);
-  if (nv % 8 == 0 && nv / 8 <= 512) return launch_collide<8, 512>(p, stream);
-  if (nv % 16 == 0 && nv / 16 <= 512) return launch_collide<16, 512>(p, stream);
-  if (nv % 16 == 0 && nv / 16 <= 1024) return launch_collide<16, 1024>(p, stream);
-  if (nv % 4 == 0 && nv / 4 <= 256) return launch_collide<4, 256>(p, stream);
-  if (nv % 2 == 0 && nv / 2 <= 256) return launch_collide<2, 256>(p, stream);
-  set_last_error("collide: unsupported nv=%d (need nv %% 8 == 0 and nv <= 16384, or a small even nv)", nv);
+                   model, scheme, nodrag, sg_m, sg_ratio, n_out, 1};
+  const bool fast = scheme == FP_CENTRAL && model != FP_SUPERGAUSSIAN && !nodrag;
+  if (nv % 16 == 0 && nv / 16 <= 256) return launch_collide<16, 256, 2>(p, fast, stream);
+  if (nv % 16 == 0 && nv / 16 <= 512) return launch_collide<16, 512, 1>(p, fast, stream);
+  if (nv % 16 == 0 && nv / 16 <= 1024) return launch_collide<16, 1024, 1>(p, fast, stream);
+  if (nv % 8 == 0 && nv / 8 <= 256) return launch_collide<8, 256, 2>(p, fast, stream);
+  if (nv % 4 == 0 && nv / 4 <= 256) return launch_collide<4, 256, 2>(p, fast, stream);
+  if (nv % 2 == 0 && nv / 2 <= 256) return launch_collide<2, 256, 2>(p, fast, stream);
+  set_last_error("collide: unsupported nv=%d (need nv %% 16 == 0 and nv <= 16384, or a small even nv)", nv);
   return ADEPT_ERR_UNSUPPORTED;
 }
 
