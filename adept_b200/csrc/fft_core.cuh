@@ -122,33 +122,98 @@ __device__ __forceinline__ void dft_r(cplx* v) {
 
 // ---- Stockham passes -------------------------------------------------------------------------
 
+// compiler-level scheduling fence: keeps the loads of one butterfly column from being hoisted above the previous
+// column's arithmetic (a radix-16 pass would otherwise hold 16 points + 15 twiddles = 124 registers in flight)
+__device__ __forceinline__ void sched_fence() { asm volatile("" ::: "memory"); }
+
+// second half of the radix-16 butterfly: inter-stage twiddles W16^{c k1}, row DFT4s, register transposition.
+// On entry v[c + 4 k1] holds the column DFT4 outputs; on exit v[k] = y[k].
+__device__ __forceinline__ void dft16_finish(cplx* v) {
+  const cplx w1 = cmake(ADEPT_COS_PI_8, -ADEPT_SIN_PI_8);
+  const cplx w3 = cmake(ADEPT_SIN_PI_8, -ADEPT_COS_PI_8);
+  v[5] = cmul(v[5], w1);
+  v[6] = cmake((v[6].x + v[6].y) * ADEPT_SQRT1_2, (v[6].y - v[6].x) * ADEPT_SQRT1_2);
+  v[7] = cmul(v[7], w3);
+  v[9] = cmake((v[9].x + v[9].y) * ADEPT_SQRT1_2, (v[9].y - v[9].x) * ADEPT_SQRT1_2);
+  v[10] = cmul_mi(v[10]);
+  v[11] = cmake((v[11].y - v[11].x) * ADEPT_SQRT1_2, -(v[11].x + v[11].y) * ADEPT_SQRT1_2);
+  v[13] = cmul(v[13], w3);
+  v[14] = cmake((v[14].y - v[14].x) * ADEPT_SQRT1_2, -(v[14].x + v[14].y) * ADEPT_SQRT1_2);
+  v[15] = cmul(v[15], cmake(-ADEPT_COS_PI_8, ADEPT_SIN_PI_8));
+#pragma unroll
+  for (int k1 = 0; k1 < 4; k1++) dft4(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
+#pragma unroll
+  for (int k1 = 0; k1 < 4; k1++)
+#pragma unroll
+    for (int k2 = k1 + 1; k2 < 4; k2++) {
+      cplx t = v[4 * k1 + k2];
+      v[4 * k1 + k2] = v[4 * k2 + k1];
+      v[4 * k2 + k1] = t;
+    }
+}
+
 template <int LOGN, int P>
 struct FftPass {
   using C = FftCfg<LOGN>;
   static __device__ __forceinline__ void run(cplx (&x)[C::E], cplx* __restrict__ buf, const cplx* __restrict__ tw,
-                                             int t) {
+                                             int t, int opaque_zero) {
     constexpr int R = C::radix(P);
     constexpr int NS = C::ns(P);
     constexpr int Q = C::E / R;
     constexpr int T = C::T;
-    if constexpr (P > 0) {
+    if constexpr (R == 16) {
+      // one radix-16 butterfly per thread (Q == 1), processed column by column: load 4 points (+ their twiddles),
+      // column DFT4, next column; then the second half of the butterfly
+      static_assert(Q == 1, "radix-16 passes use E == 16");
+      const int k = t & (NS - 1);
+      const cplx* twp = tw + C::tw_off(P) + k;
+      if constexpr (P > 0) {
 #pragma unroll
-      for (int m = 0; m < C::E; m++) x[m] = buf[fft_pad(t + T * m)];
-    }
-#pragma unroll
-    for (int q = 0; q < Q; q++) {
-      const int k = (t + T * q) & (NS - 1);
-      cplx v[R];
-#pragma unroll
-      for (int r = 0; r < R; r++) v[r] = x[q + r * Q];
-      if constexpr (NS > 1) {
-        const cplx* twp = tw + C::tw_off(P) + k;
-#pragma unroll
-        for (int r = 1; r < R; r++) v[r] = cmul(v[r], __ldg(twp + (r - 1) * NS));
+        for (int m = 0; m < 16; m++) x[m] = buf[fft_pad(t + T * m)];
       }
-      dft_r<R>(v);
+      // Twiddles are fetched one column (4 values) at a time.  The address of column c+1 carries a data dependency
+      // on a twiddle of column c (`opaque_zero` is 0 at run time, unknown to ptxas), so at most two columns of
+      // twiddles are in flight: without it ptxas hoists all 15 loads (60 registers) and spills.
+      int dep = 0;
 #pragma unroll
-      for (int r = 0; r < R; r++) x[q + r * Q] = v[r];
+      for (int c = 0; c < 4; c++) {
+        if constexpr (NS > 1) {
+          cplx w[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int r = c + 4 * j;
+            if (r > 0) w[j] = __ldg(twp + (r - 1) * NS + dep);
+          }
+          dep = __double2hiint(w[1].x) & opaque_zero;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int r = c + 4 * j;
+            if (r > 0) x[r] = cmul(x[r], w[j]);
+          }
+        }
+        dft4(x[c], x[c + 4], x[c + 8], x[c + 12]);
+      }
+      dft16_finish(x);
+    } else {
+      if constexpr (P > 0) {
+#pragma unroll
+        for (int m = 0; m < C::E; m++) x[m] = buf[fft_pad(t + T * m)];
+      }
+#pragma unroll
+      for (int q = 0; q < Q; q++) {
+        const int k = (t + T * q) & (NS - 1);
+        cplx v[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) v[r] = x[q + r * Q];
+        if constexpr (NS > 1) {
+          const cplx* twp = tw + C::tw_off(P) + k;
+#pragma unroll
+          for (int r = 1; r < R; r++) v[r] = cmul(v[r], __ldg(twp + (r - 1) * NS));
+        }
+        dft_r<R>(v);
+#pragma unroll
+        for (int r = 0; r < R; r++) x[q + r * Q] = v[r];
+      }
     }
     if constexpr (P < C::NPASS - 1) {
       __syncthreads();  // all reads of buf for this pass (and any earlier use) are done
@@ -161,7 +226,7 @@ struct FftPass {
         for (int r = 0; r < R; r++) buf[fft_pad(j0 + r * NS)] = x[q + r * Q];
       }
       __syncthreads();
-      FftPass<LOGN, P + 1>::run(x, buf, tw, t);
+      FftPass<LOGN, P + 1>::run(x, buf, tw, t, opaque_zero);
     }
   }
 };
@@ -169,8 +234,9 @@ struct FftPass {
 // Forward complex FFT of the N points held as x[m] = z[t + T*m]; result X[t + T*m] in x[m].
 // All threads of the CTA must call this together (it uses __syncthreads()).
 template <int LOGN>
-__device__ __forceinline__ void fft_forward(cplx (&x)[FftCfg<LOGN>::E], cplx* buf, const cplx* tw, int t) {
-  FftPass<LOGN, 0>::run(x, buf, tw, t);
+__device__ __forceinline__ void fft_forward(cplx (&x)[FftCfg<LOGN>::E], cplx* buf, const cplx* tw, int t,
+                                            int opaque_zero) {
+  FftPass<LOGN, 0>::run(x, buf, tw, t, opaque_zero);
 }
 
 }  // namespace adept

@@ -16,6 +16,7 @@ struct PoissonArgs {
   int mode;              // 0 poisson, 1 boltzmann
   double Te, lambda_De;  // boltzmann: lambda_De < 0 -> sqrt(Te / rho_0)
   const cplx* tw;
+  int zero;  // always 0; opaque to ptxas (see FftPass)
 };
 
 template <int LOGN>
@@ -32,7 +33,7 @@ __global__ void __launch_bounds__(FftCfg<LOGN>::T) poisson_kernel(PoissonArgs p)
   cplx x[E];
 #pragma unroll
   for (int m = 0; m < E; m++) x[m] = cmake(rho[tt + T * m], 0.0);
-  fft_forward<LOGN>(x, buf, p.tw, tt);
+  fft_forward<LOGN>(x, buf, p.tw, tt, p.zero);
   if (t == 0) rho0_s = x[0].x / (double)N;  // mean(rho) = DC / N
   __syncthreads();
   const double rho0 = rho0_s;
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(FftCfg<LOGN>::T) poisson_kernel(PoissonArgs p)
     x[m] = cmake(y.y, y.x);
   }
   if (C::NPASS > 1) __syncthreads();
-  fft_forward<LOGN>(x, buf, p.tw, tt);
+  fft_forward<LOGN>(x, buf, p.tw, tt, p.zero);
 #pragma unroll
   for (int m = 0; m < E; m++) eo[t + T * m] = x[m].y / (double)N;  // Re(ifft) = Im of swapped result
 }
@@ -71,7 +72,7 @@ int poisson_f64(const double* rho, const double* kmul, long long kmul_stride, do
     set_last_error("poisson: nx=%d must be a power of two in [2, 8192] (batch=%d)", nx, batch);
     return logn < 1 || logn > 13 ? ADEPT_ERR_UNSUPPORTED : ADEPT_ERR_BAD_SHAPE;
   }
-  PoissonArgs p = {rho, kmul, kmul_stride, e, mode, Te, lambda_De, get_twiddles(logn)};
+  PoissonArgs p = {rho, kmul, kmul_stride, e, mode, Te, lambda_De, get_twiddles(logn), 0};
   if (!p.tw) return ADEPT_ERR_CUDA;
   switch (logn) {
 #define ADEPT_CASE(L)                                                                              \
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(FftCfg<LOGN>::T) poisson_kernel_big(PoissonArg
   cplx x[E];
 #pragma unroll
   for (int m = 0; m < E; m++) x[m] = cmake(rho[t + T * m], 0.0);
-  fft_forward<LOGN>(x, buf, p.tw, t);
+  fft_forward<LOGN>(x, buf, p.tw, t, p.zero);
   if (t == 0) rho0_s = x[0].x / (double)N;
   __syncthreads();
   const double rho0 = rho0_s;
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(FftCfg<LOGN>::T) poisson_kernel_big(PoissonArg
     x[m] = cmake(y.y, y.x);
   }
   __syncthreads();
-  fft_forward<LOGN>(x, buf, p.tw, t);
+  fft_forward<LOGN>(x, buf, p.tw, t, p.zero);
 #pragma unroll
   for (int m = 0; m < E; m++) eo[t + T * m] = x[m].y / (double)N;
 }
@@ -159,7 +160,7 @@ int poisson_dispatch_f64(const double* rho, const double* kmul, long long kmul_s
                          int mode, double Te, double lambda_De, cudaStream_t stream) {
   const int logn = ilog2_exact(nx);
   if (logn == 12 || logn == 13) {
-    PoissonArgs p = {rho, kmul, kmul_stride, e, mode, Te, lambda_De, get_twiddles(logn)};
+    PoissonArgs p = {rho, kmul, kmul_stride, e, mode, Te, lambda_De, get_twiddles(logn), 0};
     if (!p.tw) return ADEPT_ERR_CUDA;
     return logn == 12 ? launch_poisson_big<12>(p, batch, stream) : launch_poisson_big<13>(p, batch, stream);
   }
