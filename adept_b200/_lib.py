@@ -21,6 +21,9 @@ SIGNATURES = {
     "adept_b200_last_error": [],
     "adept_b200_prepare": [c_i],
     "adept_b200_vdfdx_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_d, c_d, c_dp, c_dp],
+    "adept_b200_vdfdx_rho_parts": [c_i, c_i, c_i],
+    "adept_b200_vdfdx_rho_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_d, c_d, c_dp, c_dp, c_i, c_dp],
+    "adept_b200_reduce_parts_f64": [c_dp, c_i, c_ll, c_d, c_d, c_dp, c_dp, c_dp],
     "adept_b200_edfdv_exp_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_dp, c_dp, c_d, c_d, c_d, c_d, c_dp],
     "adept_b200_edfdv_spline_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_dp, c_dp, c_d, c_d, c_d, c_d, c_dp],
     "adept_b200_moments_f64": [c_dp, c_i, c_i, c_i, c_dp, c_d, C.POINTER(c_dp), C.POINTER(c_dp), C.POINTER(c_d), c_dp],

@@ -102,6 +102,11 @@ int wave_step_f64(const double*, const double*, const double*, const double*, co
                   double, double, double, cudaStream_t);
 int collide_f64(const double*, double*, int, int, int, const double*, double, double, const double*, const double*,
                 const double*, int, int, int, double, double, double*, cudaStream_t);
+int reduce_parts_f64(const double*, int, long long, double, double, const double*, double*, cudaStream_t);
+bool vdfdx_tma_supported(const double*, const double*, int, int);
+int vdfdx_tma_parts(int, int, int);
+int vdfdx_tma_f64(const double*, double*, int, int, int, const double*, double, const double*, double, double*,
+                  cudaStream_t);
 
 }  // namespace adept
 
@@ -136,7 +141,50 @@ int adept_b200_prepare(int n) {
 int adept_b200_vdfdx_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* v, double dt,
                          double k1x, const double* k1x_batch, void* stream) {
   ADEPT_REQUIRE(f_in, "f_in") ADEPT_REQUIRE(f_out, "f_out") ADEPT_REQUIRE(v, "v")
+  if (batch >= 1 && vdfdx_tma_supported(f_in, f_out, nx, nv))
+    return vdfdx_tma_f64(f_in, f_out, batch, nx, nv, v, dt, k1x_batch, k1x, nullptr, (cudaStream_t)stream);
   return vdfdx_f64(f_in, f_out, batch, nx, nv, v, dt, k1x_batch, k1x, (cudaStream_t)stream);
+}
+
+int adept_b200_vdfdx_rho_parts(int batch, int nx, int nv) {
+  if (batch < 1 || nx < 2 || nv < 2) return 1;
+  // alignment is checked again at call time; an unaligned buffer falls back to one part
+  const int parts = vdfdx_tma_supported(nullptr, nullptr, nx, nv) ? vdfdx_tma_parts(batch, nx, nv) : 1;
+  return parts < 1 ? 1 : parts;
+}
+
+int adept_b200_vdfdx_rho_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* v, double dt,
+                             double k1x, const double* k1x_batch, double* parts, int nparts, void* stream) {
+  ADEPT_REQUIRE(f_in, "f_in") ADEPT_REQUIRE(f_out, "f_out") ADEPT_REQUIRE(v, "v") ADEPT_REQUIRE(parts, "parts")
+  cudaStream_t st = (cudaStream_t)stream;
+  if (batch < 1 || nx < 2 || nv < 2) {
+    set_last_error("vdfdx_rho: bad shape batch=%d nx=%d nv=%d", batch, nx, nv);
+    return ADEPT_ERR_BAD_SHAPE;
+  }
+  const long long n = (long long)batch * nx;
+  if (nparts < adept_b200_vdfdx_rho_parts(batch, nx, nv)) {
+    set_last_error("vdfdx_rho: parts buffer has %d rows, adept_b200_vdfdx_rho_parts() asks for %d", nparts,
+                   adept_b200_vdfdx_rho_parts(batch, nx, nv));
+    return ADEPT_ERR_BAD_ARG;
+  }
+  cudaError_t err = cudaMemsetAsync(parts, 0, (size_t)nparts * n * sizeof(double), st);
+  if (err != cudaSuccess) {
+    set_last_error("vdfdx_rho: cudaMemsetAsync: %s", cudaGetErrorString(err));
+    return ADEPT_ERR_CUDA;
+  }
+  if (vdfdx_tma_supported(f_in, f_out, nx, nv))
+    return vdfdx_tma_f64(f_in, f_out, batch, nx, nv, v, dt, k1x_batch, k1x, parts, st);
+  // small or odd shapes: direct kernel, then one plain velocity sum into part 0
+  int rc = vdfdx_f64(f_in, f_out, batch, nx, nv, v, dt, k1x_batch, k1x, st);
+  if (rc != ADEPT_OK) return rc;
+  double* outs[3] = {parts, nullptr, nullptr};
+  return moments_f64(f_out, batch, nx, nv, nullptr, 1.0, nullptr, outs, nullptr, st);
+}
+
+int adept_b200_reduce_parts_f64(const double* parts, int nparts, long long n, double scale_a, double scale_b,
+                                const double* base, double* out, void* stream) {
+  ADEPT_REQUIRE(parts, "parts") ADEPT_REQUIRE(out, "out")
+  return reduce_parts_f64(parts, nparts, n, scale_a, scale_b, base, out, (cudaStream_t)stream);
 }
 
 int adept_b200_edfdv_exp_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* e,

@@ -152,7 +152,8 @@ __device__ __forceinline__ void dft16_finish(cplx* v) {
     }
 }
 
-template <int LOGN, int P>
+// BS: stride (in cplx) between consecutive buffer slots -- 2 when two transforms are interleaved slot by slot
+template <int LOGN, int P, int BS = 1>
 struct FftPass {
   using C = FftCfg<LOGN>;
   static __device__ __forceinline__ void run(cplx (&x)[C::E], cplx* __restrict__ buf, const cplx* __restrict__ tw,
@@ -169,7 +170,7 @@ struct FftPass {
       const cplx* twp = tw + C::tw_off(P) + k;
       if constexpr (P > 0) {
 #pragma unroll
-        for (int m = 0; m < 16; m++) x[m] = buf[fft_pad(t + T * m)];
+        for (int m = 0; m < 16; m++) x[m] = buf[fft_pad(t + T * m) * BS];
       }
       // Twiddles are fetched one column (4 values) at a time.  The address of column c+1 carries a data dependency
       // on a twiddle of column c (`opaque_zero` is 0 at run time, unknown to ptxas), so at most two columns of
@@ -197,7 +198,7 @@ struct FftPass {
     } else {
       if constexpr (P > 0) {
 #pragma unroll
-        for (int m = 0; m < C::E; m++) x[m] = buf[fft_pad(t + T * m)];
+        for (int m = 0; m < C::E; m++) x[m] = buf[fft_pad(t + T * m) * BS];
       }
 #pragma unroll
       for (int q = 0; q < Q; q++) {
@@ -223,20 +224,20 @@ struct FftPass {
         const int k = b & (NS - 1);
         const int j0 = (b - k) * R + k;
 #pragma unroll
-        for (int r = 0; r < R; r++) buf[fft_pad(j0 + r * NS)] = x[q + r * Q];
+        for (int r = 0; r < R; r++) buf[fft_pad(j0 + r * NS) * BS] = x[q + r * Q];
       }
       __syncthreads();
-      FftPass<LOGN, P + 1>::run(x, buf, tw, t, opaque_zero);
+      FftPass<LOGN, P + 1, BS>::run(x, buf, tw, t, opaque_zero);
     }
   }
 };
 
 // Forward complex FFT of the N points held as x[m] = z[t + T*m]; result X[t + T*m] in x[m].
 // All threads of the CTA must call this together (it uses __syncthreads()).
-template <int LOGN>
+template <int LOGN, int BS = 1>
 __device__ __forceinline__ void fft_forward(cplx (&x)[FftCfg<LOGN>::E], cplx* buf, const cplx* tw, int t,
                                             int opaque_zero) {
-  FftPass<LOGN, 0>::run(x, buf, tw, t, opaque_zero);
+  FftPass<LOGN, 0, BS>::run(x, buf, tw, t, opaque_zero);
 }
 
 }  // namespace adept

@@ -10,27 +10,11 @@
 // phase factors (Im of DC/Nyquist dropped exactly like irfft does), recombined, and transformed back with the
 // same forward kernel (swap trick).  Phase factors exp(-i m alpha) are built from two small per-sequence tables
 // (m = 64*hi + lo) so no sincos is evaluated per element.
-#include "fft_core.cuh"
+#include "push_core.cuh"
 
 namespace adept {
 
 enum { AXIS_X = 0, AXIS_V = 1 };
-
-// Per-sequence phase table (shared memory): the thread's base phase exp(-i t alpha) / (2N) is the product of a "lo"
-// and a "hi" entry (t = (hi << LOBT) + lo); the phases of its other modes t + T m follow by repeated multiplication
-// with step = exp(-i T alpha).  nyq = cos(alpha N/2) / (2N) (irfft drops the imaginary part of the Nyquist mode).
-template <int LOGN>
-struct PhaseCfg {
-  static constexpr int N = 1 << LOGN;
-  static constexpr int T = FftCfg<LOGN>::T;
-  static constexpr int LOGT = LOGN - (LOGN < 4 ? LOGN : 4);
-  static constexpr int LOBT = LOGT > 4 ? 4 : LOGT;
-  static constexpr int NLO = 1 << LOBT;
-  static constexpr int NHI = T >> LOBT;
-  static constexpr int STEP = NLO + NHI;  // index of exp(-i T alpha)
-  static constexpr int NYQ = NLO + NHI + 1;
-  static constexpr int PER_SEQ = NLO + NHI + 2;
-};
 
 template <int LOGN, int AXIS>
 struct PushCfg {
@@ -116,25 +100,7 @@ __global__ void __launch_bounds__(PushCfg<LOGN, AXIS>::THREADS, (PushCfg<LOGN, A
     }
   }
 
-  // ---- phase tables (see PhaseCfg) ---------------------------------------------------------------------------
-  for (int i = t; i < 2 * PC::PER_SEQ; i += T) {
-    const int s = i / PC::PER_SEQ, j = i % PC::PER_SEQ;
-    const double al = s ? alpha_b : alpha_a;
-    const double sc = 0.5 / (double)N;
-    double sn, cs;
-    if (j < PC::NLO) {
-      sincos((double)j * al, &sn, &cs);
-      ph[i] = cmake(cs * sc, -sn * sc);
-    } else if (j < PC::STEP) {
-      sincos((double)((j - PC::NLO) << PC::LOBT) * al, &sn, &cs);
-      ph[i] = cmake(cs, -sn);
-    } else if (j == PC::STEP) {
-      sincos((double)T * al, &sn, &cs);
-      ph[i] = cmake(cs, -sn);
-    } else {
-      ph[i] = cmake(cos((double)(N / 2) * al) * sc, 0.0);
-    }
-  }
+  phase_table_fill<LOGN>(ph, alpha_a, alpha_b, t, T);
 
   // ---- load: x[m] = a[e] + i b[e], e = t + T m -----------------------------------------------------------
   cplx x[E];
@@ -161,50 +127,7 @@ __global__ void __launch_bounds__(PushCfg<LOGN, AXIS>::THREADS, (PushCfg<LOGN, A
 
   fft_forward<LOGN>(x, buf, p.tw, t, p.zero);
 
-  // ---- half-spectrum update ------------------------------------------------------------------------------------
-  // Thread t holds Z[t + T m] in x[m].  Its lower register half (m < E/2) are the modes k = t + T m < N/2; the partner
-  // N - k of each lives in the upper register half of thread (T - t) mod T.  Upper halves are published in natural
-  // order, every thread updates its 8 (k, N-k) pairs (one phase evaluation and one spectrum separation per pair),
-  // writes the partner value back, and upper halves are read back.  Results are stored swapped (im, re): the inverse
-  // transform is swap . forward FFT . swap.
-  constexpr int H = E / 2;
-  __syncthreads();  // last forward pass has finished reading buf; phase tables are complete
-#pragma unroll
-  for (int m = H; m < E; m++) buf[fft_pad(t + T * m)] = x[m];
-  __syncthreads();
-  {
-    const cplx* pha = ph;
-    const cplx* phb = ph + PC::PER_SEQ;
-    cplx pa = cmul(pha[t & (PC::NLO - 1)], pha[PC::NLO + (t >> PC::LOBT)]);
-    cplx pb = cmul(phb[t & (PC::NLO - 1)], phb[PC::NLO + (t >> PC::LOBT)]);
-    const cplx sa = pha[PC::STEP], sb = phb[PC::STEP];
-#pragma unroll
-    for (int m = 0; m < H; m++) {
-      if (m > 0) {
-        pa = cmul(pa, sa);
-        pb = cmul(pb, sb);
-      }
-      const int k = t + T * m;
-      const bool self = (k == 0);  // DC pairs with itself (its phase is real: alpha * 0)
-      const int q = fft_pad((N - k) & (N - 1));
-      const cplx zk = x[m];
-      const cplx zq = self ? zk : buf[q];
-      const cplx A = cmake(zk.x + zq.x, zk.y - zq.y);  // 2 * spectrum of a at k
-      const cplx B = cmake(zk.y + zq.y, zq.x - zk.x);  // 2 * spectrum of b at k
-      const cplx Ap = cmul(A, pa), Bp = cmul(B, pb);
-      // Z'[k] = A' + i B' ;  Z'[N-k] = conj(A') + i conj(B')
-      x[m] = cmake(Ap.y + Bp.x, Ap.x - Bp.y);
-      if (!self) buf[q] = cmake(Bp.x - Ap.y, Ap.x + Bp.y);
-    }
-    if (t == 0) {  // Nyquist mode: real phase cos(alpha N/2), pairs with itself
-      const int q = fft_pad(N / 2);
-      const cplx z = buf[q];
-      buf[q] = cmake(2.0 * z.y * phb[PC::NYQ].x, 2.0 * z.x * pha[PC::NYQ].x);
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int m = H; m < E; m++) x[m] = buf[fft_pad(t + T * m)];
+  half_spectrum_update<LOGN, 1>(x, buf, ph, t);
 
   fft_forward<LOGN>(x, buf, p.tw + p.zero, t, p.zero);  // opaque offset: no CSE of twiddle loads with the first FFT
 

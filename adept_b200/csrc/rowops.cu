@@ -149,4 +149,34 @@ int axpy_f64(const double* a, const double* b, double s, double* out, long long 
   return check_launch("axpy_kernel");
 }
 
+// ---- second stage of the fused x-push charge density: out[i] = base[i] + scale_b * ((sum_p parts[p, i]) * scale_a) ----
+__global__ void __launch_bounds__(256) reduce_parts_kernel(const double* __restrict__ parts, int nparts, long long n,
+                                                           double scale_a, double scale_b,
+                                                           const double* __restrict__ base, double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;  // fixed summation order: deterministic
+  int pidx = 0;
+  for (; pidx + 3 < nparts; pidx += 4) {
+    s0 += parts[(long long)pidx * n + i];
+    s1 += parts[(long long)(pidx + 1) * n + i];
+    s2 += parts[(long long)(pidx + 2) * n + i];
+    s3 += parts[(long long)(pidx + 3) * n + i];
+  }
+  for (; pidx < nparts; pidx++) s0 += parts[(long long)pidx * n + i];
+  const double s = (s0 + s1) + (s2 + s3);
+  const double term = __dmul_rn(scale_b, __dmul_rn(s, scale_a));
+  out[i] = base ? __dadd_rn(base[i], term) : term;
+}
+
+int reduce_parts_f64(const double* parts, int nparts, long long n, double scale_a, double scale_b, const double* base,
+                     double* out, cudaStream_t stream) {
+  if (nparts < 1 || n < 1) {
+    set_last_error("reduce_parts: bad shape nparts=%d n=%lld", nparts, n);
+    return ADEPT_ERR_BAD_SHAPE;
+  }
+  reduce_parts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(parts, nparts, n, scale_a, scale_b, base, out);
+  return check_launch("reduce_parts_kernel");
+}
+
 }  // namespace adept

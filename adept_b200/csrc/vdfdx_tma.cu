@@ -1,0 +1,303 @@
+// x-advection for large grids: persistent CTAs, TMA-staged x-pencil tiles, two interleaved in-smem FFTs per tile,
+// charge-density partial sums fused into the epilogue.
+//
+// Reference semantics: SpaceExponential.push  adept/_vlasov1d/solvers/pushers/vlasov.py:234-251, followed by the
+// velocity sum of compute_charge_density  adept/_vlasov1d/solvers/pushers/field.py:197-208.
+//
+// f is [batch*nx, nv] row-major, so an x-pencil is strided by nv*8 bytes.  One tile = all nx rows of 4 neighbouring
+// v-columns (32 bytes per row = one DRAM sector), fetched by nx/256 TMA boxes {4, 256} of a 2-D tensor map into shared
+// memory as tile[row][4] = two interleaved complex sequences z_g[row] = (col 2g, col 2g+1), g = 0, 1.  (A measured
+// property of the TMA unit decides the tile shape: narrow boxes are request-bound at ~0.5 rows/clk/SM, so 16-byte
+// rows reach < 3 TB/s while 32-byte rows reach 4.5 TB/s; tools/micro/tma_pencil.cu.)  The CTA's 2*T threads are
+// interleaved the same way (g = tid & 1, t = tid >> 1): every shared-memory access of a warp covers 16 consecutive
+// slots x 2 sequences = 512 contiguous bytes, twiddle loads are shared by lane pairs, and the direct 16-byte stores of
+// a warp fill whole 32-byte sectors.  The landing zone is reused in place as the (padded) Stockham exchange buffer.
+// The next tile's TMA load is issued as soon as the last inverse pass has read the buffer, so it overlaps the stores.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "push_core.cuh"
+
+namespace adept {
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+                   "r"(smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+struct TmaPushArgs {
+  double* fout;
+  int batch, nx, nv;
+  int ntiles;           // batch * nv / 4
+  const double* v;      // [nv]
+  const double* k1_batch;
+  double k1, dt;
+  const cplx* tw;
+  int zero;
+  double* partial;      // [gridDim.x, batch*nx] per-CTA row sums of f_out, or null
+};
+
+template <int LOGN>
+struct TmaCfg {
+  using C = FftCfg<LOGN>;
+  using PC = PhaseCfg<LOGN>;
+  static constexpr int N = C::N, T = C::T;
+  static constexpr int THREADS = 2 * T;
+  static constexpr int BOX_ROWS = N < 256 ? N : 256;
+  static constexpr int NBOX = N / BOX_ROWS;
+  static constexpr size_t BUF_BYTES = (size_t)2 * C::BUF * sizeof(cplx);  // two interleaved padded buffers
+  static constexpr size_t PH_BYTES = (size_t)2 * 2 * PC::PER_SEQ * sizeof(cplx);
+  static constexpr size_t ACC_BYTES = (size_t)N * sizeof(double);
+  static constexpr size_t SMEM = BUF_BYTES + PH_BYTES + ACC_BYTES + 16;
+};
+
+template <int LOGN>
+__global__ void __launch_bounds__(TmaCfg<LOGN>::THREADS, 1)
+    vdfdx_tma_kernel(const __grid_constant__ CUtensorMap in_map, TmaPushArgs p) {
+  using K = TmaCfg<LOGN>;
+  using C = FftCfg<LOGN>;
+  using PC = PhaseCfg<LOGN>;
+  constexpr int N = C::N, E = C::E, T = C::T;
+  static_assert(E == 16, "TMA x-advection needs nx >= 16");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  cplx* tile = reinterpret_cast<cplx*>(smem_raw);                                   // landing zone / exchange buffer
+  cplx* ph_all = reinterpret_cast<cplx*>(smem_raw + K::BUF_BYTES);                  // [2 groups][2 seq][PER_SEQ]
+  double* rho_acc = reinterpret_cast<double*>(smem_raw + K::BUF_BYTES + K::PH_BYTES);  // [N] row sums of this CTA
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + K::BUF_BYTES + K::PH_BYTES + K::ACC_BYTES);
+
+  const int tid = threadIdx.x;
+  const int g = tid & 1, t = tid >> 1;
+  cplx* buf = tile + g;
+  cplx* ph = ph_all + g * 2 * PC::PER_SEQ;
+  const int tiles_per_member = p.nv >> 2;
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (p.partial) {
+    for (int i = tid; i < N; i += K::THREADS) rho_acc[i] = 0.0;
+  }
+  __syncthreads();
+
+  auto issue_load = [&](int tl) {
+    const int b = tl / tiles_per_member, cg = tl - b * tiles_per_member;
+    mbar_expect_tx(bar, (uint32_t)(N * 4 * sizeof(double)));
+#pragma unroll 1
+    for (int bx = 0; bx < K::NBOX; bx++)
+      tma_load_2d(reinterpret_cast<double*>(tile) + (size_t)bx * K::BOX_ROWS * 4, &in_map, bar, cg * 4,
+                  b * N + bx * K::BOX_ROWS);
+  };
+  auto flush_rho = [&](int b) {  // this CTA owns row blockIdx.x of `partial`: plain read-modify-write
+    __syncthreads();
+    double* dst = p.partial + ((size_t)blockIdx.x * p.batch + b) * N;
+    for (int i = tid; i < N; i += K::THREADS) {
+      dst[i] += rho_acc[i];
+      rho_acc[i] = 0.0;
+    }
+    __syncthreads();
+  };
+
+  int tl = blockIdx.x;
+  if (tid == 0 && tl < p.ntiles) issue_load(tl);
+  uint32_t parity = 0;
+  int cur_b = -1;
+  for (; tl < p.ntiles; tl += gridDim.x) {
+    const int b = tl / tiles_per_member, cg = tl - b * tiles_per_member;
+    if (p.partial && b != cur_b) {
+      if (cur_b >= 0) flush_rho(cur_b);
+      cur_b = b;
+    }
+    const int col = 4 * cg + 2 * g;
+    {
+      const double k1 = p.k1_batch ? p.k1_batch[b] : p.k1;
+      const double alpha_a = k1 * (p.v[col] * p.dt);
+      const double alpha_b = k1 * (p.v[col + 1] * p.dt);
+      phase_table_fill<LOGN>(ph, alpha_a, alpha_b, t, T);
+    }
+    mbar_wait(bar, parity);
+    parity ^= 1;
+
+    cplx x[E];
+#pragma unroll
+    for (int m = 0; m < E; m++) x[m] = buf[(t + T * m) * 2];  // unpadded landing layout
+    fft_forward<LOGN, 2>(x, buf, p.tw, t, p.zero);
+    half_spectrum_update<LOGN, 2>(x, buf, ph, t);
+    fft_forward<LOGN, 2>(x, buf, p.tw + p.zero, t, p.zero);
+
+    // the exchange buffer is dead once every thread has finished the last pass: hand it to the next tile's TMA load
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0 && tl + (int)gridDim.x < p.ntiles) issue_load(tl + gridDim.x);
+
+    double* dst = p.fout + ((size_t)b * N) * p.nv + col;
+#pragma unroll
+    for (int m = 0; m < E; m++) {
+      const size_t e = t + T * m;
+      *reinterpret_cast<double2*>(dst + e * p.nv) = make_double2(x[m].y, x[m].x);
+    }
+    if (p.partial) {
+#pragma unroll
+      for (int m = 0; m < E; m++) {
+        double s = x[m].y + x[m].x;
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        if (g == 0) rho_acc[t + T * m] += s;  // row t + T m is owned by this lane pair
+      }
+    }
+  }
+  if (p.partial && cur_b >= 0) flush_rho(cur_b);
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+    (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+static int encode_map(CUtensorMap* map, const double* base, long long rows, int nv, int box_rows) {
+  EncodeTiledFn enc = get_encoder();
+  if (!enc) {
+    set_last_error("vdfdx(tma): cuTensorMapEncodeTiled is not available from the driver");
+    return ADEPT_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)nv, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)nv * sizeof(double)};
+  cuuint32_t box[2] = {4, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("vdfdx(tma): cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return ADEPT_ERR_CUDA;
+  }
+  return ADEPT_OK;
+}
+
+template <int LOGN>
+static int tma_ctas(int ntiles) {
+  using K = TmaCfg<LOGN>;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int per_sm = (int)((227 * 1024) / (K::SMEM + 1024));
+  const int by_threads = 2048 / K::THREADS;
+  if (per_sm > by_threads) per_sm = by_threads;
+  if (per_sm > 4) per_sm = 4;
+  if (per_sm < 1) per_sm = 1;
+  const int grid = sms * per_sm;
+  return grid < ntiles ? grid : ntiles;
+}
+
+template <int LOGN>
+static int launch_tma(const CUtensorMap& map, TmaPushArgs p, int grid, cudaStream_t stream) {
+  using K = TmaCfg<LOGN>;
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto kern = vdfdx_tma_kernel<LOGN>;
+  if (dev < 64 && !configured[dev]) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
+    if (err != cudaSuccess) {
+      set_last_error("cudaFuncSetAttribute(vdfdx_tma, smem=%zu): %s", K::SMEM, cudaGetErrorString(err));
+      return ADEPT_ERR_CUDA;
+    }
+    configured[dev] = true;
+  }
+  kern<<<grid, K::THREADS, K::SMEM, stream>>>(map, p);
+  return check_launch("vdfdx_tma_kernel");
+}
+
+static int ilog2_exact_(int n) {
+  if (n < 2 || (n & (n - 1))) return -1;
+  int l = 0;
+  while ((1 << l) < n) l++;
+  return l;
+}
+
+// true when the TMA kernel handles this problem (otherwise callers use the direct kernel of push.cu)
+bool vdfdx_tma_supported(const double* fin, const double* fout, int nx, int nv) {
+  const int logn = ilog2_exact_(nx);
+  if (logn < 8 || logn > 12) return false;
+  if (nv % 4) return false;
+  if ((reinterpret_cast<uintptr_t>(fin) | reinterpret_cast<uintptr_t>(fout)) & 15) return false;
+  return get_encoder() != nullptr;
+}
+
+// number of partial-sum rows (persistent CTAs) the TMA kernel uses for this shape
+int vdfdx_tma_parts(int batch, int nx, int nv) {
+  const int ntiles = batch * (nv / 4);
+  switch (ilog2_exact_(nx)) {
+    case 8: return tma_ctas<8>(ntiles);
+    case 9: return tma_ctas<9>(ntiles);
+    case 10: return tma_ctas<10>(ntiles);
+    case 11: return tma_ctas<11>(ntiles);
+    case 12: return tma_ctas<12>(ntiles);
+    default: return 0;
+  }
+}
+
+// partial: [vdfdx_tma_parts(), batch*nx] zero-initialised by the caller (or null)
+int vdfdx_tma_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* v, double dt,
+                  const double* k1_batch, double k1, double* partial, cudaStream_t stream) {
+  const int logn = ilog2_exact_(nx);
+  CUtensorMap map;
+  const int box_rows = nx < 256 ? nx : 256;
+  int rc = encode_map(&map, fin, (long long)batch * nx, nv, box_rows);
+  if (rc != ADEPT_OK) return rc;
+  TmaPushArgs p = {};
+  p.fout = fout, p.batch = batch, p.nx = nx, p.nv = nv, p.ntiles = batch * (nv / 4);
+  p.v = v, p.k1_batch = k1_batch, p.k1 = k1, p.dt = dt, p.zero = 0, p.partial = partial;
+  p.tw = get_twiddles(logn);
+  if (!p.tw) return ADEPT_ERR_CUDA;
+  const int grid = vdfdx_tma_parts(batch, nx, nv);
+  switch (logn) {
+    case 8: return launch_tma<8>(map, p, grid, stream);
+    case 9: return launch_tma<9>(map, p, grid, stream);
+    case 10: return launch_tma<10>(map, p, grid, stream);
+    case 11: return launch_tma<11>(map, p, grid, stream);
+    case 12: return launch_tma<12>(map, p, grid, stream);
+    default:
+      set_last_error("vdfdx(tma): unsupported nx=%d", nx);
+      return ADEPT_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace adept

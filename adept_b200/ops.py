@@ -67,6 +67,40 @@ def vdfdx(f, v, dt, k1x, out=None, k1x_batch=None):
     return out
 
 
+def vdfdx_rho_parts(f) -> int:
+    """Rows of the partial-sum scratch that :func:`vdfdx_rho` needs for a distribution of this shape."""
+    b, nx, nv = _shape3(f)
+    return int(_lib.load().adept_b200_vdfdx_rho_parts(b, nx, nv))
+
+
+def vdfdx_rho(f, v, dt, k1x, parts, out=None, k1x_batch=None):
+    """x-advection fused with the first stage of the velocity sum of its result (vlasov.py:234-251 + field.py:197-208).
+
+    ``parts`` is a [nparts, batch*nx] scratch tensor (nparts >= vdfdx_rho_parts(f)); finish with :func:`reduce_parts`."""
+    b, nx, nv = _shape3(f)
+    out = torch.empty_like(f) if out is None else out
+    rc = _lib.load().adept_b200_vdfdx_rho_f64(
+        _ptr(f, "f"), _ptr(out, "out"), b, nx, nv, _ptr(v, "v"), float(dt), float(k1x),
+        _ptr(k1x_batch, "k1x_batch", True), _ptr(parts, "parts"), int(parts.shape[0]), _stream(),
+    )
+    _lib.check(rc, "vdfdx_rho")
+    _count(2)
+    return out
+
+
+def reduce_parts(parts, scale_a, scale_b=1.0, base=None, out=None):
+    """out = base + scale_b * ((sum_p parts[p]) * scale_a), fixed summation order."""
+    n = parts.shape[1]
+    out = torch.empty(n, dtype=torch.float64, device=parts.device) if out is None else out
+    rc = _lib.load().adept_b200_reduce_parts_f64(
+        _ptr(parts, "parts"), int(parts.shape[0]), n, float(scale_a), float(scale_b), _ptr(base, "base", True),
+        _ptr(out, "out"), _stream(),
+    )
+    _lib.check(rc, "reduce_parts")
+    _count()
+    return out
+
+
 def edfdv_exp(f, e, pond, q, m, dt, k1v, dex=None, out=None):
     """Spectral v-advection (VelocityExponential, vlasov.py:74-91); e := e + dex inside the kernel."""
     b, nx, nv = _shape3(f)

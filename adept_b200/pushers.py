@@ -63,6 +63,7 @@ class SpaceExponential:
         self.species_grids = species_grids
         self.parallel = parallel
         self._cache = _DeviceCache()
+        self._parts = {}
 
     def push(self, f, v, dt, out=None):
         return ops.vdfdx(f, v, dt, self.k1x, out=out)
@@ -73,6 +74,22 @@ class SpaceExponential:
             v = self._cache.get(name, self.species_grids[name]["v"], f.device)
             result[name] = self.push(f, v, float(dt), None if out is None else out.get(name))
         return result
+
+    def push_with_rho(self, f_dict, dt, out=None):
+        """Same push, fused with the first stage of the velocity sum of the result: returns (f_dict, parts_dict) where
+        parts_dict[name] is the per-CTA partial-sum scratch that ``ElectricFieldSolver(..., rho_parts=...)`` finishes
+        (SpaceExponential followed by compute_charge_density, vlasov.py:234-251 + field.py:197-208)."""
+        result, parts = {}, {}
+        for name, f in f_dict.items():
+            v = self._cache.get(name, self.species_grids[name]["v"], f.device)
+            key = (name, tuple(f.shape), str(f.device))
+            if key not in self._parts:
+                n = f.numel() // f.shape[-1]
+                self._parts[key] = torch.empty((ops.vdfdx_rho_parts(f), n), dtype=torch.float64, device=f.device)
+            parts[name] = self._parts[key]
+            result[name] = ops.vdfdx_rho(f, v, float(dt), self.k1x, parts[name],
+                                         out=None if out is None else out.get(name))
+        return result, parts
 
 
 class _VelocityPusher:
@@ -146,8 +163,11 @@ class ElectricFieldSolver:
         self.dx = float(grid.dx)
         self._cache = _DeviceCache()
 
-    def compute_charge_density(self, f_dict, out=None):
-        """rho = sum_s q_s dv_s sum_v f_s (+ static ion background); field.py:186-208."""
+    def compute_charge_density(self, f_dict, out=None, rho_parts=None):
+        """rho = sum_s q_s dv_s sum_v f_s (+ static ion background); field.py:186-208.
+
+        ``rho_parts`` (from ``SpaceExponential.push_with_rho``) supplies the velocity sums already accumulated by the
+        x-push kernel, so f is not read again."""
         dev = _device_of(f_dict)
         rho = None
         if self.static_charge_density is not None and self.kind == "poisson":
@@ -158,7 +178,11 @@ class ElectricFieldSolver:
         for name, f in f_dict.items():
             q, dv = self.species_params[name]["charge"], float(self.species_grids[name]["dv"])
             new = torch.empty(f.shape[:-1], dtype=torch.float64, device=dev) if out is None else out
-            ops.moments(f, None, dv, (new, None, None), bases=(rho, None, None), scale_b=(q, 1.0, 1.0))
+            if rho_parts is not None:
+                ops.reduce_parts(rho_parts[name], dv, q, base=None if rho is None else rho.reshape(-1),
+                                 out=new.reshape(-1))
+            else:
+                ops.moments(f, None, dv, (new, None, None), bases=(rho, None, None), scale_b=(q, 1.0, 1.0))
             rho = new
         return rho
 
@@ -174,13 +198,18 @@ class ElectricFieldSolver:
             j = new
         return j
 
-    def __call__(self, f_dict, a, prev_ex, dt):
+    @property
+    def wants_rho(self):
+        """True when the field solve consumes the charge density (so the x-push should accumulate it)."""
+        return self.kind != "ampere"
+
+    def __call__(self, f_dict, a, prev_ex, dt, rho_parts=None):
         dev = _device_of(f_dict)
         pond = ops.ponderomotive(a, self.dx)
         if self.kind == "ampere":
             e = ops.axpy(prev_ex, self.compute_current_density(f_dict), -float(dt))
         else:
-            rho = self.compute_charge_density(f_dict)
+            rho = self.compute_charge_density(f_dict, rho_parts=rho_parts)
             kmul = self._cache.get("kmul", self.kmul, dev)
             if self.mode == 0:
                 e = ops.poisson(rho, kmul)

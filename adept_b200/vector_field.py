@@ -50,9 +50,14 @@ class LeapfrogIntegrator(TimeIntegrator):
         self.dt_array = self.dt * np.array([0.0, 1.0])
 
     def __call__(self, f_dict, a, dex_array, prev_ex):
-        f_after_v = self.vdfdx(f_dict, dt=self.dt)
-        f_for_field = f_dict if self.field_solve.hampere else f_after_v
-        pond, e = self.field_solve(f_dict=f_for_field, a=a, prev_ex=prev_ex, dt=self.dt)
+        if self.field_solve.wants_rho and not self.field_solve.hampere:
+            # the x-push kernel accumulates sum_v f* on the fly: the field solve does not read f* again
+            f_after_v, parts = self.vdfdx.push_with_rho(f_dict, dt=self.dt)
+            pond, e = self.field_solve(f_dict=f_after_v, a=a, prev_ex=prev_ex, dt=self.dt, rho_parts=parts)
+        else:
+            f_after_v = self.vdfdx(f_dict, dt=self.dt)
+            f_for_field = f_dict if self.field_solve.hampere else f_after_v
+            pond, e = self.field_solve(f_dict=f_for_field, a=a, prev_ex=prev_ex, dt=self.dt)
         # e + dex[0] is formed inside the push kernel (same rounding as the reference's explicit sum)
         f_out = self.edfdv(f_after_v, e=e, pond=pond, dt=self.dt, dex=dex_array[0])
         return e, f_out
@@ -93,12 +98,16 @@ class SixthOrderHamIntegrator(TimeIntegrator):
     def __call__(self, f_dict, a, dex_array, prev_ex):
         Ds = (self.D1, self.D2, self.D3, self.D3, self.D2, self.D1)
         As = (self.a1, self.a2, self.a3, self.a2, self.a1)
-        e = None
+        e, parts = None, None
+        fuse = self.field_solve.wants_rho
         for i in range(6):
-            pond, e = self.field_solve(f_dict=f_dict, a=a, prev_ex=None, dt=None)
+            pond, e = self.field_solve(f_dict=f_dict, a=a, prev_ex=None, dt=None, rho_parts=parts)
             f_dict = self.edfdv(f_dict, e=e, pond=pond, dt=Ds[i] * self.dt, dex=dex_array[i])
             if i < 5:
-                f_dict = self.vdfdx(f_dict, dt=As[i] * self.dt)
+                if fuse:  # the next field solve's density comes out of this x-push
+                    f_dict, parts = self.vdfdx.push_with_rho(f_dict, dt=As[i] * self.dt)
+                else:
+                    f_dict = self.vdfdx(f_dict, dt=As[i] * self.dt)
         return e, f_dict
 
 

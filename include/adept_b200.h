@@ -56,6 +56,17 @@ int adept_b200_prepare(int n);
 int adept_b200_vdfdx_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* v, double dt,
                          double k1x, const double* k1x_batch, void* stream);
 
+/* x-advection fused with the velocity sum of the result (first stage of the charge density that the field solve
+ * needs right after the push: SpaceExponential + compute_charge_density, vlasov.py:234-251 + field.py:197-208).
+ * parts[nparts, batch*nx] receives per-CTA partial sums of sum_j f_out[b, i, j] (unscaled; rows beyond those used are
+ * zero); nparts >= adept_b200_vdfdx_rho_parts(batch, nx, nv).  adept_b200_reduce_parts_f64 finishes the reduction in a
+ * fixed order (deterministic): out[i] = (base ? base[i] : 0) + scale_b * ((sum_p parts[p, i]) * scale_a). */
+int adept_b200_vdfdx_rho_parts(int batch, int nx, int nv);
+int adept_b200_vdfdx_rho_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* v, double dt,
+                             double k1x, const double* k1x_batch, double* parts, int nparts, void* stream);
+int adept_b200_reduce_parts_f64(const double* parts, int nparts, long long n, double scale_a, double scale_b,
+                                const double* base, double* out, void* stream);
+
 /* v-advection (spectral): accel_i = (q (e_i + dex_i) + (q^2/m) pond_i)/m;
  * f_out = irfft(exp(-i kv_n dt accel_i) rfft(f_in, axis=v), axis=v).  e, dex, pond are [batch, nx]
  * (dex, pond nullable); k1v = kv_real[1] = 2 pi / (nv dv).  nv power of two (<= 8192), nx even.  In-place allowed. */

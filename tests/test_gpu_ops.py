@@ -78,6 +78,31 @@ def test_vdfdx_inplace_negative_dt_and_batch(ops):
     assert rel_l2(host(fd), np.stack(refs)) <= RTOL
 
 
+@pytest.mark.parametrize("B,nx,nv", [(1, 256, 64), (3, 512, 36), (1, 4096, 128), (2, 1024, 8), (2, 64, 32), (1, 32, 6)])
+def test_vdfdx_rho_fused_moment(ops, B, nx, nv):
+    """x-advection fused with the charge-density velocity sum (TMA path for nx >= 256 and nv % 4 == 0, else fallback)."""
+    fs, k1s, refs = [], [], []
+    for b in range(B):
+        f, x, v, dx, dv = make_f(nx, nv, seed=7 * b + nv, noise=0.02, xmax=20.0 + 2 * b)
+        kxr = np.fft.rfftfreq(nx, d=dx) * 2 * np.pi
+        fs.append(f)
+        k1s.append(kxr[1])
+        refs.append(O.space_exponential(f, kxr, v, 0.23))
+    fd = dev(np.stack(fs))
+    nparts = ops.vdfdx_rho_parts(fd)
+    parts = torch.full((nparts + 1, B * nx), 7.0, dtype=torch.float64, device="cuda")  # stale contents must not leak
+    out = ops.vdfdx_rho(fd, dev(v), 0.23, 0.0, parts, k1x_batch=dev(np.array(k1s)))
+    ref = np.stack(refs)
+    assert rel_l2(host(out), ref) <= RTOL
+    ion = np.linspace(0.9, 1.1, B * nx)
+    rho = host(ops.reduce_parts(parts, dv, -1.0, base=dev(ion)))
+    rho_ref = ion + -1.0 * (np.sum(ref, axis=-1).ravel() * dv)
+    np.testing.assert_allclose(rho, rho_ref, rtol=0, atol=1e-13 * np.max(np.abs(rho_ref)))
+    # in place, no moment: the plain entry point takes the same TMA path
+    ops.vdfdx(fd, dev(v), 0.23, 0.0, out=fd, k1x_batch=dev(np.array(k1s)))
+    assert rel_l2(host(fd), ref) <= RTOL
+
+
 def test_vdfdx_exact_characteristic_shift(ops):
     """reference test_multispecies_pushers.py:16-64 (sinusoid, nv=2 instead of 1: nv must be even)."""
     Lx = 2 * np.pi
