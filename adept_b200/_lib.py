@@ -15,11 +15,45 @@ LIB_PATH = _HERE / "libadept_b200.so"
 c_dp = C.c_void_p  # device pointers travel as integers
 c_i, c_d, c_ll = C.c_int, C.c_double, C.c_longlong
 
+MAX_SPECIES, MAX_DRIVERS, MAX_SUBSTEPS = 4, 8, 6
+
+
+class Species(C.Structure):
+    """struct adept_b200_species (include/adept_b200.h)."""
+
+    _fields_ = [("f_in", c_dp), ("f_out", c_dp), ("f_tmp", c_dp), ("v", c_dp), ("nv", c_i), ("dv", c_d), ("k1v", c_d),
+                ("charge", c_d), ("mass", c_d), ("rho_parts", c_dp), ("rho_nparts", c_i)]
+
+
+class Step(C.Structure):
+    """struct adept_b200_step (include/adept_b200.h); field order and types must match the header."""
+
+    _fields_ = [
+        ("batch", c_i), ("nx", c_i), ("n_species", c_i),
+        ("species", Species * MAX_SPECIES),
+        ("electron_species", c_i), ("collide_species", c_i), ("time_integrator", c_i), ("edfdv", c_i), ("field", c_i),
+        ("dt", c_d), ("dx", c_d), ("k1x", c_d),
+        ("k1x_batch", c_dp), ("ion_charge", c_dp), ("kmul", c_dp), ("kmul_stride", c_ll), ("Te", c_d),
+        ("lambda_De", c_d),
+        ("e_in", c_dp), ("e_out", c_dp), ("dex", c_dp), ("a", c_dp), ("prev_a", c_dp), ("djy", c_dp), ("a_out", c_dp),
+        ("c_light", c_d), ("wave_on", c_i),
+        ("pond", c_dp), ("rho", c_dp), ("ne_n", c_dp), ("ne_np1", c_dp),
+        ("n_ex", c_i), ("ex_space", c_dp), ("ex_kx", c_dp),
+        ("ex_w", c_d * MAX_DRIVERS), ("ex_a0", c_d * MAX_DRIVERS),
+        ("ex_tenv", (c_d * MAX_DRIVERS) * MAX_SUBSTEPS), ("ex_wt", (c_d * MAX_DRIVERS) * MAX_SUBSTEPS),
+        ("fp_on", c_i), ("krook_on", c_i), ("fp_model", c_i), ("fp_scheme", c_i), ("fp_nodrag", c_i),
+        ("sg_m", c_d), ("sg_ratio", c_d),
+        ("nu_fp_space", c_dp), ("nu_K_space", c_dp), ("nu_fp_time", c_d), ("nu_K_time", c_d), ("f_mx", c_dp),
+    ]
+
+
 # name -> argtypes; mirrors include/adept_b200.h one to one (checked by tests/test_abi.py)
 SIGNATURES = {
     "adept_b200_version": [],
     "adept_b200_last_error": [],
     "adept_b200_prepare": [c_i],
+    "adept_b200_profile": [c_i],
+    "adept_b200_profile_report": [C.c_char_p, c_i],
     "adept_b200_vdfdx_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_d, c_d, c_dp, c_dp],
     "adept_b200_vdfdx_rho_parts": [c_i, c_i, c_i],
     "adept_b200_vdfdx_rho_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_d, c_d, c_dp, c_dp, c_i, c_dp],
@@ -33,6 +67,7 @@ SIGNATURES = {
     "adept_b200_wave_step_f64": [c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_i, c_i, c_d, c_d, c_d, c_dp],
     "adept_b200_collide_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_d, c_d, c_dp, c_dp, c_dp, c_i, c_i, c_i, c_d, c_d,
                                c_dp, c_dp],
+    "adept_b200_step_f64": [C.POINTER(Step), c_dp],
 }
 
 

@@ -2,6 +2,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <string.h>
 
 #include <mutex>
 #include <vector>
@@ -27,6 +28,42 @@ int check_launch(const char* what) {
     return ADEPT_ERR_CUDA;
   }
   return ADEPT_OK;
+}
+
+// ---- per-kernel event timing --------------------------------------------------------------------------------------
+struct ProfileEntry {
+  const char* name;
+  cudaEvent_t e0, e1;
+};
+static std::mutex g_prof_mutex;
+static bool g_prof_on = false;
+static std::vector<ProfileEntry> g_prof;
+
+ProfileScope::ProfileScope(const char* name, cudaStream_t st) : slot(-1), stream(st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  ProfileEntry e = {name, nullptr, nullptr};
+  if (cudaEventCreate(&e.e0) != cudaSuccess || cudaEventCreate(&e.e1) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return;
+  }
+  cudaEventRecord(e.e0, st);
+  g_prof.push_back(e);
+  slot = (int)g_prof.size() - 1;
+}
+
+ProfileScope::~ProfileScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  if (slot < (int)g_prof.size()) cudaEventRecord(g_prof[slot].e1, stream);
+}
+
+static void profile_clear() {
+  for (auto& e : g_prof) {
+    cudaEventDestroy(e.e0);
+    cudaEventDestroy(e.e1);
+  }
+  g_prof.clear();
 }
 
 // ---- twiddle tables ------------------------------------------------------------------------------------------
@@ -101,7 +138,7 @@ int ponderomotive_f64(const double*, double*, int, int, double, cudaStream_t);
 int wave_step_f64(const double*, const double*, const double*, const double*, const double*, double*, int, int,
                   double, double, double, cudaStream_t);
 int collide_f64(const double*, double*, int, int, int, const double*, double, double, const double*, const double*,
-                const double*, int, int, int, double, double, double*, cudaStream_t);
+                const double*, int, int, int, double, double, double*, double, double, cudaStream_t);
 int reduce_parts_f64(const double*, int, long long, double, double, const double*, double*, cudaStream_t);
 bool vdfdx_tma_supported(const double*, const double*, int, int);
 int vdfdx_tma_parts(int, int, int);
@@ -123,6 +160,48 @@ extern "C" {
 int adept_b200_version(void) { return 100; }
 
 const char* adept_b200_last_error(void) { return g_err; }
+
+int adept_b200_profile(int enable) {
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  profile_clear();
+  g_prof_on = enable != 0;
+  return ADEPT_OK;
+}
+
+int adept_b200_profile_report(char* buf, int buflen) {
+  if (!buf || buflen < 1) {
+    set_last_error("profile_report: null / empty buffer");
+    return ADEPT_ERR_BAD_ARG;
+  }
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  struct Acc {
+    const char* name;
+    int count;
+    double ms;
+  };
+  std::vector<Acc> acc;
+  for (auto& e : g_prof) {
+    if (cudaEventSynchronize(e.e1) != cudaSuccess) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e.e0, e.e1) != cudaSuccess) continue;
+    bool found = false;
+    for (auto& a : acc)
+      if (a.name == e.name || !strcmp(a.name, e.name)) {
+        a.count++, a.ms += ms, found = true;
+        break;
+      }
+    if (!found) acc.push_back({e.name, 1, (double)ms});
+  }
+  (void)cudaGetLastError();
+  int off = 0;
+  buf[0] = 0;
+  for (auto& a : acc) {
+    const int w = snprintf(buf + off, (size_t)(buflen - off), "%s %d %.6f\n", a.name, a.count, a.ms);
+    if (w < 0 || w >= buflen - off) break;
+    off += w;
+  }
+  return ADEPT_OK;
+}
 
 int adept_b200_prepare(int n) {
   int logn = 0;
@@ -240,7 +319,7 @@ int adept_b200_collide_f64(const double* f_in, double* f_out, int batch, int nx,
                            int scheme, int nodrag, double sg_m, double sg_ratio, double* n_out, void* stream) {
   ADEPT_REQUIRE(f_in, "f_in") ADEPT_REQUIRE(f_out, "f_out") ADEPT_REQUIRE(v, "v")
   return collide_f64(f_in, f_out, batch, nx, nv, v, dv, dt, nu_fp, nu_K, f_mx, model, scheme, nodrag, sg_m, sg_ratio,
-                     n_out, (cudaStream_t)stream);
+                     n_out, 1.0, 1.0, (cudaStream_t)stream);
 }
 
 }  // extern "C"

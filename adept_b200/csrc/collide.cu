@@ -44,6 +44,7 @@ struct CollideArgs {
   double sg_m, sg_ratio;  // super-Gaussian exponent m and Gamma(3/m)/Gamma(1/m)
   double* n_out;          // [rows] or null: sum_j f_out dv
   int rows_per_cta;       // R: x-rows handled by one CTA (set by the launcher)
+  double nu_fp_scale, nu_K_scale;  // nu = scale * nu[row] (time envelope applied in the kernel)
 };
 
 // 1/x for |x| in the normal range: MUFU.RCP64H seed (about 20 bits) + two Newton steps -> rounding-level accuracy.
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(MAXT, MINB) collide_kernel(CollideArgs p) {
   const double vc = __ldg(p.v + i0);        // v of the chunk's first cell; v[i0 + l] = vc + l dv (uniform grid)
 
   if (p.nu_fp) {
-    const double nu = p.nu_fp[row];
+    const double nu = __dmul_rn(p.nu_fp_scale, p.nu_fp[row]);
     // ---- 2. moments in chunk-local index space: sum f, sum f l, sum f l^2 ------------------------------------------
     double mom[3] = {0.0, 0.0, 0.0};
 #pragma unroll
@@ -443,7 +444,7 @@ __global__ void __launch_bounds__(MAXT, MINB) collide_kernel(CollideArgs p) {
     row_reduce<1>(sn, red, parity, live ? r : 0, tt, T, RT, warp_mode, live);
     if (p.nu_K) {
       const double nprof = sn[0] * dv;
-      const double ex = exp(-(dt * p.nu_K[row]));
+      const double ex = exp(-(dt * __dmul_rn(p.nu_K_scale, p.nu_K[row])));
       double s2[1] = {0.0};
 #pragma unroll
       for (int l = 0; l < E; l++) {
@@ -503,6 +504,7 @@ static int launch_collide_t(CollideArgs p, cudaStream_t stream) {
     configured[dev] = smem;
   }
   const long long blocks = (p.rows + R - 1) / R;
+  ProfileScope prof("collide", stream);
   kern<<<(unsigned)blocks, threads, smem, stream>>>(p);
   return check_launch("collide_kernel");
 }
@@ -514,7 +516,8 @@ static int launch_collide(const CollideArgs& p, bool fast, cudaStream_t stream) 
 
 int collide_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* v, double dv, double dt,
                 const double* nu_fp, const double* nu_K, const double* f_mx, int model, int scheme, int nodrag,
-                double sg_m, double sg_ratio, double* n_out, cudaStream_t stream) {
+                double sg_m, double sg_ratio, double* n_out, double nu_fp_scale, double nu_K_scale,
+                cudaStream_t stream) {
   if (batch < 1 || nx < 1 || nv < 4) {
     set_last_error("collide: bad shape batch=%d nx=%d nv=%d", batch, nx, nv);
     return ADEPT_ERR_BAD_SHAPE;
@@ -528,7 +531,7 @@ int collide_f64(const double* fin, double* fout, int batch, int nx, int nv, cons
     return ADEPT_ERR_BAD_ARG;
   }
   CollideArgs p = {fin, fout, (long long)batch * nx, nv, v, dv, dt, nu_fp, nu_K, f_mx,
-                   model, scheme, nodrag, sg_m, sg_ratio, n_out, 1};
+                   model, scheme, nodrag, sg_m, sg_ratio, n_out, 1, nu_fp_scale, nu_K_scale};
   const bool fast = scheme == FP_CENTRAL && model != FP_SUPERGAUSSIAN && !nodrag;
   if (nv % 16 == 0 && nv / 16 <= 256) return launch_collide<16, 256, 2>(p, fast, stream);
   if (nv % 16 == 0 && nv / 16 <= 512) return launch_collide<16, 512, 1>(p, fast, stream);

@@ -42,6 +42,15 @@ enum {
 void set_last_error(const char* fmt, ...);
 int check_launch(const char* what);
 
+// Optional per-kernel timing (api.cu): when adept_b200_profile(1) is on, every launch site brackets its kernel with
+// CUDA events on the launching stream; adept_b200_profile_report() sums them per kernel name.  Off by default.
+struct ProfileScope {
+  ProfileScope(const char* name, cudaStream_t stream);
+  ~ProfileScope();
+  int slot;
+  cudaStream_t stream;
+};
+
 // twiddle-table cache (api.cu): per-pass Stockham tables for a complex FFT of length 2^logn on the current device
 const cplx* get_twiddles(int logn);
 

@@ -74,6 +74,7 @@ int poisson_f64(const double* rho, const double* kmul, long long kmul_stride, do
   }
   PoissonArgs p = {rho, kmul, kmul_stride, e, mode, Te, lambda_De, get_twiddles(logn), 0};
   if (!p.tw) return ADEPT_ERR_CUDA;
+  ProfileScope prof("poisson", stream);
   switch (logn) {
 #define ADEPT_CASE(L)                                                                              \
   case L:                                                                                          \
@@ -152,6 +153,7 @@ static int launch_poisson_big(const PoissonArgs& p, int batch, cudaStream_t stre
     }
     configured[dev] = true;
   }
+  ProfileScope prof("poisson", stream);
   poisson_kernel_big<LOGN><<<batch, FftCfg<LOGN>::T, smem, stream>>>(p);
   return check_launch("poisson_kernel_big");
 }
@@ -185,6 +187,7 @@ int ponderomotive_f64(const double* a, double* pond, int batch, int nx, double d
     return ADEPT_ERR_BAD_SHAPE;
   }
   const long long total = (long long)batch * nx;
+  ProfileScope prof("ponderomotive", stream);
   pond_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a, pond, nx, dx, total);
   return check_launch("pond_kernel");
 }
@@ -261,6 +264,7 @@ int wave_step_f64(const double* a, const double* aold, const double* djy, const 
   }
   WaveArgs p = {a, aold, djy, ne_n, ne_np1, a_new, nx, c, dx, dt};
   dim3 grid((nx + 2 + 255) / 256, batch);
+  ProfileScope prof("wave_step", stream);
   wave_kernel<<<grid, 256, 0, stream>>>(p);
   return check_launch("wave_kernel");
 }

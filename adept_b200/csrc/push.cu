@@ -168,6 +168,7 @@ static int launch_push(const PushArgs& p, cudaStream_t stream) {
     configured[dev] = true;
   }
   const long long blocks = (p.npairs + K::F - 1) / K::F;
+  ProfileScope prof(AXIS == AXIS_X ? "vdfdx" : "edfdv_exp", stream);
   kern<<<(unsigned)blocks, K::THREADS, K::SMEM, stream>>>(p);
   return check_launch("spectral_push_kernel");
 }

@@ -52,6 +52,7 @@ int edfdv_spline_f64(const double* fin, double* fout, int batch, int nx, int nv,
     set_last_error("edfdv_spline: in-place operation is not supported (f_in == f_out)");
     return ADEPT_ERR_BAD_ARG;
   }
+  ProfileScope prof("edfdv_spline", stream);
   spline_push_kernel<<<(unsigned)((long long)batch * nx), 256, 0, stream>>>(fin, fout, nv, e, dex, pond, q, m, dt, dv);
   return check_launch("spline_push_kernel");
 }
@@ -132,6 +133,7 @@ int moments_f64(const double* f, int batch, int nx, int nv, const double* v, dou
   }
   const int wpb = 8;
   const long long blocks = (p.rows + wpb - 1) / wpb;
+  ProfileScope prof("moments", stream);
   moments_kernel<<<(unsigned)blocks, wpb * 32, 0, stream>>>(p);
   return check_launch("moments_kernel");
 }
@@ -145,6 +147,7 @@ __global__ void axpy_kernel(const double* __restrict__ a, const double* __restri
 
 int axpy_f64(const double* a, const double* b, double s, double* out, long long n, cudaStream_t stream) {
   if (n < 1) return ADEPT_OK;
+  ProfileScope prof("axpy", stream);
   axpy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(a, b, s, out, n);
   return check_launch("axpy_kernel");
 }
@@ -175,6 +178,7 @@ int reduce_parts_f64(const double* parts, int nparts, long long n, double scale_
     set_last_error("reduce_parts: bad shape nparts=%d n=%lld", nparts, n);
     return ADEPT_ERR_BAD_SHAPE;
   }
+  ProfileScope prof("reduce_parts", stream);
   reduce_parts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(parts, nparts, n, scale_a, scale_b, base, out);
   return check_launch("reduce_parts_kernel");
 }

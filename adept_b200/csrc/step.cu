@@ -1,0 +1,300 @@
+// adept_b200_step_f64: one whole vlasov-1d time step enqueued from native code (no host work between kernels).
+// Reference composition (file:line relative to /root/reference):
+//   VlasovMaxwell.__call__            adept/_vlasov1d/solvers/vector_field.py:308-361
+//   VlasovPoissonFokkerPlanck         vector_field.py:232-253
+//   LeapfrogIntegrator                vector_field.py:75-95
+//   SixthOrderHamIntegrator           vector_field.py:113-186
+//   LongitudinalElectricFieldDriver   adept/_vlasov1d/solvers/pushers/field.py:21-33
+#include "../../include/adept_b200.h"
+#include "common.cuh"
+
+namespace adept {
+
+int vdfdx_f64(const double*, double*, int, int, int, const double*, double, const double*, double, cudaStream_t);
+int edfdv_exp_f64(const double*, double*, int, int, int, const double*, const double*, const double*, double, double,
+                  double, double, cudaStream_t);
+int edfdv_spline_f64(const double*, double*, int, int, int, const double*, const double*, const double*, double,
+                     double, double, double, cudaStream_t);
+int moments_f64(const double*, int, int, int, const double*, double, const double* const*, double* const*,
+                const double*, cudaStream_t);
+int axpy_f64(const double*, const double*, double, double*, long long, cudaStream_t);
+int poisson_dispatch_f64(const double*, const double*, long long, double*, int, int, int, double, double,
+                         cudaStream_t);
+int ponderomotive_f64(const double*, double*, int, int, double, cudaStream_t);
+int wave_step_f64(const double*, const double*, const double*, const double*, const double*, double*, int, int,
+                  double, double, double, cudaStream_t);
+int collide_f64(const double*, double*, int, int, int, const double*, double, double, const double*, const double*,
+                const double*, int, int, int, double, double, double*, double, double, cudaStream_t);
+int reduce_parts_f64(const double*, int, long long, double, double, const double*, double*, cudaStream_t);
+bool vdfdx_tma_supported(const double*, const double*, int, int);
+int vdfdx_tma_parts(int, int, int);
+int vdfdx_tma_f64(const double*, double*, int, int, int, const double*, double, const double*, double, double*,
+                  cudaStream_t);
+
+// ---- Ex driver field at every substep time ---------------------------------------------------------------------
+struct DriverArgs {
+  int n_ex, n_sub;
+  long long n;  // batch * nx
+  const double* space;
+  const double* kx;
+  double* dex;
+  double w[ADEPT_B200_MAX_DRIVERS], a0[ADEPT_B200_MAX_DRIVERS];
+  double tenv[ADEPT_B200_MAX_SUBSTEPS][ADEPT_B200_MAX_DRIVERS];
+  double wt[ADEPT_B200_MAX_SUBSTEPS][ADEPT_B200_MAX_DRIVERS];
+};
+
+__global__ void __launch_bounds__(256) ex_driver_kernel(DriverArgs p) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  for (int s = 0; s < p.n_sub; s++) {
+    double total = 0.0;
+    for (int d = 0; d < p.n_ex; d++) {
+      // field.py:21-26: env(x, t) * (w0 + dw0) * a0 * sin(k0 x - (w0 + dw0) t), env = time_env * space_env
+      const double factor = __dmul_rn(p.tenv[s][d], p.space[d * p.n + i]);
+      const double amp = __dmul_rn(__dmul_rn(factor, p.w[d]), p.a0[d]);
+      total = __dadd_rn(total, __dmul_rn(amp, sin(__dsub_rn(p.kx[d * p.n + i], p.wt[s][d]))));
+    }
+    p.dex[(long long)s * p.n + i] = total;
+  }
+}
+
+#define ADEPT_TRY(expr)         \
+  do {                          \
+    const int rc_ = (expr);     \
+    if (rc_ != ADEPT_OK) return rc_; \
+  } while (0)
+
+namespace {
+
+struct StepCtx {
+  const adept_b200_step& s;
+  cudaStream_t st;
+  long long n;  // batch * nx
+  mutable bool have_parts[ADEPT_B200_MAX_SPECIES] = {false, false, false, false};  // set by the last push_x
+
+  // x-advection of every species, cur[k] -> dst[k]; accumulates the charge-density partial sums when `want_rho`
+  int push_x(const double* const* cur, double* const* dst, double dt, bool want_rho) const {
+    for (int k = 0; k < s.n_species; k++) {
+      const adept_b200_species& sp = s.species[k];
+      have_parts[k] = false;
+      if (want_rho && sp.rho_parts && vdfdx_tma_supported(cur[k], dst[k], s.nx, sp.nv) &&
+          sp.rho_nparts >= vdfdx_tma_parts(s.batch, s.nx, sp.nv)) {
+        cudaError_t err = cudaMemsetAsync(sp.rho_parts, 0, (size_t)sp.rho_nparts * n * sizeof(double), st);
+        if (err != cudaSuccess) {
+          set_last_error("step: cudaMemsetAsync(rho_parts): %s", cudaGetErrorString(err));
+          return ADEPT_ERR_CUDA;
+        }
+        ADEPT_TRY(vdfdx_tma_f64(cur[k], dst[k], s.batch, s.nx, sp.nv, sp.v, dt, s.k1x_batch, s.k1x, sp.rho_parts, st));
+        have_parts[k] = true;
+      } else if (vdfdx_tma_supported(cur[k], dst[k], s.nx, sp.nv)) {
+        ADEPT_TRY(vdfdx_tma_f64(cur[k], dst[k], s.batch, s.nx, sp.nv, sp.v, dt, s.k1x_batch, s.k1x, nullptr, st));
+      } else {
+        ADEPT_TRY(vdfdx_f64(cur[k], dst[k], s.batch, s.nx, sp.nv, sp.v, dt, s.k1x_batch, s.k1x, st));
+      }
+    }
+    return ADEPT_OK;
+  }
+
+  // (pond, e) = field_solve(f); field.py:479-497.  from_parts: the velocity sums come from the preceding push_x
+  int field_solve(const double* const* cur, bool from_parts, double dt) const {
+    ADEPT_TRY(ponderomotive_f64(s.a, s.pond, s.batch, s.nx, s.dx, st));
+    if (s.field == 2) {  // ampere: E = E_prev - dt * sum_s q_s dv_s sum_v v f_s   (field.py:330-354)
+      const double* base = nullptr;
+      for (int k = 0; k < s.n_species; k++) {
+        const adept_b200_species& sp = s.species[k];
+        const double* bases[3] = {nullptr, base, nullptr};
+        double* outs[3] = {nullptr, s.rho, nullptr};
+        const double scale_b[3] = {1.0, sp.charge, 1.0};
+        ADEPT_TRY(moments_f64(cur[k], s.batch, s.nx, sp.nv, sp.v, sp.dv, bases, outs, scale_b, st));
+        base = s.rho;
+      }
+      return axpy_f64(s.e_in, s.rho, -dt, s.e_out, n, st);
+    }
+    // rho = sum_s q_s dv_s sum_v f_s (+ static background for plain poisson); field.py:197-208
+    const double* base = (s.field == 0) ? s.ion_charge : nullptr;
+    for (int k = 0; k < s.n_species; k++) {
+      const adept_b200_species& sp = s.species[k];
+      if (from_parts && have_parts[k]) {
+        ADEPT_TRY(reduce_parts_f64(sp.rho_parts, sp.rho_nparts, n, sp.dv, sp.charge, base, s.rho, st));
+      } else {
+        const double* bases[3] = {base, nullptr, nullptr};
+        double* outs[3] = {s.rho, nullptr, nullptr};
+        const double scale_b[3] = {sp.charge, 1.0, 1.0};
+        ADEPT_TRY(moments_f64(cur[k], s.batch, s.nx, sp.nv, nullptr, sp.dv, bases, outs, scale_b, st));
+      }
+      base = s.rho;
+    }
+    return poisson_dispatch_f64(s.rho, s.kmul, s.kmul_stride, s.e_out, s.batch, s.nx, s.field == 1 ? 1 : 0, s.Te,
+                                s.lambda_De, st);
+  }
+
+  // v-advection of every species cur[k] -> dst[k] under e_out + dex[sub] and pond
+  int push_v(const double* const* cur, double* const* dst, double dt, int sub) const {
+    const double* dex = s.dex + (long long)sub * n;
+    for (int k = 0; k < s.n_species; k++) {
+      const adept_b200_species& sp = s.species[k];
+      if (s.edfdv == 0)
+        ADEPT_TRY(edfdv_exp_f64(cur[k], dst[k], s.batch, s.nx, sp.nv, s.e_out, dex, s.pond, sp.charge, sp.mass, dt,
+                                sp.k1v, st));
+      else
+        ADEPT_TRY(edfdv_spline_f64(cur[k], dst[k], s.batch, s.nx, sp.nv, s.e_out, dex, s.pond, sp.charge, sp.mass, dt,
+                                   sp.dv, st));
+    }
+    return ADEPT_OK;
+  }
+
+  int electron_density(const double* f, double* out) const {  // vector_field.py:297-306
+    const adept_b200_species& sp = s.species[s.electron_species];
+    double* outs[3] = {out, nullptr, nullptr};
+    const double scale_b[3] = {sp.charge, 1.0, 1.0};
+    return moments_f64(f, s.batch, s.nx, sp.nv, nullptr, sp.dv, nullptr, outs, scale_b, st);
+  }
+};
+
+}  // namespace
+
+static int validate(const adept_b200_step& s) {
+  if (s.batch < 1 || s.nx < 2 || s.n_species < 1 || s.n_species > ADEPT_B200_MAX_SPECIES) {
+    set_last_error("step: bad shape batch=%d nx=%d n_species=%d", s.batch, s.nx, s.n_species);
+    return ADEPT_ERR_BAD_SHAPE;
+  }
+  if (s.time_integrator < 0 || s.time_integrator > 1 || s.edfdv < 0 || s.edfdv > 1 || s.field < 0 || s.field > 2) {
+    set_last_error("step: unknown integrator=%d / edfdv=%d / field=%d", s.time_integrator, s.edfdv, s.field);
+    return ADEPT_ERR_BAD_ARG;
+  }
+  if (s.field == 2 && s.time_integrator != 0) {
+    set_last_error("step: ampere + sixth has not been implemented (vector_field.py:455-463)");
+    return ADEPT_ERR_UNSUPPORTED;
+  }
+  if (s.n_ex < 0 || s.n_ex > ADEPT_B200_MAX_DRIVERS) {
+    set_last_error("step: at most %d Ex drivers (got %d)", ADEPT_B200_MAX_DRIVERS, s.n_ex);
+    return ADEPT_ERR_UNSUPPORTED;
+  }
+  if (!s.e_out || !s.dex || !s.pond || !s.rho || !s.a || (s.field != 2 && !s.kmul) || (s.field == 2 && !s.e_in)) {
+    set_last_error("step: null field / scratch pointer");
+    return ADEPT_ERR_BAD_ARG;
+  }
+  if (s.n_ex > 0 && (!s.ex_space || !s.ex_kx)) {
+    set_last_error("step: Ex drivers need ex_space and ex_kx");
+    return ADEPT_ERR_BAD_ARG;
+  }
+  for (int k = 0; k < s.n_species; k++) {
+    const adept_b200_species& sp = s.species[k];
+    if (!sp.f_in || !sp.f_out || !sp.v || sp.f_in == sp.f_out || (s.edfdv == 1 && !sp.f_tmp)) {
+      set_last_error("step: species %d: null or aliased distribution buffers", k);
+      return ADEPT_ERR_BAD_ARG;
+    }
+  }
+  if ((s.fp_on || s.krook_on) && (s.collide_species < 0 || s.collide_species >= s.n_species)) {
+    set_last_error("step: collide_species=%d out of range", s.collide_species);
+    return ADEPT_ERR_BAD_ARG;
+  }
+  if ((s.fp_on && !s.nu_fp_space) || (s.krook_on && (!s.nu_K_space || !s.f_mx))) {
+    set_last_error("step: collision operators need their nu profile (and f_mx for Krook)");
+    return ADEPT_ERR_BAD_ARG;
+  }
+  if (s.wave_on && (!s.prev_a || !s.djy || !s.a_out || (s.electron_species >= 0 && (!s.ne_n || !s.ne_np1)))) {
+    set_last_error("step: wave_on needs prev_a, djy, a_out and the ne_n / ne_np1 scratch");
+    return ADEPT_ERR_BAD_ARG;
+  }
+  return ADEPT_OK;
+}
+
+int step_f64(const adept_b200_step& s, cudaStream_t st) {
+  ADEPT_TRY(validate(s));
+  StepCtx c{s, st, (long long)s.batch * s.nx};
+  const int n_sub = s.time_integrator == 0 ? 1 : ADEPT_B200_MAX_SUBSTEPS;
+
+  // drivers at the substep times (vector_field.py:319)
+  {
+    DriverArgs d = {};
+    d.n_ex = s.n_ex, d.n_sub = n_sub, d.n = c.n, d.space = s.ex_space, d.kx = s.ex_kx, d.dex = s.dex;
+    for (int k = 0; k < ADEPT_B200_MAX_DRIVERS; k++) {
+      d.w[k] = s.ex_w[k], d.a0[k] = s.ex_a0[k];
+      for (int j = 0; j < ADEPT_B200_MAX_SUBSTEPS; j++) d.tenv[j][k] = s.ex_tenv[j][k], d.wt[j][k] = s.ex_wt[j][k];
+    }
+    ProfileScope prof("ex_driver", st);
+    ex_driver_kernel<<<(unsigned)((c.n + 255) / 256), 256, 0, st>>>(d);
+    ADEPT_TRY(check_launch("ex_driver_kernel"));
+  }
+
+  const bool wave = s.wave_on != 0;
+  const bool wave_density = wave && s.electron_species >= 0;
+  if (wave_density) ADEPT_TRY(c.electron_density(s.species[s.electron_species].f_in, s.ne_n));  // vector_field.py:336
+
+  const double* cur[ADEPT_B200_MAX_SPECIES];
+  double* out[ADEPT_B200_MAX_SPECIES];
+  double* tmp[ADEPT_B200_MAX_SPECIES];
+  for (int k = 0; k < s.n_species; k++) cur[k] = s.species[k].f_in, out[k] = s.species[k].f_out, tmp[k] = s.species[k].f_tmp;
+  const bool spline = s.edfdv == 1;
+
+  if (s.time_integrator == 0) {
+    // leapfrog (vector_field.py:87-95): f* = vdfdx(f); (pond, e) = field(f*); f' = edfdv(f*, e + dex[0], pond)
+    const bool want_rho = s.field != 2;
+    double* const* xdst = spline ? tmp : out;  // the cubic stencil cannot run in place
+    ADEPT_TRY(c.push_x(cur, xdst, s.dt, want_rho));
+    const double* fstar[ADEPT_B200_MAX_SPECIES];
+    for (int k = 0; k < s.n_species; k++) fstar[k] = xdst[k];
+    ADEPT_TRY(c.field_solve(fstar, want_rho, s.dt));
+    ADEPT_TRY(c.push_v(fstar, out, s.dt, 0));
+  } else {
+    // sixth-order Hamiltonian splitting (vector_field.py:118-186)
+    const double dt = s.dt;
+    const double a1 = 0.168735950563437422448196, a2 = 0.377851589220928303880766, a3 = -0.093175079568731452657924;
+    const double b1 = 0.049086460976116245491441, b2 = 0.264177609888976700200146, b3 = 0.186735929134907054308413;
+    const double c1 = -0.000069728715055305084099, c2 = -0.000625704827430047189169, c3 = -0.002213085124045325561636;
+    const double d2 = -2.916600457689847816445691e-6, d3 = 3.048480261700038788680723e-5;
+    const double e3 = 4.985549387875068121593988e-7;
+    const double D1 = b1 + 2.0 * c1 * pow(dt, 2.0);
+    const double D2 = b2 + 2.0 * c2 * pow(dt, 2.0) + 4.0 * d2 * pow(dt, 4.0);
+    const double D3 = b3 + 2.0 * c3 * pow(dt, 2.0) + 4.0 * d3 * pow(dt, 4.0) - 8.0 * e3 * pow(dt, 6.0);
+    const double Ds[6] = {D1, D2, D3, D3, D2, D1};
+    const double As[5] = {a1, a2, a3, a2, a1};
+    bool from_parts = false;
+    for (int i = 0; i < 6; i++) {
+      ADEPT_TRY(c.field_solve(cur, from_parts, dt));
+      // destination of this v-push: exponential runs in place after the first hop; the spline alternates tmp / out
+      // starting with tmp so that the sixth hop lands in f_out
+      double* dst[ADEPT_B200_MAX_SPECIES];
+      for (int k = 0; k < s.n_species; k++) {
+        if (spline)
+          dst[k] = (cur[k] == tmp[k]) ? out[k] : tmp[k];
+        else
+          dst[k] = out[k];
+      }
+      ADEPT_TRY(c.push_v(cur, dst, Ds[i] * dt, i));
+      for (int k = 0; k < s.n_species; k++) cur[k] = dst[k];
+      if (i < 5) {
+        double* same[ADEPT_B200_MAX_SPECIES];
+        for (int k = 0; k < s.n_species; k++) same[k] = const_cast<double*>(cur[k]);
+        ADEPT_TRY(c.push_x(cur, same, As[i] * dt, true));  // in place; its density feeds the next field solve
+        from_parts = true;
+      }
+    }
+  }
+
+  // collisions on the reference species, in place (vector_field.py:238)
+  if (s.fp_on || s.krook_on) {
+    const adept_b200_species& sp = s.species[s.collide_species];
+    ADEPT_TRY(collide_f64(sp.f_out, sp.f_out, s.batch, s.nx, sp.nv, sp.v, sp.dv, s.dt, s.fp_on ? s.nu_fp_space : nullptr,
+                          s.krook_on ? s.nu_K_space : nullptr, s.f_mx, s.fp_model, s.fp_scheme, s.fp_nodrag, s.sg_m,
+                          s.sg_ratio, nullptr, s.nu_fp_time, s.nu_K_time, st));
+  }
+
+  if (wave) {  // vector_field.py:340-347
+    if (wave_density) ADEPT_TRY(c.electron_density(s.species[s.electron_species].f_out, s.ne_np1));
+    ADEPT_TRY(wave_step_f64(s.a, s.prev_a, s.djy, wave_density ? s.ne_n : nullptr, wave_density ? s.ne_np1 : nullptr,
+                            s.a_out, s.batch, s.nx, s.c_light, s.dx, s.dt, st));
+  }
+  return ADEPT_OK;
+}
+
+}  // namespace adept
+
+extern "C" int adept_b200_step_f64(const adept_b200_step* step, void* stream) {
+  if (!step) {
+    adept::set_last_error("adept_b200_step_f64: null step descriptor");
+    return adept::ADEPT_ERR_BAD_ARG;
+  }
+  return adept::step_f64(*step, (cudaStream_t)stream);
+}

@@ -241,6 +241,7 @@ static int launch_tma(const CUtensorMap& map, TmaPushArgs p, int grid, cudaStrea
     }
     configured[dev] = true;
   }
+  ProfileScope prof("vdfdx_tma", stream);
   kern<<<grid, K::THREADS, K::SMEM, stream>>>(map, p);
   return check_launch("vdfdx_tma_kernel");
 }

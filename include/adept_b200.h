@@ -13,6 +13,7 @@
  *   adept_b200_ponderomotive_f64 ElectricFieldSolver (pond)          adept/_vlasov1d/solvers/pushers/field.py:495
  *   adept_b200_wave_step_f64     WaveSolver.__call__                 adept/_vlasov1d/solvers/pushers/field.py:109-157
  *   adept_b200_collide_f64       Collisions._apply_collisions+Krook  adept/_vlasov1d/solvers/pushers/fokker_planck.py:368-484
+ *   adept_b200_step_f64          VlasovMaxwell.__call__ (whole step) adept/_vlasov1d/solvers/vector_field.py:55-361
  *
  * Conventions
  *   - All pointers are DEVICE pointers (cudaMalloc / XLA buffers) unless the name ends in `_host`.
@@ -46,6 +47,12 @@ extern "C" {
 
 int adept_b200_version(void);
 const char* adept_b200_last_error(void);
+
+/* Per-kernel timing with CUDA events on the launching stream.  adept_b200_profile(1) clears the record and starts
+ * bracketing every kernel launch of the library; adept_b200_profile(0) stops and clears.  adept_b200_profile_report
+ * synchronises on the recorded events and writes one line per kernel, "<name> <launches> <total_ms>\n", into buf. */
+int adept_b200_profile(int enable);
+int adept_b200_profile_report(char* buf, int buflen);
 
 /* Build (once per device) the twiddle tables for a transform length n = 2^k, 2 <= n <= 8192. */
 int adept_b200_prepare(int n);
@@ -113,6 +120,70 @@ int adept_b200_wave_step_f64(const double* a, const double* aold, const double* 
 int adept_b200_collide_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* v, double dv,
                            double dt, const double* nu_fp, const double* nu_K, const double* f_mx, int model,
                            int scheme, int nodrag, double sg_m, double sg_ratio, double* n_out, void* stream);
+
+/* ---- whole time step ------------------------------------------------------------------------------------------------
+ * adept_b200_step_f64 enqueues every kernel of one `vlasov-1d` step y -> y' on `stream` with no host work in between:
+ * it replaces VlasovMaxwell.__call__ and what it calls (adept/_vlasov1d/solvers/vector_field.py:55-95 LeapfrogIntegrator,
+ * :98-186 SixthOrderHamIntegrator, :232-253 VlasovPoissonFokkerPlanck, :308-361 VlasovMaxwell).  The caller evaluates
+ * the O(1) time factors of the drivers and collision profiles for this step on the host (the reference evaluates the
+ * same closed forms inside its jitted loop, field.py:21-33, functions.py:72-80,112-118) and passes them by value; all
+ * O(nx) work runs on the device.  All per-row arrays are [batch*nx]; every pointer is a device pointer. */
+#define ADEPT_B200_MAX_SPECIES 4
+#define ADEPT_B200_MAX_DRIVERS 8
+#define ADEPT_B200_MAX_SUBSTEPS 6
+
+typedef struct adept_b200_species {
+  const double* f_in; /* [batch, nx, nv] distribution at t_n (not modified) */
+  double* f_out;      /* [batch, nx, nv] distribution at t_{n+1}; must not alias f_in */
+  double* f_tmp;      /* [batch, nx, nv] scratch, required for edfdv = cubic-spline (else may be null) */
+  const double* v;    /* [nv] */
+  int nv;
+  double dv, k1v, charge, mass;
+  double* rho_parts; /* [rho_nparts, batch*nx] scratch for the fused charge density (adept_b200_vdfdx_rho_parts) */
+  int rho_nparts;
+} adept_b200_species;
+
+typedef struct adept_b200_step {
+  int batch, nx, n_species;
+  adept_b200_species species[ADEPT_B200_MAX_SPECIES];
+  int electron_species;    /* index of the species named "electron" (wave-equation density), -1 if none */
+  int collide_species;     /* index of the species the collision operators act on (reference species) */
+  int time_integrator;     /* 0 leapfrog, 1 sixth-order Hamiltonian splitting */
+  int edfdv;               /* 0 exponential (spectral), 1 cubic-spline */
+  int field;               /* 0 poisson, 1 poisson-boltzmann, 2 ampere */
+  double dt, dx, k1x;
+  const double* k1x_batch; /* [batch] per-member 2 pi / (nx dx), nullable */
+  const double* ion_charge; /* [batch*nx] static background added to rho (poisson only), nullable */
+  const double* kmul;       /* poisson: one_over_kx; poisson-boltzmann: kx ([nx], or per member with kmul_stride = nx) */
+  long long kmul_stride;
+  double Te, lambda_De;
+  const double* e_in; /* [batch*nx] E at t_n (ampere) */
+  double* e_out;      /* [batch*nx] */
+  double* dex;        /* [n_substeps, batch*nx] driver field at the substep times (output: the saved `de` is a row) */
+  const double* a;    /* [batch, nx+2] */
+  const double* prev_a;
+  const double* djy;  /* [batch, nx+2] transverse current source at t + dt_array[1] */
+  double* a_out;      /* [batch, nx+2]; only written when wave_on */
+  double c_light;
+  int wave_on;        /* 0: a == prev_a == 0 and no Ey driver -> the wave update is the identity and is skipped */
+  double *pond, *rho, *ne_n, *ne_np1; /* [batch*nx] scratch (ne_* only when wave_on) */
+  /* longitudinal drivers: dex[s, i] = sum_d ((tenv[s][d] * space[d, i]) * w[d]) * a0[d] * sin(kx[d, i] - wt[s][d]) */
+  int n_ex;
+  const double* ex_space; /* [n_ex, batch*nx] spatial envelope */
+  const double* ex_kx;    /* [n_ex, batch*nx] k0 * x */
+  double ex_w[ADEPT_B200_MAX_DRIVERS], ex_a0[ADEPT_B200_MAX_DRIVERS];
+  double ex_tenv[ADEPT_B200_MAX_SUBSTEPS][ADEPT_B200_MAX_DRIVERS];
+  double ex_wt[ADEPT_B200_MAX_SUBSTEPS][ADEPT_B200_MAX_DRIVERS];
+  /* collisions (fokker_planck.py:272-484) */
+  int fp_on, krook_on, fp_model, fp_scheme, fp_nodrag;
+  double sg_m, sg_ratio;
+  const double* nu_fp_space; /* [batch*nx] */
+  const double* nu_K_space;  /* [batch*nx] */
+  double nu_fp_time, nu_K_time; /* nu(x, t) = time * space */
+  const double* f_mx;        /* [nv] Krook Maxwellian */
+} adept_b200_step;
+
+int adept_b200_step_f64(const adept_b200_step* step, void* stream);
 
 #ifdef __cplusplus
 }

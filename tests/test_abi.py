@@ -42,7 +42,7 @@ def test_signature_table_matches_header(lib):
         assert len(args) == len(_lib.SIGNATURES[name]), (name, args)
         for a, ct in zip(args, _lib.SIGNATURES[name]):
             if "*" in a or a.startswith("void*"):
-                assert ct in (ctypes.c_void_p,) or ct.__name__.startswith("LP_"), (name, a, ct)
+                assert ct in (ctypes.c_void_p, ctypes.c_char_p) or ct.__name__.startswith("LP_"), (name, a, ct)
             elif a.startswith("double"):
                 assert ct is ctypes.c_double, (name, a)
             elif a.startswith("long long"):
@@ -74,3 +74,23 @@ def test_product_never_imports_oracle():
     for py in (ROOT / "adept_b200").rglob("*.py"):
         src = py.read_text()
         assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f"{py} imports the oracle"
+
+
+def test_step_struct_layout_matches_header(tmp_path):
+    """ctypes mirror of struct adept_b200_step == the C layout (compiled from include/adept_b200.h with gcc)."""
+    import subprocess
+
+    from adept_b200._lib import Species, Step
+
+    src = tmp_path / "layout.c"
+    fields = ["e_in", "dex", "a_out", "wave_on", "pond", "n_ex", "ex_w", "ex_tenv", "ex_wt", "fp_on", "sg_m",
+              "nu_fp_space", "nu_fp_time", "f_mx"]
+    prints = "".join(f'printf("%zu\\n", offsetof(adept_b200_step, {f}));' for f in fields)
+    src.write_text(f'#include <stdio.h>\n#include <stddef.h>\n#include "{ROOT}/include/adept_b200.h"\n'
+                   f'int main(void){{printf("%zu\\n%zu\\n", sizeof(adept_b200_step), sizeof(adept_b200_species));{prints}return 0;}}')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", str(src), "-o", str(exe)], check=True)
+    out = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert out[0] == ctypes.sizeof(Step) and out[1] == ctypes.sizeof(Species)
+    for f, off in zip(fields, out[2:]):
+        assert getattr(Step, f).offset == off, f
