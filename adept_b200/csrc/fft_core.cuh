@@ -232,6 +232,21 @@ struct FftPass {
   }
 };
 
+// Pull this thread's twiddles of every pass towards L1 (single-CTA kernels start with a cold table).
+template <int LOGN>
+__device__ __forceinline__ void fft_prefetch_twiddles(const cplx* tw, int t) {
+  using C = FftCfg<LOGN>;
+  if constexpr (C::NP16 >= 2) {
+#pragma unroll
+    for (int p = 1; p < C::NP16; p++) {
+      const int ns = C::ns(p);
+      const cplx* twp = tw + C::tw_off(p) + (t & (ns - 1));
+#pragma unroll
+      for (int r = 1; r < 16; r++) asm volatile("prefetch.global.L1 [%0];" ::"l"(twp + (r - 1) * ns));
+    }
+  }
+}
+
 // Forward complex FFT of the N points held as x[m] = z[t + T*m]; result X[t + T*m] in x[m].
 // All threads of the CTA must call this together (it uses __syncthreads()).
 template <int LOGN, int BS = 1>

@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(FftCfg<LOGN>::T) poisson_kernel(PoissonArgs p)
   const double* kmul = p.kmul + (long long)blockIdx.x * p.kmul_stride;
   double* eo = p.e + (long long)blockIdx.x * N;
 
+  fft_prefetch_twiddles<LOGN>(p.tw, tt);
   cplx x[E];
 #pragma unroll
   for (int m = 0; m < E; m++) x[m] = cmake(rho[tt + T * m], 0.0);
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(FftCfg<LOGN>::T) poisson_kernel_big(PoissonArg
   const double* rho = p.rho + (long long)blockIdx.x * N;
   const double* kmul = p.kmul + (long long)blockIdx.x * p.kmul_stride;
   double* eo = p.e + (long long)blockIdx.x * N;
+  fft_prefetch_twiddles<LOGN>(p.tw, t);
   cplx x[E];
 #pragma unroll
   for (int m = 0; m < E; m++) x[m] = cmake(rho[t + T * m], 0.0);

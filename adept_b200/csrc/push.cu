@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(PushCfg<LOGN, AXIS>::THREADS, (PushCfg<LOGN, A
 #pragma unroll
       for (int m = 0; m < E; m++) {
         const int e = t + T * m;
-        x[m] = cmake(a[e], bq[e]);
+        x[m] = cmake(__ldcs(a + e), __ldcs(bq + e));  // streaming: keep L1 for the twiddle table
       }
     } else {
 #pragma unroll
@@ -139,8 +139,8 @@ __global__ void __launch_bounds__(PushCfg<LOGN, AXIS>::THREADS, (PushCfg<LOGN, A
 #pragma unroll
       for (int m = 0; m < E; m++) {
         const int e = t + T * m;
-        a[e] = x[m].y;
-        bq[e] = x[m].x;
+        __stcs(a + e, x[m].y);
+        __stcs(bq + e, x[m].x);
       }
     } else {
 #pragma unroll

@@ -153,23 +153,30 @@ int axpy_f64(const double* a, const double* b, double s, double* out, long long 
 }
 
 // ---- second stage of the fused x-push charge density: out[i] = base[i] + scale_b * ((sum_p parts[p, i]) * scale_a) ----
+// 64 rows per CTA; the parts are dealt to 4 thread groups (p = g, g+4, ...), each with two running sums, and combined
+// in a fixed order: deterministic, and short dependent-load chains (nparts/8 per thread).
 __global__ void __launch_bounds__(256) reduce_parts_kernel(const double* __restrict__ parts, int nparts, long long n,
                                                            double scale_a, double scale_b,
                                                            const double* __restrict__ base, double* __restrict__ out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;  // fixed summation order: deterministic
-  int pidx = 0;
-  for (; pidx + 3 < nparts; pidx += 4) {
-    s0 += parts[(long long)pidx * n + i];
-    s1 += parts[(long long)(pidx + 1) * n + i];
-    s2 += parts[(long long)(pidx + 2) * n + i];
-    s3 += parts[(long long)(pidx + 3) * n + i];
+  __shared__ double sm[4][64];
+  const int r = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const long long i = (long long)blockIdx.x * 64 + r;
+  double s0 = 0.0, s1 = 0.0;
+  if (i < n) {
+    int pidx = g;
+    for (; pidx + 4 < nparts; pidx += 8) {
+      s0 += parts[(long long)pidx * n + i];
+      s1 += parts[(long long)(pidx + 4) * n + i];
+    }
+    if (pidx < nparts) s0 += parts[(long long)pidx * n + i];
   }
-  for (; pidx < nparts; pidx++) s0 += parts[(long long)pidx * n + i];
-  const double s = (s0 + s1) + (s2 + s3);
-  const double term = __dmul_rn(scale_b, __dmul_rn(s, scale_a));
-  out[i] = base ? __dadd_rn(base[i], term) : term;
+  sm[g][r] = s0 + s1;
+  __syncthreads();
+  if (g == 0 && i < n) {
+    const double s = (sm[0][r] + sm[1][r]) + (sm[2][r] + sm[3][r]);
+    const double term = __dmul_rn(scale_b, __dmul_rn(s, scale_a));
+    out[i] = base ? __dadd_rn(base[i], term) : term;
+  }
 }
 
 int reduce_parts_f64(const double* parts, int nparts, long long n, double scale_a, double scale_b, const double* base,
@@ -179,7 +186,7 @@ int reduce_parts_f64(const double* parts, int nparts, long long n, double scale_
     return ADEPT_ERR_BAD_SHAPE;
   }
   ProfileScope prof("reduce_parts", stream);
-  reduce_parts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(parts, nparts, n, scale_a, scale_b, base, out);
+  reduce_parts_kernel<<<(unsigned)((n + 63) / 64), 256, 0, stream>>>(parts, nparts, n, scale_a, scale_b, base, out);
   return check_launch("reduce_parts_kernel");
 }
 

@@ -64,7 +64,7 @@ def workload_name(nx, nv):
 
 # ------------------------------------------------------------------------------------------------ clocks sampler
 class ClockSampler:
-    """Samples SM clock and throttle reasons through NVML (nvidia-ml-py) every 50 ms on a host thread while the timed
+    """Samples SM clock and throttle reasons through NVML (nvidia-ml-py) every 5 ms on a host thread while the timed
     region runs (nvidia-smi -lms block-buffers its pipe, so short runs would see no samples)."""
 
     REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
@@ -76,24 +76,33 @@ class ClockSampler:
         self._thread = None
         self.err = None
 
+    def _sample(self):
+        nv, h = self._nv, self._h
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+        try:
+            self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+        except Exception:  # older bindings
+            self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+
     def _run(self):
+        try:
+            while not self._stop.is_set():
+                self._sample()
+                self._stop.wait(0.005)
+        except Exception as exc:  # never fail the bench because of the sampler
+            self.err = repr(exc)
+
+    def start(self):
+        """NVML is initialised here (slow, ~0.1 s), outside the timed region; sampling then runs on a host thread."""
         try:
             import pynvml
 
             pynvml.nvmlInit()
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
-            while not self._stop.is_set():
-                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
-                try:
-                    self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
-                except Exception:  # older bindings
-                    self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
-                self._stop.wait(0.05)
-        except Exception as exc:  # no NVML: report it, never fail the bench
+            self._nv, self._h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception as exc:
             self.err = repr(exc)
-
-    def start(self):
+            return
         self._thread = threading.Thread(target=self._run, daemon=True)
         self._thread.start()
 
@@ -206,12 +215,14 @@ def run_b200(args):
         return float(tns.item())
 
     # ---- value: state resident in HBM; every kernel bracketed by CUDA events on the launching stream --------------
-    for _ in range(W):
-        sim.step()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(W):
+        sim.step()
+    barrier()
+    sampler.sm.clear()  # keep only samples taken during the timed region
+    sampler.mask = 0
     lib.adept_b200_profile(1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
