@@ -1,0 +1,199 @@
+"""Single oversized grid sharded over the GPUs of one node.
+
+Mirrors the reference's ``grid.parallel: ["x", "v"]`` decomposition (docs/source/solvers/vlasov1d/overview.md:155-177;
+shard_map call sites pushers/vlasov.py:95-101,245-248, fokker_planck.py:435-441): the x-advection runs on a v-sharded
+distribution ``f[nx, nv/P]`` (x-pencils are local), the v-advection and the collisions on an x-sharded one
+``f[nx/P, nv]`` (v-rows are local).  Where XLA inserts the collectives implicitly, they are explicit here:
+
+* ``all_reduce(SUM)`` of the nx-length partial velocity sums that the x-push kernel accumulates (32 KiB at nx=4096),
+  after which every rank solves the O(nx) field equation redundantly;
+* one ``all_to_all`` transpose v-sharded -> x-sharded before the v-push and one back after the collisions; each moves
+  ``nx nv 8 (P-1)/P^2`` bytes per rank.  The send side of the forward transpose and the receive side of the backward
+  one need no packing (row blocks of a v-shard are contiguous); the other two sides are one local permute-copy each.
+
+One process per GPU, ``torch.distributed`` (NCCL on the B200 box; the same code runs over gloo on CPU tensors when a
+CPU operator table is injected -- that is how tests/test_sharded.py covers the N > 1 logic without a GPU).  State between
+steps is kept v-sharded.  Scope: leapfrog, poisson, exponential or cubic-spline v-push, Fokker-Planck + Krook, no
+transverse wave (``a == 0``); anything else raises.  Requires ``nx % P == 0`` and every species' ``nv % P == 0``
+(overview.md:176-177).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ._lib import AdeptB200Error
+
+
+class CudaOps:
+    """Local operators backed by libadept_b200.so (the product path)."""
+
+    def __init__(self):
+        from . import ops
+
+        self.ops = ops
+        self._parts = {}
+
+    def vdfdx_rowsum(self, f, v, dt, k1x):
+        """(x-pushed f, sum over the local columns of the result [nx])."""
+        ops = self.ops
+        key = tuple(f.shape)
+        if key not in self._parts:
+            self._parts[key] = torch.empty((ops.vdfdx_rho_parts(f), f.shape[0]), dtype=torch.float64, device=f.device)
+        out = ops.vdfdx_rho(f, v, dt, k1x, self._parts[key])
+        return out, ops.reduce_parts(self._parts[key], 1.0, 1.0)
+
+    def rho_from_sum(self, total, dv, q, base):
+        return self.ops.reduce_parts(total.reshape(1, -1), dv, q, base=base)
+
+    def poisson(self, rho, one_over_kx):
+        return self.ops.poisson(rho, one_over_kx)
+
+    def edfdv(self, kind, f, e, dex, q, m, dt, k1v, dv):
+        if kind == "exponential":
+            return self.ops.edfdv_exp(f, e, None, q, m, dt, k1v, dex=dex)
+        return self.ops.edfdv_spline(f, e, None, q, m, dt, dv, dex=dex)
+
+    def collide(self, f, v, dv, dt, nu_fp, nu_K, f_mx, model, scheme, nodrag, sg_m, sg_ratio):
+        return self.ops.collide(f, v, dv, dt, nu_fp=nu_fp, nu_K=nu_K, f_mx=f_mx, model=model, scheme=scheme,
+                                nodrag=nodrag, sg_m=sg_m, sg_ratio=sg_ratio)
+
+
+class ShardedVlasov1D:
+    """``sim = ShardedVlasov1D(deck); sim.step()``; rank r owns velocity columns ``[r nv/P, (r+1) nv/P)``."""
+
+    def __init__(self, deck: dict, group=None, device=None, local_ops=None):
+        from .config import build_cfg
+        from .functions import SpaceTimeEnvelopeFunction
+        from .pushers import Collisions, EMDriver
+
+        if not dist.is_initialized():
+            raise AdeptB200Error("ShardedVlasov1D needs an initialised torch.distributed process group")
+        self.group = group
+        self.P, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if local_ops is None:
+            if not torch.cuda.is_available():
+                raise AdeptB200Error("adept_b200 needs a CUDA device: there is no CPU implementation of the time step")
+            local_ops = CudaOps()
+            device = device or torch.device("cuda", torch.cuda.current_device())
+        self.lops = local_ops
+        self.device = device or torch.device("cpu")
+        self.cfg, self.grid = build_cfg(deck)
+        cfg, t = self.cfg, self.cfg["terms"]
+        if t["time"] != "leapfrog" or t["field"] != "poisson":
+            raise NotImplementedError("sharded grid: only time=leapfrog with field=poisson is implemented")
+        if t["edfdv"] not in ("exponential", "cubic-spline"):
+            raise NotImplementedError(f"{t['edfdv']} has not been implemented")
+        if cfg["drivers"].get("ey") or cfg["diagnostics"].get("diag-vlasov-dfdt") or cfg["diagnostics"].get("diag-fp-dfdt"):
+            raise NotImplementedError("sharded grid: Ey drivers and dfdt diagnostics are not implemented")
+        g = cfg["grid"]
+        self.nx = int(g["nx"])
+        if self.nx % self.P:
+            raise AdeptB200Error(f"nx={self.nx} is not divisible by the number of ranks {self.P}")
+        self.nxp = self.nx // self.P
+        self.names = list(g["species_grids"].keys())
+        self.nvp = {}
+        for name in self.names:
+            nv = int(g["species_grids"][name]["nv"])
+            if nv % self.P:
+                raise AdeptB200Error(f"nv={nv} of species {name} is not divisible by the number of ranks {self.P}")
+            self.nvp[name] = nv // self.P
+        x = np.asarray(self.grid.x)
+        self.k1x = float(2 * np.pi * np.fft.rfftfreq(self.nx, d=float(x[1] - x[0]))[1])
+        dev = self.device
+        tt = lambda a: torch.as_tensor(np.array(a, dtype=np.float64), device=dev)  # noqa: E731
+        self.v_full = {n: tt(g["species_grids"][n]["v"]) for n in self.names}
+        self.v_loc = {n: self.v_full[n][self.rank * self.nvp[n]:(self.rank + 1) * self.nvp[n]].contiguous()
+                      for n in self.names}
+        self.one_over_kx = tt(self.grid.one_over_kx)
+        self.ion = None if g.get("ion_charge") is None else tt(g["ion_charge"])
+        c = 1.0 / g["beta"]
+        self.ex = [EMDriver.from_config(d, c) for d in cfg["drivers"].get("ex", {}).values()]
+        self.x = x
+        rows = slice(self.rank * self.nxp, (self.rank + 1) * self.nxp)
+        self.rows = rows
+        self.coll = Collisions(cfg)
+        self.fp_on, self.krook_on = bool(t["fokker_planck"]["is_on"]), bool(t["krook"]["is_on"])
+        self.nu_fp_prof = SpaceTimeEnvelopeFunction.from_config(t["fokker_planck"]) if self.fp_on else None
+        self.nu_K_prof = SpaceTimeEnvelopeFunction.from_config(t["krook"]) if self.krook_on else None
+        self.f_mx = tt(self.coll.f_mx)
+        # v-sharded initial state
+        self.state = {}
+        for n in self.names:
+            f0 = np.asarray(g["species_distributions"][n][1])
+            self.state[n] = tt(f0[:, self.rank * self.nvp[n]:(self.rank + 1) * self.nvp[n]])
+        self.state["e"] = torch.zeros(self.nx, dtype=torch.float64, device=dev)
+        self.state["de"] = torch.zeros(self.nx, dtype=torch.float64, device=dev)
+        self.t, self.step_index = 0.0, 0
+
+    # ---- layout changes -------------------------------------------------------------------------------------------
+    def to_x_sharded(self, f_vs):
+        """[nx, nv/P] (all x, my columns) -> [nx/P, nv] (my rows, all v): one all-to-all + local unpack."""
+        P, nxp, nvp = self.P, self.nxp, f_vs.shape[1]
+        recv = torch.empty((P, nxp, nvp), dtype=f_vs.dtype, device=f_vs.device)
+        dist.all_to_all_single(recv, f_vs.reshape(P, nxp, nvp), group=self.group)  # row blocks are contiguous
+        return recv.permute(1, 0, 2).reshape(nxp, P * nvp).contiguous()
+
+    def to_v_sharded(self, f_xs):
+        """[nx/P, nv] -> [nx, nv/P]: local pack + one all-to-all (the receive side is already in place)."""
+        P, nxp = self.P, self.nxp
+        nvp = f_xs.shape[1] // P
+        send = f_xs.reshape(nxp, P, nvp).permute(1, 0, 2).contiguous()
+        recv = torch.empty((P, nxp, nvp), dtype=f_xs.dtype, device=f_xs.device)
+        dist.all_to_all_single(recv, send, group=self.group)
+        return recv.reshape(P * nxp, nvp)
+
+    def gather_full(self, name):
+        """Full f[nx, nv] on every rank (diagnostics / tests)."""
+        parts = [torch.empty_like(self.state[name]) for _ in range(self.P)]
+        dist.all_gather(parts, self.state[name].contiguous(), group=self.group)
+        return torch.cat(parts, dim=1)
+
+    # ---- one leapfrog step (vector_field.py:87-95 + :232-253, collectives explicit) ----------------------------------
+    def _dex(self, t):
+        total = np.zeros_like(self.x)
+        for d in self.ex:
+            w = d.w0 + d.dw0
+            total += d.envelope(self.x, t) * w * d.a0 * np.sin(d.k0 * self.x - w * t)
+        return torch.as_tensor(total, device=self.device)
+
+    def step(self):
+        g, dt, t = self.cfg["grid"], float(self.grid.dt), self.t
+        lops = self.lops
+        dex = self._dex(t)
+        # 1. x-push on the v-shard; partial charge density of the result
+        rho = self.ion
+        fstar = {}
+        for n in self.names:
+            sg, sp = g["species_grids"][n], g["species_params"][n]
+            fstar[n], rowsum = lops.vdfdx_rowsum(self.state[n], self.v_loc[n], dt, self.k1x)
+            dist.all_reduce(rowsum, op=dist.ReduceOp.SUM, group=self.group)  # nx doubles
+            rho = lops.rho_from_sum(rowsum, float(sg["dv"]), float(sp["charge"]), rho)
+        # 2. field solve, replicated (O(nx))
+        e = lops.poisson(rho, self.one_over_kx)
+        e_loc, dex_loc = e[self.rows].contiguous(), dex[self.rows].contiguous()
+        # 3. transpose, v-push and collisions on my rows, transpose back
+        new = {}
+        for n in self.names:
+            sg, sp = g["species_grids"][n], g["species_params"][n]
+            rows = self.to_x_sharded(fstar[n])
+            rows = lops.edfdv(self.cfg["terms"]["edfdv"], rows, e_loc, dex_loc, float(sp["charge"]), float(sp["mass"]),
+                              dt, float(sg["kvr"][1]), float(sg["dv"]))
+            if n == self.coll.ref_species and (self.fp_on or self.krook_on):
+                xl = self.x[self.rows]
+                nu_fp = nu_K = None
+                if self.fp_on:
+                    nu_fp = torch.as_tensor(self.nu_fp_prof(xl, t) * np.ones_like(xl), device=self.device)
+                if self.krook_on:
+                    nu_K = torch.as_tensor(self.nu_K_prof(xl, t) * np.ones_like(xl), device=self.device)
+                c = self.coll
+                rows = lops.collide(rows, self.v_full[n], float(sg["dv"]), dt, nu_fp, nu_K, self.f_mx, c.model,
+                                    c.scheme, c.nodrag, c.m, c.sg_ratio)
+            new[n] = self.to_v_sharded(rows)
+        self.state.update(new)
+        self.state["e"], self.state["de"] = e, dex
+        self.step_index += 1
+        self.t = self.step_index * dt
+        return self.state
