@@ -55,6 +55,8 @@ SIGNATURES = {
     "adept_b200_profile": [c_i],
     "adept_b200_profile_report": [C.c_char_p, c_i],
     "adept_b200_vdfdx_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_d, c_d, c_dp, c_dp],
+    "adept_b200_save_moments_f64": [c_dp, c_dp, c_d, c_i, c_i, c_i, c_dp, c_d, c_dp, c_dp],
+    "adept_b200_filter_x_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_dp, c_dp],
     "adept_b200_vdfdx_rho_parts": [c_i, c_i, c_i],
     "adept_b200_vdfdx_rho_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_d, c_d, c_dp, c_dp, c_i, c_dp],
     "adept_b200_reduce_parts_f64": [c_dp, c_i, c_ll, c_d, c_d, c_dp, c_dp, c_dp],

@@ -48,7 +48,7 @@ def build(verbose: bool = False, force: bool = False) -> Path:
     nvcc = _nvcc()
     objdir = CSRC / "build"
     objdir.mkdir(exist_ok=True)
-    headers = list(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "adept_b200.h"]
+    headers = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [HERE.parent / "include" / "adept_b200.h"]
     extra = ["-Xptxas", "-v"] if verbose else []
 
     def compile_one(src: str):

@@ -9,6 +9,7 @@
 
 #include "../../include/adept_b200.h"
 #include "common.cuh"
+#include "internal.h"
 
 namespace adept {
 
@@ -123,28 +124,6 @@ const cplx* get_twiddles(int logn) {
   return d;
 }
 
-// implemented in push.cu / rowops.cu / field.cu / collide.cu
-int vdfdx_f64(const double*, double*, int, int, int, const double*, double, const double*, double, cudaStream_t);
-int edfdv_exp_f64(const double*, double*, int, int, int, const double*, const double*, const double*, double, double,
-                  double, double, cudaStream_t);
-int edfdv_spline_f64(const double*, double*, int, int, int, const double*, const double*, const double*, double,
-                     double, double, double, cudaStream_t);
-int moments_f64(const double*, int, int, int, const double*, double, const double* const*, double* const*,
-                const double*, cudaStream_t);
-int axpy_f64(const double*, const double*, double, double*, long long, cudaStream_t);
-int poisson_dispatch_f64(const double*, const double*, long long, double*, int, int, int, double, double,
-                         cudaStream_t);
-int ponderomotive_f64(const double*, double*, int, int, double, cudaStream_t);
-int wave_step_f64(const double*, const double*, const double*, const double*, const double*, double*, int, int,
-                  double, double, double, cudaStream_t);
-int collide_f64(const double*, double*, int, int, int, const double*, double, double, const double*, const double*,
-                const double*, int, int, int, double, double, double*, double, double, cudaStream_t);
-int reduce_parts_f64(const double*, int, long long, double, double, const double*, double*, cudaStream_t);
-bool vdfdx_tma_supported(const double*, const double*, int, int);
-int vdfdx_tma_parts(int, int, int);
-int vdfdx_tma_f64(const double*, double*, int, int, int, const double*, double, const double*, double, double*,
-                  cudaStream_t);
-
 }  // namespace adept
 
 using namespace adept;
@@ -223,6 +202,21 @@ int adept_b200_vdfdx_f64(const double* f_in, double* f_out, int batch, int nx, i
   if (batch >= 1 && vdfdx_tma_supported(f_in, f_out, nx, nv))
     return vdfdx_tma_f64(f_in, f_out, batch, nx, nv, v, dt, k1x_batch, k1x, nullptr, (cudaStream_t)stream);
   return vdfdx_f64(f_in, f_out, batch, nx, nv, v, dt, k1x_batch, k1x, (cudaStream_t)stream);
+}
+
+int adept_b200_save_moments_f64(const double* f0, const double* f1, double w, int batch, int nx, int nv,
+                                const double* v, double dv, double* out, void* stream) {
+  ADEPT_REQUIRE(f0, "f0") ADEPT_REQUIRE(v, "v") ADEPT_REQUIRE(out, "out")
+  return save_moments_f64(f0, f1, w, batch, nx, nv, v, dv, out, (cudaStream_t)stream);
+}
+
+int adept_b200_filter_x_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* filt,
+                            const double* zeros_v, void* stream) {
+  ADEPT_REQUIRE(f_in, "f_in") ADEPT_REQUIRE(f_out, "f_out") ADEPT_REQUIRE(filt, "filt") ADEPT_REQUIRE(zeros_v, "zeros_v")
+  // the x-advection kernels with zero advection speed (phase 1) and the real per-mode multiplier
+  if (batch >= 1 && vdfdx_tma_supported(f_in, f_out, nx, nv))
+    return vdfdx_tma_f64(f_in, f_out, batch, nx, nv, zeros_v, 0.0, nullptr, 0.0, nullptr, (cudaStream_t)stream, filt);
+  return vdfdx_f64(f_in, f_out, batch, nx, nv, zeros_v, 0.0, nullptr, 0.0, (cudaStream_t)stream, filt);
 }
 
 int adept_b200_vdfdx_rho_parts(int batch, int nx, int nv) {

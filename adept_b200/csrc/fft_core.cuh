@@ -194,6 +194,9 @@ struct FftPass {
         }
         dft4(x[c], x[c + 4], x[c + 8], x[c + 12]);
       }
+      // every read of buf by this thread is complete: the barrier that protects the exchange buffer goes here, so the
+      // second half of the butterfly overlaps (fp64 pipe) with the stores of the exchange (LSU pipe)
+      if constexpr (P < C::NPASS - 1) __syncthreads();
       dft16_finish(x);
     } else {
       if constexpr (P > 0) {
@@ -217,7 +220,7 @@ struct FftPass {
       }
     }
     if constexpr (P < C::NPASS - 1) {
-      __syncthreads();  // all reads of buf for this pass (and any earlier use) are done
+      if constexpr (R != 16) __syncthreads();  // all reads of buf for this pass (and any earlier use) are done
 #pragma unroll
       for (int q = 0; q < Q; q++) {
         const int b = t + T * q;

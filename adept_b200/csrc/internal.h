@@ -1,0 +1,35 @@
+// Internal C++ interface between the translation units of libadept_b200.so (kernel launchers).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace adept {
+
+int vdfdx_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* v, double dt,
+              const double* k1_batch, double k1, cudaStream_t stream, const double* filt = nullptr);
+int edfdv_exp_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* e, const double* dex,
+                  const double* pond, double q, double m, double dt, double k1, cudaStream_t stream);
+int edfdv_spline_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* e, const double* dex,
+                     const double* pond, double q, double m, double dt, double dv, cudaStream_t stream);
+int moments_f64(const double* f, int batch, int nx, int nv, const double* v, double scale_a, const double* const* base,
+                double* const* out, const double* scale_b, cudaStream_t stream);
+int axpy_f64(const double* a, const double* b, double s, double* out, long long n, cudaStream_t stream);
+int poisson_dispatch_f64(const double* rho, const double* kmul, long long kmul_stride, double* e, int batch, int nx,
+                         int mode, double Te, double lambda_De, cudaStream_t stream);
+int ponderomotive_f64(const double* a, double* pond, int batch, int nx, double dx, cudaStream_t stream);
+int wave_step_f64(const double* a, const double* aold, const double* djy, const double* ne_n, const double* ne_np1,
+                  double* a_new, int batch, int nx, double c, double dx, double dt, cudaStream_t stream);
+int collide_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* v, double dv, double dt,
+                const double* nu_fp, const double* nu_K, const double* f_mx, int model, int scheme, int nodrag,
+                double sg_m, double sg_ratio, double* n_out, double nu_fp_scale, double nu_K_scale,
+                cudaStream_t stream);
+int reduce_parts_f64(const double* parts, int nparts, long long n, double scale_a, double scale_b, const double* base,
+                     double* out, cudaStream_t stream);
+int save_moments_f64(const double* f0, const double* f1, double w, int batch, int nx, int nv, const double* v,
+                     double dv, double* out, cudaStream_t stream);
+bool vdfdx_tma_supported(const double* fin, const double* fout, int nx, int nv);
+int vdfdx_tma_parts(int batch, int nx, int nv);
+int vdfdx_tma_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* v, double dt,
+                  const double* k1_batch, double k1, double* partial, cudaStream_t stream,
+                  const double* filt = nullptr);
+
+}  // namespace adept

@@ -44,6 +44,7 @@ struct PushArgs {
   double q, m;
   const cplx* tw;
   int zero;  // always 0; opaque to ptxas (see FftPass)
+  const double* filt;  // nullable [N/2+1]: real multiplier per mode (Hou-Li filter)
 };
 
 template <int LOGN, int AXIS>
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(PushCfg<LOGN, AXIS>::THREADS, (PushCfg<LOGN, A
 
   fft_forward<LOGN>(x, buf, p.tw, t, p.zero);
 
-  half_spectrum_update<LOGN, 1>(x, buf, ph, t);
+  half_spectrum_update<LOGN, 1>(x, buf, ph, t, p.filt);
 
   fft_forward<LOGN>(x, buf, p.tw + p.zero, t, p.zero);  // opaque offset: no CSE of twiddle loads with the first FFT
 
@@ -207,7 +208,7 @@ static int ilog2_exact(int n) {
 }
 
 int vdfdx_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* v, double dt,
-              const double* k1_batch, double k1, cudaStream_t stream) {
+              const double* k1_batch, double k1, cudaStream_t stream, const double* filt) {
   if (batch < 1 || nx < 2 || nv < 2 || (nv & 1)) {
     set_last_error("vdfdx: bad shape batch=%d nx=%d nv=%d (nv must be even)", batch, nx, nv);
     return ADEPT_ERR_BAD_SHAPE;
@@ -224,7 +225,7 @@ int vdfdx_f64(const double* fin, double* fout, int batch, int nx, int nv, const 
   PushArgs p = {};
   p.fin = fin, p.fout = fout, p.batch = batch, p.nx = nx, p.nv = nv;
   p.npairs = (long long)batch * (nv / 2);
-  p.v = v, p.k1_batch = k1_batch, p.k1 = k1, p.dt = dt;
+  p.v = v, p.k1_batch = k1_batch, p.k1 = k1, p.dt = dt, p.filt = filt;
   p.tw = get_twiddles(logn);
   if (!p.tw) return ADEPT_ERR_CUDA;
   return dispatch_push<AXIS_X>(logn, p, stream);

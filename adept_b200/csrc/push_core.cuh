@@ -51,9 +51,11 @@ __device__ __forceinline__ void phase_table_fill(cplx* ph, double alpha_a, doubl
 // (T - t) mod T.  Upper halves are published in natural order, every thread updates its E/2 (k, N-k) pairs (one phase
 // evaluation and one spectrum separation per pair: A' = pa A, B' = pb B, Z' = A' + i B'), writes the partner value
 // back, and upper halves are read back.  Results are left swapped (im, re): the inverse transform is
-// swap . forward FFT . swap.  All threads of the CTA must call it (it uses __syncthreads()).
+// swap . forward FFT . swap.  `filt` (nullable, [N/2+1]) is an extra real multiplier per mode.  All threads of the CTA
+// must call it (it uses __syncthreads()).
 template <int LOGN, int BS>
-__device__ __forceinline__ void half_spectrum_update(cplx (&x)[FftCfg<LOGN>::E], cplx* buf, const cplx* ph, int t) {
+__device__ __forceinline__ void half_spectrum_update(cplx (&x)[FftCfg<LOGN>::E], cplx* buf, const cplx* ph, int t,
+                                                     const double* __restrict__ filt = nullptr) {
   using C = FftCfg<LOGN>;
   using PC = PhaseCfg<LOGN>;
   constexpr int N = C::N, E = C::E, T = C::T, H = E / 2;
@@ -80,7 +82,11 @@ __device__ __forceinline__ void half_spectrum_update(cplx (&x)[FftCfg<LOGN>::E],
       const cplx zq = self ? zk : buf[q];
       const cplx A = cmake(zk.x + zq.x, zk.y - zq.y);  // 2 * spectrum of a at k
       const cplx B = cmake(zk.y + zq.y, zq.x - zk.x);  // 2 * spectrum of b at k
-      const cplx Ap = cmul(A, pa), Bp = cmul(B, pb);
+      cplx Ap = cmul(A, pa), Bp = cmul(B, pb);
+      if (filt) {  // real per-mode multiplier (Hou-Li filter, vlasov.py:211-219)
+        const double s = __ldg(filt + k);
+        Ap.x *= s, Ap.y *= s, Bp.x *= s, Bp.y *= s;
+      }
       // Z'[k] = A' + i B' ;  Z'[N-k] = conj(A') + i conj(B')
       x[m] = cmake(Ap.y + Bp.x, Ap.x - Bp.y);
       if (!self) buf[q] = cmake(Bp.x - Ap.y, Ap.x + Bp.y);
@@ -88,7 +94,8 @@ __device__ __forceinline__ void half_spectrum_update(cplx (&x)[FftCfg<LOGN>::E],
     if (t == 0) {  // Nyquist mode: real phase cos(alpha N/2), pairs with itself
       const int q = fft_pad(N / 2) * BS;
       const cplx z = buf[q];
-      buf[q] = cmake(2.0 * z.y * phb[PC::NYQ].x, 2.0 * z.x * pha[PC::NYQ].x);
+      const double s = filt ? __ldg(filt + N / 2) : 1.0;
+      buf[q] = cmake(2.0 * z.y * phb[PC::NYQ].x * s, 2.0 * z.x * pha[PC::NYQ].x * s);
     }
   }
   __syncthreads();

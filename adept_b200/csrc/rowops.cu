@@ -190,4 +190,47 @@ int reduce_parts_f64(const double* parts, int nparts, long long n, double scale_
   return check_launch("reduce_parts_kernel");
 }
 
+// ---- in-loop save moments (storage.py:119-162, 286-327) -----------------------------------------------------------
+// one warp per row of the (optionally time-interpolated) distribution f = f0 + w (f1 - f0):
+//   out[k, row] = dv * sum_j g_k(f_j, v_j),  g = { f, f v, f v^2, f v^3, -|f| log|f|, f^2 }
+__global__ void __launch_bounds__(256) save_moments_kernel(const double* __restrict__ f0, const double* __restrict__ f1,
+                                                           double w, const double* __restrict__ v, long long rows,
+                                                           int nv, double dv, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const double* a = f0 + row * nv;
+  const double* b = f1 ? f1 + row * nv : nullptr;
+  double s[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int j = lane; j < nv; j += 32) {
+    double x = a[j];
+    if (b) x = x + w * (b[j] - x);  // diffrax's linear dense output between y0 and y1 (adept/_base_.py:40)
+    const double vv = __ldg(v + j);
+    const double ax = fabs(x);
+    s[0] += x;
+    s[1] += x * vv;
+    s[2] += x * (vv * vv);
+    s[3] += x * (vv * vv * vv);
+    s[4] += -log(ax) * ax;
+    s[5] += x * x;
+  }
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    const double t = warp_sum(s[k]);
+    if (lane == 0) out[(long long)k * rows + row] = t * dv;
+  }
+}
+
+int save_moments_f64(const double* f0, const double* f1, double w, int batch, int nx, int nv, const double* v,
+                     double dv, double* out, cudaStream_t stream) {
+  if (batch < 1 || nx < 1 || nv < 1) {
+    set_last_error("save_moments: bad shape batch=%d nx=%d nv=%d", batch, nx, nv);
+    return ADEPT_ERR_BAD_SHAPE;
+  }
+  const long long rows = (long long)batch * nx;
+  ProfileScope prof("save_moments", stream);
+  save_moments_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(f0, f1, w, v, rows, nv, dv, out);
+  return check_launch("save_moments_kernel");
+}
+
 }  // namespace adept

@@ -7,29 +7,9 @@
 //   LongitudinalElectricFieldDriver   adept/_vlasov1d/solvers/pushers/field.py:21-33
 #include "../../include/adept_b200.h"
 #include "common.cuh"
+#include "internal.h"
 
 namespace adept {
-
-int vdfdx_f64(const double*, double*, int, int, int, const double*, double, const double*, double, cudaStream_t);
-int edfdv_exp_f64(const double*, double*, int, int, int, const double*, const double*, const double*, double, double,
-                  double, double, cudaStream_t);
-int edfdv_spline_f64(const double*, double*, int, int, int, const double*, const double*, const double*, double,
-                     double, double, double, cudaStream_t);
-int moments_f64(const double*, int, int, int, const double*, double, const double* const*, double* const*,
-                const double*, cudaStream_t);
-int axpy_f64(const double*, const double*, double, double*, long long, cudaStream_t);
-int poisson_dispatch_f64(const double*, const double*, long long, double*, int, int, int, double, double,
-                         cudaStream_t);
-int ponderomotive_f64(const double*, double*, int, int, double, cudaStream_t);
-int wave_step_f64(const double*, const double*, const double*, const double*, const double*, double*, int, int,
-                  double, double, double, cudaStream_t);
-int collide_f64(const double*, double*, int, int, int, const double*, double, double, const double*, const double*,
-                const double*, int, int, int, double, double, double*, double, double, cudaStream_t);
-int reduce_parts_f64(const double*, int, long long, double, double, const double*, double*, cudaStream_t);
-bool vdfdx_tma_supported(const double*, const double*, int, int);
-int vdfdx_tma_parts(int, int, int);
-int vdfdx_tma_f64(const double*, double*, int, int, int, const double*, double, const double*, double, double*,
-                  cudaStream_t);
 
 // ---- Ex driver field at every substep time ---------------------------------------------------------------------
 struct DriverArgs {

@@ -56,6 +56,7 @@ struct TmaPushArgs {
   const cplx* tw;
   int zero;
   double* partial;      // [gridDim.x, batch*nx] per-CTA row sums of f_out, or null
+  const double* filt;   // nullable [N/2+1]: real multiplier per mode (Hou-Li filter)
 };
 
 template <int LOGN>
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(TmaCfg<LOGN>::THREADS, 1)
 #pragma unroll
     for (int m = 0; m < E; m++) x[m] = buf[(t + T * m) * 2];  // unpadded landing layout
     fft_forward<LOGN, 2>(x, buf, p.tw, t, p.zero);
-    half_spectrum_update<LOGN, 2>(x, buf, ph, t);
+    half_spectrum_update<LOGN, 2>(x, buf, ph, t, p.filt);
     fft_forward<LOGN, 2>(x, buf, p.tw + p.zero, t, p.zero);
 
     // the exchange buffer is dead once every thread has finished the last pass: hand it to the next tile's TMA load
@@ -277,7 +278,7 @@ int vdfdx_tma_parts(int batch, int nx, int nv) {
 
 // partial: [vdfdx_tma_parts(), batch*nx] zero-initialised by the caller (or null)
 int vdfdx_tma_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* v, double dt,
-                  const double* k1_batch, double k1, double* partial, cudaStream_t stream) {
+                  const double* k1_batch, double k1, double* partial, cudaStream_t stream, const double* filt) {
   const int logn = ilog2_exact_(nx);
   CUtensorMap map;
   const int box_rows = nx < 256 ? nx : 256;
@@ -285,7 +286,7 @@ int vdfdx_tma_f64(const double* fin, double* fout, int batch, int nx, int nv, co
   if (rc != ADEPT_OK) return rc;
   TmaPushArgs p = {};
   p.fout = fout, p.batch = batch, p.nx = nx, p.nv = nv, p.ntiles = batch * (nv / 4);
-  p.v = v, p.k1_batch = k1_batch, p.k1 = k1, p.dt = dt, p.zero = 0, p.partial = partial;
+  p.v = v, p.k1_batch = k1_batch, p.k1 = k1, p.dt = dt, p.zero = 0, p.partial = partial, p.filt = filt;
   p.tw = get_twiddles(logn);
   if (!p.tw) return ADEPT_ERR_CUDA;
   const int grid = vdfdx_tma_parts(batch, nx, nv);

@@ -15,35 +15,64 @@ from .config import build_cfg
 from .vector_field import VlasovMaxwell
 
 
-def default_scalars(cfg, y):
-    """Scalar time series saved at every step by the reference (storage.py:286-327); torch, on device."""
+def _lerp(y0, y1, w, key):
+    return y0[key] if y1 is None else y0[key] + w * (y1[key] - y0[key])
+
+
+def _species_moments(cfg, y0, y1, w, cache):
+    """{name: [6, nx] tensor} = dv * sum_v {f, f v, f v^2, f v^3, -|f| log|f|, f^2} of the state interpolated between
+    y0 and y1 (one fused pass per species; the interpolated f is never materialised)."""
+    from . import ops
+
+    out = {}
+    for name, sg in cfg["grid"]["species_grids"].items():
+        f0 = y0[name]
+        key = (name, str(f0.device))
+        if key not in cache:
+            cache[key] = torch.as_tensor(np.array(sg["v"], dtype=np.float64), device=f0.device)
+        out[name] = ops.save_moments(f0, cache[key], float(sg["dv"]), None if y1 is None else y1[name], w)
+    return out
+
+
+_V_CACHE = {}
+
+
+def default_scalars(cfg, y0, y1=None, w=0.0):
+    """Scalar time series saved at every step by the reference (storage.py:286-327) for the state interpolated
+    linearly between y0 and y1 (weight w); device tensors."""
     g = cfg["grid"]
     s = {}
     ke = 0.0
-    for name, sg in g["species_grids"].items():
-        f = y[name]
-        v = torch.as_tensor(sg["v"], device=f.device)[None, :]
-        dv, mass = sg["dv"], g["species_params"][name]["mass"]
-
-        def mm(inp):
-            return torch.mean(torch.sum(inp, dim=-1) * dv)
-
-        s[f"mean_P_{name}"] = mm(f * v**2.0)
-        s[f"mean_j_{name}"] = mm(f * v)
-        s[f"mean_n_{name}"] = mm(f)
-        s[f"mean_q_{name}"] = mm(f * v**3.0)
-        af = torch.abs(f)
-        s[f"mean_-flogf_{name}"] = mm(-torch.log(af) * af)
-        s[f"mean_f2_{name}"] = mm(f * f)
-        ke = ke + 0.5 * mass * s[f"mean_P_{name}"]
-    s["mean_de2"] = torch.mean(y["de"] ** 2.0)
-    s["mean_e2"] = torch.mean(y["e"] ** 2.0)
-    a2 = y["a"] ** 2.0
-    s["mean_pond"] = torch.mean(-0.5 * (a2[2:] - a2[:-2]) / (2.0 * g["dx"]))
+    for name, m in _species_moments(cfg, y0, y1, w, _V_CACHE).items():
+        mass = g["species_params"][name]["mass"]
+        mean = torch.mean(m.reshape(6, -1), dim=1)
+        s[f"mean_n_{name}"], s[f"mean_j_{name}"], s[f"mean_P_{name}"] = mean[0], mean[1], mean[2]
+        s[f"mean_q_{name}"], s[f"mean_-flogf_{name}"], s[f"mean_f2_{name}"] = mean[3], mean[4], mean[5]
+        ke = ke + 0.5 * mass * mean[2]
+    s["mean_de2"] = torch.mean(_lerp(y0, y1, w, "de") ** 2.0)
+    s["mean_e2"] = torch.mean(_lerp(y0, y1, w, "e") ** 2.0)
+    a2 = _lerp(y0, y1, w, "a") ** 2.0
+    s["mean_pond"] = torch.mean(-0.5 * (a2[..., 2:] - a2[..., :-2]) / (2.0 * g["dx"]))
     s["mean_kinetic_energy"] = ke
     s["mean_field_energy"] = 0.5 * s["mean_e2"]
     s["mean_total_energy"] = ke + 0.5 * s["mean_e2"]
     return s
+
+
+def field_moments(cfg, y0, y1=None, w=0.0):
+    """Per-species x-profiles n, j, v, p, q, -flogf, f^2 and the fields (storage.py:119-162).  p and q are central
+    moments about the local mean velocity, obtained from the raw moments of the fused pass."""
+    res = {}
+    for name, m in _species_moments(cfg, y0, y1, w, _V_CACHE).items():
+        n, j, m2, m3 = m[0], m[1], m[2], m[3]
+        u = j / n
+        res[name] = {"n": n, "j": j, "v": u, "p": m2 - 2.0 * u * j + u * u * n,
+                     "q": m3 - 3.0 * u * m2 + 3.0 * u * u * j - u**3 * n, "-flogf": m[4], "f^2": m[5]}
+    for k in ("e", "de", "a", "prev_a"):
+        res[k] = _lerp(y0, y1, w, k)
+    a2 = res["a"] ** 2.0
+    res["pond"] = -0.5 * (a2[..., 2:] - a2[..., :-2]) / (2.0 * cfg["grid"]["dx"])
+    return res
 
 
 class Vlasov1D:
@@ -83,7 +112,8 @@ class Vlasov1D:
         return self.state
 
     def run(self, nsteps=None, save=None):
-        """Advance ``nsteps`` (default: the deck's nt).  ``save``: name -> (times, fn(cfg, y)); returns
+        """Advance ``nsteps`` (default: the deck's nt).  ``save``: name -> (times, fn(cfg, y0, y1, w)) where the
+        saved state is y0 + w (y1 - y0) (diffrax's linear dense output; see default_scalars / field_moments); returns
         (state, {name: [fn outputs]})."""
         nsteps = self.grid.nt if nsteps is None else nsteps
         save = save or {}
@@ -97,8 +127,7 @@ class Vlasov1D:
             for k, (ts, fn) in save.items():
                 while cursor[k] < len(ts) and ts[cursor[k]] <= t1 + 1e-12 * max(1.0, abs(t1)):
                     w = (ts[cursor[k]] - t0) / (t1 - t0)
-                    yi = {kk: y0[kk] + w * (y1[kk] - y0[kk]) for kk in y1}
-                    out[k].append(fn(self.cfg, yi))
+                    out[k].append(fn(self.cfg, y0, y1, w))  # save functions interpolate on the fly
                     cursor[k] += 1
         return self.state, out
 

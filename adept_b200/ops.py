@@ -67,6 +67,29 @@ def vdfdx(f, v, dt, k1x, out=None, k1x_batch=None):
     return out
 
 
+def save_moments(f0, v, dv, f1=None, w=0.0, out=None):
+    """[6, batch*nx] = dv * sum_v {f, f v, f v^2, f v^3, -|f| log|f|, f^2} of f = f0 + w (f1 - f0) (storage.py:119-162,
+    286-327), one pass over f, the interpolated distribution is never materialised."""
+    b, nx, nv = _shape3(f0)
+    out = torch.empty((6, b * nx), dtype=torch.float64, device=f0.device) if out is None else out
+    rc = _lib.load().adept_b200_save_moments_f64(_ptr(f0, "f0"), _ptr(f1, "f1", True), float(w), b, nx, nv,
+                                                 _ptr(v, "v"), float(dv), _ptr(out, "out"), _stream())
+    _lib.check(rc, "save_moments")
+    _count()
+    return out
+
+
+def filter_x(f, filt, zeros_v, out=None):
+    """Real per-mode multiplier along x: irfft(filt[:, None] * rfft(f, axis=x)) (HouLiFilter, vlasov.py:215-220)."""
+    b, nx, nv = _shape3(f)
+    out = torch.empty_like(f) if out is None else out
+    rc = _lib.load().adept_b200_filter_x_f64(_ptr(f, "f"), _ptr(out, "out"), b, nx, nv, _ptr(filt, "filt"),
+                                             _ptr(zeros_v, "zeros_v"), _stream())
+    _lib.check(rc, "filter_x")
+    _count()
+    return out
+
+
 def vdfdx_rho_parts(f) -> int:
     """Rows of the partial-sum scratch that :func:`vdfdx_rho` needs for a distribution of this shape."""
     b, nx, nv = _shape3(f)

@@ -134,7 +134,7 @@ class VelocityCubicSpline(_VelocityPusher):
 class ElectricFieldSolver:
     """(pond, e) = field_solve(f_dict, a, prev_ex, dt); field.py:422-497.
 
-    ``poisson`` / ``poisson-boltzmann`` / ``ampere`` are implemented; ``hampere`` is not (raises).
+    ``poisson`` / ``poisson-boltzmann`` / ``ampere`` / ``hampere`` (single species, leapfrog).
     """
 
     def __init__(self, cfg: dict, grid):
@@ -157,7 +157,16 @@ class ElectricFieldSolver:
             if time != "leapfrog":
                 raise NotImplementedError(f"ampere + {time} has not yet been implemented")
         elif self.kind == "hampere":
-            raise NotImplementedError("adept_b200: the hampere field solver is not implemented (SURVEY.md 8a15)")
+            if time != "leapfrog":
+                raise NotImplementedError(f"hampere + {time} has not yet been implemented")
+            if len(self.species_grids) > 1:
+                raise NotImplementedError(
+                    "HampereSolver currently only supports single-species simulations. "
+                    "For multi-species, use 'ampere' or 'poisson' field solver instead."
+                )
+            self.hampere = True
+            self.kmul, self.mode = _np(grid.one_over_kx), 0
+            self.kx = _np(grid.kx)
         else:
             raise NotImplementedError("Field Solver: <" + str(self.kind) + "> has not yet been implemented")
         self.dx = float(grid.dx)
@@ -197,6 +206,31 @@ class ElectricFieldSolver:
             ops.moments(f, v, dv, (None, new, None), bases=(None, j, None), scale_b=(1.0, q, 1.0))
             j = new
         return j
+
+    def solve_hampere(self, f_dict, a, prev_ex, dt, rho_parts):
+        """HampereSolver.__call__ (field.py:395-419) without a 2-D FFT of f.
+
+        E_k += q/(i k) dv sum_v f_k(v) (e^{-i k v dt} - 1) is, mode by mode, the Poisson integral of the change of
+        charge density under the x-advection, q dv (sum_v f* - sum_v f): f* is what the x-push computes anyway and its
+        velocity sum comes out of that kernel (``rho_parts``).  Only the Nyquist mode differs -- irfft drops the
+        imaginary part of its phase while the full complex transform of the reference keeps it -- and is added
+        explicitly: (-1)^x / nx * q / k_N * dv sum_x (-1)^x sum_v f(x, v) (-sin(k_N v dt))."""
+        name = next(iter(f_dict))
+        f = f_dict[name]
+        dev = f.device
+        q, dv = self.species_params[name]["charge"], float(self.species_grids[name]["dv"])
+        nx = f.shape[-2]
+        k_ny = float(self.kx[nx // 2])
+        w = self._cache.get(("hampere-w", float(dt)), -np.sin(k_ny * float(dt) * _np(self.species_grids[name]["v"])), dev)
+        n0 = torch.empty(f.shape[:-1], dtype=torch.float64, device=dev)
+        s1 = torch.empty(f.shape[:-1], dtype=torch.float64, device=dev)
+        ops.moments(f, w, dv, (n0, s1, None), scale_b=(-q, 1.0, 1.0))  # n0 = -q dv sum f ; s1 = dv sum f w
+        drho = ops.reduce_parts(rho_parts[name], dv, q, base=n0.reshape(-1))  # q dv (sum f* - sum f)
+        de = ops.poisson(drho.reshape(n0.shape), self._cache.get("kmul", self.kmul, dev))
+        sign = self._cache.get(("sign", nx), (-1.0) ** np.arange(nx), dev)
+        s_ny = torch.sum(sign * s1, dim=-1, keepdim=True)
+        e = prev_ex + de + sign * (q * float(self.kmul[nx // 2]) / nx) * s_ny
+        return ops.ponderomotive(a, self.dx), e
 
     @property
     def wants_rho(self):
@@ -392,10 +426,21 @@ class Collisions:
 
 
 class HouLiFilter:
-    """x-only Hou-Li spectral filter (vlasov.py:187-220).  Not on the default path; not implemented as a kernel."""
+    """x-only Hou-Li spectral filter sigma_j = exp(-alpha (j / (nx/2))^(2 order)); vlasov.py:187-220."""
 
-    def __init__(self, nx, alpha, order):
-        raise NotImplementedError("adept_b200: hou_li_filter is not implemented yet (SURVEY.md 8f rank 2)")
+    def __init__(self, nx: int, alpha: float, order: int):
+        j_x = np.arange(nx // 2 + 1)
+        eta_x = j_x / (nx // 2)
+        self.filter_x = np.exp(-alpha * eta_x ** (2 * order))
+        self._cache = _DeviceCache()
+
+    def __call__(self, f_dict: dict) -> dict:
+        result = {}
+        for name, f in f_dict.items():
+            filt = self._cache.get("filt", self.filter_x, f.device)
+            zeros = self._cache.get(("z", f.shape[-1]), np.zeros(f.shape[-1]), f.device)
+            result[name] = ops.filter_x(f, filt, zeros)
+        return result
 
 
 __all__ = ["SpaceExponential", "VelocityExponential", "VelocityCubicSpline", "ElectricFieldSolver", "WaveSolver",

@@ -52,14 +52,16 @@ class LeapfrogIntegrator(TimeIntegrator):
         self.dt_array = self.dt * np.array([0.0, 1.0])
 
     def __call__(self, f_dict, a, dex_array, prev_ex):
-        if self.field_solve.wants_rho and not self.field_solve.hampere:
+        if self.field_solve.hampere:
+            f_after_v, parts = self.vdfdx.push_with_rho(f_dict, dt=self.dt)
+            pond, e = self.field_solve.solve_hampere(f_dict, a, prev_ex, self.dt, parts)
+        elif self.field_solve.wants_rho:
             # the x-push kernel accumulates sum_v f* on the fly: the field solve does not read f* again
             f_after_v, parts = self.vdfdx.push_with_rho(f_dict, dt=self.dt)
             pond, e = self.field_solve(f_dict=f_after_v, a=a, prev_ex=prev_ex, dt=self.dt, rho_parts=parts)
         else:
             f_after_v = self.vdfdx(f_dict, dt=self.dt)
-            f_for_field = f_dict if self.field_solve.hampere else f_after_v
-            pond, e = self.field_solve(f_dict=f_for_field, a=a, prev_ex=prev_ex, dt=self.dt)
+            pond, e = self.field_solve(f_dict=f_after_v, a=a, prev_ex=prev_ex, dt=self.dt)
         # e + dex[0] is formed inside the push kernel (same rounding as the reference's explicit sum)
         f_out = self.edfdv(f_after_v, e=e, pond=pond, dt=self.dt, dex=dex_array[0])
         return e, f_out

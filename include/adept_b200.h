@@ -74,6 +74,18 @@ int adept_b200_vdfdx_rho_f64(const double* f_in, double* f_out, int batch, int n
 int adept_b200_reduce_parts_f64(const double* parts, int nparts, long long n, double scale_a, double scale_b,
                                 const double* base, double* out, void* stream);
 
+/* In-loop save moments in one pass over f (get_default_save_func / get_field_save_func, adept/_vlasov1d/storage.py:
+ * 286-327, 119-162): out[k, row] = dv sum_j g_k(f_j, v_j), g = { f, f v, f v^2, f v^3, -|f| log|f|, f^2 }, out is
+ * [6, batch*nx].  With f1 != NULL the distribution is the linear interpolation f0 + w (f1 - f0) that diffrax hands to
+ * the save functions between two steps; it is never materialised. */
+int adept_b200_save_moments_f64(const double* f0, const double* f1, double w, int batch, int nx, int nv,
+                                const double* v, double dv, double* out, void* stream);
+
+/* Hou-Li spectral filter along x (HouLiFilter.__call__, vlasov.py:215-220): f_out = irfft(filt[m] rfft(f_in, axis=x)),
+ * filt[nx/2+1] real.  zeros_v: a device array of nv zeros (the x-advection kernels run with zero advection speed). */
+int adept_b200_filter_x_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* filt,
+                            const double* zeros_v, void* stream);
+
 /* v-advection (spectral): accel_i = (q (e_i + dex_i) + (q^2/m) pond_i)/m;
  * f_out = irfft(exp(-i kv_n dt accel_i) rfft(f_in, axis=v), axis=v).  e, dex, pond are [batch, nx]
  * (dex, pond nullable); k1v = kv_real[1] = 2 pi / (nv dv).  nv power of two (<= 8192), nx even.  In-place allowed. */

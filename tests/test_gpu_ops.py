@@ -103,6 +103,17 @@ def test_vdfdx_rho_fused_moment(ops, B, nx, nv):
     assert rel_l2(host(fd), ref) <= RTOL
 
 
+@pytest.mark.parametrize("nx,nv", [(32, 16), (64, 6), (512, 64), (4096, 32)])
+def test_hou_li_filter_matches_oracle(ops, nx, nv):
+    """HouLiFilter (vlasov.py:209-220) through the x-advection kernels (direct and TMA path)."""
+    from adept_b200.pushers import HouLiFilter
+
+    f, x, v, dx, dv = make_f(nx, nv, seed=nx, noise=0.05)
+    ref = O.hou_li_filter(f, nx, 36.0, 4)
+    out = host(HouLiFilter(nx, 36.0, 4)({"electron": dev(f)})["electron"])
+    assert rel_l2(out, ref) <= RTOL
+
+
 def test_vdfdx_exact_characteristic_shift(ops):
     """reference test_multispecies_pushers.py:16-64 (sinusoid, nv=2 instead of 1: nv must be even)."""
     Lx = 2 * np.pi
@@ -348,6 +359,43 @@ def test_collide_conservation_50_steps(ops):
         np.testing.assert_allclose(np.sum(out, 1) * dv, np.sum(f, 1) * dv, rtol=1e-10)
         np.testing.assert_allclose(np.sum(out * v, 1) * dv, np.sum(f * v, 1) * dv, rtol=1e-6)
         np.testing.assert_allclose(np.sum(out * v**2, 1) * dv, np.sum(f * v**2, 1) * dv, rtol=energy_rtol)
+
+
+# ---------------------------------------------------------------------------------------------------- in-loop saves
+@pytest.mark.parametrize("nx,nv,interp", [(16, 64, False), (32, 250, True), (4096, 512, True)])
+def test_save_moments_fused_pass(ops, nx, nv, interp):
+    """storage.py:119-162 / 286-327: six velocity moments of the (interpolated) state in one pass over f."""
+    f0, x, v, dx, dv = make_f(nx, nv, seed=1, noise=0.0)
+    f1 = f0 * (1 + 0.05 * np.cos(3 * v))[None, :]
+    w = 0.37
+    f = f0 + w * (f1 - f0) if interp else f0
+    got = host(ops.save_moments(dev(f0), dev(v), dv, dev(f1) if interp else None, w)).reshape(6, nx)
+    ref = [np.sum(g, axis=1) * dv for g in (f, f * v, f * v**2, f * v**3, -np.log(np.abs(f)) * np.abs(f), f * f)]
+    for k in range(6):
+        np.testing.assert_allclose(got[k], ref[k], rtol=1e-12, atol=1e-13 * np.max(np.abs(ref[k])))
+
+
+def test_field_moments_match_oracle():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from adept_b200.module import default_scalars, field_moments
+
+    nx, nv = 64, 256
+    f, x, v, dx, dv = make_f(nx, nv, seed=5)
+    cfg = {"grid": {"species_grids": {"electron": {"v": v, "dv": dv}}, "species_params": {"electron": {"mass": 1.0}},
+                    "dx": dx}}
+    y = {"electron": f, "e": np.sin(x), "de": np.cos(x), "a": np.linspace(0, 1, nx + 2), "prev_a": np.zeros(nx + 2)}
+    yd = {k: dev(val) for k, val in y.items()}
+    ref, got = O.field_moments(cfg, y), field_moments(cfg, yd)
+    for k in ("n", "j", "v", "-flogf", "f^2"):
+        np.testing.assert_allclose(host(got["electron"][k]), ref["electron"][k], rtol=1e-12, atol=1e-14)
+    for k in ("p", "q"):  # central moments via raw moments: error relative to the raw-moment scale
+        scale = np.max(np.abs(ref["electron"]["n"])) * (np.max(np.abs(ref["electron"]["v"])) + 1.0) ** 3
+        np.testing.assert_allclose(host(got["electron"][k]), ref["electron"][k], rtol=0, atol=2e-13 * scale)
+    np.testing.assert_allclose(host(got["pond"]), ref["pond"], rtol=1e-13, atol=1e-16)
+    sref, sgot = O.default_scalars(cfg, y), default_scalars(cfg, yd)
+    for k in sref:
+        np.testing.assert_allclose(float(sgot[k]), sref[k], rtol=1e-12, atol=1e-15, err_msg=k)
 
 
 # ---------------------------------------------------------------------------------------------------- error behaviour

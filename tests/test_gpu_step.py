@@ -51,6 +51,12 @@ def variants():
     d["terms"].update(field="ampere")
     d["grid"]["dt"] = 0.025
     out["C2-ampere"] = d
+    d = c2_deck()  # Hamiltonian Ampere solver (leapfrog only, single species)
+    d["terms"].update(field="hampere")
+    out["C2-hampere"] = d
+    d = c2_deck()  # Hou-Li spectral filter after the collisions
+    d["terms"]["hou_li_filter"] = {"is_on": True, "alpha": 36.0, "order": 8}
+    out["C2-houli"] = d
     out["resonance"] = load("resonance")
     out["fp-conservation"] = load("fokker_planck_conservation")
     d = load("multispecies_ion_acoustic")
