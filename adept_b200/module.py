@@ -27,7 +27,7 @@ def _species_moments(cfg, y0, y1, w, cache):
     out = {}
     for name, sg in cfg["grid"]["species_grids"].items():
         f0 = y0[name]
-        key = (name, str(f0.device))
+        key = (name, str(f0.device), len(sg["v"]), float(sg["v"][0]), float(sg["dv"]))
         if key not in cache:
             cache[key] = torch.as_tensor(np.array(sg["v"], dtype=np.float64), device=f0.device)
         out[name] = ops.save_moments(f0, cache[key], float(sg["dv"]), None if y1 is None else y1[name], w)
