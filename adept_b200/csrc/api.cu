@@ -204,6 +204,29 @@ int adept_b200_vdfdx_f64(const double* f_in, double* f_out, int batch, int nx, i
   return vdfdx_f64(f_in, f_out, batch, nx, nv, v, dt, k1x_batch, k1x, (cudaStream_t)stream);
 }
 
+int adept_b200_edfdv_exp_bwd_accel_f64(const double* f_in, const double* g, int batch, int nx, int nv, const double* e,
+                                       const double* dex, const double* pond, double charge, double mass, double dt,
+                                       double k1v, double* accel_bar, void* stream) {
+  ADEPT_REQUIRE(f_in, "f_in") ADEPT_REQUIRE(g, "g") ADEPT_REQUIRE(e, "e") ADEPT_REQUIRE(accel_bar, "accel_bar")
+  return edfdv_exp_bwd_accel_f64(f_in, g, batch, nx, nv, e, dex, pond, charge, mass, dt, k1v, accel_bar,
+                                 (cudaStream_t)stream);
+}
+
+int adept_b200_moments_bwd_f64(const double* const* out_bar_host, const double* coef_host, int batch, int nx, int nv,
+                               const double* v, int accumulate, double* f_bar, void* stream) {
+  ADEPT_REQUIRE(out_bar_host, "out_bar_host") ADEPT_REQUIRE(coef_host, "coef_host") ADEPT_REQUIRE(f_bar, "f_bar")
+  return moments_bwd_f64(out_bar_host, coef_host, batch, nx, nv, v, accumulate, f_bar, (cudaStream_t)stream);
+}
+
+int adept_b200_collide_bwd_f64(const double* f_in, const double* f_new, const double* g, double* f_bar, double* nu_bar,
+                               int batch, int nx, int nv, const double* v, double dv, double dt, const double* nu_fp,
+                               int model, int scheme, void* stream) {
+  ADEPT_REQUIRE(f_in, "f_in") ADEPT_REQUIRE(f_new, "f_new") ADEPT_REQUIRE(g, "g") ADEPT_REQUIRE(f_bar, "f_bar")
+  ADEPT_REQUIRE(v, "v") ADEPT_REQUIRE(nu_fp, "nu_fp")
+  return collide_bwd_f64(f_in, f_new, g, f_bar, nu_bar, batch, nx, nv, v, dv, dt, nu_fp, 1.0, model, scheme,
+                         (cudaStream_t)stream);
+}
+
 int adept_b200_save_moments_f64(const double* f0, const double* f1, double w, int batch, int nx, int nv,
                                 const double* v, double dv, double* out, void* stream) {
   ADEPT_REQUIRE(f0, "f0") ADEPT_REQUIRE(v, "v") ADEPT_REQUIRE(out, "out")

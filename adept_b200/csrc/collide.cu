@@ -477,6 +477,282 @@ __global__ void __launch_bounds__(MAXT, MINB) collide_kernel(CollideArgs p) {
   }
 }
 
+// =====================================================================================================================
+// Adjoint of the Fokker-Planck step (central differencing, Lenard-Bernstein / Dougherty):  f_new = A(m(f))^{-1} f with
+// m = (vbar, T) the row moments of the INPUT f.  For a cotangent g of f_new:
+//   lambda = A^{-T} g                                  (same chunked solver on the transposed matrix, delta form)
+//   f_bar  = lambda + dt nu [ s_D dT/df + s_u dvbar/df ],   s_k = lambda^T (dL/dm_k) f_new
+//   nu_bar = dt lambda^T L f_new
+// With the flux form  dt nu (L f)_i = G_i - G_{i-1}:  lambda^T (dt nu L f) = sum_e (lambda_e - lambda_{e+1}) G_e.
+struct CollideBwdArgs {
+  const double* fin;   // forward input
+  const double* fnew;  // forward output
+  const double* g;     // cotangent of the forward output
+  double* fbar;        // cotangent of the forward input
+  double* nubar;       // [rows] cotangent of nu_fp (nullable)
+  long long rows;
+  int nv;
+  const double* v;
+  double dv, dt;
+  const double* nu_fp;
+  double nu_fp_scale;
+  int model;
+};
+
+template <int E, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) collide_bwd_kernel(CollideBwdArgs p) {
+  extern __shared__ __align__(16) double sm[];
+  const int nv = p.nv;
+  const int T = nv / E;
+  const int nvp = nv + T;
+  const int t = threadIdx.x;
+  const bool live = t < T;
+  const int tt = live ? t : 0;
+  double* buf_f = sm;               // f_in, later f_new
+  double* buf_g = sm + nvp;         // g, later lambda
+  double* apbuf = sm + 2 * nvp;     // [E][T]
+  double* red = apbuf + nv;         // 2 * max(T,32) * 3
+  double* pcr = red + 2 * (T > 32 ? T : 32) * 3;  // 6 T
+  const bool warp_mode = (T & 31) == 0;
+  int parity = 0;
+  const long long row = blockIdx.x;
+  const double dv = p.dv, dt = p.dt;
+  const int i0 = E * tt;
+
+  if (live) {
+    const double* fin = p.fin + row * nv;
+    const double* gin = p.g + row * nv;
+    for (int i = t; i < nv; i += T) {
+      buf_f[i + i / E] = fin[i];
+      buf_g[i + i / E] = gin[i];
+    }
+  }
+  __syncthreads();
+  const double* chunk = buf_f + i0 + tt;
+  double* gch = buf_g + i0 + tt;
+  const double vc = __ldg(p.v + i0);
+  const double nu = __dmul_rn(p.nu_fp_scale, p.nu_fp[row]);
+
+  // moments of the forward input (same arithmetic as the forward kernel)
+  double mom[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int l = 0; l < E; l++) {
+    const double fl = chunk[l];
+    mom[0] += fl;
+    mom[1] = fma(fl, (double)l, mom[1]);
+    mom[2] = fma(fl, (double)(l * l), mom[2]);
+  }
+  {
+    const double m0 = mom[0], m1 = mom[1] * dv, m2 = mom[2] * (dv * dv);
+    mom[1] = fma(vc, m0, m1);
+    mom[2] = fma(vc * vc, m0, fma(2.0 * vc, m1, m2));
+  }
+  if (!live) mom[0] = mom[1] = mom[2] = 0.0;
+  row_reduce<3>(mom, red, parity, 0, tt, T, T, warp_mode, live);
+  const double s0 = mom[0], s1 = mom[1], s2 = mom[2];
+  const double vbar = (p.model == FP_LB) ? 0.0 : s1 / s0;
+  const double Temp = (s2 - 2.0 * vbar * s1 + vbar * vbar * s0) / s0;
+  const double beta = 1.0 / (2.0 * Temp);
+  const double D = 1.0 / (2.0 * beta);
+  const double dtnu = dt * nu;
+  const double pD = dtnu * D / (dv * dv);
+  const double c2 = 2.0 * beta * D;
+  const double q = dtnu * c2 / (2.0 * dv);
+  const double w0 = q * (vc + 0.5 * dv - vbar), dq = q * dv;
+  auto edge = [&](int l, double& U, double& L) {
+    const int e = i0 + l;
+    if (e < 0 || e > nv - 2) {
+      U = 0.0;
+      L = 0.0;
+      return;
+    }
+    const double wq = fma((double)l, dq, w0);
+    U = pD + wq;
+    L = pD - wq;
+  };
+
+  // transposed system: a_i = -U_{i-1}, c_i = -L_i, b_i = 1 + L_i + U_{i-1};
+  // rhs_i = g_i - (A^T g)_i = L_i (g_{i+1} - g_i) - U_{i-1} (g_i - g_{i-1})
+  double cpn[E], ypn[E];
+  double rpn_last, apn_last;
+  {
+    double Um, Lm;
+    edge(-1, Um, Lm);
+    double g_m = (tt > 0) ? buf_g[i0 - 1 + (tt - 1)] : 0.0;
+    double g_c = gch[0];
+    double cp_prev = 0.0, ap_prev = 0.0, rp_prev = 0.0;
+#pragma unroll
+    for (int l = 0; l < E; l++) {
+      double Uc, Lc;
+      edge(l, Uc, Lc);
+      const double g_p = (l < E - 1) ? gch[l + 1] : ((tt < T - 1) ? buf_g[i0 + E + (tt + 1)] : 0.0);
+      const double rhs = Lc * (g_p - g_c) - Um * (g_c - g_m);
+      const double a = -Um;
+      const double b = (1.0 + Lc) + Um;
+      double bp, apv, rpv;
+      if (l == 0) {
+        bp = b, apv = a, rpv = rhs;
+      } else {
+        bp = fma(-a, cp_prev, b);
+        apv = -a * ap_prev;
+        rpv = fma(-a, rp_prev, rhs);
+      }
+      const double inv = fast_rcp(bp);
+      const double cp = -Lc * inv, ap = apv * inv, rp = rpv * inv;
+      cpn[l] = cp;
+      if (live) apbuf[l * T + tt] = ap;
+      ypn[l] = (l < E - 1) ? fma(cp, g_p, g_c + rp) : g_c;
+      if (l == E - 1) rpn_last = rp, apn_last = ap;
+      cp_prev = cp, ap_prev = ap, rp_prev = rp;
+      Um = Uc, Lm = Lc, g_m = g_c, g_c = g_p;
+    }
+  }
+  double A0 = 0.0, C0 = 0.0, R0 = 0.0;
+  {
+    double RY = ypn[E - 2], A = apbuf[(E - 2) * T + tt], Cc = cpn[E - 2];
+#pragma unroll
+    for (int l = E - 3; l >= 0; l--) {
+      const double cp = cpn[l];
+      RY = fma(-cp, RY, ypn[l]);
+      A = fma(-cp, A, apbuf[l * T + tt]);
+      Cc = -cp * Cc;
+    }
+    A0 = A, C0 = Cc;
+    R0 = RY - gch[0] - Cc * gch[E - 1];
+  }
+  double* xb = pcr + 3 * T;
+  if (live) xb[tt] = A0, xb[T + tt] = C0, xb[2 * T + tt] = R0;
+  __syncthreads();
+  double al = apn_last, ga = 0.0, rh = rpn_last;
+  {
+    double be = 1.0;
+    if (tt < T - 1) {
+      const double k = cpn[E - 1];
+      be = fma(-k, xb[tt + 1], 1.0);
+      ga = -k * xb[T + tt + 1];
+      rh = fma(-k, xb[2 * T + tt + 1], rpn_last);
+    }
+    const double ib = fast_rcp(be);
+    al *= ib, ga *= ib, rh *= ib;
+  }
+  double* cur = pcr;
+  double* nxt = pcr + 3 * T;
+  __syncthreads();
+  if (live) cur[tt] = al, cur[T + tt] = ga, cur[2 * T + tt] = rh;
+  __syncthreads();
+  for (int s = 1; s < T; s <<= 1) {
+    double alj = 0.0, gaj = 0.0, rhj = 0.0, alk = 0.0, gak = 0.0, rhk = 0.0;
+    if (tt - s >= 0) alj = cur[tt - s], gaj = cur[T + tt - s], rhj = cur[2 * T + tt - s];
+    if (tt + s < T) alk = cur[tt + s], gak = cur[T + tt + s], rhk = cur[2 * T + tt + s];
+    const double be = fma(-al, gaj, fma(-ga, alk, 1.0));
+    const double ib = fast_rcp(be);
+    rh = fma(-al, rhj, fma(-ga, rhk, rh)) * ib;
+    al = -al * alj * ib;
+    ga = -ga * gak * ib;
+    if (live) nxt[tt] = al, nxt[T + tt] = ga, nxt[2 * T + tt] = rh;
+    __syncthreads();
+    double* tmp = cur;
+    cur = nxt;
+    nxt = tmp;
+  }
+  const double s_me = rh;
+  const double s_left = (tt > 0) ? cur[2 * T + tt - 1] : 0.0;
+  __syncthreads();  // every thread has read its neighbours' g values and the reduced solution
+  // lambda over g; f_new over f_in
+  {
+    double y = ypn[E - 1] + s_me;
+    if (live) gch[E - 1] = y;
+#pragma unroll
+    for (int l = E - 2; l >= 0; l--) {
+      y = fma(-cpn[l], y, fma(-apbuf[l * T + tt], s_left, ypn[l]));
+      if (live) gch[l] = y;
+    }
+  }
+  if (live) {
+    const double* fn = p.fnew + row * nv;
+    for (int i = t; i < nv; i += T) buf_f[i + i / E] = fn[i];  // rows of buf_f are only read by their owners below
+  }
+  __syncthreads();
+  // bilinear forms over the edges e = i0 + l, l = 0..E-1 (edge nv-1 does not exist)
+  double bl[3] = {0.0, 0.0, 0.0};
+  {
+    const double* fch = buf_f + i0 + tt;
+    const double lam_next_chunk = (tt < T - 1) ? buf_g[i0 + E + (tt + 1)] : 0.0;
+    const double f_next_chunk = (tt < T - 1) ? buf_f[i0 + E + (tt + 1)] : 0.0;
+#pragma unroll
+    for (int l = 0; l < E; l++) {
+      if (i0 + l > nv - 2) continue;
+      const double lp = (l < E - 1) ? gch[l + 1] : lam_next_chunk;
+      const double fp = (l < E - 1) ? fch[l + 1] : f_next_chunk;
+      const double dl = gch[l] - lp;
+      const double ve = vc + ((double)l + 0.5) * dv - vbar;
+      bl[0] += dl * (fp - fch[l]);
+      bl[1] += dl * (fp + fch[l]);
+      bl[2] += dl * ve * (fp + fch[l]);
+    }
+  }
+  if (!live) bl[0] = bl[1] = bl[2] = 0.0;
+  row_reduce<3>(bl, red, parity, 0, tt, T, T, warp_mode, live);
+  const double cD = (dtnu / (dv * dv)) * bl[0];                  // dt nu s_D
+  const double cu = (p.model == FP_LB) ? 0.0 : -q * bl[1];       // dt nu s_u
+  if (p.nubar && t == 0) p.nubar[row] = p.nu_fp_scale * dt * ((D / (dv * dv)) * bl[0] + (c2 / (2.0 * dv)) * bl[2]);
+  if (live) {
+    double* out = p.fbar + row * nv;
+    const double is0 = 1.0 / s0;
+    for (int i = t; i < nv; i += T) {
+      const double vv = (__ldg(p.v + i) - vbar);
+      out[i] = buf_g[i + i / E] + (cD * (vv * vv - Temp) + cu * vv) * is0;
+    }
+  }
+}
+
+template <int E, int MAXT>
+static int launch_collide_bwd(const CollideBwdArgs& p, cudaStream_t stream) {
+  const int T = p.nv / E;
+  const int threads = ((T + 31) / 32) * 32;
+  const size_t smem = ((size_t)2 * (p.nv + T) + p.nv + 2 * (T > 32 ? T : 32) * 3 + 6 * (size_t)T) * sizeof(double);
+  if (threads > MAXT || smem > 227 * 1024) {
+    set_last_error("collide_bwd: nv=%d does not fit (threads=%d, smem=%zu)", p.nv, threads, smem);
+    return ADEPT_ERR_UNSUPPORTED;
+  }
+  static size_t configured[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto kern = collide_bwd_kernel<E, MAXT>;
+  if (dev < 64 && configured[dev] < smem) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) {
+      set_last_error("cudaFuncSetAttribute(collide_bwd, smem=%zu): %s", smem, cudaGetErrorString(err));
+      return ADEPT_ERR_CUDA;
+    }
+    configured[dev] = smem;
+  }
+  ProfileScope prof("collide_bwd", stream);
+  kern<<<(unsigned)p.rows, threads, smem, stream>>>(p);
+  return check_launch("collide_bwd_kernel");
+}
+
+int collide_bwd_f64(const double* fin, const double* fnew, const double* g, double* fbar, double* nubar, int batch,
+                    int nx, int nv, const double* v, double dv, double dt, const double* nu_fp, double nu_fp_scale,
+                    int model, int scheme, cudaStream_t stream) {
+  if (batch < 1 || nx < 1 || nv < 4) {
+    set_last_error("collide_bwd: bad shape batch=%d nx=%d nv=%d", batch, nx, nv);
+    return ADEPT_ERR_BAD_SHAPE;
+  }
+  if (scheme != FP_CENTRAL || (model != FP_LB && model != FP_DOUGHERTY)) {
+    set_last_error("collide_bwd: only central differencing with the Lenard-Bernstein / Dougherty models is implemented");
+    return ADEPT_ERR_UNSUPPORTED;
+  }
+  CollideBwdArgs p = {fin, fnew, g, fbar, nubar, (long long)batch * nx, nv, v, dv, dt, nu_fp, nu_fp_scale, model};
+  if (nv % 16 == 0 && nv / 16 <= 256) return launch_collide_bwd<16, 256>(p, stream);
+  if (nv % 16 == 0 && nv / 16 <= 512) return launch_collide_bwd<16, 512>(p, stream);
+  if (nv % 8 == 0 && nv / 8 <= 256) return launch_collide_bwd<8, 256>(p, stream);
+  if (nv % 4 == 0 && nv / 4 <= 256) return launch_collide_bwd<4, 256>(p, stream);
+  if (nv % 2 == 0 && nv / 2 <= 256) return launch_collide_bwd<2, 256>(p, stream);
+  set_last_error("collide_bwd: unsupported nv=%d", nv);
+  return ADEPT_ERR_UNSUPPORTED;
+}
+
 template <int E, int MAXT, int MINB, bool FAST>
 static int launch_collide_t(CollideArgs p, cudaStream_t stream) {
   const int T = p.nv / E;

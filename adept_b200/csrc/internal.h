@@ -26,6 +26,14 @@ int reduce_parts_f64(const double* parts, int nparts, long long n, double scale_
                      double* out, cudaStream_t stream);
 int save_moments_f64(const double* f0, const double* f1, double w, int batch, int nx, int nv, const double* v,
                      double dv, double* out, cudaStream_t stream);
+int edfdv_exp_bwd_accel_f64(const double* f, const double* g, int batch, int nx, int nv, const double* e,
+                            const double* dex, const double* pond, double q, double m, double dt, double k1,
+                            double* abar, cudaStream_t stream);
+int moments_bwd_f64(const double* const* obar, const double* coef, int batch, int nx, int nv, const double* v,
+                    int accumulate, double* fbar, cudaStream_t stream);
+int collide_bwd_f64(const double* fin, const double* fnew, const double* g, double* fbar, double* nubar, int batch,
+                    int nx, int nv, const double* v, double dv, double dt, const double* nu_fp, double nu_fp_scale,
+                    int model, int scheme, cudaStream_t stream);
 bool vdfdx_tma_supported(const double* fin, const double* fout, int nx, int nv);
 int vdfdx_tma_parts(int batch, int nx, int nv);
 int vdfdx_tma_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* v, double dt,

@@ -67,6 +67,47 @@ def vdfdx(f, v, dt, k1x, out=None, k1x_batch=None):
     return out
 
 
+# ---------------------------------------------------------------------------------------------------- adjoints
+def edfdv_exp_bwd_accel(f_in, g, e, pond, q, m, dt, k1v, dex=None, out=None):
+    """accel_bar[.., i] = sum_j g_ij d f'_ij / d accel_i of :func:`edfdv_exp` (f_in = the forward input)."""
+    b, nx, nv = _shape3(f_in)
+    out = torch.empty(f_in.shape[:-1], dtype=torch.float64, device=f_in.device) if out is None else out
+    rc = _lib.load().adept_b200_edfdv_exp_bwd_accel_f64(
+        _ptr(f_in, "f_in"), _ptr(g, "g"), b, nx, nv, _ptr(e, "e"), _ptr(dex, "dex", True), _ptr(pond, "pond", True),
+        float(q), float(m), float(dt), float(k1v), _ptr(out, "out"), _stream())
+    _lib.check(rc, "edfdv_exp_bwd_accel")
+    _count()
+    return out
+
+
+def moments_bwd(out_bars, coefs, v, shape, accumulate_into=None):
+    """f_bar = sum_k coefs[k] * out_bars[k][:, None] * v^k (adjoint of :func:`moments`)."""
+    dev = next(o for o in out_bars if o is not None).device
+    fbar = torch.empty(shape, dtype=torch.float64, device=dev) if accumulate_into is None else accumulate_into
+    b, nx, nv = _shape3(fbar)
+    PA = C.c_void_p * 3
+    arr = PA(*[_ptr(o, f"out_bar{k}", True) for k, o in enumerate(out_bars)])
+    cf = (C.c_double * 3)(*[float(c) for c in coefs])
+    rc = _lib.load().adept_b200_moments_bwd_f64(arr, cf, b, nx, nv, _ptr(v, "v", True),
+                                                int(accumulate_into is not None), _ptr(fbar, "fbar"), _stream())
+    _lib.check(rc, "moments_bwd")
+    _count()
+    return fbar
+
+
+def collide_bwd(f_in, f_new, g, v, dv, dt, nu_fp, model=1, scheme=0, want_nu_bar=False):
+    """(f_bar, nu_bar) of the Fokker-Planck step of :func:`collide` (central differencing, LB / Dougherty)."""
+    b, nx, nv = _shape3(f_in)
+    fbar = torch.empty_like(f_in)
+    nubar = torch.empty(f_in.shape[:-1], dtype=torch.float64, device=f_in.device) if want_nu_bar else None
+    rc = _lib.load().adept_b200_collide_bwd_f64(
+        _ptr(f_in, "f_in"), _ptr(f_new, "f_new"), _ptr(g, "g"), _ptr(fbar, "fbar"), _ptr(nubar, "nubar", True), b, nx,
+        nv, _ptr(v, "v"), float(dv), float(dt), _ptr(nu_fp, "nu_fp"), int(model), int(scheme), _stream())
+    _lib.check(rc, "collide_bwd")
+    _count()
+    return fbar, nubar
+
+
 def save_moments(f0, v, dv, f1=None, w=0.0, out=None):
     """[6, batch*nx] = dv * sum_v {f, f v, f v^2, f v^3, -|f| log|f|, f^2} of f = f0 + w (f1 - f0) (storage.py:119-162,
     286-327), one pass over f, the interpolated distribution is never materialised."""

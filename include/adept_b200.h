@@ -133,6 +133,28 @@ int adept_b200_collide_f64(const double* f_in, double* f_out, int batch, int nx,
                            double dt, const double* nu_fp, const double* nu_K, const double* f_mx, int model,
                            int scheme, int nodrag, double sg_m, double sg_ratio, double* n_out, void* stream);
 
+/* ---- adjoints (what the backward rule of a jax.custom_vjp around each operator calls) -------------------------------
+ * x-advection and v-advection w.r.t. f: the forward entry points with dt -> -dt (the operators are real circulants with
+ * unit-modulus symbols, so transpose = inverse).  Poisson: antisymmetric, rho_bar = -poisson(e_bar).  The rest: */
+
+/* accel_bar[b, i] = sum_j g[b, i, j] * d f_out[b, i, j] / d accel[b, i] of adept_b200_edfdv_exp_f64 (same arguments;
+ * f_in is the forward INPUT).  Chain to the fields with e_bar = dex_bar = accel_bar q/m, pond_bar = accel_bar q^2/m^2. */
+int adept_b200_edfdv_exp_bwd_accel_f64(const double* f_in, const double* g, int batch, int nx, int nv, const double* e,
+                                       const double* dex, const double* pond, double charge, double mass, double dt,
+                                       double k1v, double* accel_bar, void* stream);
+
+/* Adjoint of adept_b200_moments_f64: f_bar[row, j] (+)= sum_k coef[k] out_bar_k[row] v_j^k with coef[k] = scale_a *
+ * scale_b[k] of the forward call; out_bar_host: 3 device pointers (nullable each); accumulate != 0 adds into f_bar. */
+int adept_b200_moments_bwd_f64(const double* const* out_bar_host, const double* coef_host, int batch, int nx, int nv,
+                               const double* v, int accumulate, double* f_bar, void* stream);
+
+/* Adjoint of the Fokker-Planck step of adept_b200_collide_f64 (central differencing, Lenard-Bernstein or Dougherty, no
+ * Krook): given the forward input f_in, the forward output f_new and the cotangent g of f_new, writes f_bar (cotangent
+ * of f_in, including the dependence of the operator on the row moments vbar, T) and nu_bar[batch*nx] (nullable). */
+int adept_b200_collide_bwd_f64(const double* f_in, const double* f_new, const double* g, double* f_bar, double* nu_bar,
+                               int batch, int nx, int nv, const double* v, double dv, double dt, const double* nu_fp,
+                               int model, int scheme, void* stream);
+
 /* ---- whole time step ------------------------------------------------------------------------------------------------
  * adept_b200_step_f64 enqueues every kernel of one `vlasov-1d` step y -> y' on `stream` with no host work in between:
  * it replaces VlasovMaxwell.__call__ and what it calls (adept/_vlasov1d/solvers/vector_field.py:55-95 LeapfrogIntegrator,
