@@ -227,6 +227,15 @@ int adept_b200_collide_bwd_f64(const double* f_in, const double* f_new, const do
                          (cudaStream_t)stream);
 }
 
+int adept_b200_vpush_collide_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* e,
+                                 const double* dex, const double* pond, double charge, double mass, double dt,
+                                 double k1v, const double* v, double dv, const double* nu_fp, int model, void* stream) {
+  ADEPT_REQUIRE(f_in, "f_in") ADEPT_REQUIRE(f_out, "f_out") ADEPT_REQUIRE(e, "e") ADEPT_REQUIRE(v, "v")
+  ADEPT_REQUIRE(nu_fp, "nu_fp")
+  return vpush_collide_f64(f_in, f_out, batch, nx, nv, e, dex, pond, charge, mass, dt, k1v, v, dv, nu_fp, 1.0, model,
+                           (cudaStream_t)stream);
+}
+
 int adept_b200_save_moments_f64(const double* f0, const double* f1, double w, int batch, int nx, int nv,
                                 const double* v, double dv, double* out, void* stream) {
   ADEPT_REQUIRE(f0, "f0") ADEPT_REQUIRE(v, "v") ADEPT_REQUIRE(out, "out")

@@ -23,12 +23,11 @@
 // cyclic reduction in shared memory (unit-diagonal form: one reciprocal per step), then chunks back-substitute
 // directly for f + delta.  The matrix is strictly diagonally dominant, so no pivoting is needed; the reference's
 // LAPACK gtsv agrees to rounding.
-#include "common.cuh"
+#include "collide_core.cuh"
+#include "internal.h"
 
 namespace adept {
 
-enum { FP_LB = 0, FP_DOUGHERTY = 1, FP_SUPERGAUSSIAN = 2 };
-enum { FP_CENTRAL = 0, FP_CHANG_COOPER = 1 };
 
 struct CollideArgs {
   const double* fin;
@@ -46,17 +45,6 @@ struct CollideArgs {
   int rows_per_cta;       // R: x-rows handled by one CTA (set by the launcher)
   double nu_fp_scale, nu_K_scale;  // nu = scale * nu[row] (time envelope applied in the kernel)
 };
-
-// 1/x for |x| in the normal range: MUFU.RCP64H seed (about 20 bits) + two Newton steps -> rounding-level accuracy.
-__device__ __forceinline__ double fast_rcp(double x) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  double e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  return r;
-}
 
 __device__ __forceinline__ double cc_delta(double w) {  // driftdiffusion.py:96-103
   if (fabs(w) < 1.0e-8) return 0.5 - w / 12.0 + w * w * w / 720.0;
@@ -76,45 +64,6 @@ __device__ __forceinline__ void bare_edge(double C, double D, double dv, int sch
     const double beta = -C * (1.0 - dl) - sD / dv;
     bu = -beta / dv;
     bl = alpha / dv;
-  }
-}
-
-// Sum NVAL values over the T threads of row r; every thread of the CTA must call it.  warp_mode: T % 32 == 0 (warps do
-// not straddle rows).  `red` is a scratch area of 2 * max(R*T, 32) * NVAL doubles used with alternating halves.
-template <int NVAL>
-__device__ __forceinline__ void row_reduce(double (&val)[NVAL], double* red, int& parity, int r, int t, int T, int RT,
-                                           bool warp_mode, bool live) {
-  double* base = red + (size_t)parity * (RT > 32 ? RT : 32) * NVAL;
-  parity ^= 1;
-  if (warp_mode) {
-#pragma unroll
-    for (int i = 0; i < NVAL; i++) val[i] = warp_sum(val[i]);
-    const int nw = T >> 5, w = t >> 5;
-    double* slot = base + (size_t)r * nw * NVAL;
-    if ((t & 31) == 0) {
-#pragma unroll
-      for (int i = 0; i < NVAL; i++) slot[w * NVAL + i] = val[i];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < NVAL; i++) val[i] = 0.0;
-    for (int j = 0; j < nw; j++) {
-#pragma unroll
-      for (int i = 0; i < NVAL; i++) val[i] += slot[j * NVAL + i];
-    }
-  } else {
-    double* slot = base + (size_t)r * T * NVAL;
-    if (live) {
-#pragma unroll
-      for (int i = 0; i < NVAL; i++) slot[t * NVAL + i] = val[i];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < NVAL; i++) val[i] = 0.0;
-    for (int j = 0; j < T; j++) {
-#pragma unroll
-      for (int i = 0; i < NVAL; i++) val[i] += slot[j * NVAL + i];
-    }
   }
 }
 

@@ -34,6 +34,10 @@ int moments_bwd_f64(const double* const* obar, const double* coef, int batch, in
 int collide_bwd_f64(const double* fin, const double* fnew, const double* g, double* fbar, double* nubar, int batch,
                     int nx, int nv, const double* v, double dv, double dt, const double* nu_fp, double nu_fp_scale,
                     int model, int scheme, cudaStream_t stream);
+bool vpush_collide_supported(int nx, int nv, int model, int scheme, int nodrag);
+int vpush_collide_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* e, const double* dex,
+                      const double* pond, double q, double m, double dt, double k1v, const double* v, double dv,
+                      const double* nu_fp, double nu_fp_scale, int model, cudaStream_t stream);
 bool vdfdx_tma_supported(const double* fin, const double* fout, int nx, int nv);
 int vdfdx_tma_parts(int batch, int nx, int nv);
 int vdfdx_tma_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* v, double dt,

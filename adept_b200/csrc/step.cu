@@ -207,6 +207,7 @@ int step_f64(const adept_b200_step& s, cudaStream_t st) {
   double* tmp[ADEPT_B200_MAX_SPECIES];
   for (int k = 0; k < s.n_species; k++) cur[k] = s.species[k].f_in, out[k] = s.species[k].f_out, tmp[k] = s.species[k].f_tmp;
   const bool spline = s.edfdv == 1;
+  bool collided = false;  // set when the fused v-push + collision kernel already applied the operator
 
   if (s.time_integrator == 0) {
     // leapfrog (vector_field.py:87-95): f* = vdfdx(f); (pond, e) = field(f*); f' = edfdv(f*, e + dex[0], pond)
@@ -216,7 +217,25 @@ int step_f64(const adept_b200_step& s, cudaStream_t st) {
     const double* fstar[ADEPT_B200_MAX_SPECIES];
     for (int k = 0; k < s.n_species; k++) fstar[k] = xdst[k];
     ADEPT_TRY(c.field_solve(fstar, want_rho, s.dt));
-    ADEPT_TRY(c.push_v(fstar, out, s.dt, 0));
+    // the colliding species takes the fused v-push + Fokker-Planck kernel when its shape and operator allow it
+    const int kc = s.collide_species;
+    if (s.fp_on && !s.krook_on && !spline && kc >= 0 && kc < s.n_species &&
+        vpush_collide_supported(s.nx, s.species[kc].nv, s.fp_model, s.fp_scheme, s.fp_nodrag)) {
+      for (int k = 0; k < s.n_species; k++) {
+        const adept_b200_species& sp = s.species[k];
+        if (k == kc) {
+          ADEPT_TRY(vpush_collide_f64(fstar[k], out[k], s.batch, s.nx, sp.nv, s.e_out, s.dex, s.pond, sp.charge,
+                                      sp.mass, s.dt, sp.k1v, sp.v, sp.dv, s.nu_fp_space, s.nu_fp_time, s.fp_model,
+                                      st));
+        } else {
+          ADEPT_TRY(edfdv_exp_f64(fstar[k], out[k], s.batch, s.nx, sp.nv, s.e_out, s.dex, s.pond, sp.charge, sp.mass,
+                                  s.dt, sp.k1v, st));
+        }
+      }
+      collided = true;
+    } else {
+      ADEPT_TRY(c.push_v(fstar, out, s.dt, 0));
+    }
   } else {
     // sixth-order Hamiltonian splitting (vector_field.py:118-186)
     const double dt = s.dt;
@@ -254,7 +273,7 @@ int step_f64(const adept_b200_step& s, cudaStream_t st) {
   }
 
   // collisions on the reference species, in place (vector_field.py:238)
-  if (s.fp_on || s.krook_on) {
+  if ((s.fp_on || s.krook_on) && !collided) {
     const adept_b200_species& sp = s.species[s.collide_species];
     ADEPT_TRY(collide_f64(sp.f_out, sp.f_out, s.batch, s.nx, sp.nv, sp.v, sp.dv, s.dt, s.fp_on ? s.nu_fp_space : nullptr,
                           s.krook_on ? s.nu_K_space : nullptr, s.f_mx, s.fp_model, s.fp_scheme, s.fp_nodrag, s.sg_m,

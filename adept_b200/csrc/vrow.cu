@@ -1,0 +1,177 @@
+// Fused v-row kernel: spectral v-advection followed by the Fokker-Planck collision step on the same rows, one HBM read
+// and one HBM write of f for both operators (32 B per cell instead of 2 x 16 B + the round trip through HBM).
+//
+// Reference semantics: VelocityExponential.push (adept/_vlasov1d/solvers/pushers/vlasov.py:74-91) followed by
+// Collisions._collide / _solve_one_x (adept/_vlasov1d/solvers/pushers/fokker_planck.py:368-433), as composed by
+// VlasovPoissonFokkerPlanck.__call__ (adept/_vlasov1d/solvers/vector_field.py:236-238).
+//
+// One row pair per CTA of T = nv/16 threads.  The pair is transformed as one complex FFT (push_core.cuh), the result
+// a'[e], b'[e] (e = t + T m) is scattered from registers into two chunk-padded row buffers that alias the Stockham
+// exchange buffer (same size: 17/16 nv complex = 2 x 17/16 nv doubles), each row is solved by fp_row_fast
+// (collide_core.cuh) with the same T threads (16 contiguous cells each), and the rows are stored coalesced.
+#include "collide_core.cuh"
+#include "internal.h"
+#include "push_core.cuh"
+
+namespace adept {
+
+struct VrowArgs {
+  const double* fin;
+  double* fout;
+  long long npairs;  // batch * nx / 2
+  int nx;
+  const double* e;
+  const double* dex;   // nullable
+  const double* pond;  // nullable
+  double q, m, dt, k1;
+  const cplx* tw;
+  int zero;
+  // collisions
+  const double* v;  // [nv]
+  double dv;
+  const double* nu_fp;  // [batch*nx]
+  double nu_fp_scale;
+  int model;
+};
+
+template <int LOGN>
+struct VrowCfg {
+  using C = FftCfg<LOGN>;
+  using PC = PhaseCfg<LOGN>;
+  static constexpr int N = C::N, T = C::T;
+  static_assert(C::E == 16, "fused v-row kernel needs nv >= 16");
+  static constexpr int THREADS = T < 32 ? 32 : T;
+  static constexpr bool WARP_MODE = (T % 32) == 0;
+  static constexpr size_t BUF_BYTES = (size_t)C::BUF * sizeof(cplx);            // == 2 rows x (N + T) doubles
+  static constexpr size_t AP_BYTES = (size_t)N * sizeof(double);                // also hosts the phase tables
+  static constexpr size_t RED_BYTES = (size_t)2 * (WARP_MODE ? T / 32 : (T > 32 ? T : 32)) * 3 * sizeof(double);
+  static constexpr size_t PCR_BYTES = (size_t)6 * T * sizeof(double);
+  static constexpr size_t SMEM = BUF_BYTES + AP_BYTES + RED_BYTES + PCR_BYTES;
+  static_assert(2 * PC::PER_SEQ * sizeof(cplx) <= AP_BYTES || N < 128, "phase tables alias the spike buffer");
+};
+
+template <int LOGN>
+__global__ void __launch_bounds__(VrowCfg<LOGN>::THREADS, (VrowCfg<LOGN>::THREADS <= 256 ? 2 : 1))
+    vpush_collide_kernel(VrowArgs p) {
+  using K = VrowCfg<LOGN>;
+  using C = FftCfg<LOGN>;
+  using PC = PhaseCfg<LOGN>;
+  constexpr int N = C::N, E = C::E, T = C::T;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* buf = reinterpret_cast<cplx*>(smem_raw);
+  double* apbuf = reinterpret_cast<double*>(smem_raw + K::BUF_BYTES);
+  cplx* ph = reinterpret_cast<cplx*>(apbuf);  // phase tables live in the spike buffer until the FFTs are done
+  double* red = reinterpret_cast<double*>(smem_raw + K::BUF_BYTES + K::AP_BYTES);
+  double* pcr = reinterpret_cast<double*>(smem_raw + K::BUF_BYTES + K::AP_BYTES + K::RED_BYTES);
+
+  const int t = threadIdx.x < T ? threadIdx.x : 0;  // spare threads (T < 32) shadow thread 0 and never store
+  const bool live = threadIdx.x < T;
+  const long long row0 = 2 * (long long)blockIdx.x;
+  const double* a_in = p.fin + row0 * N;
+  const double* b_in = a_in + N;
+
+  double alpha[2];
+  {
+    const double q2m = p.q * p.q / p.m;
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+      double ee = p.e[row0 + s];
+      if (p.dex) ee = __dadd_rn(ee, p.dex[row0 + s]);
+      const double pd = p.pond ? p.pond[row0 + s] : 0.0;
+      alpha[s] = p.k1 * (p.dt * accel_of(ee, pd, p.q, q2m, p.m));
+    }
+  }
+  if (live) phase_table_fill<LOGN>(ph, alpha[0], alpha[1], t, T);
+
+  cplx x[E];
+#pragma unroll
+  for (int m = 0; m < E; m++) {
+    const int e = t + T * m;
+    x[m] = cmake(__ldcs(a_in + e), __ldcs(b_in + e));
+  }
+  fft_forward<LOGN>(x, buf, p.tw, t, p.zero);
+  half_spectrum_update<LOGN, 1>(x, buf, ph, t);
+  fft_forward<LOGN>(x, buf, p.tw + p.zero, t, p.zero);
+
+  // registers (e = t + T m) -> chunk-padded rows (cell i at i + i/16); the row buffers alias the exchange buffer
+  double* rowA = reinterpret_cast<double*>(buf);
+  double* rowB = rowA + (N + T);
+  __syncthreads();  // every thread is done reading the exchange buffer and the phase tables
+  if (live) {
+#pragma unroll
+    for (int m = 0; m < E; m++) {
+      const int e = t + T * m;
+      rowA[e + (e >> 4)] = x[m].y;
+      rowB[e + (e >> 4)] = x[m].x;
+    }
+  }
+  __syncthreads();
+
+  int parity = 0;
+  const double vc = __ldg(p.v + 16 * t);
+  // NOTE: spare threads (T < 32) would corrupt shared state in fp_row_fast; the launcher only uses this kernel for T >= 32
+  fp_row_fast<16>(rowA, apbuf, red, pcr, parity, t, T, N, vc, p.dv, p.dt, __dmul_rn(p.nu_fp_scale, p.nu_fp[row0]),
+                  p.model);
+  fp_row_fast<16>(rowB, apbuf, red, pcr, parity, t, T, N, vc, p.dv, p.dt, __dmul_rn(p.nu_fp_scale, p.nu_fp[row0 + 1]),
+                  p.model);
+
+  double* a_out = p.fout + row0 * N;
+  double* b_out = a_out + N;
+  for (int i = t; i < N; i += T) {
+    __stcs(a_out + i, rowA[i + (i >> 4)]);
+    __stcs(b_out + i, rowB[i + (i >> 4)]);
+  }
+}
+
+template <int LOGN>
+static int launch_vrow(const VrowArgs& p, cudaStream_t stream) {
+  using K = VrowCfg<LOGN>;
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto kern = vpush_collide_kernel<LOGN>;
+  if (dev < 64 && !configured[dev]) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
+    if (err != cudaSuccess) {
+      set_last_error("cudaFuncSetAttribute(vpush_collide, smem=%zu): %s", K::SMEM, cudaGetErrorString(err));
+      return ADEPT_ERR_CUDA;
+    }
+    configured[dev] = true;
+  }
+  ProfileScope prof("vpush_collide", stream);
+  kern<<<(unsigned)p.npairs, K::THREADS, K::SMEM, stream>>>(p);
+  return check_launch("vpush_collide_kernel");
+}
+
+bool vpush_collide_supported(int nx, int nv, int model, int scheme, int nodrag) {
+  if (nx < 2 || (nx & 1)) return false;
+  if (nv < 512 || nv > 8192 || (nv & (nv - 1))) return false;  // T = nv/16 >= 32 threads, power-of-two FFT
+  return scheme == FP_CENTRAL && (model == FP_LB || model == FP_DOUGHERTY) && !nodrag;
+}
+
+int vpush_collide_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* e, const double* dex,
+                      const double* pond, double q, double m, double dt, double k1v, const double* v, double dv,
+                      const double* nu_fp, double nu_fp_scale, int model, cudaStream_t stream) {
+  if (batch < 1 || !vpush_collide_supported(nx, nv, model, FP_CENTRAL, 0)) {
+    set_last_error("vpush_collide: unsupported shape batch=%d nx=%d nv=%d / model=%d", batch, nx, nv, model);
+    return ADEPT_ERR_UNSUPPORTED;
+  }
+  int logn = 0;
+  while ((1 << logn) < nv) logn++;
+  VrowArgs p = {};
+  p.fin = fin, p.fout = fout, p.npairs = (long long)batch * nx / 2, p.nx = nx;
+  p.e = e, p.dex = dex, p.pond = pond, p.q = q, p.m = m, p.dt = dt, p.k1 = k1v;
+  p.tw = get_twiddles(logn), p.zero = 0;
+  p.v = v, p.dv = dv, p.nu_fp = nu_fp, p.nu_fp_scale = nu_fp_scale, p.model = model;
+  if (!p.tw) return ADEPT_ERR_CUDA;
+  switch (logn) {
+    case 9: return launch_vrow<9>(p, stream);
+    case 10: return launch_vrow<10>(p, stream);
+    case 11: return launch_vrow<11>(p, stream);
+    case 12: return launch_vrow<12>(p, stream);
+    case 13: return launch_vrow<13>(p, stream);
+  }
+  return ADEPT_ERR_UNSUPPORTED;
+}
+
+}  // namespace adept

@@ -67,6 +67,18 @@ def vdfdx(f, v, dt, k1x, out=None, k1x_batch=None):
     return out
 
 
+def vpush_collide(f, e, pond, q, m, dt, k1v, v, dv, nu_fp, model=1, dex=None, out=None):
+    """Fused spectral v-advection + Fokker-Planck step (vector_field.py:236-238), one read and one write of f."""
+    b, nx, nv = _shape3(f)
+    out = torch.empty_like(f) if out is None else out
+    rc = _lib.load().adept_b200_vpush_collide_f64(
+        _ptr(f, "f"), _ptr(out, "out"), b, nx, nv, _ptr(e, "e"), _ptr(dex, "dex", True), _ptr(pond, "pond", True),
+        float(q), float(m), float(dt), float(k1v), _ptr(v, "v"), float(dv), _ptr(nu_fp, "nu_fp"), int(model), _stream())
+    _lib.check(rc, "vpush_collide")
+    _count()
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------- adjoints
 def edfdv_exp_bwd_accel(f_in, g, e, pond, q, m, dt, k1v, dex=None, out=None):
     """accel_bar[.., i] = sum_j g_ij d f'_ij / d accel_i of :func:`edfdv_exp` (f_in = the forward input)."""

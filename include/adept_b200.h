@@ -74,6 +74,14 @@ int adept_b200_vdfdx_rho_f64(const double* f_in, double* f_out, int batch, int n
 int adept_b200_reduce_parts_f64(const double* parts, int nparts, long long n, double scale_a, double scale_b,
                                 const double* base, double* out, void* stream);
 
+/* Fused v-advection + Fokker-Planck step on the same rows (VelocityExponential.push followed by Collisions,
+ * vector_field.py:236-238): f_out = collide(edfdv_exp(f_in)), one read and one write of f for both operators.
+ * Central differencing, model = Lenard-Bernstein or Dougherty, no Krook; nv a power of two in [512, 8192], nx even.
+ * Returns ADEPT_B200_ERR_UNSUPPORTED otherwise (callers then use the two separate entry points).  In-place allowed. */
+int adept_b200_vpush_collide_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* e,
+                                 const double* dex, const double* pond, double charge, double mass, double dt,
+                                 double k1v, const double* v, double dv, const double* nu_fp, int model, void* stream);
+
 /* In-loop save moments in one pass over f (get_default_save_func / get_field_save_func, adept/_vlasov1d/storage.py:
  * 286-327, 119-162): out[k, row] = dv sum_j g_k(f_j, v_j), g = { f, f v, f v^2, f v^3, -|f| log|f|, f^2 }, out is
  * [6, batch*nx].  With f1 != NULL the distribution is the linear interpolation f0 + w (f1 - f0) that diffrax hands to

@@ -327,6 +327,25 @@ def test_collide_strongly_collisional(ops):
     assert rel_l2(out, ref) <= 1e-11  # ill-conditioned limit (nu dt D/dv^2 ~ 1.6e5): allow 10x
 
 
+@pytest.mark.parametrize("fp_type", ["lenard_bernstein", "dougherty"])
+@pytest.mark.parametrize("nx,nv", [(4, 512), (6, 1024), (2, 4096), (2, 8192)])
+def test_fused_vpush_collide_matches_oracle(ops, fp_type, nx, nv):
+    """VelocityExponential followed by Collisions (vector_field.py:236-238) in one kernel."""
+    coll = O.Collisions(_fp_cfg(nv, 6.4, fp_type))
+    f, x, v, dx, dv = make_f(nx, nv, seed=nv + 1, noise=0.0)
+    f = f * (1 + 0.05 * np.sin(7 * v))[None, :]
+    rng = np.random.default_rng(nv)
+    e, dex, pond = 0.3 * rng.standard_normal(nx), 0.01 * rng.standard_normal(nx), 0.02 * rng.standard_normal(nx)
+    kvr = np.fft.rfftfreq(nv, d=dv) * 2 * np.pi
+    q, m, dt = -1.0, 1.0, 0.1
+    for nu in (np.linspace(0.2, 1.0, nx), 1e-5 * np.ones(nx)):
+        ref = coll(nu, None, O.velocity_exponential(f, kvr, e + dex, pond, dt, q, m), dt)
+        out = host(ops.vpush_collide(dev(f), dev(e), dev(pond), q, m, dt, kvr[1], dev(v), dv, dev(nu),
+                                     model=MODEL[coll.model], dex=dev(dex)))
+        amp = dt * nu.max() / dv**2
+        assert rel_l2(out, ref) <= max(RTOL, 2e-16 * amp)
+
+
 @pytest.mark.parametrize("fp_on", [True, False])
 def test_collide_krook_and_density_output(ops, fp_on):
     nx, nv = 12, 256
