@@ -14,6 +14,11 @@
 #pragma once
 #include "common.cuh"
 
+// Phase tracing hook (tools/micro/vpush_trace.cu defines it to record clock64() per warp); a no-op in the library.
+#ifndef ADEPT_TRACE
+#define ADEPT_TRACE(id)
+#endif
+
 namespace adept {
 
 template <int LOGN>
@@ -172,32 +177,40 @@ struct FftPass {
 #pragma unroll
         for (int m = 0; m < 16; m++) x[m] = buf[fft_pad(t + T * m) * BS];
       }
-      // Twiddles are fetched one column (4 values) at a time.  The address of column c+1 carries a data dependency
-      // on a twiddle of column c (`opaque_zero` is 0 at run time, unknown to ptxas), so at most two columns of
-      // twiddles are in flight: without it ptxas hoists all 15 loads (60 registers) and spills.
-      int dep = 0;
+      ADEPT_TRACE(10 * P + 0);
+      // Twiddles: only w^1, w^2, w^3 and w^4, w^8, w^12 are loaded (6 of the 15 powers).  u[c + 4j] = x[c + 4j] w^(c + 4j)
+      // = w^c (x[c + 4j] (w^4)^j): the inputs are scaled by (w^4)^j, the column DFT4 runs, and its four outputs are
+      // scaled by w^c.  24 complex multiplications instead of 15, but 9 fewer 16-byte loads per butterfly: the L1/LSU
+      // data pipe is the busiest unit of the spectral pushes (about 30 % of its time went to twiddle loads), the fp64
+      // pipe has the headroom.  (With 15 loads ptxas also hoisted all of them and spilled.)
+      if constexpr (NS > 1) {
+        const cplx w4 = __ldg(twp + 3 * NS), w8 = __ldg(twp + 7 * NS), w12 = __ldg(twp + 11 * NS);
+        cplx wc[4];
 #pragma unroll
-      for (int c = 0; c < 4; c++) {
-        if constexpr (NS > 1) {
-          cplx w[4];
+        for (int c = 1; c < 4; c++) wc[c] = __ldg(twp + (c - 1) * NS);
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const int r = c + 4 * j;
-            if (r > 0) w[j] = __ldg(twp + (r - 1) * NS + dep);
-          }
-          dep = __double2hiint(w[1].x) & opaque_zero;
+        for (int c = 0; c < 4; c++) {
+          x[c + 4] = cmul(x[c + 4], w4);
+          x[c + 8] = cmul(x[c + 8], w8);
+          x[c + 12] = cmul(x[c + 12], w12);
+          dft4(x[c], x[c + 4], x[c + 8], x[c + 12]);
+          if (c > 0) {
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const int r = c + 4 * j;
-            if (r > 0) x[r] = cmul(x[r], w[j]);
+            for (int j = 0; j < 4; j++) x[c + 4 * j] = cmul(x[c + 4 * j], wc[c]);
           }
         }
-        dft4(x[c], x[c + 4], x[c + 8], x[c + 12]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; c++) dft4(x[c], x[c + 4], x[c + 8], x[c + 12]);
       }
+      (void)opaque_zero;
       // every read of buf by this thread is complete: the barrier that protects the exchange buffer goes here, so the
       // second half of the butterfly overlaps (fp64 pipe) with the stores of the exchange (LSU pipe)
+      ADEPT_TRACE(10 * P + 1);
       if constexpr (P < C::NPASS - 1) __syncthreads();
+      ADEPT_TRACE(10 * P + 2);
       dft16_finish(x);
+      ADEPT_TRACE(10 * P + 3);
     } else {
       if constexpr (P > 0) {
 #pragma unroll
@@ -229,7 +242,9 @@ struct FftPass {
 #pragma unroll
         for (int r = 0; r < R; r++) buf[fft_pad(j0 + r * NS) * BS] = x[q + r * Q];
       }
+      ADEPT_TRACE(10 * P + 4);
       __syncthreads();
+      ADEPT_TRACE(10 * P + 5);
       FftPass<LOGN, P + 1, BS>::run(x, buf, tw, t, opaque_zero);
     }
   }

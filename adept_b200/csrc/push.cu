@@ -101,8 +101,6 @@ __global__ void __launch_bounds__(PushCfg<LOGN, AXIS>::THREADS, (PushCfg<LOGN, A
     }
   }
 
-  phase_table_fill<LOGN>(ph, alpha_a, alpha_b, t, T);
-
   // ---- load: x[m] = a[e] + i b[e], e = t + T m -----------------------------------------------------------
   cplx x[E];
   if (active) {
@@ -125,6 +123,9 @@ __global__ void __launch_bounds__(PushCfg<LOGN, AXIS>::THREADS, (PushCfg<LOGN, A
 #pragma unroll
     for (int m = 0; m < E; m++) x[m] = cmake(0.0, 0.0);
   }
+
+  // after the loads are in flight: the sincos latency of the filling warps hides behind the HBM latency of the loads
+  phase_table_fill<LOGN>(ph, alpha_a, alpha_b, t, T);
 
   fft_forward<LOGN>(x, buf, p.tw, t, p.zero);
 

@@ -30,19 +30,13 @@ __device__ __forceinline__ void phase_table_fill(cplx* ph, double alpha_a, doubl
     const int s = i / PC::PER_SEQ, j = i % PC::PER_SEQ;
     const double al = s ? alpha_b : alpha_a;
     const double sc = 0.5 / (double)N;
+    // one sincos per entry on a common path (divergent per-kind branches cost the filling warps ~3000 cycles)
+    const bool lo = j < PC::NLO, nyq = j == PC::NYQ;
+    const int mult = lo ? j : (j < PC::STEP ? ((j - PC::NLO) << PC::LOBT) : (j == PC::STEP ? T : N / 2));
     double sn, cs;
-    if (j < PC::NLO) {
-      sincos((double)j * al, &sn, &cs);
-      ph[i] = cmake(cs * sc, -sn * sc);
-    } else if (j < PC::STEP) {
-      sincos((double)((j - PC::NLO) << PC::LOBT) * al, &sn, &cs);
-      ph[i] = cmake(cs, -sn);
-    } else if (j == PC::STEP) {
-      sincos((double)T * al, &sn, &cs);
-      ph[i] = cmake(cs, -sn);
-    } else {
-      ph[i] = cmake(cos((double)(N / 2) * al) * sc, 0.0);
-    }
+    sincos((double)mult * al, &sn, &cs);
+    const double amp = (lo || nyq) ? sc : 1.0;
+    ph[i] = cmake(cs * amp, nyq ? 0.0 : -sn * amp);
   }
 }
 

@@ -81,14 +81,13 @@ __global__ void __launch_bounds__(VrowCfg<LOGN>::THREADS, (VrowCfg<LOGN>::THREAD
       alpha[s] = p.k1 * (p.dt * accel_of(ee, pd, p.q, q2m, p.m));
     }
   }
-  if (live) phase_table_fill<LOGN>(ph, alpha[0], alpha[1], t, T);
-
   cplx x[E];
 #pragma unroll
   for (int m = 0; m < E; m++) {
     const int e = t + T * m;
     x[m] = cmake(__ldcs(a_in + e), __ldcs(b_in + e));
   }
+  if (live) phase_table_fill<LOGN>(ph, alpha[0], alpha[1], t, T);  // sincos latency hides behind the loads in flight
   fft_forward<LOGN>(x, buf, p.tw, t, p.zero);
   half_spectrum_update<LOGN, 1>(x, buf, ph, t);
   fft_forward<LOGN>(x, buf, p.tw + p.zero, t, p.zero);

@@ -3,6 +3,9 @@
     python tools/kbench.py [nx nv [iters]]
 """
 import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 
 import numpy as np
 import torch
@@ -58,3 +61,6 @@ timeit("moments(n)", lambda: ops.moments(fd, vd, dv, (rho, None, None)), 8.0)
 timeit("collide_dough", lambda: ops.collide(fd, vd, dv, 0.1, nu_fp=nu, model=1, scheme=0, out=gd))
 timeit("collide_cc", lambda: ops.collide(fd, vd, dv, 0.1, nu_fp=nu, model=1, scheme=1, out=gd))
 timeit("poisson", lambda: ops.poisson(rho, rho), 0.0)
+parts = torch.zeros((ops.vdfdx_rho_parts(fd), nx), dtype=torch.float64, device="cuda")
+timeit("vdfdx_rho(tma)", lambda: ops.vdfdx_rho(fd, vd, 0.1, k1x, parts, out=gd))
+timeit("vpush_collide", lambda: ops.vpush_collide(fd, e, None, -1.0, 1.0, 0.1, k1v, vd, dv, nu, model=1, out=gd), 32.0)

@@ -1,5 +1,8 @@
 """Run one operator a few times at the C3 size (for ncu captures).   python tools/kone.py <op> [nx nv iters]"""
 import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 
 import numpy as np
 import torch
