@@ -44,6 +44,7 @@ class Step(C.Structure):
         ("fp_on", c_i), ("krook_on", c_i), ("fp_model", c_i), ("fp_scheme", c_i), ("fp_nodrag", c_i),
         ("sg_m", c_d), ("sg_ratio", c_d),
         ("nu_fp_space", c_dp), ("nu_K_space", c_dp), ("nu_fp_time", c_d), ("nu_K_time", c_d), ("f_mx", c_dp),
+        ("sync_counter", c_dp),
     ]
 
 

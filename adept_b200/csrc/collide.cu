@@ -303,8 +303,9 @@ __global__ void __launch_bounds__(MAXT, MINB) collide_kernel(CollideArgs p) {
       cur[RT + me] = ga;
       cur[2 * RT + me] = rh;
     }
-    __syncthreads();
-    for (int s = 1; s < T; s <<= 1) {
+    // early termination: see fp_row_fast (collide_core.cuh); the vote covers every row of the CTA
+    int more = __syncthreads_or(live && (fabs(al) > PCR_TOL || fabs(ga) > PCR_TOL));
+    for (int s = 1; s < T && more; s <<= 1) {
       double alj = 0.0, gaj = 0.0, rhj = 0.0, alk = 0.0, gak = 0.0, rhk = 0.0;
       if (tt - s >= 0) {
         alj = cur[me - s];
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(MAXT, MINB) collide_kernel(CollideArgs p) {
         nxt[RT + me] = ga;
         nxt[2 * RT + me] = rh;
       }
-      __syncthreads();
+      more = __syncthreads_or(live && (fabs(al) > PCR_TOL || fabs(ga) > PCR_TOL));
       double* tmp = cur;
       cur = nxt;
       nxt = tmp;

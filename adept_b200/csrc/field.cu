@@ -100,26 +100,23 @@ int poisson_f64(const double* rho, const double* kmul, long long kmul_stride, do
   return check_launch("poisson_kernel");
 }
 
-// nx = 4096 / 8192: same kernel body but with dynamic shared memory (> 48 KiB)
+// Poisson / Boltzmann-Poisson solve of one member by the T threads of a CTA; `buf` is the FFT exchange buffer
+// (FftCfg<LOGN>::BUF complex), `rho0_s` one shared double.  LDCG: rho may have been written by other CTAs of the same
+// launch (fused field kernel), so the loads bypass L1.
 template <int LOGN>
-__global__ void __launch_bounds__(FftCfg<LOGN>::T) poisson_kernel_big(PoissonArgs p) {
+__device__ __forceinline__ void poisson_body(const PoissonArgs& p, const double* rho, const double* kmul, double* eo,
+                                             cplx* buf, double* rho0_s) {
   using C = FftCfg<LOGN>;
   constexpr int N = C::N, E = C::E, T = C::T;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  cplx* buf = reinterpret_cast<cplx*>(smem_raw);
-  __shared__ double rho0_s;
   const int t = threadIdx.x;
-  const double* rho = p.rho + (long long)blockIdx.x * N;
-  const double* kmul = p.kmul + (long long)blockIdx.x * p.kmul_stride;
-  double* eo = p.e + (long long)blockIdx.x * N;
   fft_prefetch_twiddles<LOGN>(p.tw, t);
   cplx x[E];
 #pragma unroll
-  for (int m = 0; m < E; m++) x[m] = cmake(rho[t + T * m], 0.0);
+  for (int m = 0; m < E; m++) x[m] = cmake(__ldcg(rho + t + T * m), 0.0);
   fft_forward<LOGN>(x, buf, p.tw, t, p.zero);
-  if (t == 0) rho0_s = x[0].x / (double)N;
+  if (t == 0) *rho0_s = x[0].x / (double)N;
   __syncthreads();
-  const double rho0 = rho0_s;
+  const double rho0 = *rho0_s;
 #pragma unroll
   for (int m = 0; m < E; m++) {
     const int k = t + T * m;
@@ -138,6 +135,16 @@ __global__ void __launch_bounds__(FftCfg<LOGN>::T) poisson_kernel_big(PoissonArg
   fft_forward<LOGN>(x, buf, p.tw, t, p.zero);
 #pragma unroll
   for (int m = 0; m < E; m++) eo[t + T * m] = x[m].y / (double)N;
+}
+
+// nx = 4096 / 8192: same solve with dynamic shared memory (> 48 KiB)
+template <int LOGN>
+__global__ void __launch_bounds__(FftCfg<LOGN>::T) poisson_kernel_big(PoissonArgs p) {
+  constexpr int N = FftCfg<LOGN>::N;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double rho0_s;
+  poisson_body<LOGN>(p, p.rho + (long long)blockIdx.x * N, p.kmul + (long long)blockIdx.x * p.kmul_stride,
+                     p.e + (long long)blockIdx.x * N, reinterpret_cast<cplx*>(smem_raw), &rho0_s);
 }
 
 template <int LOGN>
@@ -269,6 +276,149 @@ int wave_step_f64(const double* a, const double* aold, const double* djy, const 
   ProfileScope prof("wave_step", stream);
   wave_kernel<<<grid, 256, 0, stream>>>(p);
   return check_launch("wave_kernel");
+}
+
+
+// ---- fused field solve for one large grid (batch == 1) ------------------------------------------------------------
+// One launch replaces ex_driver + ponderomotive + reduce_parts (per species) + Poisson of the leapfrog step
+// (vector_field.py:87-95 calling field.py:479-497, 197-224, 21-33): every CTA finishes the charge density of 64 grid
+// points from the per-CTA partial sums the x-advection left behind (fixed summation order), evaluates the
+// ponderomotive force and the driver field there, and the CTA that arrives last at a device-side ticket counter solves
+// Poisson's equation for the whole grid.  The counter is reset by that CTA, so consecutive launches on one stream
+// need no host work; it must be zero before the first launch.
+struct FieldFusedArgs {
+  int nsp;
+  const double* parts[4];
+  int nparts[4];
+  double dv[4], charge[4];
+  const double* base;  // static background (nullable)
+  double* rho;
+  int nx;
+  const double* a;  // [nx + 2]
+  double* pond;
+  double dx;
+  int n_ex;  // 0: the driver field is not evaluated here
+  const double* ex_space;
+  const double* ex_kx;
+  double* dex;
+  double ex_w[8], ex_a0[8], ex_tenv[8], ex_wt[8];
+  PoissonArgs po;
+  unsigned int* counter;
+};
+
+template <int LOGN>
+__global__ void __launch_bounds__(FftCfg<LOGN>::T) field_fused_kernel(FieldFusedArgs p) {
+  constexpr int T = FftCfg<LOGN>::T;
+  constexpr int NG = T / 64;  // thread groups that split the partial-sum rows
+  static_assert(T >= 64 && NG <= 4, "fused field kernel: 1024 <= nx <= 4096");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double sm[4][64];
+  __shared__ double rho0_s;
+  __shared__ unsigned int ticket_s;
+  const int r = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const int i = blockIdx.x * 64 + r;
+  const int n = p.nx;
+  double acc = p.base ? p.base[i] : 0.0;
+  for (int k = 0; k < p.nsp; k++) {
+    const double* col = p.parts[k] + i;
+    const int np = p.nparts[k];
+    double s[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    int q = g;
+    for (; q + 7 * NG < np; q += 8 * NG) {  // eight independent L2 loads in flight per thread
+      double x[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) x[u] = __ldcg(col + (size_t)(q + u * NG) * n);
+#pragma unroll
+      for (int u = 0; u < 8; u++) s[u] += x[u];
+    }
+    for (; q < np; q += NG) s[0] += __ldcg(col + (size_t)q * n);
+    sm[g][r] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+    __syncthreads();
+    if (g == 0) {
+      double tot = sm[0][r];
+#pragma unroll
+      for (int u = 1; u < NG; u++) tot += sm[u][r];
+      const double term = __dmul_rn(p.charge[k], __dmul_rn(tot, p.dv[k]));
+      acc = (k == 0 && !p.base) ? term : __dadd_rn(acc, term);
+    }
+    __syncthreads();
+  }
+  if (g == 0) {
+    p.rho[i] = acc;
+    // ponderomotive force, field.py:495
+    const double lo = __dmul_rn(p.a[i], p.a[i]), hi = __dmul_rn(p.a[i + 2], p.a[i + 2]);
+    p.pond[i] = __dmul_rn(-0.5, __ddiv_rn(__dsub_rn(hi, lo), __dmul_rn(2.0, p.dx)));
+  }
+  if (p.n_ex > 0 && g == (NG > 1 ? 1 : 0)) {  // driver field at the first substep time, field.py:21-33
+    double total = 0.0;
+    for (int d = 0; d < p.n_ex; d++) {
+      const double factor = __dmul_rn(p.ex_tenv[d], p.ex_space[(size_t)d * n + i]);
+      const double amp = __dmul_rn(__dmul_rn(factor, p.ex_w[d]), p.ex_a0[d]);
+      total = __dadd_rn(total, __dmul_rn(amp, sin(__dsub_rn(p.ex_kx[(size_t)d * n + i], p.ex_wt[d]))));
+    }
+    p.dex[i] = total;
+  }
+  // ---- the last CTA to get here solves for E ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int ticket = atomicAdd(p.counter, 1u);
+    if (ticket == gridDim.x - 1) *p.counter = 0u;  // every other CTA has already taken its ticket
+    ticket_s = ticket;
+  }
+  __syncthreads();
+  if (ticket_s != gridDim.x - 1) return;
+  __threadfence();
+  poisson_body<LOGN>(p.po, p.rho, p.po.kmul, p.po.e, reinterpret_cast<cplx*>(smem_raw), &rho0_s);
+}
+
+bool field_fused_supported(int batch, int nx) { return batch == 1 && (nx == 1024 || nx == 2048 || nx == 4096); }
+
+template <int LOGN>
+static int launch_field_fused(const FieldFusedArgs& p, cudaStream_t stream) {
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const size_t smem = FftCfg<LOGN>::BUF * sizeof(cplx);
+  if (dev < 64 && !configured[dev]) {
+    cudaError_t err =
+        cudaFuncSetAttribute(field_fused_kernel<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) {
+      set_last_error("cudaFuncSetAttribute(field_fused): %s", cudaGetErrorString(err));
+      return ADEPT_ERR_CUDA;
+    }
+    configured[dev] = true;
+  }
+  ProfileScope prof("field_fused", stream);
+  field_fused_kernel<LOGN><<<p.nx / 64, FftCfg<LOGN>::T, smem, stream>>>(p);
+  return check_launch("field_fused_kernel");
+}
+
+int field_fused_f64(int nsp, const double* const* parts, const int* nparts, const double* dv, const double* charge,
+                    const double* base, double* rho, int nx, const double* a, double* pond, double dx, int n_ex,
+                    const double* ex_space, const double* ex_kx, double* dex, const double* ex_w, const double* ex_a0,
+                    const double* ex_tenv, const double* ex_wt, const double* kmul, double* e, int mode, double Te,
+                    double lambda_De, unsigned int* counter, cudaStream_t stream) {
+  if (!field_fused_supported(1, nx) || nsp < 1 || nsp > 4 || n_ex < 0 || n_ex > 8 || !counter) {
+    set_last_error("field_fused: unsupported nx=%d / n_species=%d / n_ex=%d", nx, nsp, n_ex);
+    return ADEPT_ERR_UNSUPPORTED;
+  }
+  const int logn = ilog2_exact(nx);
+  FieldFusedArgs p = {};
+  p.nsp = nsp;
+  for (int k = 0; k < nsp; k++) p.parts[k] = parts[k], p.nparts[k] = nparts[k], p.dv[k] = dv[k], p.charge[k] = charge[k];
+  p.base = base, p.rho = rho, p.nx = nx, p.a = a, p.pond = pond, p.dx = dx;
+  p.n_ex = n_ex, p.ex_space = ex_space, p.ex_kx = ex_kx, p.dex = dex;
+  for (int d = 0; d < n_ex; d++) p.ex_w[d] = ex_w[d], p.ex_a0[d] = ex_a0[d], p.ex_tenv[d] = ex_tenv[d], p.ex_wt[d] = ex_wt[d];
+  p.po = PoissonArgs{rho, kmul, 0, e, mode, Te, lambda_De, get_twiddles(logn), 0};
+  if (!p.po.tw) return ADEPT_ERR_CUDA;
+  p.counter = counter;
+  switch (logn) {
+    case 10: return launch_field_fused<10>(p, stream);
+    case 11: return launch_field_fused<11>(p, stream);
+    case 12: return launch_field_fused<12>(p, stream);
+  }
+  return ADEPT_ERR_UNSUPPORTED;
 }
 
 }  // namespace adept

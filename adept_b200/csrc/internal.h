@@ -15,6 +15,12 @@ int moments_f64(const double* f, int batch, int nx, int nv, const double* v, dou
 int axpy_f64(const double* a, const double* b, double s, double* out, long long n, cudaStream_t stream);
 int poisson_dispatch_f64(const double* rho, const double* kmul, long long kmul_stride, double* e, int batch, int nx,
                          int mode, double Te, double lambda_De, cudaStream_t stream);
+bool field_fused_supported(int batch, int nx);
+int field_fused_f64(int nsp, const double* const* parts, const int* nparts, const double* dv, const double* charge,
+                    const double* base, double* rho, int nx, const double* a, double* pond, double dx, int n_ex,
+                    const double* ex_space, const double* ex_kx, double* dex, const double* ex_w, const double* ex_a0,
+                    const double* ex_tenv, const double* ex_wt, const double* kmul, double* e, int mode, double Te,
+                    double lambda_De, unsigned int* counter, cudaStream_t stream);
 int ponderomotive_f64(const double* a, double* pond, int batch, int nx, double dx, cudaStream_t stream);
 int wave_step_f64(const double* a, const double* aold, const double* djy, const double* ne_n, const double* ne_np1,
                   double* a_new, int batch, int nx, double c, double dx, double dt, cudaStream_t stream);

@@ -59,10 +59,12 @@ struct StepCtx {
       have_parts[k] = false;
       if (want_rho && sp.rho_parts && vdfdx_tma_supported(cur[k], dst[k], s.nx, sp.nv) &&
           sp.rho_nparts >= vdfdx_tma_parts(s.batch, s.nx, sp.nv)) {
-        cudaError_t err = cudaMemsetAsync(sp.rho_parts, 0, (size_t)sp.rho_nparts * n * sizeof(double), st);
-        if (err != cudaSuccess) {
-          set_last_error("step: cudaMemsetAsync(rho_parts): %s", cudaGetErrorString(err));
-          return ADEPT_ERR_CUDA;
+        if (s.batch > 1) {  // a single member is overwritten by every CTA of the x-advection; ensembles accumulate
+          cudaError_t err = cudaMemsetAsync(sp.rho_parts, 0, (size_t)sp.rho_nparts * n * sizeof(double), st);
+          if (err != cudaSuccess) {
+            set_last_error("step: cudaMemsetAsync(rho_parts): %s", cudaGetErrorString(err));
+            return ADEPT_ERR_CUDA;
+          }
         }
         ADEPT_TRY(vdfdx_tma_f64(cur[k], dst[k], s.batch, s.nx, sp.nv, sp.v, dt, s.k1x_batch, s.k1x, sp.rho_parts, st));
         have_parts[k] = true;
@@ -75,8 +77,30 @@ struct StepCtx {
     return ADEPT_OK;
   }
 
-  // (pond, e) = field_solve(f); field.py:479-497.  from_parts: the velocity sums come from the preceding push_x
-  int field_solve(const double* const* cur, bool from_parts, double dt) const {
+  // true when the next field_solve(from_parts = true) runs as ONE fused launch (field.cu: field_fused_kernel)
+  bool can_fuse_field() const {
+    if (s.field == 2 || !s.sync_counter || !field_fused_supported(s.batch, s.nx)) return false;
+    for (int k = 0; k < s.n_species; k++)
+      if (!have_parts[k]) return false;
+    return true;
+  }
+
+  // (pond, e) = field_solve(f); field.py:479-497.  from_parts: the velocity sums come from the preceding push_x.
+  // driver_here: also evaluate the Ex driver field of substep 0 (leapfrog) in the fused launch.
+  int field_solve(const double* const* cur, bool from_parts, double dt, bool driver_here = false) const {
+    if (from_parts && can_fuse_field()) {
+      const double* parts[ADEPT_B200_MAX_SPECIES];
+      int nparts[ADEPT_B200_MAX_SPECIES];
+      double dv[ADEPT_B200_MAX_SPECIES], charge[ADEPT_B200_MAX_SPECIES];
+      for (int k = 0; k < s.n_species; k++) {
+        const adept_b200_species& sp = s.species[k];
+        parts[k] = sp.rho_parts, nparts[k] = vdfdx_tma_parts(s.batch, s.nx, sp.nv), dv[k] = sp.dv, charge[k] = sp.charge;
+      }
+      return field_fused_f64(s.n_species, parts, nparts, dv, charge, s.field == 0 ? s.ion_charge : nullptr, s.rho, s.nx,
+                             s.a, s.pond, s.dx, driver_here ? s.n_ex : 0, s.ex_space, s.ex_kx, s.dex, s.ex_w, s.ex_a0,
+                             s.ex_tenv[0], s.ex_wt[0], s.kmul, s.e_out, s.field == 1 ? 1 : 0, s.Te, s.lambda_De,
+                             s.sync_counter, st);
+    }
     ADEPT_TRY(ponderomotive_f64(s.a, s.pond, s.batch, s.nx, s.dx, st));
     if (s.field == 2) {  // ampere: E = E_prev - dt * sum_s q_s dv_s sum_v v f_s   (field.py:330-354)
       const double* base = nullptr;
@@ -185,8 +209,9 @@ int step_f64(const adept_b200_step& s, cudaStream_t st) {
   StepCtx c{s, st, (long long)s.batch * s.nx};
   const int n_sub = s.time_integrator == 0 ? 1 : ADEPT_B200_MAX_SUBSTEPS;
 
-  // drivers at the substep times (vector_field.py:319)
-  {
+  // drivers at the substep times (vector_field.py:319); the leapfrog step defers this until it knows whether the
+  // fused field kernel evaluates the driver itself
+  auto launch_drivers = [&]() -> int {
     DriverArgs d = {};
     d.n_ex = s.n_ex, d.n_sub = n_sub, d.n = c.n, d.space = s.ex_space, d.kx = s.ex_kx, d.dex = s.dex;
     for (int k = 0; k < ADEPT_B200_MAX_DRIVERS; k++) {
@@ -195,8 +220,9 @@ int step_f64(const adept_b200_step& s, cudaStream_t st) {
     }
     ProfileScope prof("ex_driver", st);
     ex_driver_kernel<<<(unsigned)((c.n + 255) / 256), 256, 0, st>>>(d);
-    ADEPT_TRY(check_launch("ex_driver_kernel"));
-  }
+    return check_launch("ex_driver_kernel");
+  };
+  if (s.time_integrator != 0) ADEPT_TRY(launch_drivers());
 
   const bool wave = s.wave_on != 0;
   const bool wave_density = wave && s.electron_species >= 0;
@@ -216,7 +242,9 @@ int step_f64(const adept_b200_step& s, cudaStream_t st) {
     ADEPT_TRY(c.push_x(cur, xdst, s.dt, want_rho));
     const double* fstar[ADEPT_B200_MAX_SPECIES];
     for (int k = 0; k < s.n_species; k++) fstar[k] = xdst[k];
-    ADEPT_TRY(c.field_solve(fstar, want_rho, s.dt));
+    const bool fused_field = want_rho && c.can_fuse_field();
+    if (!fused_field) ADEPT_TRY(launch_drivers());
+    ADEPT_TRY(c.field_solve(fstar, want_rho, s.dt, fused_field));
     // the colliding species takes the fused v-push + Fokker-Planck kernel when its shape and operator allow it
     const int kc = s.collide_species;
     if (s.fp_on && !s.krook_on && !spline && kc >= 0 && kc < s.n_species &&

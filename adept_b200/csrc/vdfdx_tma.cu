@@ -114,7 +114,8 @@ __global__ void __launch_bounds__(TmaCfg<LOGN>::THREADS, 1)
     __syncthreads();
     double* dst = p.partial + ((size_t)blockIdx.x * p.batch + b) * N;
     for (int i = tid; i < N; i += K::THREADS) {
-      dst[i] += rho_acc[i];
+      // a single member is visited once by every CTA: plain store, no zero-initialisation needed
+      dst[i] = (p.batch == 1) ? rho_acc[i] : dst[i] + rho_acc[i];
       rho_acc[i] = 0.0;
     }
     __syncthreads();

@@ -172,6 +172,7 @@ class NativeStep:
         self.field = self.FIELD[cfg["terms"]["field"]]
         self.dev = {}
         self.scratch = {}
+        self.static = {}
 
     @staticmethod
     def supported(vm) -> bool:
@@ -181,47 +182,45 @@ class NativeStep:
                 and len(cfg["grid"]["species_grids"]) <= _lib.MAX_SPECIES
                 and len(vm.ex_driver.drivers) <= _lib.MAX_DRIVERS)
 
-    def _table(self, key, host_array, device):
+    def _table(self, key, make, device):
+        """Device-resident constant table, built once from ``make()`` (a host array)."""
         k = (key, str(device))
         if k not in self.dev:
-            self.dev[k] = torch.as_tensor(np.array(host_array, dtype=np.float64, order="C"), device=device)
+            self.dev[k] = torch.as_tensor(np.array(make(), dtype=np.float64, order="C"), device=device)
         return self.dev[k]
 
-    def _scratch(self, key, shape, device):
+    def _scratch(self, key, shape, device, zero=False, dtype=torch.float64):
         k = (key, tuple(shape), str(device))
         if k not in self.scratch:
-            self.scratch[k] = torch.empty(shape, dtype=torch.float64, device=device)
+            self.scratch[k] = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=device)
         return self.scratch[k]
 
-    def __call__(self, t, y, wave_on):
+    def _static_step(self, y, dev, batch, wave_on):
+        """struct adept_b200_step with every field that does not change from step to step (tables, scratch, physics
+        switches), built once per (device, batch, wave_on, shapes) and reused: per step only pointers to the state and
+        the O(1) time factors are rewritten."""
+        shapes = tuple(tuple(y[name].shape) for name in self.names)
+        key = (str(dev), batch, bool(wave_on), shapes)
+        if key in self.static:
+            return self.static[key]
         vm, cfg, grid = self.vm, self.cfg, self.vm.grid
         g = cfg["grid"]
-        f0 = y[self.names[0]]
-        dev = f0.device
-        batch = f0.shape[0] if f0.dim() == 3 else 1
         nx = int(g["nx"])
         n = batch * nx
         st = _lib.Step()
         st.batch, st.nx, st.n_species = batch, nx, len(self.names)
-        new = {}
-        keep = []  # tensors that must stay alive until the call returns
         for k, name in enumerate(self.names):
             sg, sp = g["species_grids"][name], g["species_params"][name]
             f = y[name]
-            out = torch.empty_like(f)
-            new[name] = out
             s = st.species[k]
-            s.f_in, s.f_out = f.data_ptr(), out.data_ptr()
             if self.edfdv == 1:
                 s.f_tmp = self._scratch(("tmp", name), f.shape, dev).data_ptr()
-            s.v = self._table(("v", name), sg["v"], dev).data_ptr()
+            s.v = self._table(("v", name), lambda sg=sg: sg["v"], dev).data_ptr()
             s.nv, s.dv, s.k1v = int(f.shape[-1]), float(sg["dv"]), float(sg["kvr"][1])
             s.charge, s.mass = float(sp["charge"]), float(sp["mass"])
             nparts = ops.vdfdx_rho_parts(f)
             s.rho_parts = self._scratch(("parts", name), (nparts, n), dev).data_ptr()
             s.rho_nparts = nparts
-            if not (f.is_cuda and f.dtype == torch.float64 and f.is_contiguous()):
-                raise _lib.AdeptB200Error(f"state['{name}'] must be a contiguous float64 CUDA tensor")
         st.electron_species = self.names.index("electron") if "electron" in self.names else -1
         st.collide_species = self.names.index(vm.vpfp.fp.ref_species)
         st.time_integrator, st.edfdv, st.field = int(self.sixth), self.edfdv, self.field
@@ -230,61 +229,82 @@ class NativeStep:
         fs = vm.vpfp.vlasov_poisson.field_solve
         if self.field == 0:
             if fs.static_charge_density is not None:
-                ion = np.broadcast_to(np.asarray(fs.static_charge_density, dtype=np.float64), (batch, nx))
-                st.ion_charge = self._table(("ion", batch), ion, dev).data_ptr()
-            st.kmul = self._table("kmul", fs.kmul, dev).data_ptr()
+                st.ion_charge = self._table(("ion", batch), lambda: np.broadcast_to(
+                    np.asarray(fs.static_charge_density, dtype=np.float64), (batch, nx)), dev).data_ptr()
+            st.kmul = self._table("kmul", lambda: fs.kmul, dev).data_ptr()
         elif self.field == 1:
-            st.kmul = self._table("kmul", fs.kmul, dev).data_ptr()
+            st.kmul = self._table("kmul", lambda: fs.kmul, dev).data_ptr()
             st.Te, st.lambda_De = fs.Te, fs.lambda_De
         st.kmul_stride = 0
-        e_out = torch.empty_like(y["e"])
-        st.e_in, st.e_out = y["e"].data_ptr(), e_out.data_ptr()
-        n_sub = len(self.dt_array)
-        dex = torch.empty((n_sub,) + tuple(y["e"].shape), dtype=torch.float64, device=dev)
-        st.dex = dex.data_ptr()
-        st.a, st.prev_a = y["a"].data_ptr(), y["prev_a"].data_ptr()
         st.c_light, st.wave_on = float(vm.c), int(bool(wave_on))
         st.pond = self._scratch("pond", (n,), dev).data_ptr()
         st.rho = self._scratch("rho", (n,), dev).data_ptr()
         if wave_on:
-            djy = vm.ey_driver(t + self.dt_a1, None) if vm.has_ey else vm._zeros_a
-            a_out = torch.empty_like(y["a"])
-            keep.append(djy)
-            st.djy, st.a_out = djy.data_ptr(), a_out.data_ptr()
             st.ne_n = self._scratch("ne_n", (n,), dev).data_ptr()
             st.ne_np1 = self._scratch("ne_np1", (n,), dev).data_ptr()
-        else:
-            djy, a_out = vm._zeros_a, None
-        # longitudinal drivers: time factors on the host, space factors resident on the device
+        # longitudinal drivers: space factors resident on the device, time factors filled in per step
         drivers = vm.ex_driver.drivers
         st.n_ex = len(drivers)
         if drivers:
             x = vm._x
-            st.ex_space = self._table("ex_space", np.stack(
+            st.ex_space = self._table(("ex_space", batch), lambda: np.stack(
                 [np.broadcast_to(d.envelope.space_envelope(x), (batch, nx)).reshape(-1) for d in drivers]), dev).data_ptr()
-            st.ex_kx = self._table("ex_kx", np.stack(
+            st.ex_kx = self._table(("ex_kx", batch), lambda: np.stack(
                 [np.broadcast_to(d.k0 * x, (batch, nx)).reshape(-1) for d in drivers]), dev).data_ptr()
             for j, d in enumerate(drivers):
-                w = d.w0 + d.dw0
-                st.ex_w[j], st.ex_a0[j] = w, d.a0
-                for i, dti in enumerate(self.dt_array):
-                    ti = t + dti
-                    st.ex_tenv[i][j] = float(d.envelope.time_envelope(ti))
-                    st.ex_wt[i][j] = w * ti
+                st.ex_w[j], st.ex_a0[j] = d.w0 + d.dw0, d.a0
         # collisions
         fp = vm.vpfp.fp
         st.fp_on, st.krook_on = int(vm.fp_on), int(vm.krook_on)
         st.fp_model, st.fp_scheme, st.fp_nodrag = fp.model, fp.scheme, int(fp.nodrag)
         st.sg_m, st.sg_ratio = fp.m, fp.sg_ratio
         if vm.fp_on:
-            sp_env = np.broadcast_to(vm.nu_fp_prof.space_envelope(vm._x) * np.ones(nx), (batch, nx))
-            st.nu_fp_space = self._table(("nu_fp", batch), sp_env, dev).data_ptr()
+            st.nu_fp_space = self._table(("nu_fp", batch), lambda: np.broadcast_to(
+                vm.nu_fp_prof.space_envelope(vm._x) * np.ones(nx), (batch, nx)), dev).data_ptr()
+        if vm.krook_on:
+            st.nu_K_space = self._table(("nu_K", batch), lambda: np.broadcast_to(
+                vm.nu_K_prof.space_envelope(vm._x) * np.ones(nx), (batch, nx)), dev).data_ptr()
+        st.f_mx = self._table("f_mx", lambda: fp.f_mx, dev).data_ptr()
+        # one device word per integration, zeroed once; the library resets it after every use
+        st.sync_counter = self._scratch("sync_counter", (4,), dev, zero=True, dtype=torch.int32).data_ptr()
+        self.static[key] = st
+        return st
+
+    def __call__(self, t, y, wave_on):
+        vm = self.vm
+        f0 = y[self.names[0]]
+        dev = f0.device
+        batch = f0.shape[0] if f0.dim() == 3 else 1
+        st = self._static_step(y, dev, batch, wave_on)
+        new = {}
+        for k, name in enumerate(self.names):
+            f = y[name]
+            if not (f.is_cuda and f.dtype == torch.float64 and f.is_contiguous()):
+                raise _lib.AdeptB200Error(f"state['{name}'] must be a contiguous float64 CUDA tensor")
+            out = torch.empty_like(f)
+            new[name] = out
+            st.species[k].f_in, st.species[k].f_out = f.data_ptr(), out.data_ptr()
+        e_out = torch.empty_like(y["e"])
+        st.e_in, st.e_out = y["e"].data_ptr(), e_out.data_ptr()
+        dex = torch.empty((len(self.dt_array),) + tuple(y["e"].shape), dtype=torch.float64, device=dev)
+        st.dex = dex.data_ptr()
+        st.a, st.prev_a = y["a"].data_ptr(), y["prev_a"].data_ptr()
+        if wave_on:
+            djy = vm.ey_driver(t + self.dt_a1, None) if vm.has_ey else vm._zeros_a
+            a_out = torch.empty_like(y["a"])
+            st.djy, st.a_out = djy.data_ptr(), a_out.data_ptr()
+        else:
+            djy, a_out = vm._zeros_a, None
+        for j, d in enumerate(vm.ex_driver.drivers):
+            w = d.w0 + d.dw0
+            for i, dti in enumerate(self.dt_array):
+                ti = t + dti
+                st.ex_tenv[i][j] = float(d.envelope.time_envelope(ti))
+                st.ex_wt[i][j] = w * ti
+        if vm.fp_on:
             st.nu_fp_time = float(vm.nu_fp_prof.time_envelope(t))
         if vm.krook_on:
-            sp_env = np.broadcast_to(vm.nu_K_prof.space_envelope(vm._x) * np.ones(nx), (batch, nx))
-            st.nu_K_space = self._table(("nu_K", batch), sp_env, dev).data_ptr()
             st.nu_K_time = float(vm.nu_K_prof.time_envelope(t))
-        st.f_mx = self._table("f_mx", fp.f_mx, dev).data_ptr()
         rc = _lib.load().adept_b200_step_f64(C.byref(st), C.c_void_p(torch.cuda.current_stream().cuda_stream))
         _lib.check(rc, "step")
         ops._count(0)

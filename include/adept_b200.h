@@ -223,6 +223,10 @@ typedef struct adept_b200_step {
   const double* nu_K_space;  /* [batch*nx] */
   double nu_fp_time, nu_K_time; /* nu(x, t) = time * space */
   const double* f_mx;        /* [nv] Krook Maxwellian */
+  /* one zero-initialised device word owned by this integration (the library resets it after every use).  When given,
+   * a single large grid (batch == 1, nx in {1024, 2048, 4096}) runs driver + ponderomotive force + charge density +
+   * Poisson solve as ONE launch whose last-arriving CTA solves for E; null selects the separate kernels. */
+  unsigned int* sync_counter;
 } adept_b200_step;
 
 int adept_b200_step_f64(const adept_b200_step* step, void* stream);

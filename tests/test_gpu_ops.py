@@ -315,6 +315,11 @@ def test_collide_matches_oracle(ops, fp_type, nx, nv):
     ref = coll(nu2, None, f, dt)
     out = host(_gpu_collide(ops, coll, f, nu2, None, dt))
     assert rel_l2(out, ref) <= RTOL
+    # in between: the cyclic reduction terminates early, after a different number of steps per CTA
+    nu3 = np.geomspace(1e-4, 3e-2, nx)
+    ref = coll(nu3, None, f, dt)
+    out = host(_gpu_collide(ops, coll, f, nu3, None, dt))
+    assert rel_l2(out, ref) <= max(RTOL, 2e-16 * dt * nu3.max() / dv**2)
 
 
 def test_collide_strongly_collisional(ops):
@@ -338,7 +343,8 @@ def test_fused_vpush_collide_matches_oracle(ops, fp_type, nx, nv):
     e, dex, pond = 0.3 * rng.standard_normal(nx), 0.01 * rng.standard_normal(nx), 0.02 * rng.standard_normal(nx)
     kvr = np.fft.rfftfreq(nv, d=dv) * 2 * np.pi
     q, m, dt = -1.0, 1.0, 0.1
-    for nu in (np.linspace(0.2, 1.0, nx), 1e-5 * np.ones(nx)):
+    # strong, weak (no cyclic-reduction step needed) and in-between (early termination after a few steps)
+    for nu in (np.linspace(0.2, 1.0, nx), 1e-5 * np.ones(nx), np.geomspace(1e-4, 3e-2, nx)):
         ref = coll(nu, None, O.velocity_exponential(f, kvr, e + dex, pond, dt, q, m), dt)
         out = host(ops.vpush_collide(dev(f), dev(e), dev(pond), q, m, dt, kvr[1], dev(v), dv, dev(nu),
                                      model=MODEL[coll.model], dex=dev(dex)))

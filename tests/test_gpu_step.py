@@ -66,6 +66,22 @@ def variants():
     d["drivers"]["ey"]["0"]["params"].update(a0=1.0e-2, k0=1.0, w0=2.0)
     d["drivers"]["ey"]["0"]["envelope"]["time"].update(center=1.0, width=2.0, rise=0.2)
     out["C2-ey-wave"] = d
+    # large single grids: TMA x-advection with fused charge density, ONE fused field launch (driver + ponderomotive
+    # force + density + Poisson), fused v-push + collisions
+    d = c2_deck()
+    d["grid"].update(nx=1024, nv=1024)
+    out["L-1024x1024-fp"] = d
+    d = c2_deck()  # collisions strong enough that the reduced tridiagonal system needs every PCR step
+    d["grid"].update(nx=1024, nv=512)
+    d["terms"]["fokker_planck"]["time"]["baseline"] = 0.5
+    out["L-1024x512-strong-fp"] = d
+    d = c2_deck()  # sixth-order integrator: the fused field launch serves substeps 2..6 (density from the x-pushes)
+    d["grid"].update(nx=2048, nv=512)
+    d["terms"].update(time="sixth")
+    out["L-2048x512-sixth"] = d
+    d = load("multispecies_ion_acoustic")  # two species with different nv feed one fused field solve
+    d["grid"].update(nx=1024)
+    out["L-multispecies-1024"] = d
     return out
 
 

@@ -61,23 +61,7 @@ __global__ void __launch_bounds__(PP ? 512 : 256, PP ? 1 : 2)
   for (int m = 0; m < E; m++) x[m] = cmake(__ldcs(a + t + T * m), __ldcs(b + t + T * m));
   phase_table_fill<LOGN>(ph, alpha_a, alpha_b, t, T);
   ADEPT_TRACE(900);
-  if constexpr (PP == 1) {
-    PingPong<T> sy;
-    sy.team = team;
-    sy.prime();
-    fft_forward<LOGN, 1, PingPong<T>>(x, buf, tw, t, zero, sy);
-    half_spectrum_update<LOGN, 1, PingPong<T>>(x, buf, ph, t, nullptr, sy);
-    fft_forward<LOGN, 1, PingPong<T>>(x, buf, tw + zero, t, zero, sy);
-    sy.drain();
-  } else if constexpr (PP == 2) {
-    PingPongLsu<T> sy;
-    sy.team = team;
-    sy.prime();
-    fft_forward<LOGN, 1, PingPongLsu<T>>(x, buf, tw, t, zero, sy);
-    half_spectrum_update<LOGN, 1, PingPongLsu<T>>(x, buf, ph, t, nullptr, sy);
-    fft_forward<LOGN, 1, PingPongLsu<T>>(x, buf, tw + zero, t, zero, sy);
-    sy.drain();
-  } else {
+  {
     fft_forward<LOGN>(x, buf, tw, t, zero);
     half_spectrum_update<LOGN, 1>(x, buf, ph, t);
     fft_forward<LOGN>(x, buf, tw + zero, t, zero);
@@ -147,6 +131,7 @@ int main(int argc, char** argv) {
   cudaMemcpy(fin, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice);
   const cplx* tw = get_twiddles(LOGN);
   if (!tw) { printf("no twiddles\n"); return 1; }
-  if (pp == 1) run<1>(fin, fout, tw, nx, trace_first, pad); else if (pp == 2) run<2>(fin, fout, tw, nx, trace_first, pad); else run<0>(fin, fout, tw, nx, trace_first, pad);
+  (void)pp;
+  run<0>(fin, fout, tw, nx, trace_first, pad);
   return 0;
 }
