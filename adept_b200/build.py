@@ -72,9 +72,41 @@ def build(verbose: bool = False, force: bool = False) -> Path:
     return LIB
 
 
+def xla_include_dir():
+    """Directory holding xla/ffi/api/ffi.h: $XLA_FFI_INCLUDE_DIR, else jax.ffi.include_dir() when jax is importable."""
+    env = os.environ.get("XLA_FFI_INCLUDE_DIR")
+    if env and (Path(env) / "xla" / "ffi" / "api" / "ffi.h").exists():
+        return env
+    try:
+        import jax.ffi  # noqa: PLC0415  (absent from the B200 image; present on a maintainer's machine)
+
+        return jax.ffi.include_dir()
+    except Exception:
+        return None
+
+
+def build_xla() -> Path | None:
+    """Layer 2: libadept_b200_xla.so with the XLA FFI handlers of csrc/xla_ffi.cc, built iff the XLA FFI
+    headers are found; returns None (and builds nothing) otherwise."""
+    inc = xla_include_dir()
+    if inc is None:
+        return None
+    build()
+    out = HERE / "libadept_b200_xla.so"
+    cmd = [_nvcc(), "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-I", inc, str(CSRC / "xla_ffi.cc"), "-o",
+           str(out), "-L", str(HERE), "-ladept_b200", "-Xlinker", "-rpath=$ORIGIN", "-lcudart"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"building the XLA FFI layer failed:\n{res.stdout}\n{res.stderr}")
+    return out
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--force", action="store_true")
+    ap.add_argument("--xla", action="store_true", help="also build libadept_b200_xla.so (needs the XLA FFI headers)")
     a = ap.parse_args()
     print(build(a.verbose, a.force))
+    if a.xla:
+        print(build_xla() or "XLA FFI headers not found (set XLA_FFI_INCLUDE_DIR or install jax): layer 2 not built")
