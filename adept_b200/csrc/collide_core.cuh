@@ -68,7 +68,10 @@ __device__ __forceinline__ void row_reduce(double (&val)[NVAL], double* red, int
 // Fast-path Fokker-Planck solve of ONE row by the T = nv/E threads of a CTA (all threads of the CTA must call it; it
 // uses __syncthreads()).  rowbuf: the row in chunk-padded layout (cell i at i + i/E), overwritten with f + delta.
 // apbuf: nv doubles, red: 2*32*3 doubles when T % 32 == 0 (else 2*T*3), pcr: 6 T doubles.
-template <int E>
+// DENSE_OUT: the result is written as a dense row whose 128-byte chunks are XOR-swizzled in 16-byte units (unit j of
+// chunk c at j ^ (c & 7)): the layout a TMA tensor store with CU_TENSOR_MAP_SWIZZLE_128B reads, conflict-free for the
+// 16-byte stores of a warp; rowbuf must then be 1024-byte aligned.  Each thread fences its stores for the async proxy.
+template <int E, bool DENSE_OUT = false>
 __device__ __forceinline__ void fp_row_fast(double* rowbuf, double* apbuf, double* red, double* pcr, int& parity, int tt,
                                             int T, int nv, double vc, double dv, double dt, double nu, int model) {
   const bool warp_mode = (T & 31) == 0;
@@ -200,12 +203,26 @@ __device__ __forceinline__ void fp_row_fast(double* rowbuf, double* apbuf, doubl
   const double s_left = (tt > 0) ? cur[2 * T + tt - 1] : 0.0;
   {
     double y = ypn[E - 1] + s_me;
-    double* outc = rowbuf + i0 + tt;
-    outc[E - 1] = y;
+    if constexpr (DENSE_OUT) {
+      static_assert(E == 16, "dense output layout: 16 cells = one 128-byte chunk per thread");
+      double2* units = reinterpret_cast<double2*>(rowbuf) + 8 * tt;
+      const int sw = tt & 7;
+      double y_up = y;
 #pragma unroll
-    for (int l = E - 2; l >= 0; l--) {
-      y = fma(-cpn[l], y, fma(-apbuf[l * T + tt], s_left, ypn[l]));
-      outc[l] = y;
+      for (int l = E - 2; l >= 0; l--) {
+        y = fma(-cpn[l], y, fma(-apbuf[l * T + tt], s_left, ypn[l]));
+        if ((l & 1) == 0) units[(l >> 1) ^ sw] = make_double2(y, y_up);
+        y_up = y;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    } else {
+      double* outc = rowbuf + i0 + tt;
+      outc[E - 1] = y;
+#pragma unroll
+      for (int l = E - 2; l >= 0; l--) {
+        y = fma(-cpn[l], y, fma(-apbuf[l * T + tt], s_left, ypn[l]));
+        outc[l] = y;
+      }
     }
   }
   __syncthreads();  // pcr / red / apbuf may be reused by the caller for the next row

@@ -1,5 +1,6 @@
 // Internal C++ interface between the translation units of libadept_b200.so (kernel launchers).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 namespace adept {
@@ -44,6 +45,9 @@ bool vpush_collide_supported(int nx, int nv, int model, int scheme, int nodrag);
 int vpush_collide_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* e, const double* dex,
                       const double* pond, double q, double m, double dt, double k1v, const double* v, double dv,
                       const double* nu_fp, double nu_fp_scale, int model, cudaStream_t stream);
+bool tma_available();
+int encode_map_2d(CUtensorMap* map, const double* base, unsigned long long dim0, unsigned long long dim1,
+                  unsigned long long pitch_bytes, unsigned box0, unsigned box1, int swizzle128);
 bool vdfdx_tma_supported(const double* fin, const double* fout, int nx, int nv);
 int vdfdx_tma_parts(int batch, int nx, int nv);
 int vdfdx_tma_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* v, double dt,

@@ -17,34 +17,11 @@
 
 #include <mutex>
 
+#include "internal.h"
 #include "push_core.cuh"
+#include "tma.cuh"
 
 namespace adept {
-
-// ---- PTX wrappers ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
-                   "r"(smem_u32(dst)),
-               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-               : "memory");
-}
 
 struct TmaPushArgs {
   double* fout;
@@ -193,24 +170,34 @@ static EncodeTiledFn get_encoder() {
   return fn;
 }
 
-static int encode_map(CUtensorMap* map, const double* base, long long rows, int nv, int box_rows) {
+// 2-D fp64 tensor map: dims {dim0 (contiguous), dim1}, row pitch `pitch_bytes`, box {box0, box1}; swizzle128 selects
+// CU_TENSOR_MAP_SWIZZLE_128B (box0 * 8 must then be 128 bytes and the shared-memory tile 1024-byte aligned)
+int encode_map_2d(CUtensorMap* map, const double* base, unsigned long long dim0, unsigned long long dim1,
+                  unsigned long long pitch_bytes, unsigned box0, unsigned box1, int swizzle128) {
   EncodeTiledFn enc = get_encoder();
   if (!enc) {
-    set_last_error("vdfdx(tma): cuTensorMapEncodeTiled is not available from the driver");
+    set_last_error("tma: cuTensorMapEncodeTiled is not available from the driver");
     return ADEPT_ERR_CUDA;
   }
-  cuuint64_t dims[2] = {(cuuint64_t)nv, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)nv * sizeof(double)};
-  cuuint32_t box[2] = {4, (cuuint32_t)box_rows};
+  cuuint64_t dims[2] = {(cuuint64_t)dim0, (cuuint64_t)dim1};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_last_error("vdfdx(tma): cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    set_last_error("tma: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return ADEPT_ERR_CUDA;
   }
   return ADEPT_OK;
+}
+
+bool tma_available() { return get_encoder() != nullptr; }
+
+static int encode_map(CUtensorMap* map, const double* base, long long rows, int nv, int box_rows) {
+  return encode_map_2d(map, base, (unsigned long long)nv, (unsigned long long)rows,
+                       (unsigned long long)nv * sizeof(double), 4, (unsigned)box_rows, 0);
 }
 
 template <int LOGN>

@@ -12,6 +12,7 @@
 #include "collide_core.cuh"
 #include "internal.h"
 #include "push_core.cuh"
+#include "tma.cuh"
 
 namespace adept {
 
@@ -47,22 +48,26 @@ struct VrowCfg {
   static constexpr size_t RED_BYTES = (size_t)2 * (WARP_MODE ? T / 32 : (T > 32 ? T : 32)) * 3 * sizeof(double);
   static constexpr size_t PCR_BYTES = (size_t)6 * T * sizeof(double);
   static constexpr size_t SMEM = BUF_BYTES + AP_BYTES + RED_BYTES + PCR_BYTES;
+  static constexpr int OUT_BOX_ROWS = (N / 16) < 256 ? (N / 16) : 256;  // 128-byte chunks per TMA store box
   static_assert(2 * PC::PER_SEQ * sizeof(cplx) <= AP_BYTES || N < 128, "phase tables alias the spike buffer");
 };
 
-template <int LOGN>
+// TMA_OUT: the solved rows leave shared memory through TMA tensor stores (no LDS + STG pass for the output); the
+// tensor map views f_out as [rows * nv/16][16] with boxes {16, min(256, nv/16)}, 128-byte swizzle.
+template <int LOGN, bool TMA_OUT>
 __global__ void __launch_bounds__(VrowCfg<LOGN>::THREADS, (VrowCfg<LOGN>::THREADS <= 256 ? 2 : 1))
-    vpush_collide_kernel(VrowArgs p) {
+    vpush_collide_kernel(const __grid_constant__ CUtensorMap out_map, VrowArgs p) {
   using K = VrowCfg<LOGN>;
   using C = FftCfg<LOGN>;
   using PC = PhaseCfg<LOGN>;
   constexpr int N = C::N, E = C::E, T = C::T;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   cplx* buf = reinterpret_cast<cplx*>(smem_raw);
   double* apbuf = reinterpret_cast<double*>(smem_raw + K::BUF_BYTES);
   cplx* ph = reinterpret_cast<cplx*>(apbuf);  // phase tables live in the spike buffer until the FFTs are done
   double* red = reinterpret_cast<double*>(smem_raw + K::BUF_BYTES + K::AP_BYTES);
   double* pcr = reinterpret_cast<double*>(smem_raw + K::BUF_BYTES + K::AP_BYTES + K::RED_BYTES);
+  if (TMA_OUT && (smem_u32(smem_raw) & 1023u)) __trap();  // the swizzled tiles need a 1024-byte aligned window
 
   const int t = threadIdx.x < T ? threadIdx.x : 0;  // spare threads (T < 32) shadow thread 0 and never store
   const bool live = threadIdx.x < T;
@@ -81,6 +86,7 @@ __global__ void __launch_bounds__(VrowCfg<LOGN>::THREADS, (VrowCfg<LOGN>::THREAD
       alpha[s] = p.k1 * (p.dt * accel_of(ee, pd, p.q, q2m, p.m));
     }
   }
+
   cplx x[E];
 #pragma unroll
   for (int m = 0; m < E; m++) {
@@ -93,8 +99,9 @@ __global__ void __launch_bounds__(VrowCfg<LOGN>::THREADS, (VrowCfg<LOGN>::THREAD
   fft_forward<LOGN>(x, buf, p.tw + p.zero, t, p.zero);
 
   // registers (e = t + T m) -> chunk-padded rows (cell i at i + i/16); the row buffers alias the exchange buffer
+  constexpr int ROW_STRIDE = N + T;  // doubles; (N + T) * 8 bytes is a multiple of 1024 for N >= 2048
   double* rowA = reinterpret_cast<double*>(buf);
-  double* rowB = rowA + (N + T);
+  double* rowB = rowA + ROW_STRIDE;
   __syncthreads();  // every thread is done reading the exchange buffer and the phase tables
   if (live) {
 #pragma unroll
@@ -109,26 +116,38 @@ __global__ void __launch_bounds__(VrowCfg<LOGN>::THREADS, (VrowCfg<LOGN>::THREAD
   int parity = 0;
   const double vc = __ldg(p.v + 16 * t);
   // NOTE: spare threads (T < 32) would corrupt shared state in fp_row_fast; the launcher only uses this kernel for T >= 32
-  fp_row_fast<16>(rowA, apbuf, red, pcr, parity, t, T, N, vc, p.dv, p.dt, __dmul_rn(p.nu_fp_scale, p.nu_fp[row0]),
-                  p.model);
-  fp_row_fast<16>(rowB, apbuf, red, pcr, parity, t, T, N, vc, p.dv, p.dt, __dmul_rn(p.nu_fp_scale, p.nu_fp[row0 + 1]),
-                  p.model);
-
-  double* a_out = p.fout + row0 * N;
-  double* b_out = a_out + N;
-  for (int i = t; i < N; i += T) {
-    __stcs(a_out + i, rowA[i + (i >> 4)]);
-    __stcs(b_out + i, rowB[i + (i >> 4)]);
+#pragma unroll 1
+  for (int s = 0; s < 2; s++) {
+    double* row = rowA + s * ROW_STRIDE;
+    fp_row_fast<16, TMA_OUT>(row, apbuf, red, pcr, parity, t, T, N, vc, p.dv, p.dt,
+                             __dmul_rn(p.nu_fp_scale, p.nu_fp[row0 + s]), p.model);
+    if (TMA_OUT && threadIdx.x == 0) {  // the barrier that ends fp_row_fast ordered every thread's fenced stores
+      constexpr int BOX = K::OUT_BOX_ROWS;
+#pragma unroll 1
+      for (int bx = 0; bx < (N / 16) / BOX; bx++)
+        tma_store_2d(&out_map, row + (size_t)bx * BOX * 16, 0, (int)((row0 + s) * (N / 16)) + bx * BOX);
+      tma_commit_group();
+    }
+  }
+  if constexpr (TMA_OUT) {
+    if (threadIdx.x == 0) tma_wait_read_all();  // shared memory must outlive the TMA reads
+  } else {
+    double* a_out = p.fout + row0 * N;
+    double* b_out = a_out + N;
+    for (int i = t; i < N; i += T) {
+      __stcs(a_out + i, rowA[i + (i >> 4)]);
+      __stcs(b_out + i, rowB[i + (i >> 4)]);
+    }
   }
 }
 
-template <int LOGN>
+template <int LOGN, bool TMA_OUT>
 static int launch_vrow(const VrowArgs& p, cudaStream_t stream) {
   using K = VrowCfg<LOGN>;
   static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
-  auto kern = vpush_collide_kernel<LOGN>;
+  auto kern = vpush_collide_kernel<LOGN, TMA_OUT>;
   if (dev < 64 && !configured[dev]) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
     if (err != cudaSuccess) {
@@ -137,9 +156,28 @@ static int launch_vrow(const VrowArgs& p, cudaStream_t stream) {
     }
     configured[dev] = true;
   }
+  CUtensorMap map = {};
+  if (TMA_OUT) {
+    const int rc = encode_map_2d(&map, p.fout, 16, (unsigned long long)p.npairs * 2 * (K::N / 16), 128, 16,
+                                 K::OUT_BOX_ROWS, 1);
+    if (rc != ADEPT_OK) return rc;
+  }
   ProfileScope prof("vpush_collide", stream);
-  kern<<<(unsigned)p.npairs, K::THREADS, K::SMEM, stream>>>(p);
+  kern<<<(unsigned)p.npairs, K::THREADS, K::SMEM, stream>>>(map, p);
   return check_launch("vpush_collide_kernel");
+}
+
+// TMA output needs 1024-byte aligned row buffers ((nv + nv/16) * 8 bytes apart: nv >= 2048), 16-byte aligned f_out
+// and row coordinates that fit the tensor map's int32 coordinates
+template <int LOGN>
+static int launch_vrow_auto(const VrowArgs& p, cudaStream_t stream) {
+  using K = VrowCfg<LOGN>;
+  const bool tma_ok = LOGN >= 11 && tma_available() && (reinterpret_cast<uintptr_t>(p.fout) & 15) == 0 &&
+                      (unsigned long long)p.npairs * 2 * (K::N / 16) < (1ull << 31);
+  if constexpr (LOGN >= 11) {
+    if (tma_ok) return launch_vrow<LOGN, true>(p, stream);
+  }
+  return launch_vrow<LOGN, false>(p, stream);
 }
 
 bool vpush_collide_supported(int nx, int nv, int model, int scheme, int nodrag) {
@@ -164,11 +202,11 @@ int vpush_collide_f64(const double* fin, double* fout, int batch, int nx, int nv
   p.v = v, p.dv = dv, p.nu_fp = nu_fp, p.nu_fp_scale = nu_fp_scale, p.model = model;
   if (!p.tw) return ADEPT_ERR_CUDA;
   switch (logn) {
-    case 9: return launch_vrow<9>(p, stream);
-    case 10: return launch_vrow<10>(p, stream);
-    case 11: return launch_vrow<11>(p, stream);
-    case 12: return launch_vrow<12>(p, stream);
-    case 13: return launch_vrow<13>(p, stream);
+    case 9: return launch_vrow_auto<9>(p, stream);
+    case 10: return launch_vrow_auto<10>(p, stream);
+    case 11: return launch_vrow_auto<11>(p, stream);
+    case 12: return launch_vrow_auto<12>(p, stream);
+    case 13: return launch_vrow_auto<13>(p, stream);
   }
   return ADEPT_ERR_UNSUPPORTED;
 }

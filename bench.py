@@ -122,6 +122,12 @@ def time_oracle(nx, nv, steps, warmup, workers):
     from oracle import vlasov1d as O
 
     O.FFT_WORKERS = workers
+    try:  # torchrun exports OMP_NUM_THREADS=1: give BLAS/OpenMP pools under numpy/scipy the host cores back
+        import threadpoolctl
+
+        threadpoolctl.threadpool_limits(limits=workers)
+    except Exception:
+        pass
     cfg = O.build_cfg(c3_deck(nx, nv))
     vf = O.VlasovMaxwell(cfg)
     y = O.init_state(cfg)

@@ -333,7 +333,7 @@ def test_collide_strongly_collisional(ops):
 
 
 @pytest.mark.parametrize("fp_type", ["lenard_bernstein", "dougherty"])
-@pytest.mark.parametrize("nx,nv", [(4, 512), (6, 1024), (2, 4096), (2, 8192)])
+@pytest.mark.parametrize("nx,nv", [(4, 512), (6, 1024), (6, 2048), (2, 4096), (2, 8192)])
 def test_fused_vpush_collide_matches_oracle(ops, fp_type, nx, nv):
     """VelocityExponential followed by Collisions (vector_field.py:236-238) in one kernel."""
     coll = O.Collisions(_fp_cfg(nv, 6.4, fp_type))
