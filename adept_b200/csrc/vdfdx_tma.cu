@@ -130,15 +130,14 @@ __global__ void __launch_bounds__(TmaCfg<LOGN>::THREADS, 1)
     __syncthreads();
     if (tid == 0 && tl + (int)gridDim.x < p.ntiles) issue_load(tl + gridDim.x);
 
+    // global stores (local/global queue) interleaved with the row-sum accumulation (shuffle + shared-memory queue)
     double* dst = p.fout + ((size_t)b * N) * p.nv + col;
+    const bool want_rho = p.partial != nullptr;
 #pragma unroll
     for (int m = 0; m < E; m++) {
       const size_t e = t + T * m;
       *reinterpret_cast<double2*>(dst + e * p.nv) = make_double2(x[m].y, x[m].x);
-    }
-    if (p.partial) {
-#pragma unroll
-      for (int m = 0; m < E; m++) {
+      if (want_rho) {
         double s = x[m].y + x[m].x;
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         if (g == 0) rho_acc[t + T * m] += s;  // row t + T m is owned by this lane pair
