@@ -67,12 +67,12 @@ __device__ __forceinline__ void row_reduce(double (&val)[NVAL], double* red, int
 
 // Fast-path Fokker-Planck solve of ONE row by the T = nv/E threads of a CTA (all threads of the CTA must call it; it
 // uses __syncthreads()).  rowbuf: the row in chunk-padded layout (cell i at i + i/E), overwritten with f + delta.
-// apbuf: nv doubles, red: 2*32*3 doubles when T % 32 == 0 (else 2*T*3), pcr: 6 T doubles.
+// red: 2*32*3 doubles when T % 32 == 0 (else 2*T*3), pcr: 6 T doubles.
 // DENSE_OUT: the result is written as a dense row whose 128-byte chunks are XOR-swizzled in 16-byte units (unit j of
 // chunk c at j ^ (c & 7)): the layout a TMA tensor store with CU_TENSOR_MAP_SWIZZLE_128B reads, conflict-free for the
 // 16-byte stores of a warp; rowbuf must then be 1024-byte aligned.  Each thread fences its stores for the async proxy.
 template <int E, bool DENSE_OUT = false>
-__device__ __forceinline__ void fp_row_fast(double* rowbuf, double* apbuf, double* red, double* pcr, int& parity, int tt,
+__device__ __forceinline__ void fp_row_fast(double* rowbuf, double* red, double* pcr, int& parity, int tt,
                                             int T, int nv, double vc, double dv, double dt, double nu, int model) {
   const bool warp_mode = (T & 31) == 0;
   const int i0 = E * tt;
@@ -111,7 +111,7 @@ __device__ __forceinline__ void fp_row_fast(double* rowbuf, double* apbuf, doubl
     U = pD + wq;
     L = pD - wq;
   };
-  double cpn[E], ypn[E];
+  double cpn[E], ypn[E], apn[E];  // Thomas ratios, y-form right-hand sides and the left spike, all in registers
   double rpn_last, apn_last;
   {
     double Um, Lm;
@@ -140,7 +140,7 @@ __device__ __forceinline__ void fp_row_fast(double* rowbuf, double* apbuf, doubl
       const double inv = fast_rcp(bp);
       const double cp = -Uc * inv, ap = apv * inv, rp = rpv * inv;
       cpn[l] = cp;
-      apbuf[l * T + tt] = ap;
+      apn[l] = ap;
       ypn[l] = (l < E - 1) ? fma(cp, f_p, f_c + rp) : f_c;
       if (l == E - 1) rpn_last = rp, apn_last = ap;
       cp_prev = cp, ap_prev = ap, rp_prev = rp;
@@ -149,12 +149,12 @@ __device__ __forceinline__ void fp_row_fast(double* rowbuf, double* apbuf, doubl
   }
   double A0, C0, R0;
   {
-    double RY = ypn[E - 2], A = apbuf[(E - 2) * T + tt], Cc = cpn[E - 2];
+    double RY = ypn[E - 2], A = apn[E - 2], Cc = cpn[E - 2];
 #pragma unroll
     for (int l = E - 3; l >= 0; l--) {
       const double cp = cpn[l];
       RY = fma(-cp, RY, ypn[l]);
-      A = fma(-cp, A, apbuf[l * T + tt]);
+      A = fma(-cp, A, apn[l]);
       Cc = -cp * Cc;
     }
     A0 = A, C0 = Cc;
@@ -210,7 +210,7 @@ __device__ __forceinline__ void fp_row_fast(double* rowbuf, double* apbuf, doubl
       double y_up = y;
 #pragma unroll
       for (int l = E - 2; l >= 0; l--) {
-        y = fma(-cpn[l], y, fma(-apbuf[l * T + tt], s_left, ypn[l]));
+        y = fma(-cpn[l], y, fma(-apn[l], s_left, ypn[l]));
         if ((l & 1) == 0) units[(l >> 1) ^ sw] = make_double2(y, y_up);
         y_up = y;
       }
@@ -220,12 +220,12 @@ __device__ __forceinline__ void fp_row_fast(double* rowbuf, double* apbuf, doubl
       outc[E - 1] = y;
 #pragma unroll
       for (int l = E - 2; l >= 0; l--) {
-        y = fma(-cpn[l], y, fma(-apbuf[l * T + tt], s_left, ypn[l]));
+        y = fma(-cpn[l], y, fma(-apn[l], s_left, ypn[l]));
         outc[l] = y;
       }
     }
   }
-  __syncthreads();  // pcr / red / apbuf may be reused by the caller for the next row
+  __syncthreads();  // pcr / red may be reused by the caller for the next row
 }
 
 }  // namespace adept

@@ -44,12 +44,12 @@ struct VrowCfg {
   static constexpr int THREADS = T < 32 ? 32 : T;
   static constexpr bool WARP_MODE = (T % 32) == 0;
   static constexpr size_t BUF_BYTES = (size_t)C::BUF * sizeof(cplx);            // == 2 rows x (N + T) doubles
-  static constexpr size_t AP_BYTES = (size_t)N * sizeof(double);                // also hosts the phase tables
+  static constexpr size_t PH_BYTES = ((size_t)2 * PC::PER_SEQ * sizeof(cplx) + 127) / 128 * 128;  // phase tables
   static constexpr size_t RED_BYTES = (size_t)2 * (WARP_MODE ? T / 32 : (T > 32 ? T : 32)) * 3 * sizeof(double);
   static constexpr size_t PCR_BYTES = (size_t)6 * T * sizeof(double);
-  static constexpr size_t SMEM = BUF_BYTES + AP_BYTES + RED_BYTES + PCR_BYTES;
+  // ~84 KB at nv = 4096: two CTAs per SM leave ~60 KB of the 228 KB array to L1, enough for the twiddle rows in use
+  static constexpr size_t SMEM = BUF_BYTES + PH_BYTES + RED_BYTES + PCR_BYTES;
   static constexpr int OUT_BOX_ROWS = (N / 16) < 256 ? (N / 16) : 256;  // 128-byte chunks per TMA store box
-  static_assert(2 * PC::PER_SEQ * sizeof(cplx) <= AP_BYTES || N < 128, "phase tables alias the spike buffer");
 };
 
 // TMA_OUT: the solved rows leave shared memory through TMA tensor stores (no LDS + STG pass for the output); the
@@ -63,10 +63,9 @@ __global__ void __launch_bounds__(VrowCfg<LOGN>::THREADS, (VrowCfg<LOGN>::THREAD
   constexpr int N = C::N, E = C::E, T = C::T;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   cplx* buf = reinterpret_cast<cplx*>(smem_raw);
-  double* apbuf = reinterpret_cast<double*>(smem_raw + K::BUF_BYTES);
-  cplx* ph = reinterpret_cast<cplx*>(apbuf);  // phase tables live in the spike buffer until the FFTs are done
-  double* red = reinterpret_cast<double*>(smem_raw + K::BUF_BYTES + K::AP_BYTES);
-  double* pcr = reinterpret_cast<double*>(smem_raw + K::BUF_BYTES + K::AP_BYTES + K::RED_BYTES);
+  cplx* ph = reinterpret_cast<cplx*>(smem_raw + K::BUF_BYTES);
+  double* red = reinterpret_cast<double*>(smem_raw + K::BUF_BYTES + K::PH_BYTES);
+  double* pcr = reinterpret_cast<double*>(smem_raw + K::BUF_BYTES + K::PH_BYTES + K::RED_BYTES);
   if (TMA_OUT && (smem_u32(smem_raw) & 1023u)) __trap();  // the swizzled tiles need a 1024-byte aligned window
 
   const int t = threadIdx.x < T ? threadIdx.x : 0;  // spare threads (T < 32) shadow thread 0 and never store
@@ -119,7 +118,7 @@ __global__ void __launch_bounds__(VrowCfg<LOGN>::THREADS, (VrowCfg<LOGN>::THREAD
 #pragma unroll 1
   for (int s = 0; s < 2; s++) {
     double* row = rowA + s * ROW_STRIDE;
-    fp_row_fast<16, TMA_OUT>(row, apbuf, red, pcr, parity, t, T, N, vc, p.dv, p.dt,
+    fp_row_fast<16, TMA_OUT>(row, red, pcr, parity, t, T, N, vc, p.dv, p.dt,
                              __dmul_rn(p.nu_fp_scale, p.nu_fp[row0 + s]), p.model);
     if (TMA_OUT && threadIdx.x == 0) {  // the barrier that ends fp_row_fast ordered every thread's fenced stores
       constexpr int BOX = K::OUT_BOX_ROWS;
