@@ -52,6 +52,7 @@ class Step(C.Structure):
 SIGNATURES = {
     "adept_b200_version": [],
     "adept_b200_last_error": [],
+    "adept_b200_launch_count": [],
     "adept_b200_prepare": [c_i],
     "adept_b200_profile": [c_i],
     "adept_b200_profile_report": [C.c_char_p, c_i],
@@ -100,7 +101,7 @@ def load() -> C.CDLL:
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here means the .so and the header disagree
         fn.argtypes = argtypes
-        fn.restype = C.c_char_p if name == "adept_b200_last_error" else c_i
+        fn.restype = {"adept_b200_last_error": C.c_char_p, "adept_b200_launch_count": c_ll}.get(name, c_i)
     _lib = lib
     return lib
 

@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -22,7 +23,10 @@ void set_last_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static std::atomic<long long> g_launches{0};
+
 int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);  // every kernel launch site of the library ends here
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {
     set_last_error("%s: %s", what, cudaGetErrorString(err));
@@ -226,6 +230,8 @@ int adept_b200_collide_bwd_f64(const double* f_in, const double* f_new, const do
   return collide_bwd_f64(f_in, f_new, g, f_bar, nu_bar, batch, nx, nv, v, dv, dt, nu_fp, 1.0, model, scheme,
                          (cudaStream_t)stream);
 }
+
+long long adept_b200_launch_count(void) { return adept::g_launches.load(std::memory_order_relaxed); }
 
 int adept_b200_vpush_collide_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* e,
                                  const double* dex, const double* pond, double charge, double mass, double dt,

@@ -305,27 +305,15 @@ class NativeStep:
             st.nu_fp_time = float(vm.nu_fp_prof.time_envelope(t))
         if vm.krook_on:
             st.nu_K_time = float(vm.nu_K_prof.time_envelope(t))
-        rc = _lib.load().adept_b200_step_f64(C.byref(st), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        lib = _lib.load()
+        before = lib.adept_b200_launch_count()
+        rc = lib.adept_b200_step_f64(C.byref(st), C.c_void_p(torch.cuda.current_stream().cuda_stream))
         _lib.check(rc, "step")
-        ops._count(0)
-        ops.LAUNCHES += self._launch_count(wave_on)
+        ops.LAUNCHES += lib.adept_b200_launch_count() - before  # kernels the native step enqueued (exact)
         result = {"a": a_out if wave_on else y["a"], "prev_a": y["a"], "da": djy,
                   "de": dex[vm.vpfp.dex_save], "e": e_out}
         result.update(new)
         return result
-
-    def _launch_count(self, wave_on):
-        """Kernels enqueued by one adept_b200_step_f64 call (bench.py reports it as gpu_launches)."""
-        ns = len(self.names)
-        n = 1  # drivers
-        if self.sixth:
-            n += 6 * (1 + ns + 1) + 6 * ns + 5 * ns  # (pond + rho stages + poisson), v-pushes, x-pushes
-        else:
-            n += ns + 1 + ns + 1 + ns
-        n += int(self.vm.fp_on or self.vm.krook_on)
-        n += 3 if wave_on else 0
-        return n
-
 
 
 class VlasovMaxwell:

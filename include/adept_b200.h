@@ -51,6 +51,8 @@ const char* adept_b200_last_error(void);
 /* Per-kernel timing with CUDA events on the launching stream.  adept_b200_profile(1) clears the record and starts
  * bracketing every kernel launch of the library; adept_b200_profile(0) stops and clears.  adept_b200_profile_report
  * synchronises on the recorded events and writes one line per kernel, "<name> <launches> <total_ms>\n", into buf. */
+/* Number of kernels this library has launched in the calling process (monotonic; bench.py differences it). */
+long long adept_b200_launch_count(void);
 int adept_b200_profile(int enable);
 int adept_b200_profile_report(char* buf, int buflen);
 

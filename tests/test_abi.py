@@ -14,7 +14,7 @@ HEADER = (ROOT / "include" / "adept_b200.h").read_text()
 
 def declared_functions():
     body = re.sub(r"/\*.*?\*/", "", HEADER, flags=re.S)
-    decls = re.findall(r"(?:int|const char\*)\s+(adept_b200_\w+)\s*\(([^;]*?)\)\s*;", body, flags=re.S)
+    decls = re.findall(r"(?:long long|int|const char\*)\s+(adept_b200_\w+)\s*\(([^;]*?)\)\s*;", body, flags=re.S)
     return {name: [a.strip() for a in args.split(",") if a.strip() and a.strip() != "void"] for name, args in decls}
 
 
