@@ -283,9 +283,10 @@ int wave_step_f64(const double* a, const double* aold, const double* djy, const 
 // One launch replaces ex_driver + ponderomotive + reduce_parts (per species) + Poisson of the leapfrog step
 // (vector_field.py:87-95 calling field.py:479-497, 197-224, 21-33): every CTA finishes the charge density of 64 grid
 // points from the per-CTA partial sums the x-advection left behind (fixed summation order), evaluates the
-// ponderomotive force and the driver field there, and the CTA that arrives last at a device-side ticket counter solves
-// Poisson's equation for the whole grid.  The counter is reset by that CTA, so consecutive launches on one stream
-// need no host work; it must be zero before the first launch.
+// ponderomotive force and the driver field there, then all CTAs solve Poisson's equation together (four-step transform
+// with device-wide barriers on a ticket counter; the nx/64 <= 64 CTAs are co-resident on any B200).  The counter is
+// re-armed by the CTA that exits last, so consecutive launches on one stream need no host work; it must be zero before
+// the first launch.
 struct FieldFusedArgs {
   int nsp;
   const double* parts[4];
@@ -304,40 +305,60 @@ struct FieldFusedArgs {
   double ex_w[8], ex_a0[8], ex_tenv[8], ex_wt[8];
   PoissonArgs po;
   unsigned int* counter;
+  double* scratch;  // 4 nx doubles: two nx-long complex transposition buffers of the distributed solve
 };
 
-template <int LOGN>
-__global__ void __launch_bounds__(FftCfg<LOGN>::T) field_fused_kernel(FieldFusedArgs p) {
-  constexpr int T = FftCfg<LOGN>::T;
-  constexpr int NG = T / 64;  // thread groups that split the partial-sum rows
-  static_assert(T >= 64 && NG <= 4, "fused field kernel: 1024 <= nx <= 4096");
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+// device-wide barrier among the co-resident CTAs of this launch: tickets on a monotonic counter (target = tickets of
+// all CTAs up to and including this barrier)
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (*reinterpret_cast<volatile unsigned int*>(counter) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// sum over the 4 lanes q = 0..3 that share one output
+__device__ __forceinline__ cplx quad_sum(cplx v) {
+  v.x += __shfl_xor_sync(0xffffffffu, v.x, 1), v.y += __shfl_xor_sync(0xffffffffu, v.y, 1);
+  v.x += __shfl_xor_sync(0xffffffffu, v.x, 2), v.y += __shfl_xor_sync(0xffffffffu, v.y, 2);
+  return v;
+}
+
+// The Poisson solve is spread over the M = nx/64 CTAs as a four-step transform, N = M x 64 (n = 64 n1 + n2,
+// k = k1 + M k2):  stage A (CTA j, its share of the n2): length-M DFTs over n1;  barrier;  stage B (CTA k1): twiddle
+// W_N^(n2 k1), 64-point DFT over n2 -> X[k1 + M k2], the -i kmul multiply, and at once the transposed inverse over k2;
+// barrier;  stage A' (CTA j): inverse length-M DFTs over k1 -> E.  Two device-wide barriers instead of two
+// 4096-point FFTs in one CTA (about 15 us with 147 SMs idle).  The small DFTs are direct sums (<= 64 terms).
+__global__ void __launch_bounds__(256) field_fused_kernel(FieldFusedArgs p) {
+  constexpr int NG = 4;  // thread groups that split the partial-sum rows
   __shared__ double sm[4][64];
-  __shared__ double rho0_s;
-  __shared__ unsigned int ticket_s;
+  __shared__ cplx w64[64], wM[64], vin[64], vout[64], twn[64];
+  __shared__ double red_s[8];
   const int r = threadIdx.x & 63, g = threadIdx.x >> 6;
   const int i = blockIdx.x * 64 + r;
   const int n = p.nx;
+  const int M = gridDim.x;  // nx / 64
   double acc = p.base ? p.base[i] : 0.0;
   for (int k = 0; k < p.nsp; k++) {
     const double* col = p.parts[k] + i;
     const int np = p.nparts[k];
     double s[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    int q = g;
-    for (; q + 7 * NG < np; q += 8 * NG) {  // eight independent L2 loads in flight per thread
-      double x[8];
+    for (int q = g; q < np; q += 24 * NG) {  // 24 independent L2 loads in flight per thread (148 rows: 2 round trips)
+      double x[24];
 #pragma unroll
-      for (int u = 0; u < 8; u++) x[u] = __ldcg(col + (size_t)(q + u * NG) * n);
+      for (int u = 0; u < 24; u++) x[u] = (q + u * NG < np) ? __ldcg(col + (size_t)(q + u * NG) * n) : 0.0;
 #pragma unroll
-      for (int u = 0; u < 8; u++) s[u] += x[u];
+      for (int u = 0; u < 24; u++) s[u & 7] += x[u];
     }
-    for (; q < np; q += NG) s[0] += __ldcg(col + (size_t)q * n);
     sm[g][r] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
     __syncthreads();
     if (g == 0) {
-      double tot = sm[0][r];
-#pragma unroll
-      for (int u = 1; u < NG; u++) tot += sm[u][r];
+      const double tot = (sm[0][r] + sm[1][r]) + (sm[2][r] + sm[3][r]);
       const double term = __dmul_rn(p.charge[k], __dmul_rn(tot, p.dv[k]));
       acc = (k == 0 && !p.base) ? term : __dadd_rn(acc, term);
     }
@@ -349,7 +370,7 @@ __global__ void __launch_bounds__(FftCfg<LOGN>::T) field_fused_kernel(FieldFused
     const double lo = __dmul_rn(p.a[i], p.a[i]), hi = __dmul_rn(p.a[i + 2], p.a[i + 2]);
     p.pond[i] = __dmul_rn(-0.5, __ddiv_rn(__dsub_rn(hi, lo), __dmul_rn(2.0, p.dx)));
   }
-  if (p.n_ex > 0 && g == (NG > 1 ? 1 : 0)) {  // driver field at the first substep time, field.py:21-33
+  if (p.n_ex > 0 && g == 1) {  // driver field at the first substep time, field.py:21-33
     double total = 0.0;
     for (int d = 0; d < p.n_ex; d++) {
       const double factor = __dmul_rn(p.ex_tenv[d], p.ex_space[(size_t)d * n + i]);
@@ -358,41 +379,121 @@ __global__ void __launch_bounds__(FftCfg<LOGN>::T) field_fused_kernel(FieldFused
     }
     p.dex[i] = total;
   }
-  // ---- the last CTA to get here solves for E ----
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int ticket = atomicAdd(p.counter, 1u);
-    if (ticket == gridDim.x - 1) *p.counter = 0u;  // every other CTA has already taken its ticket
-    ticket_s = ticket;
+  // tables while the other CTAs finish their densities: W_64^j, W_M^j, and this CTA's twiddles W_N^(n2 k1), k1 = CTA
+  if (g == 2) {
+    double sn, cs;
+    sincospi(-2.0 * (double)r / 64.0, &sn, &cs);
+    w64[r] = cmake(cs, sn);
+    sincospi(-2.0 * (double)(r & (M - 1)) / (double)M, &sn, &cs);
+    wM[r] = cmake(cs, sn);
+  } else if (g == 3) {
+    double sn, cs;
+    sincospi(-2.0 * (double)(r * (int)blockIdx.x) / (double)n, &sn, &cs);
+    twn[r] = cmake(cs, sn);
   }
+  const unsigned int G = gridDim.x;
+  grid_barrier(p.counter, G);  // rho complete; the partial-sum rows are dead from here on
+
+  cplx* S1 = reinterpret_cast<cplx*>(p.scratch);  // [M][64]  stage A output, A[k1][n2]
+  cplx* S2 = S1 + n;                              // [64][M]  stage B' output, P[n2][k1]
+  const int o = threadIdx.x >> 2, q4 = threadIdx.x & 3;
+  const int S = 64 / M;  // n2 values this CTA owns in stages A / A'
+  double rho0 = 0.0;
+  if (p.po.mode != 0) {  // Boltzmann electrons need mean(rho): every CTA sums the grid itself (nx <= 4096)
+    double t = 0.0;
+    for (int j = threadIdx.x; j < n; j += 256) t += __ldcg(p.rho + j);
+    t = warp_sum(t);
+    if ((threadIdx.x & 31) == 0) red_s[threadIdx.x >> 5] = t;
+    __syncthreads();
+    for (int w = 0; w < 8; w++) rho0 += red_s[w];
+    rho0 /= (double)n;
+  }
+  // ---- stage A: A[k1][n2] = sum_n1 rho[64 n1 + n2] W_M^(n1 k1), output o -> (n2 = j S + o / M, k1 = o % M) ----
+  // (all loads of a stage are issued before the sums: the stages are latency chains of L2 round trips otherwise)
+  {
+    const int n2 = (int)blockIdx.x * S + o / M, k1 = o & (M - 1);
+    double xv[16];
+#pragma unroll
+    for (int u = 0; u < 16; u++) xv[u] = (q4 + 4 * u < M) ? __ldcg(p.rho + 64 * (q4 + 4 * u) + n2) : 0.0;
+    cplx a = cmake(0.0, 0.0);
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      const cplx w = wM[((q4 + 4 * u) * k1) & (M - 1)];
+      a.x = fma(xv[u], w.x, a.x), a.y = fma(xv[u], w.y, a.y);
+    }
+    a = quad_sum(a);
+    if (q4 == 0) S1[(size_t)k1 * 64 + n2] = a;
+  }
+  // the multiplier of this thread's mode k = k1 + M k2 (k1 = CTA, k2 = o) does not depend on the transform
+  const double kmul_k = __ldg(p.po.kmul + (int)blockIdx.x + M * o);
+  grid_barrier(p.counter, 2 * G);
+  // ---- stage B (k1 = CTA): X[k1 + M k2] = sum_n2 (A[k1][n2] W_N^(n2 k1)) W_64^(n2 k2);  Y = -i mult X;
+  //      stage B': P[n2] = conj(W_N^(n2 k1)) sum_k2 Y[k2] conj(W_64^(n2 k2)) ----
+  {
+    const int k1 = blockIdx.x;
+    if (threadIdx.x < 64) {
+      const cplx v = __ldcg(reinterpret_cast<const double2*>(S1 + (size_t)k1 * 64 + threadIdx.x));
+      vin[threadIdx.x] = cmul(v, twn[threadIdx.x]);
+    }
+    __syncthreads();
+    cplx x0 = cmake(0.0, 0.0), x1 = cmake(0.0, 0.0);
+#pragma unroll
+    for (int u = 0; u < 16; u += 2) {
+      const int na = q4 + 4 * u, nb = na + 4;
+      const cplx wa = w64[(na * o) & 63], va = vin[na], wb = w64[(nb * o) & 63], vb = vin[nb];
+      x0.x += va.x * wa.x - va.y * wa.y, x0.y += va.x * wa.y + va.y * wa.x;
+      x1.x += vb.x * wb.x - vb.y * wb.y, x1.y += vb.x * wb.y + vb.y * wb.x;
+    }
+    const cplx x = quad_sum(cadd(x0, x1));
+    if (q4 == 0) {
+      double mult = kmul_k;
+      if (p.po.mode != 0) {
+        const double kx = kmul_k;
+        const double lam_sq = p.po.lambda_De < 0.0 ? p.po.Te / rho0 : p.po.lambda_De * p.po.lambda_De;
+        mult = kx * (p.po.Te / rho0) / (1.0 + lam_sq * kx * kx);
+      }
+      vout[o] = cmake(mult * x.y, -(mult * x.x));  // -i mult X
+    }
+    __syncthreads();
+    cplx y0 = cmake(0.0, 0.0), y1 = cmake(0.0, 0.0);
+#pragma unroll
+    for (int u = 0; u < 16; u += 2) {  // o = n2 here; multiplies by conj(W_64)
+      const int ka = q4 + 4 * u, kb = ka + 4;
+      const cplx wa = w64[(ka * o) & 63], va = vout[ka], wb = w64[(kb * o) & 63], vb = vout[kb];
+      y0.x += va.x * wa.x + va.y * wa.y, y0.y += va.y * wa.x - va.x * wa.y;
+      y1.x += vb.x * wb.x + vb.y * wb.y, y1.y += vb.y * wb.x - vb.x * wb.y;
+    }
+    const cplx y = quad_sum(cadd(y0, y1));
+    if (q4 == 0) {
+      const cplx w = twn[o];
+      S2[(size_t)o * M + k1] = cmake(y.x * w.x + y.y * w.y, y.y * w.x - y.x * w.y);  // times conj(W_N^(n2 k1))
+    }
+  }
+  grid_barrier(p.counter, 3 * G);
+  // ---- stage A': E[64 n1 + n2] = Re sum_k1 P[n2][k1] conj(W_M^(n1 k1)) / N, output o -> (n2, n1 = o % M) ----
+  {
+    const int n2 = (int)blockIdx.x * S + o / M, n1 = o & (M - 1);
+    cplx pv[16];
+#pragma unroll
+    for (int u = 0; u < 16; u++)
+      pv[u] = (q4 + 4 * u < M) ? __ldcg(reinterpret_cast<const double2*>(S2 + (size_t)n2 * M + q4 + 4 * u))
+                               : cmake(0.0, 0.0);
+    double e = 0.0;
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      const cplx w = wM[(n1 * (q4 + 4 * u)) & (M - 1)];
+      e += pv[u].x * w.x + pv[u].y * w.y;  // Re(v conj(w))
+    }
+    e += __shfl_xor_sync(0xffffffffu, e, 1);
+    e += __shfl_xor_sync(0xffffffffu, e, 2);
+    if (q4 == 0) p.po.e[64 * n1 + n2] = e / (double)n;
+  }
+  // exit tickets: the CTA that leaves last re-arms the counter for the next launch
   __syncthreads();
-  if (ticket_s != gridDim.x - 1) return;
-  __threadfence();
-  poisson_body<LOGN>(p.po, p.rho, p.po.kmul, p.po.e, reinterpret_cast<cplx*>(smem_raw), &rho0_s);
+  if (threadIdx.x == 0 && atomicAdd(p.counter, 1u) == 4 * G - 1) *p.counter = 0u;
 }
 
 bool field_fused_supported(int batch, int nx) { return batch == 1 && (nx == 1024 || nx == 2048 || nx == 4096); }
-
-template <int LOGN>
-static int launch_field_fused(const FieldFusedArgs& p, cudaStream_t stream) {
-  static bool configured[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  const size_t smem = FftCfg<LOGN>::BUF * sizeof(cplx);
-  if (dev < 64 && !configured[dev]) {
-    cudaError_t err =
-        cudaFuncSetAttribute(field_fused_kernel<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) {
-      set_last_error("cudaFuncSetAttribute(field_fused): %s", cudaGetErrorString(err));
-      return ADEPT_ERR_CUDA;
-    }
-    configured[dev] = true;
-  }
-  ProfileScope prof("field_fused", stream);
-  field_fused_kernel<LOGN><<<p.nx / 64, FftCfg<LOGN>::T, smem, stream>>>(p);
-  return check_launch("field_fused_kernel");
-}
 
 int field_fused_f64(int nsp, const double* const* parts, const int* nparts, const double* dv, const double* charge,
                     const double* base, double* rho, int nx, const double* a, double* pond, double dx, int n_ex,
@@ -403,22 +504,22 @@ int field_fused_f64(int nsp, const double* const* parts, const int* nparts, cons
     set_last_error("field_fused: unsupported nx=%d / n_species=%d / n_ex=%d", nx, nsp, n_ex);
     return ADEPT_ERR_UNSUPPORTED;
   }
-  const int logn = ilog2_exact(nx);
   FieldFusedArgs p = {};
   p.nsp = nsp;
   for (int k = 0; k < nsp; k++) p.parts[k] = parts[k], p.nparts[k] = nparts[k], p.dv[k] = dv[k], p.charge[k] = charge[k];
+  if (nparts[0] < 4) {
+    set_last_error("field_fused: needs at least 4 partial-sum rows as scratch (got %d)", nparts[0]);
+    return ADEPT_ERR_UNSUPPORTED;
+  }
+  p.scratch = const_cast<double*>(parts[0]);  // rows 0..3 of the first partial-sum array, dead once rho is complete
   p.base = base, p.rho = rho, p.nx = nx, p.a = a, p.pond = pond, p.dx = dx;
   p.n_ex = n_ex, p.ex_space = ex_space, p.ex_kx = ex_kx, p.dex = dex;
   for (int d = 0; d < n_ex; d++) p.ex_w[d] = ex_w[d], p.ex_a0[d] = ex_a0[d], p.ex_tenv[d] = ex_tenv[d], p.ex_wt[d] = ex_wt[d];
-  p.po = PoissonArgs{rho, kmul, 0, e, mode, Te, lambda_De, get_twiddles(logn), 0};
-  if (!p.po.tw) return ADEPT_ERR_CUDA;
+  p.po = PoissonArgs{rho, kmul, 0, e, mode, Te, lambda_De, nullptr, 0};
   p.counter = counter;
-  switch (logn) {
-    case 10: return launch_field_fused<10>(p, stream);
-    case 11: return launch_field_fused<11>(p, stream);
-    case 12: return launch_field_fused<12>(p, stream);
-  }
-  return ADEPT_ERR_UNSUPPORTED;
+  ProfileScope prof("field_fused", stream);
+  field_fused_kernel<<<nx / 64, 256, 0, stream>>>(p);
+  return check_launch("field_fused_kernel");
 }
 
 }  // namespace adept

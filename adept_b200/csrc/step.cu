@@ -82,7 +82,8 @@ struct StepCtx {
     if (s.field == 2 || !s.sync_counter || !field_fused_supported(s.batch, s.nx)) return false;
     for (int k = 0; k < s.n_species; k++)
       if (!have_parts[k]) return false;
-    return true;
+    // rows 0..3 of the first partial-sum array double as the transposition scratch of the distributed solve
+    return vdfdx_tma_parts(s.batch, s.nx, s.species[0].nv) >= 4;
   }
 
   // (pond, e) = field_solve(f); field.py:479-497.  from_parts: the velocity sums come from the preceding push_x.
