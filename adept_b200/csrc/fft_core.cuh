@@ -157,12 +157,19 @@ __device__ __forceinline__ void dft16_finish(cplx* v) {
     }
 }
 
+// Hook called by the last pass as soon as this thread has finished reading the exchange buffer (before the second half
+// of its butterfly): callers that hand the buffer to an asynchronous producer (the next tile's TMA load) start it there.
+struct NoHook {
+  __device__ __forceinline__ void operator()() const {}
+};
+
 // BS: stride (in cplx) between consecutive buffer slots -- 2 when two transforms are interleaved slot by slot
 template <int LOGN, int P, int BS = 1>
 struct FftPass {
   using C = FftCfg<LOGN>;
+  template <class HOOK>
   static __device__ __forceinline__ void run(cplx (&x)[C::E], cplx* __restrict__ buf, const cplx* __restrict__ tw,
-                                             int t, int opaque_zero) {
+                                             int t, int opaque_zero, const HOOK& buffer_free) {
     constexpr int R = C::radix(P);
     constexpr int NS = C::ns(P);
     constexpr int Q = C::E / R;
@@ -208,6 +215,7 @@ struct FftPass {
       // second half of the butterfly overlaps (fp64 pipe) with the stores of the exchange (LSU pipe)
       ADEPT_TRACE(10 * P + 1);
       if constexpr (P < C::NPASS - 1) __syncthreads();
+      if constexpr (P == C::NPASS - 1) buffer_free();
       ADEPT_TRACE(10 * P + 2);
       dft16_finish(x);
       ADEPT_TRACE(10 * P + 3);
@@ -231,6 +239,7 @@ struct FftPass {
 #pragma unroll
         for (int r = 0; r < R; r++) x[q + r * Q] = v[r];
       }
+      if constexpr (P == C::NPASS - 1) buffer_free();
     }
     if constexpr (P < C::NPASS - 1) {
       if constexpr (R != 16) __syncthreads();  // all reads of buf for this pass (and any earlier use) are done
@@ -245,7 +254,7 @@ struct FftPass {
       ADEPT_TRACE(10 * P + 4);
       __syncthreads();
       ADEPT_TRACE(10 * P + 5);
-      FftPass<LOGN, P + 1, BS>::run(x, buf, tw, t, opaque_zero);
+      FftPass<LOGN, P + 1, BS>::run(x, buf, tw, t, opaque_zero, buffer_free);
     }
   }
 };
@@ -267,10 +276,10 @@ __device__ __forceinline__ void fft_prefetch_twiddles(const cplx* tw, int t) {
 
 // Forward complex FFT of the N points held as x[m] = z[t + T*m]; result X[t + T*m] in x[m].
 // All threads of the CTA must call this together (it uses __syncthreads()).
-template <int LOGN, int BS = 1>
+template <int LOGN, int BS = 1, class HOOK = NoHook>
 __device__ __forceinline__ void fft_forward(cplx (&x)[FftCfg<LOGN>::E], cplx* buf, const cplx* tw, int t,
-                                            int opaque_zero) {
-  FftPass<LOGN, 0, BS>::run(x, buf, tw, t, opaque_zero);
+                                            int opaque_zero, const HOOK& buffer_free = HOOK()) {
+  FftPass<LOGN, 0, BS>::run(x, buf, tw, t, opaque_zero, buffer_free);
 }
 
 }  // namespace adept

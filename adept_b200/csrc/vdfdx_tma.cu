@@ -123,12 +123,14 @@ __global__ void __launch_bounds__(TmaCfg<LOGN>::THREADS, 1)
     for (int m = 0; m < E; m++) x[m] = buf[(t + T * m) * 2];  // unpadded landing layout
     fft_forward<LOGN, 2>(x, buf, p.tw, t, p.zero);
     half_spectrum_update<LOGN, 2>(x, buf, ph, t, p.filt);
-    fft_forward<LOGN, 2>(x, buf, p.tw + p.zero, t, p.zero);
-
-    // the exchange buffer is dead once every thread has finished the last pass: hand it to the next tile's TMA load
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (tid == 0 && tl + (int)gridDim.x < p.ntiles) issue_load(tl + gridDim.x);
+    // the exchange buffer is dead once every thread has read its inputs of the last inverse pass: the next tile's TMA
+    // load is issued from inside that pass, so it also overlaps the second half of the butterflies (not only the stores)
+    auto buffer_free = [&]() {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (tid == 0 && tl + (int)gridDim.x < p.ntiles) issue_load(tl + gridDim.x);
+    };
+    fft_forward<LOGN, 2>(x, buf, p.tw + p.zero, t, p.zero, buffer_free);
 
     // global stores (local/global queue) interleaved with the row-sum accumulation (shuffle + shared-memory queue)
     double* dst = p.fout + ((size_t)b * N) * p.nv + col;
