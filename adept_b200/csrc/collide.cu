@@ -72,7 +72,7 @@ struct CollideSmem {
   // doubles per CTA for R rows of nv cells handled by RT = R*T threads
   static __host__ __device__ size_t doubles(int R, int nv, int RT) {
     const int red = 2 * (RT > 32 ? RT : 32) * 3;
-    return (size_t)R * (nv + nv / E) + (size_t)R * nv + red + 6 * (size_t)RT;
+    return (size_t)R * (nv + nv / E) + red + 6 * (size_t)RT;  // the spike of the downward sweep lives in registers
   }
 };
 
@@ -88,8 +88,7 @@ __global__ void __launch_bounds__(MAXT, MINB) collide_kernel(CollideArgs p) {
   const int r = threadIdx.x / T, t = threadIdx.x - r * T;
   const bool live = r < R;  // blockDim.x may exceed R*T when T does not divide it; spare threads only hit barriers
   double* rowbuf = sm + (size_t)(live ? r : 0) * nvp;
-  double* apbuf = sm + (size_t)R * nvp + (size_t)(live ? r : 0) * nv;  // [E][T]: spike of the downward sweep
-  double* red = sm + (size_t)R * nvp + (size_t)R * nv;
+  double* red = sm + (size_t)R * nvp;
   double* pcr = red + 2 * (RT > 32 ? RT : 32) * 3;  // 2 buffers x 3 arrays x RT
   const bool warp_mode = (T & 31) == 0;
   int parity = 0;
@@ -215,7 +214,7 @@ __global__ void __launch_bounds__(MAXT, MINB) collide_kernel(CollideArgs p) {
 
     // ---- 4. downward elimination, rows normalised to unit diagonal ---------------------------------------------------
     //   apn_l s_left + x_l + cpn_l x_{l+1} = rpn_l ;  y-form for f + x:  ypn_l = f_l + rpn_l + cpn_l f_{l+1}
-    double cpn[E], ypn[E];
+    double cpn[E], ypn[E], apn[E];  // apn: spike of the downward sweep (coupling to the left neighbour chunk)
     double rpn_last, apn_last;
     {
       double Um, Lm;  // edge l-1
@@ -246,7 +245,7 @@ __global__ void __launch_bounds__(MAXT, MINB) collide_kernel(CollideArgs p) {
         const double inv = fast_rcp(bp);
         const double cp = -Uc * inv, ap = apv * inv, rp = rpv * inv;
         cpn[l] = cp;
-        if (live) apbuf[l * T + tt] = ap;
+        apn[l] = ap;
         ypn[l] = (l < E - 1) ? fma(cp, f_p, f_c + rp) : f_c;  // the last row is solved by the reduced system
         if (l == E - 1) {
           rpn_last = rp;
@@ -260,12 +259,12 @@ __global__ void __launch_bounds__(MAXT, MINB) collide_kernel(CollideArgs p) {
     // ---- 5. upward sweep: x_first = R0 - A0 s_left - C0 s_me --------------------------------------------------------
     double A0 = 0.0, C0 = 0.0, R0 = 0.0;
     if (E >= 2) {
-      double RY = ypn[E - 2], A = apbuf[(E - 2) * T + tt], Cc = cpn[E - 2];
+      double RY = ypn[E - 2], A = apn[E - 2], Cc = cpn[E - 2];
 #pragma unroll
       for (int l = E - 3; l >= 0; l--) {
         const double cp = cpn[l];
         RY = fma(-cp, RY, ypn[l]);
-        A = fma(-cp, A, apbuf[l * T + tt]);
+        A = fma(-cp, A, apn[l]);
         Cc = -cp * Cc;
       }
       A0 = A, C0 = Cc;
@@ -342,7 +341,7 @@ __global__ void __launch_bounds__(MAXT, MINB) collide_kernel(CollideArgs p) {
       if (live) outc[E - 1] = y;
 #pragma unroll
       for (int l = E - 2; l >= 0; l--) {
-        y = fma(-cpn[l], y, fma(-apbuf[l * T + tt], s_left, ypn[l]));
+        y = fma(-cpn[l], y, fma(-apn[l], s_left, ypn[l]));
         if (live) outc[l] = y;
       }
     }
