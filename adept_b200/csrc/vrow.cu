@@ -33,6 +33,14 @@ struct VrowArgs {
   const double* nu_fp;  // [batch*nx]
   double nu_fp_scale;
   int model;
+  // peer mode (single grid sharded over GPUs, every buffer v-sharded [nx_global, nv / P] and mapped over NVLink): cell i
+  // of local row r is READ from in_peer[i >> nvp_shift] and WRITTEN to out_peer[i >> nvp_shift], both at row
+  // row0_global + r, column i & mask -- the two layout transposes of the decomposition ride on the kernel's own loads
+  // and stores (whole 8 * nv / P byte row segments per peer: NVLink-friendly).  nvp_shift < 0: off.
+  const double* in_peer[8];
+  double* out_peer[8];
+  int nvp_shift;
+  long long row0_global;
 };
 
 template <int LOGN>
@@ -87,10 +95,20 @@ __global__ void __launch_bounds__(VrowCfg<LOGN>::THREADS, (VrowCfg<LOGN>::THREAD
   }
 
   cplx x[E];
+  if (p.nvp_shift >= 0) {
+    const size_t nvp = (size_t)1 << p.nvp_shift;
 #pragma unroll
-  for (int m = 0; m < E; m++) {
-    const int e = t + T * m;
-    x[m] = cmake(__ldcs(a_in + e), __ldcs(b_in + e));
+    for (int m = 0; m < E; m++) {
+      const int e = t + T * m;
+      const double* src = p.in_peer[e >> p.nvp_shift] + (size_t)(p.row0_global + row0) * nvp + (e & (nvp - 1));
+      x[m] = cmake(__ldcs(src), __ldcs(src + nvp));
+    }
+  } else {
+#pragma unroll
+    for (int m = 0; m < E; m++) {
+      const int e = t + T * m;
+      x[m] = cmake(__ldcs(a_in + e), __ldcs(b_in + e));
+    }
   }
   if (live) phase_table_fill<LOGN>(ph, alpha[0], alpha[1], t, T);  // sincos latency hides behind the loads in flight
   fft_forward<LOGN>(x, buf, p.tw, t, p.zero);
@@ -131,11 +149,20 @@ __global__ void __launch_bounds__(VrowCfg<LOGN>::THREADS, (VrowCfg<LOGN>::THREAD
   if constexpr (TMA_OUT) {
     if (threadIdx.x == 0) tma_wait_read_all();  // shared memory must outlive the TMA reads
   } else {
-    double* a_out = p.fout + row0 * N;
-    double* b_out = a_out + N;
-    for (int i = t; i < N; i += T) {
-      __stcs(a_out + i, rowA[i + (i >> 4)]);
-      __stcs(b_out + i, rowB[i + (i >> 4)]);
+    if (p.nvp_shift >= 0) {  // the transpose back to the v-sharded layout rides on the stores (peer memory)
+      const size_t nvp = (size_t)1 << p.nvp_shift;
+      for (int i = t; i < N; i += T) {
+        double* dst = p.out_peer[i >> p.nvp_shift] + (size_t)(p.row0_global + row0) * nvp + (i & (nvp - 1));
+        dst[0] = rowA[i + (i >> 4)];
+        dst[nvp] = rowB[i + (i >> 4)];
+      }
+    } else {
+      double* a_out = p.fout + row0 * N;
+      double* b_out = a_out + N;
+      for (int i = t; i < N; i += T) {
+        __stcs(a_out + i, rowA[i + (i >> 4)]);
+        __stcs(b_out + i, rowB[i + (i >> 4)]);
+      }
     }
   }
 }
@@ -171,7 +198,7 @@ static int launch_vrow(const VrowArgs& p, cudaStream_t stream) {
 template <int LOGN>
 static int launch_vrow_auto(const VrowArgs& p, cudaStream_t stream) {
   using K = VrowCfg<LOGN>;
-  const bool tma_ok = LOGN >= 11 && tma_available() && (reinterpret_cast<uintptr_t>(p.fout) & 15) == 0 &&
+  const bool tma_ok = p.nvp_shift < 0 && LOGN >= 11 && tma_available() && (reinterpret_cast<uintptr_t>(p.fout) & 15) == 0 &&
                       (unsigned long long)p.npairs * 2 * (K::N / 16) < (1ull << 31);
   if constexpr (LOGN >= 11) {
     if (tma_ok) return launch_vrow<LOGN, true>(p, stream);
@@ -187,7 +214,8 @@ bool vpush_collide_supported(int nx, int nv, int model, int scheme, int nodrag) 
 
 int vpush_collide_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* e, const double* dex,
                       const double* pond, double q, double m, double dt, double k1v, const double* v, double dv,
-                      const double* nu_fp, double nu_fp_scale, int model, cudaStream_t stream) {
+                      const double* nu_fp, double nu_fp_scale, int model, cudaStream_t stream,
+                      const double* const* in_peers, double* const* out_peers, int n_peers, long long row0_global) {
   if (batch < 1 || !vpush_collide_supported(nx, nv, model, FP_CENTRAL, 0)) {
     set_last_error("vpush_collide: unsupported shape batch=%d nx=%d nv=%d / model=%d", batch, nx, nv, model);
     return ADEPT_ERR_UNSUPPORTED;
@@ -200,6 +228,19 @@ int vpush_collide_f64(const double* fin, double* fout, int batch, int nx, int nv
   p.tw = get_twiddles(logn), p.zero = 0;
   p.v = v, p.dv = dv, p.nu_fp = nu_fp, p.nu_fp_scale = nu_fp_scale, p.model = model;
   if (!p.tw) return ADEPT_ERR_CUDA;
+  p.nvp_shift = -1;
+  if (in_peers || out_peers) {
+    if (!in_peers || !out_peers || batch != 1 || n_peers < 1 || n_peers > 8 || (n_peers & (n_peers - 1)) ||
+        nv % n_peers) {
+      set_last_error("vpush_collide(peer mode): needs batch == 1, both pointer tables and a power-of-two number of "
+                     "peers <= 8 (got %d)", n_peers);
+      return ADEPT_ERR_BAD_ARG;
+    }
+    int sh = 0;
+    while ((nv / n_peers) >> (sh + 1)) sh++;
+    p.nvp_shift = sh, p.row0_global = row0_global;
+    for (int j = 0; j < n_peers; j++) p.in_peer[j] = in_peers[j], p.out_peer[j] = out_peers[j];
+  }
   switch (logn) {
     case 9: return launch_vrow_auto<9>(p, stream);
     case 10: return launch_vrow_auto<10>(p, stream);

@@ -79,6 +79,25 @@ def vpush_collide(f, e, pond, q, m, dt, k1v, v, dv, nu_fp, model=1, dex=None, ou
     return out
 
 
+def _peer_array(ptrs):
+    import ctypes as C
+
+    return (C.c_void_p * len(ptrs))(*[int(q) for q in ptrs])
+
+
+def vpush_collide_p2p(in_ptrs, out_ptrs, row0_global, nx_local, nv, e, pond, q, m, dt, k1v, v, dv, nu_fp, model=1,
+                      dex=None):
+    """Fused v-advection + Fokker-Planck step of this rank's ``nx_local`` rows of a grid whose buffers are all
+    v-sharded ``[nx, nv / P]``: cells are read from and written to the owning ranks' buffers over peer memory
+    (``in_ptrs`` / ``out_ptrs``: one device pointer per rank)."""
+    rc = _lib.load().adept_b200_vpush_collide_p2p_f64(
+        _peer_array(in_ptrs), _peer_array(out_ptrs), len(out_ptrs), int(row0_global), int(nx_local), int(nv),
+        _ptr(e, "e"), _ptr(dex, "dex", True), _ptr(pond, "pond", True), float(q), float(m), float(dt), float(k1v),
+        _ptr(v, "v"), float(dv), _ptr(nu_fp, "nu_fp"), int(model), _stream())
+    _lib.check(rc, "vpush_collide_p2p")
+    _count()
+
+
 # ---------------------------------------------------------------------------------------------------- adjoints
 def edfdv_exp_bwd_accel(f_in, g, e, pond, q, m, dt, k1v, dex=None, out=None):
     """accel_bar[.., i] = sum_j g_ij d f'_ij / d accel_i of :func:`edfdv_exp` (f_in = the forward input)."""

@@ -11,6 +11,14 @@ distribution ``f[nx, nv/P]`` (x-pencils are local), the v-advection and the coll
   ``nx nv 8 (P-1)/P^2`` bytes per rank.  The send side of the forward transpose and the receive side of the backward
   one need no packing (row blocks of a v-shard are contiguous); the other two sides are one local permute-copy each.
 
+On NVLink-connected GPUs the two transposes do not exist as separate operations (``transpose="p2p"``, the default
+when the shapes allow it): every buffer stays v-sharded, and the fused v-advection + collision kernel of a rank reads
+each cell of its rows straight from the rank that owns the column and writes the result straight back, through peer
+memory mapped with ``torch.distributed._symmetric_memory`` (``adept_b200_vpush_collide_p2p_f64``).  A row touches one
+contiguous ``8 nv/P``-byte segment per peer, so the link sees large transfers that overlap the kernel's math; the
+x-advection stays local.  The rho all-reduce after the x-advection and a one-word all-reduce after the v-advection
+order the ranks.  The all-to-all path (``transpose="nccl"``) remains for the other shapes and operators.
+
 One process per GPU, ``torch.distributed`` (NCCL on the B200 box; the same code runs over gloo on CPU tensors when a
 CPU operator table is injected -- that is how tests/test_sharded.py covers the N > 1 logic without a GPU).  State between
 steps is kept v-sharded.  Scope: leapfrog, poisson, exponential or cubic-spline v-push, Fokker-Planck + Krook, no
@@ -64,7 +72,7 @@ class CudaOps:
 class ShardedVlasov1D:
     """``sim = ShardedVlasov1D(deck); sim.step()``; rank r owns velocity columns ``[r nv/P, (r+1) nv/P)``."""
 
-    def __init__(self, deck: dict, group=None, device=None, local_ops=None):
+    def __init__(self, deck: dict, group=None, device=None, local_ops=None, transpose="auto"):
         from .config import build_cfg
         from .functions import SpaceTimeEnvelopeFunction
         from .pushers import Collisions, EMDriver
@@ -127,6 +135,89 @@ class ShardedVlasov1D:
         self.state["e"] = torch.zeros(self.nx, dtype=torch.float64, device=dev)
         self.state["de"] = torch.zeros(self.nx, dtype=torch.float64, device=dev)
         self.t, self.step_index = 0.0, 0
+        if transpose not in ("auto", "nccl", "p2p"):
+            raise ValueError(f"transpose={transpose!r}")
+        self.p2p = None
+        if transpose != "nccl" and isinstance(local_ops, CudaOps):
+            why = self._p2p_unsupported()
+            if why is None:
+                self._setup_p2p()
+            elif transpose == "p2p":
+                raise AdeptB200Error(f"transpose='p2p' is not available here: {why}")
+
+    # ---- peer-memory transposes -----------------------------------------------------------------------------------
+    def _p2p_unsupported(self):
+        """None when the fused-transpose kernels cover this deck, else the reason."""
+        t = self.cfg["terms"]
+        P, nx = self.P, self.nx
+        if len(self.names) != 1:
+            return "more than one species"
+        nv = self.nvp[self.names[0]] * P
+        if P & (P - 1) or P > 8:
+            return "number of ranks is not a power of two <= 8"
+        if t["edfdv"] != "exponential" or not self.fp_on or self.krook_on:
+            return "needs the spectral v-push with Fokker-Planck collisions and no Krook operator"
+        if self.coll.scheme != 0 or self.coll.model not in (0, 1) or self.coll.nodrag:
+            return "needs central-differencing Lenard-Bernstein / Dougherty collisions"
+        if nx & (nx - 1) or not 256 <= nx <= 4096 or (nv // P) % 4:
+            return "x-advection shape is not handled by the TMA kernel"
+        if nv & (nv - 1) or not 512 <= nv <= 8192 or (nx // P) % 2:
+            return "v-advection shape is not handled by the fused kernel"
+        return None
+
+    def _setup_p2p(self):
+        import torch.distributed._symmetric_memory as symm
+
+        name = self.names[0]
+        nvp, nv = self.nvp[name], self.nvp[name] * self.P
+        group = self.group if self.group is not None else dist.group.WORLD
+        f_vs = symm.empty((self.nx, nvp), dtype=torch.float64, device=self.device)   # state: all x, my columns
+        f_st = symm.empty((self.nx, nvp), dtype=torch.float64, device=self.device)   # f* after the x-push, same layout
+        h_vs, h_st = symm.rendezvous(f_vs, group), symm.rendezvous(f_st, group)
+        f_vs.copy_(self.state[name])
+        self.state[name] = f_vs
+        nparts = self.lops.ops.vdfdx_rho_parts(f_vs)
+        tt = lambda a: torch.as_tensor(np.array(a, dtype=np.float64), device=self.device)  # noqa: E731
+        self.p2p = {
+            # per-step inputs stay on the device: space factors here, O(1) time factors from the host each step
+            "ex_space": [tt(d.envelope.space_envelope(self.x)) for d in self.ex],
+            "ex_kx": [tt(d.k0 * self.x) for d in self.ex],
+            "nu_fp_space": tt(self.nu_fp_prof.space_envelope(self.x[self.rows]) * np.ones(self.nxp)),
+            "f_vs": f_vs, "f_st": f_st, "vs_ptrs": list(h_vs.buffer_ptrs), "st_ptrs": list(h_st.buffer_ptrs),
+            "handles": (h_vs, h_st), "nv": nv,
+            "parts": torch.zeros((nparts, self.nx), dtype=torch.float64, device=self.device),
+            "token": torch.zeros(1, dtype=torch.float64, device=self.device),
+        }
+        dist.barrier(group=self.group)  # every rank's buffers are mapped and initialised before anyone stores into them
+
+    def _step_p2p(self):
+        """One leapfrog step with the transposes fused into the v-row kernel's loads and stores (module docstring)."""
+        g, dt, t = self.cfg["grid"], float(self.grid.dt), self.t
+        ops, pp, n = self.lops.ops, self.p2p, self.names[0]
+        sg, sp = g["species_grids"][n], g["species_params"][n]
+        # driver field and collision frequency: same closed forms and rounding order as the reference (field.py:21-26,
+        # functions.py:112-118), evaluated on the device from resident space factors -- no host-device copy per step
+        dex = torch.zeros(self.nx, dtype=torch.float64, device=self.device)
+        for d, space, kx in zip(self.ex, pp["ex_space"], pp["ex_kx"]):
+            w = d.w0 + d.dw0
+            dex = dex + ((float(d.envelope.time_envelope(t)) * space) * w) * d.a0 * torch.sin(kx - w * t)
+        # 1. x-push on my columns, purely local (its 32-byte row pieces would waste the link)
+        ops.vdfdx_rho(pp["f_vs"], self.v_loc[n], dt, self.k1x, pp["parts"], out=pp["f_st"])
+        rowsum = ops.reduce_parts(pp["parts"], 1.0, 1.0)
+        dist.all_reduce(rowsum, op=dist.ReduceOp.SUM, group=self.group)  # also: every rank's x-push has completed
+        rho = self.lops.rho_from_sum(rowsum, float(sg["dv"]), float(sp["charge"]), self.ion)
+        e = self.lops.poisson(rho, self.one_over_kx)
+        e_loc, dex_loc = e[self.rows].contiguous(), dex[self.rows].contiguous()
+        # 2. v-push + collisions on my rows: cells come from and go back to the ranks that own their columns
+        nu_fp = float(self.nu_fp_prof.time_envelope(t)) * pp["nu_fp_space"]
+        ops.vpush_collide_p2p(pp["st_ptrs"], pp["vs_ptrs"], self.rank * self.nxp, self.nxp, pp["nv"], e_loc, None,
+                              float(sp["charge"]), float(sp["mass"]), dt, float(sg["kvr"][1]), self.v_full[n],
+                              float(sg["dv"]), nu_fp, model=self.coll.model, dex=dex_loc)
+        dist.all_reduce(pp["token"], group=self.group)  # every rank's stores into my columns have completed
+        self.state["e"], self.state["de"] = e, dex
+        self.step_index += 1
+        self.t = self.step_index * dt
+        return self.state
 
     # ---- layout changes -------------------------------------------------------------------------------------------
     def to_x_sharded(self, f_vs):
@@ -160,6 +251,8 @@ class ShardedVlasov1D:
         return torch.as_tensor(total, device=self.device)
 
     def step(self):
+        if self.p2p is not None:
+            return self._step_p2p()
         g, dt, t = self.cfg["grid"], float(self.grid.dt), self.t
         lops = self.lops
         dex = self._dex(t)

@@ -84,6 +84,23 @@ int adept_b200_vpush_collide_f64(const double* f_in, double* f_out, int batch, i
                                  const double* dex, const double* pond, double charge, double mass, double dt,
                                  double k1v, const double* v, double dv, const double* nu_fp, int model, void* stream);
 
+/* ---- single grid sharded over the GPUs of one node: transposes fused into the v-row kernel ----------------
+ * The reference's `grid.parallel: ["x", "v"]` decomposition alternates between a v-sharded layout f[nx, nv/P]
+ * (x-advection) and an x-sharded one f[nx/P, nv] (v-advection + collisions); XLA inserts all-to-all transposes.  Here
+ * every buffer stays v-sharded and the fused v-advection + collision kernel of a rank reads each cell of its rows
+ * straight from the rank that owns the column and writes the result straight back, over NVLink peer memory
+ * (in_peers / out_peers: host arrays of n_peers device pointers to the ranks' [nx_global, nv/n_peers] buffers, each
+ * mapped into this process; n_peers a power of two <= 8).  A kernel row touches one 8 nv/P-byte segment per peer,
+ * so the traffic is NVLink-friendly and no transpose pass or all-to-all exists; the x-advection stays purely local.
+ * Ordering between ranks is the caller's (the rho all-reduce after the x-advection, one barrier after this kernel).
+ * nx = rows owned by this rank (even), row0_global = index of its first row; shapes and operators as
+ * adept_b200_vpush_collide_f64.  (Scattering the x-advection's 32-byte row pieces instead was measured: 148 us
+ * against 79 us local at 4096 x 2048 per rank -- small remote stores waste the link.) */
+int adept_b200_vpush_collide_p2p_f64(const double* const* in_peers_host, double* const* out_peers_host, int n_peers,
+                                     long long row0_global, int nx, int nv, const double* e, const double* dex,
+                                     const double* pond, double charge, double mass, double dt, double k1v,
+                                     const double* v, double dv, const double* nu_fp, int model, void* stream);
+
 /* In-loop save moments in one pass over f (get_default_save_func / get_field_save_func, adept/_vlasov1d/storage.py:
  * 286-327, 119-162): out[k, row] = dv sum_j g_k(f_j, v_j), g = { f, f v, f v^2, f v^3, -|f| log|f|, f^2 }, out is
  * [6, batch*nx].  With f1 != NULL the distribution is the linear interpolation f0 + w (f1 - f0) that diffrax hands to

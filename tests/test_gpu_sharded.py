@@ -16,14 +16,15 @@ from test_sharded import deck
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, dk, nsteps, out_path):
+def _worker(rank, world, port, dk, nsteps, out_path, transpose="nccl"):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
                             device_id=torch.device("cuda", rank))
     try:
         from adept_b200.sharded import ShardedVlasov1D
 
-        sim = ShardedVlasov1D(dk)
+        sim = ShardedVlasov1D(dk, transpose=transpose)
+        assert (sim.p2p is not None) == (transpose == "p2p")
         sim.t, sim.step_index = 30.0, 300
         for _ in range(nsteps):
             sim.step()
@@ -48,6 +49,33 @@ def test_sharded_gpu_step_matches_oracle(tmp_path, edfdv, nx, nv):
         port = s.getsockname()[1]
     out = tmp_path / "sharded.npz"
     mp.spawn(_worker, args=(world, port, dk, nsteps, str(out)), nprocs=world, join=True)
+    got = np.load(out)
+    cfg = O.build_cfg(deepcopy(dk))
+    vf = O.VlasovMaxwell(cfg)
+    y = O.init_state(cfg)
+    t = 30.0
+    for i in range(nsteps):
+        y = vf(t, y, None)
+        t = (300 + i + 1) * cfg["grid"]["dt"]
+    rel = np.linalg.norm(got["f"] - y["electron"]) / np.linalg.norm(y["electron"])
+    assert rel <= 1e-12, rel
+    np.testing.assert_allclose(got["e"], y["e"], rtol=0, atol=5e-15)
+
+
+@pytest.mark.parametrize("nx,nv", [(512, 1024), (1024, 2048)])
+def test_sharded_gpu_p2p_transposes_match_oracle(tmp_path, nx, nv):
+    """Transposes fused into the kernels' stores over NVLink peer memory (no all-to-all): same bar as the NCCL path."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2
+    dk = deck("exponential", krook=False)
+    dk["grid"].update(nx=nx, nv=nv)
+    nsteps = 3
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = tmp_path / "sharded_p2p.npz"
+    mp.spawn(_worker, args=(world, port, dk, nsteps, str(out), "p2p"), nprocs=world, join=True)
     got = np.load(out)
     cfg = O.build_cfg(deepcopy(dk))
     vf = O.VlasovMaxwell(cfg)

@@ -1,7 +1,7 @@
 """Strong-scaling timing of ONE 4096 x 4096 grid sharded over the ranks (development aid; bench.py is the contract).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
-        tools/bench_sharded.py [nx nv steps]
+        tools/bench_sharded.py [nx nv steps [nccl|p2p|auto]]
 """
 import json
 import os
@@ -20,10 +20,11 @@ from adept_b200.sharded import ShardedVlasov1D  # noqa: E402
 nx = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 nv = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 K = int(sys.argv[3]) if len(sys.argv) > 3 else 30
+transpose = sys.argv[4] if len(sys.argv) > 4 else "auto"  # nccl | p2p | auto
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-sim = ShardedVlasov1D(c3_deck(nx, nv))
+sim = ShardedVlasov1D(c3_deck(nx, nv), transpose=transpose)
 sim.t, sim.step_index = 30.0, 300
 for _ in range(5):
     sim.step()
@@ -36,10 +37,29 @@ for _ in range(K):
 e1.record()
 dist.barrier()
 torch.cuda.synchronize()
+# second pass with the library's per-kernel event timing (rank 0 reports its own kernels)
+import ctypes  # noqa: E402
+
+from adept_b200 import _lib  # noqa: E402
+
+lib = _lib.load()
+lib.adept_b200_profile(1)
+for _ in range(K):
+    sim.step()
+torch.cuda.synchronize()
+buf = ctypes.create_string_buffer(1 << 16)
+lib.adept_b200_profile_report(buf, len(buf))
+kernels = {}
+for line in buf.value.decode().splitlines():
+    name, count, ms = line.split()
+    kernels[name] = round(float(ms) / int(count) * 1e3, 1)
+lib.adept_b200_profile(0)
 tm = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device="cuda")
 dist.all_reduce(tm, op=dist.ReduceOp.MAX)
 if rank == 0:
     el = float(tm.item())
-    print(json.dumps({"mode": "single grid, v-sharded (all-to-all x2 + all-reduce per step)", "n_gpus": world, "nx": nx,
-                      "nv": nv, "steps": K, "ms_per_step": el / K * 1e3, "cell_updates_per_s": nx * nv * K / el}))
+    mode = ("single grid, v-sharded, transposes fused into the kernels' stores over peer memory + all-reduce"
+            if sim.p2p is not None else "single grid, v-sharded (all-to-all x2 + all-reduce per step)")
+    print(json.dumps({"mode": mode, "n_gpus": world, "nx": nx,
+                      "nv": nv, "steps": K, "ms_per_step": el / K * 1e3, "cell_updates_per_s": nx * nv * K / el, "rank0_kernel_us": kernels}))
 dist.destroy_process_group()
