@@ -62,12 +62,12 @@ def test_sharded_gpu_step_matches_oracle(tmp_path, edfdv, nx, nv):
     np.testing.assert_allclose(got["e"], y["e"], rtol=0, atol=5e-15)
 
 
-@pytest.mark.parametrize("nx,nv", [(512, 1024), (1024, 2048)])
-def test_sharded_gpu_p2p_transposes_match_oracle(tmp_path, nx, nv):
-    """Transposes fused into the kernels' stores over NVLink peer memory (no all-to-all): same bar as the NCCL path."""
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs >= 2 GPUs")
-    world = 2
+@pytest.mark.parametrize("world,nx,nv", [(2, 512, 1024), (2, 1024, 2048), (4, 1024, 2048)])
+def test_sharded_gpu_p2p_transposes_match_oracle(tmp_path, world, nx, nv):
+    """Transposes fused into the v-row kernel's loads and stores over NVLink peer memory (no all-to-all): same bar as
+    the NCCL path."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs >= {world} GPUs")
     dk = deck("exponential", krook=False)
     dk["grid"].update(nx=nx, nv=nv)
     nsteps = 3
