@@ -114,3 +114,32 @@ def test_gradient_of_final_field_energy_wrt_drive_amplitude(ad):
     fdf = (float(loss(a0.detach(), fin.detach() + h * d)) - float(loss(a0.detach(), fin.detach() - h * d))) / (2 * h)
     adf = float((fin.grad * d).sum())
     assert abs(adf - fdf) <= 2e-6 * max(abs(fdf), 1e-14), (adf, fdf)
+
+
+def test_c5_gradient_through_2000_steps(ad):
+    """BASELINE.json configs[4] at full length: C2-sized grid (64 x 512), 2000 driven leapfrog + Dougherty steps,
+    d/d(a0) of the final field energy 0.5 mean(e^2) by reverse mode through the CUDA adjoints vs central differences
+    of the same forward run."""
+    nx, nv, nsteps = 64, 512, 2000
+    f0, x, v, p, rng = setup(nx, nv, seed=5)
+    w0, k0 = 1.1598, 0.3
+    nu = dev(np.full(nx, 1e-3))
+    kx = dev(k0 * x)
+
+    def loss(a0, fin):
+        f, e, t = fin, None, 0.0
+        for i in range(nsteps):
+            dex = a0 * w0 * torch.sin(kx - w0 * t)
+            f, e = ad.leapfrog_step(f, dex, nu, p)
+            t = (i + 1) * p["dt"]
+        return 0.5 * torch.mean(e**2.0)
+
+    a0 = torch.tensor(1.0e-3, dtype=torch.float64, device="cuda", requires_grad=True)
+    L = loss(a0, dev(f0))
+    L.backward()
+    g = float(a0.grad)
+    h = 1e-7
+    with torch.no_grad():
+        fd = (float(loss(a0.detach() + h, dev(f0))) - float(loss(a0.detach() - h, dev(f0)))) / (2 * h)
+    assert np.isfinite(g) and abs(g) > 0
+    assert abs(g - fd) <= 1e-5 * abs(fd), (g, fd, float(L))
