@@ -45,6 +45,7 @@ class Step(C.Structure):
         ("sg_m", c_d), ("sg_ratio", c_d),
         ("nu_fp_space", c_dp), ("nu_K_space", c_dp), ("nu_fp_time", c_d), ("nu_K_time", c_d), ("f_mx", c_dp),
         ("sync_counter", c_dp),
+        ("ex_w_row", c_dp), ("ex_a0_row", c_dp), ("ex_t", c_d * MAX_SUBSTEPS),
     ]
 
 

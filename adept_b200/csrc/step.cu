@@ -21,6 +21,9 @@ struct DriverArgs {
   double w[ADEPT_B200_MAX_DRIVERS], a0[ADEPT_B200_MAX_DRIVERS];
   double tenv[ADEPT_B200_MAX_SUBSTEPS][ADEPT_B200_MAX_DRIVERS];
   double wt[ADEPT_B200_MAX_SUBSTEPS][ADEPT_B200_MAX_DRIVERS];
+  const double* w_row;   // nullable [n_ex, n]: per-row frequency (ensemble members with different drivers)
+  const double* a0_row;  // nullable [n_ex, n]
+  double t_sub[ADEPT_B200_MAX_SUBSTEPS];
 };
 
 __global__ void __launch_bounds__(256) ex_driver_kernel(DriverArgs p) {
@@ -31,8 +34,11 @@ __global__ void __launch_bounds__(256) ex_driver_kernel(DriverArgs p) {
     for (int d = 0; d < p.n_ex; d++) {
       // field.py:21-26: env(x, t) * (w0 + dw0) * a0 * sin(k0 x - (w0 + dw0) t), env = time_env * space_env
       const double factor = __dmul_rn(p.tenv[s][d], p.space[d * p.n + i]);
-      const double amp = __dmul_rn(__dmul_rn(factor, p.w[d]), p.a0[d]);
-      total = __dadd_rn(total, __dmul_rn(amp, sin(__dsub_rn(p.kx[d * p.n + i], p.wt[s][d]))));
+      const double w = p.w_row ? p.w_row[d * p.n + i] : p.w[d];
+      const double a0 = p.a0_row ? p.a0_row[d * p.n + i] : p.a0[d];
+      const double wt = p.w_row ? __dmul_rn(w, p.t_sub[s]) : p.wt[s][d];
+      const double amp = __dmul_rn(__dmul_rn(factor, w), a0);
+      total = __dadd_rn(total, __dmul_rn(amp, sin(__dsub_rn(p.kx[d * p.n + i], wt))));
     }
     p.dex[(long long)s * p.n + i] = total;
   }
@@ -215,6 +221,8 @@ int step_f64(const adept_b200_step& s, cudaStream_t st) {
   auto launch_drivers = [&]() -> int {
     DriverArgs d = {};
     d.n_ex = s.n_ex, d.n_sub = n_sub, d.n = c.n, d.space = s.ex_space, d.kx = s.ex_kx, d.dex = s.dex;
+    d.w_row = s.ex_w_row, d.a0_row = s.ex_a0_row;
+    for (int j = 0; j < ADEPT_B200_MAX_SUBSTEPS; j++) d.t_sub[j] = s.ex_t[j];
     for (int k = 0; k < ADEPT_B200_MAX_DRIVERS; k++) {
       d.w[k] = s.ex_w[k], d.a0[k] = s.ex_a0[k];
       for (int j = 0; j < ADEPT_B200_MAX_SUBSTEPS; j++) d.tenv[j][k] = s.ex_tenv[j][k], d.wt[j][k] = s.ex_wt[j][k];

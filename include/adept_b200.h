@@ -246,6 +246,12 @@ typedef struct adept_b200_step {
    * a single large grid (batch == 1, nx in {1024, 2048, 4096}) runs driver + ponderomotive force + charge density +
    * Poisson solve as ONE launch whose last-arriving CTA solves for E; null selects the separate kernels. */
   unsigned int* sync_counter;
+  /* ensembles whose members differ in driver frequency / amplitude (parameter scans): per-row values
+   * [n_ex, batch*nx] that replace ex_w[d] / ex_a0[d] (both nullable), and the substep times t + dt_array[s] from which
+   * the per-row phase w t is formed on the device (only read when ex_w_row is given). */
+  const double* ex_w_row;
+  const double* ex_a0_row;
+  double ex_t[ADEPT_B200_MAX_SUBSTEPS];
 } adept_b200_step;
 
 int adept_b200_step_f64(const adept_b200_step* step, void* stream);
