@@ -245,6 +245,14 @@ int adept_b200_vpush_collide_p2p_f64(const double* const* in_peers_host, double*
                            nu_fp, 1.0, model, (cudaStream_t)stream, in_peers_host, out_peers_host, n_peers, row0_global);
 }
 
+int adept_b200_interp2d_f64(const double* f0, const double* f1, double w, int nx, int nv, const double* x,
+                            const double* v, const double* xq, const double* vq, int nxq, int nvq, double* out,
+                            void* stream) {
+  ADEPT_REQUIRE(f0, "f0") ADEPT_REQUIRE(x, "x") ADEPT_REQUIRE(v, "v") ADEPT_REQUIRE(xq, "xq") ADEPT_REQUIRE(vq, "vq")
+  ADEPT_REQUIRE(out, "out")
+  return interp2d_f64(f0, f1, w, nx, nv, x, v, xq, vq, nxq, nvq, out, (cudaStream_t)stream);
+}
+
 long long adept_b200_launch_count(void) { return adept::g_launches.load(std::memory_order_relaxed); }
 
 int adept_b200_vpush_collide_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* e,

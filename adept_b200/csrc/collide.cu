@@ -46,24 +46,27 @@ struct CollideArgs {
   double nu_fp_scale, nu_K_scale;  // nu = scale * nu[row] (time envelope applied in the kernel)
 };
 
+// Reciprocals here are fast_rcp (MUFU seed + two Newton steps, <= 1 ulp) and the per-row quotients D/dv, 1/dv, dv/D are
+// formed once per row by the caller: an IEEE division costs ~25 fp64 instructions and this runs once per cell edge.
 __device__ __forceinline__ double cc_delta(double w) {  // driftdiffusion.py:96-103
-  if (fabs(w) < 1.0e-8) return 0.5 - w / 12.0 + w * w * w / 720.0;
-  return 1.0 / w - 1.0 / expm1(w);
+  if (fabs(w) < 1.0e-8) return 0.5 - w * (1.0 / 12.0) + w * w * w * (1.0 / 720.0);
+  return fast_rcp(w) - fast_rcp(expm1(w));
 }
 
-// bare upper / lower entries of one edge, reference formulas (generic path)
-__device__ __forceinline__ void bare_edge(double C, double D, double dv, int scheme, double& bu, double& bl) {
+// bare upper / lower entries of one edge (generic path); D_dv = max(D, 1e-30) / dv, inv_dv = 1 / dv,
+// dv_D = dv / max(D, 1e-30)
+__device__ __forceinline__ void bare_edge(double C, double D_dv, double inv_dv, double dv_D, int scheme, double& bu,
+                                          double& bl) {
   if (scheme == FP_CENTRAL) {  // driftdiffusion.py:585-590
-    bu = (C / 2.0 + D / dv) / dv;
-    bl = (-C / 2.0 + D / dv) / dv;
+    bu = (0.5 * C + D_dv) * inv_dv;
+    bl = (-0.5 * C + D_dv) * inv_dv;
   } else {  // driftdiffusion.py:637-648
-    const double sD = fmax(D, 1.0e-30);
-    const double w = C * dv / sD;
+    const double w = C * dv_D;
     const double dl = cc_delta(w);
-    const double alpha = -C * dl + sD / dv;
-    const double beta = -C * (1.0 - dl) - sD / dv;
-    bu = -beta / dv;
-    bl = alpha / dv;
+    const double alpha = -C * dl + D_dv;
+    const double beta = -C * (1.0 - dl) - D_dv;
+    bu = -beta * inv_dv;
+    bl = alpha * inv_dv;
   }
 }
 
@@ -183,6 +186,9 @@ __global__ void __launch_bounds__(MAXT, MINB) collide_kernel(CollideArgs p) {
     const double pD = dtnu * D / (dv * dv);
     const double q = dtnu * (2.0 * beta * D) / (2.0 * dv);
     const double w0 = q * (vc + 0.5 * dv - vbar), dq = q * dv;
+    // per-row quotients of the generic path (one IEEE division each per row instead of several per cell edge)
+    const double sD = fmax(D, 1.0e-30), inv_dv = 1.0 / dv;
+    const double D_dv = ((p.scheme == FP_CENTRAL) ? D : sD) / dv, dv_D = dv / sD;
     auto edge = [&](int l, double& U, double& L) {
       const int e = i0 + l;  // global edge index, valid for 0 <= e <= nv-2
       if (e < 0 || e > nv - 2) {
@@ -201,12 +207,12 @@ __global__ void __launch_bounds__(MAXT, MINB) collide_kernel(CollideArgs p) {
           C = 0.0;
         } else if (p.model == FP_SUPERGAUSSIAN) {
           const double ph0 = beta * pow(fabs(va - vbar), p.sg_m), ph1 = beta * pow(fabs(vb - vbar), p.sg_m);
-          C = D * (ph1 - ph0) / dv;
+          C = D * (ph1 - ph0) * inv_dv;
         } else {
           C = (2.0 * beta * D) * (0.5 * (vb + va) - vbar);
         }
         double bu, bl;
-        bare_edge(C, D, dv, p.scheme, bu, bl);
+        bare_edge(C, D_dv, inv_dv, dv_D, p.scheme, bu, bl);
         U = dtnu * bu;
         L = dtnu * bl;
       }

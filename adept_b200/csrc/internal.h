@@ -33,6 +33,8 @@ int reduce_parts_f64(const double* parts, int nparts, long long n, double scale_
                      double* out, cudaStream_t stream);
 int save_moments_f64(const double* f0, const double* f1, double w, int batch, int nx, int nv, const double* v,
                      double dv, double* out, cudaStream_t stream);
+int interp2d_f64(const double* f0, const double* f1, double w, int nx, int nv, const double* x, const double* v,
+                 const double* xq, const double* vq, int nxq, int nvq, double* out, cudaStream_t stream);
 int edfdv_exp_bwd_accel_f64(const double* f, const double* g, int batch, int nx, int nv, const double* e,
                             const double* dex, const double* pond, double q, double m, double dt, double k1,
                             double* abar, cudaStream_t stream);

@@ -233,4 +233,54 @@ int save_moments_f64(const double* f0, const double* f1, double w, int batch, in
   return check_launch("save_moments_kernel");
 }
 
+
+// ---- distribution save on a coarser (x, v) mesh (storage.py:173-181: interpax.interp2d, method="linear") -----------
+// out[a, b] = bilinear interpolation of f (or of the time-interpolated f0 + w (f1 - f0)) at (xq[a], vq[b]); NaN outside
+// the grid, like interpax with extrap=False.  Node search = searchsorted(side="right") on the actual axes.
+__device__ __forceinline__ int upper_bound(const double* __restrict__ a, int n, double q) {  // #{k : a[k] <= q}
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] <= q) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) interp2d_kernel(const double* __restrict__ f0, const double* __restrict__ f1,
+                                                       double w, int nx, int nv, const double* __restrict__ x,
+                                                       const double* __restrict__ v, const double* __restrict__ xq,
+                                                       const double* __restrict__ vq, int nxq, int nvq,
+                                                       double* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)nxq * nvq) return;
+  const int a = (int)(idx / nvq), b = (int)(idx % nvq);
+  const double qx = xq[a], qv = vq[b];
+  int i = upper_bound(x, nx, qx), j = upper_bound(v, nv, qv);
+  i = min(max(i, 1), nx - 1), j = min(max(j, 1), nv - 1);
+  auto at = [&](int r, int c) {
+    const size_t o = (size_t)r * nv + c;
+    double val = f0[o];
+    if (f1) val = val + w * (f1[o] - val);
+    return val;
+  };
+  const double f00 = at(i - 1, j - 1), f01 = at(i - 1, j), f10 = at(i, j - 1), f11 = at(i, j);
+  const double x0 = x[i - 1], x1 = x[i], y0 = v[j - 1], y1 = v[j];
+  const double dx0 = qx - x0, dx1 = x1 - qx, dy0 = qv - y0, dy1 = y1 - qv;
+  double r = (dx1 * (f00 * dy1 + f01 * dy0) + dx0 * (f10 * dy1 + f11 * dy0)) / ((x1 - x0) * (y1 - y0));
+  if (qx < x[0] || qx > x[nx - 1] || qv < v[0] || qv > v[nv - 1]) r = __longlong_as_double(0x7ff8000000000000ll);
+  out[idx] = r;
+}
+
+int interp2d_f64(const double* f0, const double* f1, double w, int nx, int nv, const double* x, const double* v,
+                 const double* xq, const double* vq, int nxq, int nvq, double* out, cudaStream_t stream) {
+  if (nx < 2 || nv < 2 || nxq < 1 || nvq < 1) {
+    set_last_error("interp2d: bad shape nx=%d nv=%d nxq=%d nvq=%d", nx, nv, nxq, nvq);
+    return ADEPT_ERR_BAD_SHAPE;
+  }
+  const long long total = (long long)nxq * nvq;
+  ProfileScope prof("interp2d", stream);
+  interp2d_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(f0, f1, w, nx, nv, x, v, xq, vq, nxq, nvq, out);
+  return check_launch("interp2d_kernel");
+}
+
 }  // namespace adept

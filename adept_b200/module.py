@@ -75,6 +75,31 @@ def field_moments(cfg, y0, y1=None, w=0.0):
     return res
 
 
+def dist_save(name, xax=None, vax=None):
+    """Save function for a species' distribution (get_dist_save_func, storage.py:165-188): the full f for a {t} block,
+    or f interpolated linearly on the mesh ``xax x vax`` for a {t, x, v} block (NaN outside the grid, as interpax does
+    with extrapolation off).  The {t, kx, v} block (|rfft_x f|) is not implemented."""
+    if (xax is None) != (vax is None):
+        raise ValueError("dist_save: give both xax and vax or neither")
+    tables = {}
+
+    def fn(cfg, y0, y1=None, w=0.0):
+        f0 = y0[name]
+        if xax is None:
+            return f0.clone() if y1 is None else f0 + w * (y1[name] - f0)
+        from . import ops
+
+        key = str(f0.device)
+        if key not in tables:
+            sg = cfg["grid"]["species_grids"][name]
+            tables[key] = tuple(torch.as_tensor(np.array(a, dtype=np.float64), device=f0.device)
+                                for a in (cfg["grid"]["x"], sg["v"], xax, vax))
+        x, v, xq, vq = tables[key]
+        return ops.interp2d(f0, x, v, xq, vq, None if y1 is None else y1[name], w)
+
+    return fn
+
+
 class Vlasov1D:
     """``sim = Vlasov1D(deck); y = sim.run(nsteps)``; ``sim.state`` holds the reference's state dict on the GPU."""
 

@@ -151,6 +151,20 @@ def save_moments(f0, v, dv, f1=None, w=0.0, out=None):
     return out
 
 
+def interp2d(f0, x, v, xq, vq, f1=None, w=0.0, out=None):
+    """Bilinear interpolation of f[nx, nv] (or of f0 + w (f1 - f0)) on the mesh xq x vq; NaN outside the grid."""
+    if f0.dim() != 2:
+        raise _lib.AdeptB200Error("interp2d: f must be [nx, nv]")
+    nx, nv = f0.shape
+    out = torch.empty((xq.numel(), vq.numel()), dtype=torch.float64, device=f0.device) if out is None else out
+    rc = _lib.load().adept_b200_interp2d_f64(
+        _ptr(f0, "f0"), _ptr(f1, "f1", True), float(w), nx, nv, _ptr(x, "x"), _ptr(v, "v"), _ptr(xq, "xq"),
+        _ptr(vq, "vq"), int(xq.numel()), int(vq.numel()), _ptr(out, "out"), _stream())
+    _lib.check(rc, "interp2d")
+    _count()
+    return out
+
+
 def filter_x(f, filt, zeros_v, out=None):
     """Real per-mode multiplier along x: irfft(filt[:, None] * rfft(f, axis=x)) (HouLiFilter, vlasov.py:215-220)."""
     b, nx, nv = _shape3(f)

@@ -108,6 +108,14 @@ int adept_b200_vpush_collide_p2p_f64(const double* const* in_peers_host, double*
 int adept_b200_save_moments_f64(const double* f0, const double* f1, double w, int batch, int nx, int nv,
                                 const double* v, double dv, double* out, void* stream);
 
+/* Distribution save on a coarser mesh (get_dist_save_func, {t, x, v} block, adept/_vlasov1d/storage.py:173-181 ->
+ * interpax.interp2d, method "linear", extrap off): out[a, b] = bilinear interpolation of f[nx, nv] at (xq[a], vq[b]) on
+ * the axes x[nx], v[nv]; NaN outside the grid.  With f1 != NULL the distribution is f0 + w (f1 - f0) (diffrax's dense
+ * output between two steps), never materialised. */
+int adept_b200_interp2d_f64(const double* f0, const double* f1, double w, int nx, int nv, const double* x,
+                            const double* v, const double* xq, const double* vq, int nxq, int nvq, double* out,
+                            void* stream);
+
 /* Hou-Li spectral filter along x (HouLiFilter.__call__, vlasov.py:215-220): f_out = irfft(filt[m] rfft(f_in, axis=x)),
  * filt[nx/2+1] real.  zeros_v: a device array of nv zeros (the x-advection kernels run with zero advection speed). */
 int adept_b200_filter_x_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* filt,

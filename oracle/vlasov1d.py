@@ -943,6 +943,29 @@ def field_moments(cfg, y):
     return res
 
 
+def interp2d_linear(xq, yq, x, y, f):
+    """interpax.interp2d(xq, yq, x, y, f, method="linear") with its defaults (extrap=False -> NaN outside the grid,
+    no period), as called by get_dist_save_func (adept/_vlasov1d/storage.py:173-188).  interpax 0.3.12 is not installed
+    here (PARITY UNPINNED for this function): restated from its published algorithm -- i = clip(searchsorted(x, xq,
+    side="right"), 1, nx-1), same for j, bilinear blend of the four surrounding nodes divided by the cell area, queries
+    outside [x[0], x[-1]] x [y[0], y[-1]] replaced by NaN."""
+    xq, yq, x, y = (np.asarray(a, dtype=float) for a in (xq, yq, x, y))
+    i = np.clip(np.searchsorted(x, xq, side="right"), 1, len(x) - 1)
+    j = np.clip(np.searchsorted(y, yq, side="right"), 1, len(y) - 1)
+    f00, f01, f10, f11 = f[i - 1, j - 1], f[i - 1, j], f[i, j - 1], f[i, j]
+    x0, x1, y0, y1 = x[i - 1], x[i], y[j - 1], y[j]
+    dx0, dx1, dy0, dy1 = xq - x0, x1 - xq, yq - y0, y1 - yq
+    fq = (dx1 * (f00 * dy1 + f01 * dy0) + dx0 * (f10 * dy1 + f11 * dy0)) / ((x1 - x0) * (y1 - y0))
+    outside = (xq < x[0]) | (xq > x[-1]) | (yq < y[0]) | (yq > y[-1])
+    return np.where(outside, np.nan, fq)
+
+
+def dist_save_xv(f, x, v, xax, vax):
+    """get_dist_save_func for a {t, x, v} save block (storage.py:173-181): f interpolated on meshgrid(xax, vax, "ij")."""
+    xq, vq = np.meshgrid(xax, vax, indexing="ij")
+    return interp2d_linear(xq.ravel(), vq.ravel(), x, v, f).reshape(xq.shape)
+
+
 def save_axis(tcfg, grid):
     """storage.py:203-219 (_add_dim_axes for 't') + modules.py:166-181 defaults."""
     tmin = float(tcfg.get("tmin", grid["tmin"]))

@@ -438,3 +438,24 @@ def test_errors_are_loud(ops):
     g = torch.zeros(16, 16, dtype=torch.float64, device="cuda")
     with pytest.raises(AdeptB200Error, match="in-place"):
         ops.edfdv_spline(g, v, None, 1.0, 1.0, 0.1, 0.1, out=g)
+
+
+@pytest.mark.parametrize("nx,nv,nxq,nvq", [(32, 256, 16, 64), (64, 512, 32, 512), (17, 33, 41, 29)])
+def test_dist_save_interp2d_matches_oracle(ops, nx, nv, nxq, nvq):
+    """{t, x, v} distribution save (storage.py:173-181): bilinear interpolation with NaN outside the grid, also on the
+    state interpolated between two steps."""
+    rng = np.random.default_rng(nx + nv)
+    x = np.linspace(0.1, 20.8, nx)
+    v = np.linspace(-6.3, 6.3, nv)
+    f0, f1 = rng.standard_normal((nx, nv)), rng.standard_normal((nx, nv))
+    xq = np.linspace(0.0, 20.94, nxq)       # reaches past both ends of x: NaN there, like the reference
+    vq = np.linspace(-6.4, 6.4, nvq)
+    for w, b in ((0.0, None), (0.37, f1)):
+        ref = O.dist_save_xv(f0 if b is None else f0 + w * (f1 - f0), x, v, xq, vq)
+        out = host(ops.interp2d(dev(f0), dev(x), dev(v), dev(xq), dev(vq), None if b is None else dev(f1), w))
+        assert np.array_equal(np.isnan(out), np.isnan(ref))
+        ok = ~np.isnan(ref)
+        assert np.max(np.abs(out[ok] - ref[ok])) <= 1e-13 * max(1.0, np.max(np.abs(ref[ok])))
+    # a grid-node query hits the node exactly (searchsorted side="right")
+    out = host(ops.interp2d(dev(f0), dev(x), dev(v), dev(x), dev(v)))
+    assert np.max(np.abs(out - f0)) <= 1e-14

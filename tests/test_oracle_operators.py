@@ -238,3 +238,21 @@ def test_landau_damping_rate_matches_analytic_root(time, field, edfdv):
     sl = slice(-100, -50)
     gamma = np.mean(np.gradient(ek1[sl], dts) / ek1[sl])
     np.testing.assert_almost_equal(gamma, np.imag(root), decimal=2)
+
+
+def test_interp2d_linear_properties():
+    """interp2d restatement (storage.py:173-181 -> interpax, absent here): exact at the nodes, exact for bilinear
+    functions, NaN outside the grid (extrap off), right-continuous node search."""
+    rng = np.random.default_rng(0)
+    x = np.linspace(0.3, 20.0, 17)
+    v = np.linspace(-6.0, 6.0, 33)
+    f = rng.standard_normal((17, 33))
+    at_nodes = O.dist_save_xv(f, x, v, x, v)
+    np.testing.assert_allclose(at_nodes, f, rtol=0, atol=1e-14)
+    bil = 2.0 + 0.5 * x[:, None] - 0.25 * v[None, :] + 0.125 * x[:, None] * v[None, :]
+    xq, vq = np.linspace(0.3, 20.0, 41), np.linspace(-6.0, 6.0, 29)
+    want = 2.0 + 0.5 * xq[:, None] - 0.25 * vq[None, :] + 0.125 * xq[:, None] * vq[None, :]
+    np.testing.assert_allclose(O.dist_save_xv(bil, x, v, xq, vq), want, rtol=1e-13, atol=1e-13)
+    out = O.dist_save_xv(f, x, v, np.array([0.0, 1.0, 25.0]), np.array([-7.0, 0.0, 6.0]))
+    assert np.isnan(out[0]).all() and np.isnan(out[2]).all() and np.isnan(out[1, 0])
+    assert np.isfinite(out[1, 1]) and np.isfinite(out[1, 2])
