@@ -53,6 +53,23 @@ __device__ __forceinline__ double cc_delta(double w) {  // driftdiffusion.py:96-
   return fast_rcp(w) - fast_rcp(expm1(w));
 }
 
+// Chang-Cooper delta on the fast path: for |w| < 1/4 (w = C dv / D = dv (v_edge - vbar) / T, a few 1e-2 on production
+// grids) the Bernoulli series of 1/w - 1/(e^w - 1) through w^11 (next term < 2e-19) replaces expm1 and two reciprocals
+// -- and is free of the cancellation the closed form has at small w.
+__device__ __forceinline__ double cc_delta_fast(double w) {
+  if (fabs(w) < 0.25) {
+    const double w2 = w * w;
+    double p = 691.0 / 1307674368000.0;
+    p = fma(p, w2, -1.0 / 47900160.0);
+    p = fma(p, w2, 1.0 / 1209600.0);
+    p = fma(p, w2, -1.0 / 30240.0);
+    p = fma(p, w2, 1.0 / 720.0);
+    p = fma(p, w2, -1.0 / 12.0);
+    return fma(p, w, 0.5);
+  }
+  return fast_rcp(w) - fast_rcp(expm1(w));
+}
+
 // bare upper / lower entries of one edge (generic path); D_dv = max(D, 1e-30) / dv, inv_dv = 1 / dv,
 // dv_D = dv / max(D, 1e-30)
 __device__ __forceinline__ void bare_edge(double C, double D_dv, double inv_dv, double dv_D, int scheme, double& bu,
@@ -79,8 +96,10 @@ struct CollideSmem {
   }
 };
 
-// FAST: central differencing, LB / Dougherty, no `nodrag` -- the production path.
-template <int E, int MAXT, int MINB, bool FAST>
+// FAST: LB / Dougherty on the uniform grid (central differencing or Chang-Cooper), no `nodrag` -- the production path.
+// CC (fast path only): Chang-Cooper instead of central differencing, a separate instantiation so that the central
+// kernel carries no branch or extra registers.
+template <int E, int MAXT, int MINB, bool FAST, bool CC = false>
 __global__ void __launch_bounds__(MAXT, MINB) collide_kernel(CollideArgs p) {
   extern __shared__ __align__(16) double sm[];
   const int nv = p.nv;
@@ -186,6 +205,8 @@ __global__ void __launch_bounds__(MAXT, MINB) collide_kernel(CollideArgs p) {
     const double pD = dtnu * D / (dv * dv);
     const double q = dtnu * (2.0 * beta * D) / (2.0 * dv);
     const double w0 = q * (vc + 0.5 * dv - vbar), dq = q * dv;
+    // Chang-Cooper cell Peclet number w = C dv / D = 2 beta dv (v_edge - vbar), linear in the edge index
+    const double ww0 = (2.0 * beta * dv) * (vc + 0.5 * dv - vbar), dww = (2.0 * beta * dv) * dv;
     // per-row quotients of the generic path (one IEEE division each per row instead of several per cell edge)
     const double sD = fmax(D, 1.0e-30), inv_dv = 1.0 / dv;
     const double D_dv = ((p.scheme == FP_CENTRAL) ? D : sD) / dv, dv_D = dv / sD;
@@ -197,9 +218,16 @@ __global__ void __launch_bounds__(MAXT, MINB) collide_kernel(CollideArgs p) {
         return;
       }
       if (FAST) {
-        const double wq = fma((double)l, dq, w0);
-        U = pD + wq;
-        L = pD - wq;
+        const double wq = fma((double)l, dq, w0);  // dt nu C / (2 dv)
+        if (!CC) {
+          U = pD + wq;
+          L = pD - wq;
+        } else {  // Chang-Cooper: U = dt nu (C (1 - delta) + D/dv) / dv, L = dt nu (-C delta + D/dv) / dv
+          const double dl = cc_delta_fast(fma((double)l, dww, ww0));
+          const double cq = 2.0 * wq;
+          U = fma(cq, 1.0 - dl, pD);
+          L = fma(-cq, dl, pD);
+        }
       } else {
         double C;
         const double va = __ldg(p.v + e), vb = __ldg(p.v + e + 1);
@@ -708,7 +736,7 @@ int collide_bwd_f64(const double* fin, const double* fnew, const double* g, doub
   return ADEPT_ERR_UNSUPPORTED;
 }
 
-template <int E, int MAXT, int MINB, bool FAST>
+template <int E, int MAXT, int MINB, bool FAST, bool CC = false>
 static int launch_collide_t(CollideArgs p, cudaStream_t stream) {
   const int T = p.nv / E;
   int R = MAXT / T;
@@ -725,7 +753,7 @@ static int launch_collide_t(CollideArgs p, cudaStream_t stream) {
   static size_t configured[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
-  auto kern = collide_kernel<E, MAXT, MINB, FAST>;
+  auto kern = collide_kernel<E, MAXT, MINB, FAST, CC>;
   if (dev < 64 && configured[dev] < smem) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) {
@@ -742,6 +770,7 @@ static int launch_collide_t(CollideArgs p, cudaStream_t stream) {
 
 template <int E, int MAXT, int MINB>
 static int launch_collide(const CollideArgs& p, bool fast, cudaStream_t stream) {
+  if (fast && p.scheme == FP_CHANG_COOPER) return launch_collide_t<E, MAXT, MINB, true, true>(p, stream);
   return fast ? launch_collide_t<E, MAXT, MINB, true>(p, stream) : launch_collide_t<E, MAXT, MINB, false>(p, stream);
 }
 
@@ -763,7 +792,7 @@ int collide_f64(const double* fin, double* fout, int batch, int nx, int nv, cons
   }
   CollideArgs p = {fin, fout, (long long)batch * nx, nv, v, dv, dt, nu_fp, nu_K, f_mx,
                    model, scheme, nodrag, sg_m, sg_ratio, n_out, 1, nu_fp_scale, nu_K_scale};
-  const bool fast = scheme == FP_CENTRAL && model != FP_SUPERGAUSSIAN && !nodrag;
+  const bool fast = model != FP_SUPERGAUSSIAN && !nodrag;  // uniform-grid arithmetic, central or Chang-Cooper
   if (nv % 16 == 0 && nv / 16 <= 256) return launch_collide<16, 256, 2>(p, fast, stream);
   if (nv % 16 == 0 && nv / 16 <= 512) return launch_collide<16, 512, 1>(p, fast, stream);
   if (nv % 16 == 0 && nv / 16 <= 1024) return launch_collide<16, 1024, 1>(p, fast, stream);
