@@ -62,9 +62,9 @@ SIGNATURES = {
     "adept_b200_moments_bwd_f64": [C.POINTER(c_dp), C.POINTER(c_d), c_i, c_i, c_i, c_dp, c_i, c_dp, c_dp],
     "adept_b200_collide_bwd_f64": [c_dp, c_dp, c_dp, c_dp, c_dp, c_i, c_i, c_i, c_dp, c_d, c_d, c_dp, c_i, c_i, c_dp],
     "adept_b200_vpush_collide_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_dp, c_dp, c_d, c_d, c_d, c_d, c_dp, c_d, c_dp,
-                                     c_i, c_dp],
+                                     c_i, c_i, c_dp],
     "adept_b200_vpush_collide_p2p_f64": [C.POINTER(c_dp), C.POINTER(c_dp), c_i, c_ll, c_i, c_i, c_dp, c_dp, c_dp, c_d,
-                                         c_d, c_d, c_d, c_dp, c_d, c_dp, c_i, c_dp],
+                                         c_d, c_d, c_d, c_dp, c_d, c_dp, c_i, c_i, c_dp],
     "adept_b200_save_moments_f64": [c_dp, c_dp, c_d, c_i, c_i, c_i, c_dp, c_d, c_dp, c_dp],
     "adept_b200_interp2d_f64": [c_dp, c_dp, c_d, c_i, c_i, c_dp, c_dp, c_dp, c_dp, c_i, c_i, c_dp, c_dp],
     "adept_b200_filter_x_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_dp, c_dp],

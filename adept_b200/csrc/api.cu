@@ -234,7 +234,8 @@ int adept_b200_collide_bwd_f64(const double* f_in, const double* f_new, const do
 int adept_b200_vpush_collide_p2p_f64(const double* const* in_peers_host, double* const* out_peers_host, int n_peers,
                                      long long row0_global, int nx, int nv, const double* e, const double* dex,
                                      const double* pond, double charge, double mass, double dt, double k1v,
-                                     const double* v, double dv, const double* nu_fp, int model, void* stream) {
+                                     const double* v, double dv, const double* nu_fp, int model, int scheme,
+                                     void* stream) {
   ADEPT_REQUIRE(in_peers_host, "in_peers") ADEPT_REQUIRE(out_peers_host, "out_peers") ADEPT_REQUIRE(e, "e")
   ADEPT_REQUIRE(v, "v") ADEPT_REQUIRE(nu_fp, "nu_fp")
   for (int j = 0; j < n_peers && j < 8; j++) {
@@ -242,7 +243,8 @@ int adept_b200_vpush_collide_p2p_f64(const double* const* in_peers_host, double*
   }
   // f_in / f_out are unused in peer mode; pass the local slots so that argument checks see non-null pointers
   return vpush_collide_f64(in_peers_host[0], out_peers_host[0], 1, nx, nv, e, dex, pond, charge, mass, dt, k1v, v, dv,
-                           nu_fp, 1.0, model, (cudaStream_t)stream, in_peers_host, out_peers_host, n_peers, row0_global);
+                           nu_fp, 1.0, model, scheme, (cudaStream_t)stream, in_peers_host, out_peers_host, n_peers,
+                           row0_global);
 }
 
 int adept_b200_interp2d_f64(const double* f0, const double* f1, double w, int nx, int nv, const double* x,
@@ -257,11 +259,12 @@ long long adept_b200_launch_count(void) { return adept::g_launches.load(std::mem
 
 int adept_b200_vpush_collide_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* e,
                                  const double* dex, const double* pond, double charge, double mass, double dt,
-                                 double k1v, const double* v, double dv, const double* nu_fp, int model, void* stream) {
+                                 double k1v, const double* v, double dv, const double* nu_fp, int model, int scheme,
+                                 void* stream) {
   ADEPT_REQUIRE(f_in, "f_in") ADEPT_REQUIRE(f_out, "f_out") ADEPT_REQUIRE(e, "e") ADEPT_REQUIRE(v, "v")
   ADEPT_REQUIRE(nu_fp, "nu_fp")
   return vpush_collide_f64(f_in, f_out, batch, nx, nv, e, dex, pond, charge, mass, dt, k1v, v, dv, nu_fp, 1.0, model,
-                           (cudaStream_t)stream);
+                           scheme, (cudaStream_t)stream);
 }
 
 int adept_b200_save_moments_f64(const double* f0, const double* f1, double w, int batch, int nx, int nv,

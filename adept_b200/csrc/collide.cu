@@ -53,23 +53,6 @@ __device__ __forceinline__ double cc_delta(double w) {  // driftdiffusion.py:96-
   return fast_rcp(w) - fast_rcp(expm1(w));
 }
 
-// Chang-Cooper delta on the fast path: for |w| < 1/4 (w = C dv / D = dv (v_edge - vbar) / T, a few 1e-2 on production
-// grids) the Bernoulli series of 1/w - 1/(e^w - 1) through w^11 (next term < 2e-19) replaces expm1 and two reciprocals
-// -- and is free of the cancellation the closed form has at small w.
-__device__ __forceinline__ double cc_delta_fast(double w) {
-  if (fabs(w) < 0.25) {
-    const double w2 = w * w;
-    double p = 691.0 / 1307674368000.0;
-    p = fma(p, w2, -1.0 / 47900160.0);
-    p = fma(p, w2, 1.0 / 1209600.0);
-    p = fma(p, w2, -1.0 / 30240.0);
-    p = fma(p, w2, 1.0 / 720.0);
-    p = fma(p, w2, -1.0 / 12.0);
-    return fma(p, w, 0.5);
-  }
-  return fast_rcp(w) - fast_rcp(expm1(w));
-}
-
 // bare upper / lower entries of one edge (generic path); D_dv = max(D, 1e-30) / dv, inv_dv = 1 / dv,
 // dv_D = dv / max(D, 1e-30)
 __device__ __forceinline__ void bare_edge(double C, double D_dv, double inv_dv, double dv_D, int scheme, double& bu,

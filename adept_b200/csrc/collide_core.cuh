@@ -25,6 +25,23 @@ __device__ __forceinline__ double fast_rcp(double x) {
   return r;
 }
 
+// Chang-Cooper delta on the fast path: for |w| < 1/4 (w = C dv / D = dv (v_edge - vbar) / T, a few 1e-2 on production
+// grids) the Bernoulli series of 1/w - 1/(e^w - 1) through w^11 (next term < 2e-19) replaces expm1 and two reciprocals
+// -- and is free of the cancellation the closed form has at small w.
+__device__ __forceinline__ double cc_delta_fast(double w) {
+  if (fabs(w) < 0.25) {
+    const double w2 = w * w;
+    double p = 691.0 / 1307674368000.0;
+    p = fma(p, w2, -1.0 / 47900160.0);
+    p = fma(p, w2, 1.0 / 1209600.0);
+    p = fma(p, w2, -1.0 / 30240.0);
+    p = fma(p, w2, 1.0 / 720.0);
+    p = fma(p, w2, -1.0 / 12.0);
+    return fma(p, w, 0.5);
+  }
+  return fast_rcp(w) - fast_rcp(expm1(w));
+}
+
 // Sum NVAL values over the T threads of row r; every thread of the CTA must call it.  warp_mode: T % 32 == 0 (warps do
 // not straddle rows).  `red` is a scratch area of 2 * S * NVAL doubles used with alternating halves, S = 32 in warp
 // mode and max(R*T, 32) otherwise.
@@ -71,7 +88,8 @@ __device__ __forceinline__ void row_reduce(double (&val)[NVAL], double* red, int
 // DENSE_OUT: the result is written as a dense row whose 128-byte chunks are XOR-swizzled in 16-byte units (unit j of
 // chunk c at j ^ (c & 7)): the layout a TMA tensor store with CU_TENSOR_MAP_SWIZZLE_128B reads, conflict-free for the
 // 16-byte stores of a warp; rowbuf must then be 1024-byte aligned.  Each thread fences its stores for the async proxy.
-template <int E, bool DENSE_OUT = false>
+// CC: Chang-Cooper weighting of the drag term instead of central differencing.
+template <int E, bool DENSE_OUT = false, bool CC = false>
 __device__ __forceinline__ void fp_row_fast(double* rowbuf, double* red, double* pcr, int& parity, int tt,
                                             int T, int nv, double vc, double dv, double dt, double nu, int model) {
   const bool warp_mode = (T & 31) == 0;
@@ -100,6 +118,7 @@ __device__ __forceinline__ void fp_row_fast(double* rowbuf, double* red, double*
   const double pD = dtnu * D / (dv * dv);
   const double q = dtnu * (2.0 * beta * D) / (2.0 * dv);
   const double w0 = q * (vc + 0.5 * dv - vbar), dq = q * dv;
+  const double ww0 = (2.0 * beta * dv) * (vc + 0.5 * dv - vbar), dww = (2.0 * beta * dv) * dv;  // Chang-Cooper w
   auto edge = [&](int l, double& U, double& L) {
     const int e = i0 + l;
     if (e < 0 || e > nv - 2) {
@@ -107,9 +126,16 @@ __device__ __forceinline__ void fp_row_fast(double* rowbuf, double* red, double*
       L = 0.0;
       return;
     }
-    const double wq = fma((double)l, dq, w0);
-    U = pD + wq;
-    L = pD - wq;
+    const double wq = fma((double)l, dq, w0);  // dt nu C / (2 dv)
+    if (!CC) {
+      U = pD + wq;
+      L = pD - wq;
+    } else {  // U = dt nu (C (1 - delta) + D/dv) / dv, L = dt nu (-C delta + D/dv) / dv, delta(w = C dv / D)
+      const double dl = cc_delta_fast(fma((double)l, dww, ww0));
+      const double cq = 2.0 * wq;
+      U = fma(cq, 1.0 - dl, pD);
+      L = fma(-cq, dl, pD);
+    }
   };
   double cpn[E], ypn[E], apn[E];  // Thomas ratios, y-form right-hand sides and the left spike, all in registers
   double rpn_last, apn_last;

@@ -46,7 +46,7 @@ int collide_bwd_f64(const double* fin, const double* fnew, const double* g, doub
 bool vpush_collide_supported(int nx, int nv, int model, int scheme, int nodrag);
 int vpush_collide_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* e, const double* dex,
                       const double* pond, double q, double m, double dt, double k1v, const double* v, double dv,
-                      const double* nu_fp, double nu_fp_scale, int model, cudaStream_t stream,
+                      const double* nu_fp, double nu_fp_scale, int model, int scheme, cudaStream_t stream,
                       const double* const* in_peers = nullptr, double* const* out_peers = nullptr, int n_peers = 0,
                       long long row0_global = 0);
 bool tma_available();

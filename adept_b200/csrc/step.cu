@@ -263,7 +263,7 @@ int step_f64(const adept_b200_step& s, cudaStream_t st) {
         if (k == kc) {
           ADEPT_TRY(vpush_collide_f64(fstar[k], out[k], s.batch, s.nx, sp.nv, s.e_out, s.dex, s.pond, sp.charge,
                                       sp.mass, s.dt, sp.k1v, sp.v, sp.dv, s.nu_fp_space, s.nu_fp_time, s.fp_model,
-                                      st));
+                                      s.fp_scheme, st));
         } else {
           ADEPT_TRY(edfdv_exp_f64(fstar[k], out[k], s.batch, s.nx, sp.nv, s.e_out, s.dex, s.pond, sp.charge, sp.mass,
                                   s.dt, sp.k1v, st));

@@ -32,7 +32,7 @@ struct VrowArgs {
   double dv;
   const double* nu_fp;  // [batch*nx]
   double nu_fp_scale;
-  int model;
+  int model, scheme;
   // peer mode (single grid sharded over GPUs, every buffer v-sharded [nx_global, nv / P] and mapped over NVLink): cell i
   // of local row r is READ from in_peer[i >> nvp_shift] and WRITTEN to out_peer[i >> nvp_shift], both at row
   // row0_global + r, column i & mask -- the two layout transposes of the decomposition ride on the kernel's own loads
@@ -62,7 +62,7 @@ struct VrowCfg {
 
 // TMA_OUT: the solved rows leave shared memory through TMA tensor stores (no LDS + STG pass for the output); the
 // tensor map views f_out as [rows * nv/16][16] with boxes {16, min(256, nv/16)}, 128-byte swizzle.
-template <int LOGN, bool TMA_OUT>
+template <int LOGN, bool TMA_OUT, bool CC>
 __global__ void __launch_bounds__(VrowCfg<LOGN>::THREADS, (VrowCfg<LOGN>::THREADS <= 256 ? 2 : 1))
     vpush_collide_kernel(const __grid_constant__ CUtensorMap out_map, VrowArgs p) {
   using K = VrowCfg<LOGN>;
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(VrowCfg<LOGN>::THREADS, (VrowCfg<LOGN>::THREAD
 #pragma unroll 1
   for (int s = 0; s < 2; s++) {
     double* row = rowA + s * ROW_STRIDE;
-    fp_row_fast<16, TMA_OUT>(row, red, pcr, parity, t, T, N, vc, p.dv, p.dt,
+    fp_row_fast<16, TMA_OUT, CC>(row, red, pcr, parity, t, T, N, vc, p.dv, p.dt,
                              __dmul_rn(p.nu_fp_scale, p.nu_fp[row0 + s]), p.model);
     if (TMA_OUT && threadIdx.x == 0) {  // the barrier that ends fp_row_fast ordered every thread's fenced stores
       constexpr int BOX = K::OUT_BOX_ROWS;
@@ -167,13 +167,13 @@ __global__ void __launch_bounds__(VrowCfg<LOGN>::THREADS, (VrowCfg<LOGN>::THREAD
   }
 }
 
-template <int LOGN, bool TMA_OUT>
+template <int LOGN, bool TMA_OUT, bool CC>
 static int launch_vrow(const VrowArgs& p, cudaStream_t stream) {
   using K = VrowCfg<LOGN>;
   static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
-  auto kern = vpush_collide_kernel<LOGN, TMA_OUT>;
+  auto kern = vpush_collide_kernel<LOGN, TMA_OUT, CC>;
   if (dev < 64 && !configured[dev]) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
     if (err != cudaSuccess) {
@@ -200,24 +200,26 @@ static int launch_vrow_auto(const VrowArgs& p, cudaStream_t stream) {
   using K = VrowCfg<LOGN>;
   const bool tma_ok = p.nvp_shift < 0 && LOGN >= 11 && tma_available() && (reinterpret_cast<uintptr_t>(p.fout) & 15) == 0 &&
                       (unsigned long long)p.npairs * 2 * (K::N / 16) < (1ull << 31);
+  const bool cc = p.scheme == FP_CHANG_COOPER;
   if constexpr (LOGN >= 11) {
-    if (tma_ok) return launch_vrow<LOGN, true>(p, stream);
+    if (tma_ok) return cc ? launch_vrow<LOGN, true, true>(p, stream) : launch_vrow<LOGN, true, false>(p, stream);
   }
-  return launch_vrow<LOGN, false>(p, stream);
+  return cc ? launch_vrow<LOGN, false, true>(p, stream) : launch_vrow<LOGN, false, false>(p, stream);
 }
 
 bool vpush_collide_supported(int nx, int nv, int model, int scheme, int nodrag) {
   if (nx < 2 || (nx & 1)) return false;
   if (nv < 512 || nv > 8192 || (nv & (nv - 1))) return false;  // T = nv/16 >= 32 threads, power-of-two FFT
-  return scheme == FP_CENTRAL && (model == FP_LB || model == FP_DOUGHERTY) && !nodrag;
+  return (scheme == FP_CENTRAL || scheme == FP_CHANG_COOPER) && (model == FP_LB || model == FP_DOUGHERTY) && !nodrag;
 }
 
 int vpush_collide_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* e, const double* dex,
                       const double* pond, double q, double m, double dt, double k1v, const double* v, double dv,
-                      const double* nu_fp, double nu_fp_scale, int model, cudaStream_t stream,
+                      const double* nu_fp, double nu_fp_scale, int model, int scheme, cudaStream_t stream,
                       const double* const* in_peers, double* const* out_peers, int n_peers, long long row0_global) {
-  if (batch < 1 || !vpush_collide_supported(nx, nv, model, FP_CENTRAL, 0)) {
-    set_last_error("vpush_collide: unsupported shape batch=%d nx=%d nv=%d / model=%d", batch, nx, nv, model);
+  if (batch < 1 || !vpush_collide_supported(nx, nv, model, scheme, 0)) {
+    set_last_error("vpush_collide: unsupported shape batch=%d nx=%d nv=%d / model=%d scheme=%d", batch, nx, nv, model,
+                   scheme);
     return ADEPT_ERR_UNSUPPORTED;
   }
   int logn = 0;
@@ -226,7 +228,7 @@ int vpush_collide_f64(const double* fin, double* fout, int batch, int nx, int nv
   p.fin = fin, p.fout = fout, p.npairs = (long long)batch * nx / 2, p.nx = nx;
   p.e = e, p.dex = dex, p.pond = pond, p.q = q, p.m = m, p.dt = dt, p.k1 = k1v;
   p.tw = get_twiddles(logn), p.zero = 0;
-  p.v = v, p.dv = dv, p.nu_fp = nu_fp, p.nu_fp_scale = nu_fp_scale, p.model = model;
+  p.v = v, p.dv = dv, p.nu_fp = nu_fp, p.nu_fp_scale = nu_fp_scale, p.model = model, p.scheme = scheme;
   if (!p.tw) return ADEPT_ERR_CUDA;
   p.nvp_shift = -1;
   if (in_peers || out_peers) {

@@ -131,12 +131,12 @@ ffi::Error CollideBwdImpl(cudaStream_t stream, F64 f_in, F64 f_new, F64 g, F64 v
 
 // VelocityExponential.push followed by Collisions on the same rows, one pass over f (vector_field.py:236-238)
 ffi::Error VpushCollideImpl(cudaStream_t stream, F64 f, F64 e, F64 dex, F64 pond, F64 v, F64 nu_fp, double charge,
-                            double mass, double dt, double k1v, double dv, int64_t model, F64Out out) {
+                            double mass, double dt, double k1v, double dv, int64_t model, int64_t scheme, F64Out out) {
   const Shape3 s = shape3(f);
   if (!s.ok) return bad_rank();
   return check(adept_b200_vpush_collide_f64(f.typed_data(), out->typed_data(), s.batch, s.nx, s.nv, e.typed_data(),
                                             dex.typed_data(), pond.typed_data(), charge, mass, dt, k1v, v.typed_data(),
-                                            dv, nu_fp.typed_data(), (int)model, stream));
+                                            dv, nu_fp.typed_data(), (int)model, (int)scheme, stream));
 }
 
 // in-loop save moments (storage.py:286-327, 119-162): out [6, batch*nx].  diffrax hands the save functions the state
@@ -181,6 +181,6 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(adept_b200_xla_collide_bwd, CollideBwdImpl,
 XLA_FFI_DEFINE_HANDLER_SYMBOL(adept_b200_xla_vpush_collide, VpushCollideImpl,
                               ADEPT_STREAM.Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>()
                                   .Attr<double>("charge").Attr<double>("mass").Attr<double>("dt").Attr<double>("k1v")
-                                  .Attr<double>("dv").Attr<int64_t>("model").Ret<F64>());
+                                  .Attr<double>("dv").Attr<int64_t>("model").Attr<int64_t>("scheme").Ret<F64>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(adept_b200_xla_save_moments, SaveMomentsImpl,
                               ADEPT_STREAM.Arg<F64>().Arg<F64>().Attr<double>("dv").Ret<F64>());

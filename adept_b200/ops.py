@@ -67,13 +67,14 @@ def vdfdx(f, v, dt, k1x, out=None, k1x_batch=None):
     return out
 
 
-def vpush_collide(f, e, pond, q, m, dt, k1v, v, dv, nu_fp, model=1, dex=None, out=None):
+def vpush_collide(f, e, pond, q, m, dt, k1v, v, dv, nu_fp, model=1, dex=None, out=None, scheme=0):
     """Fused spectral v-advection + Fokker-Planck step (vector_field.py:236-238), one read and one write of f."""
     b, nx, nv = _shape3(f)
     out = torch.empty_like(f) if out is None else out
     rc = _lib.load().adept_b200_vpush_collide_f64(
         _ptr(f, "f"), _ptr(out, "out"), b, nx, nv, _ptr(e, "e"), _ptr(dex, "dex", True), _ptr(pond, "pond", True),
-        float(q), float(m), float(dt), float(k1v), _ptr(v, "v"), float(dv), _ptr(nu_fp, "nu_fp"), int(model), _stream())
+        float(q), float(m), float(dt), float(k1v), _ptr(v, "v"), float(dv), _ptr(nu_fp, "nu_fp"), int(model),
+        int(scheme), _stream())
     _lib.check(rc, "vpush_collide")
     _count()
     return out
@@ -86,14 +87,14 @@ def _peer_array(ptrs):
 
 
 def vpush_collide_p2p(in_ptrs, out_ptrs, row0_global, nx_local, nv, e, pond, q, m, dt, k1v, v, dv, nu_fp, model=1,
-                      dex=None):
+                      dex=None, scheme=0):
     """Fused v-advection + Fokker-Planck step of this rank's ``nx_local`` rows of a grid whose buffers are all
     v-sharded ``[nx, nv / P]``: cells are read from and written to the owning ranks' buffers over peer memory
     (``in_ptrs`` / ``out_ptrs``: one device pointer per rank)."""
     rc = _lib.load().adept_b200_vpush_collide_p2p_f64(
         _peer_array(in_ptrs), _peer_array(out_ptrs), len(out_ptrs), int(row0_global), int(nx_local), int(nv),
         _ptr(e, "e"), _ptr(dex, "dex", True), _ptr(pond, "pond", True), float(q), float(m), float(dt), float(k1v),
-        _ptr(v, "v"), float(dv), _ptr(nu_fp, "nu_fp"), int(model), _stream())
+        _ptr(v, "v"), float(dv), _ptr(nu_fp, "nu_fp"), int(model), int(scheme), _stream())
     _lib.check(rc, "vpush_collide_p2p")
     _count()
 

@@ -157,8 +157,8 @@ class ShardedVlasov1D:
             return "number of ranks is not a power of two <= 8"
         if t["edfdv"] != "exponential" or not self.fp_on or self.krook_on:
             return "needs the spectral v-push with Fokker-Planck collisions and no Krook operator"
-        if self.coll.scheme != 0 or self.coll.model not in (0, 1) or self.coll.nodrag:
-            return "needs central-differencing Lenard-Bernstein / Dougherty collisions"
+        if self.coll.model not in (0, 1) or self.coll.nodrag:
+            return "needs Lenard-Bernstein / Dougherty collisions (central or Chang-Cooper)"
         if nx & (nx - 1) or not 256 <= nx <= 4096 or (nv // P) % 4:
             return "x-advection shape is not handled by the TMA kernel"
         if nv & (nv - 1) or not 512 <= nv <= 8192 or (nx // P) % 2:
@@ -212,7 +212,7 @@ class ShardedVlasov1D:
         nu_fp = float(self.nu_fp_prof.time_envelope(t)) * pp["nu_fp_space"]
         ops.vpush_collide_p2p(pp["st_ptrs"], pp["vs_ptrs"], self.rank * self.nxp, self.nxp, pp["nv"], e_loc, None,
                               float(sp["charge"]), float(sp["mass"]), dt, float(sg["kvr"][1]), self.v_full[n],
-                              float(sg["dv"]), nu_fp, model=self.coll.model, dex=dex_loc)
+                              float(sg["dv"]), nu_fp, model=self.coll.model, dex=dex_loc, scheme=self.coll.scheme)
         dist.all_reduce(pp["token"], group=self.group)  # every rank's stores into my columns have completed
         self.state["e"], self.state["de"] = e, dex
         self.step_index += 1

@@ -78,11 +78,13 @@ int adept_b200_reduce_parts_f64(const double* parts, int nparts, long long n, do
 
 /* Fused v-advection + Fokker-Planck step on the same rows (VelocityExponential.push followed by Collisions,
  * vector_field.py:236-238): f_out = collide(edfdv_exp(f_in)), one read and one write of f for both operators.
- * Central differencing, model = Lenard-Bernstein or Dougherty, no Krook; nv a power of two in [512, 8192], nx even.
+ * model = Lenard-Bernstein (0) or Dougherty (1), scheme = central differencing (0) or Chang-Cooper (1), no Krook; nv a
+ * power of two in [512, 8192], nx even.
  * Returns ADEPT_B200_ERR_UNSUPPORTED otherwise (callers then use the two separate entry points).  In-place allowed. */
 int adept_b200_vpush_collide_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* e,
                                  const double* dex, const double* pond, double charge, double mass, double dt,
-                                 double k1v, const double* v, double dv, const double* nu_fp, int model, void* stream);
+                                 double k1v, const double* v, double dv, const double* nu_fp, int model, int scheme,
+                                 void* stream);
 
 /* ---- single grid sharded over the GPUs of one node: transposes fused into the v-row kernel ----------------
  * The reference's `grid.parallel: ["x", "v"]` decomposition alternates between a v-sharded layout f[nx, nv/P]
@@ -99,7 +101,8 @@ int adept_b200_vpush_collide_f64(const double* f_in, double* f_out, int batch, i
 int adept_b200_vpush_collide_p2p_f64(const double* const* in_peers_host, double* const* out_peers_host, int n_peers,
                                      long long row0_global, int nx, int nv, const double* e, const double* dex,
                                      const double* pond, double charge, double mass, double dt, double k1v,
-                                     const double* v, double dv, const double* nu_fp, int model, void* stream);
+                                     const double* v, double dv, const double* nu_fp, int model, int scheme,
+                                     void* stream);
 
 /* In-loop save moments in one pass over f (get_default_save_func / get_field_save_func, adept/_vlasov1d/storage.py:
  * 286-327, 119-162): out[k, row] = dv sum_j g_k(f_j, v_j), g = { f, f v, f v^2, f v^3, -|f| log|f|, f^2 }, out is

@@ -332,7 +332,7 @@ def test_collide_strongly_collisional(ops):
     assert rel_l2(out, ref) <= 1e-11  # ill-conditioned limit (nu dt D/dv^2 ~ 1.6e5): allow 10x
 
 
-@pytest.mark.parametrize("fp_type", ["lenard_bernstein", "dougherty"])
+@pytest.mark.parametrize("fp_type", ["lenard_bernstein", "dougherty", "chang_cooper", "chang_cooper_dougherty"])
 @pytest.mark.parametrize("nx,nv", [(4, 512), (6, 1024), (6, 2048), (2, 4096), (2, 8192)])
 def test_fused_vpush_collide_matches_oracle(ops, fp_type, nx, nv):
     """VelocityExponential followed by Collisions (vector_field.py:236-238) in one kernel."""
@@ -347,7 +347,7 @@ def test_fused_vpush_collide_matches_oracle(ops, fp_type, nx, nv):
     for nu in (np.linspace(0.2, 1.0, nx), 1e-5 * np.ones(nx), np.geomspace(1e-4, 3e-2, nx)):
         ref = coll(nu, None, O.velocity_exponential(f, kvr, e + dex, pond, dt, q, m), dt)
         out = host(ops.vpush_collide(dev(f), dev(e), dev(pond), q, m, dt, kvr[1], dev(v), dv, dev(nu),
-                                     model=MODEL[coll.model], dex=dev(dex)))
+                                     model=MODEL[coll.model], dex=dev(dex), scheme=SCHEME[coll.scheme]))
         amp = dt * nu.max() / dv**2
         assert rel_l2(out, ref) <= max(RTOL, 2e-16 * amp)
 

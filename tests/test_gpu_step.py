@@ -75,6 +75,10 @@ def variants():
     d["grid"].update(nx=1024, nv=512)
     d["terms"]["fokker_planck"]["time"]["baseline"] = 0.5
     out["L-1024x512-strong-fp"] = d
+    d = c2_deck()  # Chang-Cooper weighting in the fused v-push + collision kernel
+    d["grid"].update(nx=1024, nv=1024)
+    d["terms"]["fokker_planck"]["type"] = "chang_cooper_dougherty"
+    out["L-1024x1024-cc"] = d
     d = c2_deck()  # sixth-order integrator: the fused field launch serves substeps 2..6 (density from the x-pushes)
     d["grid"].update(nx=2048, nv=512)
     d["terms"].update(time="sixth")
