@@ -1,0 +1,53 @@
+"""The reference's Landau-damping test (tests/test_vlasov1d/test_landau_damping.py:35-88) on the B200 path: a driven
+electron plasma wave rings down at the rate of the analytic root of the dispersion relation (2 decimals, the reference's
+own bar), and the measured rate agrees with the oracle's to 1e-9 (north_star's diagnostics bar)."""
+
+from copy import deepcopy
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+from oracle import vlasov1d as O
+from test_oracle_operators import _dispersion_root
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+
+
+def _gamma(efs, ts, nx):
+    ek1 = np.abs(2.0 / nx * np.fft.fft(efs, axis=1)[:, 1])
+    sl = slice(-100, -50)
+    return float(np.mean(np.gradient(ek1[sl], ts[1] - ts[0]) / ek1[sl]))
+
+
+@pytest.mark.parametrize("time,edfdv", [("leapfrog", "exponential"), ("sixth", "cubic-spline")])
+def test_landau_damping_rate_on_gpu(time, edfdv):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from adept_b200.module import Vlasov1D
+
+    with open(GOLD / "resonance.yaml") as fh:
+        deck = yaml.safe_load(fh)
+    k0 = 0.32
+    root = _dispersion_root(k0)
+    deck["terms"].update(time=time, field="poisson", edfdv=edfdv)
+    deck["drivers"]["ex"]["0"]["params"]["k0"] = k0
+    deck["drivers"]["ex"]["0"]["params"]["w0"] = float(np.real(root))
+    deck["grid"]["xmax"] = float(2 * np.pi / k0)
+    deck["grid"]["tmax"] = 300.0
+    cfg = O.build_cfg(deepcopy(deck))
+    ts = O.save_axis({"nt": 601}, cfg["grid"])
+    _, ref = O.run(cfg, save={"e": (ts, lambda c, y: y["e"].copy())})
+    sim = Vlasov1D(deepcopy(deck))
+    _, got = sim.run(save={"e": (ts, lambda c, y0, y1=None, w=0.0: (y0["e"] if y1 is None
+                                                                    else y0["e"] + w * (y1["e"] - y0["e"])).clone())})
+    e_ref = np.array(ref["e"])
+    e_gpu = np.array([t.cpu().numpy() for t in got["e"]])
+    assert e_gpu.shape == e_ref.shape
+    g_ref, g_gpu = _gamma(e_ref, ts, cfg["grid"]["nx"]), _gamma(e_gpu, ts, cfg["grid"]["nx"])
+    np.testing.assert_almost_equal(g_gpu, np.imag(root), decimal=2)  # the reference's own assertion
+    assert abs(g_gpu - g_ref) <= 1e-9 * abs(g_ref), (g_gpu, g_ref)
+    assert np.max(np.abs(e_gpu - e_ref)) <= 1e-9 * np.max(np.abs(e_ref))  # field history, whole run

@@ -75,6 +75,12 @@ def variants():
     d["grid"].update(nx=1024, nv=512)
     d["terms"]["fokker_planck"]["time"]["baseline"] = 0.5
     out["L-1024x512-strong-fp"] = d
+    d = c2_deck()  # configs/vlasov-1d/wavepacket.yaml in miniature: nv = 3 x 2^k, cubic-spline v-push, FP + Krook
+    d["grid"].update(nx=256, nv=384)
+    d["terms"].update(edfdv="cubic-spline")
+    d["terms"]["krook"]["is_on"] = True
+    d["terms"]["krook"]["time"]["baseline"] = 1e-3
+    out["wavepacket-like-256x384"] = d
     d = c2_deck()  # Chang-Cooper weighting in the fused v-push + collision kernel
     d["grid"].update(nx=1024, nv=1024)
     d["terms"]["fokker_planck"]["type"] = "chang_cooper_dougherty"
