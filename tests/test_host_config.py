@@ -1,0 +1,75 @@
+"""Host logic without a GPU: the deck completion of the product (adept_b200.config.build_cfg, mirroring
+adept/_vlasov1d/modules.py:190-317 and helpers.py:37-161) against the oracle's and against the reference's golden
+arrays, and the save-time axes."""
+
+from copy import deepcopy
+from pathlib import Path
+
+import numpy as np
+import pytest
+import yaml
+
+from adept_b200.config import build_cfg
+from oracle import vlasov1d as O
+
+GOLD = Path(__file__).parent / "golden"
+DECKS = ["epw", "resonance", "fokker_planck_conservation", "multispecies_ion_acoustic"]
+
+
+def load(name):
+    with open(GOLD / f"{name}.yaml") as fh:
+        return yaml.safe_load(fh)
+
+
+@pytest.mark.parametrize("name", DECKS)
+def test_host_cfg_equals_oracle_cfg(name):
+    deck = load(name)
+    cfg, grid = build_cfg(deepcopy(deck))
+    ref = O.build_cfg(deepcopy(deck))
+    g, r = cfg["grid"], ref["grid"]
+    for key in ("nx", "nt", "max_steps"):
+        assert int(g[key]) == int(r[key]), key
+    for key in ("dt", "dx", "tmax", "beta"):
+        assert float(g[key]) == float(r[key]), key
+    for key in ("x", "x_a", "kx", "kxr", "one_over_kx", "one_over_kxr", "t", "ion_charge", "n_prof_total"):
+        np.testing.assert_array_equal(np.asarray(g[key]), np.asarray(r[key]), err_msg=key)
+    assert list(g["species_grids"]) == list(r["species_grids"])
+    for s in g["species_grids"]:
+        for key in ("v", "kv", "kvr", "one_over_kv", "one_over_kvr"):
+            np.testing.assert_array_equal(np.asarray(g["species_grids"][s][key]), np.asarray(r["species_grids"][s][key]))
+        assert float(g["species_grids"][s]["dv"]) == float(r["species_grids"][s]["dv"])
+        assert g["species_params"][s] == r["species_params"][s]
+        np.testing.assert_array_equal(g["species_distributions"][s][1], r["species_distributions"][s][1])
+
+
+@pytest.mark.parametrize("name", ["resonance", "fokker_planck_conservation", "multispecies_ion_acoustic"])
+def test_host_cfg_matches_reference_golden_arrays(name):
+    """The reference's regression fixtures (tests/test_vlasov1d/test_config_regression/*_array_config.yml, committed as
+    tests/golden/*.npz) pin grids and the full initial distribution to 14 significant figures."""
+    gold = np.load(GOLD / f"{name}.npz")
+    cfg, _ = build_cfg(load(name))
+    g = cfg["grid"]
+    checked = 0
+    for key in gold.files:
+        parts = key.split(".")
+        if parts[0] == "grid" and parts[1] in ("x", "x_a", "kx", "kxr", "one_over_kx", "one_over_kxr", "t", "ion_charge",
+                                               "n_prof_total"):
+            np.testing.assert_allclose(np.asarray(g[parts[1]]), gold[key], rtol=1e-13, atol=1e-300, err_msg=key)
+            checked += 1
+        elif parts[0] == "species_grids" and parts[2] in ("v", "kv", "kvr", "one_over_kv", "one_over_kvr"):
+            np.testing.assert_allclose(np.asarray(g["species_grids"][parts[1]][parts[2]]), gold[key], rtol=1e-13,
+                                       atol=1e-300, err_msg=key)
+            checked += 1
+        elif parts[0] == "species_distributions" and parts[2] == "f0":
+            np.testing.assert_allclose(g["species_distributions"][parts[1]][1], gold[key], rtol=1e-13, atol=1e-300)
+            checked += 1
+    assert checked >= 12, gold.files
+
+
+def test_save_axis_matches_oracle():
+    from adept_b200.module import save_axis
+
+    cfg, grid = build_cfg(load("epw"))
+    ref = O.build_cfg(load("epw"))
+    for tcfg in ({"nt": 11}, {"nt": 7, "tmin": 1.0, "tmax": 5.0}):
+        np.testing.assert_array_equal(save_axis(tcfg, grid), O.save_axis(tcfg, ref["grid"]))
