@@ -128,6 +128,85 @@ const cplx* get_twiddles(int logn) {
   return d;
 }
 
+// ---- Bluestein (chirp-z) tables for transform lengths that are not powers of two ------------------------------------
+// DFT_n(z)[k] = w[k] sum_j (z[j] w[j]) conj(w)[k - j], w[j] = exp(-i pi j^2 / n): a circular convolution of length
+// M = 2^logm >= 2n - 1.  chirp[j] = w[j], j < n; bhat = FFT_M(b) / M with b[j] = conj(w[|j|]) wrapped (the 1/M of the
+// inverse transform is folded in).  j^2 is reduced mod 2n in integers; everything is evaluated in long double.
+struct BluesteinTables {
+  int n, logm;
+  cplx* chirp;
+  cplx* bhat;
+};
+static std::mutex g_bs_mutex;
+static std::vector<BluesteinTables> g_bs[64];
+
+static void host_fft_ld(std::vector<long double>& re, std::vector<long double>& im) {  // radix-2, forward, in place
+  const size_t m = re.size();
+  for (size_t i = 1, j = 0; i < m; i++) {
+    size_t bit = m >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) std::swap(re[i], re[j]), std::swap(im[i], im[j]);
+  }
+  const long double pi = 3.141592653589793238462643383279502884L;
+  for (size_t len = 2; len <= m; len <<= 1) {
+    for (size_t k = 0; k < len / 2; k++) {
+      const long double ang = -2.0L * pi * (long double)k / (long double)len;
+      const long double wr = cosl(ang), wi = sinl(ang);
+      for (size_t i = k; i < m; i += len) {
+        const size_t j = i + len / 2;
+        const long double tr = re[j] * wr - im[j] * wi, ti = re[j] * wi + im[j] * wr;
+        re[j] = re[i] - tr, im[j] = im[i] - ti;
+        re[i] += tr, im[i] += ti;
+      }
+    }
+  }
+}
+
+int get_bluestein(int n, int* logm_out, const cplx** chirp_out, const cplx** bhat_out) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || n < 2 || n > 4096) {
+    set_last_error("bluestein: no CUDA device or unsupported length n=%d (2..4096)", n);
+    (void)cudaGetLastError();
+    return ADEPT_ERR_UNSUPPORTED;
+  }
+  std::lock_guard<std::mutex> lock(g_bs_mutex);
+  for (const auto& t : g_bs[dev])
+    if (t.n == n) {
+      *logm_out = t.logm, *chirp_out = t.chirp, *bhat_out = t.bhat;
+      return ADEPT_OK;
+    }
+  int logm = 1;
+  while ((1 << logm) < 2 * n - 1) logm++;
+  const size_t m = (size_t)1 << logm;
+  const long double pi = 3.141592653589793238462643383279502884L;
+  std::vector<long double> wr(n), wi(n), br(m, 0.0L), bi(m, 0.0L);
+  for (int j = 0; j < n; j++) {
+    const long long q = ((long long)j * j) % (2LL * n);
+    const long double ang = pi * (long double)q / (long double)n;
+    wr[j] = cosl(ang), wi[j] = -sinl(ang);
+    br[j] = wr[j], bi[j] = -wi[j];  // conj(w[j])
+    if (j) br[m - j] = br[j], bi[m - j] = bi[j];
+  }
+  host_fft_ld(br, bi);
+  std::vector<cplx> hc(n), hb(m);
+  for (int j = 0; j < n; j++) hc[j] = make_double2((double)wr[j], (double)wi[j]);
+  for (size_t k = 0; k < m; k++) hb[k] = make_double2((double)(br[k] / (long double)m), (double)(bi[k] / (long double)m));
+  BluesteinTables t = {n, logm, nullptr, nullptr};
+  cudaError_t err = cudaMalloc(&t.chirp, n * sizeof(cplx));
+  if (err == cudaSuccess) err = cudaMalloc(&t.bhat, m * sizeof(cplx));
+  if (err == cudaSuccess) err = cudaMemcpy(t.chirp, hc.data(), n * sizeof(cplx), cudaMemcpyHostToDevice);
+  if (err == cudaSuccess) err = cudaMemcpy(t.bhat, hb.data(), m * sizeof(cplx), cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) {
+    set_last_error("bluestein(n=%d): %s", n, cudaGetErrorString(err));
+    (void)cudaGetLastError();
+    return ADEPT_ERR_CUDA;
+  }
+  g_bs[dev].push_back(t);
+  *logm_out = logm, *chirp_out = t.chirp, *bhat_out = t.bhat;
+  return ADEPT_OK;
+}
+
 }  // namespace adept
 
 using namespace adept;

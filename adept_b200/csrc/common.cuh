@@ -53,5 +53,7 @@ struct ProfileScope {
 
 // twiddle-table cache (api.cu): per-pass Stockham tables for a complex FFT of length 2^logn on the current device
 const cplx* get_twiddles(int logn);
+// Bluestein tables for a transform of any length 2 <= n <= 4096 (api.cu): M = 2^logm >= 2n - 1
+int get_bluestein(int n, int* logm_out, const cplx** chirp_out, const cplx** bhat_out);
 
 }  // namespace adept

@@ -5,6 +5,7 @@
 //   ponderomotive      adept/_vlasov1d/solvers/pushers/field.py:495      -0.5 * gradient(a^2, dx)[1:-1]
 //   wave equation      adept/_vlasov1d/solvers/pushers/field.py:109-157  (WaveSolver + 2nd-order ABC)
 #include "fft_core.cuh"
+#include "internal.h"
 
 namespace adept {
 
@@ -170,6 +171,8 @@ static int launch_poisson_big(const PoissonArgs& p, int batch, cudaStream_t stre
 int poisson_dispatch_f64(const double* rho, const double* kmul, long long kmul_stride, double* e, int batch, int nx,
                          int mode, double Te, double lambda_De, cudaStream_t stream) {
   const int logn = ilog2_exact(nx);
+  if (logn < 0 && bluestein_supported(nx))
+    return bluestein_poisson_f64(rho, kmul, kmul_stride, e, batch, nx, mode, Te, lambda_De, stream);
   if (logn == 12 || logn == 13) {
     PoissonArgs p = {rho, kmul, kmul_stride, e, mode, Te, lambda_De, get_twiddles(logn), 0};
     if (!p.tw) return ADEPT_ERR_CUDA;

@@ -16,6 +16,12 @@ int moments_f64(const double* f, int batch, int nx, int nv, const double* v, dou
 int axpy_f64(const double* a, const double* b, double s, double* out, long long n, cudaStream_t stream);
 int poisson_dispatch_f64(const double* rho, const double* kmul, long long kmul_stride, double* e, int batch, int nx,
                          int mode, double Te, double lambda_De, cudaStream_t stream);
+bool bluestein_supported(int n);
+int bluestein_push_f64(int axis, const double* fin, double* fout, int batch, int nx, int nv, const double* v, double dt,
+                       const double* k1_batch, double k1, const double* e, const double* dex, const double* pond,
+                       double q, double m, const double* filt, cudaStream_t stream);
+int bluestein_poisson_f64(const double* rho, const double* kmul, long long kmul_stride, double* e, int batch, int nx,
+                          int mode, double Te, double lambda_De, cudaStream_t stream);
 bool field_fused_supported(int batch, int nx);
 int field_fused_f64(int nsp, const double* const* parts, const int* nparts, const double* dv, const double* charge,
                     const double* base, double* rho, int nx, const double* a, double* pond, double dx, int n_ex,

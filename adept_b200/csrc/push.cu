@@ -10,6 +10,7 @@
 // phase factors (Im of DC/Nyquist dropped exactly like irfft does), recombined, and transformed back with the
 // same forward kernel (swap trick).  Phase factors exp(-i m alpha) are built from two small per-sequence tables
 // (m = 64*hi + lo) so no sincos is evaluated per element.
+#include "internal.h"
 #include "push_core.cuh"
 
 namespace adept {
@@ -215,8 +216,11 @@ int vdfdx_f64(const double* fin, double* fout, int batch, int nx, int nv, const 
     return ADEPT_ERR_BAD_SHAPE;
   }
   const int logn = ilog2_exact(nx);
+  if (logn < 0 && bluestein_supported(nx))  // any even length <= 4096: chirp-z on the power-of-two core
+    return bluestein_push_f64(0, fin, fout, batch, nx, nv, v, dt, k1_batch, k1, nullptr, nullptr, nullptr, 0.0, 1.0,
+                              filt, stream);
   if (logn < 1 || logn > 13) {
-    set_last_error("vdfdx: nx=%d is not a power of two in [2, 8192]", nx);
+    set_last_error("vdfdx: nx=%d must be a power of two <= 8192 or an even number <= 4096", nx);
     return ADEPT_ERR_UNSUPPORTED;
   }
   if ((reinterpret_cast<uintptr_t>(fin) | reinterpret_cast<uintptr_t>(fout)) & 15) {
@@ -239,8 +243,10 @@ int edfdv_exp_f64(const double* fin, double* fout, int batch, int nx, int nv, co
     return ADEPT_ERR_BAD_SHAPE;
   }
   const int logn = ilog2_exact(nv);
+  if (logn < 0 && bluestein_supported(nv))
+    return bluestein_push_f64(1, fin, fout, batch, nx, nv, nullptr, dt, nullptr, k1, e, dex, pond, q, m, nullptr, stream);
   if (logn < 1 || logn > 13) {
-    set_last_error("edfdv_exp: nv=%d is not a power of two in [2, 8192]", nv);
+    set_last_error("edfdv_exp: nv=%d must be a power of two <= 8192 or an even number <= 4096", nv);
     return ADEPT_ERR_UNSUPPORTED;
   }
   PushArgs p = {};

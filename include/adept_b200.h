@@ -61,7 +61,7 @@ int adept_b200_prepare(int n);
 
 /* x-advection: f_out = irfft(exp(-i kx_m v_j dt) rfft(f_in, axis=x), axis=x).
  * v[nv] velocity grid; k1x = kx_real[1] = 2 pi / (nx dx); k1x_batch[batch] (nullable) overrides it per member.
- * nx power of two (<= 8192), nv even.  In-place (f_out == f_in) allowed. */
+ * nx a power of two (<= 8192) or any even number <= 4096 (chirp-z path, 4-8x the work), nv even.  In-place allowed. */
 int adept_b200_vdfdx_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* v, double dt,
                          double k1x, const double* k1x_batch, void* stream);
 
@@ -126,7 +126,8 @@ int adept_b200_filter_x_f64(const double* f_in, double* f_out, int batch, int nx
 
 /* v-advection (spectral): accel_i = (q (e_i + dex_i) + (q^2/m) pond_i)/m;
  * f_out = irfft(exp(-i kv_n dt accel_i) rfft(f_in, axis=v), axis=v).  e, dex, pond are [batch, nx]
- * (dex, pond nullable); k1v = kv_real[1] = 2 pi / (nv dv).  nv power of two (<= 8192), nx even.  In-place allowed. */
+ * (dex, pond nullable); k1v = kv_real[1] = 2 pi / (nv dv).  nv a power of two (<= 8192) or any even number <= 4096
+ * (chirp-z path), nx even.  In-place allowed. */
 int adept_b200_edfdv_exp_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* e,
                              const double* dex, const double* pond, double charge, double mass, double dt, double k1v,
                              void* stream);
@@ -146,7 +147,8 @@ int adept_b200_moments_f64(const double* f, int batch, int nx, int nv, const dou
 
 /* Field solve, one FFT of length nx per member.  mode 0: E = Re ifft(-i kmul fft(rho)), kmul = one_over_kx[nx].
  * mode 1 (Boltzmann electrons): kmul = kx[nx], kernel kx (Te/rho0) / (1 + lambda^2 kx^2), rho0 = mean(rho),
- * lambda_De < 0 selects lambda^2 = Te/rho0.  kmul_stride = 0 shares kmul between members, nx = per-member tables. */
+ * lambda_De < 0 selects lambda^2 = Te/rho0.  kmul_stride = 0 shares kmul between members, nx = per-member tables.
+ * nx a power of two (<= 8192) or any even number <= 4096. */
 int adept_b200_poisson_f64(const double* rho, const double* kmul, long long kmul_stride, double* e, int batch, int nx,
                            int mode, double Te, double lambda_De, void* stream);
 

@@ -459,3 +459,46 @@ def test_dist_save_interp2d_matches_oracle(ops, nx, nv, nxq, nvq):
     # a grid-node query hits the node exactly (searchsorted side="right")
     out = host(ops.interp2d(dev(f0), dev(x), dev(v), dev(x), dev(v)))
     assert np.max(np.abs(out - f0)) <= 1e-14
+
+
+@pytest.mark.parametrize("nx,nv", [(6, 8), (12, 20), (96, 24), (1028, 16), (1728, 8), (3456, 4), (4094, 4)])
+def test_vdfdx_any_even_length(ops, nx, nv):
+    """Transform lengths that are not powers of two (stock decks: nx = 1028, 1728, 3456) take the chirp-z path."""
+    f, x, v, dx, dv = make_f(nx, nv, seed=nx, noise=1e-3)
+    kxr = np.fft.rfftfreq(nx, d=dx) * 2 * np.pi
+    ref = O.space_exponential(f, kxr, v, 0.37)
+    out = host(ops.vdfdx(dev(f), dev(v), 0.37, kxr[1]))
+    assert rel_l2(out, ref) <= RTOL
+    # a batch of two members with their own box lengths
+    fb = np.stack([f, 0.5 * f[::-1].copy()])
+    k1s = [kxr[1], 1.3 * kxr[1]]
+    refb = np.stack([O.space_exponential(fb[i], k1s[i] / kxr[1] * kxr, v, -0.21) for i in range(2)])
+    outb = host(ops.vdfdx(dev(fb), dev(v), -0.21, 0.0, k1x_batch=dev(np.array(k1s))))
+    assert rel_l2(outb, refb) <= RTOL
+
+
+@pytest.mark.parametrize("nx,nv", [(4, 6), (6, 96), (2, 384), (4, 1028), (2, 3000)])
+def test_edfdv_exp_any_even_length(ops, nx, nv):
+    f, x, v, dx, dv = make_f(nx, nv, seed=nv, noise=1e-3)
+    rng = np.random.default_rng(nv)
+    e, dex, pond = 0.3 * rng.standard_normal(nx), 0.01 * rng.standard_normal(nx), 0.02 * rng.standard_normal(nx)
+    kvr = np.fft.rfftfreq(nv, d=dv) * 2 * np.pi
+    ref = O.velocity_exponential(f, kvr, e + dex, pond, 0.1, -1.0, 1.0)
+    out = host(ops.edfdv_exp(dev(f), dev(e), dev(pond), -1.0, 1.0, 0.1, kvr[1], dex=dev(dex)))
+    assert rel_l2(out, ref) <= RTOL
+
+
+@pytest.mark.parametrize("nx", [6, 100, 1028, 1728, 3456])
+def test_poisson_any_even_length(ops, nx):
+    rng = np.random.default_rng(nx)
+    dx = 20.94 / nx
+    rho = rng.standard_normal((3, nx))
+    kx = 2 * np.pi * np.fft.fftfreq(nx, d=dx)
+    ook = np.zeros(nx)
+    ook[1:] = 1.0 / kx[1:]
+    ref = np.stack([O.poisson(r, ook) for r in rho])
+    out = host(ops.poisson(dev(rho), dev(ook)))
+    assert np.max(np.abs(out - ref)) <= 1e-12 * np.max(np.abs(ref))
+    rho_i = 1.0 + 0.1 * rng.standard_normal(nx)
+    e = host(ops.poisson(dev(rho_i), dev(kx), mode=1, Te=2.0, lambda_De=0.7))
+    assert rel_l2(e, O.boltzmann_poisson(rho_i, kx, 2.0, 0.7)) <= RTOL

@@ -81,6 +81,13 @@ def variants():
     d["terms"]["krook"]["is_on"] = True
     d["terms"]["krook"]["time"]["baseline"] = 1e-3
     out["wavepacket-like-256x384"] = d
+    d = c2_deck()  # configs/vlasov-1d/srs-debug-small.yaml's grid: nx = 1028 = 4 x 257 (chirp-z transforms in x)
+    d["grid"].update(nx=1028, nv=64)
+    out["srs-debug-small-like-1028x64"] = d
+    d = c2_deck()  # non-power-of-two in both directions, sixth-order integrator
+    d["grid"].update(nx=96, nv=384)
+    d["terms"].update(time="sixth")
+    out["any-length-96x384-sixth"] = d
     d = c2_deck()  # Chang-Cooper weighting in the fused v-push + collision kernel
     d["grid"].update(nx=1024, nv=1024)
     d["terms"]["fokker_planck"]["type"] = "chang_cooper_dougherty"
