@@ -64,3 +64,22 @@ timeit("poisson", lambda: ops.poisson(rho, rho), 0.0)
 parts = torch.zeros((ops.vdfdx_rho_parts(fd), nx), dtype=torch.float64, device="cuda")
 timeit("vdfdx_rho(tma)", lambda: ops.vdfdx_rho(fd, vd, 0.1, k1x, parts, out=gd))
 timeit("vpush_collide", lambda: ops.vpush_collide(fd, e, None, -1.0, 1.0, 0.1, k1v, vd, dv, nu, model=1, out=gd), 32.0)
+nu_cc = nu
+timeit("vpush_collide_cc", lambda: ops.vpush_collide(fd, e, None, -1.0, 1.0, 0.1, k1v, vd, dv, nu_cc, model=1, out=gd, scheme=1), 32.0)
+# non-power-of-two lengths (chirp-z path), same cell count as a 2048 x 2048 grid for orientation
+nb = 3456
+fb = torch.as_tensor(np.ascontiguousarray(f[:nb, :1024]), device="cuda")
+gb = torch.empty_like(fb)
+vb = torch.as_tensor(v[:1024].copy(), device="cuda")
+for _name, _fn, _cells in (("vdfdx 3456x1024 (bluestein)", lambda: ops.vdfdx(fb, vb, 0.1, k1x, out=gb), nb * 1024),):
+    for _ in range(3):
+        _fn()
+    torch.cuda.synchronize()
+    s_, t_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s_.record()
+    for _ in range(5):
+        _fn()
+    t_.record()
+    torch.cuda.synchronize()
+    us = s_.elapsed_time(t_) * 1e3 / 5
+    print(f"{_name:28s} {us:8.1f} us   {_cells * 16 / us / 1e3:7.0f} GB/s")
