@@ -429,8 +429,10 @@ def test_errors_are_loud(ops):
 
     f = torch.zeros(12, 16, dtype=torch.float64, device="cuda")
     v = torch.zeros(16, dtype=torch.float64, device="cuda")
-    with pytest.raises(AdeptB200Error, match="power of two"):
-        ops.vdfdx(f, v, 0.1, 1.0)  # nx = 12
+    ops.vdfdx(f, v, 0.1, 1.0)  # nx = 12: even, runs through the chirp-z path
+    for nx_bad in (13, 4098):  # odd lengths and even non-powers of two above 4096 have no kernel (and no fallback)
+        with pytest.raises(AdeptB200Error, match="power of two"):
+            ops.vdfdx(torch.zeros(nx_bad, 16, dtype=torch.float64, device="cuda"), v, 0.1, 1.0)
     with pytest.raises(AdeptB200Error, match="no CPU path"):
         ops.vdfdx(f.cpu(), v, 0.1, 1.0)
     with pytest.raises(AdeptB200Error, match="float64"):
