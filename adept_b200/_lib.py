@@ -46,6 +46,7 @@ class Step(C.Structure):
         ("nu_fp_space", c_dp), ("nu_K_space", c_dp), ("nu_fp_time", c_d), ("nu_K_time", c_d), ("f_mx", c_dp),
         ("sync_counter", c_dp),
         ("ex_w_row", c_dp), ("ex_a0_row", c_dp), ("ex_t", c_d * MAX_SUBSTEPS),
+        ("fp_sc_steps", c_i), ("fp_sc_rtol", c_d), ("fp_sc_atol", c_d),
     ]
 
 
@@ -80,6 +81,8 @@ SIGNATURES = {
     "adept_b200_wave_step_f64": [c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_i, c_i, c_d, c_d, c_d, c_dp],
     "adept_b200_collide_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_d, c_d, c_dp, c_dp, c_dp, c_i, c_i, c_i, c_d, c_d,
                                c_dp, c_dp],
+    "adept_b200_collide_sc_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_d, c_d, c_dp, c_dp, c_dp, c_i, c_i, c_i, c_d, c_d,
+                                  c_dp, c_i, c_d, c_d, c_dp],
     "adept_b200_step_f64": [C.POINTER(Step), c_dp],
 }
 

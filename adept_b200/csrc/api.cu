@@ -458,4 +458,13 @@ int adept_b200_collide_f64(const double* f_in, double* f_out, int batch, int nx,
                      n_out, 1.0, 1.0, (cudaStream_t)stream);
 }
 
+int adept_b200_collide_sc_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* v, double dv,
+                              double dt, const double* nu_fp, const double* nu_K, const double* f_mx, int model,
+                              int scheme, int nodrag, double sg_m, double sg_ratio, double* n_out, int sc_max_steps,
+                              double sc_rtol, double sc_atol, void* stream) {
+  ADEPT_REQUIRE(f_in, "f_in") ADEPT_REQUIRE(f_out, "f_out") ADEPT_REQUIRE(v, "v")
+  return collide_f64(f_in, f_out, batch, nx, nv, v, dv, dt, nu_fp, nu_K, f_mx, model, scheme, nodrag, sg_m, sg_ratio,
+                     n_out, 1.0, 1.0, (cudaStream_t)stream, sc_max_steps, sc_rtol, sc_atol);
+}
+
 }  // extern "C"

@@ -24,6 +24,7 @@
 // directly for f + delta.  The matrix is strictly diagonally dominant, so no pivoting is needed; the reference's
 // LAPACK gtsv agrees to rounding.
 #include "collide_core.cuh"
+#include <math_constants.h>
 #include "internal.h"
 
 namespace adept {
@@ -44,7 +45,34 @@ struct CollideArgs {
   double* n_out;          // [rows] or null: sum_j f_out dv
   int rows_per_cta;       // R: x-rows handled by one CTA (set by the launcher)
   double nu_fp_scale, nu_K_scale;  // nu = scale * nu[row] (time envelope applied in the kernel)
+  int sc_steps;                    // self-consistent beta: Newton iterations (0 = off), fokker_planck.py:296-301
+  double sc_rtol, sc_atol;
 };
+
+// d delta / d w of the Chang-Cooper weight, branch by branch as autodiff differentiates driftdiffusion.py:96-103
+__device__ __forceinline__ double cc_delta_prime(double w) {
+  if (fabs(w) < 1.0e-8) return -1.0 / 12.0 + w * w * (1.0 / 240.0);
+  const double em = expm1(w);
+  const double r = exp(w) / (em * em);
+  return -1.0 / (w * w) + (isfinite(r) ? r : 0.0);
+}
+
+// One Newton update of optimistix 0.1.0's root finder for a scalar (oracle/vlasov1d.py::newton_root_find): the Cauchy
+// test runs before the step and a finished row keeps its value.
+struct NewtonState {
+  double diff, fprev;
+  bool done;
+};
+__device__ __forceinline__ void newton_update(double& y, NewtonState& st, double fx, double slope, double rtol,
+                                              double atol) {
+  st.done = st.done || (fabs(st.diff) < atol + rtol * fabs(y) && fabs(st.fprev) < atol);
+  if (!st.done) {
+    const double d = fx / slope;
+    y -= d;
+    st.diff = d;
+    st.fprev = fx;
+  }
+}
 
 // Reciprocals here are fast_rcp (MUFU seed + two Newton steps, <= 1 ulp) and the per-row quotients D/dv, 1/dv, dv/D are
 // formed once per row by the caller: an IEEE division costs ~25 fp64 instructions and this runs once per cell edge.
@@ -160,6 +188,34 @@ __global__ void __launch_bounds__(MAXT, MINB) collide_kernel(CollideArgs p) {
       if (!live) sp[0] = 0.0;
       row_reduce<1>(sp, red, parity, live ? r : 0, tt, T, RT, warp_mode, live);
       beta = s0 / (p.sg_m * sp[0]);
+      if (p.sc_steps > 0) {
+        // SuperGaussianDougherty.compute_beta, fokker_planck.py:195-207: Newton on the discrete energy-flux condition
+        // h(beta) = sum_e v_e (w ftilde(w) + df), w = beta dpsi, over the edges e = i0 + l owned by this chunk
+        NewtonState st = {CUDART_INF, CUDART_INF, false};
+        for (int it = 0; it < p.sc_steps; it++) {
+          double hs[2] = {0.0, 0.0};
+#pragma unroll
+          for (int l = 0; l < E; l++) {
+            const int e = i0 + l;
+            if (e <= nv - 2) {
+              const double va = __ldg(p.v + e), vb = __ldg(p.v + e + 1);
+              const double fa = chunk[l], fb = (l < E - 1) ? chunk[l + 1] : rowbuf[i0 + E + (tt + 1)];
+              const double dpsi = pow(fabs(vb - vbar), p.sg_m) - pow(fabs(va - vbar), p.sg_m);
+              const double w = beta * dpsi;
+              double dl;
+              if (fabs(w) < 1.0e-8) dl = 0.5 - w * (1.0 / 12.0) + w * w * w * (1.0 / 720.0);
+              else dl = 1.0 / w - 1.0 / expm1(w);
+              const double ft = dl * fa + (1.0 - dl) * fb;
+              const double ve = 0.5 * (vb + va);
+              hs[0] += ve * (w * ft + (fb - fa));
+              hs[1] += ve * dpsi * (ft + w * cc_delta_prime(w) * (fa - fb));
+            }
+          }
+          if (!live) hs[0] = hs[1] = 0.0;
+          row_reduce<2>(hs, red, parity, live ? r : 0, tt, T, RT, warp_mode, live);
+          newton_update(beta, st, hs[0], hs[1], p.sc_rtol, p.sc_atol);
+        }
+      }
       D = pow(beta, -2.0 / p.sg_m) * p.sg_ratio;
     } else {
       double Temp;
@@ -179,6 +235,27 @@ __global__ void __launch_bounds__(MAXT, MINB) collide_kernel(CollideArgs p) {
         Temp = tm[0] / tm[1];
       }
       beta = 1.0 / (2.0 * Temp);
+      if (!FAST && p.sc_steps > 0) {
+        // find_self_consistent_beta, driftdiffusion.py:161-233: beta* whose sampled Maxwellian exp(-beta (v - vbar)^2)
+        // has the discrete temperature of f; slope = d(v2 / norm) / d beta
+        NewtonState st = {CUDART_INF, CUDART_INF, false};
+        for (int it = 0; it < p.sc_steps; it++) {
+          double ms[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+          for (int l = 0; l < E; l++) {
+            const double vs = __ldg(p.v + i0 + l) - vbar;
+            const double sq = vs * vs;
+            const double fm = exp(-beta * sq);
+            ms[0] += fm * dv;
+            ms[1] += fm * sq * dv;
+            ms[2] += fm * sq * sq * dv;
+          }
+          if (!live) ms[0] = ms[1] = ms[2] = 0.0;
+          row_reduce<3>(ms, red, parity, live ? r : 0, tt, T, RT, warp_mode, live);
+          const double norm = ms[0], v2 = ms[1];
+          newton_update(beta, st, v2 / norm - Temp, (-ms[2] * norm + v2 * ms[1]) / (norm * norm), p.sc_rtol, p.sc_atol);
+        }
+      }
       D = 1.0 / (2.0 * beta);
     }
     const double dtnu = dt * nu;
@@ -760,7 +837,7 @@ static int launch_collide(const CollideArgs& p, bool fast, cudaStream_t stream) 
 int collide_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* v, double dv, double dt,
                 const double* nu_fp, const double* nu_K, const double* f_mx, int model, int scheme, int nodrag,
                 double sg_m, double sg_ratio, double* n_out, double nu_fp_scale, double nu_K_scale,
-                cudaStream_t stream) {
+                cudaStream_t stream, int sc_steps, double sc_rtol, double sc_atol) {
   if (batch < 1 || nx < 1 || nv < 4) {
     set_last_error("collide: bad shape batch=%d nx=%d nv=%d", batch, nx, nv);
     return ADEPT_ERR_BAD_SHAPE;
@@ -774,8 +851,14 @@ int collide_f64(const double* fin, double* fout, int batch, int nx, int nv, cons
     return ADEPT_ERR_BAD_ARG;
   }
   CollideArgs p = {fin, fout, (long long)batch * nx, nv, v, dv, dt, nu_fp, nu_K, f_mx,
-                   model, scheme, nodrag, sg_m, sg_ratio, n_out, 1, nu_fp_scale, nu_K_scale};
-  const bool fast = model != FP_SUPERGAUSSIAN && !nodrag;  // uniform-grid arithmetic, central or Chang-Cooper
+                   model, scheme, nodrag, sg_m, sg_ratio, n_out, 1, nu_fp_scale, nu_K_scale,
+                   sc_steps, sc_rtol, sc_atol};
+  if (sc_steps < 0 || sc_steps > 64) {
+    set_last_error("collide: self-consistent beta max_steps=%d out of range [0, 64]", sc_steps);
+    return ADEPT_ERR_BAD_ARG;
+  }
+  // uniform-grid arithmetic, central or Chang-Cooper; the Newton refinement of beta lives in the general kernel
+  const bool fast = model != FP_SUPERGAUSSIAN && !nodrag && sc_steps == 0;
   if (nv % 16 == 0 && nv / 16 <= 256) return launch_collide<16, 256, 2>(p, fast, stream);
   if (nv % 16 == 0 && nv / 16 <= 512) return launch_collide<16, 512, 1>(p, fast, stream);
   if (nv % 16 == 0 && nv / 16 <= 1024) return launch_collide<16, 1024, 1>(p, fast, stream);

@@ -34,7 +34,7 @@ int wave_step_f64(const double* a, const double* aold, const double* djy, const 
 int collide_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* v, double dv, double dt,
                 const double* nu_fp, const double* nu_K, const double* f_mx, int model, int scheme, int nodrag,
                 double sg_m, double sg_ratio, double* n_out, double nu_fp_scale, double nu_K_scale,
-                cudaStream_t stream);
+                cudaStream_t stream, int sc_steps = 0, double sc_rtol = 1e-8, double sc_atol = 1e-12);
 int reduce_parts_f64(const double* parts, int nparts, long long n, double scale_a, double scale_b, const double* base,
                      double* out, cudaStream_t stream);
 int save_moments_f64(const double* f0, const double* f1, double w, int batch, int nx, int nv, const double* v,

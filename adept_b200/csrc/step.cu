@@ -256,7 +256,7 @@ int step_f64(const adept_b200_step& s, cudaStream_t st) {
     ADEPT_TRY(c.field_solve(fstar, want_rho, s.dt, fused_field));
     // the colliding species takes the fused v-push + Fokker-Planck kernel when its shape and operator allow it
     const int kc = s.collide_species;
-    if (s.fp_on && !s.krook_on && !spline && kc >= 0 && kc < s.n_species &&
+    if (s.fp_on && !s.krook_on && !spline && s.fp_sc_steps == 0 && kc >= 0 && kc < s.n_species &&
         vpush_collide_supported(s.nx, s.species[kc].nv, s.fp_model, s.fp_scheme, s.fp_nodrag)) {
       for (int k = 0; k < s.n_species; k++) {
         const adept_b200_species& sp = s.species[k];
@@ -314,7 +314,8 @@ int step_f64(const adept_b200_step& s, cudaStream_t st) {
     const adept_b200_species& sp = s.species[s.collide_species];
     ADEPT_TRY(collide_f64(sp.f_out, sp.f_out, s.batch, s.nx, sp.nv, sp.v, sp.dv, s.dt, s.fp_on ? s.nu_fp_space : nullptr,
                           s.krook_on ? s.nu_K_space : nullptr, s.f_mx, s.fp_model, s.fp_scheme, s.fp_nodrag, s.sg_m,
-                          s.sg_ratio, nullptr, s.nu_fp_time, s.nu_K_time, st));
+                          s.sg_ratio, nullptr, s.nu_fp_time, s.nu_K_time, st, s.fp_sc_steps, s.fp_sc_rtol,
+                          s.fp_sc_atol));
   }
 
   if (wave) {  // vector_field.py:340-347

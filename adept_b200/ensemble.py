@@ -60,6 +60,8 @@ class EnsembleVlasov1D:
                     float(c["grid"]["species_grids"][name]["dv"])) for c in self.cfgs], f"the velocity grid of {name}")
             _same([(c["grid"]["species_params"][name]["charge"], c["grid"]["species_params"][name]["mass"])
                    for c in self.cfgs], f"charge and mass of {name}")
+        if any(c.get("drivers", {}).get("ex_stochastic") is not None for c in self.cfgs):
+            raise NotImplementedError("ensembles with the stochastic Ex driver are not implemented")
         if any(vm.has_ey for vm in self.vms):
             raise NotImplementedError("ensembles with transverse (Ey) drivers are not implemented")
         if not all(NativeStep.supported(vm) for vm in self.vms) or cfg0["terms"]["field"] not in ("poisson",):
@@ -162,6 +164,7 @@ class EnsembleVlasov1D:
         st.fp_on, st.krook_on = int(vm0.fp_on), int(vm0.krook_on)
         st.fp_model, st.fp_scheme, st.fp_nodrag = fp.model, fp.scheme, int(fp.nodrag)
         st.sg_m, st.sg_ratio = fp.m, fp.sg_ratio
+        st.fp_sc_steps, st.fp_sc_rtol, st.fp_sc_atol = fp.sc_steps, fp.sc_rtol, fp.sc_atol
         if vm0.fp_on:
             st.nu_fp_space = self.tab["nu_fp"].data_ptr()
         if vm0.krook_on:

@@ -302,14 +302,15 @@ def wave_step(a, aold, djy, ne_n, ne_np1, c, dx, dt, out=None):
 
 
 def collide(f, v, dv, dt, nu_fp=None, nu_K=None, f_mx=None, model=1, scheme=0, nodrag=False, sg_m=2.0, sg_ratio=0.5,
-            n_out=None, out=None):
-    """Fokker-Planck (delta-form implicit) + Krook (fokker_planck.py:368-484)."""
+            n_out=None, out=None, sc_steps=0, sc_rtol=1e-8, sc_atol=1e-12):
+    """Fokker-Planck (delta-form implicit) + Krook (fokker_planck.py:368-484); ``sc_steps > 0`` refines beta by the
+    self-consistent Newton solve first (driftdiffusion.py:161-283, fokker_planck.py:139-210)."""
     b, nx, nv = _shape3(f)
     out = torch.empty_like(f) if out is None else out
-    rc = _lib.load().adept_b200_collide_f64(
+    rc = _lib.load().adept_b200_collide_sc_f64(
         _ptr(f, "f"), _ptr(out, "out"), b, nx, nv, _ptr(v, "v"), float(dv), float(dt), _ptr(nu_fp, "nu_fp", True),
         _ptr(nu_K, "nu_K", True), _ptr(f_mx, "f_mx", True), int(model), int(scheme), int(bool(nodrag)), float(sg_m),
-        float(sg_ratio), _ptr(n_out, "n_out", True), _stream(),
+        float(sg_ratio), _ptr(n_out, "n_out", True), int(sc_steps), float(sc_rtol), float(sc_atol), _stream(),
     )
     _lib.check(rc, "collide")
     _count()

@@ -277,6 +277,10 @@ class EMDriver:
         self.envelope = envelope
         self.is_point_source = bool(is_point_source)
 
+    def phase(self, t):
+        """Temporal phase of the carrier, (w0 + dw0) t (field.py:31)."""
+        return (self.w0 + self.dw0) * t
+
     @staticmethod
     def from_config(cfg: dict, c_light: float) -> "EMDriver":
         from .functions import SpaceTimeEnvelopeFunction
@@ -293,6 +297,71 @@ class EMDriver:
             w0 = c_light * k0
         return EMDriver(p["a0"], k0, w0, p.get("dw0", 0.0), SpaceTimeEnvelopeFunction.from_config(cfg["envelope"]),
                         cfg.get("source_type", "extended") == "point")
+
+
+class StochasticDriver:
+    """Ornstein-Uhlenbeck amplitudes of a few box modes, drawn once on the host with numpy's Generator exactly as the
+    reference does (simulation.py:95-148), linearly interpolated in time."""
+
+    def __init__(self, scfg: dict, grid):
+        modes = [int(m) for m in scfg.get("modes", [1])]
+        if not modes or any(m < 1 for m in modes):  # datamodel.py:177-182
+            raise ValueError(f"stochastic driver modes must be positive integers, got {modes}")
+        amplitude, tau = float(scfg["amplitude"]), float(scfg["tau"])
+        if tau <= 0:  # datamodel.py:184-189
+            raise ValueError(f"stochastic driver correlation time tau must be > 0, got {tau}")
+        dt_update = float(scfg["dt_update"]) if scfg.get("dt_update") is not None else tau / 10.0
+        dt_update = min(dt_update, tau / 2.0)
+        nt = int(np.ceil((grid.tmax - grid.tmin) / dt_update)) + 2
+        rng = np.random.default_rng(int(scfg.get("seed", 42)))
+        theta = np.exp(-dt_update / tau)
+        kick = amplitude * np.sqrt(1.0 - theta**2)
+        n = len(modes)
+        amps = np.zeros((nt, n), dtype=np.complex128)
+        amps[0] = amplitude * (rng.standard_normal(n) + 1j * rng.standard_normal(n)) / np.sqrt(2.0)
+        for it in range(1, nt):
+            xi = (rng.standard_normal(n) + 1j * rng.standard_normal(n)) / np.sqrt(2.0)
+            amps[it] = theta * amps[it - 1] + kick * xi
+        self.t_grid = grid.tmin + dt_update * np.arange(nt)
+        self.amp_real, self.amp_imag = amps.real.copy(), amps.imag.copy()
+        self.k_modes = 2.0 * np.pi * np.asarray(modes, dtype=np.float64) / (grid.xmax - grid.xmin)
+
+    def modes(self):
+        """One pseudo driver per mode for LongitudinalElectricFieldDriver / the native step: the mode's field
+        ar cos(kx) - ai sin(kx) is A sin(kx - phase) with A = hypot(ar, ai), phase = -atan2(ar, -ai)."""
+        return [_StochasticMode(self, j) for j in range(len(self.k_modes))]
+
+
+class _Ones:
+    def __call__(self, x):
+        return np.ones_like(np.asarray(x, dtype=np.float64))
+
+
+class _StochasticMode:
+    """Quacks like EMDriver (a0 = w0 = 1): time_envelope(t) is the mode's modulus, phase(t) minus its argument."""
+
+    is_point_source = False
+
+    def __init__(self, parent, j):
+        self.a0, self.w0, self.dw0, self.k0 = 1.0, 1.0, 0.0, float(parent.k_modes[j])
+        self._p, self._j = parent, j
+        self.envelope = self
+        self.space_envelope = _Ones()
+
+    def _amp(self, t):
+        p, j = self._p, self._j
+        return float(np.interp(t, p.t_grid, p.amp_real[:, j])), float(np.interp(t, p.t_grid, p.amp_imag[:, j]))
+
+    def time_envelope(self, t):
+        ar, ai = self._amp(t)
+        return math.hypot(ar, ai)
+
+    def phase(self, t):
+        ar, ai = self._amp(t)
+        return -math.atan2(ar, -ai)
+
+    def __call__(self, x, t):  # envelope(x, t)
+        return self.time_envelope(t) * np.ones_like(np.asarray(x, dtype=np.float64))
 
 
 class LongitudinalElectricFieldDriver:
@@ -312,7 +381,7 @@ class LongitudinalElectricFieldDriver:
         for d, sp, kx in zip(self.drivers, self._space, self._kx):
             w = d.w0 + d.dw0
             amp = float(d.envelope.time_envelope(t)) * w * d.a0
-            total += torch.sin(kx - w * t) * sp * amp
+            total += torch.sin(kx - d.phase(t)) * sp * amp
         return total
 
     def host(self, t):
@@ -320,7 +389,7 @@ class LongitudinalElectricFieldDriver:
         total = np.zeros_like(self.xax)
         for d in self.drivers:
             w = d.w0 + d.dw0
-            total += d.envelope(self.xax, t) * w * d.a0 * np.sin(d.k0 * self.xax - w * t)
+            total += d.envelope(self.xax, t) * w * d.a0 * np.sin(d.k0 * self.xax - d.phase(t))
         return total
 
 
@@ -391,8 +460,8 @@ class Collisions:
         self.m = float(fp_cfg.get("m", 2.0))
         self.sg_ratio = float(math.exp(gammaln(3.0 / self.m) - gammaln(1.0 / self.m)))
         sc = fp_cfg.get("self_consistent_beta", {})
-        if sc.get("enabled", False) and sc.get("max_steps", 3) != 0:
-            raise NotImplementedError("adept_b200: self_consistent_beta Newton refinement is not implemented")
+        self.sc_steps = int(sc.get("max_steps", 3)) if sc.get("enabled", False) else 0  # fokker_planck.py:296-301
+        self.sc_rtol, self.sc_atol = float(sc.get("rtol", 1e-8)), float(sc.get("atol", 1e-12))
         sg = cfg["grid"]["species_grids"][self.ref_species]
         self.v = _np(sg["v"])
         self.dv = float(sg["dv"])
@@ -422,7 +491,8 @@ class Collisions:
         f_mx = self._cache.get("f_mx", self.f_mx, f.device)
         return ops.collide(f, v, self.dv, float(dt), nu_fp=nu_fp if use_fp else None, nu_K=nu_K if use_k else None,
                            f_mx=f_mx, model=self.model, scheme=self.scheme, nodrag=self.nodrag, sg_m=self.m,
-                           sg_ratio=self.sg_ratio, n_out=n_out, out=out)
+                           sg_ratio=self.sg_ratio, n_out=n_out, out=out, sc_steps=self.sc_steps, sc_rtol=self.sc_rtol,
+                           sc_atol=self.sc_atol)
 
 
 class HouLiFilter:

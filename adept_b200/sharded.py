@@ -123,6 +123,8 @@ class ShardedVlasov1D:
         rows = slice(self.rank * self.nxp, (self.rank + 1) * self.nxp)
         self.rows = rows
         self.coll = Collisions(cfg)
+        if self.coll.sc_steps:
+            raise NotImplementedError("sharded runs do not take terms.fokker_planck.self_consistent_beta yet")
         self.fp_on, self.krook_on = bool(t["fokker_planck"]["is_on"]), bool(t["krook"]["is_on"])
         self.nu_fp_prof = SpaceTimeEnvelopeFunction.from_config(t["fokker_planck"]) if self.fp_on else None
         self.nu_K_prof = SpaceTimeEnvelopeFunction.from_config(t["krook"]) if self.krook_on else None
@@ -157,8 +159,8 @@ class ShardedVlasov1D:
             return "number of ranks is not a power of two <= 8"
         if t["edfdv"] != "exponential" or not self.fp_on or self.krook_on:
             return "needs the spectral v-push with Fokker-Planck collisions and no Krook operator"
-        if self.coll.model not in (0, 1) or self.coll.nodrag:
-            return "needs Lenard-Bernstein / Dougherty collisions (central or Chang-Cooper)"
+        if self.coll.model not in (0, 1) or self.coll.nodrag or self.coll.sc_steps:
+            return "needs Lenard-Bernstein / Dougherty collisions (central or Chang-Cooper), no self-consistent beta"
         if nx & (nx - 1) or not 256 <= nx <= 4096 or (nv // P) % 4:
             return "x-advection shape is not handled by the TMA kernel"
         if nv & (nv - 1) or not 512 <= nv <= 8192 or (nx // P) % 2:

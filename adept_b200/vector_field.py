@@ -258,6 +258,7 @@ class NativeStep:
         st.fp_on, st.krook_on = int(vm.fp_on), int(vm.krook_on)
         st.fp_model, st.fp_scheme, st.fp_nodrag = fp.model, fp.scheme, int(fp.nodrag)
         st.sg_m, st.sg_ratio = fp.m, fp.sg_ratio
+        st.fp_sc_steps, st.fp_sc_rtol, st.fp_sc_atol = fp.sc_steps, fp.sc_rtol, fp.sc_atol
         if vm.fp_on:
             st.nu_fp_space = self._table(("nu_fp", batch), lambda: np.broadcast_to(
                 vm.nu_fp_prof.space_envelope(vm._x) * np.ones(nx), (batch, nx)), dev).data_ptr()
@@ -300,7 +301,7 @@ class NativeStep:
             for i, dti in enumerate(self.dt_array):
                 ti = t + dti
                 st.ex_tenv[i][j] = float(d.envelope.time_envelope(ti))
-                st.ex_wt[i][j] = w * ti
+                st.ex_wt[i][j] = d.phase(ti)
         if vm.fp_on:
             st.nu_fp_time = float(vm.nu_fp_prof.time_envelope(t))
         if vm.krook_on:
@@ -333,8 +334,8 @@ class VlasovMaxwell:
         if drivers is None:
             ex = [pushers.EMDriver.from_config(d, c) for d in dcfg.get("ex", {}).values()]
             ey = [pushers.EMDriver.from_config(d, c) for d in dcfg.get("ey", {}).values()]
-            if dcfg.get("ex_stochastic") is not None:
-                raise NotImplementedError("adept_b200: the stochastic Ex driver is not implemented")
+            if dcfg.get("ex_stochastic") is not None:  # simulation.py:160-168, vector_field.py:290-295
+                ex = ex + pushers.StochasticDriver(dcfg["ex_stochastic"], grid).modes()
         else:
             ex, ey = drivers["ex"], drivers["ey"]
         self.ey_driver = pushers.TransverseCurrentSourceDriver(grid.x_a, drivers=ey, c=c, device=device)

@@ -172,6 +172,13 @@ int adept_b200_wave_step_f64(const double* a, const double* aold, const double* 
 int adept_b200_collide_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* v, double dv,
                            double dt, const double* nu_fp, const double* nu_K, const double* f_mx, int model,
                            int scheme, int nodrag, double sg_m, double sg_ratio, double* n_out, void* stream);
+/* Same with the self-consistent-beta refinement (find_self_consistent_beta, adept/driftdiffusion.py:161-283;
+ * SuperGaussianDougherty.compute_beta, fokker_planck.py:139-210): beta of every row is refined by up to sc_max_steps
+ * Newton iterations with optimistix's Cauchy termination (rtol, atol) before the operator is assembled. */
+int adept_b200_collide_sc_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* v, double dv,
+                              double dt, const double* nu_fp, const double* nu_K, const double* f_mx, int model,
+                              int scheme, int nodrag, double sg_m, double sg_ratio, double* n_out, int sc_max_steps,
+                              double sc_rtol, double sc_atol, void* stream);
 
 /* ---- adjoints (what the backward rule of a jax.custom_vjp around each operator calls) -------------------------------
  * x-advection and v-advection w.r.t. f: the forward entry points with dt -> -dt (the operators are real circulants with
@@ -265,6 +272,10 @@ typedef struct adept_b200_step {
   const double* ex_w_row;
   const double* ex_a0_row;
   double ex_t[ADEPT_B200_MAX_SUBSTEPS];
+  /* self-consistent beta (terms.fokker_planck.self_consistent_beta, fokker_planck.py:295-301): Newton iterations
+   * (0 = off, the default), rtol, atol */
+  int fp_sc_steps;
+  double fp_sc_rtol, fp_sc_atol;
 } adept_b200_step;
 
 int adept_b200_step_f64(const adept_b200_step* step, void* stream);

@@ -263,7 +263,7 @@ def test_ponderomotive_axpy_wave(ops):
 
 
 # ---------------------------------------------------------------------------------------------------- collisions
-def _fp_cfg(nv, vmax, fp_type, krook=False, T0=1.0, m=2.0):
+def _fp_cfg(nv, vmax, fp_type, krook=False, T0=1.0, m=2.0, sc_steps=0):
     dv = 2.0 * vmax / nv
     v = np.linspace(-vmax + dv / 2.0, vmax - dv / 2.0, nv)
     return {
@@ -271,7 +271,9 @@ def _fp_cfg(nv, vmax, fp_type, krook=False, T0=1.0, m=2.0):
             "species_grids": {"electron": {"v": v, "dv": dv, "nv": nv, "vmax": vmax}},
             "species_params": {"electron": {"charge": -1.0, "mass": 1.0, "charge_to_mass": -1.0, "T0": T0}},
         },
-        "terms": {"fokker_planck": {"is_on": True, "type": fp_type, "m": m}, "krook": {"is_on": krook}},
+        "terms": {"fokker_planck": {"is_on": True, "type": fp_type, "m": m,
+                                    "self_consistent_beta": {"enabled": sc_steps > 0, "max_steps": sc_steps}},
+                  "krook": {"is_on": krook}},
     }
 
 
@@ -288,7 +290,7 @@ def _gpu_collide(ops, coll, f, nu_fp, nu_K, dt, n_out=None):
         dev(f), dev(coll.v), coll.dv, dt,
         nu_fp=None if nu_fp is None else dev(nu_fp), nu_K=None if nu_K is None else dev(nu_K),
         f_mx=dev(coll.f_mx[0]), model=MODEL[coll.model], scheme=SCHEME[coll.scheme], nodrag=coll.nodrag,
-        sg_m=m, sg_ratio=ratio, n_out=n_out,
+        sg_m=m, sg_ratio=ratio, n_out=n_out, sc_steps=coll.sc_max_steps, sc_rtol=coll.sc_rtol, sc_atol=coll.sc_atol,
     )
 
 
@@ -320,6 +322,58 @@ def test_collide_matches_oracle(ops, fp_type, nx, nv):
     ref = coll(nu3, None, f, dt)
     out = host(_gpu_collide(ops, coll, f, nu3, None, dt))
     assert rel_l2(out, ref) <= max(RTOL, 2e-16 * dt * nu3.max() / dv**2)
+
+
+@pytest.mark.parametrize("fp_type", ["lenard_bernstein", "chang_cooper", "dougherty", "chang_cooper_dougherty",
+                                     "dougherty_nodrag", "super_gaussian"])
+@pytest.mark.parametrize("nx,nv,sc_steps", [(16, 128, 3), (5, 64, 1), (8, 512, 3), (3, 96, 2), (2, 4096, 3)])
+def test_collide_self_consistent_beta_matches_oracle(ops, fp_type, nx, nv, sc_steps):
+    """terms.fokker_planck.self_consistent_beta (fokker_planck.py:295-301, 391-410): beta refined by Newton on the
+    discrete temperature (driftdiffusion.py:161-233) or, super-Gaussian, on the discrete energy flux
+    (fokker_planck.py:139-210), then the same operator."""
+    cfg = _fp_cfg(nv, 6.0, fp_type, m=3.0 if fp_type == "super_gaussian" else 2.0, sc_steps=sc_steps)
+    coll = O.Collisions(cfg)
+    assert coll.sc_max_steps == sc_steps
+    f, x, v, dx, dv = make_f(nx, nv, seed=nv + sc_steps, noise=0.0, vmax=6.0)
+    # rows of different widths and drifts: the discrete and continuum temperatures differ most on narrow rows
+    width = np.linspace(0.05 if nv <= 128 else 0.4, 1.5, nx)[:, None]
+    drift = np.linspace(-0.7, 0.9, nx)[:, None]
+    f = np.exp(-np.abs(v[None, :] - drift) ** coll.m / (2 * width)) * (1 + 0.05 * np.sin(7 * v))[None, :]
+    for nu in (np.linspace(0.2, 1.0, nx), 1e-5 * np.ones(nx)):
+        ref = coll(nu, None, f, 0.1)
+        out = host(_gpu_collide(ops, coll, f, nu, None, 0.1))
+        assert rel_l2(out, ref) <= max(RTOL, 2e-16 * 0.1 * nu.max() / dv**2)
+    # the refinement is not a no-op on this input (otherwise the test would not see it)
+    coll0 = O.Collisions(_fp_cfg(nv, 6.0, fp_type, m=coll.m, sc_steps=0))
+    nu = np.linspace(0.2, 1.0, nx)
+    assert rel_l2(coll0(nu, None, f, 0.1), coll(nu, None, f, 0.1)) > 1e-9
+
+
+def test_collide_sc_beta_supergaussian_fixed_point_on_gpu(ops):
+    """The reference's own known answer (tests/test_vlasov1d/test_super_gaussian_fp.py:127-141) through the C ABI:
+    100 settling steps, then 1000 more move f by < 1e-8."""
+    from scipy.special import gamma
+
+    m, nv = 3.0, 128
+    cfg = _fp_cfg(nv, 6.0, "super_gaussian", m=m, sc_steps=3)
+    coll = O.Collisions(cfg)
+    v, dv = coll.v, coll.dv
+    vm = np.sqrt(gamma(1.0 / m) / gamma(3.0 / m))
+    f = np.exp(-(np.abs(v / vm) ** m))
+    f = dev((f / np.sum(f * dv))[None, :])
+    nu = dev(np.ones(1))
+    args = dict(nu_fp=nu, f_mx=None, model=2, scheme=1, sg_m=m, sg_ratio=float(gamma(3.0 / m) / gamma(1.0 / m)),
+                sc_steps=3)
+    vd = dev(v)
+    for _ in range(100):
+        f = ops.collide(f, vd, dv, 0.1, **args)
+    f_eq = host(f)
+    for _ in range(1000):
+        f = ops.collide(f, vd, dv, 0.1, **args)
+    f_end = host(f)
+    assert np.linalg.norm(f_end - f_eq) / np.linalg.norm(f_eq) < 1e-8
+    T = lambda g: np.sum(g[0] * v**2 * dv) / np.sum(g[0] * dv)
+    assert abs(T(f_end) / T(f_eq) - 1.0) < 1e-8
 
 
 def test_collide_strongly_collisional(ops):

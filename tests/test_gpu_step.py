@@ -99,6 +99,22 @@ def variants():
     d = load("multispecies_ion_acoustic")  # two species with different nv feed one fused field solve
     d["grid"].update(nx=1024)
     out["L-multispecies-1024"] = d
+    d = c2_deck()  # self-consistent beta (Newton on the discrete temperature) in a driven step
+    d["terms"]["fokker_planck"].update(type="chang_cooper_dougherty",
+                                       self_consistent_beta={"enabled": True, "max_steps": 3})
+    d["terms"]["fokker_planck"]["time"]["baseline"] = 0.1
+    out["C2-cc-sc-beta"] = d
+    d = c2_deck()  # Ornstein-Uhlenbeck forcing of three box modes on top of the deterministic driver
+    d["drivers"]["ex_stochastic"] = {"modes": [1, 2, 5], "amplitude": 2.0e-3, "tau": 1.5, "seed": 7}
+    out["C2-ex-stochastic"] = d
+    d = c2_deck()
+    d["terms"].update(time="sixth")
+    d["drivers"]["ex_stochastic"] = {"modes": [3], "amplitude": 1.0e-3, "tau": 0.4, "dt_update": 0.05}
+    out["C2-ex-stochastic-sixth"] = d
+    d = c2_deck()  # the same on a large grid: the deck leaves the fused v-row kernel for the general collision kernel
+    d["grid"].update(nx=1024, nv=1024)
+    d["terms"]["fokker_planck"]["self_consistent_beta"] = {"enabled": True, "max_steps": 2}
+    out["L-1024x1024-sc-beta"] = d
     return out
 
 

@@ -73,3 +73,31 @@ def test_save_axis_matches_oracle():
     ref = O.build_cfg(load("epw"))
     for tcfg in ({"nt": 11}, {"nt": 7, "tmin": 1.0, "tmax": 5.0}):
         np.testing.assert_array_equal(save_axis(tcfg, grid), O.save_axis(tcfg, ref["grid"]))
+
+
+def test_stochastic_driver_matches_oracle_realisation():
+    """simulation.py:95-148: same numpy Generator stream, same OU series; the host hands every mode to the device as
+    an amplitude/phase pair (A sin(kx - phase)), which must reproduce ar cos(kx) - ai sin(kx)."""
+    from adept_b200 import pushers
+
+    class G:
+        xmin, xmax, tmin, tmax = 0.0, 20.94, 0.0, 50.0
+
+    sc = {"modes": [1, 2, 5], "amplitude": 1e-3, "tau": 3.0, "seed": 7}
+    o = O.StochasticDriver(sc, G.xmin, G.xmax, G.tmin, G.tmax)
+    h = pushers.StochasticDriver(sc, G)
+    np.testing.assert_array_equal(o.amp_real, h.amp_real)
+    np.testing.assert_array_equal(o.t_grid, h.t_grid)
+    x = np.linspace(0.1, 20.8, 64)
+    for t in (0.0, 0.37, 12.3, 49.9):
+        tot = np.zeros_like(x)
+        for d in h.modes():
+            tot += d.envelope(x, t) * (d.w0 + d.dw0) * d.a0 * np.sin(d.k0 * x - d.phase(t))
+        ref = o(t, x)
+        assert np.linalg.norm(tot - ref) <= 1e-14 * np.linalg.norm(ref)
+    # stationary RMS of the OU process is `amplitude` per mode (|a_m|^2 averages to amplitude^2)
+    long = O.StochasticDriver({"modes": [1], "amplitude": 0.5, "tau": 1.0, "seed": 1}, 0.0, 1.0, 0.0, 4000.0)
+    rms = np.sqrt(np.mean(long.amp_real**2 + long.amp_imag**2))
+    assert abs(rms / 0.5 - 1.0) < 0.05
+    with pytest.raises(ValueError):
+        pushers.StochasticDriver({"modes": [0], "amplitude": 1.0, "tau": 1.0}, G)
