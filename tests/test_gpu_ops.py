@@ -342,7 +342,8 @@ def test_collide_self_consistent_beta_matches_oracle(ops, fp_type, nx, nv, sc_st
     for nu in (np.linspace(0.2, 1.0, nx), 1e-5 * np.ones(nx)):
         ref = coll(nu, None, f, 0.1)
         out = host(_gpu_collide(ops, coll, f, nu, None, 0.1))
-        assert rel_l2(out, ref) <= max(RTOL, 2e-16 * 0.1 * nu.max() / dv**2)
+        # conditioning as in test_collide_matches_oracle; the rows here reach D = T ~ width.max() = 1.5
+        assert rel_l2(out, ref) <= max(RTOL, 4e-16 * 0.1 * nu.max() * width.max() / dv**2)
     # the refinement is not a no-op on this input (otherwise the test would not see it)
     coll0 = O.Collisions(_fp_cfg(nv, 6.0, fp_type, m=coll.m, sc_steps=0))
     nu = np.linspace(0.2, 1.0, nx)
