@@ -216,3 +216,54 @@ class EnsembleVlasov1D:
     def member_state(self, i):
         """State dict of member ``i`` (views into the batched tensors), keyed like ``Vlasov1D.state``."""
         return {k: v[i] for k, v in self.state.items()}
+
+
+# ---------------------------------------------------------------------------------------------- sharding across GPUs
+def member_slice(n_members: int, rank: int, world: int) -> slice:
+    """Members owned by ``rank``: contiguous blocks whose sizes differ by at most one (the first ``n % world`` ranks
+    take one more).  Independent members: no data-path collective (ensembles)."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, extra = divmod(int(n_members), world)
+    start = rank * base + min(rank, extra)
+    return slice(start, start + base + (1 if rank < extra else 0))
+
+
+def run_sharded_ensemble(decks, nsteps, diagnostics, make=None, group=None):
+    """Advance ``decks`` split over the ranks of ``torch.distributed`` (one process per GPU; works unsharded when the
+    process group is not initialised).  Each rank builds ``make(decks[member_slice(...)])`` (default:
+    ``EnsembleVlasov1D``), runs ``nsteps`` and evaluates ``diagnostics(ens) -> float64 tensor [members_here, ...]``;
+    the only communication is the final gather of those small per-member results, returned on every rank in deck order
+    (``all_gather`` on padded blocks, so it runs on NCCL and on gloo).  A rank whose slice is empty takes part in the
+    gather only."""
+    import torch.distributed as dist
+
+    sharded = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if sharded else 1
+    rank = dist.get_rank(group) if sharded else 0
+    sl = member_slice(len(decks), rank, world)
+    mine = list(decks[sl])
+    out = None
+    if mine:
+        ens = (make or EnsembleVlasov1D)(mine)
+        ens.run(nsteps)
+        out = diagnostics(ens)
+        if out.shape[0] != len(mine):
+            raise ValueError("diagnostics must return one row per member of this rank")
+    if not sharded:
+        return out
+    counts = [member_slice(len(decks), r, world) for r in range(world)]
+    counts = [c.stop - c.start for c in counts]
+    # shape of one member's result: agreed through rank 0's (every rank with members has the same trailing shape)
+    trailing = [list(out.shape[1:])] if out is not None else [None]
+    shapes = [None] * world
+    dist.all_gather_object(shapes, trailing[0], group=group)
+    tshape = next(s for s in shapes if s is not None)
+    dev = out.device if out is not None else (torch.device("cuda", torch.cuda.current_device())
+                                              if dist.get_backend(group) == "nccl" else torch.device("cpu"))
+    pad = torch.zeros((max(counts),) + tuple(tshape), dtype=torch.float64, device=dev)
+    if out is not None:
+        pad[: out.shape[0]] = out.to(torch.float64)
+    blocks = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(blocks, pad, group=group)
+    return torch.cat([b[:c] for b, c in zip(blocks, counts)], dim=0)

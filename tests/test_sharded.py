@@ -3,6 +3,7 @@ sharded leapfrog step with the numpy oracle injected as the local operator table
 oracle's own single-process step.  This covers the partitioning, both all-to-all transposes and the moment all-reduce;
 the CUDA kernels themselves are covered by the -m gpu tests."""
 
+import os
 import socket
 from copy import deepcopy
 from pathlib import Path
@@ -132,3 +133,66 @@ def _bad_worker(rank, world, port, dk):
             ShardedVlasov1D(dk, local_ops=object(), device=torch.device("cpu"))
     finally:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------ ensembles sharded by members (C4)
+def test_member_slice_covers_every_member_once():
+    from adept_b200.ensemble import member_slice
+
+    for n in (0, 1, 7, 8, 121, 1024):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                s = member_slice(n, r, world)
+                seen += list(range(s.start, s.stop))
+            assert seen == list(range(n))
+            sizes = [member_slice(n, r, world).stop - member_slice(n, r, world).start for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        member_slice(4, 2, 2)
+
+
+class _FakeEnsemble:
+    """Stands in for EnsembleVlasov1D on a CPU-only box: a 'member' is a number, a step adds its own value."""
+
+    def __init__(self, decks):
+        self.x = torch.tensor([float(d) for d in decks], dtype=torch.float64)
+        self.acc = torch.zeros_like(self.x)
+
+    def run(self, nsteps):
+        self.acc = self.acc + nsteps * self.x
+
+
+def _ensemble_worker(rank, world, port, n_members, q):
+    import torch.distributed as dist
+
+    from adept_b200.ensemble import run_sharded_ensemble
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        decks = list(range(1, n_members + 1))
+        out = run_sharded_ensemble(decks, 3, lambda e: torch.stack([e.acc, e.x], dim=1), make=_FakeEnsemble)
+        q.put((rank, out.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_members", [5, 1])
+def test_sharded_ensemble_gathers_in_deck_order_gloo(n_members):
+    """world_size 2 over gloo: uneven split (3 + 2 members) and a rank with an empty slice (1 member)."""
+    import torch.multiprocessing as mp
+
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 7 * n_members
+    procs = [ctx.Process(target=_ensemble_worker, args=(r, world, port, n_members, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = np.stack([3.0 * np.arange(1, n_members + 1), 1.0 * np.arange(1, n_members + 1)], axis=1)
+    for r in range(world):
+        np.testing.assert_array_equal(got[r], want)
