@@ -496,6 +496,177 @@ __global__ void __launch_bounds__(256) field_fused_kernel(FieldFusedArgs p) {
   if (threadIdx.x == 0 && atomicAdd(p.counter, 1u) == 4 * G - 1) *p.counter = 0u;
 }
 
+// ---- small grids / ensembles: the whole field solve of one member in one CTA ----------------------------------------
+// Replaces, for nx <= 256 (one launch instead of 3 + n_species): pond_kernel, moments_kernel per species, poisson_kernel
+// and, for the leapfrog step, ex_driver_kernel.  A 64 x 512 member is 256 KB: an ensemble of them lives in L2, the step
+// is bound by launch latency and dependent round trips, not by bandwidth (BASELINE.json configs[1] and [3]).
+// Velocity sums: one warp per row with the lane striding and rounding of moments_kernel (bit-identical densities).
+// Poisson: direct length-nx DFT sums against a W_N table in shared memory (<= 256 terms), then the reference's
+// Re(ifft(-i mult fft(rho))) (field.py:221-224, 293-298) with every mode kept.
+struct FieldMemberArgs {
+  int nsp;
+  const double* f[4];
+  int nv[4];
+  double dv[4], charge[4];
+  const double* base;  // [batch, nx] static background (nullable)
+  double* rho;         // [batch, nx]
+  int nx;
+  const double* a;     // [batch, nx + 2]
+  double* pond;
+  double dx;
+  int n_ex;            // 0: the driver field is not evaluated here
+  long long n_rows;    // batch * nx (row stride of the driver tables)
+  const double* ex_space;
+  const double* ex_kx;
+  double* dex;
+  double ex_w[8], ex_a0[8], ex_tenv[8], ex_wt[8];
+  const double* ex_w_row;
+  const double* ex_a0_row;
+  double ex_t0;
+  const double* kmul;
+  long long kmul_stride;
+  double* e;
+  int mode;
+  double Te, lambda_De;
+};
+
+__global__ void __launch_bounds__(1024) field_member_kernel(FieldMemberArgs p) {
+  __shared__ double rho_s[256];
+  __shared__ cplx w_s[256], y_s[256];
+  const int N = p.nx;
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int per_round = blockDim.x >> 2;  // outputs per round of the DFT sums (4 lanes each)
+  const long long row0 = (long long)b * N;
+  if (threadIdx.x < N) {
+    double sn, cs;
+    sincospi(-2.0 * (double)threadIdx.x / (double)N, &sn, &cs);
+    w_s[threadIdx.x] = cmake(cs, sn);
+  }
+  // ---- charge density, field.py:197-208 ----
+  for (int i = warp; i < N; i += nwarp) {
+    double acc = p.base ? p.base[row0 + i] : 0.0;
+    for (int k = 0; k < p.nsp; k++) {
+      const int nv = p.nv[k];
+      const double* fr = p.f[k] + (row0 + i) * nv;
+      double s0 = 0.0;
+      if ((nv & 1) == 0 && ((reinterpret_cast<uintptr_t>(fr) & 15) == 0)) {
+        const double2* f2 = reinterpret_cast<const double2*>(fr);
+        for (int j = lane; j < (nv >> 1); j += 32) {
+          const double2 x = f2[j];
+          s0 += x.x + x.y;
+        }
+      } else {
+        for (int j = lane; j < nv; j += 32) s0 += fr[j];
+      }
+      s0 = warp_sum(s0);
+      const double term = __dmul_rn(p.charge[k], __dmul_rn(s0, p.dv[k]));
+      acc = (k == 0 && !p.base) ? term : __dadd_rn(acc, term);
+    }
+    if (lane == 0) {
+      rho_s[i] = acc;
+      p.rho[row0 + i] = acc;
+    }
+  }
+  // ---- ponderomotive force (field.py:495) and the driver field at the first substep time (field.py:21-33) ----
+  if (threadIdx.x < N) {
+    const int i = threadIdx.x;
+    const double* a = p.a + (long long)b * (N + 2);
+    const double lo = __dmul_rn(a[i], a[i]), hi = __dmul_rn(a[i + 2], a[i + 2]);
+    p.pond[row0 + i] = __dmul_rn(-0.5, __ddiv_rn(__dsub_rn(hi, lo), __dmul_rn(2.0, p.dx)));
+    if (p.n_ex > 0) {
+      double total = 0.0;
+      for (int d = 0; d < p.n_ex; d++) {
+        const long long o = d * p.n_rows + row0 + i;
+        const double factor = __dmul_rn(p.ex_tenv[d], p.ex_space[o]);
+        const double w = p.ex_w_row ? p.ex_w_row[o] : p.ex_w[d];
+        const double a0 = p.ex_a0_row ? p.ex_a0_row[o] : p.ex_a0[d];
+        const double wt = p.ex_w_row ? __dmul_rn(w, p.ex_t0) : p.ex_wt[d];
+        const double amp = __dmul_rn(__dmul_rn(factor, w), a0);
+        total = __dadd_rn(total, __dmul_rn(amp, sin(__dsub_rn(p.ex_kx[o], wt))));
+      }
+      p.dex[row0 + i] = total;
+    }
+  }
+  __syncthreads();
+  // ---- X_k = sum_j rho_j W^(jk); 4 lanes per output, blockDim / 4 outputs per round ----
+  const int o = threadIdx.x >> 2, q4 = threadIdx.x & 3;
+  const int mask = N - 1;
+  double rho0 = 0.0;
+  if (p.mode != 0) {  // Boltzmann electrons: mean(rho)
+    for (int j = 0; j < N; j++) rho0 += rho_s[j];
+    rho0 /= (double)N;
+  }
+  const double* kmul = p.kmul + (long long)b * p.kmul_stride;
+  for (int k0 = 0; k0 < N; k0 += per_round) {
+    const int k = k0 + o;
+    cplx x = cmake(0.0, 0.0);
+    if (k < N) {
+      for (int j = q4; j < N; j += 4) {
+        const cplx w = w_s[(j * k) & mask];
+        const double r = rho_s[j];
+        x.x = fma(r, w.x, x.x), x.y = fma(r, w.y, x.y);
+      }
+    }
+    x = quad_sum(x);
+    if (k < N && q4 == 0) {
+      double mult = kmul[k];
+      if (p.mode != 0) {
+        const double kx = mult;
+        const double lam_sq = p.lambda_De < 0.0 ? p.Te / rho0 : p.lambda_De * p.lambda_De;
+        mult = kx * (p.Te / rho0) / (1.0 + lam_sq * kx * kx);
+      }
+      y_s[k] = cmake(mult * x.y, -(mult * x.x));  // -i mult X
+    }
+  }
+  __syncthreads();
+  // ---- E_i = Re sum_k Y_k conj(W^(ik)) / N ----
+  for (int i0 = 0; i0 < N; i0 += per_round) {
+    const int i = i0 + o;
+    double e = 0.0;
+    if (i < N) {
+      for (int k = q4; k < N; k += 4) {
+        const cplx w = w_s[(i * k) & mask], y = y_s[k];
+        e += y.x * w.x + y.y * w.y;
+      }
+    }
+    e += __shfl_xor_sync(0xffffffffu, e, 1);
+    e += __shfl_xor_sync(0xffffffffu, e, 2);
+    if (i < N && q4 == 0) p.e[row0 + i] = e / (double)N;
+  }
+}
+
+bool field_member_supported(int nx) { return nx >= 4 && nx <= 256 && (nx & (nx - 1)) == 0; }
+
+int field_member_f64(int nsp, const double* const* f, const int* nv, const double* dv, const double* charge,
+                     const double* base, double* rho, int batch, int nx, const double* a, double* pond, double dx,
+                     int n_ex, const double* ex_space, const double* ex_kx, double* dex, const double* ex_w,
+                     const double* ex_a0, const double* ex_tenv, const double* ex_wt, const double* ex_w_row,
+                     const double* ex_a0_row, double ex_t0, const double* kmul, long long kmul_stride, double* e,
+                     int mode, double Te, double lambda_De, cudaStream_t stream) {
+  if (!field_member_supported(nx) || batch < 1 || nsp < 1 || nsp > 4 || n_ex < 0 || n_ex > 8) {
+    set_last_error("field_member: unsupported batch=%d nx=%d n_species=%d n_ex=%d", batch, nx, nsp, n_ex);
+    return ADEPT_ERR_UNSUPPORTED;
+  }
+  FieldMemberArgs p = {};
+  p.nsp = nsp;
+  for (int k = 0; k < nsp; k++) p.f[k] = f[k], p.nv[k] = nv[k], p.dv[k] = dv[k], p.charge[k] = charge[k];
+  p.base = base, p.rho = rho, p.nx = nx, p.a = a, p.pond = pond, p.dx = dx;
+  p.n_ex = n_ex, p.n_rows = (long long)batch * nx, p.ex_space = ex_space, p.ex_kx = ex_kx, p.dex = dex;
+  for (int d = 0; d < n_ex; d++) p.ex_w[d] = ex_w[d], p.ex_a0[d] = ex_a0[d], p.ex_tenv[d] = ex_tenv[d], p.ex_wt[d] = ex_wt[d];
+  p.ex_w_row = ex_w_row, p.ex_a0_row = ex_a0_row, p.ex_t0 = ex_t0;
+  p.kmul = kmul, p.kmul_stride = kmul_stride, p.e = e, p.mode = mode, p.Te = Te, p.lambda_De = lambda_De;
+  ProfileScope prof("field_member", stream);
+  // few members: latency-bound, 32 warps per member shorten the chain of L2 round trips (121 members: 18.3 -> 14.0 us);
+  // many members: bandwidth-bound, several small CTAs per SM stream better (1024 members: 73 us against 89 us)
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int threads = (nx >= 32 && batch < 2 * sms) ? 1024 : 256;
+  field_member_kernel<<<batch, threads, 0, stream>>>(p);
+  return check_launch("field_member_kernel");
+}
+
 bool field_fused_supported(int batch, int nx) { return batch == 1 && (nx == 1024 || nx == 2048 || nx == 4096); }
 
 int field_fused_f64(int nsp, const double* const* parts, const int* nparts, const double* dv, const double* charge,

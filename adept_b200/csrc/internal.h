@@ -22,6 +22,13 @@ int bluestein_push_f64(int axis, const double* fin, double* fout, int batch, int
                        double q, double m, const double* filt, cudaStream_t stream);
 int bluestein_poisson_f64(const double* rho, const double* kmul, long long kmul_stride, double* e, int batch, int nx,
                           int mode, double Te, double lambda_De, cudaStream_t stream);
+bool field_member_supported(int nx);
+int field_member_f64(int nsp, const double* const* f, const int* nv, const double* dv, const double* charge,
+                     const double* base, double* rho, int batch, int nx, const double* a, double* pond, double dx,
+                     int n_ex, const double* ex_space, const double* ex_kx, double* dex, const double* ex_w,
+                     const double* ex_a0, const double* ex_tenv, const double* ex_wt, const double* ex_w_row,
+                     const double* ex_a0_row, double ex_t0, const double* kmul, long long kmul_stride, double* e,
+                     int mode, double Te, double lambda_De, cudaStream_t stream);
 bool field_fused_supported(int batch, int nx);
 int field_fused_f64(int nsp, const double* const* parts, const int* nparts, const double* dv, const double* charge,
                     const double* base, double* rho, int nx, const double* a, double* pond, double dx, int n_ex,

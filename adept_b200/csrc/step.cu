@@ -92,6 +92,16 @@ struct StepCtx {
     return vdfdx_tma_parts(s.batch, s.nx, s.species[0].nv) >= 4;
   }
 
+  // true when the next field_solve runs as one launch per ensemble member (field.cu: field_member_kernel): small
+  // grids, Poisson or Boltzmann-Poisson, velocity sums read from f (no partial sums from a TMA x-advection)
+  bool can_member_field(bool from_parts) const {
+    if (s.field == 2 || !field_member_supported(s.nx)) return false;
+    if (from_parts)
+      for (int k = 0; k < s.n_species; k++)
+        if (have_parts[k]) return false;
+    return true;
+  }
+
   // (pond, e) = field_solve(f); field.py:479-497.  from_parts: the velocity sums come from the preceding push_x.
   // driver_here: also evaluate the Ex driver field of substep 0 (leapfrog) in the fused launch.
   int field_solve(const double* const* cur, bool from_parts, double dt, bool driver_here = false) const {
@@ -107,6 +117,19 @@ struct StepCtx {
                              s.a, s.pond, s.dx, driver_here ? s.n_ex : 0, s.ex_space, s.ex_kx, s.dex, s.ex_w, s.ex_a0,
                              s.ex_tenv[0], s.ex_wt[0], s.kmul, s.e_out, s.field == 1 ? 1 : 0, s.Te, s.lambda_De,
                              s.sync_counter, st);
+    }
+    if (can_member_field(from_parts)) {
+      const double* fs[ADEPT_B200_MAX_SPECIES];
+      int nvs[ADEPT_B200_MAX_SPECIES];
+      double dv[ADEPT_B200_MAX_SPECIES], charge[ADEPT_B200_MAX_SPECIES];
+      for (int k = 0; k < s.n_species; k++) {
+        const adept_b200_species& sp = s.species[k];
+        fs[k] = cur[k], nvs[k] = sp.nv, dv[k] = sp.dv, charge[k] = sp.charge;
+      }
+      return field_member_f64(s.n_species, fs, nvs, dv, charge, s.field == 0 ? s.ion_charge : nullptr, s.rho, s.batch,
+                              s.nx, s.a, s.pond, s.dx, driver_here ? s.n_ex : 0, s.ex_space, s.ex_kx, s.dex, s.ex_w,
+                              s.ex_a0, s.ex_tenv[0], s.ex_wt[0], s.ex_w_row, s.ex_a0_row, s.ex_t[0], s.kmul,
+                              s.kmul_stride, s.e_out, s.field == 1 ? 1 : 0, s.Te, s.lambda_De, st);
     }
     ADEPT_TRY(ponderomotive_f64(s.a, s.pond, s.batch, s.nx, s.dx, st));
     if (s.field == 2) {  // ampere: E = E_prev - dt * sum_s q_s dv_s sum_v v f_s   (field.py:330-354)
@@ -251,8 +274,9 @@ int step_f64(const adept_b200_step& s, cudaStream_t st) {
     ADEPT_TRY(c.push_x(cur, xdst, s.dt, want_rho));
     const double* fstar[ADEPT_B200_MAX_SPECIES];
     for (int k = 0; k < s.n_species; k++) fstar[k] = xdst[k];
-    const bool fused_field = want_rho && c.can_fuse_field();
-    if (!fused_field) ADEPT_TRY(launch_drivers());
+    const bool fused_field = want_rho && (c.can_fuse_field() || c.can_member_field(true));
+    // with no driver the fused field kernels leave dex untouched: the driver kernel zero-fills it
+    if (!fused_field || s.n_ex == 0) ADEPT_TRY(launch_drivers());
     ADEPT_TRY(c.field_solve(fstar, want_rho, s.dt, fused_field));
     // the colliding species takes the fused v-push + Fokker-Planck kernel when its shape and operator allow it
     const int kc = s.collide_species;

@@ -99,6 +99,24 @@ def variants():
     d = load("multispecies_ion_acoustic")  # two species with different nv feed one fused field solve
     d["grid"].update(nx=1024)
     out["L-multispecies-1024"] = d
+    d = c2_deck()  # no Ex driver at all on a large grid: the fused field launch must still leave dex = 0
+    d["grid"].update(nx=1024, nv=512)
+    d["drivers"]["ex"] = {}
+    d["density"]["species-background"].update(basis="sine", baseline=1.0, amplitude=1.0e-2, wavenumber=0.3)
+    out["L-1024x512-no-driver"] = d
+    for nx in (64, 1024):  # configs/vlasov-1d/iaw-turbulence.yaml in miniature: kinetic ions, Boltzmann electrons,
+        d = c2_deck()      # cubic-spline v-push, sixth-order integrator, stochastic box-scale forcing, no collisions
+        d["grid"].update(nx=nx, nv=256, xmax=45.8, dt=0.25)
+        d["density"] = {"quasineutrality": True,
+                        "species-ion-background": {"noise_seed": 416, "noise_type": "gaussian", "noise_val": 0.0,
+                                                   "v0": 0.0, "T0": 1.0, "m": 2.0, "basis": "sine", "baseline": 1.0,
+                                                   "amplitude": 1.0e-3, "wavenumber": 2 * np.pi / 45.8}}
+        d["drivers"] = {"ex": {}, "ey": {}, "ex_stochastic": {"modes": [1], "amplitude": 2.0e-3, "tau": 45.8, "seed": 42}}
+        d["terms"].update(field="poisson-boltzmann", boltzmann_electrons={"Te": 0.05}, edfdv="cubic-spline", time="sixth",
+                          species=[{"name": "ion", "charge": 1.0, "mass": 1.0, "vmax": 6.4, "nv": 256,
+                                    "density_components": ["species-ion-background"]}])
+        d["terms"]["fokker_planck"]["is_on"] = False
+        out[f"iaw-like-{nx}x256"] = d
     d = c2_deck()  # self-consistent beta (Newton on the discrete temperature) in a driven step
     d["terms"]["fokker_planck"].update(type="chang_cooper_dougherty",
                                        self_consistent_beta={"enabled": True, "max_steps": 3})
