@@ -13,6 +13,7 @@
  *   adept_b200_ponderomotive_f64 ElectricFieldSolver (pond)          adept/_vlasov1d/solvers/pushers/field.py:495
  *   adept_b200_wave_step_f64     WaveSolver.__call__                 adept/_vlasov1d/solvers/pushers/field.py:109-157
  *   adept_b200_collide_f64       Collisions._apply_collisions+Krook  adept/_vlasov1d/solvers/pushers/fokker_planck.py:368-484
+ *   adept_b200_collide_sc_f64    same + find_self_consistent_beta    adept/driftdiffusion.py:161-283, fokker_planck.py:139-210
  *   adept_b200_step_f64          VlasovMaxwell.__call__ (whole step) adept/_vlasov1d/solvers/vector_field.py:55-361
  *
  * Conventions
