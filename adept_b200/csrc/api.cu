@@ -433,6 +433,12 @@ int adept_b200_poisson_f64(const double* rho, const double* kmul, long long kmul
   return poisson_dispatch_f64(rho, kmul, kmul_stride, e, batch, nx, mode, Te, lambda_De, (cudaStream_t)stream);
 }
 
+int adept_b200_field_energy_f64(const double* e0, const double* de0, const double* e1, const double* de1, double w,
+                                int batch, int nx, double* out, void* stream) {
+  ADEPT_REQUIRE(e0, "e0") ADEPT_REQUIRE(de0, "de0") ADEPT_REQUIRE(out, "out")
+  return field_energy_f64(e0, de0, e1, de1, w, batch, nx, out, (cudaStream_t)stream);
+}
+
 int adept_b200_axpy_f64(const double* a, const double* b, double s, double* out, long long n, void* stream) {
   ADEPT_REQUIRE(a, "a") ADEPT_REQUIRE(b, "b") ADEPT_REQUIRE(out, "out")
   return axpy_f64(a, b, s, out, n, (cudaStream_t)stream);

@@ -152,6 +152,48 @@ int axpy_f64(const double* a, const double* b, double s, double* out, long long 
   return check_launch("axpy_kernel");
 }
 
+// ---- field-energy scalars of the default save: out[b] = {mean(e_b^2), mean(de_b^2)}  (storage.py:316-317) ----------
+// (e0, de0) alone, or the state interpolated linearly towards (e1, de1) with weight w (diffrax's dense output)
+__global__ void __launch_bounds__(256) field_energy_kernel(const double* __restrict__ e0, const double* __restrict__ de0,
+                                                           const double* __restrict__ e1, const double* __restrict__ de1,
+                                                           double w, int nx, double* __restrict__ out) {
+  __shared__ double red[2][8];
+  const long long off = (long long)blockIdx.x * nx;
+  double s0 = 0.0, s1 = 0.0;
+  for (int i = threadIdx.x; i < nx; i += 256) {
+    double a = e0[off + i], b = de0[off + i];
+    if (e1) {
+      a = __dadd_rn(a, __dmul_rn(w, __dsub_rn(e1[off + i], a)));
+      b = __dadd_rn(b, __dmul_rn(w, __dsub_rn(de1[off + i], b)));
+    }
+    s0 = fma(a, a, s0);
+    s1 = fma(b, b, s1);
+  }
+  s0 = warp_sum(s0), s1 = warp_sum(s1);
+  if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = s0, red[1][threadIdx.x >> 5] = s1;
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double t = 0.0;
+    for (int k = 0; k < 8; k++) t += red[threadIdx.x][k];
+    out[2 * blockIdx.x + threadIdx.x] = t / (double)nx;
+  }
+}
+
+int field_energy_f64(const double* e0, const double* de0, const double* e1, const double* de1, double w, int batch,
+                     int nx, double* out, cudaStream_t stream) {
+  if (batch < 1 || nx < 1) {
+    set_last_error("field_energy: bad shape batch=%d nx=%d", batch, nx);
+    return ADEPT_ERR_BAD_SHAPE;
+  }
+  if ((e1 == nullptr) != (de1 == nullptr)) {
+    set_last_error("field_energy: give both e1 and de1 or neither");
+    return ADEPT_ERR_BAD_ARG;
+  }
+  ProfileScope prof("field_energy", stream);
+  field_energy_kernel<<<batch, 256, 0, stream>>>(e0, de0, e1, de1, w, nx, out);
+  return check_launch("field_energy_kernel");
+}
+
 // ---- second stage of the fused x-push charge density: out[i] = base[i] + scale_b * ((sum_p parts[p, i]) * scale_a) ----
 // 64 rows per CTA; the parts are dealt to 4 thread groups (p = g, g+4, ...), each with two running sums, and combined
 // in a fixed order: deterministic, and short dependent-load chains (nparts/8 per thread).

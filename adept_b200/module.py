@@ -49,8 +49,10 @@ def default_scalars(cfg, y0, y1=None, w=0.0):
         s[f"mean_n_{name}"], s[f"mean_j_{name}"], s[f"mean_P_{name}"] = mean[0], mean[1], mean[2]
         s[f"mean_q_{name}"], s[f"mean_-flogf_{name}"], s[f"mean_f2_{name}"] = mean[3], mean[4], mean[5]
         ke = ke + 0.5 * mass * mean[2]
-    s["mean_de2"] = torch.mean(_lerp(y0, y1, w, "de") ** 2.0)
-    s["mean_e2"] = torch.mean(_lerp(y0, y1, w, "e") ** 2.0)
+    from . import ops
+
+    e2 = ops.field_energy(y0["e"], y0["de"], None if y1 is None else y1["e"], None if y1 is None else y1["de"], w)
+    s["mean_e2"], s["mean_de2"] = e2[..., 0], e2[..., 1]
     a2 = _lerp(y0, y1, w, "a") ** 2.0
     s["mean_pond"] = torch.mean(-0.5 * (a2[..., 2:] - a2[..., :-2]) / (2.0 * g["dx"]))
     s["mean_kinetic_energy"] = ke

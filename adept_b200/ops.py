@@ -267,6 +267,20 @@ def poisson(rho, kmul, mode=0, Te=1.0, lambda_De=-1.0, out=None):
     return out
 
 
+def field_energy(e, de, e1=None, de1=None, w=0.0, out=None):
+    """{mean(e^2), mean(de^2)} per member in one launch (storage.py:316-317), optionally of the state interpolated
+    towards (e1, de1) with weight w.  Returns a [batch, 2] (or [2]) tensor."""
+    nx = e.shape[-1]
+    batch = e.numel() // nx
+    if out is None:
+        out = torch.empty(e.shape[:-1] + (2,), dtype=torch.float64, device=e.device)
+    rc = _lib.load().adept_b200_field_energy_f64(_ptr(e, "e"), _ptr(de, "de"), _ptr(e1, "e1", True),
+                                                 _ptr(de1, "de1", True), float(w), batch, nx, _ptr(out, "out"), _stream())
+    _lib.check(rc, "field_energy")
+    _count()
+    return out
+
+
 def axpy(a, b, s, out=None):
     """out = a + s*b (Ampere update, field.py:354)."""
     out = torch.empty_like(a) if out is None else out

@@ -190,7 +190,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
 
-    from adept_b200 import _lib
+    from adept_b200 import _lib, ops
     from adept_b200._lib import AdeptB200Error
     from adept_b200.module import Vlasov1D
 
@@ -303,7 +303,7 @@ def run_b200(args):
         sim.state[name] = f_host.to("cuda", non_blocking=True)
         for i in range(nsteps):
             st = sim.step()
-            torch.mean(torch.stack((st["e"], st["de"])) ** 2.0, dim=1, out=diag_dev[i])
+            ops.field_energy(st["e"], st["de"], out=diag_dev[i])
             diag_host[i].copy_(diag_dev[i], non_blocking=True)
         f_back.copy_(sim.state[name], non_blocking=True)
         torch.cuda.synchronize()

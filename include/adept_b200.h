@@ -156,6 +156,12 @@ int adept_b200_poisson_f64(const double* rho, const double* kmul, long long kmul
 /* out[i] = a[i] + s * b[i]  (Ampere: E = E_prev - dt j). */
 int adept_b200_axpy_f64(const double* a, const double* b, double s, double* out, long long n, void* stream);
 
+/* Field-energy scalars of the default save function (mean_e2, mean_de2; adept/_vlasov1d/storage.py:316-317), one
+ * launch: out[b] = {mean(e_b^2), mean(de_b^2)} of (e0, de0)[batch, nx], or of the state interpolated linearly towards
+ * (e1, de1) with weight w when those are given (both or neither). */
+int adept_b200_field_energy_f64(const double* e0, const double* de0, const double* e1, const double* de1, double w,
+                                int batch, int nx, double* out, void* stream);
+
 /* pond[b, i] = -0.5 (a[b, i+2]^2 - a[b, i]^2) / (2 dx); a is [batch, nx+2]. */
 int adept_b200_ponderomotive_f64(const double* a, double* pond, int batch, int nx, double dx, void* stream);
 

@@ -559,3 +559,21 @@ def test_poisson_any_even_length(ops, nx):
     rho_i = 1.0 + 0.1 * rng.standard_normal(nx)
     e = host(ops.poisson(dev(rho_i), dev(kx), mode=1, Te=2.0, lambda_De=0.7))
     assert rel_l2(e, O.boltzmann_poisson(rho_i, kx, 2.0, 0.7)) <= RTOL
+
+
+@pytest.mark.parametrize("batch,nx", [(1, 32), (1, 4096), (3, 100), (5, 7)])
+def test_field_energy_matches_numpy(ops, batch, nx):
+    """mean_e2 / mean_de2 of the default save (storage.py:316-317), plain and on the interpolated state."""
+    rng = np.random.default_rng(nx)
+    e0, de0, e1, de1 = (rng.standard_normal((batch, nx)) for _ in range(4))
+    out = host(ops.field_energy(dev(e0), dev(de0)))
+    np.testing.assert_allclose(out[:, 0], np.mean(e0**2.0, axis=1), rtol=1e-13)
+    np.testing.assert_allclose(out[:, 1], np.mean(de0**2.0, axis=1), rtol=1e-13)
+    w = 0.37
+    out = host(ops.field_energy(dev(e0), dev(de0), dev(e1), dev(de1), w))
+    np.testing.assert_allclose(out[:, 0], np.mean((e0 + w * (e1 - e0)) ** 2.0, axis=1), rtol=1e-13)
+    np.testing.assert_allclose(out[:, 1], np.mean((de0 + w * (de1 - de0)) ** 2.0, axis=1), rtol=1e-13)
+    from adept_b200._lib import AdeptB200Error
+
+    with pytest.raises(AdeptB200Error, match="both e1 and de1"):
+        ops.field_energy(dev(e0), dev(de0), dev(e1), None, w)
