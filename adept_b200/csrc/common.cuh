@@ -23,6 +23,20 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// device-wide barrier among the co-resident CTAs of this launch: tickets on a monotonic counter (target = tickets of
+// all CTAs up to and including this barrier)
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (*reinterpret_cast<volatile unsigned int*>(counter) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
 // accel = (q*e + (q^2/m)*pond)/m with the reference's rounding sequence (no FMA contraction):
 // adept/_vlasov1d/solvers/pushers/vlasov.py:83-84
 __device__ __forceinline__ double accel_of(double e, double pond, double q, double q2m, double m) {

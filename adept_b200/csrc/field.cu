@@ -311,20 +311,6 @@ struct FieldFusedArgs {
   double* scratch;  // 4 nx doubles: two nx-long complex transposition buffers of the distributed solve
 };
 
-// device-wide barrier among the co-resident CTAs of this launch: tickets on a monotonic counter (target = tickets of
-// all CTAs up to and including this barrier)
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(counter, 1u);
-    while (*reinterpret_cast<volatile unsigned int*>(counter) < target) {
-    }
-    __threadfence();
-  }
-  __syncthreads();
-}
-
 // sum over the 4 lanes q = 0..3 that share one output
 __device__ __forceinline__ cplx quad_sum(cplx v) {
   v.x += __shfl_xor_sync(0xffffffffu, v.x, 1), v.y += __shfl_xor_sync(0xffffffffu, v.y, 1);
@@ -692,7 +678,15 @@ int field_fused_f64(int nsp, const double* const* parts, const int* nparts, cons
   p.po = PoissonArgs{rho, kmul, 0, e, mode, Te, lambda_De, nullptr, 0};
   p.counter = counter;
   ProfileScope prof("field_fused", stream);
-  field_fused_kernel<<<nx / 64, 256, 0, stream>>>(p);
+  // cooperative launch: the ticket barriers need all nx/64 CTAs resident whatever other streams are running
+  void* args[1] = {&p};
+  cudaError_t err = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(field_fused_kernel), dim3(nx / 64), dim3(256),
+                                                args, 0, stream);
+  if (err != cudaSuccess) {
+    set_last_error("cudaLaunchCooperativeKernel(field_fused): %s", cudaGetErrorString(err));
+    (void)cudaGetLastError();
+    return ADEPT_ERR_CUDA;
+  }
   return check_launch("field_fused_kernel");
 }
 

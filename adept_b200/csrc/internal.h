@@ -67,10 +67,31 @@ int vpush_collide_f64(const double* fin, double* fout, int batch, int nx, int nv
 bool tma_available();
 int encode_map_2d(CUtensorMap* map, const double* base, unsigned long long dim0, unsigned long long dim1,
                   unsigned long long pitch_bytes, unsigned box0, unsigned box1, int swizzle128);
+// Field solve folded into the tail of the TMA x-advection (vdfdx_tma.cu): after its last tile every persistent CTA
+// joins a device-wide barrier, finishes the charge density of its slice of x from the per-CTA partial rows, evaluates
+// the ponderomotive force and the driver there, and after a second barrier solves Poisson's equation for its slice as a
+// circular convolution with the Green's function green = Re ifft(-i / kx) (field.py:221-224 is linear in rho).
+struct FieldTail {
+  unsigned int* counter;  // one zero-initialised word; re-armed by the CTA that exits last
+  const double* base;     // static ion background (nullable)
+  double dv, charge;
+  double* rho;
+  double* e;
+  const double* green;    // [nx]
+  const double* a;        // [nx + 2]
+  double* pond;
+  double dx;
+  int n_ex;               // 0: the driver field is not evaluated here
+  const double* ex_space;
+  const double* ex_kx;
+  double* dex;
+  double ex_w[8], ex_a0[8], ex_tenv[8], ex_wt[8];
+};
 bool vdfdx_tma_supported(const double* fin, const double* fout, int nx, int nv);
 int vdfdx_tma_parts(int batch, int nx, int nv);
 int vdfdx_tma_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* v, double dt,
                   const double* k1_batch, double k1, double* partial, cudaStream_t stream,
-                  const double* filt = nullptr);
+                  const double* filt = nullptr, const FieldTail* field = nullptr);
+bool vdfdx_tma_field_supported(int batch, int nx, int nv);
 
 }  // namespace adept

@@ -57,9 +57,33 @@ struct StepCtx {
   cudaStream_t st;
   long long n;  // batch * nx
   mutable bool have_parts[ADEPT_B200_MAX_SPECIES] = {false, false, false, false};  // set by the last push_x
+  mutable bool field_done = false;  // set by push_x when the field solve ran in the tail of the x-advection launch
+
+  // one species, one member, plain Poisson, a large power-of-two grid: the x-advection launch also solves the field
+  bool can_tail_field(const double* fin, const double* fout) const {
+    const adept_b200_species& sp = s.species[0];
+    return s.n_species == 1 && s.field == 0 && s.sync_counter && s.poisson_green && sp.rho_parts &&
+           vdfdx_tma_supported(fin, fout, s.nx, sp.nv) && sp.rho_nparts >= vdfdx_tma_parts(s.batch, s.nx, sp.nv) &&
+           vdfdx_tma_field_supported(s.batch, s.nx, sp.nv);
+  }
 
   // x-advection of every species, cur[k] -> dst[k]; accumulates the charge-density partial sums when `want_rho`
-  int push_x(const double* const* cur, double* const* dst, double dt, bool want_rho) const {
+  int push_x(const double* const* cur, double* const* dst, double dt, bool want_rho, bool driver_here = false) const {
+    field_done = false;
+    if (want_rho && can_tail_field(cur[0], dst[0])) {
+      const adept_b200_species& sp = s.species[0];
+      FieldTail ft = {};
+      ft.counter = s.sync_counter, ft.base = s.ion_charge, ft.dv = sp.dv, ft.charge = sp.charge;
+      ft.rho = s.rho, ft.e = s.e_out, ft.green = s.poisson_green, ft.a = s.a, ft.pond = s.pond, ft.dx = s.dx;
+      ft.n_ex = driver_here ? s.n_ex : 0, ft.ex_space = s.ex_space, ft.ex_kx = s.ex_kx, ft.dex = s.dex;
+      for (int d = 0; d < s.n_ex; d++)
+        ft.ex_w[d] = s.ex_w[d], ft.ex_a0[d] = s.ex_a0[d], ft.ex_tenv[d] = s.ex_tenv[0][d], ft.ex_wt[d] = s.ex_wt[0][d];
+      ADEPT_TRY(vdfdx_tma_f64(cur[0], dst[0], s.batch, s.nx, sp.nv, sp.v, dt, s.k1x_batch, s.k1x, sp.rho_parts, st,
+                              nullptr, &ft));
+      have_parts[0] = true;
+      field_done = true;
+      return ADEPT_OK;
+    }
     for (int k = 0; k < s.n_species; k++) {
       const adept_b200_species& sp = s.species[k];
       have_parts[k] = false;
@@ -105,6 +129,10 @@ struct StepCtx {
   // (pond, e) = field_solve(f); field.py:479-497.  from_parts: the velocity sums come from the preceding push_x.
   // driver_here: also evaluate the Ex driver field of substep 0 (leapfrog) in the fused launch.
   int field_solve(const double* const* cur, bool from_parts, double dt, bool driver_here = false) const {
+    if (from_parts && field_done) {  // already solved in the tail of the x-advection launch
+      field_done = false;
+      return ADEPT_OK;
+    }
     if (from_parts && can_fuse_field()) {
       const double* parts[ADEPT_B200_MAX_SPECIES];
       int nparts[ADEPT_B200_MAX_SPECIES];
@@ -271,10 +299,12 @@ int step_f64(const adept_b200_step& s, cudaStream_t st) {
     // leapfrog (vector_field.py:87-95): f* = vdfdx(f); (pond, e) = field(f*); f' = edfdv(f*, e + dex[0], pond)
     const bool want_rho = s.field != 2;
     double* const* xdst = spline ? tmp : out;  // the cubic stencil cannot run in place
-    ADEPT_TRY(c.push_x(cur, xdst, s.dt, want_rho));
+    // the driver field of per-row parameter scans (ex_w_row) is only evaluated by the driver kernel
+    ADEPT_TRY(c.push_x(cur, xdst, s.dt, want_rho, s.n_ex > 0 && !s.ex_w_row && !s.ex_a0_row));
     const double* fstar[ADEPT_B200_MAX_SPECIES];
     for (int k = 0; k < s.n_species; k++) fstar[k] = xdst[k];
-    const bool fused_field = want_rho && (c.can_fuse_field() || c.can_member_field(true));
+    const bool tail_driver = c.field_done && s.n_ex > 0 && !s.ex_w_row && !s.ex_a0_row;
+    const bool fused_field = tail_driver || (!c.field_done && want_rho && (c.can_fuse_field() || c.can_member_field(true)));
     // with no driver the fused field kernels leave dex untouched: the driver kernel zero-fills it
     if (!fused_field || s.n_ex == 0) ADEPT_TRY(launch_drivers());
     ADEPT_TRY(c.field_solve(fstar, want_rho, s.dt, fused_field));

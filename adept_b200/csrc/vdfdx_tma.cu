@@ -34,6 +34,7 @@ struct TmaPushArgs {
   int zero;
   double* partial;      // [gridDim.x, batch*nx] per-CTA row sums of f_out, or null
   const double* filt;   // nullable [N/2+1]: real multiplier per mode (Hou-Li filter)
+  FieldTail ft;         // used by the FIELD instantiation only
 };
 
 template <int LOGN>
@@ -50,7 +51,7 @@ struct TmaCfg {
   static constexpr size_t SMEM = BUF_BYTES + PH_BYTES + ACC_BYTES + 16;
 };
 
-template <int LOGN>
+template <int LOGN, bool FIELD = false>
 __global__ void __launch_bounds__(TmaCfg<LOGN>::THREADS, 1)
     vdfdx_tma_kernel(const __grid_constant__ CUtensorMap in_map, TmaPushArgs p) {
   using K = TmaCfg<LOGN>;
@@ -147,6 +148,92 @@ __global__ void __launch_bounds__(TmaCfg<LOGN>::THREADS, 1)
     }
   }
   if (p.partial && cur_b >= 0) flush_rho(cur_b);
+
+  if constexpr (FIELD) {
+    // ---- field solve in the tail (batch == 1, one species): see FieldTail in internal.h ---------------------------
+    // Every global load of a phase is issued before its first use (the phases are chains of L2 round trips otherwise).
+    const FieldTail& ft = p.ft;
+    const unsigned int G = gridDim.x;
+    double* rho_s = reinterpret_cast<double*>(tile);  // the exchange buffer is dead: rho[N] | green[N]
+    double* g_s = rho_s + N;
+    double* red = rho_acc;                            // [NGRP groups][32 columns], dead after the last flush
+    constexpr int NGRP = K::THREADS / 32;
+    constexpr int PER_T = N / K::THREADS;             // 8 grid points per thread
+    const int colr = tid & 31, grp = tid >> 5;        // warp `grp` sums the partial rows grp, grp + NGRP, ...
+    {  // the Green's function does not depend on this step: fetched while the slowest CTAs finish their tiles
+      double gv[PER_T];
+#pragma unroll
+      for (int u = 0; u < PER_T; u++) gv[u] = __ldg(ft.green + tid + u * K::THREADS);
+#pragma unroll
+      for (int u = 0; u < PER_T; u++) g_s[tid + u * K::THREADS] = gv[u];
+    }
+    grid_barrier(ft.counter, G);  // every CTA's partial row is complete
+    const int per = (N + (int)G - 1) / (int)G;
+    const int i_lo = (int)blockIdx.x * per, i_hi = min(N, i_lo + per);
+    for (int c0 = i_lo; c0 < i_hi; c0 += 32) {
+      const int i = c0 + colr;
+      double s0 = 0.0, s1 = 0.0;
+      if (i < i_hi) {
+        for (unsigned int q0 = grp; q0 < G; q0 += 10 * NGRP) {
+          double x[10];
+#pragma unroll
+          for (int u = 0; u < 10; u++) {
+            const unsigned int q = q0 + u * NGRP;
+            x[u] = q < G ? __ldcg(p.partial + (size_t)q * N + i) : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 10; u += 2) s0 += x[u], s1 += x[u + 1];
+        }
+      }
+      __syncthreads();
+      red[grp * 32 + colr] = s0 + s1;
+      __syncthreads();
+      if (grp == 0 && i < i_hi) {
+        double tot = 0.0;
+#pragma unroll
+        for (int g2 = 0; g2 < NGRP; g2++) tot += red[g2 * 32 + colr];
+        const double term = __dmul_rn(ft.charge, __dmul_rn(tot, ft.dv));  // field.py:197-208
+        ft.rho[i] = ft.base ? __dadd_rn(ft.base[i], term) : term;
+      }
+      if (grp == 1 && i < i_hi) {
+        const double lo = __dmul_rn(ft.a[i], ft.a[i]), hi = __dmul_rn(ft.a[i + 2], ft.a[i + 2]);
+        ft.pond[i] = __dmul_rn(-0.5, __ddiv_rn(__dsub_rn(hi, lo), __dmul_rn(2.0, ft.dx)));  // field.py:495
+      }
+      if (grp == 2 % NGRP && i < i_hi && ft.n_ex > 0) {  // field.py:21-33
+        double total = 0.0;
+        for (int d = 0; d < ft.n_ex; d++) {
+          const double factor = __dmul_rn(ft.ex_tenv[d], ft.ex_space[(size_t)d * N + i]);
+          const double amp = __dmul_rn(__dmul_rn(factor, ft.ex_w[d]), ft.ex_a0[d]);
+          total = __dadd_rn(total, __dmul_rn(amp, sin(__dsub_rn(ft.ex_kx[(size_t)d * N + i], ft.ex_wt[d]))));
+        }
+        ft.dex[i] = total;
+      }
+    }
+    grid_barrier(ft.counter, 2 * G);  // rho complete on every CTA
+    {
+      double rv[PER_T];
+#pragma unroll
+      for (int u = 0; u < PER_T; u++) rv[u] = __ldcg(ft.rho + tid + u * K::THREADS);
+#pragma unroll
+      for (int u = 0; u < PER_T; u++) rho_s[tid + u * K::THREADS] = rv[u];
+    }
+    __syncthreads();
+    // E_i = sum_j green[(i - j) mod N] rho_j: one warp per output, lanes stride j, four running sums
+    for (int i = i_lo + grp; i < i_hi; i += NGRP) {
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll 4
+      for (int j = colr; j < N; j += 128) {  // N is a multiple of 128
+        a0 = fma(g_s[(i - j) & (N - 1)], rho_s[j], a0);
+        a1 = fma(g_s[(i - j - 32) & (N - 1)], rho_s[j + 32], a1);
+        a2 = fma(g_s[(i - j - 64) & (N - 1)], rho_s[j + 64], a2);
+        a3 = fma(g_s[(i - j - 96) & (N - 1)], rho_s[j + 96], a3);
+      }
+      const double e = warp_sum((a0 + a1) + (a2 + a3));
+      if (colr == 0) ft.e[i] = e;
+    }
+    __syncthreads();
+    if (tid == 0 && atomicAdd(ft.counter, 1u) == 3 * G - 1) *ft.counter = 0u;  // last one out re-arms the counter
+  }
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
@@ -216,13 +303,13 @@ static int tma_ctas(int ntiles) {
   return grid < ntiles ? grid : ntiles;
 }
 
-template <int LOGN>
-static int launch_tma(const CUtensorMap& map, TmaPushArgs p, int grid, cudaStream_t stream) {
+template <int LOGN, bool FIELD = false>
+static int launch_tma(const CUtensorMap& map, const TmaPushArgs& p, int grid, cudaStream_t stream) {
   using K = TmaCfg<LOGN>;
   static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
-  auto kern = vdfdx_tma_kernel<LOGN>;
+  auto kern = vdfdx_tma_kernel<LOGN, FIELD>;
   if (dev < 64 && !configured[dev]) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
     if (err != cudaSuccess) {
@@ -231,7 +318,20 @@ static int launch_tma(const CUtensorMap& map, TmaPushArgs p, int grid, cudaStrea
     }
     configured[dev] = true;
   }
-  ProfileScope prof("vdfdx_tma", stream);
+  ProfileScope prof(FIELD ? "vdfdx_tma_field" : "vdfdx_tma", stream);
+  if (FIELD) {
+    // cooperative launch: the device-wide barriers of the field tail need every CTA resident at once, and only this
+    // launch mode guarantees it when kernels of other streams compete for the SMs (no deadlock by construction)
+    void* args[2] = {const_cast<CUtensorMap*>(&map), const_cast<TmaPushArgs*>(&p)};
+    cudaError_t err = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3(grid), dim3(K::THREADS), args,
+                                                  K::SMEM, stream);
+    if (err != cudaSuccess) {
+      set_last_error("cudaLaunchCooperativeKernel(vdfdx_tma + field): %s", cudaGetErrorString(err));
+      (void)cudaGetLastError();
+      return ADEPT_ERR_CUDA;
+    }
+    return check_launch("vdfdx_tma_kernel(field)");
+  }
   kern<<<grid, K::THREADS, K::SMEM, stream>>>(map, p);
   return check_launch("vdfdx_tma_kernel");
 }
@@ -266,8 +366,44 @@ int vdfdx_tma_parts(int batch, int nx, int nv) {
 }
 
 // partial: [vdfdx_tma_parts(), batch*nx] zero-initialised by the caller (or null)
+// the field tail needs every CTA of the launch co-resident (device-wide barriers), a single member and enough rows of
+// the exchange buffer for rho + green (2 nx doubles <= the tile)
+template <int LOGN>
+static bool field_grid_fits(int grid) {  // cached per (device, LOGN): resident CTAs of the FIELD instantiation
+  using K = TmaCfg<LOGN>;
+  static int resident[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 64) return false;
+  if (resident[dev] == 0) {
+    auto kern = vdfdx_tma_kernel<LOGN, true>;
+    int per_sm = 0, sms = 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K::THREADS, K::SMEM) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+      (void)cudaGetLastError();
+      resident[dev] = -1;
+    } else {
+      resident[dev] = per_sm * sms > 0 ? per_sm * sms : -1;
+    }
+  }
+  return resident[dev] > 0 && grid <= resident[dev];
+}
+
+bool vdfdx_tma_field_supported(int batch, int nx, int nv) {
+  if (batch != 1 || nv % 4 != 0 || get_encoder() == nullptr) return false;
+  const int grid = vdfdx_tma_parts(batch, nx, nv);
+  switch (nx) {  // the device-wide barriers need the whole grid resident at once
+    case 1024: return field_grid_fits<10>(grid);
+    case 2048: return field_grid_fits<11>(grid);
+    case 4096: return field_grid_fits<12>(grid);
+    default: return false;
+  }
+}
+
 int vdfdx_tma_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* v, double dt,
-                  const double* k1_batch, double k1, double* partial, cudaStream_t stream, const double* filt) {
+                  const double* k1_batch, double k1, double* partial, cudaStream_t stream, const double* filt,
+                  const FieldTail* field) {
   const int logn = ilog2_exact_(nx);
   CUtensorMap map;
   const int box_rows = nx < 256 ? nx : 256;
@@ -279,6 +415,19 @@ int vdfdx_tma_f64(const double* fin, double* fout, int batch, int nx, int nv, co
   p.tw = get_twiddles(logn);
   if (!p.tw) return ADEPT_ERR_CUDA;
   const int grid = vdfdx_tma_parts(batch, nx, nv);
+  if (field) {
+    if (!vdfdx_tma_field_supported(batch, nx, nv) || !partial || !field->counter || !field->green || !field->rho ||
+        !field->e || !field->a || !field->pond || field->n_ex < 0 || field->n_ex > 8) {
+      set_last_error("vdfdx(tma + field): unsupported batch=%d nx=%d nv=%d or missing buffers", batch, nx, nv);
+      return ADEPT_ERR_UNSUPPORTED;
+    }
+    p.ft = *field;
+    switch (logn) {
+      case 10: return launch_tma<10, true>(map, p, grid, stream);
+      case 11: return launch_tma<11, true>(map, p, grid, stream);
+      default: return launch_tma<12, true>(map, p, grid, stream);
+    }
+  }
   switch (logn) {
     case 8: return launch_tma<8>(map, p, grid, stream);
     case 9: return launch_tma<9>(map, p, grid, stream);

@@ -7,6 +7,8 @@ is a map y -> y' exactly like the reference's (adept/_base_.py:37-41).
 
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -232,6 +234,11 @@ class NativeStep:
                 st.ion_charge = self._table(("ion", batch), lambda: np.broadcast_to(
                     np.asarray(fs.static_charge_density, dtype=np.float64), (batch, nx)), dev).data_ptr()
             st.kmul = self._table("kmul", lambda: fs.kmul, dev).data_ptr()
+            if batch == 1 and os.environ.get("ADEPT_B200_FIELD_TAIL", "1") != "0":
+                # Green's function of E = Re ifft(-i (1/kx) fft(rho)) (field.py:221-224): the x-advection launch of a
+                # large one-species grid solves the field in its tail as a circular convolution with it
+                st.poisson_green = self._table("green", lambda: np.real(np.fft.ifft(
+                    -1j * np.asarray(fs.kmul, dtype=np.float64))), dev).data_ptr()
         elif self.field == 1:
             st.kmul = self._table("kmul", lambda: fs.kmul, dev).data_ptr()
             st.Te, st.lambda_De = fs.Te, fs.lambda_De

@@ -170,7 +170,7 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------ B200 arm
 # algorithmic bytes per cell and launch: one fp64 read + one fp64 write of f per operator application;
 # the fused v-push + collision kernel performs two operator applications per launch (it moves 16 B/cell)
-FULL_PASS = {"vdfdx": 16.0, "vdfdx_tma": 16.0, "edfdv_exp": 16.0, "edfdv_spline": 16.0, "collide": 16.0,
+FULL_PASS = {"vdfdx": 16.0, "vdfdx_tma": 16.0, "vdfdx_tma_field": 16.0, "edfdv_exp": 16.0, "edfdv_spline": 16.0, "collide": 16.0,
              "vpush_collide": 32.0}
 
 
@@ -283,7 +283,11 @@ def run_b200(args):
                 "operator_applications_per_launch": FULL_PASS[dom] / 16.0,
                 "kernel_timing": "CUDA events around every launch in a second pass of the same K steps",
                 "ms_per_step_with_events": elapsed_prof / K * 1e3,
-                "step_frac_of_48B_roofline": (48.0 * cells / (elapsed / K) / 1e9) / peak}
+                "step_frac_of_48B_roofline": (48.0 * cells / (elapsed / K) / 1e9) / peak,
+                # the same figure for every full-pass kernel of the step (the two big kernels are within 1 % of each
+                # other, so which one is "dominant" can flip from run to run)
+                "per_kernel_frac": {k: FULL_PASS[k] * cells / (v["avg_us"] * 1e-6) / 1e9 / peak
+                                    for k, v in full_pass.items()}}
 
     # ---- e2e: a K-step run through the public API starting and ending in HOST memory -------------------------------
     # timed region: H2D of the initial distribution from pinned memory, K x (step + D2H of the two field-energy

@@ -283,6 +283,11 @@ typedef struct adept_b200_step {
    * (0 = off, the default), rtol, atol */
   int fp_sc_steps;
   double fp_sc_rtol, fp_sc_atol;
+  /* Green's function of the Poisson solve, green[nx] = Re ifft(-i / kx) (nullable).  When given together with
+   * sync_counter, a single large one-species grid (batch == 1, nx in {1024, 2048, 4096}, field = poisson) solves the
+   * field in the tail of the x-advection launch: E = green (*) rho as a circular convolution (field.py:221-224 is
+   * linear in rho), no separate field launch. */
+  const double* poisson_green;
 } adept_b200_step;
 
 int adept_b200_step_f64(const adept_b200_step* step, void* stream);
