@@ -211,3 +211,37 @@ def test_free_running_energy_history(name):
         np.testing.assert_allclose(g, r, rtol=1e-9, atol=1e-9 * np.max(np.abs(r)), err_msg=key)
     f_ref = O.run(cfg, nsteps=0)[0]  # shapes only
     assert sim.state["electron"].shape == f_ref["electron"].shape
+
+
+def test_c3_full_size_free_running_parity():
+    """BASELINE.json configs[2] at its FULL size (4096 x 4096, the bench workload, two launches per step: x-advection
+    with the field solve in its tail, fused v-push + collisions): three free-running steps from t = 30 (driver on)
+    against the oracle; every state entry to 1e-12, the field energy to 1e-9."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import sys
+
+    sys.path.insert(0, str(GOLD.parents[1]))
+    from bench import c3_deck
+
+    from adept_b200.module import Vlasov1D
+
+    deck = c3_deck(4096, 4096)
+    sim = Vlasov1D(deepcopy(deck))
+    cfg = O.build_cfg(deepcopy(deck))
+    vf = O.VlasovMaxwell(cfg)
+    y = O.init_state(cfg)
+    dt = cfg["grid"]["dt"]
+    t0 = 30.0
+    sim.t, sim.step_index = t0, int(round(t0 / dt))
+    for n in range(3):
+        y = vf(t0 + n * dt, y, None)
+        sim.step()
+    for k in ("electron", "de", "a", "prev_a"):
+        assert rel_l2(sim.state[k].cpu().numpy(), y[k]) <= 1e-12, k
+    e_gpu = sim.state["e"].cpu().numpy()
+    assert np.max(np.abs(e_gpu - y["e"])) <= 1e-12 * max(np.max(np.abs(y["e"])), 1e-3)
+    assert abs(np.mean(e_gpu**2) - np.mean(y["e"] ** 2)) <= 1e-9 * np.mean(y["e"] ** 2)
+    from adept_b200 import ops
+
+    assert ops.LAUNCHES > 0
