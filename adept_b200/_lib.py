@@ -48,6 +48,7 @@ class Step(C.Structure):
         ("ex_w_row", c_dp), ("ex_a0_row", c_dp), ("ex_t", c_d * MAX_SUBSTEPS),
         ("fp_sc_steps", c_i), ("fp_sc_rtol", c_d), ("fp_sc_atol", c_d),
         ("poisson_green", c_dp),
+        ("diag_vlasov_dfdt", c_dp), ("diag_fp_dfdt", c_dp), ("diag_species", c_i), ("hou_li_filt", c_dp),
     ]
 
 

@@ -42,6 +42,7 @@ int collide_f64(const double* fin, double* fout, int batch, int nx, int nv, cons
                 const double* nu_fp, const double* nu_K, const double* f_mx, int model, int scheme, int nodrag,
                 double sg_m, double sg_ratio, double* n_out, double nu_fp_scale, double nu_K_scale,
                 cudaStream_t stream, int sc_steps = 0, double sc_rtol = 1e-8, double sc_atol = 1e-12);
+int diff_over_dt_f64(const double* a, const double* b, double dt, double* out, long long n, cudaStream_t stream);
 int field_energy_f64(const double* e0, const double* de0, const double* e1, const double* de1, double w, int batch,
                      int nx, double* out, cudaStream_t stream);
 int reduce_parts_f64(const double* parts, int nparts, long long n, double scale_a, double scale_b, const double* base,

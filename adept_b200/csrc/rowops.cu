@@ -152,6 +152,22 @@ int axpy_f64(const double* a, const double* b, double s, double* out, long long 
   return check_launch("axpy_kernel");
 }
 
+// ---- dfdt diagnostics: out = (a - b) / dt with the reference's rounding (vector_field.py:245-250); out may alias b ----
+__global__ void diff_over_dt_kernel(const double* __restrict__ a, const double* b, double dt, double* out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long j = i; j < n; j += stride) out[j] = __ddiv_rn(__dsub_rn(a[j], b[j]), dt);
+}
+
+int diff_over_dt_f64(const double* a, const double* b, double dt, double* out, long long n, cudaStream_t stream) {
+  if (n < 1) return ADEPT_OK;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  ProfileScope prof("diff_over_dt", stream);
+  diff_over_dt_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a, b, dt, out, n);
+  return check_launch("diff_over_dt_kernel");
+}
+
 // ---- field-energy scalars of the default save: out[b] = {mean(e_b^2), mean(de_b^2)}  (storage.py:316-317) ----------
 // (e0, de0) alone, or the state interpolated linearly towards (e1, de1) with weight w (diffrax's dense output)
 __global__ void __launch_bounds__(256) field_energy_kernel(const double* __restrict__ e0, const double* __restrict__ de0,

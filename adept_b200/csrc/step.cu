@@ -255,6 +255,10 @@ static int validate(const adept_b200_step& s) {
     set_last_error("step: collision operators need their nu profile (and f_mx for Krook)");
     return ADEPT_ERR_BAD_ARG;
   }
+  if ((s.diag_vlasov_dfdt || s.diag_fp_dfdt) && (s.diag_species < 0 || s.diag_species >= s.n_species)) {
+    set_last_error("step: diag_species=%d out of range", s.diag_species);
+    return ADEPT_ERR_BAD_ARG;
+  }
   if (s.wave_on && (!s.prev_a || !s.djy || !s.a_out || (s.electron_species >= 0 && (!s.ne_n || !s.ne_np1)))) {
     set_last_error("step: wave_on needs prev_a, djy, a_out and the ne_n / ne_np1 scratch");
     return ADEPT_ERR_BAD_ARG;
@@ -293,6 +297,7 @@ int step_f64(const adept_b200_step& s, cudaStream_t st) {
   double* tmp[ADEPT_B200_MAX_SPECIES];
   for (int k = 0; k < s.n_species; k++) cur[k] = s.species[k].f_in, out[k] = s.species[k].f_out, tmp[k] = s.species[k].f_tmp;
   const bool spline = s.edfdv == 1;
+  const bool want_diag = s.diag_vlasov_dfdt || s.diag_fp_dfdt;  // the diagnostics need the intermediate f_vlasov
   bool collided = false;  // set when the fused v-push + collision kernel already applied the operator
 
   if (s.time_integrator == 0) {
@@ -310,7 +315,7 @@ int step_f64(const adept_b200_step& s, cudaStream_t st) {
     ADEPT_TRY(c.field_solve(fstar, want_rho, s.dt, fused_field));
     // the colliding species takes the fused v-push + Fokker-Planck kernel when its shape and operator allow it
     const int kc = s.collide_species;
-    if (s.fp_on && !s.krook_on && !spline && s.fp_sc_steps == 0 && kc >= 0 && kc < s.n_species &&
+    if (s.fp_on && !s.krook_on && !spline && s.fp_sc_steps == 0 && !want_diag && kc >= 0 && kc < s.n_species &&
         vpush_collide_supported(s.nx, s.species[kc].nv, s.fp_model, s.fp_scheme, s.fp_nodrag)) {
       for (int k = 0; k < s.n_species; k++) {
         const adept_b200_species& sp = s.species[k];
@@ -363,6 +368,19 @@ int step_f64(const adept_b200_step& s, cudaStream_t st) {
     }
   }
 
+  // dfdt diagnostics of the reference species (vector_field.py:245-250) around the collision step
+  const adept_b200_species* dsp = want_diag ? &s.species[s.diag_species] : nullptr;
+  const long long n_diag = want_diag ? c.n * dsp->nv : 0;
+  if (s.diag_vlasov_dfdt) ADEPT_TRY(diff_over_dt_f64(dsp->f_out, dsp->f_in, s.dt, s.diag_vlasov_dfdt, n_diag, st));
+  if (s.diag_fp_dfdt) {  // keep f_vlasov in the output buffer until f_fp exists
+    cudaError_t err = cudaMemcpyAsync(s.diag_fp_dfdt, dsp->f_out, (size_t)n_diag * sizeof(double),
+                                      cudaMemcpyDeviceToDevice, st);
+    if (err != cudaSuccess) {
+      set_last_error("step: cudaMemcpyAsync(diag-fp-dfdt): %s", cudaGetErrorString(err));
+      return ADEPT_ERR_CUDA;
+    }
+  }
+
   // collisions on the reference species, in place (vector_field.py:238)
   if ((s.fp_on || s.krook_on) && !collided) {
     const adept_b200_species& sp = s.species[s.collide_species];
@@ -371,6 +389,20 @@ int step_f64(const adept_b200_step& s, cudaStream_t st) {
                           s.sg_ratio, nullptr, s.nu_fp_time, s.nu_K_time, st, s.fp_sc_steps, s.fp_sc_rtol,
                           s.fp_sc_atol));
   }
+
+  // Hou-Li filter on every species (vector_field.py:240-241): the x-advection kernels with dt = 0 (unit phases) and
+  // the real per-mode multiplier, in place
+  if (s.hou_li_filt) {
+    for (int k = 0; k < s.n_species; k++) {
+      const adept_b200_species& sp = s.species[k];
+      if (vdfdx_tma_supported(sp.f_out, sp.f_out, s.nx, sp.nv))
+        ADEPT_TRY(vdfdx_tma_f64(sp.f_out, sp.f_out, s.batch, s.nx, sp.nv, sp.v, 0.0, nullptr, 0.0, nullptr, st,
+                                s.hou_li_filt));
+      else
+        ADEPT_TRY(vdfdx_f64(sp.f_out, sp.f_out, s.batch, s.nx, sp.nv, sp.v, 0.0, nullptr, 0.0, st, s.hou_li_filt));
+    }
+  }
+  if (s.diag_fp_dfdt) ADEPT_TRY(diff_over_dt_f64(dsp->f_out, s.diag_fp_dfdt, s.dt, s.diag_fp_dfdt, n_diag, st));
 
   if (wave) {  // vector_field.py:340-347
     if (wave_density) ADEPT_TRY(c.electron_density(s.species[s.electron_species].f_out, s.ne_np1));

@@ -64,7 +64,8 @@ class EnsembleVlasov1D:
             raise NotImplementedError("ensembles with the stochastic Ex driver are not implemented")
         if any(vm.has_ey for vm in self.vms):
             raise NotImplementedError("ensembles with transverse (Ey) drivers are not implemented")
-        if not all(NativeStep.supported(vm) for vm in self.vms) or cfg0["terms"]["field"] not in ("poisson",):
+        if (not all(NativeStep.supported(vm) for vm in self.vms) or cfg0["terms"]["field"] not in ("poisson",)
+                or any(vm.vpfp.vlasov_dfdt or vm.vpfp.fp_dfdt or vm.vpfp.hou_li_filter_on for vm in self.vms)):
             raise NotImplementedError("ensembles need field=poisson and no dfdt diagnostics / Hou-Li filter")
         self.n_ex = _same([len(vm.ex_driver.drivers) for vm in self.vms], "the number of Ex drivers")
         if self.n_ex > _lib.MAX_DRIVERS:

@@ -156,8 +156,9 @@ class NativeStep:
     """Fills ``struct adept_b200_step`` and calls ``adept_b200_step_f64``: the whole step is enqueued by native code.
 
     Built once per VlasovMaxwell; per step only the O(1) time factors (driver envelopes / phases, collision-frequency
-    time envelopes) are evaluated on the host.  Not used when a dfdt diagnostic or the Hou-Li filter is on (those
-    need intermediate distributions): VlasovMaxwell then composes the step from the operator objects instead."""
+    time envelopes) are evaluated on the host.  The dfdt diagnostics and the Hou-Li filter are part of the native
+    step; VlasovMaxwell composes the step from the operator objects only for the Hamiltonian Ampere solver and when
+    the caller supplies the per-step inputs itself."""
 
     FIELD = {"poisson": 0, "poisson-boltzmann": 1, "ampere": 2}
 
@@ -179,8 +180,7 @@ class NativeStep:
     @staticmethod
     def supported(vm) -> bool:
         cfg = vm.cfg
-        return (not vm.vpfp.vlasov_dfdt and not vm.vpfp.fp_dfdt and not vm.vpfp.hou_li_filter_on
-                and cfg["terms"]["field"] in NativeStep.FIELD and cfg["terms"]["edfdv"] in ("exponential", "cubic-spline")
+        return (cfg["terms"]["field"] in NativeStep.FIELD and cfg["terms"]["edfdv"] in ("exponential", "cubic-spline")
                 and len(cfg["grid"]["species_grids"]) <= _lib.MAX_SPECIES
                 and len(vm.ex_driver.drivers) <= _lib.MAX_DRIVERS)
 
@@ -273,6 +273,10 @@ class NativeStep:
             st.nu_K_space = self._table(("nu_K", batch), lambda: np.broadcast_to(
                 vm.nu_K_prof.space_envelope(vm._x) * np.ones(nx), (batch, nx)), dev).data_ptr()
         st.f_mx = self._table("f_mx", lambda: fp.f_mx, dev).data_ptr()
+        if vm.vpfp.hou_li_filter_on:
+            st.hou_li_filt = self._table("hou_li", lambda: vm.vpfp.hou_li_filter.filter_x, dev).data_ptr()
+        ref = "electron" if "electron" in self.names else self.names[0]  # vector_field.py:243-244
+        st.diag_species = self.names.index(ref)
         # one device word per integration, zeroed once; the library resets it after every use
         st.sync_counter = self._scratch("sync_counter", (4,), dev, zero=True, dtype=torch.int32).data_ptr()
         self.static[key] = st
@@ -313,6 +317,13 @@ class NativeStep:
             st.nu_fp_time = float(vm.nu_fp_prof.time_envelope(t))
         if vm.krook_on:
             st.nu_K_time = float(vm.nu_K_prof.time_envelope(t))
+        diags = {}
+        ref_f = y[self.names[st.diag_species]]
+        for on, key, field in ((vm.vpfp.vlasov_dfdt, "diag-vlasov-dfdt", "diag_vlasov_dfdt"),
+                               (vm.vpfp.fp_dfdt, "diag-fp-dfdt", "diag_fp_dfdt")):
+            if on:
+                diags[key] = torch.empty_like(ref_f)
+                setattr(st, field, diags[key].data_ptr())
         lib = _lib.load()
         before = lib.adept_b200_launch_count()
         rc = lib.adept_b200_step_f64(C.byref(st), C.c_void_p(torch.cuda.current_stream().cuda_stream))
@@ -321,6 +332,7 @@ class NativeStep:
         result = {"a": a_out if wave_on else y["a"], "prev_a": y["a"], "da": djy,
                   "de": dex[vm.vpfp.dex_save], "e": e_out}
         result.update(new)
+        result.update(diags)
         return result
 
 

@@ -288,6 +288,16 @@ typedef struct adept_b200_step {
    * field in the tail of the x-advection launch: E = green (*) rho as a circular convolution (field.py:221-224 is
    * linear in rho), no separate field launch. */
   const double* poisson_green;
+  /* dfdt diagnostics of the reference species (diagnostics.diag-vlasov-dfdt / diag-fp-dfdt, vector_field.py:245-250):
+   * [batch, nx, nv] outputs (f_vlasov - f) / dt and (f_fp - f_vlasov) / dt, each nullable; diag_species indexes the
+   * species they refer to ("electron" if present, else the first).  They need the intermediate distribution, so a
+   * step that asks for them does not take the fused v-push + collision kernel. */
+  double* diag_vlasov_dfdt;
+  double* diag_fp_dfdt;
+  int diag_species;
+  /* Hou-Li spectral filter in x applied to every species after the collisions (terms.hou_li_filter, vlasov.py:187-220):
+   * real multiplier per mode, [nx/2 + 1] (nullable = off) */
+  const double* hou_li_filt;
 } adept_b200_step;
 
 int adept_b200_step_f64(const adept_b200_step* step, void* stream);
