@@ -167,6 +167,55 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ library-FFT stand-in
+def time_cufft_stand_in(sim, nx, nv, steps=10):
+    """SURVEY.md 8d "Reference GPU path": jax[cuda12] is not installable offline, so the stand-in for XLA's lowering of
+    the reference step is the same operators composed from torch.fft (cuFFT, fp64) on this GPU: x-advection
+    (vlasov.py:236-238), charge density + spectral Poisson (field.py:197-224), spectral v-advection (vlasov.py:83-90).
+    There is no batched tridiagonal solver in torch, so the collision step is LEFT OUT: this times two of the three
+    operator applications of the step and is a lower bound on the library time.  A reported baseline only; nothing in
+    the library or in the parity tests uses torch.fft."""
+    import torch
+
+    cfg = sim.cfg
+    g = cfg["grid"]
+    name = next(iter(g["species_grids"]))
+    sg, sp = g["species_grids"][name], g["species_params"][name]
+    dev = sim.state[name].device
+    f = sim.state[name].clone()
+    t64 = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64), device=dev)  # noqa: E731
+    v, kxr, kvr, ook = t64(sg["v"]), t64(g["kxr"]), t64(sg["kvr"]), t64(g["one_over_kx"])
+    ion = t64(g["ion_charge"])
+    dt, dv, q, m = float(g["dt"]), float(sg["dv"]), float(sp["charge"]), float(sp["mass"])
+    xphase = torch.exp(-1j * kxr[:, None] * v[None, :] * dt)  # static table, kept resident like XLA would constant-fold
+
+    def step(f):
+        f = torch.fft.irfft(torch.fft.rfft(f, dim=0) * xphase, n=nx, dim=0)
+        rho = ion + q * (f.sum(dim=1) * dv)
+        e = torch.real(torch.fft.ifft(-1j * ook * torch.fft.fft(rho)))
+        accel = (q * e) / m
+        return torch.fft.irfft(torch.fft.rfft(f, dim=1) * torch.exp(-1j * kvr[None, :] * dt * accel[:, None]), n=nv, dim=1)
+
+    for _ in range(3):
+        f = step(f)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        f = step(f)
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3 / steps
+    assert bool(torch.isfinite(f).all())
+    del f, xphase
+    torch.cuda.empty_cache()
+    return {"value": nx * nv / sec, "unit": UNIT, "ms_per_step": sec * 1e3, "kind": "torch.fft (cuFFT) fp64 composition",
+            "what": "x-advection + charge density + spectral Poisson + spectral v-advection on this GPU, collision "
+                    "step left out (no batched tridiagonal solver in torch): 2 of the 3 operator applications, a lower "
+                    "bound on the library time; stand-in for jax[cuda12] (not installable offline)",
+            "steps": steps}
+
+
 # ------------------------------------------------------------------------------------------------ B200 arm
 # algorithmic bytes per cell and launch: one fp64 read + one fp64 write of f per operator application (SURVEY.md 8d);
 # the fused v-push + collision kernel performs two operator applications per launch (it moves 16 B/cell)
@@ -328,6 +377,12 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
+    gpu_library_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            gpu_library_baseline = time_cufft_stand_in(sim, nx, nv)
+        except Exception as exc:  # a reported baseline must never take the bench line down (e.g. cuFFT plan memory)
+            gpu_library_baseline = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         workers = os.cpu_count() or 1
@@ -350,7 +405,7 @@ def run_b200(args):
                         "of the final f inside the timed region (amortised per step), per-step asynchronous D2H of "
                         "mean_e2/mean_de2 into a pinned ring, one host wait at the end of the run"},
         "roofline": roofline, "kernels": per_kernel, "gpu_launches": launches, "clocks": clocks,
-        "cpu_baseline": cpu_baseline,
+        "cpu_baseline": cpu_baseline, "gpu_library_baseline": gpu_library_baseline,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
