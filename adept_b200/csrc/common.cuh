@@ -37,6 +37,23 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   __syncthreads();
 }
 
+// the same barrier in two halves, so that work that does not depend on the other CTAs can run between them
+__device__ __forceinline__ void grid_arrive(unsigned int* counter) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+  }
+}
+__device__ __forceinline__ void grid_wait(unsigned int* counter, unsigned int target) {
+  if (threadIdx.x == 0) {
+    while (*reinterpret_cast<volatile unsigned int*>(counter) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
 // accel = (q*e + (q^2/m)*pond)/m with the reference's rounding sequence (no FMA contraction):
 // adept/_vlasov1d/solvers/pushers/vlasov.py:83-84
 __device__ __forceinline__ double accel_of(double e, double pond, double q, double q2m, double m) {

@@ -177,7 +177,9 @@ __global__ void __launch_bounds__(TmaCfg<LOGN>::THREADS, 1)
     }
   }
   if (p.partial && cur_b >= 0) flush_rho(cur_b);
-  if (K::NSTAGE > 0 && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // staged stores complete
+  // the last tile's staged stores must be complete before the CTA exits (its shared memory is their source); the field
+  // tail does not touch the staging area or f_out, so it runs first and the wait costs nothing
+  if (!FIELD && K::NSTAGE > 0 && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 
   if constexpr (FIELD) {
     // ---- field solve in the tail (batch == 1, one species): see FieldTail in internal.h ---------------------------
@@ -190,14 +192,15 @@ __global__ void __launch_bounds__(TmaCfg<LOGN>::THREADS, 1)
     constexpr int NGRP = K::THREADS / 32;
     constexpr int PER_T = N / K::THREADS;             // 8 grid points per thread
     const int colr = tid & 31, grp = tid >> 5;        // warp `grp` sums the partial rows grp, grp + NGRP, ...
-    {  // the Green's function does not depend on this step: fetched while the slowest CTAs finish their tiles
+    grid_arrive(ft.counter);  // this CTA's partial row is complete
+    {  // the Green's function does not depend on the other CTAs: fetched while the barrier fills
       double gv[PER_T];
 #pragma unroll
       for (int u = 0; u < PER_T; u++) gv[u] = __ldg(ft.green + tid + u * K::THREADS);
 #pragma unroll
       for (int u = 0; u < PER_T; u++) g_s[tid + u * K::THREADS] = gv[u];
     }
-    grid_barrier(ft.counter, G);  // every CTA's partial row is complete
+    grid_wait(ft.counter, G);  // every CTA's partial row is complete
     const int per = (N + (int)G - 1) / (int)G;
     const int i_lo = (int)blockIdx.x * per, i_hi = min(N, i_lo + per);
     for (int c0 = i_lo; c0 < i_hi; c0 += 32) {
@@ -263,6 +266,7 @@ __global__ void __launch_bounds__(TmaCfg<LOGN>::THREADS, 1)
     }
     __syncthreads();
     if (tid == 0 && atomicAdd(ft.counter, 1u) == 3 * G - 1) *ft.counter = 0u;  // last one out re-arms the counter
+    if (K::NSTAGE > 0 && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 }
 
