@@ -433,6 +433,12 @@ int adept_b200_poisson_f64(const double* rho, const double* kmul, long long kmul
   return poisson_dispatch_f64(rho, kmul, kmul_stride, e, batch, nx, mode, Te, lambda_De, (cudaStream_t)stream);
 }
 
+int adept_b200_poisson_green_f64(const double* rho, const double* green, long long green_stride, double* e, int batch,
+                                 int nx, void* stream) {
+  ADEPT_REQUIRE(rho, "rho") ADEPT_REQUIRE(green, "green") ADEPT_REQUIRE(e, "e")
+  return poisson_green_f64(rho, green, green_stride, e, batch, nx, (cudaStream_t)stream);
+}
+
 int adept_b200_field_energy_f64(const double* e0, const double* de0, const double* e1, const double* de1, double w,
                                 int batch, int nx, double* out, void* stream) {
   ADEPT_REQUIRE(e0, "e0") ADEPT_REQUIRE(de0, "de0") ADEPT_REQUIRE(out, "out")

@@ -482,6 +482,97 @@ __global__ void __launch_bounds__(256) field_fused_kernel(FieldFusedArgs p) {
   if (threadIdx.x == 0 && atomicAdd(p.counter, 1u) == 4 * G - 1) *p.counter = 0u;
 }
 
+// ---- Poisson solve as a circular convolution with the Green's function, spread over nx/32 CTAs ------------------------
+// E = Re ifft(-i (1/kx) fft(rho)) is linear in rho (field.py:221-224): E_i = sum_j green[(i - j) mod nx] rho_j with
+// green = Re ifft(-i / kx).  One 4096-point FFT solve keeps a single SM busy for ~15-19 us with 147 SMs idle; the direct
+// sum is nx^2 fused multiply-adds spread over the whole GPU.  One warp per output, lanes stride j, four running sums
+// (the same arithmetic as the field tail of the x-advection, vdfdx_tma.cu).
+__global__ void __launch_bounds__(1024) poisson_green_kernel(const double* __restrict__ rho,
+                                                             const double* __restrict__ green, long long green_stride,
+                                                             double* __restrict__ e, int nx) {
+  // Shared memory: G2[2 nx] (the Green's function twice, so that a window never wraps), rho[nx], partial[8][32].
+  // The direct sum reads 16 bytes of shared memory per multiply-add when every product fetches its own operands; that
+  // is 2.1 M wavefronts at nx = 4096, ~8 us over 148 SMs.  Register tile instead: a lane owns two consecutive j and
+  // eight consecutive outputs, the 9 Green's-function values it needs come from 5 aligned 16-byte loads:
+  // 6 loads per 16 multiply-adds.
+  extern __shared__ __align__(16) double sm_pg[];
+  double* g2 = sm_pg;
+  double* rho_s = sm_pg + 2 * nx;
+  double* part = rho_s + nx;
+  const int b = blockIdx.y;
+  const double* rb = rho + (long long)b * nx;
+  const double* gb = green + (long long)b * green_stride;
+  {  // all loads of the CTA in flight at once (nx <= 8192: at most 8 per thread and array), then the stores
+    double rv[8], gv[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int j = threadIdx.x + u * 1024;
+      rv[u] = j < nx ? rb[j] : 0.0;
+      gv[u] = j < nx ? __ldg(gb + j) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int j = threadIdx.x + u * 1024;
+      if (j < nx) rho_s[j] = rv[u], g2[j] = gv[u], g2[j + nx] = gv[u];
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int og = warp & 3, jr = warp >> 2;       // output group (8 outputs), j range (nx / 8 values)
+  const int i0 = blockIdx.x * 32 + 8 * og;
+  const int jn = nx >> 3;
+  double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int j = jr * jn + 2 * lane; j < (jr + 1) * jn; j += 64) {
+    const double2 r2 = *reinterpret_cast<const double2*>(rho_s + j);
+    // G2 index of (output i0 + r, column j + d): i0 + r - j - d + nx = m0 + r + 2 - d with m0 = i0 - j - 2 + nx (even)
+    const double2* wp = reinterpret_cast<const double2*>(g2 + (i0 - j - 2 + nx));
+    double w[10];
+#pragma unroll
+    for (int q = 0; q < 5; q++) {
+      const double2 t2 = wp[q];
+      w[2 * q] = t2.x, w[2 * q + 1] = t2.y;
+    }
+#pragma unroll
+    for (int r = 0; r < 8; r++) acc[r] = fma(w[r + 1], r2.y, fma(w[r + 2], r2.x, acc[r]));
+  }
+#pragma unroll
+  for (int r = 0; r < 8; r++) acc[r] = warp_sum(acc[r]);
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) part[jr * 32 + og * 8 + r] = acc[r];
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) s += part[q * 32 + threadIdx.x];
+    e[(long long)b * nx + blockIdx.x * 32 + threadIdx.x] = s;
+  }
+}
+
+int poisson_green_f64(const double* rho, const double* green, long long green_stride, double* e, int batch, int nx,
+                      cudaStream_t stream) {
+  if (batch < 1 || nx < 512 || nx > 8192 || (nx & (nx - 1))) {
+    set_last_error("poisson_green: nx=%d must be a power of two in [512, 8192] (batch=%d)", nx, batch);
+    return batch < 1 ? ADEPT_ERR_BAD_SHAPE : ADEPT_ERR_UNSUPPORTED;
+  }
+  const size_t smem = ((size_t)3 * nx + 8 * 32) * sizeof(double);
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (smem > 48 * 1024 && dev < 64 && !configured[dev]) {
+    cudaError_t err = cudaFuncSetAttribute(poisson_green_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (err != cudaSuccess) {
+      set_last_error("cudaFuncSetAttribute(poisson_green): %s", cudaGetErrorString(err));
+      return ADEPT_ERR_CUDA;
+    }
+    configured[dev] = true;
+  }
+  ProfileScope prof("poisson_green", stream);
+  poisson_green_kernel<<<dim3(nx / 32, batch), 1024, smem, stream>>>(rho, green, green_stride, e, nx);
+  return check_launch("poisson_green_kernel");
+}
+
 // ---- small grids / ensembles: the whole field solve of one member in one CTA ----------------------------------------
 // Replaces, for nx <= 256 (one launch instead of 3 + n_species): pond_kernel, moments_kernel per species, poisson_kernel
 // and, for the leapfrog step, ex_driver_kernel.  A 64 x 512 member is 256 KB: an ensemble of them lives in L2, the step

@@ -22,6 +22,8 @@ int bluestein_push_f64(int axis, const double* fin, double* fout, int batch, int
                        double q, double m, const double* filt, cudaStream_t stream);
 int bluestein_poisson_f64(const double* rho, const double* kmul, long long kmul_stride, double* e, int batch, int nx,
                           int mode, double Te, double lambda_De, cudaStream_t stream);
+int poisson_green_f64(const double* rho, const double* green, long long green_stride, double* e, int batch, int nx,
+                      cudaStream_t stream);
 bool field_member_supported(int nx);
 int field_member_f64(int nsp, const double* const* f, const int* nv, const double* dv, const double* charge,
                      const double* base, double* rho, int batch, int nx, const double* a, double* pond, double dx,

@@ -267,6 +267,20 @@ def poisson(rho, kmul, mode=0, Te=1.0, lambda_De=-1.0, out=None):
     return out
 
 
+def poisson_green(rho, green, out=None):
+    """Plain Poisson solve as a circular convolution with ``green = Re ifft(-i / kx)`` (field.py:221-224 is linear in
+    rho), spread over the whole GPU.  rho [nx] or [batch, nx]; green [nx] (shared) or [batch, nx]."""
+    nx = rho.shape[-1]
+    batch = rho.numel() // nx
+    stride = nx if (green.dim() == 2 and green.shape[0] == batch and batch > 1) else 0
+    out = torch.empty_like(rho) if out is None else out
+    rc = _lib.load().adept_b200_poisson_green_f64(_ptr(rho, "rho"), _ptr(green, "green"), stride, _ptr(out, "out"),
+                                                  batch, nx, _stream())
+    _lib.check(rc, "poisson_green")
+    _count()
+    return out
+
+
 def field_energy(e, de, e1=None, de1=None, w=0.0, out=None):
     """{mean(e^2), mean(de^2)} per member in one launch (storage.py:316-317), optionally of the state interpolated
     towards (e1, de1) with weight w.  Returns a [batch, 2] (or [2]) tensor."""

@@ -185,6 +185,7 @@ class ShardedVlasov1D:
             "ex_space": [tt(d.envelope.space_envelope(self.x)) for d in self.ex],
             "ex_kx": [tt(d.k0 * self.x) for d in self.ex],
             "nu_fp_space": tt(self.nu_fp_prof.space_envelope(self.x[self.rows]) * np.ones(self.nxp)),
+            "green": tt(np.real(np.fft.ifft(-1j * np.asarray(self.grid.one_over_kx, dtype=np.float64)))),
             "f_vs": f_vs, "f_st": f_st, "vs_ptrs": list(h_vs.buffer_ptrs), "st_ptrs": list(h_st.buffer_ptrs),
             "handles": (h_vs, h_st), "nv": nv,
             "parts": torch.zeros((nparts, self.nx), dtype=torch.float64, device=self.device),
@@ -208,7 +209,7 @@ class ShardedVlasov1D:
         rowsum = ops.reduce_parts(pp["parts"], 1.0, 1.0)
         dist.all_reduce(rowsum, op=dist.ReduceOp.SUM, group=self.group)  # also: every rank's x-push has completed
         rho = self.lops.rho_from_sum(rowsum, float(sg["dv"]), float(sp["charge"]), self.ion)
-        e = self.lops.poisson(rho, self.one_over_kx)
+        e = ops.poisson_green(rho, pp["green"])  # nx/32 CTAs instead of one 4096-point FFT in a single CTA
         e_loc, dex_loc = e[self.rows].contiguous(), dex[self.rows].contiguous()
         # 2. v-push + collisions on my rows: cells come from and go back to the ranks that own their columns
         nu_fp = float(self.nu_fp_prof.time_envelope(t)) * pp["nu_fp_space"]

@@ -156,6 +156,12 @@ int adept_b200_poisson_f64(const double* rho, const double* kmul, long long kmul
 /* out[i] = a[i] + s * b[i]  (Ampere: E = E_prev - dt j). */
 int adept_b200_axpy_f64(const double* a, const double* b, double s, double* out, long long n, void* stream);
 
+/* The plain Poisson solve (field.py:221-224) as a circular convolution with the Green's function
+ * green[nx] = Re ifft(-i / kx), spread over nx/32 CTAs: e[b, i] = sum_j green[b, (i - j) mod nx] rho[b, j].
+ * green_stride: 0 when every member shares one table, nx for per-member tables.  nx: power of two in [512, 8192]. */
+int adept_b200_poisson_green_f64(const double* rho, const double* green, long long green_stride, double* e, int batch,
+                                 int nx, void* stream);
+
 /* Field-energy scalars of the default save function (mean_e2, mean_de2; adept/_vlasov1d/storage.py:316-317), one
  * launch: out[b] = {mean(e_b^2), mean(de_b^2)} of (e0, de0)[batch, nx], or of the state interpolated linearly towards
  * (e1, de1) with weight w when those are given (both or neither). */

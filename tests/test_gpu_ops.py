@@ -577,3 +577,24 @@ def test_field_energy_matches_numpy(ops, batch, nx):
 
     with pytest.raises(AdeptB200Error, match="both e1 and de1"):
         ops.field_energy(dev(e0), dev(de0), dev(e1), None, w)
+
+
+@pytest.mark.parametrize("batch,nx", [(1, 512), (1, 1024), (1, 4096), (3, 512), (2, 8192)])
+def test_poisson_green_matches_oracle(ops, batch, nx):
+    """field.py:221-224 as a circular convolution with green = Re ifft(-i / kx): same operator as the FFT solve."""
+    rng = np.random.default_rng(nx)
+    dx = 20.94 / nx
+    kx = np.fft.fftfreq(nx, d=dx) * 2 * np.pi
+    ook = np.zeros(nx)
+    ook[1:] = 1.0 / kx[1:]
+    green = np.real(np.fft.ifft(-1j * ook))
+    rho = 0.01 * rng.standard_normal((batch, nx)) + 1e-2 * np.cos(0.3 * np.arange(nx) * dx)[None, :]
+    e = host(ops.poisson_green(dev(rho), dev(green)))
+    for b in range(batch):
+        ref = O.poisson(rho[b], ook)
+        assert np.max(np.abs(e[b] - ref)) <= 1e-13 * max(1.0, np.max(np.abs(ref)))
+        assert rel_l2(e[b], ref) <= RTOL
+    from adept_b200._lib import AdeptB200Error
+
+    with pytest.raises(AdeptB200Error, match="power of two"):
+        ops.poisson_green(dev(rho[:, :100].copy()), dev(green[:100].copy()))
