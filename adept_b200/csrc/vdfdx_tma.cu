@@ -198,7 +198,10 @@ __global__ void __launch_bounds__(TmaCfg<LOGN>::THREADS, 1)
 #pragma unroll
       for (int u = 0; u < PER_T; u++) gv[u] = __ldg(ft.green + tid + u * K::THREADS);
 #pragma unroll
-      for (int u = 0; u < PER_T; u++) g_s[tid + u * K::THREADS] = gv[u];
+      for (int u = 0; u < PER_T; u++) {  // twice in a row: a window of the convolution never wraps
+        g_s[tid + u * K::THREADS] = gv[u];
+        g_s[tid + u * K::THREADS + N] = gv[u];
+      }
     }
     grid_wait(ft.counter, G);  // every CTA's partial row is complete
     const int per = (N + (int)G - 1) / (int)G;
@@ -251,7 +254,40 @@ __global__ void __launch_bounds__(TmaCfg<LOGN>::THREADS, 1)
       for (int u = 0; u < PER_T; u++) rho_s[tid + u * K::THREADS] = rv[u];
     }
     __syncthreads();
-    // E_i = sum_j green[(i - j) mod N] rho_j: one warp per output, lanes stride j, four running sums
+    // E_i = sum_j green[(i - j) mod N] rho_j.  Fetching both operands of every product costs 16 bytes of shared memory
+    // per multiply-add (14 k wavefronts for 28 outputs: the largest item of the tail), so where the slice allows it the
+    // sum is register-tiled like poisson_green_kernel (field.cu): a lane owns two consecutive j and eight consecutive
+    // outputs, 6 aligned 16-byte loads per 16 multiply-adds.
+    if (NGRP == 16 && (per & 1) == 0 && per <= 32) {
+      double* part = rho_s + 3 * N;              // [4 j ranges][32 outputs]
+      const int og = grp & 3, jr = grp >> 2;
+      const int i0 = i_lo + 8 * og;
+      double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      if (i0 < i_hi) {
+        for (int j = jr * (N / 4) + 2 * colr; j < (jr + 1) * (N / 4); j += 64) {
+          const double2 r2 = *reinterpret_cast<const double2*>(rho_s + j);
+          // g2 index of (output i0 + r, column j + d): m0 + r + 2 - d with m0 = i0 - j - 2 + N (even)
+          const double2* wp = reinterpret_cast<const double2*>(g_s + (i0 - j - 2 + N));
+          double w[10];
+#pragma unroll
+          for (int q = 0; q < 5; q++) {
+            const double2 t2 = wp[q];
+            w[2 * q] = t2.x, w[2 * q + 1] = t2.y;
+          }
+#pragma unroll
+          for (int r = 0; r < 8; r++) acc[r] = fma(w[r + 1], r2.y, fma(w[r + 2], r2.x, acc[r]));
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 8; r++) acc[r] = warp_sum(acc[r]);
+      if (colr == 0) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) part[jr * 32 + og * 8 + r] = acc[r];
+      }
+      __syncthreads();
+      if (tid < 32 && i_lo + tid < i_hi)
+        ft.e[i_lo + tid] = (part[tid] + part[32 + tid]) + (part[64 + tid] + part[96 + tid]);
+    } else
     for (int i = i_lo + grp; i < i_hi; i += NGRP) {
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll 4
