@@ -26,7 +26,7 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 sim = ShardedVlasov1D(c3_deck(nx, nv), transpose=transpose)
 sim.t, sim.step_index = 30.0, 300
-for _ in range(5):
+for _ in range(30):  # NCCL and the symmetric-memory rendezvous keep initialising lazily for tens of steps at 4+ ranks
     sim.step()
 dist.barrier()
 torch.cuda.synchronize()
