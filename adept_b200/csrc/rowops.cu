@@ -170,27 +170,39 @@ int diff_over_dt_f64(const double* a, const double* b, double dt, double* out, l
 
 // ---- field-energy scalars of the default save: out[b] = {mean(e_b^2), mean(de_b^2)}  (storage.py:316-317) ----------
 // (e0, de0) alone, or the state interpolated linearly towards (e1, de1) with weight w (diffrax's dense output)
-__global__ void __launch_bounds__(256) field_energy_kernel(const double* __restrict__ e0, const double* __restrict__ de0,
+__global__ void __launch_bounds__(1024) field_energy_kernel(const double* __restrict__ e0, const double* __restrict__ de0,
                                                            const double* __restrict__ e1, const double* __restrict__ de1,
                                                            double w, int nx, double* __restrict__ out) {
-  __shared__ double red[2][8];
+  __shared__ double red[2][32];
   const long long off = (long long)blockIdx.x * nx;
   double s0 = 0.0, s1 = 0.0;
-  for (int i = threadIdx.x; i < nx; i += 256) {
-    double a = e0[off + i], b = de0[off + i];
-    if (e1) {
-      a = __dadd_rn(a, __dmul_rn(w, __dsub_rn(e1[off + i], a)));
-      b = __dadd_rn(b, __dmul_rn(w, __dsub_rn(de1[off + i], b)));
+  // a latency-bound kernel: four grid points per thread and pass, every load issued before the first use
+  for (int i0 = threadIdx.x; i0 < nx; i0 += 4 * 1024) {
+    double a[4], b[4], a1[4], b1[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u * 1024;
+      const bool in = i < nx;
+      a[u] = in ? e0[off + i] : 0.0, b[u] = in ? de0[off + i] : 0.0;
+      a1[u] = (in && e1) ? e1[off + i] : a[u], b1[u] = (in && e1) ? de1[off + i] : b[u];
     }
-    s0 = fma(a, a, s0);
-    s1 = fma(b, b, s1);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      double x = a[u], y = b[u];
+      if (e1) {
+        x = __dadd_rn(x, __dmul_rn(w, __dsub_rn(a1[u], x)));
+        y = __dadd_rn(y, __dmul_rn(w, __dsub_rn(b1[u], y)));
+      }
+      s0 = fma(x, x, s0);
+      s1 = fma(y, y, s1);
+    }
   }
   s0 = warp_sum(s0), s1 = warp_sum(s1);
   if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = s0, red[1][threadIdx.x >> 5] = s1;
   __syncthreads();
   if (threadIdx.x < 2) {
     double t = 0.0;
-    for (int k = 0; k < 8; k++) t += red[threadIdx.x][k];
+    for (int k = 0; k < 32; k++) t += red[threadIdx.x][k];
     out[2 * blockIdx.x + threadIdx.x] = t / (double)nx;
   }
 }
@@ -206,7 +218,7 @@ int field_energy_f64(const double* e0, const double* de0, const double* e1, cons
     return ADEPT_ERR_BAD_ARG;
   }
   ProfileScope prof("field_energy", stream);
-  field_energy_kernel<<<batch, 256, 0, stream>>>(e0, de0, e1, de1, w, nx, out);
+  field_energy_kernel<<<batch, 1024, 0, stream>>>(e0, de0, e1, de1, w, nx, out);
   return check_launch("field_energy_kernel");
 }
 

@@ -283,13 +283,20 @@ def poisson_green(rho, green, out=None):
 
 def field_energy(e, de, e1=None, de1=None, w=0.0, out=None):
     """{mean(e^2), mean(de^2)} per member in one launch (storage.py:316-317), optionally of the state interpolated
-    towards (e1, de1) with weight w.  Returns a [batch, 2] (or [2]) tensor."""
+    towards (e1, de1) with weight w.  Returns a [batch, 2] (or [2]) tensor.  ``out`` may be a PINNED host tensor
+    (page-locked memory is mapped into the device's address space): the kernel then writes the scalars straight into
+    host memory, which is the device-to-host transfer of a per-step diagnostic without a separate copy; the values are
+    valid after the stream has been synchronised."""
     nx = e.shape[-1]
     batch = e.numel() // nx
     if out is None:
         out = torch.empty(e.shape[:-1] + (2,), dtype=torch.float64, device=e.device)
+    if not out.is_cuda and out.is_pinned() and out.dtype == torch.float64 and out.is_contiguous():
+        out_ptr = C.c_void_p(out.data_ptr())
+    else:
+        out_ptr = _ptr(out, "out")
     rc = _lib.load().adept_b200_field_energy_f64(_ptr(e, "e"), _ptr(de, "de"), _ptr(e1, "e1", True),
-                                                 _ptr(de1, "de1", True), float(w), batch, nx, _ptr(out, "out"), _stream())
+                                                 _ptr(de1, "de1", True), float(w), batch, nx, out_ptr, _stream())
     _lib.check(rc, "field_energy")
     _count()
     return out

@@ -349,15 +349,15 @@ def run_b200(args):
     f_host.copy_(sim.state[name])
     f_back = torch.empty((nx, nv), dtype=torch.float64).pin_memory()
     n_ring = max(K, W, 3)
-    diag_dev = torch.empty((n_ring, 2), dtype=torch.float64, device="cuda")
     diag_host = torch.zeros((n_ring, 2), dtype=torch.float64).pin_memory()
 
     def e2e_run(nsteps):
         sim.state[name] = f_host.to("cuda", non_blocking=True)
         for i in range(nsteps):
             st = sim.step()
-            ops.field_energy(st["e"], st["de"], out=diag_dev[i])
-            diag_host[i].copy_(diag_dev[i], non_blocking=True)
+            # the kernel writes the two scalars straight into the pinned host ring (mapped memory): the per-step
+            # device-to-host transfer without a separate copy operation on the stream
+            ops.field_energy(st["e"], st["de"], out=diag_host[i])
         f_back.copy_(sim.state[name], non_blocking=True)
         torch.cuda.synchronize()
         return float(diag_host[nsteps - 1, 0])
@@ -402,8 +402,9 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": e2e_elapsed / K * 1e3,
                 "what": f"Vlasov1D.step() public API, {K}-step run from and to pinned HOST memory: H2D of f0 and D2H "
-                        "of the final f inside the timed region (amortised per step), per-step asynchronous D2H of "
-                        "mean_e2/mean_de2 into a pinned ring, one host wait at the end of the run"},
+                        "of the final f inside the timed region (amortised per step), per-step D2H of mean_e2/mean_de2 "
+                        "(written by the field-energy kernel straight into a pinned, mapped host ring), one host wait "
+                        "at the end of the run"},
         "roofline": roofline, "kernels": per_kernel, "gpu_launches": launches, "clocks": clocks,
         "cpu_baseline": cpu_baseline, "gpu_library_baseline": gpu_library_baseline,
     }

@@ -598,3 +598,13 @@ def test_poisson_green_matches_oracle(ops, batch, nx):
 
     with pytest.raises(AdeptB200Error, match="power of two"):
         ops.poisson_green(dev(rho[:, :100].copy()), dev(green[:100].copy()))
+
+
+def test_field_energy_writes_into_pinned_host_memory(ops):
+    rng = np.random.default_rng(5)
+    e, de = rng.standard_normal(4096), rng.standard_normal(4096)
+    ring = torch.zeros((3, 2), dtype=torch.float64).pin_memory()
+    ops.field_energy(dev(e), dev(de), out=ring[1])
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(ring[1].numpy(), [np.mean(e**2), np.mean(de**2)], rtol=1e-13)
+    assert float(ring[0].abs().sum() + ring[2].abs().sum()) == 0.0
