@@ -608,3 +608,32 @@ def test_field_energy_writes_into_pinned_host_memory(ops):
     torch.cuda.synchronize()
     np.testing.assert_allclose(ring[1].numpy(), [np.mean(e**2), np.mean(de**2)], rtol=1e-13)
     assert float(ring[0].abs().sum() + ring[2].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("fp_type", ["chang_cooper", "chang_cooper_dougherty"])
+def test_reference_relaxation_sweep_on_gpu(ops, fp_type):
+    """The reference's own relaxation assertions (tests/test_vlasov1d/test_fp_relaxation.py:84-118: Chang-Cooper,
+    self-consistent beta with max_steps = 2, dt = tau, 10 collision times, five initial conditions) through the C ABI,
+    and the final distribution against the oracle's."""
+    from test_oracle_operators import _relax_metrics, _relax_problems, _relax_run, _sg_cfg
+
+    cfg, v, dv = _sg_cfg(128, fp_type, sc_steps=2)
+    coll = O.Collisions(cfg)
+    nu, vd = dev(np.ones(1)), dev(v)
+    model, scheme = MODEL[coll.model], SCHEME[coll.scheme]
+
+    def gpu_collide(f):
+        return host(ops.collide(dev(f), vd, dv, 1.0, nu_fp=nu, model=model, scheme=scheme, sc_steps=2))
+
+    for name, f0 in _relax_problems(v, dv).items():
+        hist = _relax_run(gpu_collide, fp_type, f0)
+        ref = _relax_run(lambda f: coll(np.ones(1), np.zeros(1), f, 1.0), fp_type, f0)
+        assert rel_l2(hist[-1], ref[-1]) <= 1e-11, name  # ten strongly collisional steps (dt nu D / dv^2 ~ 114)
+        m = _relax_metrics(hist, v, dv)
+        assert abs(m["rel_density"]) < 2e-13, (name, m)
+        assert abs(m["T_ratio"] - 1.0) < 5e-3, (name, m)
+        assert m["rmse_instant"] < 1e-4, (name, m)
+        assert m["positivity"] < 1e-20, (name, m)
+        if "dougherty" in fp_type:
+            assert m["rmse_expected"] < 1e-2, (name, m)
+            assert abs(m["momentum_drift"]) < 5e-5, (name, m)

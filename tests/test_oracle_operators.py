@@ -338,3 +338,64 @@ def test_sc_beta_m2_matches_discrete_temperature():
     h = 1e-6
     np.testing.assert_allclose(O.chang_cooper_delta_prime(w),
                                (O.chang_cooper_delta(w + h) - O.chang_cooper_delta(w - h)) / (2 * h), rtol=1e-6)
+
+
+# ---- the reference's relaxation sweep (tests/test_vlasov1d/test_fp_relaxation.py:58-118, tests/fp_relaxation/*) -------
+def _relax_problems(v, dv):
+    """Initial conditions of tests/fp_relaxation/problems.py (cartesian grid), unit density."""
+    norm = lambda f: f / np.sum(f * dv)  # noqa: E731
+    mx = lambda T, s=0.0: norm(np.exp(-((v - s) ** 2) / (2.0 * T)))  # noqa: E731
+    return {
+        "maxwellian": mx(1.0),
+        "supergaussian-m5": norm(np.exp(-(np.abs(v / np.sqrt(2.0)) ** 5))),
+        "two-temperature": norm(0.7 * mx(0.5) + 0.3 * mx(2.0)),
+        "shifted-1.8-T0.162": mx(0.162, 1.8),
+        "shifted-1.0-T1.0": mx(1.0, 1.0),
+    }
+
+
+def _relax_metrics(f_hist, v, dv):
+    """tests/fp_relaxation/metrics.py:117-175 (cartesian branch): final-time values of the asserted metrics."""
+    f0, f1 = f_hist[0], f_hist[-1]
+    n0, n1 = np.sum(f0 * dv), np.sum(f1 * dv)
+    vb0, vb1 = np.sum(v * f0 * dv) / n0, np.sum(v * f1 * dv) / n1
+    T0 = O.discrete_temperature(f0[None], v, dv)[0]
+    T1 = O.discrete_temperature(f1[None], v, dv)[0]
+    Tsc0 = 1.0 / (2.0 * O.find_self_consistent_beta(f0[None], v, dv, np.array([vb0]), max_steps=2)[0])
+    Tsc1 = 1.0 / (2.0 * O.find_self_consistent_beta(f1[None], v, dv, np.array([vb1]), max_steps=2)[0])
+    mx = lambda T, s, n: n * np.exp(-((v - s) ** 2) / (2.0 * T)) / np.sum(np.exp(-((v - s) ** 2) / (2.0 * T)) * dv)  # noqa: E731
+    rmse = lambda a, b: np.sqrt(np.sum((a - b) ** 2 * dv))  # noqa: E731
+    return {"rel_density": (n1 - n0) / n0, "T_ratio": T1 / T0, "momentum_drift": vb1 - vb0,
+            "rmse_instant": rmse(f1, mx(Tsc1, vb1, n1)), "rmse_expected": rmse(f1, mx(Tsc0, vb0, n0)),
+            "positivity": np.sum(np.where(f1 < 0, -f1, 0.0) * dv)}
+
+
+def _relax_run(collide, fp_type, f0, nv=128, vmax=6.0):
+    """Base sweep point of tests/fp_relaxation/runner.py:44-51: dt = tau = 1 / nu = 1, sc_iterations = 2, 10 collision
+    times."""
+    f = f0[None, :].copy()
+    hist = [f[0].copy()]
+    for _ in range(10):
+        f = collide(f)
+        hist.append(f[0].copy())
+    return hist
+
+
+@pytest.mark.parametrize("fp_type", ["chang_cooper", "chang_cooper_dougherty"])
+def test_reference_relaxation_sweep_holds_for_the_oracle(fp_type):
+    """The assertions of test_fp_relaxation.py:84-118 (Chang-Cooper schemes, self-consistent beta with max_steps = 2,
+    dt = tau, 10 collision times) hold for the oracle's Collisions: density 2e-13, discrete temperature 5e-3, RMSE to
+    the instantaneous Maxwellian 1e-4, positivity 1e-20, and for Dougherty RMSE to the expected equilibrium 1e-2 and
+    momentum drift 5e-5.  Another pin of the Newton restatement besides the super-Gaussian fixed point."""
+    cfg, v, dv = _sg_cfg(128, fp_type, sc_steps=2)
+    coll = O.Collisions(cfg)
+    for name, f0 in _relax_problems(v, dv).items():
+        hist = _relax_run(lambda f: coll(np.ones(1), np.zeros(1), f, 1.0), fp_type, f0)
+        m = _relax_metrics(hist, v, dv)
+        assert abs(m["rel_density"]) < 2e-13, (name, m)
+        assert abs(m["T_ratio"] - 1.0) < 5e-3, (name, m)
+        assert m["rmse_instant"] < 1e-4, (name, m)
+        assert m["positivity"] < 1e-20, (name, m)
+        if "dougherty" in fp_type:
+            assert m["rmse_expected"] < 1e-2, (name, m)
+            assert abs(m["momentum_drift"]) < 5e-5, (name, m)
