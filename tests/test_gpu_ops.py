@@ -637,3 +637,25 @@ def test_reference_relaxation_sweep_on_gpu(ops, fp_type):
         if "dougherty" in fp_type:
             assert m["rmse_expected"] < 1e-2, (name, m)
             assert abs(m["momentum_drift"]) < 5e-5, (name, m)
+
+
+def test_supergaussian_known_answers_on_gpu(ops):
+    """tests/test_vlasov1d/test_super_gaussian_fp.py:144-216 through the C ABI (control, Maxwellian -> super-Gaussian
+    with an O(nu dt) energy error, momentum of a drifting initial condition, m = 2 == Chang-Cooper Dougherty)."""
+    from scipy.special import gammaln
+    from test_oracle_operators import _sg_cfg, check_supergaussian_known_answers
+
+    def make(fp_type, m, sc_steps):
+        cfg, v, dv = _sg_cfg(128, fp_type, m=m, sc_steps=sc_steps)
+        coll = O.Collisions(cfg)
+        mm = coll.m
+        ratio = float(np.exp(gammaln(3.0 / mm) - gammaln(1.0 / mm)))
+        nu, vd = dev(np.ones(1)), dev(v)
+
+        def collide(f, dt):
+            return host(ops.collide(dev(f), vd, dv, dt, nu_fp=nu, model=MODEL[coll.model], scheme=SCHEME[coll.scheme],
+                                    sg_m=mm, sg_ratio=ratio, sc_steps=sc_steps))
+
+        return collide, v, dv
+
+    check_supergaussian_known_answers(make)

@@ -399,3 +399,69 @@ def test_reference_relaxation_sweep_holds_for_the_oracle(fp_type):
         if "dougherty" in fp_type:
             assert m["rmse_expected"] < 1e-2, (name, m)
             assert abs(m["momentum_drift"]) < 5e-5, (name, m)
+
+
+# ---- the rest of tests/test_vlasov1d/test_super_gaussian_fp.py (lines 144-216), as functions of a `collide` callable ---
+def _sg_moments(f, v, dv):
+    n = np.sum(f * dv)
+    vbar = np.sum(f * v * dv) / n
+    T = np.sum(f * (v - vbar) ** 2 * dv) / n
+    return n, vbar, T, np.sum(f * (v - vbar) ** 4 * dv) / n / T**2
+
+
+def _sg_kurtosis(m):
+    from scipy.special import gamma
+
+    return gamma(5.0 / m) * gamma(1.0 / m) / gamma(3.0 / m) ** 2
+
+
+def check_supergaussian_known_answers(make):
+    """``make(fp_type, m, sc_steps) -> (collide(f, dt) -> f', v, dv)``; the assertions are the reference's."""
+    # :144-150 control: plain Dougherty maxwellianises a super-Gaussian
+    collide, v, dv = make("chang_cooper_dougherty", None, 3)
+    f = _supergaussian(v, dv, 3.0, 1.0)[None, :]
+    for _ in range(100):
+        f = collide(f, 0.1)
+    assert abs(_sg_moments(f[0], v, dv)[3] - 3.0) < 0.02
+    # :153-183 a Maxwellian relaxes to the super-Gaussian shape; the energy error is O(nu dt)
+    T_drift = {}
+    for dt in (0.1, 0.05):
+        collide, v, dv = make("super_gaussian", 3.0, 3)
+        f0 = _supergaussian(v, dv, 2.0, 1.0)[None, :]
+        f = f0
+        for _ in range(round(20.0 / dt)):
+            f = collide(f, dt)
+        n0, _, T0, _ = _sg_moments(f0[0], v, dv)
+        n1, _, T1, k1 = _sg_moments(f[0], v, dv)
+        T_drift[dt] = abs(T1 / T0 - 1.0)
+        assert abs(n1 / n0 - 1.0) < 1e-12
+        assert abs(k1 - _sg_kurtosis(3.0)) < 0.02
+        target = n1 * _supergaussian(v, dv, 3.0, T1)
+        assert np.linalg.norm(f[0] - target) / np.linalg.norm(target) < 1e-2
+    assert T_drift[0.1] < 2e-2 and T_drift[0.05] < T_drift[0.1] / 1.7
+    # :186-199 a drifting initial condition keeps its momentum
+    collide, v, dv = make("super_gaussian", 3.0, 3)
+    f0 = _supergaussian(v, dv, 2.0, 0.5, 1.5)[None, :]
+    f = f0
+    for _ in range(200):
+        f = collide(f, 0.1)
+    _, vb0, T0, _ = _sg_moments(f0[0], v, dv)
+    _, vb1, T1, k1 = _sg_moments(f[0], v, dv)
+    assert abs(vb1 - vb0) < 5e-5 and abs(T1 / T0 - 1.0) < 2e-2 and abs(k1 - _sg_kurtosis(3.0)) < 0.02
+    # :202-216 m = 2 is the Chang-Cooper Dougherty operator, step for step
+    sg, v, dv = make("super_gaussian", 2.0, 0)
+    dough, _, _ = make("chang_cooper_dougherty", None, 0)
+    f0 = (0.7 * _supergaussian(v, dv, 2.0, 0.5) + 0.3 * _supergaussian(v, dv, 2.0, 2.0, 0.5))[None, :]
+    fa, fb = f0, f0
+    for _ in range(10):
+        fa, fb = sg(fa, 0.1), dough(fb, 0.1)
+    np.testing.assert_allclose(fa, fb, rtol=1e-10, atol=1e-14)
+
+
+def test_supergaussian_known_answers_hold_for_the_oracle():
+    def make(fp_type, m, sc_steps):
+        cfg, v, dv = _sg_cfg(128, fp_type, m=m, sc_steps=sc_steps)
+        coll = O.Collisions(cfg)
+        return (lambda f, dt: coll(np.ones(1), np.zeros(1), f, dt)), v, dv
+
+    check_supergaussian_known_answers(make)
