@@ -74,12 +74,15 @@ def initialize_supergaussian(nx, nv, v0, order, T0, mass, vmax, vmin, n_prof):
 
 
 def speed_of_light_norm(units: dict | None) -> float:
-    """c / v0 with v0 = sqrt(T0/m_e) (electron Debye normalisation, normalization.py:101-119)."""
+    """c / v0 with v0 = sqrt(T0/m0): m0 = m_e for the electron Debye normalisation (normalization.py:100-121), or
+    A m_p for ``units.reference: ion`` (ion_debye_normalization, normalization.py:124-152)."""
     if not units:
         return 1.0
     s = str(units["normalizing_temperature"]).strip()
-    if units.get("reference", "electron") != "electron":
-        raise NotImplementedError("adept_b200: only the electron normalisation is parsed on the host")
+    ref = units.get("reference", "electron")
+    if ref not in ("electron", "ion"):
+        raise NotImplementedError(f"adept_b200: units.reference={ref!r} (electron or ion)")
+    rest_energy_eV = 510998.95 if ref == "electron" else float(units.get("A", 1.0)) * 938272088.16
     scale = 1.0
     if s.endswith("keV"):
         scale, s = 1.0e3, s[:-3]
@@ -87,7 +90,7 @@ def speed_of_light_norm(units: dict | None) -> float:
         s = s[:-2]
     else:
         raise ValueError(f"cannot parse normalizing_temperature={units['normalizing_temperature']!r} (eV / keV only)")
-    return 1.0 / math.sqrt(float(s) * scale / 510998.95)
+    return 1.0 / math.sqrt(float(s) * scale / rest_energy_eV)
 
 
 def species_list(cfg: dict) -> list[dict]:

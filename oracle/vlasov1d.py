@@ -160,8 +160,9 @@ def density_profile(comp: dict, x: np.ndarray) -> np.ndarray:
     return prof * (1.0 + np.zeros_like(prof))
 
 
-def electron_beta(normalizing_temperature: str) -> float:
-    """beta = v0/c with v0 = sqrt(T0/m_e): adept/normalization.py:75-76,116-117; modules.py:55."""
+def electron_beta(normalizing_temperature: str, reference: str = "electron", A: float = 1.0) -> float:
+    """beta = v0/c with v0 = sqrt(T0/m0), m0 = m_e (adept/normalization.py:100-121) or A m_p for units.reference = ion
+    (normalization.py:124-152); modules.py:55."""
     s = normalizing_temperature.strip()
     scale = 1.0
     if s.endswith("keV"):
@@ -172,7 +173,8 @@ def electron_beta(normalizing_temperature: str) -> float:
         raise ValueError(f"oracle only parses eV/keV temperatures, got {normalizing_temperature}")
     T_eV = float(s) * scale
     me_c2_eV = 510998.95  # CODATA m_e c^2 (pint's registry value to 8 s.f.)
-    return math.sqrt(T_eV / me_c2_eV)
+    mp_c2_eV = 938272088.16
+    return math.sqrt(T_eV / (me_c2_eV if reference == "electron" else A * mp_c2_eV))
 
 
 def build_cfg(cfg_in: dict) -> dict:
@@ -182,7 +184,9 @@ def build_cfg(cfg_in: dict) -> dict:
     ion_charge), :279-317 (state dict).  Only dimensionless decks (no pint strings).
     """
     cfg = deepcopy(cfg_in)
-    beta = electron_beta(cfg["units"]["normalizing_temperature"]) if "units" in cfg else 1.0
+    units = cfg.get("units")
+    beta = electron_beta(units["normalizing_temperature"], units.get("reference", "electron"),
+                         float(units.get("A", 1.0))) if units else 1.0
     gin = cfg["grid"]
     has_ey = len(cfg["drivers"].get("ey", {})) > 0
     grid = make_grid(gin["xmin"], gin["xmax"], gin["nx"], gin.get("tmin", 0.0), gin["tmax"], gin["dt"], has_ey, beta)

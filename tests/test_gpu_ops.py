@@ -659,3 +659,21 @@ def test_supergaussian_known_answers_on_gpu(ops):
         return collide, v, dv
 
     check_supergaussian_known_answers(make)
+
+
+def test_boltzmann_field_solver_matches_screened_poisson_on_gpu(ops):
+    """test_boltzmann_electrons.py:46-75 through the C ABI (velocity sum + Boltzmann-Poisson solve)."""
+    nx, nv = 64, 256
+    length = 2 * np.pi / 0.1
+    dx = length / nx
+    x = np.linspace(dx / 2, length - dx / 2, nx)
+    kx = np.fft.fftfreq(nx, d=dx) * 2 * np.pi
+    vmax, k, eps, Te = 0.64, 0.1, 1e-3, 1.0
+    dv = 2 * vmax / nv
+    v = np.linspace(-vmax + dv / 2, vmax - dv / 2, nv)
+    f = (1 + eps * np.cos(k * x))[:, None] * (np.exp(-(v**2) / 0.02) / np.sqrt(2 * np.pi * 0.01))[None, :]
+    rho = torch.empty(nx, dtype=torch.float64, device="cuda")
+    ops.moments(dev(f), None, dv, (rho, None, None), scale_b=(1.0, 1.0, 1.0))
+    for lam, screening in [(1.0, 1 + k**2), (0.0, 1.0), (None, 1 + k**2 * Te)]:
+        e = host(ops.poisson(rho, dev(kx), mode=1, Te=Te, lambda_De=-1.0 if lam is None else lam))
+        np.testing.assert_allclose(e, Te * eps * k / screening * np.sin(k * x), atol=1e-8 * eps * k)

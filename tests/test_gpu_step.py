@@ -245,3 +245,38 @@ def test_c3_full_size_free_running_parity():
     from adept_b200 import ops
 
     assert ops.LAUNCHES > 0
+
+
+def test_iaw_dispersion_boltzmann_on_gpu():
+    """The reference's tests/test_vlasov1d/test_boltzmann_electrons.py:109-135 on the GPU path: kinetic ions with
+    Boltzmann electrons, 8000 sixth-order steps; the ion-acoustic frequency matches the dispersion relation to 5 %, and
+    the density history matches the oracle's first 200 steps to 1e-9."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from test_oracle_operators import boltzmann_iaw_deck, iaw_expected_omega, measure_frequency
+
+    from adept_b200.module import Vlasov1D
+
+    deck = boltzmann_iaw_deck()
+    sim = Vlasov1D(deepcopy(deck))
+    dv = float(sim.cfg["grid"]["species_grids"]["ion"]["dv"])
+    dt = sim.grid.dt
+    hist = [sim.state["ion"].sum(dim=1) * dv]
+    for n in range(8000):
+        sim.step()
+        if (n + 1) % 10 == 0:
+            hist.append(sim.state["ion"].sum(dim=1) * dv)
+    n_hist = torch.stack(hist).cpu().numpy()
+    t_hist = np.arange(len(hist)) * 10 * dt
+    want = iaw_expected_omega(deck)
+    got = measure_frequency(n_hist, t_hist, want)
+    np.testing.assert_allclose(got, want, rtol=0.05)
+    # and against the oracle over the first 200 steps
+    cfg = O.build_cfg(deepcopy(deck))
+    vf = O.VlasovMaxwell(cfg)
+    y = O.init_state(cfg)
+    for n in range(200):
+        y = vf(n * dt, y, None)
+        if (n + 1) % 10 == 0:
+            ref = np.sum(y["ion"], axis=1) * dv
+            assert np.max(np.abs(n_hist[(n + 1) // 10] - ref)) <= 1e-9 * np.max(np.abs(ref - 1.0)) + 1e-13

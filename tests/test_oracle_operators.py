@@ -465,3 +465,87 @@ def test_supergaussian_known_answers_hold_for_the_oracle():
         return (lambda f, dt: coll(np.ones(1), np.zeros(1), f, dt)), v, dv
 
     check_supergaussian_known_answers(make)
+
+
+# ---- tests/test_vlasov1d/test_boltzmann_electrons.py ------------------------------------------------------------------
+def boltzmann_iaw_deck():
+    """tests/test_vlasov1d/configs/boltzmann_iaw.yaml: kinetic ions (T0 = 0.01, vti = 0.1) with linearised Boltzmann
+    electrons (Te = 1, lambda_De = 1) in ion units, k = 0.1, sixth-order integrator, no collisions, 8000 steps."""
+    env = {"baseline": 1.0, "bump_or_trough": "bump", "center": 0.0, "rise": 25.0, "slope": 0.0, "bump_height": 0.0,
+           "width": 100000.0}
+    return {
+        "units": {"normalizing_temperature": "2000eV", "normalizing_density": "1.5e21/cc", "reference": "ion"},
+        "density": {"quasineutrality": True,
+                    "species-ion-background": {"noise_seed": 420, "noise_type": "gaussian", "noise_val": 0.0, "v0": 0.0,
+                                               "T0": 0.01, "m": 2.0, "basis": "sine", "baseline": 1.0,
+                                               "amplitude": 1.0e-3, "wavenumber": 0.1}},
+        "grid": {"dt": 0.25, "nx": 64, "tmin": 0.0, "tmax": 2000.0, "xmax": 62.8318530718, "xmin": 0.0},
+        "save": {"fields": {"t": {"nt": 801}}},
+        "solver": "vlasov-1d", "mlflow": {"experiment": "vlasov1d-test-boltzmann", "run": "iaw-dispersion"},
+        "drivers": {"ex": {}, "ey": {}},
+        "diagnostics": {"diag-vlasov-dfdt": False, "diag-fp-dfdt": False},
+        "terms": {"field": "poisson-boltzmann", "boltzmann_electrons": {"Te": 1.0, "lambda_De": 1.0},
+                  "edfdv": "exponential", "time": "sixth",
+                  "species": [{"name": "ion", "charge": 1.0, "mass": 1.0, "vmax": 0.64, "nv": 256,
+                               "density_components": ["species-ion-background"]}],
+                  "fokker_planck": {"is_on": False, "type": "Dougherty", "time": dict(env), "space": dict(env)},
+                  "krook": {"is_on": False, "time": dict(env), "space": dict(env)}},
+    }
+
+
+def iaw_expected_omega(deck):
+    """test_boltzmann_electrons.py:113-124."""
+    k = deck["density"]["species-ion-background"]["wavenumber"]
+    Te, lam = deck["terms"]["boltzmann_electrons"]["Te"], deck["terms"]["boltzmann_electrons"]["lambda_De"]
+    sp = deck["terms"]["species"][0]
+    T_i = deck["density"]["species-ion-background"]["T0"]
+    return np.sqrt(k**2 * (sp["charge"] * Te / sp["mass"]) / (1 + k**2 * lam**2) + 3 * k**2 * T_i / sp["mass"])
+
+
+def measure_frequency(signal, time_axis, expected_omega):
+    """test_boltzmann_electrons.py:31-43: dominant frequency of the k = 1 box mode over the last 3/4 of the run."""
+    nx = signal.shape[1]
+    mode = 2.0 / nx * np.fft.fft(signal, axis=1)[:, 1]
+    late = mode[len(time_axis) // 4:]
+    dt = time_axis[1] - time_axis[0]
+    omega_axis = 2 * np.pi * np.fft.fftfreq(len(late), dt)
+    spectrum = np.abs(np.fft.fft(late))
+    search = (omega_axis > expected_omega / 5) & (omega_axis < 5 * expected_omega)
+    return omega_axis[search][np.argmax(spectrum[search])]
+
+
+def test_boltzmann_field_solver_matches_screened_poisson():
+    """test_boltzmann_electrons.py:46-75: n_i = n_0 (1 + eps cos kx) gives E = Te eps k / (1 + k^2 lambda_De^2) sin kx
+    for lambda_De = 1, 0 and None (-> sqrt(Te / n_0))."""
+    nx, nv = 64, 256
+    length = 2 * np.pi / 0.1
+    dx = length / nx
+    x = np.linspace(dx / 2, length - dx / 2, nx)
+    kx = np.fft.fftfreq(nx, d=dx) * 2 * np.pi
+    vmax, k, eps, Te = 0.64, 0.1, 1e-3, 1.0
+    dv = 2 * vmax / nv
+    v = np.linspace(-vmax + dv / 2, vmax - dv / 2, nv)
+    f = (1 + eps * np.cos(k * x))[:, None] * (np.exp(-(v**2) / 0.02) / np.sqrt(2 * np.pi * 0.01))[None, :]
+    rho = 1.0 * np.sum(f, axis=1) * dv
+    for lam, screening in [(1.0, 1 + k**2), (0.0, 1.0), (None, 1 + k**2 * Te)]:
+        e = O.boltzmann_poisson(rho, kx, Te, lam)
+        np.testing.assert_allclose(e, Te * eps * k / screening * np.sin(k * x), atol=1e-8 * eps * k)
+
+
+def test_iaw_dispersion_boltzmann_oracle():
+    """test_boltzmann_electrons.py:109-135 for the oracle: the ion-acoustic frequency of the full run (8000 sixth-order
+    steps) matches omega^2 = k^2 cs^2 / (1 + k^2 lambda_De^2) + 3 k^2 vti^2 to 5 %."""
+    deck = boltzmann_iaw_deck()
+    cfg = O.build_cfg(deck)
+    vf = O.VlasovMaxwell(cfg)
+    y = O.init_state(cfg)
+    dt, dv = cfg["grid"]["dt"], cfg["grid"]["species_grids"]["ion"]["dv"]
+    n_hist, t_hist = [np.sum(y["ion"], axis=1) * dv], [0.0]
+    for n in range(8000):
+        y = vf(n * dt, y, None)
+        if (n + 1) % 10 == 0:  # save.fields.t.nt = 801 over [0, 2000]: every 10th step, no interpolation needed
+            n_hist.append(np.sum(y["ion"], axis=1) * dv)
+            t_hist.append((n + 1) * dt)
+    want = iaw_expected_omega(deck)
+    got = measure_frequency(np.array(n_hist), np.array(t_hist), want)
+    np.testing.assert_allclose(got, want, rtol=0.05)
