@@ -280,3 +280,27 @@ def test_iaw_dispersion_boltzmann_on_gpu():
         if (n + 1) % 10 == 0:
             ref = np.sum(y["ion"], axis=1) * dv
             assert np.max(np.abs(n_hist[(n + 1) // 10] - ref)) <= 1e-9 * np.max(np.abs(ref - 1.0)) + 1e-13
+
+
+def test_ex_driver_quiver_on_gpu():
+    """tests/test_vlasov1d/test_ex_driver_quiver.py:146-203 on the GPU path: the quiver velocity amplitude of electrons
+    in the driver field is a0 to 5 %."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from test_oracle_operators import ex_quiver_deck, quiver_amplitude
+
+    from adept_b200.module import Vlasov1D
+
+    deck, a0, k0, w0 = ex_quiver_deck()
+    sim = Vlasov1D(deepcopy(deck))
+    sg = sim.cfg["grid"]["species_grids"]["electron"]
+    v, dv, dt = torch.as_tensor(np.asarray(sg["v"]), device="cuda"), float(sg["dv"]), sim.grid.dt
+    mv = lambda f: (f * v[None, :]).sum(dim=1) / f.sum(dim=1)  # noqa: E731  (dv cancels)
+    hist, ts = [mv(sim.state["electron"])], [0.0]
+    for n in range(2000):
+        sim.step()
+        if (n + 1) % 4 == 0:
+            hist.append(mv(sim.state["electron"]))
+            ts.append((n + 1) * dt)
+    amp = quiver_amplitude(torch.stack(hist).cpu().numpy(), np.array(ts), w0)
+    assert abs(amp - a0) / a0 < 0.05

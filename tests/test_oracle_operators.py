@@ -549,3 +549,60 @@ def test_iaw_dispersion_boltzmann_oracle():
     want = iaw_expected_omega(deck)
     got = measure_frequency(np.array(n_hist), np.array(t_hist), want)
     np.testing.assert_allclose(got, want, rtol=0.05)
+
+
+# ---- tests/test_vlasov1d/test_ex_driver_quiver.py -------------------------------------------------------------------
+def ex_quiver_deck():
+    """build_config() of test_ex_driver_quiver.py:19-143: a0 = 1e-3, k0 = 0.3, w0 = 10 (far above omega_pe), 32 x 128,
+    dt = 0.01, 2001 leapfrog steps, no collisions."""
+    env0 = {"baseline": 0.0, "bump_or_trough": "bump", "center": 0.0, "rise": 1.0, "slope": 0.0, "bump_height": 0.0,
+            "width": 1.0}
+    a0, k0, w0 = 1e-3, 0.3, 10.0
+    deck = {
+        "solver": "vlasov-1d",
+        "units": {"laser_wavelength": "351nm", "normalizing_temperature": "2000eV", "normalizing_density": "1e18/cc",
+                  "Z": 1, "Zp": 1},
+        "density": {"quasineutrality": True,
+                    "species-background": {"noise_seed": 42, "noise_type": "uniform", "noise_val": 0.0, "v0": 0.0,
+                                           "T0": 1.0, "m": 2.0, "basis": "uniform"}},
+        "grid": {"dt": 0.01, "nv": 128, "nx": 32, "tmin": 0.0, "tmax": 20.0, "vmax": 6.4, "xmin": 0.0,
+                 "xmax": float(2 * np.pi / k0)},
+        "save": {"fields": {"t": {"tmin": 0.0, "tmax": 20.0, "nt": 501}}},
+        "mlflow": {"experiment": "test-ex-driver-quiver", "run": "test"},
+        "drivers": {"ex": {"0": {"params": {"a0": a0, "k0": k0, "w0": w0, "dw0": 0.0},
+                                 "envelope": {"time": {"center": 1000.0, "rise": 5.0, "width": 2000.0},
+                                              "space": {"center": 0.0, "rise": 10.0, "width": 1e6}}}},
+                    "ey": {}},
+        "diagnostics": {"diag-vlasov-dfdt": False, "diag-fp-dfdt": False},
+        "terms": {"field": "poisson", "edfdv": "exponential", "time": "leapfrog",
+                  "fokker_planck": {"is_on": False, "type": "Dougherty", "time": dict(env0), "space": dict(env0)},
+                  "krook": {"is_on": False, "time": dict(env0), "space": dict(env0)}},
+    }
+    return deck, a0, k0, w0
+
+
+def quiver_amplitude(mean_v, t, w0):
+    """test_ex_driver_quiver.py:175-191: k0 Fourier mode of <v>(x, t), matched filter at the driver frequency over
+    t > 2."""
+    nx = mean_v.shape[1]
+    k1 = np.fft.fft(mean_v, axis=1)[:, 1] * (2.0 / nx)
+    late = t > 2.0
+    return np.abs(np.mean(k1[late] * np.exp(1j * w0 * t[late])))
+
+
+def test_ex_driver_quiver_oracle():
+    """An electron in E = w a0 sin(kx - wt) quivers with velocity amplitude a0 (test_ex_driver_quiver.py:146-203)."""
+    deck, a0, k0, w0 = ex_quiver_deck()
+    cfg = O.build_cfg(deck)
+    vf = O.VlasovMaxwell(cfg)
+    y = O.init_state(cfg)
+    v, dv, dt = cfg["grid"]["species_grids"]["electron"]["v"], cfg["grid"]["species_grids"]["electron"]["dv"], cfg["grid"]["dt"]
+    mv = lambda f: (np.sum(f * v[None, :], axis=1) * dv) / (np.sum(f, axis=1) * dv)  # noqa: E731
+    hist, ts = [mv(y["electron"])], [0.0]
+    for n in range(2000):
+        y = vf(n * dt, y, None)
+        if (n + 1) % 4 == 0:  # the save axis: 501 points over [0, 20]
+            hist.append(mv(y["electron"]))
+            ts.append((n + 1) * dt)
+    amp = quiver_amplitude(np.array(hist), np.array(ts), w0)
+    assert abs(amp - a0) / a0 < 0.05
