@@ -246,6 +246,10 @@ def build_cfg(cfg_in: dict) -> dict:
         n_prof_total += n_prof_s
     grid["n_prof_total"] = n_prof_total
     grid["ion_charge"] = np.zeros_like(n_prof_total) if len(species) > 1 else n_prof_total.copy()
+    if len(species) == 1 and "electron" in grid["species_grids"]:  # modules.py:269-275 (grid-level aliases)
+        for k in ("v", "kv", "kvr", "one_over_kv", "one_over_kvr"):
+            if k in grid["species_grids"]["electron"]:
+                grid[k] = grid["species_grids"]["electron"][k]
     cfg["grid"] = {**gin, **grid}
     cfg.setdefault("diagnostics", {"diag-vlasov-dfdt": False, "diag-fp-dfdt": False})
     return cfg

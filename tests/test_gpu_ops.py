@@ -677,3 +677,31 @@ def test_boltzmann_field_solver_matches_screened_poisson_on_gpu(ops):
     for lam, screening in [(1.0, 1 + k**2), (0.0, 1.0), (None, 1 + k**2 * Te)]:
         e = host(ops.poisson(rho, dev(kx), mode=1, Te=Te, lambda_De=-1.0 if lam is None else lam))
         np.testing.assert_allclose(e, Te * eps * k / screening * np.sin(k * x), atol=1e-8 * eps * k)
+
+
+def test_collisions_conserve_density_on_asymmetric_grid_gpu():
+    """tests/test_vlasov1d/test_asymmetric_velocity_grid.py:109-137 through the host Collisions object and the kernel:
+    Fokker-Planck + Krook of resonance.yaml on vmin = -5, vmax = 8 conserve density to 1e-6 and match the oracle."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from copy import deepcopy
+    from pathlib import Path
+
+    import yaml
+
+    from adept_b200 import pushers
+    from adept_b200.config import build_cfg
+
+    with open(Path(__file__).parent / "golden" / "resonance.yaml") as fh:
+        d = yaml.safe_load(fh)
+    d["grid"].update(vmin=-5.0, vmax=8.0)
+    cfg, grid = build_cfg(deepcopy(d))
+    g = cfg["grid"]
+    dv = g["species_grids"]["electron"]["dv"]
+    f0 = np.asarray(g["species_distributions"]["electron"][1])
+    nu = np.ones(f0.shape[0])
+    f1 = host(pushers.Collisions(cfg)(dev(nu), dev(nu), dev(f0), grid.dt))
+    assert np.all(np.isfinite(f1))
+    np.testing.assert_allclose(f1.sum(axis=1) * dv, f0.sum(axis=1) * dv, rtol=1e-6)
+    ref = O.Collisions(O.build_cfg(deepcopy(d)))(nu, nu, f0, grid.dt)
+    assert rel_l2(f1, ref) <= 1e-11

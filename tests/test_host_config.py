@@ -101,3 +101,81 @@ def test_stochastic_driver_matches_oracle_realisation():
     assert abs(rms / 0.5 - 1.0) < 0.05
     with pytest.raises(ValueError):
         pushers.StochasticDriver({"modes": [0], "amplitude": 1.0, "tau": 1.0}, G)
+
+
+def test_nonuniform_density_quasineutral_init():
+    """tests/test_vlasov1d/test_quasineutral_init.py: with a tanh density profile the static ion background cancels the
+    electron charge of the initial state, so the charge density and the Poisson field vanish (atol 1e-6) - for the
+    oracle's initialiser and for the host's (adept_b200.config), whose state feeds the kernels."""
+    with open(GOLD / "resonance.yaml") as fh:
+        deck = yaml.safe_load(fh)
+    deck["density"]["species-background"].update(basis="tanh", baseline=1.0, bump_height=0.1, bump_or_trough="bump",
+                                                 width=10.0, center=10.0, rise=2.0)
+    deck["drivers"]["ex"] = {}
+    for build in (lambda d: O.build_cfg(d), lambda d: build_cfg(d)[0]):
+        cfg = build(deepcopy(deck))
+        g = cfg["grid"]
+        ion = np.asarray(g["ion_charge"])
+        assert float(np.max(ion) - np.min(ion)) > 0.01  # the background is non-uniform
+        f_dict = {name: np.asarray(d[1]) for name, d in g["species_distributions"].items()}
+        rho = O.charge_density(f_dict, g["species_grids"], g["species_params"], ion)
+        np.testing.assert_allclose(rho, 0.0, atol=1e-6)
+        np.testing.assert_allclose(O.poisson(rho, np.asarray(g["one_over_kx"])), 0.0, atol=1e-6)
+
+
+# ---- tests/test_vlasov1d/test_asymmetric_velocity_grid.py, for the oracle's and the host's config builders ------------
+def _assert_grid(sg, vmin, vmax, nv):
+    dv = (vmax - vmin) / nv
+    v = np.asarray(sg["v"])
+    assert sg["nv"] == nv and len(v) == nv
+    assert np.isclose(sg["vmin"], vmin) and np.isclose(sg["vmax"], vmax) and np.isclose(sg["dv"], dv)
+    assert np.isclose(v[0], vmin + dv / 2.0) and np.isclose(v[-1], vmax - dv / 2.0)
+    assert np.allclose(np.diff(v), dv)
+
+
+BUILDERS = {"oracle": lambda d: O.build_cfg(d), "host": lambda d: build_cfg(d)[0]}
+
+
+@pytest.mark.parametrize("which", list(BUILDERS))
+def test_asymmetric_velocity_grids(which):
+    """:45-106: grid-level vmin/vmax, the symmetric default, a per-species override, and the normalisation of f."""
+    build = BUILDERS[which]
+    with open(GOLD / "resonance.yaml") as fh:
+        res = yaml.safe_load(fh)
+    with open(GOLD / "multispecies_ion_acoustic.yaml") as fh:
+        multi = yaml.safe_load(fh)
+    d = deepcopy(res)
+    d["grid"].update(vmin=-4.0, vmax=8.0)
+    g = build(d)["grid"]
+    _assert_grid(g["species_grids"]["electron"], -4.0, 8.0, d["grid"]["nv"])
+    np.testing.assert_allclose(np.asarray(g["v"]), np.asarray(g["species_grids"]["electron"]["v"]))
+    d = deepcopy(res)
+    d["grid"].pop("vmin", None)
+    _assert_grid(build(d)["grid"]["species_grids"]["electron"], -d["grid"]["vmax"], d["grid"]["vmax"], d["grid"]["nv"])
+    d = deepcopy(multi)
+    el = next(s for s in d["terms"]["species"] if s["name"] == "electron")
+    ion = next(s for s in d["terms"]["species"] if s["name"] == "ion")
+    el.update(vmin=-3.0, vmax=9.0)
+    sgs = build(d)["grid"]["species_grids"]
+    _assert_grid(sgs["electron"], -3.0, 9.0, el["nv"])
+    _assert_grid(sgs["ion"], -ion["vmax"], ion["vmax"], ion["nv"])
+    d = deepcopy(res)
+    d["grid"].update(vmin=-5.0, vmax=10.0)
+    g = build(d)["grid"]
+    f = np.asarray(g["species_distributions"]["electron"][1])
+    np.testing.assert_allclose(f.sum(axis=1) * g["species_grids"]["electron"]["dv"], 1.0, rtol=1e-3)
+
+
+def test_collisions_conserve_density_on_asymmetric_grid_oracle():
+    """:109-137: Fokker-Planck + Krook of resonance.yaml on vmin = -5, vmax = 8 conserve density to 1e-6."""
+    with open(GOLD / "resonance.yaml") as fh:
+        d = yaml.safe_load(fh)
+    d["grid"].update(vmin=-5.0, vmax=8.0)
+    cfg = O.build_cfg(d)
+    g = cfg["grid"]
+    dv = g["species_grids"]["electron"]["dv"]
+    f0 = np.asarray(g["species_distributions"]["electron"][1])
+    nu = np.ones(f0.shape[0])
+    f1 = O.Collisions(cfg)(nu, nu, f0, g["dt"])
+    assert np.all(np.isfinite(f1))
+    np.testing.assert_allclose(f1.sum(axis=1) * dv, f0.sum(axis=1) * dv, rtol=1e-6)
