@@ -304,3 +304,39 @@ def test_ex_driver_quiver_on_gpu():
             ts.append((n + 1) * dt)
     amp = quiver_amplitude(torch.stack(hist).cpu().numpy(), np.array(ts), w0)
     assert abs(amp - a0) / a0 < 0.05
+
+
+def test_ion_acoustic_dispersion_multispecies_on_gpu():
+    """tests/test_vlasov1d/test_ion_acoustic_wave.py (test_ion_acoustic_dispersion): kinetic electrons AND ions
+    (m_i = 18360), 10001 sixth-order steps of multispecies_ion_acoustic.yaml at nx = 64; the frequency of the electron
+    density's k = 1 mode matches omega = k cs / sqrt(1 + k^2 lambda_D^2) to 15 %."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from adept_b200.module import Vlasov1D
+
+    deck = load("multispecies_ion_acoustic")
+    deck["grid"]["nx"] = 64
+    deck["terms"]["time"] = "sixth"
+    k = deck["density"]["species-electron-background"]["wavenumber"]
+    ion = deck["terms"]["species"][1]
+    T_e = deck["density"]["species-electron-background"]["T0"]
+    want = np.sqrt(k**2 * (ion["charge"] * T_e / ion["mass"]) / (1 + k**2))
+    sim = Vlasov1D(deepcopy(deck))
+    dv = float(sim.cfg["grid"]["species_grids"]["electron"]["dv"])
+    dt = sim.grid.dt
+    nsteps = sim.grid.nt
+    hist, ts = [sim.state["electron"].sum(dim=1) * dv], [0.0]
+    for n in range(nsteps):
+        sim.step()
+        if (n + 1) % 10 == 0:  # save.fields.t: 1001 points over [0, 5000]
+            hist.append(sim.state["electron"].sum(dim=1) * dv)
+            ts.append((n + 1) * dt)
+    dens, t = torch.stack(hist).cpu().numpy(), np.array(ts)
+    assert np.all(np.isfinite(dens)) and np.std(sim.state["e"].cpu().numpy()) > 0
+    nk1 = 2.0 / dens.shape[1] * np.fft.fft(dens, axis=1)[:, 1]
+    late = nk1[len(t) // 2:]
+    omega = 2 * np.pi * np.fft.fftfreq(len(late), t[1] - t[0])
+    spec = np.abs(np.fft.fft(late))
+    search = (omega > 0) & (omega < 5 * want) & (omega > want / 5)
+    got = omega[search][np.argmax(spec[search])]
+    np.testing.assert_allclose(got, want, rtol=0.15)
