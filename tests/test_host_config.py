@@ -179,3 +179,32 @@ def test_collisions_conserve_density_on_asymmetric_grid_oracle():
     f1 = O.Collisions(cfg)(nu, nu, f0, g["dt"])
     assert np.all(np.isfinite(f1))
     np.testing.assert_allclose(f1.sum(axis=1) * dv, f0.sum(axis=1) * dv, rtol=1e-6)
+
+
+@pytest.mark.parametrize("which", list(BUILDERS))
+def test_multispecies_and_single_species_state_structures(which):
+    """tests/test_vlasov1d/test_multispecies_init.py:11-104: species grids / params / shapes of the two-species deck and
+    the backward-compatible single-species structure (grid-level v, ion background = total density profile)."""
+    build = BUILDERS[which]
+    with open(GOLD / "multispecies_ion_acoustic.yaml") as fh:
+        cfg = build(yaml.safe_load(fh))
+    g = cfg["grid"]
+    assert set(g["species_grids"]) == {"electron", "ion"} and set(g["species_params"]) == {"electron", "ion"}
+    assert np.asarray(g["species_distributions"]["electron"][1]).shape == (32, 512)
+    assert np.asarray(g["species_distributions"]["ion"][1]).shape == (32, 256)
+    eg, ig = g["species_grids"]["electron"], g["species_grids"]["ion"]
+    assert eg["nv"] == 512 and eg["vmax"] == 6.4 and len(eg["v"]) == 512
+    assert ig["nv"] == 256 and ig["vmax"] == 0.005 and len(ig["v"]) == 256
+    ep, ip = g["species_params"]["electron"], g["species_params"]["ion"]
+    assert ep["charge"] == -1.0 and ep["mass"] == 1.0 and ep["charge_to_mass"] == -1.0
+    assert ip["charge"] == 10.0 and ip["mass"] == 18360.0 and np.isclose(ip["charge_to_mass"], 10.0 / 18360.0)
+    assert np.allclose(g["ion_charge"], 0.0)
+    with open(GOLD / "resonance.yaml") as fh:
+        cfg = build(yaml.safe_load(fh))
+    g = cfg["grid"]
+    assert np.asarray(g["species_distributions"]["electron"][1]).shape == (g["nx"], g["nv"])
+    assert len(g["v"]) == g["nv"]
+    assert np.allclose(g["ion_charge"], g["n_prof_total"])
+    if which == "oracle":  # the state dict of modules.py:279-317
+        y = O.init_state(cfg)
+        assert {"electron", "e", "de", "a", "da", "prev_a"} <= set(y)
