@@ -208,3 +208,26 @@ def test_multispecies_and_single_species_state_structures(which):
     if which == "oracle":  # the state dict of modules.py:279-317
         y = O.init_state(cfg)
         assert {"electron", "e", "de", "a", "da", "prev_a"} <= set(y)
+
+
+def test_two_component_species_like_twostream():
+    """configs/vlasov-1d/twostream.yaml: one electron species built from two drifting density components
+    (helpers.py:136-153 sums them); host and oracle initialisers agree, the two beams are there, density is 1."""
+    with open(GOLD / "epw.yaml") as fh:
+        deck = yaml.safe_load(fh)
+    comp = {"noise_seed": 420, "noise_type": "gaussian", "noise_val": 0.0, "T0": 0.2, "m": 2.0, "basis": "sine",
+            "baseline": 0.5, "wavenumber": 0.3}
+    deck["density"] = {"quasineutrality": True, "species-electron1": dict(comp, v0=-1.5, amplitude=1.0e-4),
+                       "species-electron2": dict(comp, v0=1.5, amplitude=-1.0e-4)}
+    deck["grid"].update(nx=64, nv=512)
+    host_cfg, _ = build_cfg(deepcopy(deck))
+    ora_cfg = O.build_cfg(deepcopy(deck))
+    fh_, fo = (np.asarray(c["grid"]["species_distributions"]["electron"][1]) for c in (host_cfg, ora_cfg))
+    np.testing.assert_allclose(fh_, fo, rtol=1e-14, atol=1e-300)
+    g = host_cfg["grid"]
+    v, dv = np.asarray(g["species_grids"]["electron"]["v"]), g["species_grids"]["electron"]["dv"]
+    np.testing.assert_allclose(fh_.sum(axis=1) * dv, 1.0, rtol=1e-3)
+    row = fh_[0]
+    assert abs(v[np.argmax(np.where(v < 0, row, 0))] + 1.5) < 2 * dv and abs(v[np.argmax(np.where(v > 0, row, 0))] - 1.5) < 2 * dv
+    assert row[np.argmin(np.abs(v))] < 1e-2 * row.max()  # the beams are separated: exp(-1.5^2 / 0.4) = 3.6e-3
+    np.testing.assert_allclose(g["ion_charge"], g["n_prof_total"])
