@@ -340,3 +340,24 @@ def test_ion_acoustic_dispersion_multispecies_on_gpu():
     search = (omega > 0) & (omega < 5 * want) & (omega > want / 5)
     got = omega[search][np.argmax(spec[search])]
     np.testing.assert_allclose(got, want, rtol=0.15)
+
+
+@pytest.mark.parametrize("operator_type", ["chang_cooper_dougherty", "chang_cooper", "Dougherty", "Lenard_Bernstein",
+                                           "dougherty_nodrag"])
+def test_fokker_planck_conservation_run_on_gpu(operator_type):
+    """tests/test_vlasov1d/test_fokker_planck_conservation.py on the GPU path: the whole deck, every operator type,
+    density to 1e-10 and energy to 1e-6 at every grid point and step."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from test_oracle_operators import check_fp_conservation
+
+    from adept_b200.module import Vlasov1D
+
+    deck = load("fokker_planck_conservation")
+    deck["terms"]["fokker_planck"]["type"] = operator_type
+    sim = Vlasov1D(deepcopy(deck))
+    hist = [sim.state["electron"].cpu().numpy()]
+    for _ in range(sim.grid.nt - 1):
+        sim.step()
+        hist.append(sim.state["electron"].cpu().numpy())
+    check_fp_conservation(hist, sim.cfg)

@@ -606,3 +606,37 @@ def test_ex_driver_quiver_oracle():
             ts.append((n + 1) * dt)
     amp = quiver_amplitude(np.array(hist), np.array(ts), w0)
     assert abs(amp - a0) / a0 < 0.05
+
+
+# ---- tests/test_vlasov1d/test_fokker_planck_conservation.py -------------------------------------------------------------
+FP_CONSERVATION_TYPES = ["chang_cooper_dougherty", "chang_cooper", "Dougherty", "Lenard_Bernstein", "dougherty_nodrag"]
+
+
+def check_fp_conservation(f_hist, cfg):
+    """:47-83: density to 1e-10 and energy sum f v^2 dv to 1e-6 at every grid point and every saved time."""
+    g = cfg["grid"]
+    dv = g["vmax"] * 2.0 / g["nv"]
+    v = np.linspace(-g["vmax"] + dv / 2, g["vmax"] - dv / 2, g["nv"])
+    f = np.asarray(f_hist)
+    density, energy = np.sum(f, axis=-1) * dv, np.sum(f * v**2, axis=-1) * dv
+    assert np.max(np.abs(density - density[0:1]) / density[0:1]) < 1e-10
+    assert np.max(np.abs(energy - energy[0:1]) / energy[0:1]) < 1e-6
+
+
+@pytest.mark.parametrize("operator_type", FP_CONSERVATION_TYPES)
+def test_fokker_planck_conservation_oracle(operator_type):
+    """The full fokker_planck_conservation.yaml run (101 leapfrog + cubic-spline steps with collisions) conserves
+    density and energy for every operator type the reference parametrises."""
+    import yaml
+
+    with open(Path(__file__).parent / "golden" / "fokker_planck_conservation.yaml") as fh:
+        deck = yaml.safe_load(fh)
+    deck["terms"]["fokker_planck"]["type"] = operator_type
+    cfg = O.build_cfg(deck)
+    vf = O.VlasovMaxwell(cfg)
+    y = O.init_state(cfg)
+    hist = [y["electron"].copy()]
+    for n in range(cfg["grid"]["nt"] - 1):
+        y = vf(n * cfg["grid"]["dt"], y, None)
+        hist.append(y["electron"].copy())
+    check_fp_conservation(hist, cfg)
