@@ -17,7 +17,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libadept_b200.so"
-SOURCES = ["api.cu", "push.cu", "vdfdx_tma.cu", "rowops.cu", "field.cu", "collide.cu", "step.cu", "backward.cu", "vrow.cu", "bluestein.cu"]
+SOURCES = ["api.cu", "push.cu", "vdfdx_tma.cu", "vdfdx_dual.cu", "rowops.cu", "field.cu", "collide.cu", "step.cu", "backward.cu", "vrow.cu", "bluestein.cu"]
 NVCC_FLAGS = [
     "-O3",
     "-std=c++17",

@@ -96,5 +96,11 @@ int vdfdx_tma_f64(const double* fin, double* fout, int batch, int nx, int nv, co
                   const double* k1_batch, double k1, double* partial, cudaStream_t stream,
                   const double* filt = nullptr, const FieldTail* field = nullptr);
 bool vdfdx_tma_field_supported(int batch, int nx, int nv);
+// vdfdx_dual.cu: two transforms per thread (nx = 4096); same contract as vdfdx_tma_f64
+bool vdfdx_dual_supported(int nx);
+int vdfdx_dual_parts(int batch, int nx, int nv);
+int vdfdx_dual_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* v, double dt,
+                   const double* k1_batch, double k1, double* partial, cudaStream_t stream, const double* filt,
+                   const FieldTail* field);
 
 }  // namespace adept

@@ -15,8 +15,12 @@
 // The next tile's TMA load is issued as soon as the last inverse pass has read the buffer, so it overlaps the stores.
 #include <cuda.h>
 
+#include <stdlib.h>
+#include <string.h>
+
 #include <mutex>
 
+#include "field_tail.cuh"
 #include "internal.h"
 #include "push_core.cuh"
 #include "tma.cuh"
@@ -182,126 +186,9 @@ __global__ void __launch_bounds__(TmaCfg<LOGN>::THREADS, 1)
   if (!FIELD && K::NSTAGE > 0 && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 
   if constexpr (FIELD) {
-    // ---- field solve in the tail (batch == 1, one species): see FieldTail in internal.h ---------------------------
-    // Every global load of a phase is issued before its first use (the phases are chains of L2 round trips otherwise).
-    const FieldTail& ft = p.ft;
-    const unsigned int G = gridDim.x;
-    double* rho_s = reinterpret_cast<double*>(tile);  // the exchange buffer is dead: rho[N] | green[N]
-    double* g_s = rho_s + N;
-    double* red = rho_acc;                            // [NGRP groups][32 columns], dead after the last flush
-    constexpr int NGRP = K::THREADS / 32;
-    constexpr int PER_T = N / K::THREADS;             // 8 grid points per thread
-    const int colr = tid & 31, grp = tid >> 5;        // warp `grp` sums the partial rows grp, grp + NGRP, ...
-    grid_arrive(ft.counter);  // this CTA's partial row is complete
-    {  // the Green's function does not depend on the other CTAs: fetched while the barrier fills
-      double gv[PER_T];
-#pragma unroll
-      for (int u = 0; u < PER_T; u++) gv[u] = __ldg(ft.green + tid + u * K::THREADS);
-#pragma unroll
-      for (int u = 0; u < PER_T; u++) {  // twice in a row: a window of the convolution never wraps
-        g_s[tid + u * K::THREADS] = gv[u];
-        g_s[tid + u * K::THREADS + N] = gv[u];
-      }
-    }
-    grid_wait(ft.counter, G);  // every CTA's partial row is complete
-    const int per = (N + (int)G - 1) / (int)G;
-    const int i_lo = (int)blockIdx.x * per, i_hi = min(N, i_lo + per);
-    for (int c0 = i_lo; c0 < i_hi; c0 += 32) {
-      const int i = c0 + colr;
-      double s0 = 0.0, s1 = 0.0;
-      if (i < i_hi) {
-        for (unsigned int q0 = grp; q0 < G; q0 += 10 * NGRP) {
-          double x[10];
-#pragma unroll
-          for (int u = 0; u < 10; u++) {
-            const unsigned int q = q0 + u * NGRP;
-            x[u] = q < G ? __ldcg(p.partial + (size_t)q * N + i) : 0.0;
-          }
-#pragma unroll
-          for (int u = 0; u < 10; u += 2) s0 += x[u], s1 += x[u + 1];
-        }
-      }
-      __syncthreads();
-      red[grp * 32 + colr] = s0 + s1;
-      __syncthreads();
-      if (grp == 0 && i < i_hi) {
-        double tot = 0.0;
-#pragma unroll
-        for (int g2 = 0; g2 < NGRP; g2++) tot += red[g2 * 32 + colr];
-        const double term = __dmul_rn(ft.charge, __dmul_rn(tot, ft.dv));  // field.py:197-208
-        ft.rho[i] = ft.base ? __dadd_rn(ft.base[i], term) : term;
-      }
-      if (grp == 1 && i < i_hi) {
-        const double lo = __dmul_rn(ft.a[i], ft.a[i]), hi = __dmul_rn(ft.a[i + 2], ft.a[i + 2]);
-        ft.pond[i] = __dmul_rn(-0.5, __ddiv_rn(__dsub_rn(hi, lo), __dmul_rn(2.0, ft.dx)));  // field.py:495
-      }
-      if (grp == 2 % NGRP && i < i_hi && ft.n_ex > 0) {  // field.py:21-33
-        double total = 0.0;
-        for (int d = 0; d < ft.n_ex; d++) {
-          const double factor = __dmul_rn(ft.ex_tenv[d], ft.ex_space[(size_t)d * N + i]);
-          const double amp = __dmul_rn(__dmul_rn(factor, ft.ex_w[d]), ft.ex_a0[d]);
-          total = __dadd_rn(total, __dmul_rn(amp, sin(__dsub_rn(ft.ex_kx[(size_t)d * N + i], ft.ex_wt[d]))));
-        }
-        ft.dex[i] = total;
-      }
-    }
-    grid_barrier(ft.counter, 2 * G);  // rho complete on every CTA
-    {
-      double rv[PER_T];
-#pragma unroll
-      for (int u = 0; u < PER_T; u++) rv[u] = __ldcg(ft.rho + tid + u * K::THREADS);
-#pragma unroll
-      for (int u = 0; u < PER_T; u++) rho_s[tid + u * K::THREADS] = rv[u];
-    }
-    __syncthreads();
-    // E_i = sum_j green[(i - j) mod N] rho_j.  Fetching both operands of every product costs 16 bytes of shared memory
-    // per multiply-add (14 k wavefronts for 28 outputs: the largest item of the tail), so where the slice allows it the
-    // sum is register-tiled like poisson_green_kernel (field.cu): a lane owns two consecutive j and eight consecutive
-    // outputs, 6 aligned 16-byte loads per 16 multiply-adds.
-    if (NGRP == 16 && (per & 1) == 0 && per <= 32) {
-      double* part = rho_s + 3 * N;              // [4 j ranges][32 outputs]
-      const int og = grp & 3, jr = grp >> 2;
-      const int i0 = i_lo + 8 * og;
-      double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-      if (i0 < i_hi) {
-        for (int j = jr * (N / 4) + 2 * colr; j < (jr + 1) * (N / 4); j += 64) {
-          const double2 r2 = *reinterpret_cast<const double2*>(rho_s + j);
-          // g2 index of (output i0 + r, column j + d): m0 + r + 2 - d with m0 = i0 - j - 2 + N (even)
-          const double2* wp = reinterpret_cast<const double2*>(g_s + (i0 - j - 2 + N));
-          double w[10];
-#pragma unroll
-          for (int q = 0; q < 5; q++) {
-            const double2 t2 = wp[q];
-            w[2 * q] = t2.x, w[2 * q + 1] = t2.y;
-          }
-#pragma unroll
-          for (int r = 0; r < 8; r++) acc[r] = fma(w[r + 1], r2.y, fma(w[r + 2], r2.x, acc[r]));
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < 8; r++) acc[r] = warp_sum(acc[r]);
-      if (colr == 0) {
-#pragma unroll
-        for (int r = 0; r < 8; r++) part[jr * 32 + og * 8 + r] = acc[r];
-      }
-      __syncthreads();
-      if (tid < 32 && i_lo + tid < i_hi)
-        ft.e[i_lo + tid] = (part[tid] + part[32 + tid]) + (part[64 + tid] + part[96 + tid]);
-    } else
-    for (int i = i_lo + grp; i < i_hi; i += NGRP) {
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll 4
-      for (int j = colr; j < N; j += 128) {  // N is a multiple of 128
-        a0 = fma(g_s[(i - j) & (N - 1)], rho_s[j], a0);
-        a1 = fma(g_s[(i - j - 32) & (N - 1)], rho_s[j + 32], a1);
-        a2 = fma(g_s[(i - j - 64) & (N - 1)], rho_s[j + 64], a2);
-        a3 = fma(g_s[(i - j - 96) & (N - 1)], rho_s[j + 96], a3);
-      }
-      const double e = warp_sum((a0 + a1) + (a2 + a3));
-      if (colr == 0) ft.e[i] = e;
-    }
-    __syncthreads();
-    if (tid == 0 && atomicAdd(ft.counter, 1u) == 3 * G - 1) *ft.counter = 0u;  // last one out re-arms the counter
+    // ---- field solve in the tail (batch == 1, one species): field_tail.cuh; the exchange buffer and the row-sum
+    // accumulator are dead after the last flush and serve as its scratch
+    field_tail_solve<N, K::THREADS>(p.ft, p.partial, reinterpret_cast<double*>(tile), rho_acc);
     if (K::NSTAGE > 0 && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 }
@@ -422,9 +309,22 @@ bool vdfdx_tma_supported(const double* fin, const double* fout, int nx, int nv) 
   return get_encoder() != nullptr;
 }
 
+// ADEPT_B200_XPUSH=dual routes nx = 4096 to the two-transforms-per-thread kernel of vdfdx_dual.cu for A/B timing (it
+// is parity-green but slower: 150 us against 128 us, profiles/r02a_*); both use one persistent CTA per SM, so the
+// partial-sum contract is the same.
+static bool use_dual(int nx) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("ADEPT_B200_XPUSH");
+    mode = (e && strcmp(e, "dual") == 0) ? 1 : 0;
+  }
+  return mode == 1 && vdfdx_dual_supported(nx);
+}
+
 // number of partial-sum rows (persistent CTAs) the TMA kernel uses for this shape
 int vdfdx_tma_parts(int batch, int nx, int nv) {
   const int ntiles = batch * (nv / 4);
+  if (use_dual(nx)) return vdfdx_dual_parts(batch, nx, nv);
   switch (ilog2_exact_(nx)) {
     case 8: return tma_ctas<8>(ntiles);
     case 9: return tma_ctas<9>(ntiles);
@@ -474,6 +374,14 @@ bool vdfdx_tma_field_supported(int batch, int nx, int nv) {
 int vdfdx_tma_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* v, double dt,
                   const double* k1_batch, double k1, double* partial, cudaStream_t stream, const double* filt,
                   const FieldTail* field) {
+  if (use_dual(nx)) {
+    if (field && (!vdfdx_tma_field_supported(batch, nx, nv) || !partial || !field->counter || !field->green ||
+                  !field->rho || !field->e || !field->a || !field->pond || field->n_ex < 0 || field->n_ex > 8)) {
+      set_last_error("vdfdx(dual + field): unsupported batch=%d nx=%d nv=%d or missing buffers", batch, nx, nv);
+      return ADEPT_ERR_UNSUPPORTED;
+    }
+    return vdfdx_dual_f64(fin, fout, batch, nx, nv, v, dt, k1_batch, k1, partial, stream, filt, field);
+  }
   const int logn = ilog2_exact_(nx);
   CUtensorMap map;
   const int box_rows = nx < 256 ? nx : 256;

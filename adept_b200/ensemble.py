@@ -52,8 +52,12 @@ class EnsembleVlasov1D:
         self.nx = _same([int(c["grid"]["nx"]) for c in self.cfgs], "grid.nx")
         self.dt = _same([float(g.dt) for g in self.grids], "grid.dt")
         _same([(c["terms"]["time"], c["terms"]["edfdv"], c["terms"]["field"]) for c in self.cfgs], "terms")
-        _same([(vm.fp_on, vm.krook_on, vm.vpfp.fp.model, vm.vpfp.fp.scheme, vm.vpfp.fp.nodrag) for vm in self.vms],
-              "the collision operators")
+        # everything _static_step takes from member 0: operator type, super-Gaussian exponent, the self-consistent beta
+        # controls and the Krook Maxwellian (reference species T0 / mass); dx only enters through pond (a == 0 here)
+        _same([(vm.fp_on, vm.krook_on, vm.vpfp.fp.model, vm.vpfp.fp.scheme, vm.vpfp.fp.nodrag, vm.vpfp.fp.m,
+                vm.vpfp.fp.sc_steps, vm.vpfp.fp.sc_rtol, vm.vpfp.fp.sc_atol,
+                hash(np.asarray(vm.vpfp.fp.f_mx, dtype=np.float64).tobytes())) for vm in self.vms],
+              "the collision operators (type, m, self_consistent_beta, Krook Maxwellian)")
         self.names = _same([list(c["grid"]["species_grids"].keys()) for c in self.cfgs], "the species list")
         for name in self.names:
             _same([(len(c["grid"]["species_grids"][name]["v"]), float(c["grid"]["species_grids"][name]["v"][0]),

@@ -96,6 +96,11 @@ class ShardedVlasov1D:
             raise NotImplementedError(f"{t['edfdv']} has not been implemented")
         if cfg["drivers"].get("ey") or cfg["diagnostics"].get("diag-vlasov-dfdt") or cfg["diagnostics"].get("diag-fp-dfdt"):
             raise NotImplementedError("sharded grid: Ey drivers and dfdt diagnostics are not implemented")
+        hl = t.get("hou_li_filter")
+        if hl and hl.get("is_on", False):
+            raise NotImplementedError("sharded grid: terms.hou_li_filter is not implemented (it would be dropped)")
+        if cfg["drivers"].get("ex_stochastic") is not None:
+            raise NotImplementedError("sharded grid: drivers.ex_stochastic is not implemented (it would be dropped)")
         g = cfg["grid"]
         self.nx = int(g["nx"])
         if self.nx % self.P:

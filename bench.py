@@ -219,7 +219,7 @@ def time_cufft_stand_in(sim, nx, nv, steps=10):
 # ------------------------------------------------------------------------------------------------ B200 arm
 # algorithmic bytes per cell and launch: one fp64 read + one fp64 write of f per operator application;
 # the fused v-push + collision kernel performs two operator applications per launch (it moves 16 B/cell)
-FULL_PASS = {"vdfdx": 16.0, "vdfdx_tma": 16.0, "vdfdx_tma_field": 16.0, "edfdv_exp": 16.0, "edfdv_spline": 16.0, "collide": 16.0,
+FULL_PASS = {"vdfdx": 16.0, "vdfdx_tma": 16.0, "vdfdx_tma_field": 16.0, "vdfdx_dual": 16.0, "vdfdx_dual_field": 16.0, "edfdv_exp": 16.0, "edfdv_spline": 16.0, "collide": 16.0,
              "vpush_collide": 32.0}
 
 
@@ -232,6 +232,218 @@ def profile_report(lib):
     for line in buf.value.decode().splitlines():
         name, count, ms = line.split()
         out[name] = (int(count), float(ms))
+    return out
+
+
+
+# ------------------------------------------------------------------------------------------------ extras (N > 1)
+def c4_decks(n_members: int, nx: int = 64, nv: int = 512):
+    """BASELINE.json configs[3]: members scan k0 in linspace(0.2, 0.4) x a0 in logspace(-4, -1); every
+    member has its own box length 2 pi / k0 (so its own kx) and a driver matched to the Bohm-Gross frequency."""
+    nk = max(d for d in range(1, int(np.sqrt(n_members)) + 1) if n_members % d == 0)  # 1024 -> 32 x 32, 128 -> 8 x 16
+    na = n_members // nk
+    decks = []
+    for k0 in np.linspace(0.2, 0.4, nk):
+        for a0 in np.logspace(-4, -1, na):
+            d = c3_deck(nx, nv)
+            d["grid"]["xmax"] = float(2 * np.pi / k0)
+            d["density"]["species-background"]["wavenumber"] = float(k0)
+            d["drivers"]["ex"]["0"]["params"].update(k0=float(k0), a0=float(a0), w0=float(np.sqrt(1 + 3 * k0**2)))
+            decks.append(d)
+    return decks
+
+
+def oracle_steps(deck, nsteps, t_start=30.0):
+    """The numpy oracle advanced `nsteps` from t_start (checker only)."""
+    import yaml
+
+    from oracle import vlasov1d as O
+
+    cfg = O.build_cfg(yaml.safe_load(yaml.safe_dump(deck)))
+    vf = O.VlasovMaxwell(cfg)
+    y = O.init_state(cfg)
+    dt = cfg["grid"]["dt"]
+    i0 = int(round(t_start / dt))
+    t = t_start
+    for i in range(nsteps):
+        y = vf(t, y, None)
+        t = (i0 + i + 1) * dt
+    return y
+
+
+def run_sharded_extra(world, rank, nx, nv, K, cells_n1_ms, max_over_ranks, barrier):
+    """BASELINE.json configs[2], second half: the SAME single nx x nv grid sharded along v over the N ranks (the
+    reference's grid.parallel: ["x", "v"]; pushers/vlasov.py:95-101,245-248, fokker_planck.py:435-441): strong scaling.
+    Timed like the main figure (K steps between barriers, CUDA events, max over ranks); parity: 3 steps of a 1024 x
+    2048 sharded grid gathered on rank 0 and compared with the oracle."""
+    import ctypes
+
+    import torch
+    import torch.distributed as dist
+
+    from adept_b200 import _lib
+    from adept_b200.sharded import ShardedVlasov1D
+
+    out = {"what": f"ONE {nx}x{nv} grid sharded along v over {world} GPUs (strong scaling), transposes fused into the "
+                   "v-row kernel over NVLink peer memory"}
+    # ---- parity first (small grid, 3 steps, against the oracle on rank 0) ----------------------------------------
+    pnx, pnv, psteps = 1024, 2048, 3
+    pdeck = c3_deck(pnx, pnv)
+    sim = ShardedVlasov1D(c3_deck(pnx, pnv))
+    sim.t, sim.step_index = 30.0, 300
+    for _ in range(psteps):
+        sim.step()
+    name = sim.names[0]
+    full = sim.gather_full(name).cpu().numpy()
+    e_gpu = sim.state["e"].cpu().numpy()
+    out["parity_mode"] = "p2p" if sim.p2p is not None else "nccl"
+    del sim
+    if rank == 0:
+        y = oracle_steps(pdeck, psteps)
+        out["parity_rel_l2"] = float(np.linalg.norm(full - y[name]) / np.linalg.norm(y[name]))
+        out["parity_e_max_abs"] = float(np.max(np.abs(e_gpu - y["e"])))
+        out["parity_what"] = f"{psteps} steps of a {pnx}x{pnv} grid sharded over {world} ranks vs the numpy oracle"
+    barrier()
+    # ---- timing on the full grid ----------------------------------------------------------------------------------
+    sim = ShardedVlasov1D(c3_deck(nx, nv))
+    sim.t, sim.step_index = 30.0, 300
+    out["transpose"] = "p2p" if sim.p2p is not None else "nccl"
+    for _ in range(30):  # NCCL and the symmetric-memory rendezvous keep initialising lazily for tens of steps
+        sim.step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        sim.step()
+    e1.record()
+    barrier()
+    el = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    lib = _lib.load()
+    lib.adept_b200_profile(1)
+    for _ in range(K):
+        sim.step()
+    torch.cuda.synchronize()
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib.adept_b200_profile_report(buf, len(buf))
+    lib.adept_b200_profile(0)
+    kern = {}
+    for ln in buf.value.decode().splitlines():
+        nm, cnt, ms = ln.split()
+        kern[nm] = round(float(ms) / int(cnt) * 1e3, 1)
+    barrier()
+    del sim
+    out.update({"ms_per_step": el / K * 1e3, "value": nx * nv * K / el, "unit": UNIT, "steps": K,
+                "strong_scaling_vs_n1": (cells_n1_ms / (el / K * 1e3)) if cells_n1_ms else None,
+                "n1_ms_per_step": cells_n1_ms, "rank0_kernel_us": kern})
+    return out
+
+
+def run_c4_extra(world, rank, K, max_over_ranks, barrier, n_members=1024):
+    """BASELINE.json configs[3]: 1024 independent 64 x 512 runs scanning k lambda_D and drive amplitude, members sharded
+    over the ranks with no data-path collective.  Parity: members 0 and -1 of rank 0's slice against the
+    oracle after 3 steps."""
+    import torch
+
+    from adept_b200.ensemble import EnsembleVlasov1D, member_slice
+
+    nx, nv = 64, 512
+    decks = c4_decks(n_members, nx, nv)
+    sl = member_slice(n_members, rank, world)
+    mine = decks[sl]
+    ens = EnsembleVlasov1D(mine)
+    ens.t, ens.step_index = 30.0, 300
+    out = {"what": f"{n_members} independent {nx}x{nv} leapfrog + Dougherty runs (k0 x a0 scan), "
+                   f"{len(mine)} members per GPU, no collective", "members": n_members, "members_per_gpu": len(mine)}
+    for _ in range(3):
+        ens.step()
+    if rank == 0:
+        errs = []
+        for i in (0, len(mine) - 1):
+            y = oracle_steps(mine[i], 3)
+            got = ens.member_state(i)["electron"].cpu().numpy()
+            errs.append(float(np.linalg.norm(got - y["electron"]) / np.linalg.norm(y["electron"])))
+        out["parity_rel_l2"] = max(errs)
+        out["parity_what"] = "members 0 and last of rank 0 after 3 steps vs the numpy oracle"
+    for _ in range(5):
+        ens.step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        ens.step()
+    e1.record()
+    barrier()
+    el = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    cells = n_members * nx * nv
+    out.update({"us_per_step": el / K * 1e6, "value": cells * K / el, "unit": UNIT, "steps": K,
+                "frac_of_48B_roofline_per_gpu": None})
+    del ens
+    return out, cells * K / el
+
+
+
+def _time_steps(step, nsteps, warm=10):
+    import torch
+
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(nsteps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / nsteps
+
+
+def run_single_gpu_extras(nx, nv, peak):
+    """N = 1 only: per-step times of the other BASELINE configs (parity-test cases, reported beside the contract line):
+    C1 = the stock configs/vlasov-1d/epw.yaml (32 x 256, sixth + cubic-spline + Dougherty + both dfdt diagnostics),
+    C2 = 64 x 512 leapfrog + Dougherty, C3 with `time: sixth` (192 B/cell), C4's per-GPU share (128
+    members of 64 x 512)."""
+    import torch
+    import yaml
+
+    from adept_b200.ensemble import EnsembleVlasov1D
+    from adept_b200.module import Vlasov1D
+
+    out = {}
+    with open(ROOT / "tests" / "golden" / "epw.yaml") as fh:
+        c1 = yaml.safe_load(fh)
+    for key, deck, n in (("c1_epw_32x256_sixth_spline", c1, 300), ("c2_64x512_leapfrog_fp", c3_deck(64, 512), 300)):
+        sim = Vlasov1D(deck)
+        sim.t, sim.step_index = 30.0, 300
+        sec = _time_steps(sim.step, n)
+        g = sim.cfg["grid"]
+        entry = {"us_per_step": sec * 1e6, "cells": int(g["nx"]) * int(g["nv"]), "how": "Vlasov1D.step(), host-issued"}
+        try:
+            gsec = sim.graph_steps_per_second(n)  # CUDA-graph replay of the native step (device-resident time tables)
+            entry["us_per_step_cuda_graph"] = 1e6 / gsec
+        except Exception as exc:
+            entry["us_per_step_cuda_graph"] = None
+            entry["graph_unavailable"] = f"{type(exc).__name__}: {exc}"[:200]
+        out[key] = entry
+        del sim
+    d6 = c3_deck(nx, nv)
+    d6["terms"]["time"] = "sixth"
+    sim = Vlasov1D(d6)
+    sim.t, sim.step_index = 30.0, 300
+    sec = _time_steps(sim.step, 10, warm=3)
+    out["c3_sixth"] = {"ms_per_step": sec * 1e3, "value": nx * nv / sec, "unit": UNIT,
+                       "frac_of_192B_roofline": 192.0 * nx * nv / sec / 1e9 / peak,
+                       "what": f"{nx}x{nv} sixth-order Hamiltonian splitting (5 x-pushes, 6 v-pushes, 6 field solves) + "
+                               "Dougherty: 12 operator applications = 192 B/cell"}
+    del sim
+    torch.cuda.empty_cache()
+    ens = EnsembleVlasov1D(c4_decks(128))
+    ens.t, ens.step_index = 30.0, 300
+    sec = _time_steps(ens.step, 100)
+    cells = 128 * 64 * 512
+    out["c4_share_128_members"] = {"us_per_step": sec * 1e6, "value": cells / sec, "unit": UNIT,
+                                   "frac_of_48B_roofline": 48.0 * cells / sec / 1e9 / peak}
+    del ens
+    torch.cuda.empty_cache()
     return out
 
 
@@ -351,32 +563,68 @@ def run_b200(args):
     n_ring = max(K, W, 3)
     diag_host = torch.zeros((n_ring, 2), dtype=torch.float64).pin_memory()
 
-    def e2e_run(nsteps):
+    mom_host = torch.zeros((n_ring, 6), dtype=torch.float64).pin_memory()
+    sgrid = sim.cfg["grid"]["species_grids"][name]
+    v_dev = torch.as_tensor(np.array(sgrid["v"], dtype=np.float64), device="cuda")
+    mom_dev = torch.empty((6, nx), dtype=torch.float64, device="cuda")
+
+    def e2e_run(nsteps, with_save):
         sim.state[name] = f_host.to("cuda", non_blocking=True)
         for i in range(nsteps):
             st = sim.step()
             # the kernel writes the two scalars straight into the pinned host ring (mapped memory): the per-step
             # device-to-host transfer without a separate copy operation on the stream
             ops.field_energy(st["e"], st["de"], out=diag_host[i])
+            if with_save:
+                # the reference's always-on default save (storage.py:282, 306-323): mean_x sum_v {f, f v, f v^2, f v^3,
+                # -|f| log|f|, f^2} dv of the new state, one more pass over f every step, read back per step
+                ops.save_moments(st[name], v_dev, float(sgrid["dv"]), out=mom_dev)
+                mom_host[i].copy_(mom_dev.mean(dim=1), non_blocking=True)
         f_back.copy_(sim.state[name], non_blocking=True)
         torch.cuda.synchronize()
         return float(diag_host[nsteps - 1, 0])
 
-    e2e_run(max(W, 3))
-    barrier()
-    t0 = time.perf_counter()
-    last_e2 = e2e_run(K)
-    e2e_elapsed = max_over_ranks(time.perf_counter() - t0)
-    assert np.isfinite(last_e2) and np.all(np.isfinite(diag_host[:K].numpy()))
+    e2e_res = {}
+    for with_save in (False, True):
+        e2e_run(max(W, 3), with_save)
+        barrier()
+        t0 = time.perf_counter()
+        last_e2 = e2e_run(K, with_save)
+        e2e_res[with_save] = max_over_ranks(time.perf_counter() - t0)
+        assert np.isfinite(last_e2) and np.all(np.isfinite(diag_host[:K].numpy()))
+    assert np.all(np.isfinite(mom_host[:K].numpy())) and abs(float(mom_host[K - 1, 0]) - 1.0) < 1e-6  # mean density
+    e2e_elapsed = e2e_res[True]  # headline: with the default save, as the reference always runs
     e2e_value = world * cells * K / e2e_elapsed
     h2d_bytes = f_host.numel() * 8 / K + C_sizeof_step  # initial state amortised over the run + the step descriptor
-    d2h_bytes = 16 + f_back.numel() * 8 / K
+    d2h_bytes = 16 + 48 + f_back.numel() * 8 / K
+
+    # ---- N > 1 only: the two BASELINE configs that need several GPUs, measured in the same job -------------------
+    extra = {}
+    if world > 1 and not args.no_extras:
+        del f_host, f_back
+        sim.state = None
+        torch.cuda.empty_cache()
+        try:
+            extra["sharded"] = run_sharded_extra(world, rank, nx, nv, K, elapsed / K * 1e3, max_over_ranks, barrier)
+        except Exception as exc:  # an extra must never take the contract line down
+            extra["sharded"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
+        try:
+            c4, c4_value = run_c4_extra(world, rank, K, max_over_ranks, barrier)
+            c4["frac_of_48B_roofline_per_gpu"] = 48.0 * c4_value / world / 1e9 / peak
+            extra["ensemble_c4"] = c4
+        except Exception as exc:
+            extra["ensemble_c4"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
+    if world == 1 and not args.no_extras:
+        try:
+            extra.update(run_single_gpu_extras(nx, nv, peak))
+        except Exception as exc:
+            extra["single_gpu_extras"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
     gpu_library_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         try:
@@ -401,12 +649,15 @@ def run_b200(args):
                    "t_start": t_start},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": e2e_elapsed / K * 1e3,
+                "without_default_save": {"value": world * cells * K / e2e_res[False],
+                                         "ms_per_step": e2e_res[False] / K * 1e3},
                 "what": f"Vlasov1D.step() public API, {K}-step run from and to pinned HOST memory: H2D of f0 and D2H "
                         "of the final f inside the timed region (amortised per step), per-step D2H of mean_e2/mean_de2 "
-                        "(written by the field-energy kernel straight into a pinned, mapped host ring), one host wait "
-                        "at the end of the run"},
+                        "(written by the field-energy kernel straight into a pinned, mapped host ring) and of the six "
+                        "default-save moments of the new state (one more pass over f per step, storage.py:306-323), "
+                        "one host wait at the end of the run; without_default_save = the same without the moment pass"},
         "roofline": roofline, "kernels": per_kernel, "gpu_launches": launches, "clocks": clocks,
-        "cpu_baseline": cpu_baseline, "gpu_library_baseline": gpu_library_baseline,
+        "cpu_baseline": cpu_baseline, "gpu_library_baseline": gpu_library_baseline, "extra": extra,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -422,6 +673,7 @@ def main():
     ap.add_argument("--nx", type=int, default=4096)
     ap.add_argument("--nv", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sharded-grid / C4 / small-deck extras")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -135,6 +135,30 @@ def _bad_worker(rank, world, port, dk):
         dist.destroy_process_group()
 
 
+def _reject_worker(rank, world, port, dk, match):
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        from adept_b200.sharded import ShardedVlasov1D
+
+        with pytest.raises(NotImplementedError, match=match):
+            ShardedVlasov1D(dk, local_ops=object(), device=torch.device("cpu"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("feature", ["hou_li_filter", "ex_stochastic"])
+def test_sharded_rejects_features_it_would_drop(feature):
+    """Decks whose Hou-Li filter or stochastic Ex driver the sharded step does not apply must be refused, not run
+    with the feature silently missing (the single-GPU Vlasov1D and the reference do apply them)."""
+    dk = deck()
+    if feature == "hou_li_filter":
+        dk["terms"]["hou_li_filter"] = {"is_on": True, "alpha": 36.0, "order": 36}
+    else:
+        dk["drivers"]["ex_stochastic"] = {"n_modes": 2, "k_min": 0.3, "k_max": 0.6, "amplitude": 1e-3, "tau": 5.0,
+                                          "seed": 1}
+    mp.spawn(_reject_worker, args=(2, _free_port(), dk, feature), nprocs=2, join=True)
+
+
 # ------------------------------------------------------------------------------ ensembles sharded by members (C4)
 def test_member_slice_covers_every_member_once():
     from adept_b200.ensemble import member_slice
