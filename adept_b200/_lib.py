@@ -49,7 +49,11 @@ class Step(C.Structure):
         ("fp_sc_steps", c_i), ("fp_sc_rtol", c_d), ("fp_sc_atol", c_d),
         ("poisson_green", c_dp),
         ("diag_vlasov_dfdt", c_dp), ("diag_fp_dfdt", c_dp), ("diag_species", c_i), ("hou_li_filt", c_dp),
+        ("time_row", c_dp),
     ]
+
+
+TIME_ROW_LEN = 104  # ADEPT_B200_TIME_ROW_LEN: tenv[6][8] | wt[6][8] | nu_fp_time | nu_K_time | ex_t[6]
 
 
 # name -> argtypes; mirrors include/adept_b200.h one to one (checked by tests/test_abi.py)
@@ -64,6 +68,8 @@ SIGNATURES = {
     "adept_b200_edfdv_exp_bwd_accel_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_dp, c_dp, c_d, c_d, c_d, c_d, c_dp, c_dp],
     "adept_b200_moments_bwd_f64": [C.POINTER(c_dp), C.POINTER(c_d), c_i, c_i, c_i, c_dp, c_i, c_dp, c_dp],
     "adept_b200_collide_bwd_f64": [c_dp, c_dp, c_dp, c_dp, c_dp, c_i, c_i, c_i, c_dp, c_d, c_d, c_dp, c_i, c_i, c_dp],
+    "adept_b200_edfdv_spline_bwd_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_dp, c_dp, c_d, c_d, c_d, c_d, c_dp, c_dp, c_dp],
+    "adept_b200_krook_bwd_f64": [c_dp, c_dp, c_i, c_i, c_i, c_d, c_d, c_dp, c_dp, c_dp, c_dp, c_dp],
     "adept_b200_vpush_collide_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_dp, c_dp, c_d, c_d, c_d, c_d, c_dp, c_d, c_dp,
                                      c_i, c_i, c_dp],
     "adept_b200_vpush_collide_p2p_f64": [C.POINTER(c_dp), C.POINTER(c_dp), c_i, c_ll, c_i, c_i, c_dp, c_dp, c_dp, c_d,
@@ -88,6 +94,7 @@ SIGNATURES = {
     "adept_b200_collide_sc_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_d, c_d, c_dp, c_dp, c_dp, c_i, c_i, c_i, c_d, c_d,
                                   c_dp, c_i, c_d, c_d, c_dp],
     "adept_b200_step_f64": [C.POINTER(Step), c_dp],
+    "adept_b200_time_row_advance": [c_dp, c_ll, c_dp, c_dp, c_dp],
 }
 
 

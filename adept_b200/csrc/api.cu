@@ -14,6 +14,11 @@
 
 namespace adept {
 
+static thread_local const double* tl_time_row = nullptr;
+const double* current_time_row() { return tl_time_row; }
+void set_current_time_row(const double* row) { tl_time_row = row; }
+
+
 static thread_local char g_err[512] = "";
 
 void set_last_error(const char* fmt, ...) {
@@ -308,6 +313,20 @@ int adept_b200_collide_bwd_f64(const double* f_in, const double* f_new, const do
   ADEPT_REQUIRE(v, "v") ADEPT_REQUIRE(nu_fp, "nu_fp")
   return collide_bwd_f64(f_in, f_new, g, f_bar, nu_bar, batch, nx, nv, v, dv, dt, nu_fp, 1.0, model, scheme,
                          (cudaStream_t)stream);
+}
+
+int adept_b200_edfdv_spline_bwd_f64(const double* f_in, const double* g, int batch, int nx, int nv, const double* e,
+                                    const double* dex, const double* pond, double charge, double mass, double dt,
+                                    double dv, double* f_bar, double* accel_bar, void* stream) {
+  ADEPT_REQUIRE(f_in, "f_in") ADEPT_REQUIRE(g, "g") ADEPT_REQUIRE(e, "e")
+  return edfdv_spline_bwd_f64(f_in, g, batch, nx, nv, e, dex, pond, charge, mass, dt, dv, f_bar, accel_bar,
+                              (cudaStream_t)stream);
+}
+
+int adept_b200_krook_bwd_f64(const double* f_in, const double* g, int batch, int nx, int nv, double dv, double dt,
+                             const double* nu_K, const double* f_mx, double* f_bar, double* nu_bar, void* stream) {
+  ADEPT_REQUIRE(f_in, "f_in") ADEPT_REQUIRE(g, "g") ADEPT_REQUIRE(nu_K, "nu_K") ADEPT_REQUIRE(f_mx, "f_mx")
+  return krook_bwd_f64(f_in, g, batch, nx, nv, dv, dt, nu_K, f_mx, f_bar, nu_bar, (cudaStream_t)stream);
 }
 
 int adept_b200_vpush_collide_p2p_f64(const double* const* in_peers_host, double* const* out_peers_host, int n_peers,

@@ -45,6 +45,7 @@ struct CollideArgs {
   double* n_out;          // [rows] or null: sum_j f_out dv
   int rows_per_cta;       // R: x-rows handled by one CTA (set by the launcher)
   double nu_fp_scale, nu_K_scale;  // nu = scale * nu[row] (time envelope applied in the kernel)
+  const double* trow;              // nullable device-resident time row (common.cuh) that replaces the two scales
   int sc_steps;                    // self-consistent beta: Newton iterations (0 = off), fokker_planck.py:296-301
   double sc_rtol, sc_atol;
 };
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(MAXT, MINB) collide_kernel(CollideArgs p) {
   const double vc = __ldg(p.v + i0);        // v of the chunk's first cell; v[i0 + l] = vc + l dv (uniform grid)
 
   if (p.nu_fp) {
-    const double nu = __dmul_rn(p.nu_fp_scale, p.nu_fp[row]);
+    const double nu = __dmul_rn(p.trow ? p.trow[TROW_NU_FP] : p.nu_fp_scale, p.nu_fp[row]);
     // ---- 2. moments in chunk-local index space: sum f, sum f l, sum f l^2 ------------------------------------------
     double mom[3] = {0.0, 0.0, 0.0};
 #pragma unroll
@@ -487,7 +488,7 @@ __global__ void __launch_bounds__(MAXT, MINB) collide_kernel(CollideArgs p) {
     row_reduce<1>(sn, red, parity, live ? r : 0, tt, T, RT, warp_mode, live);
     if (p.nu_K) {
       const double nprof = sn[0] * dv;
-      const double ex = exp(-(dt * __dmul_rn(p.nu_K_scale, p.nu_K[row])));
+      const double ex = exp(-(dt * __dmul_rn(p.trow ? p.trow[TROW_NU_K] : p.nu_K_scale, p.nu_K[row])));
       double s2[1] = {0.0};
 #pragma unroll
       for (int l = 0; l < E; l++) {
@@ -540,9 +541,10 @@ struct CollideBwdArgs {
   const double* nu_fp;
   double nu_fp_scale;
   int model;
+  int scheme;
 };
 
-template <int E, int MAXT>
+template <int E, int MAXT, bool CC>
 __global__ void __launch_bounds__(MAXT, 1) collide_bwd_kernel(CollideBwdArgs p) {
   extern __shared__ __align__(16) double sm[];
   const int nv = p.nv;
@@ -602,6 +604,7 @@ __global__ void __launch_bounds__(MAXT, 1) collide_bwd_kernel(CollideBwdArgs p) 
   const double c2 = 2.0 * beta * D;
   const double q = dtnu * c2 / (2.0 * dv);
   const double w0 = q * (vc + 0.5 * dv - vbar), dq = q * dv;
+  const double ww0 = (2.0 * beta * dv) * (vc + 0.5 * dv - vbar), dww = (2.0 * beta * dv) * dv;  // Chang-Cooper w
   auto edge = [&](int l, double& U, double& L) {
     const int e = i0 + l;
     if (e < 0 || e > nv - 2) {
@@ -610,8 +613,15 @@ __global__ void __launch_bounds__(MAXT, 1) collide_bwd_kernel(CollideBwdArgs p) 
       return;
     }
     const double wq = fma((double)l, dq, w0);
-    U = pD + wq;
-    L = pD - wq;
+    if (!CC) {
+      U = pD + wq;
+      L = pD - wq;
+    } else {  // same coefficients as the forward kernel (collide_core.cuh)
+      const double dl = cc_delta_fast(fma((double)l, dww, ww0));
+      const double cq = 2.0 * wq;
+      U = fma(cq, 1.0 - dl, pD);
+      L = fma(-cq, dl, pD);
+    }
   };
 
   // transposed system: a_i = -U_{i-1}, c_i = -L_i, b_i = 1 + L_i + U_{i-1};
@@ -729,16 +739,29 @@ __global__ void __launch_bounds__(MAXT, 1) collide_bwd_kernel(CollideBwdArgs p) 
       const double fp = (l < E - 1) ? fch[l + 1] : f_next_chunk;
       const double dl = gch[l] - lp;
       const double ve = vc + ((double)l + 0.5) * dv - vbar;
-      bl[0] += dl * (fp - fch[l]);
-      bl[1] += dl * (fp + fch[l]);
-      bl[2] += dl * ve * (fp + fch[l]);
+      if (!CC) {
+        bl[0] += dl * (fp - fch[l]);
+        bl[1] += dl * (fp + fch[l]);
+        bl[2] += dl * ve * (fp + fch[l]);
+      } else {
+        // edge flux (dt nu / dv) [D/dv (f+ - f) + C ((1 - delta) f+ + delta f)], C = c2 (v_e - vbar), delta(w = C dv / D):
+        // its derivatives w.r.t. D and vbar carry delta'(w) through dw/dD = -w/D and dw/dvbar = -c2 dv/D
+        const double w = fma((double)l, dww, ww0);
+        const double de = cc_delta_fast(w), dp = cc_delta_prime_fast(w);
+        const double drag = fma(1.0 - de, fp, de * fch[l]);
+        bl[0] += dl * (fp - fch[l]) * fma(dp, w * w, 1.0);
+        bl[1] += dl * (dp * w * (fp - fch[l]) - drag);
+        bl[2] += dl * ((D / dv) * (fp - fch[l]) + c2 * ve * drag);
+      }
     }
   }
   if (!live) bl[0] = bl[1] = bl[2] = 0.0;
   row_reduce<3>(bl, red, parity, 0, tt, T, T, warp_mode, live);
   const double cD = (dtnu / (dv * dv)) * bl[0];                  // dt nu s_D
-  const double cu = (p.model == FP_LB) ? 0.0 : -q * bl[1];       // dt nu s_u
-  if (p.nubar && t == 0) p.nubar[row] = p.nu_fp_scale * dt * ((D / (dv * dv)) * bl[0] + (c2 / (2.0 * dv)) * bl[2]);
+  const double cu = (p.model == FP_LB) ? 0.0 : (CC ? (dtnu * c2 / dv) * bl[1] : -q * bl[1]);  // dt nu s_u
+  if (p.nubar && t == 0)
+    p.nubar[row] = CC ? p.nu_fp_scale * (dt / dv) * bl[2]
+                      : p.nu_fp_scale * dt * ((D / (dv * dv)) * bl[0] + (c2 / (2.0 * dv)) * bl[2]);
   if (live) {
     double* out = p.fbar + row * nv;
     const double is0 = 1.0 / s0;
@@ -749,8 +772,8 @@ __global__ void __launch_bounds__(MAXT, 1) collide_bwd_kernel(CollideBwdArgs p) 
   }
 }
 
-template <int E, int MAXT>
-static int launch_collide_bwd(const CollideBwdArgs& p, cudaStream_t stream) {
+template <int E, int MAXT, bool CC>
+static int launch_collide_bwd_t(const CollideBwdArgs& p, cudaStream_t stream) {
   const int T = p.nv / E;
   const int threads = ((T + 31) / 32) * 32;
   const size_t smem = ((size_t)2 * (p.nv + T) + p.nv + 2 * (T > 32 ? T : 32) * 3 + 6 * (size_t)T) * sizeof(double);
@@ -761,7 +784,7 @@ static int launch_collide_bwd(const CollideBwdArgs& p, cudaStream_t stream) {
   static size_t configured[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
-  auto kern = collide_bwd_kernel<E, MAXT>;
+  auto kern = collide_bwd_kernel<E, MAXT, CC>;
   if (dev < 64 && configured[dev] < smem) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) {
@@ -775,6 +798,12 @@ static int launch_collide_bwd(const CollideBwdArgs& p, cudaStream_t stream) {
   return check_launch("collide_bwd_kernel");
 }
 
+template <int E, int MAXT>
+static int launch_collide_bwd(const CollideBwdArgs& p, cudaStream_t stream) {
+  return p.scheme == FP_CHANG_COOPER ? launch_collide_bwd_t<E, MAXT, true>(p, stream)
+                                     : launch_collide_bwd_t<E, MAXT, false>(p, stream);
+}
+
 int collide_bwd_f64(const double* fin, const double* fnew, const double* g, double* fbar, double* nubar, int batch,
                     int nx, int nv, const double* v, double dv, double dt, const double* nu_fp, double nu_fp_scale,
                     int model, int scheme, cudaStream_t stream) {
@@ -782,11 +811,11 @@ int collide_bwd_f64(const double* fin, const double* fnew, const double* g, doub
     set_last_error("collide_bwd: bad shape batch=%d nx=%d nv=%d", batch, nx, nv);
     return ADEPT_ERR_BAD_SHAPE;
   }
-  if (scheme != FP_CENTRAL || (model != FP_LB && model != FP_DOUGHERTY)) {
-    set_last_error("collide_bwd: only central differencing with the Lenard-Bernstein / Dougherty models is implemented");
+  if ((scheme != FP_CENTRAL && scheme != FP_CHANG_COOPER) || (model != FP_LB && model != FP_DOUGHERTY)) {
+    set_last_error("collide_bwd: only the Lenard-Bernstein / Dougherty models (central or Chang-Cooper) are implemented");
     return ADEPT_ERR_UNSUPPORTED;
   }
-  CollideBwdArgs p = {fin, fnew, g, fbar, nubar, (long long)batch * nx, nv, v, dv, dt, nu_fp, nu_fp_scale, model};
+  CollideBwdArgs p = {fin, fnew, g, fbar, nubar, (long long)batch * nx, nv, v, dv, dt, nu_fp, nu_fp_scale, model, scheme};
   if (nv % 16 == 0 && nv / 16 <= 256) return launch_collide_bwd<16, 256>(p, stream);
   if (nv % 16 == 0 && nv / 16 <= 512) return launch_collide_bwd<16, 512>(p, stream);
   if (nv % 8 == 0 && nv / 8 <= 256) return launch_collide_bwd<8, 256>(p, stream);
@@ -852,7 +881,7 @@ int collide_f64(const double* fin, double* fout, int batch, int nx, int nv, cons
   }
   CollideArgs p = {fin, fout, (long long)batch * nx, nv, v, dv, dt, nu_fp, nu_K, f_mx,
                    model, scheme, nodrag, sg_m, sg_ratio, n_out, 1, nu_fp_scale, nu_K_scale,
-                   sc_steps, sc_rtol, sc_atol};
+                   current_time_row(), sc_steps, sc_rtol, sc_atol};
   if (sc_steps < 0 || sc_steps > 64) {
     set_last_error("collide: self-consistent beta max_steps=%d out of range [0, 64]", sc_steps);
     return ADEPT_ERR_BAD_ARG;

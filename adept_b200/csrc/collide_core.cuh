@@ -42,6 +42,22 @@ __device__ __forceinline__ double cc_delta_fast(double w) {
   return fast_rcp(w) - fast_rcp(expm1(w));
 }
 
+// d delta / d w of the Chang-Cooper weight delta(w) = 1/w - 1/(e^w - 1) (adjoint kernels): series through w^10 for
+// |w| < 0.3 (next term < 1e-16), closed form -1/w^2 + e^w / (e^w - 1)^2 beyond.
+__device__ __forceinline__ double cc_delta_prime_fast(double w) {
+  if (fabs(w) < 0.3) {
+    const double w2 = w * w;
+    double p = 691.0 / 118879488000.0;      // 11 * 691 / 1307674368000
+    p = fma(p, w2, -1.0 / 5322240.0);       // -9 / 47900160
+    p = fma(p, w2, 1.0 / 172800.0);         // 7 / 1209600
+    p = fma(p, w2, -1.0 / 6048.0);          // -5 / 30240
+    p = fma(p, w2, 1.0 / 240.0);            // 3 / 720
+    return fma(p, w2, -1.0 / 12.0);
+  }
+  const double em = expm1(w);
+  return (em + 1.0) / (em * em) - 1.0 / (w * w);
+}
+
 // Sum NVAL values over the T threads of row r; every thread of the CTA must call it.  warp_mode: T % 32 == 0 (warps do
 // not straddle rows).  `red` is a scratch area of 2 * S * NVAL doubles used with alternating halves, S = 32 in warp
 // mode and max(R*T, 32) otherwise.

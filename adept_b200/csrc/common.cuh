@@ -61,6 +61,16 @@ __device__ __forceinline__ double accel_of(double e, double pond, double q, doub
   return __ddiv_rn(force, m);
 }
 
+// Device-resident time row (adept_b200_step::time_row): when a step descriptor carries one, the kernels take the O(1)
+// time factors of the drivers and collision profiles from it instead of the by-value fields, so that a captured CUDA
+// graph can be replayed for later steps.  Layout (doubles): tenv[s][d] at 8 s + d, wt[s][d] at 48 + 8 s + d, nu_fp_time
+// at 96, nu_K_time at 97, ex_t[s] at 98 + s.
+enum { TROW_TENV = 0, TROW_WT = 48, TROW_NU_FP = 96, TROW_NU_K = 97, TROW_EX_T = 98, TROW_LEN = 104 };
+// the row of the step being enqueued by this host thread (step.cu sets it around adept_b200_step_f64); launchers copy
+// it into their argument structs
+const double* current_time_row();
+void set_current_time_row(const double* row);
+
 // error codes returned across the C ABI (include/adept_b200.h)
 enum {
   ADEPT_OK = 0,

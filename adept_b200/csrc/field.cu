@@ -306,6 +306,7 @@ struct FieldFusedArgs {
   const double* ex_kx;
   double* dex;
   double ex_w[8], ex_a0[8], ex_tenv[8], ex_wt[8];
+  const double* trow;  // nullable device-resident time row (common.cuh)
   PoissonArgs po;
   unsigned int* counter;
   double* scratch;  // 4 nx doubles: two nx-long complex transposition buffers of the distributed solve
@@ -362,9 +363,11 @@ __global__ void __launch_bounds__(256) field_fused_kernel(FieldFusedArgs p) {
   if (p.n_ex > 0 && g == 1) {  // driver field at the first substep time, field.py:21-33
     double total = 0.0;
     for (int d = 0; d < p.n_ex; d++) {
-      const double factor = __dmul_rn(p.ex_tenv[d], p.ex_space[(size_t)d * n + i]);
+      const double tenv = p.trow ? p.trow[TROW_TENV + d] : p.ex_tenv[d];
+      const double wt = p.trow ? p.trow[TROW_WT + d] : p.ex_wt[d];
+      const double factor = __dmul_rn(tenv, p.ex_space[(size_t)d * n + i]);
       const double amp = __dmul_rn(__dmul_rn(factor, p.ex_w[d]), p.ex_a0[d]);
-      total = __dadd_rn(total, __dmul_rn(amp, sin(__dsub_rn(p.ex_kx[(size_t)d * n + i], p.ex_wt[d]))));
+      total = __dadd_rn(total, __dmul_rn(amp, sin(__dsub_rn(p.ex_kx[(size_t)d * n + i], wt))));
     }
     p.dex[i] = total;
   }
@@ -600,6 +603,7 @@ struct FieldMemberArgs {
   const double* ex_w_row;
   const double* ex_a0_row;
   double ex_t0;
+  const double* trow;  // nullable device-resident time row (common.cuh)
   const double* kmul;
   long long kmul_stride;
   double* e;
@@ -655,10 +659,11 @@ __global__ void __launch_bounds__(1024) field_member_kernel(FieldMemberArgs p) {
       double total = 0.0;
       for (int d = 0; d < p.n_ex; d++) {
         const long long o = d * p.n_rows + row0 + i;
-        const double factor = __dmul_rn(p.ex_tenv[d], p.ex_space[o]);
+        const double factor = __dmul_rn(p.trow ? p.trow[TROW_TENV + d] : p.ex_tenv[d], p.ex_space[o]);
         const double w = p.ex_w_row ? p.ex_w_row[o] : p.ex_w[d];
         const double a0 = p.ex_a0_row ? p.ex_a0_row[o] : p.ex_a0[d];
-        const double wt = p.ex_w_row ? __dmul_rn(w, p.ex_t0) : p.ex_wt[d];
+        const double wt = p.ex_w_row ? __dmul_rn(w, p.trow ? p.trow[TROW_EX_T] : p.ex_t0)
+                                     : (p.trow ? p.trow[TROW_WT + d] : p.ex_wt[d]);
         const double amp = __dmul_rn(__dmul_rn(factor, w), a0);
         total = __dadd_rn(total, __dmul_rn(amp, sin(__dsub_rn(p.ex_kx[o], wt))));
       }
@@ -731,6 +736,7 @@ int field_member_f64(int nsp, const double* const* f, const int* nv, const doubl
   p.base = base, p.rho = rho, p.nx = nx, p.a = a, p.pond = pond, p.dx = dx;
   p.n_ex = n_ex, p.n_rows = (long long)batch * nx, p.ex_space = ex_space, p.ex_kx = ex_kx, p.dex = dex;
   for (int d = 0; d < n_ex; d++) p.ex_w[d] = ex_w[d], p.ex_a0[d] = ex_a0[d], p.ex_tenv[d] = ex_tenv[d], p.ex_wt[d] = ex_wt[d];
+  p.trow = current_time_row();
   p.ex_w_row = ex_w_row, p.ex_a0_row = ex_a0_row, p.ex_t0 = ex_t0;
   p.kmul = kmul, p.kmul_stride = kmul_stride, p.e = e, p.mode = mode, p.Te = Te, p.lambda_De = lambda_De;
   ProfileScope prof("field_member", stream);
@@ -766,6 +772,7 @@ int field_fused_f64(int nsp, const double* const* parts, const int* nparts, cons
   p.base = base, p.rho = rho, p.nx = nx, p.a = a, p.pond = pond, p.dx = dx;
   p.n_ex = n_ex, p.ex_space = ex_space, p.ex_kx = ex_kx, p.dex = dex;
   for (int d = 0; d < n_ex; d++) p.ex_w[d] = ex_w[d], p.ex_a0[d] = ex_a0[d], p.ex_tenv[d] = ex_tenv[d], p.ex_wt[d] = ex_wt[d];
+  p.trow = current_time_row();
   p.po = PoissonArgs{rho, kmul, 0, e, mode, Te, lambda_De, nullptr, 0};
   p.counter = counter;
   ProfileScope prof("field_fused", stream);

@@ -77,9 +77,11 @@ __device__ __forceinline__ void field_tail_solve(const FieldTail& ft, const doub
     if (grp == 2 % NGRP && i < i_hi && ft.n_ex > 0) {  // field.py:21-33
       double total = 0.0;
       for (int d = 0; d < ft.n_ex; d++) {
-        const double factor = __dmul_rn(ft.ex_tenv[d], ft.ex_space[(size_t)d * N + i]);
+        const double tenv = ft.trow ? ft.trow[TROW_TENV + d] : ft.ex_tenv[d];
+        const double wt = ft.trow ? ft.trow[TROW_WT + d] : ft.ex_wt[d];
+        const double factor = __dmul_rn(tenv, ft.ex_space[(size_t)d * N + i]);
         const double amp = __dmul_rn(__dmul_rn(factor, ft.ex_w[d]), ft.ex_a0[d]);
-        total = __dadd_rn(total, __dmul_rn(amp, sin(__dsub_rn(ft.ex_kx[(size_t)d * N + i], ft.ex_wt[d]))));
+        total = __dadd_rn(total, __dmul_rn(amp, sin(__dsub_rn(ft.ex_kx[(size_t)d * N + i], wt))));
       }
       ft.dex[i] = total;
     }

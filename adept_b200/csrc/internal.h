@@ -61,12 +61,17 @@ int moments_bwd_f64(const double* const* obar, const double* coef, int batch, in
 int collide_bwd_f64(const double* fin, const double* fnew, const double* g, double* fbar, double* nubar, int batch,
                     int nx, int nv, const double* v, double dv, double dt, const double* nu_fp, double nu_fp_scale,
                     int model, int scheme, cudaStream_t stream);
+int edfdv_spline_bwd_f64(const double* f, const double* g, int batch, int nx, int nv, const double* e, const double* dex,
+                         const double* pond, double q, double m, double dt, double dv, double* fbar, double* abar,
+                         cudaStream_t stream);
+int krook_bwd_f64(const double* f, const double* g, int batch, int nx, int nv, double dv, double dt, const double* nu_K,
+                  const double* f_mx, double* fbar, double* nubar, cudaStream_t stream);
 bool vpush_collide_supported(int nx, int nv, int model, int scheme, int nodrag);
 int vpush_collide_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* e, const double* dex,
                       const double* pond, double q, double m, double dt, double k1v, const double* v, double dv,
                       const double* nu_fp, double nu_fp_scale, int model, int scheme, cudaStream_t stream,
                       const double* const* in_peers = nullptr, double* const* out_peers = nullptr, int n_peers = 0,
-                      long long row0_global = 0);
+                      long long row0_global = 0, double dt_fp = 0.0 /* collision time step; 0: the same as dt */);
 bool tma_available();
 int encode_map_2d(CUtensorMap* map, const double* base, unsigned long long dim0, unsigned long long dim1,
                   unsigned long long pitch_bytes, unsigned box0, unsigned box1, int swizzle128);
@@ -89,6 +94,7 @@ struct FieldTail {
   const double* ex_kx;
   double* dex;
   double ex_w[8], ex_a0[8], ex_tenv[8], ex_wt[8];
+  const double* trow;     // nullable device-resident time row (common.cuh): replaces ex_tenv / ex_wt (substep 0)
 };
 bool vdfdx_tma_supported(const double* fin, const double* fout, int nx, int nv);
 int vdfdx_tma_parts(int batch, int nx, int nv);

@@ -24,6 +24,7 @@ struct DriverArgs {
   const double* w_row;   // nullable [n_ex, n]: per-row frequency (ensemble members with different drivers)
   const double* a0_row;  // nullable [n_ex, n]
   double t_sub[ADEPT_B200_MAX_SUBSTEPS];
+  const double* trow;    // nullable: device-resident time row (common.cuh) that replaces tenv / wt / t_sub
 };
 
 __global__ void __launch_bounds__(256) ex_driver_kernel(DriverArgs p) {
@@ -33,10 +34,12 @@ __global__ void __launch_bounds__(256) ex_driver_kernel(DriverArgs p) {
     double total = 0.0;
     for (int d = 0; d < p.n_ex; d++) {
       // field.py:21-26: env(x, t) * (w0 + dw0) * a0 * sin(k0 x - (w0 + dw0) t), env = time_env * space_env
-      const double factor = __dmul_rn(p.tenv[s][d], p.space[d * p.n + i]);
+      const double tenv = p.trow ? p.trow[TROW_TENV + 8 * s + d] : p.tenv[s][d];
+      const double factor = __dmul_rn(tenv, p.space[d * p.n + i]);
       const double w = p.w_row ? p.w_row[d * p.n + i] : p.w[d];
       const double a0 = p.a0_row ? p.a0_row[d * p.n + i] : p.a0[d];
-      const double wt = p.w_row ? __dmul_rn(w, p.t_sub[s]) : p.wt[s][d];
+      const double wt = p.w_row ? __dmul_rn(w, p.trow ? p.trow[TROW_EX_T + s] : p.t_sub[s])
+                                : (p.trow ? p.trow[TROW_WT + 8 * s + d] : p.wt[s][d]);
       const double amp = __dmul_rn(__dmul_rn(factor, w), a0);
       total = __dadd_rn(total, __dmul_rn(amp, sin(__dsub_rn(p.kx[d * p.n + i], wt))));
     }
@@ -76,6 +79,7 @@ struct StepCtx {
       ft.counter = s.sync_counter, ft.base = s.ion_charge, ft.dv = sp.dv, ft.charge = sp.charge;
       ft.rho = s.rho, ft.e = s.e_out, ft.green = s.poisson_green, ft.a = s.a, ft.pond = s.pond, ft.dx = s.dx;
       ft.n_ex = driver_here ? s.n_ex : 0, ft.ex_space = s.ex_space, ft.ex_kx = s.ex_kx, ft.dex = s.dex;
+      ft.trow = s.time_row;
       for (int d = 0; d < s.n_ex; d++)
         ft.ex_w[d] = s.ex_w[d], ft.ex_a0[d] = s.ex_a0[d], ft.ex_tenv[d] = s.ex_tenv[0][d], ft.ex_wt[d] = s.ex_wt[0][d];
       ADEPT_TRY(vdfdx_tma_f64(cur[0], dst[0], s.batch, s.nx, sp.nv, sp.v, dt, s.k1x_batch, s.k1x, sp.rho_parts, st,
@@ -266,8 +270,16 @@ static int validate(const adept_b200_step& s) {
   return ADEPT_OK;
 }
 
+namespace {
+struct TimeRowScope {  // launchers called from this thread read the step's device-resident time row (common.cuh)
+  explicit TimeRowScope(const double* row) { set_current_time_row(row); }
+  ~TimeRowScope() { set_current_time_row(nullptr); }
+};
+}  // namespace
+
 int step_f64(const adept_b200_step& s, cudaStream_t st) {
   ADEPT_TRY(validate(s));
+  TimeRowScope time_row_scope(s.time_row);
   StepCtx c{s, st, (long long)s.batch * s.nx};
   const int n_sub = s.time_integrator == 0 ? 1 : ADEPT_B200_MAX_SUBSTEPS;
 
@@ -276,7 +288,7 @@ int step_f64(const adept_b200_step& s, cudaStream_t st) {
   auto launch_drivers = [&]() -> int {
     DriverArgs d = {};
     d.n_ex = s.n_ex, d.n_sub = n_sub, d.n = c.n, d.space = s.ex_space, d.kx = s.ex_kx, d.dex = s.dex;
-    d.w_row = s.ex_w_row, d.a0_row = s.ex_a0_row;
+    d.w_row = s.ex_w_row, d.a0_row = s.ex_a0_row, d.trow = s.time_row;
     for (int j = 0; j < ADEPT_B200_MAX_SUBSTEPS; j++) d.t_sub[j] = s.ex_t[j];
     for (int k = 0; k < ADEPT_B200_MAX_DRIVERS; k++) {
       d.w[k] = s.ex_w[k], d.a0[k] = s.ex_a0[k];
@@ -357,7 +369,26 @@ int step_f64(const adept_b200_step& s, cudaStream_t st) {
         else
           dst[k] = out[k];
       }
-      ADEPT_TRY(c.push_v(cur, dst, Ds[i] * dt, i));
+      // the last v-push shares its pass over f with the collision step when shape and operator allow it
+      const int kc = s.collide_species;
+      if (i == 5 && s.fp_on && !s.krook_on && !spline && s.fp_sc_steps == 0 && !want_diag && kc >= 0 &&
+          kc < s.n_species && vpush_collide_supported(s.nx, s.species[kc].nv, s.fp_model, s.fp_scheme, s.fp_nodrag)) {
+        const double* dexi = s.dex + (long long)i * c.n;
+        for (int k = 0; k < s.n_species; k++) {
+          const adept_b200_species& sp = s.species[k];
+          if (k == kc) {
+            ADEPT_TRY(vpush_collide_f64(cur[k], dst[k], s.batch, s.nx, sp.nv, s.e_out, dexi, s.pond, sp.charge, sp.mass,
+                                        Ds[i] * dt, sp.k1v, sp.v, sp.dv, s.nu_fp_space, s.nu_fp_time, s.fp_model,
+                                        s.fp_scheme, st, nullptr, nullptr, 0, 0, s.dt));
+          } else {
+            ADEPT_TRY(edfdv_exp_f64(cur[k], dst[k], s.batch, s.nx, sp.nv, s.e_out, dexi, s.pond, sp.charge, sp.mass,
+                                    Ds[i] * dt, sp.k1v, st));
+          }
+        }
+        collided = true;
+      } else {
+        ADEPT_TRY(c.push_v(cur, dst, Ds[i] * dt, i));
+      }
       for (int k = 0; k < s.n_species; k++) cur[k] = dst[k];
       if (i < 5) {
         double* same[ADEPT_B200_MAX_SPECIES];
@@ -413,6 +444,29 @@ int step_f64(const adept_b200_step& s, cudaStream_t st) {
 }
 
 }  // namespace adept
+
+namespace adept {
+__global__ void time_row_advance_kernel(const double* __restrict__ table, long long n_rows, long long* counter,
+                                        double* __restrict__ row) {
+  const long long i = *counter;
+  const long long r = i < n_rows ? (i < 0 ? 0 : i) : n_rows - 1;
+  row[threadIdx.x] = table[r * TROW_LEN + threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) *counter = i + 1;
+}
+}  // namespace adept
+
+extern "C" int adept_b200_time_row_advance(const double* table, long long n_rows, long long* counter, double* row,
+                                           void* stream) {
+  if (!table || !counter || !row || n_rows < 1) {
+    adept::set_last_error("adept_b200_time_row_advance: null pointer or empty table");
+    return adept::ADEPT_ERR_BAD_ARG;
+  }
+  static_assert(adept::TROW_LEN == ADEPT_B200_TIME_ROW_LEN, "time row layout");
+  adept::ProfileScope prof("time_row_advance", (cudaStream_t)stream);
+  adept::time_row_advance_kernel<<<1, adept::TROW_LEN, 0, (cudaStream_t)stream>>>(table, n_rows, counter, row);
+  return adept::check_launch("time_row_advance_kernel");
+}
 
 extern "C" int adept_b200_step_f64(const adept_b200_step* step, void* stream) {
   if (!step) {

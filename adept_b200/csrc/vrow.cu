@@ -25,6 +25,7 @@ struct VrowArgs {
   const double* dex;   // nullable
   const double* pond;  // nullable
   double q, m, dt, k1;
+  double dt_fp;  // time step of the collision operator (the push may be a substep of a splitting scheme)
   const cplx* tw;
   int zero;
   // collisions
@@ -32,6 +33,7 @@ struct VrowArgs {
   double dv;
   const double* nu_fp;  // [batch*nx]
   double nu_fp_scale;
+  const double* trow;  // nullable device-resident time row (common.cuh): nu_fp_scale = trow[TROW_NU_FP]
   int model, scheme;
   // peer mode (single grid sharded over GPUs, every buffer v-sharded [nx_global, nv / P] and mapped over NVLink): cell i
   // of local row r is READ from in_peer[i >> nvp_shift] and WRITTEN to out_peer[i >> nvp_shift], both at row
@@ -136,8 +138,8 @@ __global__ void __launch_bounds__(VrowCfg<LOGN>::THREADS, (VrowCfg<LOGN>::THREAD
 #pragma unroll 1
   for (int s = 0; s < 2; s++) {
     double* row = rowA + s * ROW_STRIDE;
-    fp_row_fast<16, TMA_OUT, CC>(row, red, pcr, parity, t, T, N, vc, p.dv, p.dt,
-                             __dmul_rn(p.nu_fp_scale, p.nu_fp[row0 + s]), p.model);
+    fp_row_fast<16, TMA_OUT, CC>(row, red, pcr, parity, t, T, N, vc, p.dv, p.dt_fp,
+                             __dmul_rn(p.trow ? p.trow[TROW_NU_FP] : p.nu_fp_scale, p.nu_fp[row0 + s]), p.model);
     if (TMA_OUT && threadIdx.x == 0) {  // the barrier that ends fp_row_fast ordered every thread's fenced stores
       constexpr int BOX = K::OUT_BOX_ROWS;
 #pragma unroll 1
@@ -216,7 +218,8 @@ bool vpush_collide_supported(int nx, int nv, int model, int scheme, int nodrag) 
 int vpush_collide_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* e, const double* dex,
                       const double* pond, double q, double m, double dt, double k1v, const double* v, double dv,
                       const double* nu_fp, double nu_fp_scale, int model, int scheme, cudaStream_t stream,
-                      const double* const* in_peers, double* const* out_peers, int n_peers, long long row0_global) {
+                      const double* const* in_peers, double* const* out_peers, int n_peers, long long row0_global,
+                      double dt_fp) {
   if (batch < 1 || !vpush_collide_supported(nx, nv, model, scheme, 0)) {
     set_last_error("vpush_collide: unsupported shape batch=%d nx=%d nv=%d / model=%d scheme=%d", batch, nx, nv, model,
                    scheme);
@@ -227,8 +230,10 @@ int vpush_collide_f64(const double* fin, double* fout, int batch, int nx, int nv
   VrowArgs p = {};
   p.fin = fin, p.fout = fout, p.npairs = (long long)batch * nx / 2, p.nx = nx;
   p.e = e, p.dex = dex, p.pond = pond, p.q = q, p.m = m, p.dt = dt, p.k1 = k1v;
+  p.dt_fp = dt_fp > 0.0 ? dt_fp : dt;
   p.tw = get_twiddles(logn), p.zero = 0;
   p.v = v, p.dv = dv, p.nu_fp = nu_fp, p.nu_fp_scale = nu_fp_scale, p.model = model, p.scheme = scheme;
+  p.trow = current_time_row();
   if (!p.tw) return ADEPT_ERR_CUDA;
   p.nvp_shift = -1;
   if (in_peers || out_peers) {

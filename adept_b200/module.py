@@ -138,6 +138,22 @@ class Vlasov1D:
         self.t = self.step_index * self.grid.dt
         return self.state
 
+    def graph_stepper(self, max_steps: int) -> "GraphStepper":
+        """CUDA-graph replay of the next ``max_steps`` steps (see GraphStepper); the first call costs one eager step."""
+        return GraphStepper(self, max_steps)
+
+    def graph_steps_per_second(self, nsteps: int) -> float:
+        """Steps per second of graph replay over ``nsteps`` (even) steps, timed with CUDA events (bench helper)."""
+        nsteps += nsteps % 2
+        gs = GraphStepper(self, 2 * nsteps + 2)
+        gs.run(nsteps)  # warm replay
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        gs.run(nsteps)
+        e1.record()
+        torch.cuda.synchronize()
+        return nsteps / (e0.elapsed_time(e1) * 1e-3)
+
     def run(self, nsteps=None, save=None):
         """Advance ``nsteps`` (default: the deck's nt).  ``save``: name -> (times, fn(cfg, y0, y1, w)) where the
         saved state is y0 + w (y1 - y0) (diffrax's linear dense output; see default_scalars / field_moments); returns
@@ -157,6 +173,111 @@ class Vlasov1D:
                     out[k].append(fn(self.cfg, y0, y1, w))  # save functions interpolate on the fly
                     cursor[k] += 1
         return self.state, out
+
+
+class GraphStepper:
+    """CUDA-graph replay of the native time step for decks whose host-issue time dominates (small grids: C1, C2, C5).
+
+    One replay advances TWO steps (state buffers A -> B -> A), each preceded by ``adept_b200_time_row_advance``: the
+    time factors of the drivers and collision profiles of every step of the run live in a device table, the kernels
+    read the current row through ``adept_b200_step.time_row``, so the same captured graph serves every step.  Decks
+    with Ey drivers or a live transverse field are refused (their per-step inputs are evaluated by host code)."""
+
+    def __init__(self, sim: "Vlasov1D", max_steps: int):
+        import ctypes as C
+
+        from . import _lib
+
+        vm = sim.vector_field
+        if vm.native is None or vm.has_ey:
+            raise NotImplementedError("GraphStepper: needs the native step and no Ey driver")
+        y = sim.state
+        if bool(torch.any(y["a"] != 0)) or bool(torch.any(y["prev_a"] != 0)):
+            raise NotImplementedError("GraphStepper: the transverse field must be zero (wave update skipped)")
+        vm._a_live = False
+        self.sim, self.lib, self.nat = sim, _lib.load(), vm.native
+        nat = self.nat
+        dev = y[nat.names[0]].device
+        f0 = y[nat.names[0]]
+        batch = f0.shape[0] if f0.dim() == 3 else 1
+        sim.step()  # one eager step: builds the static descriptor, twiddle tables and kernel attributes
+        y = sim.state
+        static = nat._static_step(y, dev, batch, False)
+        nsub = len(nat.dt_array)
+        # ping-pong state: every tensor of the state dict twice
+        self.buf = []
+        for _ in range(2):
+            b = {k: torch.empty_like(v) for k, v in y.items() if k not in ("a", "prev_a", "da", "de")}
+            b["dex"] = torch.zeros((nsub,) + tuple(y["e"].shape), dtype=torch.float64, device=dev)
+            self.buf.append(b)
+        for k, v in y.items():
+            if k in self.buf[0]:
+                self.buf[0][k].copy_(v)
+        self.fixed = {"a": y["a"], "prev_a": y["a"], "da": vm._zeros_a}
+        self.row = torch.zeros(_lib.TIME_ROW_LEN, dtype=torch.float64, device=dev)
+        self.counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.max_steps = int(max_steps)
+        t0, dt = sim.step_index, sim.grid.dt
+        self.first_step = t0
+        self.table = torch.as_tensor(np.stack([nat.time_row((t0 + k) * dt) for k in range(self.max_steps)]), device=dev)
+        self.steps_done = 0
+        self.sts = []
+        for src, dst in ((0, 1), (1, 0)):
+            st = _lib.Step.from_buffer_copy(static)
+            a, b = self.buf[src], self.buf[dst]
+            for k, name in enumerate(nat.names):
+                st.species[k].f_in, st.species[k].f_out = a[name].data_ptr(), b[name].data_ptr()
+            st.e_in, st.e_out, st.dex = a["e"].data_ptr(), b["e"].data_ptr(), b["dex"].data_ptr()
+            st.a, st.prev_a = y["a"].data_ptr(), y["prev_a"].data_ptr()
+            st.wave_on = 0
+            st.diag_vlasov_dfdt = b["diag-vlasov-dfdt"].data_ptr() if "diag-vlasov-dfdt" in b else None
+            st.diag_fp_dfdt = b["diag-fp-dfdt"].data_ptr() if "diag-fp-dfdt" in b else None
+            st.time_row = self.row.data_ptr()
+            self.sts.append(st)
+        self._C = C
+        # eager pass of both descriptors (warms every launch path with the device time row), then rewind
+        saved = {k: v.clone() for k, v in self.buf[0].items()}
+        self._enqueue_pair()
+        torch.cuda.synchronize()
+        for k, v in saved.items():
+            self.buf[0][k].copy_(v)
+        self.counter.zero_()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._enqueue_pair()
+        self.counter.zero_()
+
+    def _enqueue_pair(self):
+        from . import _lib
+
+        C, lib = self._C, self.lib
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        before = lib.adept_b200_launch_count()
+        for st in self.sts:
+            _lib.check(lib.adept_b200_time_row_advance(self.table.data_ptr(), self.max_steps, self.counter.data_ptr(),
+                                                       self.row.data_ptr(), stream), "time_row_advance")
+            _lib.check(lib.adept_b200_step_f64(C.byref(st), stream), "step")
+        self.launches_per_replay = lib.adept_b200_launch_count() - before
+
+    def run(self, nsteps: int):
+        """Advance an even number of steps by graph replay; returns the state dict (views of the A buffers)."""
+        if nsteps % 2 or nsteps < 0 or self.steps_done + nsteps > self.max_steps:
+            raise ValueError("GraphStepper.run: nsteps must be even and within the table built at construction")
+        for _ in range(nsteps // 2):
+            self.graph.replay()
+        self.steps_done += nsteps
+        sim, a = self.sim, self.buf[0]
+        nat = self.nat
+        state = {k: v for k, v in a.items() if k != "dex"}
+        state["de"] = a["dex"][sim.vector_field.vpfp.dex_save]
+        state.update(self.fixed)
+        sim.state = state
+        sim.step_index = self.first_step + self.steps_done
+        sim.t = sim.step_index * sim.grid.dt
+        from . import ops
+
+        ops.LAUNCHES += self.launches_per_replay * (nsteps // 2)
+        return state
 
 
 def save_axis(tcfg: dict, grid) -> np.ndarray:

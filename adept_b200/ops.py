@@ -140,6 +140,32 @@ def collide_bwd(f_in, f_new, g, v, dv, dt, nu_fp, model=1, scheme=0, want_nu_bar
     return fbar, nubar
 
 
+def edfdv_spline_bwd(f_in, g, e, pond, q, m, dt, dv, dex=None, want_f=True, want_accel=True):
+    """(f_bar, accel_bar) of :func:`edfdv_spline` (f_in = the forward input)."""
+    b, nx, nv = _shape3(f_in)
+    fbar = torch.empty_like(f_in) if want_f else None
+    abar = torch.empty(f_in.shape[:-1], dtype=torch.float64, device=f_in.device) if want_accel else None
+    rc = _lib.load().adept_b200_edfdv_spline_bwd_f64(
+        _ptr(f_in, "f_in"), _ptr(g, "g"), b, nx, nv, _ptr(e, "e"), _ptr(dex, "dex", True), _ptr(pond, "pond", True),
+        float(q), float(m), float(dt), float(dv), _ptr(fbar, "fbar", True), _ptr(abar, "abar", True), _stream())
+    _lib.check(rc, "edfdv_spline_bwd")
+    _count()
+    return fbar, abar
+
+
+def krook_bwd(f_in, g, dv, dt, nu_K, f_mx, want_nu_bar=False):
+    """(f_bar, nu_bar) of the Krook step of :func:`collide`."""
+    b, nx, nv = _shape3(f_in)
+    fbar = torch.empty_like(f_in)
+    nubar = torch.empty(f_in.shape[:-1], dtype=torch.float64, device=f_in.device) if want_nu_bar else None
+    rc = _lib.load().adept_b200_krook_bwd_f64(_ptr(f_in, "f_in"), _ptr(g, "g"), b, nx, nv, float(dv), float(dt),
+                                              _ptr(nu_K, "nu_K"), _ptr(f_mx, "f_mx"), _ptr(fbar, "fbar"),
+                                              _ptr(nubar, "nubar", True), _stream())
+    _lib.check(rc, "krook_bwd")
+    _count()
+    return fbar, nubar
+
+
 def save_moments(f0, v, dv, f1=None, w=0.0, out=None):
     """[6, batch*nx] = dv * sum_v {f, f v, f v^2, f v^3, -|f| log|f|, f^2} of f = f0 + w (f1 - f0) (storage.py:119-162,
     286-327), one pass over f, the interpolated distribution is never materialised."""

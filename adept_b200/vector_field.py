@@ -282,6 +282,25 @@ class NativeStep:
         self.static[key] = st
         return st
 
+    def time_row(self, t):
+        """The O(1) time factors of one step starting at time t as a host row of ``_lib.TIME_ROW_LEN`` doubles
+        (layout of include/adept_b200.h: tenv[s][d], wt[s][d], nu_fp_time, nu_K_time, ex_t[s]) -- the same closed forms
+        ``__call__`` evaluates per step (field.py:21-33, functions.py:72-80,112-118)."""
+        vm = self.vm
+        row = np.zeros(_lib.TIME_ROW_LEN, dtype=np.float64)
+        for j, d in enumerate(vm.ex_driver.drivers):
+            for i, dti in enumerate(self.dt_array):
+                ti = t + dti
+                row[8 * i + j] = float(d.envelope.time_envelope(ti))
+                row[48 + 8 * i + j] = d.phase(ti)
+        if vm.fp_on:
+            row[96] = float(vm.nu_fp_prof.time_envelope(t))
+        if vm.krook_on:
+            row[97] = float(vm.nu_K_prof.time_envelope(t))
+        for i, dti in enumerate(self.dt_array):
+            row[98 + i] = t + dti
+        return row
+
     def __call__(self, t, y, wave_on):
         vm = self.vm
         f0 = y[self.names[0]]

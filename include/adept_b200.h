@@ -215,6 +215,20 @@ int adept_b200_collide_bwd_f64(const double* f_in, const double* f_new, const do
                                int batch, int nx, int nv, const double* v, double dv, double dt, const double* nu_fp,
                                int model, int scheme, void* stream);
 
+/* Adjoint of adept_b200_edfdv_spline_f64 (pinned by the reference's tests/test_vlasov1d/test_velocity_cubic_spline.py:
+ * 49-70, gradients w.r.t. f and the field): f_bar[b, i, .] = the four cubic-Hermite taps of every output scattered back
+ * (nullable), accel_bar[b, i] = sum_j g_ij d f'_ij / d accel_i (nullable; chain to the fields as for the spectral
+ * push).  Same arguments as the forward call; f_in is the forward INPUT. */
+int adept_b200_edfdv_spline_bwd_f64(const double* f_in, const double* g, int batch, int nx, int nv, const double* e,
+                                    const double* dex, const double* pond, double charge, double mass, double dt,
+                                    double dv, double* f_bar, double* accel_bar, void* stream);
+
+/* Adjoint of the Krook step of adept_b200_collide_f64 (f' = f e^{-nu_K dt} + n f_mx (1 - e^{-nu_K dt}), n = dv sum f;
+ * fokker_planck.py:463-484): f_bar (nullable) and nu_bar[batch*nx] (nullable) from the forward input f_in and the
+ * cotangent g of the output. */
+int adept_b200_krook_bwd_f64(const double* f_in, const double* g, int batch, int nx, int nv, double dv, double dt,
+                             const double* nu_K, const double* f_mx, double* f_bar, double* nu_bar, void* stream);
+
 /* ---- whole time step ------------------------------------------------------------------------------------------------
  * adept_b200_step_f64 enqueues every kernel of one `vlasov-1d` step y -> y' on `stream` with no host work in between:
  * it replaces VlasovMaxwell.__call__ and what it calls (adept/_vlasov1d/solvers/vector_field.py:55-95 LeapfrogIntegrator,
@@ -304,9 +318,21 @@ typedef struct adept_b200_step {
   /* Hou-Li spectral filter in x applied to every species after the collisions (terms.hou_li_filter, vlasov.py:187-220):
    * real multiplier per mode, [nx/2 + 1] (nullable = off) */
   const double* hou_li_filt;
+  /* Device-resident time factors (nullable).  When given, the kernels read ex_tenv / ex_wt / ex_t / nu_fp_time /
+   * nu_K_time from this [ADEPT_B200_TIME_ROW_LEN] device array instead of the by-value fields above, so a CUDA graph
+   * captured around adept_b200_step_f64 can be replayed for later steps: the caller keeps a [n_steps, LEN] table on the
+   * device and puts adept_b200_time_row_advance in front of every captured step.  Layout: tenv[s][d] at 8 s + d,
+   * wt[s][d] at 48 + 8 s + d, nu_fp_time at 96, nu_K_time at 97, ex_t[s] at 98 + s. */
+  const double* time_row;
 } adept_b200_step;
 
+#define ADEPT_B200_TIME_ROW_LEN 104
+
 int adept_b200_step_f64(const adept_b200_step* step, void* stream);
+
+/* row[0 .. LEN) = table[min(*counter, n_rows - 1)][0 .. LEN); *counter += 1.  One tiny launch; capturable.  counter is
+ * a device long long owned by the caller (set it to the index of the step the next replay starts from). */
+int adept_b200_time_row_advance(const double* table, long long n_rows, long long* counter, double* row, void* stream);
 
 #ifdef __cplusplus
 }
