@@ -53,6 +53,13 @@ class Step(C.Structure):
     ]
 
 
+class StepBwd(C.Structure):
+    """struct adept_b200_step_bwd (include/adept_b200.h)."""
+
+    _fields_ = [("f_out_bar", c_dp), ("e_out_bar", c_dp), ("f_in_bar", c_dp), ("dex_bar", c_dp), ("nu_fp_bar", c_dp),
+                ("nu_K_bar", c_dp), ("scratch_f", c_dp * 3), ("scratch_row", c_dp * 2)]
+
+
 TIME_ROW_LEN = 104  # ADEPT_B200_TIME_ROW_LEN: tenv[6][8] | wt[6][8] | nu_fp_time | nu_K_time | ex_t[6]
 
 
@@ -94,6 +101,7 @@ SIGNATURES = {
     "adept_b200_collide_sc_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_d, c_d, c_dp, c_dp, c_dp, c_i, c_i, c_i, c_d, c_d,
                                   c_dp, c_i, c_d, c_d, c_dp],
     "adept_b200_step_f64": [C.POINTER(Step), c_dp],
+    "adept_b200_step_bwd_f64": [C.POINTER(Step), C.POINTER(StepBwd), c_dp],
     "adept_b200_time_row_advance": [c_dp, c_ll, c_dp, c_dp, c_dp],
 }
 

@@ -446,6 +446,116 @@ int step_f64(const adept_b200_step& s, cudaStream_t st) {
 }  // namespace adept
 
 namespace adept {
+
+// e_bar = accel_bar * q/m (+ e_out_bar); dex_bar = accel_bar * q/m
+__global__ void accel_chain_kernel(const double* __restrict__ abar, const double* __restrict__ e_out_bar, double qm,
+                                   double* __restrict__ e_bar, double* __restrict__ dex_bar, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double a = abar[i] * qm;
+  if (dex_bar) dex_bar[i] = a;
+  e_bar[i] = e_out_bar ? a + e_out_bar[i] : a;
+}
+__global__ void scale_rows_kernel(double* __restrict__ x, double s, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] *= s;
+}
+
+int step_bwd_f64(const adept_b200_step& s, const adept_b200_step_bwd& b, cudaStream_t st) {
+  ADEPT_TRY(validate(s));
+  if (s.n_species != 1 || s.time_integrator != 0 || s.field != 0 || s.wave_on || s.fp_sc_steps != 0 ||
+      s.hou_li_filt || s.ex_w_row || s.ex_a0_row || (s.fp_on && (s.fp_model == 2 || s.fp_nodrag))) {
+    set_last_error("step_bwd: only one species, leapfrog, poisson, LB / Dougherty (+ Krook), wave off are implemented");
+    return ADEPT_ERR_UNSUPPORTED;
+  }
+  if (!b.f_out_bar || !b.f_in_bar || !b.scratch_f[0] || !b.scratch_f[1] || !b.scratch_f[2] || !b.scratch_row[0] ||
+      !b.scratch_row[1]) {
+    set_last_error("step_bwd: null cotangent / scratch pointer");
+    return ADEPT_ERR_BAD_ARG;
+  }
+  TimeRowScope time_row_scope(nullptr);
+  const adept_b200_species& sp = s.species[0];
+  const long long n = (long long)s.batch * s.nx;
+  const int nv = sp.nv;
+  double* fs = b.scratch_f[0];   // f* = vdfdx(f)
+  double* f2 = b.scratch_f[1];   // f** = edfdv(f*)
+  double* f3 = b.scratch_f[2];   // Fokker-Planck output (before Krook) / cotangent scratch
+  const bool spline = s.edfdv == 1;
+  // ---- recompute the intermediates of the forward step ----------------------------------------------------------
+  if (vdfdx_tma_supported(sp.f_in, fs, s.nx, nv))
+    ADEPT_TRY(vdfdx_tma_f64(sp.f_in, fs, s.batch, s.nx, nv, sp.v, s.dt, s.k1x_batch, s.k1x, nullptr, st));
+  else
+    ADEPT_TRY(vdfdx_f64(sp.f_in, fs, s.batch, s.nx, nv, sp.v, s.dt, s.k1x_batch, s.k1x, st));
+  if (spline)
+    ADEPT_TRY(edfdv_spline_f64(fs, f2, s.batch, s.nx, nv, s.e_out, s.dex, s.pond, sp.charge, sp.mass, s.dt, sp.dv, st));
+  else
+    ADEPT_TRY(edfdv_exp_f64(fs, f2, s.batch, s.nx, nv, s.e_out, s.dex, s.pond, sp.charge, sp.mass, s.dt, sp.k1v, st));
+  // ---- collisions, reversed: Krook then Fokker-Planck; g lives in f_in_bar from here on --------------------------
+  const double* g = b.f_out_bar;
+  double* gbuf = b.f_in_bar;
+  if (s.krook_on) {
+    const double* f_pre_krook = f2;
+    if (s.fp_on) {
+      ADEPT_TRY(collide_f64(f2, f3, s.batch, s.nx, nv, sp.v, sp.dv, s.dt, s.nu_fp_space, nullptr, nullptr, s.fp_model,
+                            s.fp_scheme, 0, s.sg_m, s.sg_ratio, nullptr, s.nu_fp_time, 1.0, st));
+      f_pre_krook = f3;
+    }
+    // nu_K(x, t) = time * space: the kernel takes the product, the cotangent is w.r.t. the product
+    ADEPT_TRY(axpy_f64(s.nu_K_space, s.nu_K_space, s.nu_K_time - 1.0, b.scratch_row[0], n, st));  // time * space
+    ADEPT_TRY(krook_bwd_f64(f_pre_krook, g, s.batch, s.nx, nv, sp.dv, s.dt, b.scratch_row[0], s.f_mx, gbuf, b.nu_K_bar,
+                            st));
+    g = gbuf;
+  }
+  if (s.fp_on) {
+    if (!s.krook_on)  // f3 = FP(f2) is the forward output itself, but f_out may have been overwritten: recompute
+      ADEPT_TRY(collide_f64(f2, f3, s.batch, s.nx, nv, sp.v, sp.dv, s.dt, s.nu_fp_space, nullptr, nullptr, s.fp_model,
+                            s.fp_scheme, 0, s.sg_m, s.sg_ratio, nullptr, s.nu_fp_time, 1.0, st));
+    // the cotangent of f2 may land in f3's buffer: collide_bwd loads a row of f_new into shared memory before it writes
+    // the same row of f_bar, and rows are independent
+    double* g2 = (g == gbuf) ? f3 : gbuf;
+    ADEPT_TRY(collide_bwd_f64(f2, f3, g, g2, b.nu_fp_bar, s.batch, s.nx, nv, sp.v, sp.dv, s.dt, s.nu_fp_space,
+                              s.nu_fp_time, s.fp_model, s.fp_scheme, st));
+    if (b.nu_fp_bar) {  // collide_bwd returns d/d(space profile) = time * d/d(nu): undo the scale
+      if (s.nu_fp_time != 0.0) {
+        ProfileScope prof("scale_rows", st);
+        scale_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b.nu_fp_bar, 1.0 / s.nu_fp_time, n);
+        ADEPT_TRY(check_launch("scale_rows_kernel"));
+      }
+    }
+    g = g2;
+  }
+  // ---- v-advection, reversed: cotangent of f* into f2's buffer, cotangent of the acceleration --------------------
+  double* abar = b.scratch_row[0];
+  double* ebar = b.scratch_row[1];
+  double* gfs = f2;
+  if (spline) {
+    ADEPT_TRY(edfdv_spline_bwd_f64(fs, g, s.batch, s.nx, nv, s.e_out, s.dex, s.pond, sp.charge, sp.mass, s.dt, sp.dv,
+                                   gfs, abar, st));
+  } else {
+    ADEPT_TRY(edfdv_exp_bwd_accel_f64(fs, g, s.batch, s.nx, nv, s.e_out, s.dex, s.pond, sp.charge, sp.mass, s.dt,
+                                      sp.k1v, abar, st));
+    ADEPT_TRY(edfdv_exp_f64(g, gfs, s.batch, s.nx, nv, s.e_out, s.dex, s.pond, sp.charge, sp.mass, -s.dt, sp.k1v, st));
+  }
+  {
+    ProfileScope prof("accel_chain", st);
+    accel_chain_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(abar, b.e_out_bar, sp.charge / sp.mass, ebar,
+                                                                    b.dex_bar, n);
+    ADEPT_TRY(check_launch("accel_chain_kernel"));
+  }
+  // ---- field solve, reversed: rho_bar = -poisson(e_bar) (antisymmetric), f*_bar += q dv rho_bar -------------------
+  double* rhobar = b.scratch_row[0];
+  ADEPT_TRY(poisson_dispatch_f64(ebar, s.kmul, s.kmul_stride, rhobar, s.batch, s.nx, 0, 0.0, 0.0, st));
+  {
+    const double* obar[3] = {rhobar, nullptr, nullptr};
+    const double coef[3] = {-sp.dv * sp.charge, 0.0, 0.0};
+    ADEPT_TRY(moments_bwd_f64(obar, coef, s.batch, s.nx, nv, nullptr, 1, gfs, st));
+  }
+  // ---- x-advection, reversed --------------------------------------------------------------------------------------
+  if (vdfdx_tma_supported(gfs, b.f_in_bar, s.nx, nv))
+    return vdfdx_tma_f64(gfs, b.f_in_bar, s.batch, s.nx, nv, sp.v, -s.dt, s.k1x_batch, s.k1x, nullptr, st);
+  return vdfdx_f64(gfs, b.f_in_bar, s.batch, s.nx, nv, sp.v, -s.dt, s.k1x_batch, s.k1x, st);
+}
+
 __global__ void time_row_advance_kernel(const double* __restrict__ table, long long n_rows, long long* counter,
                                         double* __restrict__ row) {
   const long long i = *counter;
@@ -466,6 +576,14 @@ extern "C" int adept_b200_time_row_advance(const double* table, long long n_rows
   adept::ProfileScope prof("time_row_advance", (cudaStream_t)stream);
   adept::time_row_advance_kernel<<<1, adept::TROW_LEN, 0, (cudaStream_t)stream>>>(table, n_rows, counter, row);
   return adept::check_launch("time_row_advance_kernel");
+}
+
+extern "C" int adept_b200_step_bwd_f64(const adept_b200_step* step, const adept_b200_step_bwd* bwd, void* stream) {
+  if (!step || !bwd) {
+    adept::set_last_error("adept_b200_step_bwd_f64: null descriptor");
+    return adept::ADEPT_ERR_BAD_ARG;
+  }
+  return adept::step_bwd_f64(*step, *bwd, (cudaStream_t)stream);
 }
 
 extern "C" int adept_b200_step_f64(const adept_b200_step* step, void* stream) {

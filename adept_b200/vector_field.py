@@ -354,6 +354,42 @@ class NativeStep:
         result.update(diags)
         return result
 
+    def vjp(self, t, y, f_out_bar, e_out_bar=None, want=("dex", "nu_fp", "nu_K")):
+        """Reverse mode through one native step (adept_b200_step_bwd_f64): re-runs the forward step from ``y`` at time
+        ``t`` (its field arrays feed the backward pass), then returns ``(y_new, bars)`` with bars = {"f": cotangent of
+        the input distribution, "dex": cotangent of the driver field [nx], "nu_fp" / "nu_K": cotangents of nu(x, t)}.
+        One species, leapfrog, poisson, LB / Dougherty (+ Krook), no transverse wave -- anything else raises."""
+        y_new = self(t, y, False)
+        name = self.names[0]
+        f = y[name]
+        dev = f.device
+        batch = f.shape[0] if f.dim() == 3 else 1
+        st = self._static_step(y, dev, batch, False)  # still holds this step's pointers and time factors
+        n = batch * int(self.cfg["grid"]["nx"])
+        bw = _lib.StepBwd()
+        g = f_out_bar.contiguous()
+        f_in_bar = torch.empty_like(f)
+        bars = {"f": f_in_bar}
+        bw.f_out_bar, bw.f_in_bar = g.data_ptr(), f_in_bar.data_ptr()
+        if e_out_bar is not None:
+            eb = e_out_bar.contiguous()
+            bw.e_out_bar = eb.data_ptr()
+        for key, field, on in (("dex", "dex_bar", True), ("nu_fp", "nu_fp_bar", self.vm.fp_on),
+                               ("nu_K", "nu_K_bar", self.vm.krook_on)):
+            if key in want and on:
+                bars[key] = torch.zeros(y["e"].shape, dtype=torch.float64, device=dev)
+                setattr(bw, field, bars[key].data_ptr())
+        for i in range(3):
+            bw.scratch_f[i] = self._scratch(("bwd_f", i), f.shape, dev).data_ptr()
+        for i in range(2):
+            bw.scratch_row[i] = self._scratch(("bwd_row", i), (n,), dev).data_ptr()
+        lib = _lib.load()
+        before = lib.adept_b200_launch_count()
+        rc = lib.adept_b200_step_bwd_f64(C.byref(st), C.byref(bw), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, "step_bwd")
+        ops.LAUNCHES += lib.adept_b200_launch_count() - before
+        return y_new, bars
+
 
 class VlasovMaxwell:
     """One full vlasov-1d step y -> y'; vector_field.py:256-361."""

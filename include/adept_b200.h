@@ -334,6 +334,28 @@ int adept_b200_step_f64(const adept_b200_step* step, void* stream);
  * a device long long owned by the caller (set it to the index of the step the next replay starts from). */
 int adept_b200_time_row_advance(const double* table, long long n_rows, long long* counter, double* row, void* stream);
 
+/* ---- whole-step backward (what the _bwd rule of a jax.custom_vjp around adept_b200_step_f64 calls) ------------------
+ * Reverse mode through ONE leapfrog step (LeapfrogIntegrator + Collisions, vector_field.py:87-95, 236-238) of a single
+ * species with field = poisson, edfdv = exponential or cubic-spline, Fokker-Planck (Lenard-Bernstein / Dougherty, central
+ * or Chang-Cooper, no self-consistent beta) and Krook optional, transverse wave off.  `step` is the descriptor of the
+ * forward call, which must have run first: its e_out, dex and pond arrays still hold the forward values, and f_in is
+ * the forward input (f_out is not read).  The intermediates f* = vdfdx(f) and f** = edfdv(f*) are recomputed into the
+ * scratch buffers.  Outputs: f_in_bar; dex_bar[batch*nx] (cotangent of the driver field, nullable); nu_fp_bar /
+ * nu_K_bar[batch*nx] (cotangents of nu(x, t) = time * space, nullable).  Returns ADEPT_B200_ERR_UNSUPPORTED for
+ * anything else (the operator-level adjoints above compose every other case). */
+typedef struct adept_b200_step_bwd {
+  const double* f_out_bar; /* [batch, nx, nv] cotangent of species[0].f_out */
+  const double* e_out_bar; /* [batch*nx] cotangent of e_out (nullable) */
+  double* f_in_bar;        /* [batch, nx, nv] */
+  double* dex_bar;         /* [batch*nx] nullable */
+  double* nu_fp_bar;       /* [batch*nx] nullable */
+  double* nu_K_bar;        /* [batch*nx] nullable */
+  double* scratch_f[3];    /* three [batch, nx, nv] buffers */
+  double* scratch_row[2];  /* two [batch*nx] buffers */
+} adept_b200_step_bwd;
+
+int adept_b200_step_bwd_f64(const adept_b200_step* step, const adept_b200_step_bwd* bwd, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,17 +80,18 @@ def test_step_struct_layout_matches_header(tmp_path):
     """ctypes mirror of struct adept_b200_step == the C layout (compiled from include/adept_b200.h with gcc)."""
     import subprocess
 
-    from adept_b200._lib import Species, Step
+    from adept_b200._lib import Species, Step, StepBwd
 
     src = tmp_path / "layout.c"
     fields = ["e_in", "dex", "a_out", "wave_on", "pond", "n_ex", "ex_w", "ex_tenv", "ex_wt", "fp_on", "sg_m",
-              "nu_fp_space", "nu_fp_time", "f_mx"]
+              "nu_fp_space", "nu_fp_time", "f_mx", "poisson_green", "hou_li_filt", "time_row"]
     prints = "".join(f'printf("%zu\\n", offsetof(adept_b200_step, {f}));' for f in fields)
     src.write_text(f'#include <stdio.h>\n#include <stddef.h>\n#include "{ROOT}/include/adept_b200.h"\n'
-                   f'int main(void){{printf("%zu\\n%zu\\n", sizeof(adept_b200_step), sizeof(adept_b200_species));{prints}return 0;}}')
+                   f'int main(void){{printf("%zu\\n%zu\\n%zu\\n", sizeof(adept_b200_step), sizeof(adept_b200_species), '
+                   f'sizeof(adept_b200_step_bwd));{prints}return 0;}}')
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-std=c99", str(src), "-o", str(exe)], check=True)
     out = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
-    assert out[0] == ctypes.sizeof(Step) and out[1] == ctypes.sizeof(Species)
-    for f, off in zip(fields, out[2:]):
+    assert out[0] == ctypes.sizeof(Step) and out[1] == ctypes.sizeof(Species) and out[2] == ctypes.sizeof(StepBwd)
+    for f, off in zip(fields, out[3:]):
         assert getattr(Step, f).offset == off, f
