@@ -83,6 +83,7 @@ SIGNATURES = {
                                          c_d, c_d, c_d, c_dp, c_d, c_dp, c_i, c_i, c_dp],
     "adept_b200_save_moments_f64": [c_dp, c_dp, c_d, c_i, c_i, c_i, c_dp, c_d, c_dp, c_dp],
     "adept_b200_interp2d_f64": [c_dp, c_dp, c_d, c_i, c_i, c_dp, c_dp, c_dp, c_dp, c_i, c_i, c_dp, c_dp],
+    "adept_b200_abs_rfft_x_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp],
     "adept_b200_filter_x_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_dp, c_dp],
     "adept_b200_vdfdx_rho_parts": [c_i, c_i, c_i],
     "adept_b200_vdfdx_rho_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_d, c_d, c_dp, c_dp, c_i, c_dp],

@@ -315,6 +315,11 @@ int adept_b200_collide_bwd_f64(const double* f_in, const double* f_new, const do
                          (cudaStream_t)stream);
 }
 
+int adept_b200_abs_rfft_x_f64(const double* f, double* out, int batch, int nx, int nv, void* stream) {
+  ADEPT_REQUIRE(f, "f") ADEPT_REQUIRE(out, "out")
+  return abs_rfft_x_f64(f, out, batch, nx, nv, (cudaStream_t)stream);
+}
+
 int adept_b200_edfdv_spline_bwd_f64(const double* f_in, const double* g, int batch, int nx, int nv, const double* e,
                                     const double* dex, const double* pond, double charge, double mass, double dt,
                                     double dv, double* f_bar, double* accel_bar, void* stream) {

@@ -66,6 +66,7 @@ int edfdv_spline_bwd_f64(const double* f, const double* g, int batch, int nx, in
                          cudaStream_t stream);
 int krook_bwd_f64(const double* f, const double* g, int batch, int nx, int nv, double dv, double dt, const double* nu_K,
                   const double* f_mx, double* fbar, double* nubar, cudaStream_t stream);
+int abs_rfft_x_f64(const double* fin, double* fout, int batch, int nx, int nv, cudaStream_t stream);
 bool vpush_collide_supported(int nx, int nv, int model, int scheme, int nodrag);
 int vpush_collide_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* e, const double* dex,
                       const double* pond, double q, double m, double dt, double k1v, const double* v, double dv,

@@ -258,4 +258,97 @@ int edfdv_exp_f64(const double* fin, double* fout, int batch, int nx, int nv, co
   return dispatch_push<AXIS_V>(logn, p, stream);
 }
 
+// ---- |rfft_x f|: the spectrum save of get_dist_save_func's {t, kx, v} block (adept/_vlasov1d/storage.py:183-190) ------
+// One complex FFT per column pair like the x-advection; the two real spectra are separated with the k <-> N - k
+// symmetry and their moduli written to out[k, col], k = 0 .. N/2.
+template <int LOGN>
+__global__ void __launch_bounds__(PushCfg<LOGN, AXIS_X>::THREADS, (PushCfg<LOGN, AXIS_X>::THREADS <= 256 ? 2 : 1))
+    abs_rfft_x_kernel(PushArgs p) {
+  using C = FftCfg<LOGN>;
+  using K = PushCfg<LOGN, AXIS_X>;
+  constexpr int N = C::N, E = C::E, T = C::T;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* smem = reinterpret_cast<cplx*>(smem_raw);
+  const int g = threadIdx.x / T, t = threadIdx.x % T;
+  cplx* buf = smem + (size_t)g * C::BUF;
+  const long long G = (long long)blockIdx.x * K::F + g;
+  const bool active = G < p.npairs;
+  const int half = p.nv / 2;
+  const int b = active ? (int)(G / half) : 0, cp = active ? (int)(G % half) : 0;
+  const double* src = p.fin + (long long)b * p.nx * p.nv + 2 * cp;
+  double* dst = p.fout + (long long)b * (N / 2 + 1) * p.nv + 2 * cp;
+  cplx x[E];
+#pragma unroll
+  for (int m = 0; m < E; m++)
+    x[m] = active ? *reinterpret_cast<const double2*>(src + (long long)(t + T * m) * p.nv) : cmake(0.0, 0.0);
+  fft_forward<LOGN>(x, buf, p.tw, t, p.zero);
+  __syncthreads();
+#pragma unroll
+  for (int m = 0; m < E; m++) buf[fft_pad(t + T * m)] = x[m];
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int m = 0; m < E; m++) {
+      const int k = t + T * m;
+      if (k > N / 2) continue;
+      const cplx zq = buf[fft_pad((N - k) & (N - 1))];
+      // A_k = (Z_k + conj(Z_{N-k})) / 2,  B_k = (Z_k - conj(Z_{N-k})) / (2 i)
+      const double ar = 0.5 * (x[m].x + zq.x), ai = 0.5 * (x[m].y - zq.y);
+      const double br = 0.5 * (x[m].y + zq.y), bi = 0.5 * (zq.x - x[m].x);
+      *reinterpret_cast<double2*>(dst + (long long)k * p.nv) = make_double2(hypot(ar, ai), hypot(br, bi));
+    }
+  }
+}
+
+template <int LOGN>
+static int launch_abs_rfft_x(const PushArgs& p, cudaStream_t stream) {
+  using K = PushCfg<LOGN, AXIS_X>;
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto kern = abs_rfft_x_kernel<LOGN>;
+  if (dev < 64 && !configured[dev]) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
+    if (err != cudaSuccess) {
+      set_last_error("cudaFuncSetAttribute(abs_rfft_x, smem=%zu): %s", K::SMEM, cudaGetErrorString(err));
+      return ADEPT_ERR_CUDA;
+    }
+    configured[dev] = true;
+  }
+  const long long blocks = (p.npairs + K::F - 1) / K::F;
+  ProfileScope prof("abs_rfft_x", stream);
+  kern<<<(unsigned)blocks, K::THREADS, K::SMEM, stream>>>(p);
+  return check_launch("abs_rfft_x_kernel");
+}
+
+int abs_rfft_x_f64(const double* fin, double* fout, int batch, int nx, int nv, cudaStream_t stream) {
+  if (batch < 1 || nx < 2 || nv < 2 || (nv & 1)) {
+    set_last_error("abs_rfft_x: bad shape batch=%d nx=%d nv=%d (nv must be even)", batch, nx, nv);
+    return ADEPT_ERR_BAD_SHAPE;
+  }
+  const int logn = ilog2_exact(nx);
+  if (logn < 1 || logn > 13) {
+    set_last_error("abs_rfft_x: nx=%d must be a power of two <= 8192", nx);
+    return ADEPT_ERR_UNSUPPORTED;
+  }
+  if ((reinterpret_cast<uintptr_t>(fin) | reinterpret_cast<uintptr_t>(fout)) & 15) {
+    set_last_error("abs_rfft_x: buffers must be 16-byte aligned");
+    return ADEPT_ERR_BAD_ARG;
+  }
+  PushArgs p = {};
+  p.fin = fin, p.fout = fout, p.batch = batch, p.nx = nx, p.nv = nv;
+  p.npairs = (long long)batch * (nv / 2);
+  p.tw = get_twiddles(logn);
+  if (!p.tw) return ADEPT_ERR_CUDA;
+  switch (logn) {
+#define ADEPT_CASE(L) \
+  case L:             \
+    return launch_abs_rfft_x<L>(p, stream);
+    ADEPT_CASE(1) ADEPT_CASE(2) ADEPT_CASE(3) ADEPT_CASE(4) ADEPT_CASE(5) ADEPT_CASE(6) ADEPT_CASE(7)
+    ADEPT_CASE(8) ADEPT_CASE(9) ADEPT_CASE(10) ADEPT_CASE(11) ADEPT_CASE(12) ADEPT_CASE(13)
+#undef ADEPT_CASE
+  }
+  return ADEPT_ERR_UNSUPPORTED;
+}
+
 }  // namespace adept

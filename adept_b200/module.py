@@ -77,29 +77,86 @@ def field_moments(cfg, y0, y1=None, w=0.0):
     return res
 
 
-def dist_save(name, xax=None, vax=None):
-    """Save function for a species' distribution (get_dist_save_func, storage.py:165-188): the full f for a {t} block,
-    or f interpolated linearly on the mesh ``xax x vax`` for a {t, x, v} block (NaN outside the grid, as interpax does
-    with extrapolation off).  The {t, kx, v} block (|rfft_x f|) is not implemented."""
-    if (xax is None) != (vax is None):
-        raise ValueError("dist_save: give both xax and vax or neither")
+def dist_save(name, xax=None, vax=None, kxax=None):
+    """Save function for a species' distribution (get_dist_save_func, storage.py:165-190): the full f for a {t} block,
+    f interpolated linearly on the mesh ``xax x vax`` for a {t, x, v} block, or |rfft_x f| interpolated on
+    ``kxax x vax`` for a {t, kx, v} block (NaN outside the grid, as interpax does with extrapolation off).  The
+    spectrum block uses the one-sided axis 2 pi rfftfreq(nx, dx) that matches rfft's rows (the reference passes the
+    two-sided nx-long axis, which does not fit the array: storage.py:259, 271)."""
+    if xax is not None and kxax is not None:
+        raise ValueError("dist_save: give xax or kxax, not both")
+    if (xax is None and kxax is None) != (vax is None):
+        raise ValueError("dist_save: give (xax or kxax) together with vax, or none of them")
     tables = {}
 
     def fn(cfg, y0, y1=None, w=0.0):
         f0 = y0[name]
-        if xax is None:
+        if vax is None:
             return f0.clone() if y1 is None else f0 + w * (y1[name] - f0)
         from . import ops
 
         key = str(f0.device)
         if key not in tables:
             sg = cfg["grid"]["species_grids"][name]
+            first = cfg["grid"]["x"] if kxax is None else cfg["grid"]["kxr"]
             tables[key] = tuple(torch.as_tensor(np.array(a, dtype=np.float64), device=f0.device)
-                                for a in (cfg["grid"]["x"], sg["v"], xax, vax))
+                                for a in (first, sg["v"], xax if kxax is None else kxax, vax))
         x, v, xq, vq = tables[key]
-        return ops.interp2d(f0, x, v, xq, vq, None if y1 is None else y1[name], w)
+        if kxax is None:
+            return ops.interp2d(f0, x, v, xq, vq, None if y1 is None else y1[name], w)
+        f = f0 if y1 is None else f0 + w * (y1[name] - f0)  # the modulus is not linear: interpolate first
+        return ops.interp2d(ops.abs_rfft_x(f.contiguous()), x, v, xq, vq)
 
     return fn
+
+
+def _dim_axis(key, c):
+    """_add_dim_axes (storage.py:203-219): cell-centred for x, end-point inclusive otherwise."""
+    lo, hi, n = float(c[f"{key}min"]), float(c[f"{key}max"]), int(c[f"n{key}"])
+    d = (hi - lo) / n if key == "x" else 0.0
+    return np.linspace(lo + d / 2.0, hi - d / 2.0, n)
+
+
+def save_functions(cfg, grid):
+    """The deck's ``save:`` block as {key: (times, fn)} for :meth:`Vlasov1D.run` (get_save_quantities,
+    storage.py:222-283): ``fields*`` -> field_moments, ``<species>: {label: {t[, x, v | kx, v]}}`` ->
+    "<species>.<label>" distribution saves, dfdt diagnostics, plus the always-on ``default`` scalars at every step."""
+    out = {}
+    species = list(cfg["grid"]["species_grids"].keys())
+    for key, sc in (cfg.get("save") or {}).items():
+        if key.startswith("fields"):
+            out[key] = (save_axis(sc["t"], grid), field_moments)
+        elif key in species or key in ("diag-vlasov-dfdt", "diag-fp-dfdt"):
+            blocks = sc.items() if key in species else [(None, sc)]
+            for label, lc in blocks:
+                dims = set(k for k in lc if k in ("t", "x", "v", "kx"))
+                if dims == {"t"}:
+                    fn = dist_save(key)
+                elif dims == {"t", "x", "v"}:
+                    fn = dist_save(key, xax=_dim_axis("x", lc["x"]), vax=_dim_axis("v", lc["v"]))
+                elif dims == {"t", "kx", "v"}:
+                    fn = dist_save(key, kxax=_dim_axis("kx", lc["kx"]), vax=_dim_axis("v", lc["v"]))
+                else:
+                    raise NotImplementedError(f"save block {key}/{label}: dimensions {sorted(dims)}")
+                if key not in species:  # the diagnostics live on the electron grid (storage.py:262-270)
+                    fn = _on_species_grid(fn, key, "electron" if "electron" in species else species[0])
+                out[key if label is None else f"{key}.{label}"] = (save_axis(lc["t"], grid), fn)
+        else:
+            raise NotImplementedError(f"Unknown save type: {key}")
+    out["default"] = (np.asarray(grid.t, dtype=np.float64), default_scalars)
+    return out
+
+
+def _on_species_grid(fn, key, species):
+    """A distribution save function applied to a state entry that is not a species (dfdt diagnostics)."""
+
+    def wrapped(cfg, y0, y1=None, w=0.0):
+        cfg2 = dict(cfg)
+        cfg2["grid"] = dict(cfg["grid"])
+        cfg2["grid"]["species_grids"] = {key: cfg["grid"]["species_grids"][species]}
+        return fn(cfg2, y0, y1, w)
+
+    return wrapped
 
 
 class Vlasov1D:
@@ -159,6 +216,8 @@ class Vlasov1D:
         saved state is y0 + w (y1 - y0) (diffrax's linear dense output; see default_scalars / field_moments); returns
         (state, {name: [fn outputs]})."""
         nsteps = self.grid.nt if nsteps is None else nsteps
+        if save == "deck":  # the deck's own save: block, as the reference wires it (storage.py:222-283)
+            save = save_functions(self.cfg, self.grid)
         save = save or {}
         out = {k: [] for k in save}
         cursor = {k: 0 for k in save}

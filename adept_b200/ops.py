@@ -166,6 +166,17 @@ def krook_bwd(f_in, g, dv, dt, nu_K, f_mx, want_nu_bar=False):
     return fbar, nubar
 
 
+def abs_rfft_x(f, out=None):
+    """|rfft(f, axis=x)|: [.., nx/2 + 1, nv] (the spectrum of the {t, kx, v} distribution save, storage.py:189)."""
+    b, nx, nv = _shape3(f)
+    shape = tuple(f.shape[:-2]) + (nx // 2 + 1, nv)
+    out = torch.empty(shape, dtype=torch.float64, device=f.device) if out is None else out
+    rc = _lib.load().adept_b200_abs_rfft_x_f64(_ptr(f, "f"), _ptr(out, "out"), b, nx, nv, _stream())
+    _lib.check(rc, "abs_rfft_x")
+    _count()
+    return out
+
+
 def save_moments(f0, v, dv, f1=None, w=0.0, out=None):
     """[6, batch*nx] = dv * sum_v {f, f v, f v^2, f v^3, -|f| log|f|, f^2} of f = f0 + w (f1 - f0) (storage.py:119-162,
     286-327), one pass over f, the interpolated distribution is never materialised."""

@@ -120,6 +120,11 @@ int adept_b200_interp2d_f64(const double* f0, const double* f1, double w, int nx
                             const double* v, const double* xq, const double* vq, int nxq, int nvq, double* out,
                             void* stream);
 
+/* Spectrum save (get_dist_save_func, {t, kx, v} block, adept/_vlasov1d/storage.py:183-190): out[b, m, j] =
+ * |rfft(f[b, :, j])_m|, m = 0 .. nx/2; out is [batch, nx/2 + 1, nv].  nx a power of two <= 8192, nv even.  The caller
+ * interpolates on its (kx, v) sample points with adept_b200_interp2d_f64 over the one-sided axis 2 pi rfftfreq(nx, dx). */
+int adept_b200_abs_rfft_x_f64(const double* f, double* out, int batch, int nx, int nv, void* stream);
+
 /* Hou-Li spectral filter along x (HouLiFilter.__call__, vlasov.py:215-220): f_out = irfft(filt[m] rfft(f_in, axis=x)),
  * filt[nx/2+1] real.  zeros_v: a device array of nv zeros (the x-advection kernels run with zero advection speed). */
 int adept_b200_filter_x_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* filt,

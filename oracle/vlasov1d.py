@@ -1089,6 +1089,16 @@ def dist_save_xv(f, x, v, xax, vax):
     return interp2d_linear(xq.ravel(), vq.ravel(), x, v, f).reshape(xq.shape)
 
 
+def dist_save_kxv(f, kxr, v, kxax, vax):
+    """get_dist_save_func for a {t, kx, v} save block (storage.py:183-190): abs(rfft(f, axis=x)) interpolated on
+    meshgrid(kxax, vax, "ij").  The reference hands interp2d the nx-long two-sided axis cfg["grid"]["kx"] for an array
+    with nx/2 + 1 rows (storage.py:259, 271), which interpax rejects; the one-sided axis kxr = 2 pi rfftfreq(nx, dx)
+    that matches rfft's rows is used here (PARITY UNPINNED: the reference path cannot produce an array)."""
+    fk = np.abs(np.fft.rfft(f, axis=0))
+    kq, vq = np.meshgrid(kxax, vax, indexing="ij")
+    return interp2d_linear(kq.ravel(), vq.ravel(), kxr, v, fk).reshape(kq.shape)
+
+
 def save_axis(tcfg, grid):
     """storage.py:203-219 (_add_dim_axes for 't') + modules.py:166-181 defaults."""
     tmin = float(tcfg.get("tmin", grid["tmin"]))

@@ -705,3 +705,68 @@ def test_collisions_conserve_density_on_asymmetric_grid_gpu():
     np.testing.assert_allclose(f1.sum(axis=1) * dv, f0.sum(axis=1) * dv, rtol=1e-6)
     ref = O.Collisions(O.build_cfg(deepcopy(d)))(nu, nu, f0, grid.dt)
     assert rel_l2(f1, ref) <= 1e-11
+
+
+@pytest.mark.parametrize("nx,nv", [(32, 64), (256, 48), (4096, 16)])
+def test_abs_rfft_x_matches_numpy(ops, nx, nv):
+    """|rfft_x f| (the spectrum of the {t, kx, v} distribution save, storage.py:189) against numpy's rfft."""
+    rng = np.random.default_rng(nx)
+    f = rng.standard_normal((nx, nv))
+    out = host(ops.abs_rfft_x(dev(f)))
+    ref = np.abs(np.fft.rfft(f, axis=0))
+    assert out.shape == ref.shape == (nx // 2 + 1, nv)
+    assert np.max(np.abs(out - ref)) <= 1e-12 * np.max(ref)
+
+
+def test_dist_save_kx_block_matches_oracle():
+    """{t, kx, v} distribution save through the module's save function against the oracle's restatement (one-sided kx
+    axis), also on the state interpolated between two steps."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from adept_b200.module import dist_save
+
+    nx, nv = 64, 128
+    rng = np.random.default_rng(5)
+    dx = 20.94 / nx
+    kxr = 2 * np.pi * np.fft.rfftfreq(nx, d=dx)
+    v = np.linspace(-6.35, 6.35, nv)
+    f0, f1 = rng.standard_normal((nx, nv)), rng.standard_normal((nx, nv))
+    kq = np.linspace(0.0, 3.0, 17)
+    vq = np.linspace(-6.4, 6.4, 33)
+    cfg = {"grid": {"kxr": kxr, "x": None, "species_grids": {"electron": {"v": v}}}}
+    fn = dist_save("electron", kxax=kq, vax=vq)
+    for w, y1 in ((0.0, None), (0.4, {"electron": dev(f1)})):
+        out = host(fn(cfg, {"electron": dev(f0)}, y1, w))
+        ref = O.dist_save_kxv(f0 if y1 is None else f0 + w * (f1 - f0), kxr, v, kq, vq)
+        assert np.array_equal(np.isnan(out), np.isnan(ref))
+        ok = ~np.isnan(ref)
+        assert np.max(np.abs(out[ok] - ref[ok])) <= 1e-12 * np.max(np.abs(ref[ok]))
+
+
+def test_run_with_the_decks_own_save_block():
+    """Vlasov1D.run(save="deck") wires the YAML save: block like get_save_quantities (storage.py:222-283): fields,
+    "<species>.<label>" distribution saves, the dfdt diagnostics and the always-on default scalars."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import yaml
+    from pathlib import Path
+
+    from adept_b200.module import Vlasov1D
+
+    with open(Path(__file__).parent / "golden" / "epw.yaml") as fh:
+        deck = yaml.safe_load(fh)
+    deck["grid"]["tmax"] = 2.0
+    for k in ("fields", "diag-vlasov-dfdt", "diag-fp-dfdt"):
+        deck["save"][k]["t"].update(tmax=2.0, nt=5)
+    deck["save"]["electron"]["main"]["t"].update(tmax=2.0, nt=3)
+    deck["save"]["electron"]["spec"] = {"t": {"tmin": 0.0, "tmax": 2.0, "nt": 2},
+                                        "kx": {"kxmin": 0.0, "kxmax": 2.0, "nkx": 9},
+                                        "v": {"vmin": -6.0, "vmax": 6.0, "nv": 25}}
+    sim = Vlasov1D(deck)
+    _, saved = sim.run(save="deck")
+    assert set(saved) == {"fields", "electron.main", "electron.spec", "diag-vlasov-dfdt", "diag-fp-dfdt", "default"}
+    assert len(saved["default"]) == sim.grid.nt - 1 or len(saved["default"]) == sim.grid.nt
+    assert len(saved["electron.main"]) >= 2 and saved["electron.main"][0].shape == (32, 256)
+    assert saved["electron.spec"][-1].shape == (9, 25) and bool(torch.isfinite(saved["electron.spec"][-1]).all())
+    assert saved["diag-fp-dfdt"][-1].shape == (32, 256)
+    assert "n" in saved["fields"][-1]["electron"] and float(saved["default"][-1]["mean_n_electron"]) > 0.99
