@@ -35,17 +35,17 @@ struct CollideArgs {
   double* fout;
   long long rows;  // batch * nx
   int nv;
-  const double* v;  // [nv]
+  const double* v;  // f64  [nv]
   double dv, dt;
-  const double* nu_fp;  // [rows] or null (Fokker-Planck off)
-  const double* nu_K;   // [rows] or null (Krook off)
-  const double* f_mx;   // [nv] Krook Maxwellian (unit density)
+  const double* nu_fp;  // f64  [rows] or null (Fokker-Planck off)
+  const double* nu_K;   // f64  [rows] or null (Krook off)
+  const double* f_mx;   // f64  [nv] Krook Maxwellian (unit density)
   int model, scheme, nodrag;
   double sg_m, sg_ratio;  // super-Gaussian exponent m and Gamma(3/m)/Gamma(1/m)
   double* n_out;          // [rows] or null: sum_j f_out dv
   int rows_per_cta;       // R: x-rows handled by one CTA (set by the launcher)
   double nu_fp_scale, nu_K_scale;  // nu = scale * nu[row] (time envelope applied in the kernel)
-  const double* trow;              // nullable device-resident time row (common.cuh) that replaces the two scales
+  const double* trow;              // f64  nullable device-resident time row (common.cuh) that replaces the two scales
   int sc_steps;                    // self-consistent beta: Newton iterations (0 = off), fokker_planck.py:296-301
   double sc_rtol, sc_atol;
 };
@@ -521,6 +521,7 @@ __global__ void __launch_bounds__(MAXT, MINB) collide_kernel(CollideArgs p) {
   }
 }
 
+#ifndef ADEPT_F32_BUILD  // the adjoint exists in fp64 only
 // =====================================================================================================================
 // Adjoint of the Fokker-Planck step (central differencing, Lenard-Bernstein / Dougherty):  f_new = A(m(f))^{-1} f with
 // m = (vbar, T) the row moments of the INPUT f.  For a cotangent g of f_new:
@@ -825,6 +826,8 @@ int collide_bwd_f64(const double* fin, const double* fnew, const double* g, doub
   return ADEPT_ERR_UNSUPPORTED;
 }
 
+#endif  // ADEPT_F32_BUILD
+
 template <int E, int MAXT, int MINB, bool FAST, bool CC = false>
 static int launch_collide_t(CollideArgs p, cudaStream_t stream) {
   const int T = p.nv / E;
@@ -863,10 +866,13 @@ static int launch_collide(const CollideArgs& p, bool fast, cudaStream_t stream) 
   return fast ? launch_collide_t<E, MAXT, MINB, true>(p, stream) : launch_collide_t<E, MAXT, MINB, false>(p, stream);
 }
 
-int collide_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* v, double dv, double dt,
-                const double* nu_fp, const double* nu_K, const double* f_mx, int model, int scheme, int nodrag,
-                double sg_m, double sg_ratio, double* n_out, double nu_fp_scale, double nu_K_scale,
-                cudaStream_t stream, int sc_steps, double sc_rtol, double sc_atol) {
+int collide_f64(const double* fin, double* fout,
+                int batch, int nx, int nv, const double* v, double dv, double dt,                   // f64
+                const double* nu_fp, const double* nu_K, const double* f_mx,                        // f64
+                int model, int scheme, int nodrag, double sg_m, double sg_ratio,                    // f64
+                double* n_out,
+                double nu_fp_scale, double nu_K_scale,                                              // f64
+                cudaStream_t stream, int sc_steps, double sc_rtol, double sc_atol) {                // f64
   if (batch < 1 || nx < 1 || nv < 4) {
     set_last_error("collide: bad shape batch=%d nx=%d nv=%d", batch, nx, nv);
     return ADEPT_ERR_BAD_SHAPE;
@@ -888,6 +894,12 @@ int collide_f64(const double* fin, double* fout, int batch, int nx, int nv, cons
   }
   // uniform-grid arithmetic, central or Chang-Cooper; the Newton refinement of beta lives in the general kernel
   const bool fast = model != FP_SUPERGAUSSIAN && !nodrag && sc_steps == 0;
+#ifdef ADEPT_F32_BUILD
+  if (!fast) {  // the closed-form Chang-Cooper weights and the Newton iteration of the general path need fp64
+    set_last_error("collide(f32): only Lenard-Bernstein / Dougherty (central or Chang-Cooper) + Krook are offered in fp32");
+    return ADEPT_ERR_UNSUPPORTED;
+  }
+#endif
   if (nv % 16 == 0 && nv / 16 <= 256) return launch_collide<16, 256, 2>(p, fast, stream);
   if (nv % 16 == 0 && nv / 16 <= 512) return launch_collide<16, 512, 1>(p, fast, stream);
   if (nv % 16 == 0 && nv / 16 <= 1024) return launch_collide<16, 1024, 1>(p, fast, stream);

@@ -10,6 +10,7 @@ namespace adept {
 enum { FP_LB = 0, FP_DOUGHERTY = 1, FP_SUPERGAUSSIAN = 2 };
 enum { FP_CENTRAL = 0, FP_CHANG_COOPER = 1 };
 
+#ifndef ADEPT_F32_BUILD  // the generated fp32 build takes both from common32.cuh
 // couplings of the unit-diagonal reduced system below 2^-56 (an eighth of the fp64 machine epsilon) cannot change
 // the solution at rounding level: parallel cyclic reduction stops there
 #define PCR_TOL 1.3877787807814457e-17
@@ -24,6 +25,7 @@ __device__ __forceinline__ double fast_rcp(double x) {
   r = fma(r, e, r);
   return r;
 }
+#endif  // ADEPT_F32_BUILD
 
 // Chang-Cooper delta on the fast path: for |w| < 1/4 (w = C dv / D = dv (v_edge - vbar) / T, a few 1e-2 on production
 // grids) the Bernoulli series of 1/w - 1/(e^w - 1) through w^11 (next term < 2e-19) replaces expm1 and two reciprocals

@@ -33,16 +33,17 @@ struct PushArgs {
   double* fout;
   int batch, nx, nv;
   long long npairs;  // total sequence pairs over the batch
+  // (lines tagged "f64" keep double precision in the generated fp32 build: phases are formed in fp64)
   // AXIS_X: alpha_j = k1[b] * (v[j] * dt)
-  const double* v;
-  const double* k1_batch;  // nullable -> k1
-  double k1;
-  double dt;
+  const double* v;         // f64
+  const double* k1_batch;  // f64  nullable -> k1
+  double k1;               // f64
+  double dt;               // f64
   // AXIS_V: accel_i = (q*(e_i+dex_i) + (q*q/m)*pond_i)/m ; alpha_i = k1 * (dt * accel_i)
-  const double* e;
-  const double* dex;   // nullable
-  const double* pond;  // nullable
-  double q, m;
+  const double* e;     // f64
+  const double* dex;   // f64  nullable
+  const double* pond;  // f64  nullable
+  double q, m;         // f64
   const cplx* tw;
   int zero;  // always 0; opaque to ptxas (see FftPass)
   const double* filt;  // nullable [N/2+1]: real multiplier per mode (Hou-Li filter)
@@ -70,21 +71,21 @@ __global__ void __launch_bounds__(PushCfg<LOGN, AXIS>::THREADS, (PushCfg<LOGN, A
   const double* src = p.fin;
   double* dst = p.fout;
   long long stride = 1;  // element stride along the transformed axis
-  double alpha_a = 0.0, alpha_b = 0.0;
+  double alpha_a = 0.0, alpha_b = 0.0;  // f64
   if (active) {
     if (AXIS == AXIS_V) {
       const long long row0 = 2 * G;  // global row over [batch, nx]
       src += row0 * p.nv;
       dst += row0 * p.nv;
       const int b = (int)(row0 / p.nx);
-      const double k1 = p.k1_batch ? p.k1_batch[b] : p.k1;
-      const double q2m = p.q * p.q / p.m;
-      double acc[2];
+      const double k1 = p.k1_batch ? p.k1_batch[b] : p.k1;  // f64
+      const double q2m = p.q * p.q / p.m;                     // f64
+      double acc[2];                                          // f64
 #pragma unroll
       for (int s = 0; s < 2; s++) {
-        double ee = p.e[row0 + s];
-        if (p.dex) ee = __dadd_rn(ee, p.dex[row0 + s]);
-        const double pd = p.pond ? p.pond[row0 + s] : 0.0;
+        double ee = p.e[row0 + s];                           // f64
+        if (p.dex) ee = __dadd_rn(ee, p.dex[row0 + s]);      // f64
+        const double pd = p.pond ? p.pond[row0 + s] : 0.0;   // f64
         acc[s] = accel_of(ee, pd, p.q, q2m, p.m);
       }
       alpha_a = k1 * (p.dt * acc[0]);
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(PushCfg<LOGN, AXIS>::THREADS, (PushCfg<LOGN, A
       src += (long long)b * p.nx * p.nv + 2 * cp;
       dst += (long long)b * p.nx * p.nv + 2 * cp;
       stride = p.nv;
-      const double k1 = p.k1_batch ? p.k1_batch[b] : p.k1;
+      const double k1 = p.k1_batch ? p.k1_batch[b] : p.k1;  // f64
       alpha_a = k1 * (p.v[2 * cp] * p.dt);
       alpha_b = k1 * (p.v[2 * cp + 1] * p.dt);
     }
@@ -209,8 +210,9 @@ static int ilog2_exact(int n) {
   return l;
 }
 
-int vdfdx_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* v, double dt,
-              const double* k1_batch, double k1, cudaStream_t stream, const double* filt) {
+int vdfdx_f64(const double* fin, double* fout,
+              int batch, int nx, int nv, const double* v, double dt, const double* k1_batch, double k1,  // f64
+              cudaStream_t stream, const double* filt) {
   if (batch < 1 || nx < 2 || nv < 2 || (nv & 1)) {
     set_last_error("vdfdx: bad shape batch=%d nx=%d nv=%d (nv must be even)", batch, nx, nv);
     return ADEPT_ERR_BAD_SHAPE;
@@ -236,8 +238,10 @@ int vdfdx_f64(const double* fin, double* fout, int batch, int nx, int nv, const 
   return dispatch_push<AXIS_X>(logn, p, stream);
 }
 
-int edfdv_exp_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* e, const double* dex,
-                  const double* pond, double q, double m, double dt, double k1, cudaStream_t stream) {
+int edfdv_exp_f64(const double* fin, double* fout,
+                  int batch, int nx, int nv, const double* e, const double* dex, const double* pond,  // f64
+                  double q, double m, double dt, double k1,                                           // f64
+                  cudaStream_t stream) {
   if (batch < 1 || nx < 2 || nv < 2 || (nx & 1)) {
     set_last_error("edfdv_exp: bad shape batch=%d nx=%d nv=%d (nx must be even)", batch, nx, nv);
     return ADEPT_ERR_BAD_SHAPE;

@@ -22,6 +22,7 @@ struct PhaseCfg {
 };
 
 // Fill the two phase tables of one sequence pair; called by the `stride` threads t = 0..stride-1 of the FFT group.
+// F64-BEGIN (the generated fp32 build keeps the phase arithmetic in fp64 and rounds the table entries once)
 template <int LOGN>
 __device__ __forceinline__ void phase_table_fill(cplx* ph, double alpha_a, double alpha_b, int t, int stride) {
   using PC = PhaseCfg<LOGN>;
@@ -39,6 +40,7 @@ __device__ __forceinline__ void phase_table_fill(cplx* ph, double alpha_a, doubl
     ph[i] = cmake(cs * amp, nyq ? 0.0 : -sn * amp);
   }
 }
+// F64-END
 
 // Half-spectrum update.  On entry thread t holds Z[t + T m] in x[m], Z = FFT(a + i b).  Its lower register half
 // (m < E/2) are the modes k = t + T m < N/2; the partner N - k of each lives in the upper register half of thread

@@ -41,6 +41,15 @@ def _ptr(t, name, allow_none=False):
     return C.c_void_p(t.data_ptr())
 
 
+def _ptr32(t, name, allow_none=False):
+    """float32 twin of :func:`_ptr` for the ``_f32`` entry points."""
+    if t is None and allow_none:
+        return None
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+        raise AdeptB200Error(f"{name}: expected a contiguous float32 CUDA tensor")
+    return C.c_void_p(t.data_ptr())
+
+
 def _shape3(f):
     if f.dim() == 2:
         return 1, f.shape[0], f.shape[1]
@@ -164,6 +173,43 @@ def krook_bwd(f_in, g, dv, dt, nu_K, f_mx, want_nu_bar=False):
     _lib.check(rc, "krook_bwd")
     _count()
     return fbar, nubar
+
+
+# ------------------------------------------------------------------------------------- single precision (extra)
+def vdfdx_f32(f, v, dt, k1x, out=None, k1x_batch=None):
+    """x-advection of a float32 distribution (v, k1x in double: phases are formed in fp64)."""
+    b, nx, nv = _shape3(f)
+    out = torch.empty_like(f) if out is None else out
+    rc = _lib.load().adept_b200_vdfdx_f32(_ptr32(f, "f"), _ptr32(out, "out"), b, nx, nv, _ptr(v, "v"), float(dt),
+                                          float(k1x), _ptr(k1x_batch, "k1x_batch", True), _stream())
+    _lib.check(rc, "vdfdx_f32")
+    _count()
+    return out
+
+
+def edfdv_exp_f32(f, e, pond, q, m, dt, k1v, out=None, dex=None):
+    """Spectral v-advection of a float32 distribution (fields in double)."""
+    b, nx, nv = _shape3(f)
+    out = torch.empty_like(f) if out is None else out
+    rc = _lib.load().adept_b200_edfdv_exp_f32(_ptr32(f, "f"), _ptr32(out, "out"), b, nx, nv, _ptr(e, "e"),
+                                              _ptr(dex, "dex", True), _ptr(pond, "pond", True), float(q), float(m),
+                                              float(dt), float(k1v), _stream())
+    _lib.check(rc, "edfdv_exp_f32")
+    _count()
+    return out
+
+
+def collide_f32(f, v, dv, dt, nu_fp=None, nu_K=None, f_mx=None, model=1, scheme=0, n_out=None, out=None):
+    """Fokker-Planck (LB / Dougherty, central or Chang-Cooper) + Krook on a float32 distribution."""
+    b, nx, nv = _shape3(f)
+    out = torch.empty_like(f) if out is None else out
+    rc = _lib.load().adept_b200_collide_f32(_ptr32(f, "f"), _ptr32(out, "out"), b, nx, nv, _ptr(v, "v"), float(dv),
+                                            float(dt), _ptr(nu_fp, "nu_fp", True), _ptr(nu_K, "nu_K", True),
+                                            _ptr(f_mx, "f_mx", True), int(model), int(scheme),
+                                            _ptr32(n_out, "n_out", True), _stream())
+    _lib.check(rc, "collide_f32")
+    _count()
+    return out
 
 
 def abs_rfft_x(f, out=None):

@@ -234,6 +234,20 @@ int adept_b200_edfdv_spline_bwd_f64(const double* f_in, const double* g, int bat
 int adept_b200_krook_bwd_f64(const double* f_in, const double* g, int batch, int nx, int nv, double dv, double dt,
                              const double* nu_K, const double* f_mx, double* f_bar, double* nu_bar, void* stream);
 
+/* ---- single precision (explicit extra of SURVEY.md 8b; the reference itself always runs in fp64, _base_.py:287-292) --
+ * The same kernels with f in float (generated from the fp64 sources, adept_b200/build.py): velocity grids, fields,
+ * collision profiles and all scalars stay double, so phases, accelerations and operator coefficients are formed as
+ * in the fp64 path and rounded once.  Bar: relative L2 <= 1e-5 against the fp64 oracle.  Power-of-two transform
+ * lengths only; collisions: Lenard-Bernstein / Dougherty (central or Chang-Cooper) and Krook. */
+int adept_b200_vdfdx_f32(const float* f_in, float* f_out, int batch, int nx, int nv, const double* v, double dt,
+                         double k1x, const double* k1x_batch, void* stream);
+int adept_b200_edfdv_exp_f32(const float* f_in, float* f_out, int batch, int nx, int nv, const double* e,
+                             const double* dex, const double* pond, double charge, double mass, double dt, double k1v,
+                             void* stream);
+int adept_b200_collide_f32(const float* f_in, float* f_out, int batch, int nx, int nv, const double* v, double dv,
+                           double dt, const double* nu_fp, const double* nu_K, const double* f_mx, int model,
+                           int scheme, float* n_out, void* stream);
+
 /* ---- whole time step ------------------------------------------------------------------------------------------------
  * adept_b200_step_f64 enqueues every kernel of one `vlasov-1d` step y -> y' on `stream` with no host work in between:
  * it replaces VlasovMaxwell.__call__ and what it calls (adept/_vlasov1d/solvers/vector_field.py:55-95 LeapfrogIntegrator,
