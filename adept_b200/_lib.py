@@ -83,6 +83,10 @@ SIGNATURES = {
                                          c_d, c_d, c_d, c_dp, c_d, c_dp, c_i, c_i, c_dp],
     "adept_b200_save_moments_f64": [c_dp, c_dp, c_d, c_i, c_i, c_i, c_dp, c_d, c_dp, c_dp],
     "adept_b200_interp2d_f64": [c_dp, c_dp, c_d, c_i, c_i, c_dp, c_dp, c_dp, c_dp, c_i, c_i, c_dp, c_dp],
+    "adept_b200_marginal_f64": [c_dp, c_dp, c_ll, c_i, c_dp, c_dp],
+    "adept_b200_transpose_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp],
+    "adept_b200_collide_coef_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_d, c_d, c_dp, c_i, c_i, c_i, c_i, c_d, c_d,
+                                    c_dp, c_dp, c_i, c_dp],
     "adept_b200_vdfdx_f32": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_d, c_d, c_dp, c_dp],
     "adept_b200_edfdv_exp_f32": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_dp, c_dp, c_d, c_d, c_d, c_d, c_dp],
     "adept_b200_collide_f32": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_d, c_d, c_dp, c_dp, c_dp, c_i, c_i, c_dp, c_dp],

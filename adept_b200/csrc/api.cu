@@ -503,4 +503,28 @@ int adept_b200_collide_sc_f64(const double* f_in, double* f_out, int batch, int 
                      n_out, 1.0, 1.0, (cudaStream_t)stream, sc_max_steps, sc_rtol, sc_atol);
 }
 
+/* ---- vlasov-1d2v ---- */
+int adept_b200_marginal_f64(const double* f, const double* wperp, long long rows, int nvperp, double* out, void* stream) {
+  ADEPT_REQUIRE(f, "f") ADEPT_REQUIRE(wperp, "wperp") ADEPT_REQUIRE(out, "out")
+  return marginal_f64(f, wperp, rows, nvperp, out, (cudaStream_t)stream);
+}
+
+int adept_b200_transpose_f64(const double* in, double* out, int batch, int n0, int n1, void* stream) {
+  ADEPT_REQUIRE(in, "in") ADEPT_REQUIRE(out, "out")
+  return transpose_f64(in, out, batch, n0, n1, (cudaStream_t)stream);
+}
+
+int adept_b200_collide_coef_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* v, double dv,
+                                double dt, const double* nu_fp, int model, int scheme, int nodrag, int sc_max_steps,
+                                double sc_rtol, double sc_atol, const double* coef_in, double* coef_out, int coef_div,
+                                void* stream) {
+  ADEPT_REQUIRE(f_in, "f_in") ADEPT_REQUIRE(f_out, "f_out") ADEPT_REQUIRE(v, "v") ADEPT_REQUIRE(nu_fp, "nu_fp")
+  if (!coef_in && !coef_out) {
+    set_last_error("adept_b200_collide_coef_f64: give coef_in or coef_out");
+    return ADEPT_ERR_BAD_ARG;
+  }
+  return collide_f64(f_in, f_out, batch, nx, nv, v, dv, dt, nu_fp, nullptr, nullptr, model, scheme, nodrag, 2.0, 0.5,
+                     nullptr, 1.0, 1.0, (cudaStream_t)stream, sc_max_steps, sc_rtol, sc_atol, coef_in, coef_out, coef_div);
+}
+
 }  // extern "C"

@@ -48,6 +48,13 @@ struct CollideArgs {
   const double* trow;              // f64  nullable device-resident time row (common.cuh) that replaces the two scales
   int sc_steps;                    // self-consistent beta: Newton iterations (0 = off), fokker_planck.py:296-301
   double sc_rtol, sc_atol;
+  // vlasov-1d2v (adept/_vlasov1d2v/solvers/pushers/fokker_planck.py:104-140): the operator coefficients of a group of
+  // coef_div consecutive rows (the v_perp slices of one x) come from the group's marginal, not from the row itself.
+  // coef_out [rows, 2] (nullable): (vbar, beta) of every row as computed here; coef_in [rows / coef_div, 2] (nullable):
+  // (vbar, beta) to use instead, and nu_fp is then indexed per group.  General (non-fast) path only.
+  const double* coef_in;  // f64
+  double* coef_out;       // f64
+  int coef_div;
 };
 
 // d delta / d w of the Chang-Cooper weight, branch by branch as autodiff differentiates driftdiffusion.py:96-103
@@ -157,7 +164,8 @@ __global__ void __launch_bounds__(MAXT, MINB) collide_kernel(CollideArgs p) {
   const double vc = __ldg(p.v + i0);        // v of the chunk's first cell; v[i0 + l] = vc + l dv (uniform grid)
 
   if (p.nu_fp) {
-    const double nu = __dmul_rn(p.trow ? p.trow[TROW_NU_FP] : p.nu_fp_scale, p.nu_fp[row]);
+    const long long grp = p.coef_in ? row / p.coef_div : row;
+    const double nu = __dmul_rn(p.trow ? p.trow[TROW_NU_FP] : p.nu_fp_scale, p.nu_fp[grp]);
     // ---- 2. moments in chunk-local index space: sum f, sum f l, sum f l^2 ------------------------------------------
     double mom[3] = {0.0, 0.0, 0.0};
 #pragma unroll
@@ -180,9 +188,12 @@ __global__ void __launch_bounds__(MAXT, MINB) collide_kernel(CollideArgs p) {
     if (!live) mom[0] = mom[1] = mom[2] = 0.0;
     row_reduce<3>(mom, red, parity, live ? r : 0, tt, T, RT, warp_mode, live);
     const double s0 = mom[0], s1 = mom[1], s2 = mom[2];
-    const double vbar = (p.model == FP_LB) ? 0.0 : s1 / s0;
+    const double vbar = (!FAST && p.coef_in) ? p.coef_in[2 * grp] : ((p.model == FP_LB) ? 0.0 : s1 / s0);
     double beta, D;
-    if (!FAST && p.model == FP_SUPERGAUSSIAN) {
+    if (!FAST && p.coef_in) {  // coefficients of the group's marginal (computed by an earlier launch with coef_out)
+      beta = p.coef_in[2 * grp + 1];
+      D = 1.0 / (2.0 * beta);
+    } else if (!FAST && p.model == FP_SUPERGAUSSIAN) {
       double sp[1] = {0.0};
 #pragma unroll
       for (int l = 0; l < E; l++) sp[0] += chunk[l] * pow(fabs(__ldg(p.v + i0 + l) - vbar), p.sg_m);
@@ -259,6 +270,7 @@ __global__ void __launch_bounds__(MAXT, MINB) collide_kernel(CollideArgs p) {
       }
       D = 1.0 / (2.0 * beta);
     }
+    if (!FAST && p.coef_out && tt == 0 && active) p.coef_out[2 * row] = vbar, p.coef_out[2 * row + 1] = beta;
     const double dtnu = dt * nu;
 
     // ---- 3. edge coefficients U_l, L_l of edge (i0 + l) for l = -1 .. E-1 ------------------------------------------
@@ -872,7 +884,8 @@ int collide_f64(const double* fin, double* fout,
                 int model, int scheme, int nodrag, double sg_m, double sg_ratio,                    // f64
                 double* n_out,
                 double nu_fp_scale, double nu_K_scale,                                              // f64
-                cudaStream_t stream, int sc_steps, double sc_rtol, double sc_atol) {                // f64
+                cudaStream_t stream, int sc_steps, double sc_rtol, double sc_atol,                  // f64
+                const double* coef_in, double* coef_out, int coef_div) {                            // f64
   if (batch < 1 || nx < 1 || nv < 4) {
     set_last_error("collide: bad shape batch=%d nx=%d nv=%d", batch, nx, nv);
     return ADEPT_ERR_BAD_SHAPE;
@@ -887,13 +900,21 @@ int collide_f64(const double* fin, double* fout,
   }
   CollideArgs p = {fin, fout, (long long)batch * nx, nv, v, dv, dt, nu_fp, nu_K, f_mx,
                    model, scheme, nodrag, sg_m, sg_ratio, n_out, 1, nu_fp_scale, nu_K_scale,
-                   current_time_row(), sc_steps, sc_rtol, sc_atol};
+                   current_time_row(), sc_steps, sc_rtol, sc_atol, coef_in, coef_out, coef_div > 0 ? coef_div : 1};
+  if ((coef_in || coef_out) && model == FP_SUPERGAUSSIAN) {
+    set_last_error("collide: marginal coefficients (coef_in / coef_out) are defined for Lenard-Bernstein / Dougherty");
+    return ADEPT_ERR_UNSUPPORTED;
+  }
+  if (coef_in && (coef_div < 1 || ((long long)batch * nx) % coef_div)) {
+    set_last_error("collide: coef_div=%d must divide the number of rows", coef_div);
+    return ADEPT_ERR_BAD_ARG;
+  }
   if (sc_steps < 0 || sc_steps > 64) {
     set_last_error("collide: self-consistent beta max_steps=%d out of range [0, 64]", sc_steps);
     return ADEPT_ERR_BAD_ARG;
   }
   // uniform-grid arithmetic, central or Chang-Cooper; the Newton refinement of beta lives in the general kernel
-  const bool fast = model != FP_SUPERGAUSSIAN && !nodrag && sc_steps == 0;
+  const bool fast = model != FP_SUPERGAUSSIAN && !nodrag && sc_steps == 0 && !coef_in && !coef_out;
 #ifdef ADEPT_F32_BUILD
   if (!fast) {  // the closed-form Chang-Cooper weights and the Newton iteration of the general path need fp64
     set_last_error("collide(f32): only Lenard-Bernstein / Dougherty (central or Chang-Cooper) + Krook are offered in fp32");

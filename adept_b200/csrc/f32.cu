@@ -19,7 +19,7 @@ int edfdv_exp_f32(const float* fin, float* fout, int batch, int nx, int nv, cons
 int collide_f32(const float* fin, float* fout, int batch, int nx, int nv, const double* v, double dv, double dt,
                 const double* nu_fp, const double* nu_K, const double* f_mx, int model, int scheme, int nodrag,
                 double sg_m, double sg_ratio, float* n_out, double nu_fp_scale, double nu_K_scale, cudaStream_t stream,
-                int sc_steps, double sc_rtol, double sc_atol);
+                int sc_steps, double sc_rtol, double sc_atol, const double* coef_in, double* coef_out, int coef_div);
 
 static std::mutex g_tw_mutex;
 static cplx* g_tw[64][16] = {};
@@ -94,5 +94,5 @@ extern "C" int adept_b200_collide_f32(const float* f_in, float* f_out, int batch
                                       const double* f_mx, int model, int scheme, float* n_out, void* stream) {
   F32_REQUIRE(f_in, "f_in") F32_REQUIRE(f_out, "f_out") F32_REQUIRE(v, "v")
   return adept32::collide_f32(f_in, f_out, batch, nx, nv, v, dv, dt, nu_fp, nu_K, f_mx, model, scheme, 0, 2.0, 0.5,
-                              n_out, 1.0, 1.0, (cudaStream_t)stream, 0, 1e-8, 1e-12);
+                              n_out, 1.0, 1.0, (cudaStream_t)stream, 0, 1e-8, 1e-12, nullptr, nullptr, 1);
 }

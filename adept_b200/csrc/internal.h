@@ -43,7 +43,8 @@ int wave_step_f64(const double* a, const double* aold, const double* djy, const 
 int collide_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* v, double dv, double dt,
                 const double* nu_fp, const double* nu_K, const double* f_mx, int model, int scheme, int nodrag,
                 double sg_m, double sg_ratio, double* n_out, double nu_fp_scale, double nu_K_scale,
-                cudaStream_t stream, int sc_steps = 0, double sc_rtol = 1e-8, double sc_atol = 1e-12);
+                cudaStream_t stream, int sc_steps = 0, double sc_rtol = 1e-8, double sc_atol = 1e-12,
+                const double* coef_in = nullptr, double* coef_out = nullptr, int coef_div = 1);
 int diff_over_dt_f64(const double* a, const double* b, double dt, double* out, long long n, cudaStream_t stream);
 int field_energy_f64(const double* e0, const double* de0, const double* e1, const double* de1, double w, int batch,
                      int nx, double* out, cudaStream_t stream);
@@ -66,6 +67,8 @@ int edfdv_spline_bwd_f64(const double* f, const double* g, int batch, int nx, in
                          cudaStream_t stream);
 int krook_bwd_f64(const double* f, const double* g, int batch, int nx, int nv, double dv, double dt, const double* nu_K,
                   const double* f_mx, double* fbar, double* nubar, cudaStream_t stream);
+int marginal_f64(const double* f, const double* w, long long rows, int np, double* out, cudaStream_t stream);
+int transpose_f64(const double* in, double* out, int batch, int n0, int n1, cudaStream_t stream);
 int abs_rfft_x_f64(const double* fin, double* fout, int batch, int nx, int nv, cudaStream_t stream);
 bool vpush_collide_supported(int nx, int nv, int model, int scheme, int nodrag);
 int vpush_collide_f64(const double* fin, double* fout, int batch, int nx, int nv, const double* e, const double* dex,

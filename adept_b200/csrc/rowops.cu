@@ -353,4 +353,50 @@ int interp2d_f64(const double* f0, const double* f1, double w, int nx, int nv, c
   return check_launch("interp2d_kernel");
 }
 
+// ---- vlasov-1d2v helpers (adept/_vlasov1d2v/solvers/vector_field.py:36-38, pushers/fokker_planck.py:81-83) -----------
+// marginal F[row] = sum_p f[row, p] w[p]  (einsum "xvp,p->xv"), rows = nx * nv, fixed summation order per row
+__global__ void __launch_bounds__(256) marginal_kernel(const double* __restrict__ f, const double* __restrict__ w,
+                                                       long long rows, int np, double* __restrict__ out) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  const double* fr = f + row * np;
+  double s = 0.0;
+  for (int j = 0; j < np; j++) s += fr[j] * __ldg(w + j);
+  out[row] = s;
+}
+
+int marginal_f64(const double* f, const double* w, long long rows, int np, double* out, cudaStream_t stream) {
+  if (rows < 1 || np < 1) {
+    set_last_error("marginal: bad shape rows=%lld np=%d", rows, np);
+    return ADEPT_ERR_BAD_SHAPE;
+  }
+  ProfileScope prof("marginal", stream);
+  marginal_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, stream>>>(f, w, rows, np, out);
+  return check_launch("marginal_kernel");
+}
+
+// batched transpose in[b, n0, n1] -> out[b, n1, n0] through a padded 32 x 32 shared-memory tile
+__global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict__ in, double* __restrict__ out, int n0,
+                                                        int n1) {
+  __shared__ double tile[32][33];
+  const long long base = (long long)blockIdx.z * n0 * n1;
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8)
+    if (i0 + r < n0 && j0 + tx < n1) tile[r][tx] = in[base + (long long)(i0 + r) * n1 + j0 + tx];
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8)
+    if (j0 + r < n1 && i0 + tx < n0) out[base + (long long)(j0 + r) * n0 + i0 + tx] = tile[tx][r];
+}
+
+int transpose_f64(const double* in, double* out, int batch, int n0, int n1, cudaStream_t stream) {
+  if (batch < 1 || n0 < 1 || n1 < 1 || batch > 65535 || in == out) {
+    set_last_error("transpose: bad shape batch=%d n0=%d n1=%d (or in-place)", batch, n0, n1);
+    return ADEPT_ERR_BAD_SHAPE;
+  }
+  ProfileScope prof("transpose", stream);
+  transpose_kernel<<<dim3((n1 + 31) / 32, (n0 + 31) / 32, batch), 256, 0, stream>>>(in, out, n0, n1);
+  return check_launch("transpose_kernel");
+}
+
 }  // namespace adept

@@ -175,6 +175,44 @@ def krook_bwd(f_in, g, dv, dt, nu_K, f_mx, want_nu_bar=False):
     return fbar, nubar
 
 
+# ----------------------------------------------------------------------------------------------- vlasov-1d2v
+def marginal(f, wperp, out=None):
+    """F[..., v] = sum_p f[..., v, p] wperp[p] (vector_field.py:36-38 of adept/_vlasov1d2v)."""
+    np_ = f.shape[-1]
+    rows = f.numel() // np_
+    out = torch.empty(f.shape[:-1], dtype=torch.float64, device=f.device) if out is None else out
+    rc = _lib.load().adept_b200_marginal_f64(_ptr(f, "f"), _ptr(wperp, "wperp"), rows, np_, _ptr(out, "out"), _stream())
+    _lib.check(rc, "marginal")
+    _count()
+    return out
+
+
+def transpose_last2(f, out=None):
+    """[..., n0, n1] -> [..., n1, n0], out of place."""
+    n0, n1 = f.shape[-2], f.shape[-1]
+    b = f.numel() // (n0 * n1)
+    out = torch.empty(tuple(f.shape[:-2]) + (n1, n0), dtype=torch.float64, device=f.device) if out is None else out
+    rc = _lib.load().adept_b200_transpose_f64(_ptr(f, "f"), _ptr(out, "out"), b, n0, n1, _stream())
+    _lib.check(rc, "transpose")
+    _count()
+    return out
+
+
+def collide_coef(f, v, dv, dt, nu_fp, model=1, scheme=0, nodrag=False, sc_steps=0, sc_rtol=1e-8, sc_atol=1e-12,
+                 coef_in=None, coef_out=None, coef_div=1, out=None):
+    """Fokker-Planck step whose (vbar, beta) are recorded (coef_out[rows, 2]) or imposed per group of ``coef_div`` rows
+    (coef_in[rows / coef_div, 2]); see adept_b200_collide_coef_f64."""
+    b, nx, nv = _shape3(f)
+    out = torch.empty_like(f) if out is None else out
+    rc = _lib.load().adept_b200_collide_coef_f64(
+        _ptr(f, "f"), _ptr(out, "out"), b, nx, nv, _ptr(v, "v"), float(dv), float(dt), _ptr(nu_fp, "nu_fp"), int(model),
+        int(scheme), int(bool(nodrag)), int(sc_steps), float(sc_rtol), float(sc_atol), _ptr(coef_in, "coef_in", True),
+        _ptr(coef_out, "coef_out", True), int(coef_div), _stream())
+    _lib.check(rc, "collide_coef")
+    _count()
+    return out
+
+
 # ------------------------------------------------------------------------------------- single precision (extra)
 def vdfdx_f32(f, v, dt, k1x, out=None, k1x_batch=None):
     """x-advection of a float32 distribution (v, k1x in double: phases are formed in fp64)."""

@@ -234,6 +234,23 @@ int adept_b200_edfdv_spline_bwd_f64(const double* f_in, const double* g, int bat
 int adept_b200_krook_bwd_f64(const double* f_in, const double* g, int batch, int nx, int nv, double dv, double dt,
                              const double* nu_K, const double* f_mx, double* f_bar, double* nu_bar, void* stream);
 
+/* ---- vlasov-1d2v (f[nx, nv, nvperp], cylindrical v_perp, adept/_vlasov1d2v/) -----------------------
+ * The advection kernels serve the 2V layout unchanged (v_perp is a spectator: the x-advection sees nv * nvperp columns,
+ * the v_par-advection is the strided-pencil kernel with one [nv, nvperp] member per x and per-member phase increments).
+ * What is new: the v_perp marginal F[x, v] = sum_p f[x, v, p] wperp[p] (vector_field.py:36-38) that feeds the 1-D field
+ * solve, a batched transpose [b, n0, n1] -> [b, n1, n0] (out of place) that lays the v_par rows of every (x, v_perp)
+ * slice out contiguously, and the collision step with the operator coefficients taken from the marginal
+ * (pushers/fokker_planck.py:104-140): a first call on the marginal rows with coef_out[rows, 2] records (vbar, beta) of
+ * every row (after the self-consistent Newton refinement, if any; its f_out is the collided marginal), a second call on
+ * the nx * nvperp slice rows with coef_in[rows / coef_div, 2] and coef_div = nvperp applies the same tridiagonal
+ * operator to every slice (nu_fp is then indexed per group).  Lenard-Bernstein / Dougherty / dougherty_nodrag. */
+int adept_b200_marginal_f64(const double* f, const double* wperp, long long rows, int nvperp, double* out, void* stream);
+int adept_b200_transpose_f64(const double* in, double* out, int batch, int n0, int n1, void* stream);
+int adept_b200_collide_coef_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* v, double dv,
+                                double dt, const double* nu_fp, int model, int scheme, int nodrag, int sc_max_steps,
+                                double sc_rtol, double sc_atol, const double* coef_in, double* coef_out, int coef_div,
+                                void* stream);
+
 /* ---- single precision (explicit extra of SURVEY.md 8b; the reference itself always runs in fp64, _base_.py:287-292) --
  * The same kernels with f in float (generated from the fp64 sources, adept_b200/build.py): velocity grids, fields,
  * collision profiles and all scalars stay double, so phases, accelerations and operator coefficients are formed as

@@ -66,6 +66,11 @@ timeit("vdfdx_rho(tma)", lambda: ops.vdfdx_rho(fd, vd, 0.1, k1x, parts, out=gd))
 timeit("vpush_collide", lambda: ops.vpush_collide(fd, e, None, -1.0, 1.0, 0.1, k1v, vd, dv, nu, model=1, out=gd), 32.0)
 nu_cc = nu
 timeit("vpush_collide_cc", lambda: ops.vpush_collide(fd, e, None, -1.0, 1.0, 0.1, k1v, vd, dv, nu_cc, model=1, out=gd, scheme=1), 32.0)
+# single precision (8 B/cell per operator application)
+f32, g32 = fd.float(), torch.empty_like(fd, dtype=torch.float32)
+timeit("vdfdx_f32", lambda: ops.vdfdx_f32(f32, vd, 0.1, k1x, out=g32), 8.0)
+timeit("edfdv_exp_f32", lambda: ops.edfdv_exp_f32(f32, e, None, -1.0, 1.0, 0.1, k1v, out=g32), 8.0)
+timeit("collide_f32", lambda: ops.collide_f32(f32, vd, dv, 0.1, nu_fp=nu, model=1, scheme=0, out=g32), 8.0)
 # non-power-of-two lengths (chirp-z path), same cell count as a 2048 x 2048 grid for orientation
 nb = 3456
 fb = torch.as_tensor(np.ascontiguousarray(f[:nb, :1024]), device="cuda")
