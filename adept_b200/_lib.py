@@ -72,6 +72,7 @@ SIGNATURES = {
     "adept_b200_profile": [c_i],
     "adept_b200_profile_report": [C.c_char_p, c_i],
     "adept_b200_vdfdx_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_d, c_d, c_dp, c_dp],
+    "adept_b200_vdfdx_scratch_f64": [c_dp, c_dp, c_dp, c_i, c_i, c_i, c_dp, c_d, c_d, c_dp, c_dp],
     "adept_b200_edfdv_exp_bwd_accel_f64": [c_dp, c_dp, c_i, c_i, c_i, c_dp, c_dp, c_dp, c_d, c_d, c_d, c_d, c_dp, c_dp],
     "adept_b200_moments_bwd_f64": [C.POINTER(c_dp), C.POINTER(c_d), c_i, c_i, c_i, c_dp, c_i, c_dp, c_dp],
     "adept_b200_collide_bwd_f64": [c_dp, c_dp, c_dp, c_dp, c_dp, c_i, c_i, c_i, c_dp, c_d, c_d, c_dp, c_i, c_i, c_dp],

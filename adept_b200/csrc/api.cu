@@ -503,6 +503,12 @@ int adept_b200_collide_sc_f64(const double* f_in, double* f_out, int batch, int 
                      n_out, 1.0, 1.0, (cudaStream_t)stream, sc_max_steps, sc_rtol, sc_atol);
 }
 
+int adept_b200_vdfdx_scratch_f64(const double* f_in, double* f_out, double* scratch, int batch, int nx, int nv,
+                                 const double* v, double dt, double k1x, const double* k1x_batch, void* stream) {
+  ADEPT_REQUIRE(f_in, "f_in") ADEPT_REQUIRE(f_out, "f_out") ADEPT_REQUIRE(v, "v") ADEPT_REQUIRE(scratch, "scratch")
+  return bigx_apply_f64(f_in, f_out, scratch, batch, nx, nv, v, dt, k1x_batch, k1x, nullptr, 0, (cudaStream_t)stream);
+}
+
 /* ---- vlasov-1d2v ---- */
 int adept_b200_marginal_f64(const double* f, const double* wperp, long long rows, int nvperp, double* out, void* stream) {
   ADEPT_REQUIRE(f, "f") ADEPT_REQUIRE(wperp, "wperp") ADEPT_REQUIRE(out, "out")

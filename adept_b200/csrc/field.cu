@@ -173,6 +173,8 @@ int poisson_dispatch_f64(const double* rho, const double* kmul, long long kmul_s
   const int logn = ilog2_exact(nx);
   if (logn < 0 && bluestein_supported(nx))
     return bluestein_poisson_f64(rho, kmul, kmul_stride, e, batch, nx, mode, Te, lambda_De, stream);
+  if (logn < 0 && bigx_supported(nx, 64))  // long mixed-length grids (nx = 17280 = 128 x 135, ...)
+    return bigx_poisson_f64(rho, kmul, kmul_stride, e, batch, nx, mode, Te, lambda_De, stream);
   if (logn == 12 || logn == 13) {
     PoissonArgs p = {rho, kmul, kmul_stride, e, mode, Te, lambda_De, get_twiddles(logn), 0};
     if (!p.tw) return ADEPT_ERR_CUDA;

@@ -67,6 +67,12 @@ int edfdv_spline_bwd_f64(const double* f, const double* g, int batch, int nx, in
                          cudaStream_t stream);
 int krook_bwd_f64(const double* f, const double* g, int batch, int nx, int nv, double dv, double dt, const double* nu_K,
                   const double* f_mx, double* fbar, double* nubar, cudaStream_t stream);
+// bigx.cu: x-direction spectral operators for long pencils of mixed length (nx = 2^a m, e.g. 17280 = 128 x 135)
+bool bigx_supported(int nx, int nv);
+int bigx_apply_f64(const double* in, double* out, double* scratch, int batch, int nx, int nv, const double* v, double dt,
+                   const double* k1_batch, double k1, const double2* mtab, long long mtab_stride, cudaStream_t stream);
+int bigx_poisson_f64(const double* rho, const double* kmul, long long kmul_stride, double* e, int batch, int nx,
+                     int mode, double Te, double lambda_De, cudaStream_t stream);
 int marginal_f64(const double* f, const double* w, long long rows, int np, double* out, cudaStream_t stream);
 int transpose_f64(const double* in, double* out, int batch, int n0, int n1, cudaStream_t stream);
 int abs_rfft_x_f64(const double* fin, double* fout, int batch, int nx, int nv, cudaStream_t stream);

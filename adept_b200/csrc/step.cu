@@ -91,6 +91,17 @@ struct StepCtx {
     for (int k = 0; k < s.n_species; k++) {
       const adept_b200_species& sp = s.species[k];
       have_parts[k] = false;
+      if (bigx_supported(s.nx, sp.nv) && !vdfdx_tma_supported(cur[k], dst[k], s.nx, sp.nv)) {
+        // long mixed-length pencils go through a scratch array: whichever of f_tmp / f_out is dead right now
+        double* scratch = (dst[k] == sp.f_out || cur[k] == sp.f_out) ? sp.f_tmp : sp.f_out;
+        if (!scratch || scratch == dst[k] || scratch == cur[k]) {
+          set_last_error("step: nx=%d needs species.f_tmp as the scratch array of the x-advection", s.nx);
+          return ADEPT_ERR_BAD_ARG;
+        }
+        ADEPT_TRY(bigx_apply_f64(cur[k], dst[k], scratch, s.batch, s.nx, sp.nv, sp.v, dt, s.k1x_batch, s.k1x, nullptr, 0,
+                                 st));
+        continue;
+      }
       if (want_rho && sp.rho_parts && vdfdx_tma_supported(cur[k], dst[k], s.nx, sp.nv) &&
           sp.rho_nparts >= vdfdx_tma_parts(s.batch, s.nx, sp.nv)) {
         if (s.batch > 1) {  // a single member is overwritten by every CTA of the x-advection; ensembles accumulate

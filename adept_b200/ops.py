@@ -63,10 +63,36 @@ def prepare(n: int) -> None:
     _lib.check(_lib.load().adept_b200_prepare(int(n)), "prepare")
 
 
+def is_long_mixed_nx(nx: int, nv: int) -> bool:
+    """True for the pencils adept_b200_vdfdx_scratch_f64 serves: nx > 4096, not a power of two, nx = 2^a m with a >= 6
+    and a small odd m, nv % 64 == 0 (e.g. nx = 17280 = 128 x 135)."""
+    if nx <= 4096 or nx & (nx - 1) == 0 or nv % 64:
+        return False
+    a, m = 0, nx
+    while m % 2 == 0:
+        m //= 2
+        a += 1
+    return a >= 6 and m * (1 << max(a - 8, 0)) <= 160
+
+
+_SCRATCH = {}
+
+
 def vdfdx(f, v, dt, k1x, out=None, k1x_batch=None):
     """x-advection (SpaceExponential, vlasov.py:234-251)."""
     b, nx, nv = _shape3(f)
     out = torch.empty_like(f) if out is None else out
+    if is_long_mixed_nx(nx, nv):
+        key = (str(f.device), tuple(f.shape))
+        if key not in _SCRATCH:
+            _SCRATCH.clear()  # one work array at a time
+            _SCRATCH[key] = torch.empty_like(f)
+        rc = _lib.load().adept_b200_vdfdx_scratch_f64(
+            _ptr(f, "f"), _ptr(out, "out"), _ptr(_SCRATCH[key], "scratch"), b, nx, nv, _ptr(v, "v"), float(dt),
+            float(k1x), _ptr(k1x_batch, "k1x_batch", True), _stream())
+        _lib.check(rc, "vdfdx (long pencils)")
+        _count(3)
+        return out
     rc = _lib.load().adept_b200_vdfdx_f64(
         _ptr(f, "f"), _ptr(out, "out"), b, nx, nv, _ptr(v, "v"), float(dt), float(k1x),
         _ptr(k1x_batch, "k1x_batch", True), _stream(),

@@ -215,7 +215,7 @@ class NativeStep:
             sg, sp = g["species_grids"][name], g["species_params"][name]
             f = y[name]
             s = st.species[k]
-            if self.edfdv == 1:
+            if self.edfdv == 1 or ops.is_long_mixed_nx(nx, int(f.shape[-1])):  # spline stencil / long-pencil scratch
                 s.f_tmp = self._scratch(("tmp", name), f.shape, dev).data_ptr()
             s.v = self._table(("v", name), lambda sg=sg: sg["v"], dev).data_ptr()
             s.nv, s.dv, s.k1v = int(f.shape[-1]), float(sg["dv"]), float(sg["kvr"][1])

@@ -770,3 +770,38 @@ def test_run_with_the_decks_own_save_block():
     assert saved["electron.spec"][-1].shape == (9, 25) and bool(torch.isfinite(saved["electron.spec"][-1]).all())
     assert saved["diag-fp-dfdt"][-1].shape == (32, 256)
     assert "n" in saved["fields"][-1]["electron"] and float(saved["default"][-1]["mean_n_electron"]) > 0.99
+
+
+# ------------------------------------------------------------------------------ long pencils of mixed length (bigx.cu)
+@pytest.mark.parametrize("nx,nv", [(17280, 64), (8640, 128), (6912, 64), (5760, 64), (34560, 64)])
+def test_vdfdx_long_mixed_length_matches_oracle(ops, nx, nv):
+    """nx = 2^a m beyond one SM's shared memory (configs/vlasov-1d/iaw-turbulence-big*.yaml: nx = 17280 = 128 x 135):
+    128-point FFTs, m-point DFTs + phase, inverse -- three launches through a scratch array."""
+    f, x, v, dx, dv = make_f(nx, nv, seed=nx, noise=0.05, xmax=966.0)
+    kxr = np.fft.rfftfreq(nx, d=dx) * 2 * np.pi
+    for dt in (0.25, -0.1):
+        ref = O.space_exponential(f, kxr, v, dt)
+        fd = dev(f)
+        out = host(ops.vdfdx(fd, dev(v), dt, kxr[1]))
+        assert rel_l2(out, ref) <= RTOL
+        ops.vdfdx(fd, dev(v), dt, kxr[1], out=fd)  # in place
+        assert rel_l2(host(fd), ref) <= RTOL
+
+
+@pytest.mark.parametrize("nx", [17280, 6912])
+def test_poisson_long_mixed_length_matches_oracle(ops, nx):
+    rng = np.random.default_rng(nx)
+    dx = 966.0 / nx
+    x = (np.arange(nx) + 0.5) * dx
+    kx = np.fft.fftfreq(nx, d=dx) * 2 * np.pi
+    ook = np.zeros(nx)
+    ook[1:] = 1.0 / kx[1:]
+    rho = 0.01 * np.sin(2 * np.pi * x / 966.0) + 1e-3 * rng.standard_normal(nx)
+    ref = O.poisson(rho, ook)
+    out = host(ops.poisson(dev(rho), dev(ook)))
+    assert np.max(np.abs(out - ref)) <= 1e-12 * np.max(np.abs(ref))
+    rho_b = 1.0 + rho
+    for lam in (None, 0.3):
+        ref = O.boltzmann_poisson(rho_b, kx, 0.05, lam)
+        out = host(ops.poisson(dev(rho_b), dev(kx), mode=1, Te=0.05, lambda_De=-1.0 if lam is None else lam))
+        assert np.max(np.abs(out - ref)) <= 1e-12 * np.max(np.abs(ref))

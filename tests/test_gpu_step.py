@@ -117,6 +117,15 @@ def variants():
                                     "density_components": ["species-ion-background"]}])
         d["terms"]["fokker_planck"]["is_on"] = False
         out[f"iaw-like-{nx}x256"] = d
+    d = deepcopy(out["iaw-like-64x256"])  # configs/vlasov-1d/iaw-turbulence-big-bench.yaml's x-grid: nx = 17280 = 128 x 135
+    d["grid"].update(nx=17280, nv=64, xmax=966.0)
+    d["density"]["species-ion-background"]["wavenumber"] = 2 * np.pi / 966.0
+    d["drivers"]["ex_stochastic"]["tau"] = 966.0
+    d["terms"]["species"][0]["nv"] = 64
+    out["iaw-big-bench-like-17280x64"] = d
+    d = deepcopy(d)  # the same grid with the spectral v-push and leapfrog (scratch = f_tmp allocated for the x-push)
+    d["terms"].update(edfdv="exponential", time="leapfrog")
+    out["iaw-big-leapfrog-exp-17280x64"] = d
     d = c2_deck()  # self-consistent beta (Newton on the discrete temperature) in a driven step
     d["terms"]["fokker_planck"].update(type="chang_cooper_dougherty",
                                        self_consistent_beta={"enabled": True, "max_steps": 3})
