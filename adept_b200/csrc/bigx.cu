@@ -1,5 +1,5 @@
 // x-direction spectral operators for LONG pencils whose length is not a power of two: nx = N1 * N2 with N1 = 64 / 128 /
-// 256 and N2 odd, N2 <= 160 -- e.g. nx = 17280 = 128 * 135 of configs/vlasov-1d/iaw-turbulence-big*.yaml, whose x-pencil
+// 256 and N2 <= 150 -- e.g. nx = 17280 = 128 * 135 of configs/vlasov-1d/iaw-turbulence-big*.yaml, whose x-pencil
 // (276 KB per column pair) does not fit one SM's shared memory.
 //
 // Reference semantics: out = irfft(M rfft(in, axis=x), axis=x) per column, with M the advection phase
@@ -13,9 +13,8 @@
 //       two-for-one separation of the two real columns, multiplier, recombination, inverse DFTs over k2,
 //       conjugate twiddle                                                                       Y  -> Y (in place)
 //   K3  inverse N1-point FFTs over k1 (swap . forward . swap)                                   Y  -> f_out
-// Every thread block reads and writes whole 512-byte row segments.  The direct N2-point sums cost O(N2) per point
-// instead of O(log N2): at N2 = 135 the transform is fp64-bound (about 1 ms per 17280 x 2048 advection on one B200), a
-// radix-3 / radix-5 factorisation of that stage is the known next step.
+// Every thread block reads and writes whole 512-byte row segments.  The N2-point transforms are one Cooley-Tukey level
+// N2 = P Q of direct sums (135 = 9 x 15: 24 multiply-adds per output instead of 135).
 #include <math.h>
 
 #include <mutex>
@@ -30,11 +29,13 @@ namespace {
 
 constexpr int BX_COLS = 32;   // column pairs per CTA
 constexpr int BX_MAXK = 10;   // N2 <= 16 * BX_MAXK
+constexpr int BX_MAXN2 = 150; // three [N2][32] complex arrays + the table must fit 227 KB of shared memory
 
 struct BigXArgs {
   const double* in;
   double* out;
   int N1, N2, nv;
+  int P2;          // N2 = P2 * Q2, the factor pair closest to sqrt(N2) (1 for a prime N2)
   const cplx* tw;  // Stockham tables of the N1-point transform
   const cplx* wN;  // [N1 * N2]  exp(-2 pi i j / N)
   const cplx* w2;  // [N2]       exp(-2 pi i j / N2)
@@ -94,32 +95,59 @@ __global__ void __launch_bounds__(BX_COLS * FftCfg<LOGN1>::T) bigx_k3_kernel(Big
 }
 
 // ---- K2: N2-point DFTs, spectrum update, inverse N2-point DFTs ---------------------------------------------------------
-// acc[j] = sum_n S[n][lane] W^(sign n k), k = s + 16 j
+// acc[j] = sum_n S[n][lane] W^(sign n k), k = s + 16 j, by one Cooley-Tukey level N2 = P Q (n = P a + b, k = c + Q d):
+//   T[b Q + c] = sum_a S[P a + b] W_Q^(a c),   X[k] = sum_b T[b Q + (k mod Q)] W_N2^(b k)
+// (P + Q multiply-adds per output instead of N2; P = 1 for a prime N2 is the plain sum).  T: a third [N2][32] array.
+// Every thread of the CTA must call it (two barriers).
 template <bool INVERSE>
-__device__ __forceinline__ void dft_n2(const cplx* __restrict__ S, const cplx* __restrict__ W, int N2, int lane, int s,
-                                       cplx (&acc)[BX_MAXK]) {
+__device__ __forceinline__ void dft_n2(const cplx* __restrict__ S, cplx* __restrict__ Tm, const cplx* __restrict__ W,
+                                       int N2, int P, int Q, int lane, int s, cplx (&acc)[BX_MAXK]) {
+  __syncthreads();  // T may still be read by the previous call
+  int oidx[BX_MAXK], ostep[BX_MAXK], obase[BX_MAXK];
 #pragma unroll
-  for (int j = 0; j < BX_MAXK; j++) acc[j] = cmake(0.0, 0.0);
-  int idx0 = 0, step = 0;  // idx0 = n s mod N2, step = 16 n mod N2
-  const int s16 = 16 % N2;
-  for (int n = 0; n < N2; n++) {
-    const cplx x = S[n * BX_COLS + lane];
-    int idx = idx0;
+  for (int j = 0; j < BX_MAXK; j++) {
+    const int o = s + 16 * j;          // stage-1 output (b, c) = (o / Q, o % Q)
+    const int b = o / Q, c = o - b * Q;
+    acc[j] = cmake(0.0, 0.0);
+    oidx[j] = 0;
+    ostep[j] = (P * c) % N2;           // W_Q^(a c) = W_N2^(P a c)
+    obase[j] = b;
+  }
+  for (int a = 0; a < Q; a++) {
 #pragma unroll
     for (int j = 0; j < BX_MAXK; j++) {
       if (s + 16 * j < N2) {
+        const cplx x = S[(P * a + obase[j]) * BX_COLS + lane];
+        cplx w = W[oidx[j]];
+        if (INVERSE) w.y = -w.y;
+        acc[j].x = fma(x.x, w.x, fma(-x.y, w.y, acc[j].x));
+        acc[j].y = fma(x.x, w.y, fma(x.y, w.x, acc[j].y));
+        oidx[j] += ostep[j];
+        if (oidx[j] >= N2) oidx[j] -= N2;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < BX_MAXK; j++)
+    if (s + 16 * j < N2) Tm[(s + 16 * j) * BX_COLS + lane] = acc[j];
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < BX_MAXK; j++) {
+    const int k = s + 16 * j;
+    acc[j] = cmake(0.0, 0.0);
+    if (k < N2) {
+      const int c = k % Q;
+      int idx = 0;
+      for (int b = 0; b < P; b++) {
+        const cplx x = Tm[(b * Q + c) * BX_COLS + lane];
         cplx w = W[idx];
         if (INVERSE) w.y = -w.y;
         acc[j].x = fma(x.x, w.x, fma(-x.y, w.y, acc[j].x));
         acc[j].y = fma(x.x, w.y, fma(x.y, w.x, acc[j].y));
+        idx += k;
+        if (idx >= N2) idx -= N2;
       }
-      idx += step;
-      if (idx >= N2) idx -= N2;
     }
-    idx0 += s;
-    if (idx0 >= N2) idx0 -= N2;
-    step += s16;
-    if (step >= N2) step -= N2;
   }
 }
 
@@ -128,7 +156,9 @@ __global__ void __launch_bounds__(512, 1) bigx_k2_kernel(BigXArgs p) {
   const int N1 = p.N1, N2 = p.N2, N = N1 * N2;
   cplx* SA = reinterpret_cast<cplx*>(smem_raw);
   cplx* SB = SA + (size_t)N2 * BX_COLS;
-  cplx* W = SB + (size_t)N2 * BX_COLS;
+  cplx* ST = SB + (size_t)N2 * BX_COLS;
+  cplx* W = ST + (size_t)N2 * BX_COLS;
+  const int P = p.P2, Q = N2 / P;
   const int lane = threadIdx.x & 31, s = threadIdx.x >> 5;
   const int ka = blockIdx.y;              // group A: k = ka + N1 k2
   const int kb = (N1 - ka) % N1;          // group B holds the partners N - k
@@ -144,13 +174,13 @@ __global__ void __launch_bounds__(512, 1) bigx_k2_kernel(BigXArgs p) {
   __syncthreads();
 
   cplx acc[BX_MAXK];
-  dft_n2<false>(SA, W, N2, lane, s, acc);
+  dft_n2<false>(SA, ST, W, N2, P, Q, lane, s, acc);
   __syncthreads();
 #pragma unroll
   for (int j = 0; j < BX_MAXK; j++)
     if (s + 16 * j < N2) SA[(s + 16 * j) * BX_COLS + lane] = acc[j];
   if (!self) {
-    dft_n2<false>(SB, W, N2, lane, s, acc);
+    dft_n2<false>(SB, ST, W, N2, P, Q, lane, s, acc);
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < BX_MAXK; j++)
@@ -206,7 +236,7 @@ __global__ void __launch_bounds__(512, 1) bigx_k2_kernel(BigXArgs p) {
   __syncthreads();
 
   // ---- inverse N2-point DFTs, conjugate twiddle, write back -----------------------------------------------------------
-  dft_n2<true>(SA, W, N2, lane, s, acc);
+  dft_n2<true>(SA, ST, W, N2, P, Q, lane, s, acc);
 #pragma unroll
   for (int j = 0; j < BX_MAXK; j++) {
     const int n = s + 16 * j;
@@ -217,7 +247,7 @@ __global__ void __launch_bounds__(512, 1) bigx_k2_kernel(BigXArgs p) {
     }
   }
   if (!self) {
-    dft_n2<true>(SB, W, N2, lane, s, acc);
+    dft_n2<true>(SB, ST, W, N2, P, Q, lane, s, acc);
 #pragma unroll
     for (int j = 0; j < BX_MAXK; j++) {
       const int n = s + 16 * j;
@@ -283,7 +313,7 @@ bool factor(int nx, int* logn1, int* n2) {
   while ((m & 1) == 0) m >>= 1, a++;
   if (m == 1 || a < 6) return false;  // powers of two and short pencils have their own kernels
   while (a > 8) m <<= 1, a--;         // fold surplus factors of two into N2
-  if (m > 16 * BX_MAXK) return false;
+  if (m > BX_MAXN2) return false;
   *logn1 = a, *n2 = m;
   return true;
 }
@@ -323,7 +353,7 @@ int bigx_apply_f64(const double* in, double* out, double* scratch, int batch, in
   int logn1 = 0, n2 = 0;
   if (batch < 1 || !factor(nx, &logn1, &n2) || nv % (2 * BX_COLS)) {
     set_last_error("bigx: unsupported batch=%d nx=%d nv=%d (nx = 2^a m, 6 <= a, m odd, m 2^max(a-8,0) <= %d; nv %% %d == 0)",
-                   batch, nx, nv, 16 * BX_MAXK, 2 * BX_COLS);
+                   batch, nx, nv, BX_MAXN2, 2 * BX_COLS);
     return ADEPT_ERR_UNSUPPORTED;
   }
   if (!scratch || scratch == in || scratch == out || (!mtab && !v)) {
@@ -336,6 +366,9 @@ int bigx_apply_f64(const double* in, double* out, double* scratch, int batch, in
   }
   BigXArgs p = {};
   p.N1 = 1 << logn1, p.N2 = n2, p.nv = nv;
+  p.P2 = 1;
+  for (int d = 2; d * d <= n2; d++)
+    if (n2 % d == 0) p.P2 = d;
   p.tw = get_twiddles(logn1);
   if (!p.tw) return ADEPT_ERR_CUDA;
   const int rc = get_tables(p.N1, p.N2, &p.wN, &p.w2);
@@ -348,7 +381,11 @@ int bigx_apply_f64(const double* in, double* out, double* scratch, int batch, in
   if (r != ADEPT_OK) return r;
   // K2: scratch in place
   {
-    const size_t smem = ((size_t)2 * n2 * BX_COLS + n2) * sizeof(cplx);
+    const size_t smem = ((size_t)3 * n2 * BX_COLS + n2) * sizeof(cplx);
+    if (smem > 227 * 1024) {
+      set_last_error("bigx: N2=%d does not fit shared memory", n2);
+      return ADEPT_ERR_UNSUPPORTED;
+    }
     static size_t configured[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);

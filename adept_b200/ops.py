@@ -72,7 +72,7 @@ def is_long_mixed_nx(nx: int, nv: int) -> bool:
     while m % 2 == 0:
         m //= 2
         a += 1
-    return a >= 6 and m * (1 << max(a - 8, 0)) <= 160
+    return a >= 6 and m * (1 << max(a - 8, 0)) <= 150
 
 
 _SCRATCH = {}

@@ -66,7 +66,7 @@ int adept_b200_prepare(int n);
 int adept_b200_vdfdx_f64(const double* f_in, double* f_out, int batch, int nx, int nv, const double* v, double dt,
                          double k1x, const double* k1x_batch, void* stream);
 
-/* x-advection of LONG pencils of mixed length, nx = 2^a m with 6 <= a and m odd (m 2^max(a - 8, 0) <= 160), nv % 64 == 0
+/* x-advection of LONG pencils of mixed length, nx = 2^a m with 6 <= a and m odd (m 2^max(a - 8, 0) <= 150), nv % 64 == 0
  * -- e.g. nx = 17280 = 128 x 135 of configs/vlasov-1d/iaw-turbulence-big*.yaml, whose pencils do not fit one SM: three
  * launches (128-point FFTs, 135-point DFTs + phase, inverse FFTs) through `scratch`, an array of the size of f that
  * aliases neither f_in nor f_out (f_in == f_out is allowed).  adept_b200_step_f64 takes this path on its own and uses
