@@ -24,6 +24,7 @@
 #include "internal.h"
 #include "push_core.cuh"
 #include "tma.cuh"
+#include "tmem.cuh"
 
 namespace adept {
 
@@ -42,7 +43,11 @@ struct TmaPushArgs {
   FieldTail ft;         // used by the FIELD instantiation only
 };
 
-template <int LOGN>
+// VAR (nx = 4096 only) divides the 80 KB beside the exchange buffer between NEARLY boxes of the NEXT tile that land
+// early (their TMA loads are issued at the start of the current tile instead of inside its last pass, where the load of
+// 4096 box rows at ~0.5 rows/clk is exposed) and NSTAGE staged output chunks: 0 = (0, 10), 1 = (10, 0), 2 = (5, 5),
+// 3 = (7, 3).
+template <int LOGN, int VAR = 0>
 struct TmaCfg {
   using C = FftCfg<LOGN>;
   using PC = PhaseCfg<LOGN>;
@@ -52,23 +57,33 @@ struct TmaCfg {
   static constexpr int NBOX = N / BOX_ROWS;
   static constexpr size_t BUF_BYTES = (size_t)2 * C::BUF * sizeof(cplx);  // two interleaved padded buffers
   static constexpr size_t PH_BYTES = (size_t)2 * 2 * PC::PER_SEQ * sizeof(cplx);
-  static constexpr size_t ACC_BYTES = (size_t)N * sizeof(double);
+  // nx = 4096: the per-CTA row sums live in tensor memory (16 doubles = 32 columns per thread, tmem.cuh) instead of a
+  // 32 KB shared-memory accumulator: no shuffle + read-modify-write per row, and the freed shared memory stages four
+  // more output chunks for TMA stores (the kernel has no matrix product, so the 256 KB of TMEM are otherwise idle)
+  static constexpr bool TMEM_ACC = (LOGN == 12);
+  static constexpr int TMEM_COLS = 128;  // 4 warps share a lane quadrant, 32 columns each
+  static constexpr size_t ACC_BYTES = TMEM_ACC ? 0 : (size_t)N * sizeof(double);
   // Output chunks (one TMA box {4, 256} = 8 KB each) that leave through a shared-memory staging area and TMA tensor
   // stores instead of direct 16-byte stores.  A warp's direct store touches 16 lines (~2 L1 cycles each), so the store
   // phase of a 4096-row tile costs ~8200 LSU cycles; the TMA unit drains a box in ~512 cycles on its own.  The staging
   // area cannot hold a whole tile (227 KB per SM), so the two paths share the tile: NSTAGE chunks by TMA, the rest
   // direct, both draining concurrently.  Only where the CTA is alone on its SM anyway (nx = 4096).
-  static constexpr int NSTAGE = (LOGN == 12) ? 6 : 0;  // measured: 4 -> 141.2 us, 6 -> 137.9 us, 7 -> 139.5 us (x-push + field tail)
+  // (with the shared-memory accumulator, r01: 4 -> 141.2 us, 6 -> 137.9 us, 7 -> 139.5 us for x-push + field tail: L1
+  // shrinks with the staging area; 10 chunks beside the TMEM accumulator occupy the same 223 KB as 6 did before)
+  static constexpr int NEARLY = (LOGN != 12) ? 0 : (VAR == 1 ? 10 : (VAR == 2 ? 5 : (VAR == 3 ? 7 : 0)));
+  static constexpr int NSTAGE = (LOGN == 12) ? 10 - NEARLY : 0;
+  static constexpr size_t BOX_BYTES = (size_t)BOX_ROWS * 4 * sizeof(double);
   static constexpr size_t BAR_OFF = BUF_BYTES + PH_BYTES + ACC_BYTES;
-  static constexpr size_t STAGE_OFF = (BAR_OFF + 16 + 127) / 128 * 128;
-  static constexpr size_t STAGE_BYTES = (size_t)NSTAGE * BOX_ROWS * 4 * sizeof(double);
-  static constexpr size_t SMEM = NSTAGE ? STAGE_OFF + STAGE_BYTES : BAR_OFF + 16;
+  static constexpr size_t EARLY_OFF = (BAR_OFF + 32 + 127) / 128 * 128;  // two mbarriers + the TMEM slot in front
+  static constexpr size_t STAGE_OFF = EARLY_OFF + (size_t)NEARLY * BOX_BYTES;
+  static constexpr size_t STAGE_BYTES = (size_t)NSTAGE * BOX_BYTES;
+  static constexpr size_t SMEM = (NSTAGE + NEARLY) ? STAGE_OFF + STAGE_BYTES : BAR_OFF + 32;
 };
 
-template <int LOGN, bool FIELD = false>
+template <int LOGN, bool FIELD = false, int VAR = 0>
 __global__ void __launch_bounds__(TmaCfg<LOGN>::THREADS, 1)
     vdfdx_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ TmaPushArgs p) {
-  using K = TmaCfg<LOGN>;
+  using K = TmaCfg<LOGN, VAR>;
   using C = FftCfg<LOGN>;
   using PC = PhaseCfg<LOGN>;
   constexpr int N = C::N, E = C::E, T = C::T;
@@ -86,26 +101,71 @@ __global__ void __launch_bounds__(TmaCfg<LOGN>::THREADS, 1)
   cplx* ph = ph_all + g * 2 * PC::PER_SEQ;
   const int tiles_per_member = p.nv >> 2;
 
+  uint64_t* bar_early = bar + 1;
+  const cplx* early = reinterpret_cast<const cplx*>(smem_raw + K::EARLY_OFF);  // boxes 0 .. NEARLY-1 of the tile: [row][2 cplx]
   if (tid == 0) {
     mbar_init(bar, 1);
+    mbar_init(bar_early, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (p.partial) {
-    for (int i = tid; i < N; i += K::THREADS) rho_acc[i] = 0.0;
+  uint32_t racc_addr = 0, tmem_base = 0;
+  if constexpr (K::TMEM_ACC) {
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+    if (tid < 32) tmem_alloc(tmem_slot, K::TMEM_COLS);
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
+    tmem_base = *tmem_slot;
+    racc_addr = tmem_addr(tmem_base, tid >> 5, 32 * (tid >> 7));
+    const double zeros[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    tmem_st8(racc_addr, zeros);
+    tmem_st8(racc_addr + 16, zeros);
+    tmem_wait_st();
+  } else {
+    if (p.partial) {
+      for (int i = tid; i < N; i += K::THREADS) rho_acc[i] = 0.0;
+    }
+    __syncthreads();
   }
-  __syncthreads();
 
-  auto issue_load = [&](int tl) {
+  auto issue_load = [&](int tl) {  // the boxes that land in the exchange buffer (all of them when NEARLY == 0)
     const int b = tl / tiles_per_member, cg = tl - b * tiles_per_member;
-    mbar_expect_tx(bar, (uint32_t)(N * 4 * sizeof(double)));
+    mbar_expect_tx(bar, (uint32_t)((K::NBOX - K::NEARLY) * K::BOX_BYTES));
 #pragma unroll 1
-    for (int bx = 0; bx < K::NBOX; bx++)
+    for (int bx = K::NEARLY; bx < K::NBOX; bx++)
       tma_load_2d(reinterpret_cast<double*>(tile) + (size_t)bx * K::BOX_ROWS * 4, &in_map, bar, cg * 4,
                   b * N + bx * K::BOX_ROWS);
   };
+  auto issue_early = [&](int tl) {  // boxes 0 .. NEARLY-1 into their own landing zone
+    if constexpr (K::NEARLY > 0) {
+      const int b = tl / tiles_per_member, cg = tl - b * tiles_per_member;
+      mbar_expect_tx(bar_early, (uint32_t)(K::NEARLY * K::BOX_BYTES));
+#pragma unroll 1
+      for (int bx = 0; bx < K::NEARLY; bx++)
+        tma_load_2d(reinterpret_cast<double*>(smem_raw + K::EARLY_OFF) + (size_t)bx * K::BOX_ROWS * 4, &in_map, bar_early,
+                    cg * 4, b * N + bx * K::BOX_ROWS);
+    }
+  };
   auto flush_rho = [&](int b) {  // this CTA owns row blockIdx.x of `partial`: plain read-modify-write
-    __syncthreads();
     double* dst = p.partial + ((size_t)blockIdx.x * p.batch + b) * N;
+    if constexpr (K::TMEM_ACC) {  // rows t + T m of both lanes of a pair: sum across the pair, the even lane writes
+      const double zeros[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        double r[8];
+        tmem_ld8(racc_addr + 16 * h, r);
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+          const double s = r[m] + __shfl_xor_sync(0xffffffffu, r[m], 1);
+          double* d = dst + t + T * (8 * h + m);
+          if (g == 0) *d = (p.batch == 1) ? s : *d + s;
+        }
+        tmem_st8(racc_addr + 16 * h, zeros);
+      }
+      tmem_wait_st();
+      return;
+    }
+    __syncthreads();
     for (int i = tid; i < N; i += K::THREADS) {
       // a single member is visited once by every CTA: plain store, no zero-initialisation needed
       dst[i] = (p.batch == 1) ? rho_acc[i] : dst[i] + rho_acc[i];
@@ -115,7 +175,7 @@ __global__ void __launch_bounds__(TmaCfg<LOGN>::THREADS, 1)
   };
 
   int tl = blockIdx.x;
-  if (tid == 0 && tl < p.ntiles) issue_load(tl);
+  if (tid == 0 && tl < p.ntiles) issue_early(tl), issue_load(tl);
   uint32_t parity = 0;
   int cur_b = -1;
   for (; tl < p.ntiles; tl += gridDim.x) {
@@ -131,12 +191,19 @@ __global__ void __launch_bounds__(TmaCfg<LOGN>::THREADS, 1)
       const double alpha_b = k1 * (p.v[col + 1] * p.dt);
       phase_table_fill<LOGN>(ph, alpha_a, alpha_b, t, T);
     }
+    if constexpr (K::NEARLY > 0) mbar_wait(bar_early, parity);
     mbar_wait(bar, parity);
     parity ^= 1;
 
     cplx x[E];
 #pragma unroll
-    for (int m = 0; m < E; m++) x[m] = buf[(t + T * m) * 2];  // unpadded landing layout
+    for (int m = 0; m < E; m++)  // unpadded landing layout; chunk m = box m (T == BOX_ROWS when NEARLY > 0)
+      x[m] = (m < K::NEARLY) ? early[(t + T * m) * 2 + g] : buf[(t + T * m) * 2];
+    if constexpr (K::NEARLY > 0) {  // the early zone has been read by everybody: the next tile's first boxes may land
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (tid == 0 && tl + (int)gridDim.x < p.ntiles) issue_early(tl + gridDim.x);
+    }
     fft_forward<LOGN, 2>(x, buf, p.tw, t, p.zero);
     half_spectrum_update<LOGN, 2>(x, buf, ph, t, p.filt);
     // the exchange buffer is dead once every thread has read its inputs of the last inverse pass: the next tile's TMA
@@ -173,10 +240,25 @@ __global__ void __launch_bounds__(TmaCfg<LOGN>::THREADS, 1)
     for (int m = 0; m < E; m++) {
       const size_t e = t + T * m;
       if (m >= K::NSTAGE) *reinterpret_cast<double2*>(dst + e * p.nv) = make_double2(x[m].y, x[m].x);
-      if (want_rho) {
-        double s = x[m].y + x[m].x;
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        if (g == 0) rho_acc[t + T * m] += s;  // row t + T m is owned by this lane pair
+      if constexpr (!K::TMEM_ACC) {
+        if (want_rho) {
+          double s = x[m].y + x[m].x;
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          if (g == 0) rho_acc[t + T * m] += s;  // row t + T m is owned by this lane pair
+        }
+      }
+    }
+    if constexpr (K::TMEM_ACC) {
+      if (want_rho) {  // this thread's share of rows t + T m: accumulated in its own TMEM columns
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          double r[8];
+          tmem_ld8(racc_addr + 16 * h, r);
+#pragma unroll
+          for (int m = 0; m < 8; m++) r[m] += x[8 * h + m].y + x[8 * h + m].x;
+          tmem_st8(racc_addr + 16 * h, r);
+        }
+        tmem_wait_st();
       }
     }
   }
@@ -188,8 +270,17 @@ __global__ void __launch_bounds__(TmaCfg<LOGN>::THREADS, 1)
   if constexpr (FIELD) {
     // ---- field solve in the tail (batch == 1, one species): field_tail.cuh; the exchange buffer and the row-sum
     // accumulator are dead after the last flush and serve as its scratch
-    field_tail_solve<N, K::THREADS>(p.ft, p.partial, reinterpret_cast<double*>(tile), rho_acc);
+    // reduction scratch of the tail: the row-sum accumulator where it lives in shared memory, else the part of the
+    // (dead) exchange buffer behind the tail's rho | green | partial-output arrays (3 N + 256 doubles)
+    double* tail_red = K::TMEM_ACC ? reinterpret_cast<double*>(tile) + 3 * N + 256 : rho_acc;
+    static_assert(!K::TMEM_ACC || (3 * N + 256 + (K::THREADS / 32) * 32) * sizeof(double) <= K::BUF_BYTES, "tail scratch");
+    field_tail_solve<N, K::THREADS>(p.ft, p.partial, reinterpret_cast<double*>(tile), tail_red);
     if (K::NSTAGE > 0 && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  if constexpr (K::TMEM_ACC) {
+    tmem_fence_before_sync();
+    __syncthreads();
+    if (tid < 32) tmem_dealloc(tmem_base, K::TMEM_COLS);
   }
 }
 
@@ -260,13 +351,13 @@ static int tma_ctas(int ntiles) {
   return grid < ntiles ? grid : ntiles;
 }
 
-template <int LOGN, bool FIELD = false>
+template <int LOGN, bool FIELD = false, int VAR = 0>
 static int launch_tma(const CUtensorMap& map, const TmaPushArgs& p, int grid, cudaStream_t stream) {
-  using K = TmaCfg<LOGN>;
+  using K = TmaCfg<LOGN, VAR>;
   static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
-  auto kern = vdfdx_tma_kernel<LOGN, FIELD>;
+  auto kern = vdfdx_tma_kernel<LOGN, FIELD, VAR>;
   if (dev < 64 && !configured[dev]) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
     if (err != cudaSuccess) {
@@ -291,6 +382,26 @@ static int launch_tma(const CUtensorMap& map, const TmaPushArgs& p, int grid, cu
   }
   kern<<<grid, K::THREADS, K::SMEM, stream>>>(map, p);
   return check_launch("vdfdx_tma_kernel");
+}
+
+// ADEPT_B200_XVAR = 0 .. 3 selects the early-landing / staging split of the nx = 4096 kernel (TmaCfg) for A/B timing
+static int x_variant() {
+  static int var = -1;
+  if (var < 0) {
+    const char* e = getenv("ADEPT_B200_XVAR");
+    var = e ? atoi(e) : 1;  // measured (r02, x-push + field tail): 0 -> 136.4 us, 1 -> 129.9, 2 -> 132.9, 3 -> 133.2
+    if (var < 0 || var > 3) var = 1;
+  }
+  return var;
+}
+template <bool FIELD>
+static int launch_tma12(const CUtensorMap& map, const TmaPushArgs& p, int grid, cudaStream_t stream) {
+  switch (x_variant()) {
+    case 1: return launch_tma<12, FIELD, 1>(map, p, grid, stream);
+    case 2: return launch_tma<12, FIELD, 2>(map, p, grid, stream);
+    case 3: return launch_tma<12, FIELD, 3>(map, p, grid, stream);
+    default: return launch_tma<12, FIELD, 0>(map, p, grid, stream);
+  }
 }
 
 static int ilog2_exact_(int n) {
@@ -405,7 +516,7 @@ int vdfdx_tma_f64(const double* fin, double* fout, int batch, int nx, int nv, co
     switch (logn) {
       case 10: return launch_tma<10, true>(map, p, grid, stream);
       case 11: return launch_tma<11, true>(map, p, grid, stream);
-      default: return launch_tma<12, true>(map, p, grid, stream);
+      default: return launch_tma12<true>(map, p, grid, stream);
     }
   }
   switch (logn) {
@@ -413,7 +524,7 @@ int vdfdx_tma_f64(const double* fin, double* fout, int batch, int nx, int nv, co
     case 9: return launch_tma<9>(map, p, grid, stream);
     case 10: return launch_tma<10>(map, p, grid, stream);
     case 11: return launch_tma<11>(map, p, grid, stream);
-    case 12: return launch_tma<12>(map, p, grid, stream);
+    case 12: return launch_tma12<false>(map, p, grid, stream);
     default:
       set_last_error("vdfdx(tma): unsupported nx=%d", nx);
       return ADEPT_ERR_UNSUPPORTED;

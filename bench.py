@@ -444,6 +444,37 @@ def run_single_gpu_extras(nx, nv, peak):
                                    "frac_of_48B_roofline": 48.0 * cells / sec / 1e9 / peak}
     del ens
     torch.cuda.empty_cache()
+    # the one deck the reference publishes a number for (configs/vlasov-1d/iaw-turbulence-big-bench.yaml: nx = 17280,
+    # nv = 2048, sixth-order, cubic-spline, Boltzmann electrons, stochastic forcing; "~45 ms/step ... on 4x A100-40GB",
+    # configs/vlasov-1d/run-iaw-big.sbatch:5-6), on this one GPU
+    sys.path.insert(0, str(ROOT / "tools"))
+    from bigbench_probe import deck as big_deck
+
+    for tkind, nst in (("sixth", 5), ("leapfrog", 10)):
+        sim = Vlasov1D(big_deck(tkind))
+        sec = _time_steps(sim.step, nst, warm=2)
+        finite = bool(torch.isfinite(sim.state["ion"]).all())
+        out[f"iaw_big_bench_17280x2048_{tkind}"] = {
+            "ms_per_step": sec * 1e3, "value": 17280 * 2048 / sec, "unit": UNIT, "finite": finite,
+            "reference_published_ms_per_step": 45.0 if tkind == "sixth" else None,
+            "reference_hardware": "4 x A100-40GB (run-iaw-big.sbatch:5-6)" if tkind == "sixth" else None}
+        del sim
+        torch.cuda.empty_cache()
+    # single-precision operators (explicit extra; 8 B/cell per operator application)
+    from adept_b200 import ops as _ops
+
+    f32 = torch.rand((nx, nv), dtype=torch.float32, device="cuda") + 0.5
+    g32 = torch.empty_like(f32)
+    vv = torch.linspace(-6.4, 6.4, nv, dtype=torch.float64, device="cuda")
+    ee = torch.full((nx,), 1e-2, dtype=torch.float64, device="cuda")
+    nu = torch.full((nx,), 1e-5, dtype=torch.float64, device="cuda")
+    f32_ops = {}
+    for nm, fn in (("vdfdx_f32", lambda: _ops.vdfdx_f32(f32, vv, 0.1, 0.3, out=g32)),
+                   ("edfdv_exp_f32", lambda: _ops.edfdv_exp_f32(f32, ee, None, -1.0, 1.0, 0.1, 0.49, out=g32)),
+                   ("collide_f32", lambda: _ops.collide_f32(f32, vv, 12.8 / nv, 0.1, nu_fp=nu, out=g32))):
+        sec = _time_steps(fn, 10, warm=3)
+        f32_ops[nm] = {"us": sec * 1e6, "frac_of_8B_roofline": 8.0 * nx * nv / sec / 1e9 / peak}
+    out["f32_operators_4096x4096"] = f32_ops
     return out
 
 
