@@ -263,31 +263,63 @@ int reduce_parts_f64(const double* parts, int nparts, long long n, double scale_
 // ---- in-loop save moments (storage.py:119-162, 286-327) -----------------------------------------------------------
 // one warp per row of the (optionally time-interpolated) distribution f = f0 + w (f1 - f0):
 //   out[k, row] = dv * sum_j g_k(f_j, v_j),  g = { f, f v, f v^2, f v^3, -|f| log|f|, f^2 }
+// SPLIT warps share a row (each takes a contiguous part of it): the logarithm makes the pass instruction-bound, and
+// 4096 rows alone fill less than half of the warp slots of 148 SMs
+template <int SPLIT>
 __global__ void __launch_bounds__(256) save_moments_kernel(const double* __restrict__ f0, const double* __restrict__ f1,
                                                            double w, const double* __restrict__ v, long long rows,
                                                            int nv, double dv, double* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const double* a = f0 + row * nv;
-  const double* b = f1 ? f1 + row * nv : nullptr;
+  __shared__ double part[8][6];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long row = (long long)blockIdx.x * (8 / SPLIT) + wid / SPLIT;
+  const int q = wid % SPLIT;
+  const bool live = row < rows;
+  const int len = nv / SPLIT;  // the launcher picks SPLIT so that this is a multiple of 4
+  const double* a = f0 + (live ? row : 0) * nv + (size_t)q * len;
+  const double* b = f1 ? f1 + (live ? row : 0) * nv + (size_t)q * len : nullptr;
+  const double* vq = v + (size_t)q * len;
   double s[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  for (int j = lane; j < nv; j += 32) {
-    double x = a[j];
-    if (b) x = x + w * (b[j] - x);  // diffrax's linear dense output between y0 and y1 (adept/_base_.py:40)
-    const double vv = __ldg(v + j);
+  auto add = [&](double x, double y, double vv, double (&acc)[6]) {
+    if (b) x = x + w * (y - x);  // diffrax's linear dense output between y0 and y1 (adept/_base_.py:40)
     const double ax = fabs(x);
-    s[0] += x;
-    s[1] += x * vv;
-    s[2] += x * (vv * vv);
-    s[3] += x * (vv * vv * vv);
-    s[4] += -log(ax) * ax;
-    s[5] += x * x;
+    acc[0] += x;
+    acc[1] += x * vv;
+    acc[2] += x * (vv * vv);
+    acc[3] += x * (vv * vv * vv);
+    acc[4] += -log(ax) * ax;
+    acc[5] += x * x;
+  };
+  if (live) {
+    int j0 = 0;
+    if ((len & 1) == 0 && ((reinterpret_cast<uintptr_t>(a) | (b ? reinterpret_cast<uintptr_t>(b) : 0) |
+                            reinterpret_cast<uintptr_t>(vq)) & 15) == 0) {
+      double s1[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      const double2* a2 = reinterpret_cast<const double2*>(a);
+      const double2* b2 = reinterpret_cast<const double2*>(b);
+      const double2* v2 = reinterpret_cast<const double2*>(vq);
+      for (int i = lane; i < (len >> 1); i += 32) {
+        const double2 xa = a2[i], va = __ldg(v2 + i);
+        const double2 ya = b ? b2[i] : make_double2(0.0, 0.0);
+        add(xa.x, ya.x, va.x, s);
+        add(xa.y, ya.y, va.y, s1);
+      }
+#pragma unroll
+      for (int k = 0; k < 6; k++) s[k] += s1[k];
+      j0 = len;
+    }
+    for (int j = j0 + lane; j < len; j += 32) add(a[j], b ? b[j] : 0.0, __ldg(vq + j), s);
   }
 #pragma unroll
   for (int k = 0; k < 6; k++) {
     const double t = warp_sum(s[k]);
-    if (lane == 0) out[(long long)k * rows + row] = t * dv;
+    if (lane == 0) part[wid][k] = t;
+  }
+  __syncthreads();
+  if (live && q == 0 && lane < 6) {
+    double t = 0.0;
+#pragma unroll
+    for (int u = 0; u < SPLIT; u++) t += part[wid + u][lane];
+    out[(long long)lane * rows + row] = t * dv;
   }
 }
 
@@ -299,7 +331,10 @@ int save_moments_f64(const double* f0, const double* f1, double w, int batch, in
   }
   const long long rows = (long long)batch * nx;
   ProfileScope prof("save_moments", stream);
-  save_moments_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(f0, f1, w, v, rows, nv, dv, out);
+  if (nv % 16 == 0 && nv >= 2048)
+    save_moments_kernel<4><<<(unsigned)((rows + 1) / 2), 256, 0, stream>>>(f0, f1, w, v, rows, nv, dv, out);
+  else
+    save_moments_kernel<1><<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(f0, f1, w, v, rows, nv, dv, out);
   return check_launch("save_moments_kernel");
 }
 

@@ -66,6 +66,9 @@ timeit("vdfdx_rho(tma)", lambda: ops.vdfdx_rho(fd, vd, 0.1, k1x, parts, out=gd))
 timeit("vpush_collide", lambda: ops.vpush_collide(fd, e, None, -1.0, 1.0, 0.1, k1v, vd, dv, nu, model=1, out=gd), 32.0)
 nu_cc = nu
 timeit("vpush_collide_cc", lambda: ops.vpush_collide(fd, e, None, -1.0, 1.0, 0.1, k1v, vd, dv, nu_cc, model=1, out=gd, scheme=1), 32.0)
+mom6 = torch.empty((6, nx), dtype=torch.float64, device="cuda")
+timeit("save_moments", lambda: ops.save_moments(fd, vd, dv, out=mom6), 8.0)
+timeit("save_mom_interp", lambda: ops.save_moments(fd, vd, dv, gd, 0.3, out=mom6), 16.0)
 # single precision (8 B/cell per operator application)
 f32, g32 = fd.float(), torch.empty_like(fd, dtype=torch.float32)
 timeit("vdfdx_f32", lambda: ops.vdfdx_f32(f32, vd, 0.1, k1x, out=g32), 8.0)
