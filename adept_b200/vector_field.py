@@ -430,6 +430,15 @@ class VlasovMaxwell:
     def _dev(self, arr):
         return torch.as_tensor(np.ascontiguousarray(arr, dtype=np.float64), device=self.device)
 
+    def _check_a_live(self, y):
+        """Whether the wave equation has to run: an Ey driver, or a nonzero a / prev_a.  The answer is cached only while
+        the caller feeds back the very tensors the previous step returned; a state that comes from elsewhere (restart,
+        another trajectory through the same object) is inspected again."""
+        seen = getattr(self, "_a_seen", None)
+        if self._a_live is None or seen is None or y["a"] is not seen[0] or y["prev_a"] is not seen[1]:
+            self._a_live = self.has_ey or bool(torch.any(y["a"] != 0)) or bool(torch.any(y["prev_a"] != 0))
+            self._a_seen = (y["a"], y["prev_a"])
+
     def total_dex(self, t, args=None):
         return self.ex_driver(t, args)
 
@@ -471,9 +480,10 @@ class VlasovMaxwell:
         if self.native is not None and (args is None or "dex" not in args):
             # With no Ey driver and a == prev_a == 0 the wave update returns exactly 0 whatever the density is
             # (field.py:149-153), so the two density reductions and the wave kernel are skipped.  Checked once.
-            if self._a_live is None:
-                self._a_live = self.has_ey or bool(torch.any(y["a"] != 0)) or bool(torch.any(y["prev_a"] != 0))
-            return self.native(t, y, self._a_live)
+            self._check_a_live(y)
+            out = self.native(t, y, self._a_live)
+            self._a_seen = (out["a"], out["prev_a"])
+            return out
         dt_array = self.vpfp.vlasov_poisson.dt_array
         n_dex = 1 if self.vpfp.dex_save == 0 else len(dt_array)  # leapfrog only ever reads dex[0]
         if args is not None and "dex" in args:
@@ -492,8 +502,7 @@ class VlasovMaxwell:
 
         # With no Ey driver and a == prev_a == 0 the wave update returns exactly 0 whatever the density is
         # (field.py:149-153), so the two density reductions and the wave kernel are skipped.  Checked once.
-        if self._a_live is None:
-            self._a_live = self.has_ey or bool(torch.any(y["a"] != 0)) or bool(torch.any(y["prev_a"] != 0))
+        self._check_a_live(y)
         need_wave = self._a_live
         if not need_wave:
             e, f_new, diags = self.vpfp(f_dict=f_dict, a=y["a"], prev_ex=y["e"], dex_array=dex, nu_fp=nu_fp,
@@ -501,6 +510,7 @@ class VlasovMaxwell:
             result = {"a": y["a"], "prev_a": y["a"], "da": djy, "de": dex[self.vpfp.dex_save], "e": e}
             result.update(f_new)
             result.update(diags)
+            self._a_seen = (result["a"], result["prev_a"])
             return result
         ne_n = self.compute_electron_charge_density(f_dict) if need_wave else None
         e, f_new, diags = self.vpfp(f_dict=f_dict, a=y["a"], prev_ex=y["e"], dex_array=dex, nu_fp=nu_fp, nu_K=nu_K)
@@ -510,4 +520,5 @@ class VlasovMaxwell:
         result = {"a": a["a"], "prev_a": a["prev_a"], "da": djy, "de": dex[self.vpfp.dex_save], "e": e}
         result.update(f_new)
         result.update(diags)
+        self._a_seen = (result["a"], result["prev_a"])
         return result

@@ -567,10 +567,12 @@ def run_b200(args):
     achieved = alg_bytes / (full_pass[dom]["avg_us"] * 1e-6) / 1e9
     traffic_path = ROOT / "profiles" / "dram_traffic.json"
     traffic = None
+    traffic_src = None
     if traffic_path.exists():
-        traffic = json.loads(traffic_path.read_text()).get(dom)
+        tj = json.loads(traffic_path.read_text())
+        traffic, traffic_src = tj.get(dom), f"ncu run {tj.get('_ncu_run')} (profiles/dram_traffic.json), not measured in this run"
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "operator_applications_per_launch": FULL_PASS[dom] / 16.0,
                 "kernel_timing": "CUDA events around every launch in a second pass of the same K steps",

@@ -8,8 +8,9 @@ python -m pytest tests -m gpu -q --timeout 600 > $O/${R}_pytest.log 2>&1; echo "
 python bench.py --steps 100 --warmup 5 > $O/${R}_bench.json 2> $O/${R}_bench.err; cat $O/${R}_bench.json
 python bench.py --impl reference --steps 3 --warmup 1 > $O/${R}_bench_reference.json 2>> $O/${R}_bench.err
 python tools/kbench.py > $O/${R}_kbench.txt 2>&1; cat $O/${R}_kbench.txt
+python tools/bigbench_probe.py > $O/${R}_bigbench.txt 2>&1; tail -2 $O/${R}_bigbench.txt | cut -c1-200
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${R}_launches.csv \
-    python bench.py --steps 6 --warmup 3 --no-cpu-baseline > $O/${R}_ncu_bench.log 2>&1
+    python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-extras > $O/${R}_ncu_bench.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'vdfdx_tma|field_fused|vpush_collide' -s 6 -c 3 -f \
-    -o $O/${R}_full python bench.py --steps 4 --warmup 3 --no-cpu-baseline > $O/${R}_ncu_full.log 2>&1
+    -o $O/${R}_full python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-extras > $O/${R}_ncu_full.log 2>&1
 ls -la $O | grep ${R}
