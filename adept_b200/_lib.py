@@ -82,6 +82,7 @@ SIGNATURES = {
                                      c_i, c_i, c_dp],
     "adept_b200_vpush_collide_p2p_f64": [C.POINTER(c_dp), C.POINTER(c_dp), c_i, c_ll, c_i, c_i, c_dp, c_dp, c_dp, c_d,
                                          c_d, c_d, c_d, c_dp, c_d, c_dp, c_i, c_i, c_dp],
+    "adept_b200_sum_peers_f64": [C.POINTER(c_dp), c_i, c_ll, c_dp, c_dp],
     "adept_b200_save_moments_f64": [c_dp, c_dp, c_d, c_i, c_i, c_i, c_dp, c_d, c_dp, c_dp],
     "adept_b200_interp2d_f64": [c_dp, c_dp, c_d, c_i, c_i, c_dp, c_dp, c_dp, c_dp, c_i, c_i, c_dp, c_dp],
     "adept_b200_marginal_f64": [c_dp, c_dp, c_ll, c_i, c_dp, c_dp],
@@ -111,6 +112,8 @@ SIGNATURES = {
                                   c_dp, c_i, c_d, c_d, c_dp],
     "adept_b200_step_f64": [C.POINTER(Step), c_dp],
     "adept_b200_step_bwd_f64": [C.POINTER(Step), C.POINTER(StepBwd), c_dp],
+    "adept_b200_ex_driver_f64": [c_dp, c_dp, c_i, C.POINTER(c_d), C.POINTER(c_d), C.POINTER(c_d), C.POINTER(c_d), c_ll, c_dp,
+                                 c_dp],
     "adept_b200_time_row_advance": [c_dp, c_ll, c_dp, c_dp, c_dp],
 }
 

@@ -509,6 +509,12 @@ int adept_b200_vdfdx_scratch_f64(const double* f_in, double* f_out, double* scra
   return bigx_apply_f64(f_in, f_out, scratch, batch, nx, nv, v, dt, k1x_batch, k1x, nullptr, 0, (cudaStream_t)stream);
 }
 
+int adept_b200_sum_peers_f64(const double* const* peers_host, int n_peers, long long n, double* out, void* stream) {
+  ADEPT_REQUIRE(peers_host, "peers") ADEPT_REQUIRE(out, "out")
+  for (int j = 0; j < n_peers && j < 8; j++) ADEPT_REQUIRE(peers_host[j], "peers[j]")
+  return sum_peers_f64(peers_host, n_peers, n, out, (cudaStream_t)stream);
+}
+
 /* ---- vlasov-1d2v ---- */
 int adept_b200_marginal_f64(const double* f, const double* wperp, long long rows, int nvperp, double* out, void* stream) {
   ADEPT_REQUIRE(f, "f") ADEPT_REQUIRE(wperp, "wperp") ADEPT_REQUIRE(out, "out")

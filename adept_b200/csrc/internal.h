@@ -73,6 +73,7 @@ int bigx_apply_f64(const double* in, double* out, double* scratch, int batch, in
                    const double* k1_batch, double k1, const double2* mtab, long long mtab_stride, cudaStream_t stream);
 int bigx_poisson_f64(const double* rho, const double* kmul, long long kmul_stride, double* e, int batch, int nx,
                      int mode, double Te, double lambda_De, cudaStream_t stream);
+int sum_peers_f64(const double* const* peers, int n_peers, long long n, double* out, cudaStream_t stream);
 int marginal_f64(const double* f, const double* w, long long rows, int np, double* out, cudaStream_t stream);
 int transpose_f64(const double* in, double* out, int batch, int n0, int n1, cudaStream_t stream);
 int abs_rfft_x_f64(const double* fin, double* fout, int batch, int nx, int nv, cudaStream_t stream);

@@ -225,26 +225,34 @@ int field_energy_f64(const double* e0, const double* de0, const double* e1, cons
 // ---- second stage of the fused x-push charge density: out[i] = base[i] + scale_b * ((sum_p parts[p, i]) * scale_a) ----
 // 64 rows per CTA; the parts are dealt to 4 thread groups (p = g, g+4, ...), each with two running sums, and combined
 // in a fixed order: deterministic, and short dependent-load chains (nparts/8 per thread).
-__global__ void __launch_bounds__(256) reduce_parts_kernel(const double* __restrict__ parts, int nparts, long long n,
-                                                           double scale_a, double scale_b,
-                                                           const double* __restrict__ base, double* __restrict__ out) {
-  __shared__ double sm[4][64];
+// 16 groups of 64 columns per CTA; a thread keeps up to 10 loads in flight (rows g, g + 16, ...: 148 rows of a persistent
+// x-advection in one batch), the sums are formed in a fixed order
+__global__ void __launch_bounds__(1024) reduce_parts_kernel(const double* __restrict__ parts, int nparts, long long n,
+                                                            double scale_a, double scale_b,
+                                                            const double* __restrict__ base, double* __restrict__ out) {
+  __shared__ double sm[16][64];
   const int r = threadIdx.x & 63, g = threadIdx.x >> 6;
   const long long i = (long long)blockIdx.x * 64 + r;
-  double s0 = 0.0, s1 = 0.0;
+  double s = 0.0;
   if (i < n) {
-    int pidx = g;
-    for (; pidx + 4 < nparts; pidx += 8) {
-      s0 += parts[(long long)pidx * n + i];
-      s1 += parts[(long long)(pidx + 4) * n + i];
+    for (int p0 = g; p0 < nparts; p0 += 160) {
+      double x[10];
+#pragma unroll
+      for (int u = 0; u < 10; u++) {
+        const int pidx = p0 + 16 * u;
+        x[u] = pidx < nparts ? parts[(long long)pidx * n + i] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 10; u++) s += x[u];
     }
-    if (pidx < nparts) s0 += parts[(long long)pidx * n + i];
   }
-  sm[g][r] = s0 + s1;
+  sm[g][r] = s;
   __syncthreads();
   if (g == 0 && i < n) {
-    const double s = (sm[0][r] + sm[1][r]) + (sm[2][r] + sm[3][r]);
-    const double term = __dmul_rn(scale_b, __dmul_rn(s, scale_a));
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; q++) t += sm[q][r];
+    const double term = __dmul_rn(scale_b, __dmul_rn(t, scale_a));
     out[i] = base ? __dadd_rn(base[i], term) : term;
   }
 }
@@ -256,7 +264,7 @@ int reduce_parts_f64(const double* parts, int nparts, long long n, double scale_
     return ADEPT_ERR_BAD_SHAPE;
   }
   ProfileScope prof("reduce_parts", stream);
-  reduce_parts_kernel<<<(unsigned)((n + 63) / 64), 256, 0, stream>>>(parts, nparts, n, scale_a, scale_b, base, out);
+  reduce_parts_kernel<<<(unsigned)((n + 63) / 64), 1024, 0, stream>>>(parts, nparts, n, scale_a, scale_b, base, out);
   return check_launch("reduce_parts_kernel");
 }
 
@@ -386,6 +394,38 @@ int interp2d_f64(const double* f0, const double* f1, double w, int nx, int nv, c
   ProfileScope prof("interp2d", stream);
   interp2d_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(f0, f1, w, nx, nv, x, v, xq, vq, nxq, nvq, out);
   return check_launch("interp2d_kernel");
+}
+
+// ---- out[i] = sum_r peers[r][i] in rank order (the same order on every rank: bit-identical results everywhere) ---------
+struct SumPeersArgs {
+  const double* src[8];
+  int n_peers;
+  long long n;
+  double* out;
+};
+__global__ void __launch_bounds__(256) sum_peers_kernel(SumPeersArgs p) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  double x[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) x[r] = r < p.n_peers ? __ldcv(p.src[r] + i) : 0.0;  // all peer loads in flight; no caching
+  double s = 0.0;
+#pragma unroll
+  for (int r = 0; r < 8; r++) s += x[r];
+  p.out[i] = s;
+}
+
+int sum_peers_f64(const double* const* peers, int n_peers, long long n, double* out, cudaStream_t stream) {
+  if (n_peers < 1 || n_peers > 8 || n < 1) {
+    set_last_error("sum_peers: bad arguments (n_peers=%d, n=%lld)", n_peers, n);
+    return ADEPT_ERR_BAD_ARG;
+  }
+  SumPeersArgs p = {};
+  for (int r = 0; r < n_peers; r++) p.src[r] = peers[r];
+  p.n_peers = n_peers, p.n = n, p.out = out;
+  ProfileScope prof("sum_peers", stream);
+  sum_peers_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p);
+  return check_launch("sum_peers_kernel");
 }
 
 // ---- vlasov-1d2v helpers (adept/_vlasov1d2v/solvers/vector_field.py:36-38, pushers/fokker_planck.py:81-83) -----------

@@ -577,6 +577,23 @@ __global__ void time_row_advance_kernel(const double* __restrict__ table, long l
 }
 }  // namespace adept
 
+extern "C" int adept_b200_ex_driver_f64(const double* ex_space, const double* ex_kx, int n_ex, const double* w_host,
+                                        const double* a0_host, const double* tenv_host, const double* wt_host,
+                                        long long n, double* dex, void* stream) {
+  using namespace adept;
+  if (!dex || n < 1 || n_ex < 0 || n_ex > ADEPT_B200_MAX_DRIVERS || (n_ex > 0 && (!ex_space || !ex_kx || !w_host ||
+                                                                                 !a0_host || !tenv_host || !wt_host))) {
+    set_last_error("adept_b200_ex_driver_f64: bad arguments (n=%lld, n_ex=%d)", n, n_ex);
+    return ADEPT_ERR_BAD_ARG;
+  }
+  DriverArgs d = {};
+  d.n_ex = n_ex, d.n_sub = 1, d.n = n, d.space = ex_space, d.kx = ex_kx, d.dex = dex;
+  for (int k = 0; k < n_ex; k++) d.w[k] = w_host[k], d.a0[k] = a0_host[k], d.tenv[0][k] = tenv_host[k], d.wt[0][k] = wt_host[k];
+  ProfileScope prof("ex_driver", (cudaStream_t)stream);
+  ex_driver_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d);
+  return check_launch("ex_driver_kernel");
+}
+
 extern "C" int adept_b200_time_row_advance(const double* table, long long n_rows, long long* counter, double* row,
                                            void* stream) {
   if (!table || !counter || !row || n_rows < 1) {

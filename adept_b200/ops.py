@@ -345,6 +345,30 @@ def vdfdx_rho(f, v, dt, k1x, parts, out=None, k1x_batch=None):
     return out
 
 
+def sum_peers(ptrs, n, out):
+    """out[i] = sum_r peer_r[i] in rank order over peer-mapped buffers (``ptrs``: one device pointer per rank)."""
+    rc = _lib.load().adept_b200_sum_peers_f64(_peer_array(ptrs), len(ptrs), int(n), _ptr(out, "out"), _stream())
+    _lib.check(rc, "sum_peers")
+    _count()
+    return out
+
+
+def ex_driver(ex_space, ex_kx, w, a0, tenv, wt, out=None):
+    """dex[i] = sum_d ((tenv[d] space[d, i]) w[d]) a0[d] sin(kx[d, i] - wt[d]) (field.py:21-33), one launch; ex_space /
+    ex_kx: [n_ex, n] device tensors (or None when there is no driver), the rest host sequences."""
+    n_ex = len(w)
+    if n_ex == 0:
+        return out.zero_() if out is not None else None
+    n = ex_space.shape[-1]
+    out = torch.empty(n, dtype=torch.float64, device=ex_space.device) if out is None else out
+    arr = lambda xs: (C.c_double * n_ex)(*[float(x) for x in xs])  # noqa: E731
+    rc = _lib.load().adept_b200_ex_driver_f64(_ptr(ex_space, "ex_space"), _ptr(ex_kx, "ex_kx"), n_ex, arr(w), arr(a0),
+                                              arr(tenv), arr(wt), n, _ptr(out, "out"), _stream())
+    _lib.check(rc, "ex_driver")
+    _count()
+    return out
+
+
 def reduce_parts(parts, scale_a, scale_b=1.0, base=None, out=None):
     """out = base + scale_b * ((sum_p parts[p]) * scale_a), fixed summation order."""
     n = parts.shape[1]

@@ -28,6 +28,8 @@ transverse wave (``a == 0``); anything else raises.  Requires ``nx % P == 0`` an
 
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -180,19 +182,29 @@ class ShardedVlasov1D:
         group = self.group if self.group is not None else dist.group.WORLD
         f_vs = symm.empty((self.nx, nvp), dtype=torch.float64, device=self.device)   # state: all x, my columns
         f_st = symm.empty((self.nx, nvp), dtype=torch.float64, device=self.device)   # f* after the x-push, same layout
+        share = symm.empty((self.nx,), dtype=torch.float64, device=self.device)      # my share of the charge density
         h_vs, h_st = symm.rendezvous(f_vs, group), symm.rendezvous(f_st, group)
+        h_sh = symm.rendezvous(share, group)
+        share.zero_()
         f_vs.copy_(self.state[name])
         self.state[name] = f_vs
         nparts = self.lops.ops.vdfdx_rho_parts(f_vs)
         tt = lambda a: torch.as_tensor(np.array(a, dtype=np.float64), device=self.device)  # noqa: E731
         self.p2p = {
             # per-step inputs stay on the device: space factors here, O(1) time factors from the host each step
-            "ex_space": [tt(d.envelope.space_envelope(self.x)) for d in self.ex],
-            "ex_kx": [tt(d.k0 * self.x) for d in self.ex],
+            "ex_space": tt(np.stack([d.envelope.space_envelope(self.x) * np.ones_like(self.x) for d in self.ex]))
+            if self.ex else None,
+            "ex_kx": tt(np.stack([d.k0 * self.x for d in self.ex])) if self.ex else None,
+            "dex": torch.zeros(self.nx, dtype=torch.float64, device=self.device),
+            # ion / P: every rank adds its share, the all-reduce of the scaled partial densities is rho itself
+            "ion_share": None if self.ion is None else (self.ion / self.P).contiguous(),
             "nu_fp_space": tt(self.nu_fp_prof.space_envelope(self.x[self.rows]) * np.ones(self.nxp)),
             "green": tt(np.real(np.fft.ifft(-1j * np.asarray(self.grid.one_over_kx, dtype=np.float64)))),
             "f_vs": f_vs, "f_st": f_st, "vs_ptrs": list(h_vs.buffer_ptrs), "st_ptrs": list(h_st.buffer_ptrs),
-            "handles": (h_vs, h_st), "nv": nv,
+            "handles": (h_vs, h_st, h_sh), "nv": nv, "share": share, "share_ptrs": list(h_sh.buffer_ptrs),
+            # ADEPT_B200_SHARDED_SYNC=nccl keeps the two NCCL all-reduces (A/B timing); default: symmetric-memory barriers
+            # + a peer-memory sum in rank order (no collective library call in the step)
+            "symm_sync": os.environ.get("ADEPT_B200_SHARDED_SYNC", "symm") != "nccl",
             "parts": torch.zeros((nparts, self.nx), dtype=torch.float64, device=self.device),
             "token": torch.zeros(1, dtype=torch.float64, device=self.device),
         }
@@ -205,15 +217,23 @@ class ShardedVlasov1D:
         sg, sp = g["species_grids"][n], g["species_params"][n]
         # driver field and collision frequency: same closed forms and rounding order as the reference (field.py:21-26,
         # functions.py:112-118), evaluated on the device from resident space factors -- no host-device copy per step
-        dex = torch.zeros(self.nx, dtype=torch.float64, device=self.device)
-        for d, space, kx in zip(self.ex, pp["ex_space"], pp["ex_kx"]):
-            w = d.w0 + d.dw0
-            dex = dex + ((float(d.envelope.time_envelope(t)) * space) * w) * d.a0 * torch.sin(kx - w * t)
+        dex = torch.empty(self.nx, dtype=torch.float64, device=self.device)
+        if self.ex:  # one launch (adept_b200_ex_driver_f64), time factors from the host like the native step
+            ws = [d.w0 + d.dw0 for d in self.ex]
+            ops.ex_driver(pp["ex_space"], pp["ex_kx"], ws, [d.a0 for d in self.ex],
+                          [float(d.envelope.time_envelope(t)) for d in self.ex], [d.phase(t) for d in self.ex], out=dex)
+        else:
+            dex.zero_()
         # 1. x-push on my columns, purely local (its 32-byte row pieces would waste the link)
         ops.vdfdx_rho(pp["f_vs"], self.v_loc[n], dt, self.k1x, pp["parts"], out=pp["f_st"])
-        rowsum = ops.reduce_parts(pp["parts"], 1.0, 1.0)
-        dist.all_reduce(rowsum, op=dist.ReduceOp.SUM, group=self.group)  # also: every rank's x-push has completed
-        rho = self.lops.rho_from_sum(rowsum, float(sg["dv"]), float(sp["charge"]), self.ion)
+        # my share of rho = ion / P + q dv (my partial velocity sums); the all-reduce finishes the charge density
+        if pp["symm_sync"]:
+            ops.reduce_parts(pp["parts"], float(sg["dv"]), float(sp["charge"]), base=pp["ion_share"], out=pp["share"])
+            pp["handles"][2].barrier(channel=0)  # every rank's share is written (and its x-push has completed)
+            rho = ops.sum_peers(pp["share_ptrs"], self.nx, torch.empty(self.nx, dtype=torch.float64, device=self.device))
+        else:
+            rho = ops.reduce_parts(pp["parts"], float(sg["dv"]), float(sp["charge"]), base=pp["ion_share"])
+            dist.all_reduce(rho, op=dist.ReduceOp.SUM, group=self.group)  # also: every rank's x-push has completed
         e = ops.poisson_green(rho, pp["green"])  # nx/32 CTAs instead of one 4096-point FFT in a single CTA
         e_loc, dex_loc = e[self.rows].contiguous(), dex[self.rows].contiguous()
         # 2. v-push + collisions on my rows: cells come from and go back to the ranks that own their columns
@@ -221,7 +241,10 @@ class ShardedVlasov1D:
         ops.vpush_collide_p2p(pp["st_ptrs"], pp["vs_ptrs"], self.rank * self.nxp, self.nxp, pp["nv"], e_loc, None,
                               float(sp["charge"]), float(sp["mass"]), dt, float(sg["kvr"][1]), self.v_full[n],
                               float(sg["dv"]), nu_fp, model=self.coll.model, dex=dex_loc, scheme=self.coll.scheme)
-        dist.all_reduce(pp["token"], group=self.group)  # every rank's stores into my columns have completed
+        if pp["symm_sync"]:
+            pp["handles"][2].barrier(channel=1)  # every rank's stores into my columns (and its reads of the shares) are done
+        else:
+            dist.all_reduce(pp["token"], group=self.group)  # every rank's stores into my columns have completed
         self.state["e"], self.state["de"] = e, dex
         self.step_index += 1
         self.t = self.step_index * dt

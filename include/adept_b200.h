@@ -113,6 +113,12 @@ int adept_b200_vpush_collide_p2p_f64(const double* const* in_peers_host, double*
                                      const double* v, double dv, const double* nu_fp, int model, int scheme,
                                      void* stream);
 
+/* out[i] = sum_r peers[r][i], r = 0 .. n_peers-1 in that order (the nx-long all-reduce of the charge density of a
+ * sharded grid without a collective library call: every rank reads every rank's share over NVLink peer memory and adds
+ * them in rank order, so all ranks hold bit-identical sums).  peers_host: host array of device pointers mapped into
+ * this process; the caller orders the ranks (a barrier before: shares written; one before they are overwritten). */
+int adept_b200_sum_peers_f64(const double* const* peers_host, int n_peers, long long n, double* out, void* stream);
+
 /* In-loop save moments in one pass over f (get_default_save_func / get_field_save_func, adept/_vlasov1d/storage.py:
  * 286-327, 119-162): out[k, row] = dv sum_j g_k(f_j, v_j), g = { f, f v, f v^2, f v^3, -|f| log|f|, f^2 }, out is
  * [6, batch*nx].  With f1 != NULL the distribution is the linear interpolation f0 + w (f1 - f0) that diffrax hands to
@@ -369,6 +375,14 @@ typedef struct adept_b200_step {
    * wt[s][d] at 48 + 8 s + d, nu_fp_time at 96, nu_K_time at 97, ex_t[s] at 98 + s. */
   const double* time_row;
 } adept_b200_step;
+
+/* Longitudinal driver field at one time (LongitudinalElectricFieldDriver.__call__, field.py:21-33), one launch:
+ * dex[i] = sum_d ((tenv[d] * ex_space[d, i]) * w[d]) * a0[d] * sin(ex_kx[d, i] - wt[d]); w / a0 / tenv / wt are HOST arrays
+ * of n_ex entries (the step descriptor's ex_w, ex_a0, ex_tenv[s], ex_wt[s]); ex_space / ex_kx device arrays [n_ex, n].
+ * For callers that compose the step themselves (the sharded grid). */
+int adept_b200_ex_driver_f64(const double* ex_space, const double* ex_kx, int n_ex, const double* w_host,
+                             const double* a0_host, const double* tenv_host, const double* wt_host, long long n,
+                             double* dex, void* stream);
 
 #define ADEPT_B200_TIME_ROW_LEN 104
 
