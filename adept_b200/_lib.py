@@ -60,6 +60,16 @@ class StepBwd(C.Structure):
                 ("nu_K_bar", c_dp), ("scratch_f", c_dp * 3), ("scratch_row", c_dp * 2)]
 
 
+class FieldPeers(C.Structure):
+    """ctypes mirror of struct adept_b200_field_peers (include/adept_b200.h)."""
+
+    _fields_ = [("n_peers", c_i), ("my_rank", c_i), ("epoch", C.c_ulonglong), ("share_in", c_dp * 8),
+                ("flag_in", c_dp * 8), ("sync_counter", c_dp), ("ion_share", c_dp), ("dv", c_d), ("charge", c_d),
+                ("dx", c_d), ("green", c_dp), ("rho", c_dp), ("e", c_dp), ("dex", c_dp), ("pond", c_dp),
+                ("a_zero", c_dp), ("n_ex", c_i), ("ex_space", c_dp), ("ex_kx", c_dp), ("ex_w", c_d * 8),
+                ("ex_a0", c_d * 8), ("ex_tenv", c_d * 8), ("ex_wt", c_d * 8)]
+
+
 TIME_ROW_LEN = 104  # ADEPT_B200_TIME_ROW_LEN: tenv[6][8] | wt[6][8] | nu_fp_time | nu_K_time | ex_t[6]
 
 
@@ -83,6 +93,7 @@ SIGNATURES = {
     "adept_b200_vpush_collide_p2p_f64": [C.POINTER(c_dp), C.POINTER(c_dp), c_i, c_ll, c_i, c_i, c_dp, c_dp, c_dp, c_d,
                                          c_d, c_d, c_d, c_dp, c_d, c_dp, c_i, c_i, c_dp],
     "adept_b200_sum_peers_f64": [C.POINTER(c_dp), c_i, c_ll, c_dp, c_dp],
+    "adept_b200_vdfdx_field_peers_f64": [c_dp, c_dp, c_i, c_i, c_dp, c_d, c_d, c_dp, c_i, C.POINTER(FieldPeers), c_dp],
     "adept_b200_save_moments_f64": [c_dp, c_dp, c_d, c_i, c_i, c_i, c_dp, c_d, c_dp, c_dp],
     "adept_b200_interp2d_f64": [c_dp, c_dp, c_d, c_i, c_i, c_dp, c_dp, c_dp, c_dp, c_i, c_i, c_dp, c_dp],
     "adept_b200_marginal_f64": [c_dp, c_dp, c_ll, c_i, c_dp, c_dp],

@@ -420,6 +420,40 @@ int adept_b200_vdfdx_rho_f64(const double* f_in, double* f_out, int batch, int n
   return moments_f64(f_out, batch, nx, nv, nullptr, 1.0, nullptr, outs, nullptr, st);
 }
 
+int adept_b200_vdfdx_field_peers_f64(const double* f_in, double* f_out, int nx, int nv_local, const double* v_local,
+                                     double dt, double k1x, double* parts, int nparts,
+                                     const adept_b200_field_peers* fp, void* stream) {
+  ADEPT_REQUIRE(f_in, "f_in") ADEPT_REQUIRE(f_out, "f_out") ADEPT_REQUIRE(v_local, "v_local")
+  ADEPT_REQUIRE(parts, "parts") ADEPT_REQUIRE(fp, "fp")
+  if (fp->n_peers < 2 || fp->n_peers > 8 || fp->my_rank < 0 || fp->my_rank >= fp->n_peers || fp->epoch < 1 ||
+      fp->n_ex < 0 || fp->n_ex > 8) {
+    set_last_error("vdfdx_field_peers: n_peers=%d my_rank=%d epoch=%llu n_ex=%d", fp->n_peers, fp->my_rank, fp->epoch,
+                   fp->n_ex);
+    return ADEPT_ERR_BAD_ARG;
+  }
+  for (int r = 0; r < fp->n_peers; r++) {
+    ADEPT_REQUIRE(fp->share_in[r], "share_in[r]") ADEPT_REQUIRE(fp->flag_in[r], "flag_in[r]")
+  }
+  if (!vdfdx_tma_supported(f_in, f_out, nx, nv_local) || !vdfdx_tma_field_supported(1, nx, nv_local)) {
+    set_last_error("vdfdx_field_peers: unsupported shape nx=%d nv_local=%d (or the grid cannot be co-resident)", nx,
+                   nv_local);
+    return ADEPT_ERR_UNSUPPORTED;
+  }
+  if (nparts < vdfdx_tma_parts(1, nx, nv_local)) {
+    set_last_error("vdfdx_field_peers: parts buffer has %d rows, needs %d", nparts, vdfdx_tma_parts(1, nx, nv_local));
+    return ADEPT_ERR_BAD_ARG;
+  }
+  FieldTail ft = {};
+  ft.counter = fp->sync_counter, ft.base = fp->ion_share, ft.dv = fp->dv, ft.charge = fp->charge;
+  ft.rho = fp->rho, ft.e = fp->e, ft.green = fp->green, ft.a = fp->a_zero, ft.pond = fp->pond, ft.dx = fp->dx;
+  ft.n_ex = fp->n_ex, ft.ex_space = fp->ex_space, ft.ex_kx = fp->ex_kx, ft.dex = fp->dex;
+  for (int d = 0; d < fp->n_ex; d++)
+    ft.ex_w[d] = fp->ex_w[d], ft.ex_a0[d] = fp->ex_a0[d], ft.ex_tenv[d] = fp->ex_tenv[d], ft.ex_wt[d] = fp->ex_wt[d];
+  ft.n_peers = fp->n_peers, ft.my_rank = fp->my_rank, ft.epoch = fp->epoch;
+  for (int r = 0; r < fp->n_peers; r++) ft.share_in[r] = fp->share_in[r], ft.flag_in[r] = fp->flag_in[r];
+  return vdfdx_tma_f64(f_in, f_out, 1, nx, nv_local, v_local, dt, nullptr, k1x, parts, (cudaStream_t)stream, nullptr, &ft);
+}
+
 int adept_b200_reduce_parts_f64(const double* parts, int nparts, long long n, double scale_a, double scale_b,
                                 const double* base, double* out, void* stream) {
   ADEPT_REQUIRE(parts, "parts") ADEPT_REQUIRE(out, "out")

@@ -162,9 +162,29 @@ __device__ __forceinline__ void dft16_finish(cplx* v) {
 struct NoHook {
   __device__ __forceinline__ void operator()() const {}
 };
+// A hook type that declares `static constexpr bool HAS_AT = true` is also called as hook.at<P, W>() at the start of
+// the two arithmetic stretches of every radix-16 pass P: W = 0 after the pass's exchange loads have been issued (before
+// the column butterflies), W = 1 after its mid-pass barrier (before the second half).  Callers queue asynchronous work
+// for the load/store pipe there (deferred global stores), which then drains under the fp64 work that follows.
+template <class H, class = void>
+struct hook_has_at {
+  static constexpr bool value = false;
+};
+template <class H>
+struct hook_has_at<H, decltype((void)H::HAS_AT)> {
+  static constexpr bool value = true;
+};
+template <int P, int W, class H>
+__device__ __forceinline__ void hook_at(const H& h) {
+  if constexpr (hook_has_at<H>::value) h.template at<P, W>();
+}
+
+__device__ __forceinline__ cplx csqr(const cplx a) { return cmake(fma(a.x, a.x, -(a.y * a.y)), (a.x + a.x) * a.y); }
 
 // BS: stride (in cplx) between consecutive buffer slots -- 2 when two transforms are interleaved slot by slot
-template <int LOGN, int P, int BS = 1>
+// TW: 0 = six twiddle loads per radix-16 pass (w^1..3, w^4, w^8, w^12); 1 = two loads (w^1, w^4), the other four by
+// squaring / multiplication (14 more fp64 instructions, 4 fewer 16-byte loads per thread and pass)
+template <int LOGN, int P, int BS = 1, int TW = 0>
 struct FftPass {
   using C = FftCfg<LOGN>;
   template <class HOOK>
@@ -184,6 +204,7 @@ struct FftPass {
 #pragma unroll
         for (int m = 0; m < 16; m++) x[m] = buf[fft_pad(t + T * m) * BS];
       }
+      hook_at<P, 0>(buffer_free);
       ADEPT_TRACE(10 * P + 0);
       // Twiddles: only w^1, w^2, w^3 and w^4, w^8, w^12 are loaded (6 of the 15 powers).  u[c + 4j] = x[c + 4j] w^(c + 4j)
       // = w^c (x[c + 4j] (w^4)^j): the inputs are scaled by (w^4)^j, the column DFT4 runs, and its four outputs are
@@ -191,10 +212,16 @@ struct FftPass {
       // data pipe is the busiest unit of the spectral pushes (about 30 % of its time went to twiddle loads), the fp64
       // pipe has the headroom.  (With 15 loads ptxas also hoisted all of them and spilled.)
       if constexpr (NS > 1) {
-        const cplx w4 = __ldg(twp + 3 * NS), w8 = __ldg(twp + 7 * NS), w12 = __ldg(twp + 11 * NS);
-        cplx wc[4];
+        cplx w4, w8, w12, wc[4];
+        if constexpr (TW == 1) {
+          wc[1] = __ldg(twp), w4 = __ldg(twp + 3 * NS);
+          wc[2] = csqr(wc[1]), w8 = csqr(w4);
+          wc[3] = cmul(wc[1], wc[2]), w12 = cmul(w4, w8);
+        } else {
+          w4 = __ldg(twp + 3 * NS), w8 = __ldg(twp + 7 * NS), w12 = __ldg(twp + 11 * NS);
 #pragma unroll
-        for (int c = 1; c < 4; c++) wc[c] = __ldg(twp + (c - 1) * NS);
+          for (int c = 1; c < 4; c++) wc[c] = __ldg(twp + (c - 1) * NS);
+        }
 #pragma unroll
         for (int c = 0; c < 4; c++) {
           x[c + 4] = cmul(x[c + 4], w4);
@@ -216,6 +243,7 @@ struct FftPass {
       ADEPT_TRACE(10 * P + 1);
       if constexpr (P < C::NPASS - 1) __syncthreads();
       if constexpr (P == C::NPASS - 1) buffer_free();
+      hook_at<P, 1>(buffer_free);
       ADEPT_TRACE(10 * P + 2);
       dft16_finish(x);
       ADEPT_TRACE(10 * P + 3);
@@ -254,7 +282,7 @@ struct FftPass {
       ADEPT_TRACE(10 * P + 4);
       __syncthreads();
       ADEPT_TRACE(10 * P + 5);
-      FftPass<LOGN, P + 1, BS>::run(x, buf, tw, t, opaque_zero, buffer_free);
+      FftPass<LOGN, P + 1, BS, TW>::run(x, buf, tw, t, opaque_zero, buffer_free);
     }
   }
 };
@@ -276,10 +304,10 @@ __device__ __forceinline__ void fft_prefetch_twiddles(const cplx* tw, int t) {
 
 // Forward complex FFT of the N points held as x[m] = z[t + T*m]; result X[t + T*m] in x[m].
 // All threads of the CTA must call this together (it uses __syncthreads()).
-template <int LOGN, int BS = 1, class HOOK = NoHook>
+template <int LOGN, int BS = 1, int TW = 0, class HOOK = NoHook>
 __device__ __forceinline__ void fft_forward(cplx (&x)[FftCfg<LOGN>::E], cplx* buf, const cplx* tw, int t,
                                             int opaque_zero, const HOOK& buffer_free = HOOK()) {
-  FftPass<LOGN, 0, BS>::run(x, buf, tw, t, opaque_zero, buffer_free);
+  FftPass<LOGN, 0, BS, TW>::run(x, buf, tw, t, opaque_zero, buffer_free);
 }
 
 }  // namespace adept

@@ -68,7 +68,14 @@ __device__ __forceinline__ void field_tail_solve(const FieldTail& ft, const doub
 #pragma unroll
       for (int g2 = 0; g2 < NGRP; g2++) tot += red[g2 * 32 + colr];
       const double term = __dmul_rn(ft.charge, __dmul_rn(tot, ft.dv));  // field.py:197-208
-      ft.rho[i] = ft.base ? __dadd_rn(ft.base[i], term) : term;
+      const double mine = ft.base ? __dadd_rn(ft.base[i], term) : term;
+      if (ft.n_peers > 1) {  // my share of rho at i goes to slot my_rank of every rank's inbox
+        const size_t slot = ((size_t)(ft.epoch & 1) * ft.n_peers + ft.my_rank) * N + i;
+        for (int r = 0; r < ft.n_peers; r++) ft.share_in[r][slot] = mine;
+        __threadfence_system();
+      } else {
+        ft.rho[i] = mine;
+      }
     }
     if (grp == 1 && i < i_hi) {
       const double lo = __dmul_rn(ft.a[i], ft.a[i]), hi = __dmul_rn(ft.a[i + 2], ft.a[i + 2]);
@@ -86,7 +93,36 @@ __device__ __forceinline__ void field_tail_solve(const FieldTail& ft, const doub
       ft.dex[i] = total;
     }
   }
-  grid_barrier(ft.counter, 2 * G);  // rho complete on every CTA
+  grid_barrier(ft.counter, 2 * G);  // rho (or this rank's share of it, pushed to every inbox) complete on every CTA
+  unsigned int nbar = 3;     // arrivals per CTA on the ticket counter by the end of the tail
+  if (ft.n_peers > 1) {
+    nbar = 4;
+    if (blockIdx.x == 0 && tid < ft.n_peers) {  // all CTAs of this rank have fenced their pushes (barrier above)
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(ft.flag_in[tid] + ft.my_rank), "l"(ft.epoch) : "memory");
+    }
+    if (tid < ft.n_peers) {  // every CTA watches the rank's own inbox flags (local memory)
+      const unsigned long long* fl = ft.flag_in[ft.my_rank] + tid;
+      unsigned long long seen;
+      do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(fl) : "memory");
+      } while (seen < ft.epoch);
+    }
+    __syncthreads();
+    // rho at my slice = the P shares in rank order (identical on every rank); L2 loads: the inbox was written by peers
+    const double* inbox = ft.share_in[ft.my_rank] + (size_t)(ft.epoch & 1) * ft.n_peers * N;
+    for (int i = i_lo + tid; i < i_hi; i += THREADS) {
+      double x[8];
+#pragma unroll
+      for (int r = 0; r < 8; r++) x[r] = r < ft.n_peers ? __ldcg(inbox + (size_t)r * N + i) : 0.0;
+      double tot = x[0];
+#pragma unroll
+      for (int r = 1; r < 8; r++)
+        if (r < ft.n_peers) tot = __dadd_rn(tot, x[r]);
+      ft.rho[i] = tot;
+    }
+    grid_barrier(ft.counter, 3 * G);  // rho complete on every CTA
+  }
   {
 #pragma unroll
     for (int u0 = 0; u0 < PER_T; u0 += 8) {
@@ -156,7 +192,7 @@ __device__ __forceinline__ void field_tail_solve(const FieldTail& ft, const doub
     }
   }
   __syncthreads();
-  if (tid == 0 && atomicAdd(ft.counter, 1u) == 3 * G - 1) *ft.counter = 0u;  // last one out re-arms the counter
+  if (tid == 0 && atomicAdd(ft.counter, 1u) == nbar * G - 1) *ft.counter = 0u;  // last one out re-arms the counter
 }
 
 }  // namespace adept

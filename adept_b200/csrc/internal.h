@@ -106,6 +106,15 @@ struct FieldTail {
   double* dex;
   double ex_w[8], ex_a0[8], ex_tenv[8], ex_wt[8];
   const double* trow;     // nullable device-resident time row (common.cuh): replaces ex_tenv / ex_wt (substep 0)
+  // Sharded grid (n_peers > 1): this launch only saw the rank's own velocity columns, so the slice sums are the rank's
+  // SHARE of the charge density (base = ion / P).  Every CTA pushes its slice of the share into all ranks' inboxes over
+  // peer memory, rank `my_rank` raises flag my_rank in every inbox (epoch = step count, monotonic), waits for the P flags
+  // of its own inbox and sums the P shares in rank order -- the all-reduce of the reference's sharded charge density
+  // (field.py:197-208 under shard_map) without a collective call or a second launch.
+  int n_peers, my_rank;
+  double* share_in[8];              // rank r's inbox: [2 (epoch parity)][n_peers][nx]
+  unsigned long long* flag_in[8];   // rank r's flags: [n_peers]
+  unsigned long long epoch;
 };
 bool vdfdx_tma_supported(const double* fin, const double* fout, int nx, int nv);
 int vdfdx_tma_parts(int batch, int nx, int nv);

@@ -273,11 +273,40 @@ int reduce_parts_f64(const double* parts, int nparts, long long n, double scale_
 //   out[k, row] = dv * sum_j g_k(f_j, v_j),  g = { f, f v, f v^2, f v^3, -|f| log|f|, f^2 }
 // SPLIT warps share a row (each takes a contiguous part of it): the logarithm makes the pass instruction-bound, and
 // 4096 rows alone fill less than half of the warp slots of 148 SMs
+// Natural logarithm for the entropy moment, absolute error ~2e-16 (the library log costs ~45 fp64 instructions per cell and
+// made the pass fp64-bound at 80 us for 4096^2): x = 2^e m, m in [1, 2); the top 7 mantissa bits pick c = 1 + i/128 from
+// a shared-memory table of (1/c rounded, -log(1/c rounded)), r = m (1/c) - 1 in [0, 2^-7] exactly (one fma), and
+// log1p(r) is its Taylor polynomial through r^8 (next term < 1.2e-20).  Zero, subnormals, inf and NaN take the library
+// path (log(0) = -inf must survive: -|f| log|f| is NaN at f = 0 in the reference too).
+__device__ __noinline__ double slow_log(double ax) { return log(ax); }  // out of line: keeps the streaming loop small
+__device__ __forceinline__ double fast_log_pos(double ax, const double2* __restrict__ tab) {
+  const long long bits = __double_as_longlong(ax);
+  const int hi = (int)(bits >> 32);
+  if ((unsigned)(hi - 0x00100000) >= (unsigned)(0x7ff00000 - 0x00100000)) return slow_log(ax);
+  const double2 tb = tab[(hi >> 13) & 127];
+  const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+  const double r = fma(m, tb.x, -1.0);
+  double q = fma(r, -1.0 / 8.0, 1.0 / 7.0);
+  q = fma(r, q, -1.0 / 6.0);
+  q = fma(r, q, 1.0 / 5.0);
+  q = fma(r, q, -1.0 / 4.0);
+  q = fma(r, q, 1.0 / 3.0);
+  q = fma(r, q, -0.5);
+  const double p1 = fma(r * r, q, r);
+  return fma((double)((hi >> 20) - 1023), 0.693147180559945309417232, tb.y + p1);
+}
+
 template <int SPLIT>
-__global__ void __launch_bounds__(256) save_moments_kernel(const double* __restrict__ f0, const double* __restrict__ f1,
+__global__ void __launch_bounds__(256, 3) save_moments_kernel(const double* __restrict__ f0, const double* __restrict__ f1,
                                                            double w, const double* __restrict__ v, long long rows,
                                                            int nv, double dv, double* __restrict__ out) {
   __shared__ double part[8][6];
+  __shared__ double2 logtab[128];
+  if (threadIdx.x < 128) {
+    const double inv = 1.0 / (1.0 + (double)threadIdx.x * (1.0 / 128.0));
+    logtab[threadIdx.x] = make_double2(inv, -log(inv));
+  }
+  __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const long long row = (long long)blockIdx.x * (8 / SPLIT) + wid / SPLIT;
   const int q = wid % SPLIT;
@@ -294,7 +323,7 @@ __global__ void __launch_bounds__(256) save_moments_kernel(const double* __restr
     acc[1] += x * vv;
     acc[2] += x * (vv * vv);
     acc[3] += x * (vv * vv * vv);
-    acc[4] += -log(ax) * ax;
+    acc[4] = fma(-fast_log_pos(ax, logtab), ax, acc[4]);
     acc[5] += x * x;
   };
   if (live) {
@@ -305,7 +334,26 @@ __global__ void __launch_bounds__(256) save_moments_kernel(const double* __restr
       const double2* a2 = reinterpret_cast<const double2*>(a);
       const double2* b2 = reinterpret_cast<const double2*>(b);
       const double2* v2 = reinterpret_cast<const double2*>(vq);
-      for (int i = lane; i < (len >> 1); i += 32) {
+      const int n2 = len >> 1;
+      int i = lane;
+      // four independent 16-byte loads of f per lane in flight (one per iteration left the pass latency-bound on DRAM:
+      // 16 KB in flight per SM, 70 us for 4096^2)
+      for (; i + 96 < n2; i += 128) {
+        double2 xa[4], ya[4], va[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          xa[u] = __ldcs(a2 + i + 32 * u);
+          ya[u] = b ? __ldcs(b2 + i + 32 * u) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) va[u] = __ldg(v2 + i + 32 * u);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          add(xa[u].x, ya[u].x, va[u].x, s);
+          add(xa[u].y, ya[u].y, va[u].y, s1);
+        }
+      }
+      for (; i < n2; i += 32) {
         const double2 xa = a2[i], va = __ldg(v2 + i);
         const double2 ya = b ? b2[i] : make_double2(0.0, 0.0);
         add(xa.x, ya.x, va.x, s);

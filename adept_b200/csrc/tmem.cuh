@@ -63,4 +63,26 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, double (&v)[8]) {  // f
   for (int i = 0; i < 8; i++) v[i] = __hiloint2double((int)r[2 * i + 1], (int)r[2 * i]);
 }
 
+// 4 doubles (8 columns) / 2 doubles (4 columns) per call
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, double (&v)[4]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  tmem_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 4; i++) v[i] = __hiloint2double((int)r[2 * i + 1], (int)r[2 * i]);
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, double (&v)[2]) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+  tmem_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 2; i++) v[i] = __hiloint2double((int)r[2 * i + 1], (int)r[2 * i]);
+}
+
 }  // namespace adept

@@ -46,7 +46,10 @@ struct TmaPushArgs {
 // VAR (nx = 4096 only) divides the 80 KB beside the exchange buffer between NEARLY boxes of the NEXT tile that land
 // early (their TMA loads are issued at the start of the current tile instead of inside its last pass, where the load of
 // 4096 box rows at ~0.5 rows/clk is exposed) and NSTAGE staged output chunks: 0 = (0, 10), 1 = (10, 0), 2 = (5, 5),
-// 3 = (7, 3).
+// 3 = (7, 3); 4 = (10, 0) with DEFERRED output stores: the finished tile is parked in tensor memory (64 columns per
+// thread) and its direct global stores are issued a few at a time at the start of the arithmetic stretches of the NEXT
+// tile's transforms (FftPass hook points), where the load/store pipe is idle and the fp64 pipe busy -- the store phase
+// (8200 LSU cycles per tile with the fp64 pipe idle, 17 % of the stall samples in r02e) disappears from the timeline.
 template <int LOGN, int VAR = 0>
 struct TmaCfg {
   using C = FftCfg<LOGN>;
@@ -61,7 +64,11 @@ struct TmaCfg {
   // 32 KB shared-memory accumulator: no shuffle + read-modify-write per row, and the freed shared memory stages four
   // more output chunks for TMA stores (the kernel has no matrix product, so the 256 KB of TMEM are otherwise idle)
   static constexpr bool TMEM_ACC = (LOGN == 12);
-  static constexpr int TMEM_COLS = 128;  // 4 warps share a lane quadrant, 32 columns each
+  static constexpr bool DEFER = (LOGN == 12 && VAR == 4);
+  static constexpr int TW = (LOGN == 12 && VAR == 5) ? 1 : 0;  // 5 = (10, 0) with two twiddle loads per pass (fft_core.cuh)
+  // 4 warps share a lane quadrant: 32 columns of row sums each, + 64 columns of parked outputs with DEFER
+  static constexpr int TMEM_COLS = DEFER ? 512 : 128;
+  static constexpr int TMEM_WARP_COLS = TMEM_COLS / 4;
   static constexpr size_t ACC_BYTES = TMEM_ACC ? 0 : (size_t)N * sizeof(double);
   // Output chunks (one TMA box {4, 256} = 8 KB each) that leave through a shared-memory staging area and TMA tensor
   // stores instead of direct 16-byte stores.  A warp's direct store touches 16 lines (~2 L1 cycles each), so the store
@@ -70,7 +77,7 @@ struct TmaCfg {
   // direct, both draining concurrently.  Only where the CTA is alone on its SM anyway (nx = 4096).
   // (with the shared-memory accumulator, r01: 4 -> 141.2 us, 6 -> 137.9 us, 7 -> 139.5 us for x-push + field tail: L1
   // shrinks with the staging area; 10 chunks beside the TMEM accumulator occupy the same 223 KB as 6 did before)
-  static constexpr int NEARLY = (LOGN != 12) ? 0 : (VAR == 1 ? 10 : (VAR == 2 ? 5 : (VAR == 3 ? 7 : 0)));
+  static constexpr int NEARLY = (LOGN != 12) ? 0 : ((VAR == 1 || VAR == 4 || VAR == 5) ? 10 : (VAR == 2 ? 5 : (VAR == 3 ? 7 : 0)));
   static constexpr int NSTAGE = (LOGN == 12) ? 10 - NEARLY : 0;
   static constexpr size_t BOX_BYTES = (size_t)BOX_ROWS * 4 * sizeof(double);
   static constexpr size_t BAR_OFF = BUF_BYTES + PH_BYTES + ACC_BYTES;
@@ -78,6 +85,48 @@ struct TmaCfg {
   static constexpr size_t STAGE_OFF = EARLY_OFF + (size_t)NEARLY * BOX_BYTES;
   static constexpr size_t STAGE_BYTES = (size_t)NSTAGE * BOX_BYTES;
   static constexpr size_t SMEM = (NSTAGE + NEARLY) ? STAGE_OFF + STAGE_BYTES : BAR_OFF + 32;
+};
+
+// Hook handed to the FFT passes of the nx = 4096 kernel (fft_core.cuh: hook_at).  `free_fn` is the buffer-free action of
+// the last inverse pass.  With `pending`, registers base .. base + 7 of the PREVIOUS tile (parked in tensor memory at
+// `park`, 4 columns each, as (col, col + 1) of row t + T m) leave as direct 16-byte stores, one or two per hook point.
+template <int T, class F>
+struct XHook {
+  static constexpr bool HAS_AT = true;
+  const F& free_fn;
+  uint32_t park;
+  double* dst;  // previous tile: f_out at row 0 of the member, this thread's column pair
+  size_t nv;
+  int t, base;
+  bool pending;
+  __device__ __forceinline__ void operator()() const { free_fn(); }
+  template <int START, int COUNT>
+  __device__ __forceinline__ void drain() const {
+    if constexpr (COUNT == 2) {
+      double r[4];
+      tmem_ld4(park + 4 * (base + START), r);
+      *reinterpret_cast<double2*>(dst + (size_t)(t + T * (base + START)) * nv) = make_double2(r[0], r[1]);
+      *reinterpret_cast<double2*>(dst + (size_t)(t + T * (base + START + 1)) * nv) = make_double2(r[2], r[3]);
+    } else {
+      double r[2];
+      tmem_ld2(park + 4 * (base + START), r);
+      *reinterpret_cast<double2*>(dst + (size_t)(t + T * (base + START)) * nv) = make_double2(r[0], r[1]);
+    }
+  }
+  template <int P, int W>
+  __device__ __forceinline__ void at() const {
+    if (!pending) return;
+    // 8 registers over the six stretches of a three-pass transform; two where the twiddled column butterflies follow
+    if constexpr (P == 0 && W == 0) drain<0, 1>();
+    if constexpr (P == 0 && W == 1) drain<1, 1>();
+    if constexpr (P == 1 && W == 0) drain<2, 2>();
+    if constexpr (P == 1 && W == 1) drain<4, 1>();
+    if constexpr (P == 2 && W == 0) drain<5, 2>();
+    if constexpr (P == 2 && W == 1) drain<7, 1>();
+  }
+};
+struct NoFree {
+  __device__ __forceinline__ void operator()() const {}
 };
 
 template <int LOGN, bool FIELD = false, int VAR = 0>
@@ -116,7 +165,7 @@ __global__ void __launch_bounds__(TmaCfg<LOGN>::THREADS, 1)
     __syncthreads();
     tmem_fence_after_sync();
     tmem_base = *tmem_slot;
-    racc_addr = tmem_addr(tmem_base, tid >> 5, 32 * (tid >> 7));
+    racc_addr = tmem_addr(tmem_base, tid >> 5, K::TMEM_WARP_COLS * (tid >> 7));
     const double zeros[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     tmem_st8(racc_addr, zeros);
     tmem_st8(racc_addr + 16, zeros);
@@ -178,6 +227,8 @@ __global__ void __launch_bounds__(TmaCfg<LOGN>::THREADS, 1)
   if (tid == 0 && tl < p.ntiles) issue_early(tl), issue_load(tl);
   uint32_t parity = 0;
   int cur_b = -1;
+  const uint32_t park_addr = racc_addr + 32;  // DEFER: 64 columns behind the row sums
+  double* dst_prev = nullptr;                 // DEFER: output base of the tile parked in tensor memory, if any
   for (; tl < p.ntiles; tl += gridDim.x) {
     const int b = tl / tiles_per_member, cg = tl - b * tiles_per_member;
     if (p.partial && b != cur_b) {
@@ -204,7 +255,13 @@ __global__ void __launch_bounds__(TmaCfg<LOGN>::THREADS, 1)
       __syncthreads();
       if (tid == 0 && tl + (int)gridDim.x < p.ntiles) issue_early(tl + gridDim.x);
     }
-    fft_forward<LOGN, 2>(x, buf, p.tw, t, p.zero);
+    if constexpr (K::DEFER) {
+      const NoFree nofree;
+      const XHook<T, NoFree> hk{nofree, park_addr, dst_prev, (size_t)p.nv, t, 0, dst_prev != nullptr};
+      fft_forward<LOGN, 2>(x, buf, p.tw, t, p.zero, hk);
+    } else {
+      fft_forward<LOGN, 2, K::TW>(x, buf, p.tw, t, p.zero);
+    }
     half_spectrum_update<LOGN, 2>(x, buf, ph, t, p.filt);
     // the exchange buffer is dead once every thread has read its inputs of the last inverse pass: the next tile's TMA
     // load is issued from inside that pass, so it also overlaps the second half of the butterflies (not only the stores)
@@ -216,7 +273,12 @@ __global__ void __launch_bounds__(TmaCfg<LOGN>::THREADS, 1)
       __syncthreads();
       if (tid == 0 && tl + (int)gridDim.x < p.ntiles) issue_load(tl + gridDim.x);
     };
-    fft_forward<LOGN, 2>(x, buf, p.tw + p.zero, t, p.zero, buffer_free);
+    if constexpr (K::DEFER) {
+      const XHook<T, decltype(buffer_free)> hk{buffer_free, park_addr, dst_prev, (size_t)p.nv, t, 8, dst_prev != nullptr};
+      fft_forward<LOGN, 2>(x, buf, p.tw + p.zero, t, p.zero, hk);
+    } else {
+      fft_forward<LOGN, 2, K::TW>(x, buf, p.tw + p.zero, t, p.zero, buffer_free);
+    }
 
     // global stores (local/global queue) interleaved with the row-sum accumulation (shuffle + shared-memory queue)
     double* dst = p.fout + ((size_t)b * N) * p.nv + col;
@@ -236,10 +298,25 @@ __global__ void __launch_bounds__(TmaCfg<LOGN>::THREADS, 1)
         tma_commit_group();
       }
     }
+    // DEFER: every tile but the CTA's last is parked in tensor memory and stored during the next tile's transforms
+    const bool park_tile = K::DEFER && tl + (int)gridDim.x < p.ntiles;
+    if constexpr (K::DEFER) {
+      dst_prev = nullptr;
+      if (park_tile) {
+#pragma unroll
+        for (int h = 0; h < 4; h++) {
+          const double r[8] = {x[4 * h].y,     x[4 * h].x,     x[4 * h + 1].y, x[4 * h + 1].x,
+                               x[4 * h + 2].y, x[4 * h + 2].x, x[4 * h + 3].y, x[4 * h + 3].x};
+          tmem_st8(park_addr + 16 * h, r);
+        }
+        tmem_wait_st();
+        dst_prev = dst;
+      }
+    }
 #pragma unroll
     for (int m = 0; m < E; m++) {
       const size_t e = t + T * m;
-      if (m >= K::NSTAGE) *reinterpret_cast<double2*>(dst + e * p.nv) = make_double2(x[m].y, x[m].x);
+      if (m >= K::NSTAGE && !park_tile) *reinterpret_cast<double2*>(dst + e * p.nv) = make_double2(x[m].y, x[m].x);
       if constexpr (!K::TMEM_ACC) {
         if (want_rho) {
           double s = x[m].y + x[m].x;
@@ -390,7 +467,7 @@ static int x_variant() {
   if (var < 0) {
     const char* e = getenv("ADEPT_B200_XVAR");
     var = e ? atoi(e) : 1;  // measured (r02, x-push + field tail): 0 -> 136.4 us, 1 -> 129.9, 2 -> 132.9, 3 -> 133.2
-    if (var < 0 || var > 3) var = 1;
+    if (var < 0 || var > 5) var = 1;
   }
   return var;
 }
@@ -400,6 +477,8 @@ static int launch_tma12(const CUtensorMap& map, const TmaPushArgs& p, int grid, 
     case 1: return launch_tma<12, FIELD, 1>(map, p, grid, stream);
     case 2: return launch_tma<12, FIELD, 2>(map, p, grid, stream);
     case 3: return launch_tma<12, FIELD, 3>(map, p, grid, stream);
+    case 4: return launch_tma<12, FIELD, 4>(map, p, grid, stream);
+    case 5: return launch_tma<12, FIELD, 5>(map, p, grid, stream);
     default: return launch_tma<12, FIELD, 0>(map, p, grid, stream);
   }
 }

@@ -9,6 +9,8 @@
 // a'[e], b'[e] (e = t + T m) is scattered from registers into two chunk-padded row buffers that alias the Stockham
 // exchange buffer (same size: 17/16 nv complex = 2 x 17/16 nv doubles), each row is solved by fp_row_fast
 // (collide_core.cuh) with the same T threads (16 contiguous cells each), and the rows are stored coalesced.
+#include <stdlib.h>
+
 #include "collide_core.cuh"
 #include "internal.h"
 #include "push_core.cuh"
@@ -43,6 +45,12 @@ struct VrowArgs {
   double* out_peer[8];
   int nvp_shift;
   long long row0_global;
+  long long nx_global;  // rows of every rank's v-sharded buffer
+};
+
+// Peer mode with bulk transfers (PEER instantiation): the tensor maps of the P output buffers, one per rank
+struct alignas(64) PeerMaps {
+  CUtensorMap m[8];
 };
 
 template <int LOGN>
@@ -58,15 +66,18 @@ struct VrowCfg {
   static constexpr size_t RED_BYTES = (size_t)2 * (WARP_MODE ? T / 32 : (T > 32 ? T : 32)) * 3 * sizeof(double);
   static constexpr size_t PCR_BYTES = (size_t)6 * T * sizeof(double);
   // ~84 KB at nv = 4096: two CTAs per SM leave ~60 KB of the 228 KB array to L1, enough for the twiddle rows in use
-  static constexpr size_t SMEM = BUF_BYTES + PH_BYTES + RED_BYTES + PCR_BYTES;
+  static constexpr size_t SMEM = BUF_BYTES + PH_BYTES + RED_BYTES + PCR_BYTES + 16;  // + one mbarrier (peer bulk loads)
   static constexpr int OUT_BOX_ROWS = (N / 16) < 256 ? (N / 16) : 256;  // 128-byte chunks per TMA store box
 };
 
 // TMA_OUT: the solved rows leave shared memory through TMA tensor stores (no LDS + STG pass for the output); the
 // tensor map views f_out as [rows * nv/16][16] with boxes {16, min(256, nv/16)}, 128-byte swizzle.
-template <int LOGN, bool TMA_OUT, bool CC>
-__global__ void __launch_bounds__(VrowCfg<LOGN>::THREADS, (VrowCfg<LOGN>::THREADS <= 256 ? 2 : 1))
-    vpush_collide_kernel(const __grid_constant__ CUtensorMap out_map, VrowArgs p) {
+// PEER (with TMA_OUT): every row segment travels as one bulk transfer -- cp.async.bulk loads of the 8 nv/P-byte
+// segments of both rows from the P owning ranks into the (still unused) exchange buffer, and one TMA tensor store per
+// rank and row from the solved dense row (out_maps[j] views rank j's buffer); the NVLink sees 4-16 KB requests instead
+// of a warp's 256-byte loads and stores, and the stores leave the load/store pipe.
+template <int LOGN, bool TMA_OUT, bool CC, int TW, bool PEER>
+__device__ __forceinline__ void vrow_body(const CUtensorMap* out_maps, const VrowArgs& p) {
   using K = VrowCfg<LOGN>;
   using C = FftCfg<LOGN>;
   using PC = PhaseCfg<LOGN>;
@@ -76,6 +87,7 @@ __global__ void __launch_bounds__(VrowCfg<LOGN>::THREADS, (VrowCfg<LOGN>::THREAD
   cplx* ph = reinterpret_cast<cplx*>(smem_raw + K::BUF_BYTES);
   double* red = reinterpret_cast<double*>(smem_raw + K::BUF_BYTES + K::PH_BYTES);
   double* pcr = reinterpret_cast<double*>(smem_raw + K::BUF_BYTES + K::PH_BYTES + K::RED_BYTES);
+  uint64_t* ld_bar = reinterpret_cast<uint64_t*>(smem_raw + K::BUF_BYTES + K::PH_BYTES + K::RED_BYTES + K::PCR_BYTES);
   if (TMA_OUT && (smem_u32(smem_raw) & 1023u)) __trap();  // the swizzled tiles need a 1024-byte aligned window
 
   const int t = threadIdx.x < T ? threadIdx.x : 0;  // spare threads (T < 32) shadow thread 0 and never store
@@ -97,7 +109,35 @@ __global__ void __launch_bounds__(VrowCfg<LOGN>::THREADS, (VrowCfg<LOGN>::THREAD
   }
 
   cplx x[E];
-  if (p.nvp_shift >= 0) {
+  if constexpr (PEER) {
+    const size_t nvp = (size_t)1 << p.nvp_shift;
+    double* in_rows = reinterpret_cast<double*>(buf);  // two dense rows [2][N] in the exchange buffer
+    if (threadIdx.x == 0) {
+      mbar_init(ld_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbar_expect_tx(ld_bar, (uint32_t)(2 * N * sizeof(double)));
+      const int np = N >> p.nvp_shift;
+#pragma unroll 1
+      for (int j = 0; j < np; j++) {
+        const double* src = p.in_peer[j] + (size_t)(p.row0_global + row0) * nvp;
+#pragma unroll
+        for (int s2 = 0; s2 < 2; s2++)
+          asm volatile(
+              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                  smem_u32(in_rows + (size_t)s2 * N + j * nvp)),
+              "l"(src + s2 * nvp), "r"((uint32_t)(nvp * sizeof(double))), "r"(smem_u32(ld_bar))
+              : "memory");
+      }
+    }
+    __syncthreads();  // the barrier is initialised before anybody polls it
+    if (live) phase_table_fill<LOGN>(ph, alpha[0], alpha[1], t, T);
+    mbar_wait(ld_bar, 0);
+#pragma unroll
+    for (int m = 0; m < E; m++) {
+      const int e = t + T * m;
+      x[m] = cmake(in_rows[e], in_rows[N + e]);
+    }
+  } else if (p.nvp_shift >= 0) {
     const size_t nvp = (size_t)1 << p.nvp_shift;
 #pragma unroll
     for (int m = 0; m < E; m++) {
@@ -112,10 +152,10 @@ __global__ void __launch_bounds__(VrowCfg<LOGN>::THREADS, (VrowCfg<LOGN>::THREAD
       x[m] = cmake(__ldcs(a_in + e), __ldcs(b_in + e));
     }
   }
-  if (live) phase_table_fill<LOGN>(ph, alpha[0], alpha[1], t, T);  // sincos latency hides behind the loads in flight
-  fft_forward<LOGN>(x, buf, p.tw, t, p.zero);
+  if (!PEER && live) phase_table_fill<LOGN>(ph, alpha[0], alpha[1], t, T);  // sincos latency hides behind the loads in flight
+  fft_forward<LOGN, 1, TW>(x, buf, p.tw, t, p.zero);
   half_spectrum_update<LOGN, 1>(x, buf, ph, t);
-  fft_forward<LOGN>(x, buf, p.tw + p.zero, t, p.zero);
+  fft_forward<LOGN, 1, TW>(x, buf, p.tw + p.zero, t, p.zero);
 
   // registers (e = t + T m) -> chunk-padded rows (cell i at i + i/16); the row buffers alias the exchange buffer
   constexpr int ROW_STRIDE = N + T;  // doubles; (N + T) * 8 bytes is a multiple of 1024 for N >= 2048
@@ -141,10 +181,17 @@ __global__ void __launch_bounds__(VrowCfg<LOGN>::THREADS, (VrowCfg<LOGN>::THREAD
     fp_row_fast<16, TMA_OUT, CC>(row, red, pcr, parity, t, T, N, vc, p.dv, p.dt_fp,
                              __dmul_rn(p.trow ? p.trow[TROW_NU_FP] : p.nu_fp_scale, p.nu_fp[row0 + s]), p.model);
     if (TMA_OUT && threadIdx.x == 0) {  // the barrier that ends fp_row_fast ordered every thread's fenced stores
-      constexpr int BOX = K::OUT_BOX_ROWS;
+      if constexpr (PEER) {  // one box {16, nvp/16} per owning rank
+        const int nvp = 1 << p.nvp_shift, np = N >> p.nvp_shift;
 #pragma unroll 1
-      for (int bx = 0; bx < (N / 16) / BOX; bx++)
-        tma_store_2d(&out_map, row + (size_t)bx * BOX * 16, 0, (int)((row0 + s) * (N / 16)) + bx * BOX);
+        for (int j = 0; j < np; j++)
+          tma_store_2d(&out_maps[j], row + (size_t)j * nvp, 0, (int)((p.row0_global + row0 + s) * (nvp / 16)));
+      } else {
+        constexpr int BOX = K::OUT_BOX_ROWS;
+#pragma unroll 1
+        for (int bx = 0; bx < (N / 16) / BOX; bx++)
+          tma_store_2d(out_maps, row + (size_t)bx * BOX * 16, 0, (int)((row0 + s) * (N / 16)) + bx * BOX);
+      }
       tma_commit_group();
     }
   }
@@ -169,13 +216,25 @@ __global__ void __launch_bounds__(VrowCfg<LOGN>::THREADS, (VrowCfg<LOGN>::THREAD
   }
 }
 
-template <int LOGN, bool TMA_OUT, bool CC>
+template <int LOGN, bool TMA_OUT, bool CC, int TW = 0>
+__global__ void __launch_bounds__(VrowCfg<LOGN>::THREADS, (VrowCfg<LOGN>::THREADS <= 256 ? 2 : 1))
+    vpush_collide_kernel(const __grid_constant__ CUtensorMap out_map, VrowArgs p) {
+  vrow_body<LOGN, TMA_OUT, CC, TW, false>(&out_map, p);
+}
+
+template <int LOGN, bool CC>
+__global__ void __launch_bounds__(VrowCfg<LOGN>::THREADS, (VrowCfg<LOGN>::THREADS <= 256 ? 2 : 1))
+    vpush_collide_peer_kernel(const __grid_constant__ PeerMaps maps, VrowArgs p) {
+  vrow_body<LOGN, true, CC, 0, true>(maps.m, p);
+}
+
+template <int LOGN, bool TMA_OUT, bool CC, int TW = 0>
 static int launch_vrow(const VrowArgs& p, cudaStream_t stream) {
   using K = VrowCfg<LOGN>;
   static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
-  auto kern = vpush_collide_kernel<LOGN, TMA_OUT, CC>;
+  auto kern = vpush_collide_kernel<LOGN, TMA_OUT, CC, TW>;
   if (dev < 64 && !configured[dev]) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
     if (err != cudaSuccess) {
@@ -195,6 +254,43 @@ static int launch_vrow(const VrowArgs& p, cudaStream_t stream) {
   return check_launch("vpush_collide_kernel");
 }
 
+template <int LOGN, bool CC>
+static int launch_vrow_peer(const VrowArgs& p, cudaStream_t stream) {
+  using K = VrowCfg<LOGN>;
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto kern = vpush_collide_peer_kernel<LOGN, CC>;
+  if (dev < 64 && !configured[dev]) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
+    if (err != cudaSuccess) {
+      set_last_error("cudaFuncSetAttribute(vpush_collide_peer, smem=%zu): %s", K::SMEM, cudaGetErrorString(err));
+      return ADEPT_ERR_CUDA;
+    }
+    configured[dev] = true;
+  }
+  PeerMaps maps = {};
+  const int nvp = 1 << p.nvp_shift, np = K::N >> p.nvp_shift;
+  for (int j = 0; j < np; j++) {
+    const int rc = encode_map_2d(&maps.m[j], p.out_peer[j], 16, (unsigned long long)p.nx_global * (nvp / 16), 128, 16,
+                                 nvp / 16, 1);
+    if (rc != ADEPT_OK) return rc;
+  }
+  ProfileScope prof("vpush_collide", stream);
+  kern<<<(unsigned)p.npairs, K::THREADS, K::SMEM, stream>>>(maps, p);
+  return check_launch("vpush_collide_peer_kernel");
+}
+
+// ADEPT_B200_PEER_TMA=0 keeps the per-thread peer loads and stores (A/B timing of the sharded grid)
+static bool peer_tma_enabled() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("ADEPT_B200_PEER_TMA");
+    mode = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return mode == 1;
+}
+
 // TMA output needs 1024-byte aligned row buffers ((nv + nv/16) * 8 bytes apart: nv >= 2048), 16-byte aligned f_out
 // and row coordinates that fit the tensor map's int32 coordinates
 template <int LOGN>
@@ -203,6 +299,24 @@ static int launch_vrow_auto(const VrowArgs& p, cudaStream_t stream) {
   const bool tma_ok = p.nvp_shift < 0 && LOGN >= 11 && tma_available() && (reinterpret_cast<uintptr_t>(p.fout) & 15) == 0 &&
                       (unsigned long long)p.npairs * 2 * (K::N / 16) < (1ull << 31);
   const bool cc = p.scheme == FP_CHANG_COOPER;
+  if constexpr (LOGN >= 11) {  // peer mode with bulk transfers: whole 1 KB-multiple row segments of at most 256 chunks
+    if (p.nvp_shift >= 7 && p.nvp_shift <= 12 && tma_available() && peer_tma_enabled() &&
+        (unsigned long long)p.nx_global * ((1ull << p.nvp_shift) / 16) < (1ull << 31)) {
+      bool aligned = true;
+      for (int j = 0; j < (K::N >> p.nvp_shift); j++)
+        aligned = aligned && ((reinterpret_cast<uintptr_t>(p.in_peer[j]) | reinterpret_cast<uintptr_t>(p.out_peer[j])) & 15) == 0;
+      if (aligned) return cc ? launch_vrow_peer<LOGN, true>(p, stream) : launch_vrow_peer<LOGN, false>(p, stream);
+    }
+  }
+  if constexpr (LOGN == 12) {  // two twiddle loads per pass (fft_core.cuh): 144.3 -> 142.1 us at 4096^2 (r02i);
+    static int vtw = -1;        // ADEPT_B200_VTW=0 selects the six-load passes for A/B timing
+    if (vtw < 0) {
+      const char* e = getenv("ADEPT_B200_VTW");
+      vtw = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    if (tma_ok && vtw == 1)
+      return cc ? launch_vrow<LOGN, true, true, 1>(p, stream) : launch_vrow<LOGN, true, false, 1>(p, stream);
+  }
   if constexpr (LOGN >= 11) {
     if (tma_ok) return cc ? launch_vrow<LOGN, true, true>(p, stream) : launch_vrow<LOGN, true, false>(p, stream);
   }
@@ -245,7 +359,7 @@ int vpush_collide_f64(const double* fin, double* fout, int batch, int nx, int nv
     }
     int sh = 0;
     while ((nv / n_peers) >> (sh + 1)) sh++;
-    p.nvp_shift = sh, p.row0_global = row0_global;
+    p.nvp_shift = sh, p.row0_global = row0_global, p.nx_global = (long long)nx * n_peers;
     for (int j = 0; j < n_peers; j++) p.in_peer[j] = in_peers[j], p.out_peer[j] = out_peers[j];
   }
   switch (logn) {

@@ -353,6 +353,37 @@ def sum_peers(ptrs, n, out):
     return out
 
 
+def vdfdx_field_peers(f, v_loc, dt, k1x, parts, out, peers):
+    """First launch of a sharded-grid step: x-advection of this rank's columns with the charge-density exchange over
+    peer memory and the field solve of the whole grid in the tail (``adept_b200_vdfdx_field_peers_f64``).  ``peers``:
+    dict with the inbox / flag pointers of every rank, this rank's scratch tensors and the driver's host factors (see
+    ``ShardedVlasov1D._setup_p2p``); its ``rho``, ``e`` and ``dex`` tensors are overwritten."""
+    nx, nvl = f.shape
+    fp = _lib.FieldPeers()
+    P = len(peers["share_ptrs"])
+    fp.n_peers, fp.my_rank, fp.epoch = P, int(peers["rank"]), int(peers["epoch"])
+    for r in range(P):
+        fp.share_in[r], fp.flag_in[r] = int(peers["share_ptrs"][r]), int(peers["flag_ptrs"][r])
+    fp.sync_counter = peers["counter"].data_ptr()
+    fp.ion_share = None if peers["ion_share"] is None else _ptr(peers["ion_share"], "ion_share").value
+    fp.dv, fp.charge, fp.dx = float(peers["dv"]), float(peers["charge"]), float(peers["dx"])
+    fp.green, fp.rho, fp.e = (_ptr(peers[k], k).value for k in ("green", "rho", "e"))
+    fp.dex, fp.pond, fp.a_zero = (_ptr(peers[k], k).value for k in ("dex", "pond", "a_zero"))
+    n_ex = len(peers["ex_w"])
+    fp.n_ex = n_ex
+    if n_ex:
+        fp.ex_space, fp.ex_kx = _ptr(peers["ex_space"], "ex_space").value, _ptr(peers["ex_kx"], "ex_kx").value
+        for d in range(n_ex):
+            fp.ex_w[d], fp.ex_a0[d] = float(peers["ex_w"][d]), float(peers["ex_a0"][d])
+            fp.ex_tenv[d], fp.ex_wt[d] = float(peers["ex_tenv"][d]), float(peers["ex_wt"][d])
+    rc = _lib.load().adept_b200_vdfdx_field_peers_f64(_ptr(f, "f"), _ptr(out, "out"), nx, nvl, _ptr(v_loc, "v"),
+                                                      float(dt), float(k1x), _ptr(parts, "parts"), int(parts.shape[0]),
+                                                      C.byref(fp), _stream())
+    _lib.check(rc, "vdfdx_field_peers")
+    _count()
+    return out
+
+
 def ex_driver(ex_space, ex_kx, w, a0, tenv, wt, out=None):
     """dex[i] = sum_d ((tenv[d] space[d, i]) w[d]) a0[d] sin(kx[d, i] - wt[d]) (field.py:21-33), one launch; ex_space /
     ex_kx: [n_ex, n] device tensors (or None when there is no driver), the rest host sequences."""

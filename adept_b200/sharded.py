@@ -186,6 +186,13 @@ class ShardedVlasov1D:
         h_vs, h_st = symm.rendezvous(f_vs, group), symm.rendezvous(f_st, group)
         h_sh = symm.rendezvous(share, group)
         share.zero_()
+        # inboxes of the field tail (adept_b200_vdfdx_field_peers_f64): every rank's share of rho lands here, double-
+        # buffered by the parity of the step count; one flag per sending rank
+        inbox = symm.empty((2 * self.P * self.nx,), dtype=torch.float64, device=self.device)
+        flags = symm.empty((8,), dtype=torch.int64, device=self.device)
+        h_in, h_fl = symm.rendezvous(inbox, group), symm.rendezvous(flags, group)
+        inbox.zero_()
+        flags.zero_()
         f_vs.copy_(self.state[name])
         self.state[name] = f_vs
         nparts = self.lops.ops.vdfdx_rho_parts(f_vs)
@@ -208,6 +215,24 @@ class ShardedVlasov1D:
             "parts": torch.zeros((nparts, self.nx), dtype=torch.float64, device=self.device),
             "token": torch.zeros(1, dtype=torch.float64, device=self.device),
         }
+        # ADEPT_B200_SHARDED_TAIL=0 keeps the separate reduce / exchange / Poisson launches (A/B timing)
+        tail_ok = (self.nx in (1024, 2048, 4096) and self.p2p["symm_sync"]
+                   and os.environ.get("ADEPT_B200_SHARDED_TAIL", "1") != "0" and nvp % 4 == 0)
+        g = self.cfg["grid"]
+        self.p2p["tail"] = None if not tail_ok else {
+            "rank": self.rank, "epoch": 0, "share_ptrs": list(h_in.buffer_ptrs), "flag_ptrs": list(h_fl.buffer_ptrs),
+            "handles": (h_in, h_fl), "inbox": inbox, "flags": flags,
+            "counter": torch.zeros(4, dtype=torch.int32, device=self.device),
+            "ion_share": self.p2p["ion_share"], "dv": float(g["species_grids"][name]["dv"]),
+            "charge": float(g["species_params"][name]["charge"]), "dx": float(g["dx"]), "green": self.p2p["green"],
+            "rho": torch.zeros(self.nx, dtype=torch.float64, device=self.device),
+            "e": torch.zeros(self.nx, dtype=torch.float64, device=self.device),
+            "dex": torch.zeros(self.nx, dtype=torch.float64, device=self.device),
+            "pond": torch.zeros(self.nx, dtype=torch.float64, device=self.device),
+            "a_zero": torch.zeros(self.nx + 2, dtype=torch.float64, device=self.device),
+            "ex_space": self.p2p["ex_space"], "ex_kx": self.p2p["ex_kx"],
+            "ex_w": [d.w0 + d.dw0 for d in self.ex], "ex_a0": [d.a0 for d in self.ex], "ex_tenv": [], "ex_wt": [],
+        }
         dist.barrier(group=self.group)  # every rank's buffers are mapped and initialised before anyone stores into them
 
     def _step_p2p(self):
@@ -215,6 +240,13 @@ class ShardedVlasov1D:
         g, dt, t = self.cfg["grid"], float(self.grid.dt), self.t
         ops, pp, n = self.lops.ops, self.p2p, self.names[0]
         sg, sp = g["species_grids"][n], g["species_params"][n]
+        if pp["tail"] is not None:
+            try:
+                return self._step_p2p_tail()
+            except AdeptB200Error:
+                if pp["tail"]["epoch"] != 1:  # only the very first call may decline (shape / residency); nothing ran yet
+                    raise
+                pp["tail"] = None
         # driver field and collision frequency: same closed forms and rounding order as the reference (field.py:21-26,
         # functions.py:112-118), evaluated on the device from resident space factors -- no host-device copy per step
         dex = torch.empty(self.nx, dtype=torch.float64, device=self.device)
@@ -245,6 +277,29 @@ class ShardedVlasov1D:
             pp["handles"][2].barrier(channel=1)  # every rank's stores into my columns (and its reads of the shares) are done
         else:
             dist.all_reduce(pp["token"], group=self.group)  # every rank's stores into my columns have completed
+        self.state["e"], self.state["de"] = e, dex
+        self.step_index += 1
+        self.t = self.step_index * dt
+        return self.state
+
+    def _step_p2p_tail(self):
+        """The same step as two launches + one barrier: x-push with the peer exchange of the charge density and the field
+        solve in its tail, fused v-row kernel over peer memory, symmetric-memory barrier."""
+        g, dt, t = self.cfg["grid"], float(self.grid.dt), self.t
+        ops, pp, n = self.lops.ops, self.p2p, self.names[0]
+        sg, sp, tl = g["species_grids"][n], g["species_params"][n], self.p2p["tail"]
+        tl["epoch"] += 1
+        tl["ex_tenv"] = [float(d.envelope.time_envelope(t)) for d in self.ex]
+        tl["ex_wt"] = [d.phase(t) for d in self.ex]
+        if not self.ex:
+            tl["dex"].zero_()
+        ops.vdfdx_field_peers(pp["f_vs"], self.v_loc[n], dt, self.k1x, pp["parts"], pp["f_st"], tl)
+        e, dex = tl["e"], tl["dex"]
+        nu_fp = float(self.nu_fp_prof.time_envelope(t)) * pp["nu_fp_space"]
+        ops.vpush_collide_p2p(pp["st_ptrs"], pp["vs_ptrs"], self.rank * self.nxp, self.nxp, pp["nv"], e[self.rows], None,
+                              float(sp["charge"]), float(sp["mass"]), dt, float(sg["kvr"][1]), self.v_full[n],
+                              float(sg["dv"]), nu_fp, model=self.coll.model, dex=dex[self.rows], scheme=self.coll.scheme)
+        pp["handles"][2].barrier(channel=1)  # every rank's stores into my columns are done
         self.state["e"], self.state["de"] = e, dex
         self.step_index += 1
         self.t = self.step_index * dt

@@ -113,6 +113,39 @@ int adept_b200_vpush_collide_p2p_f64(const double* const* in_peers_host, double*
                                      const double* v, double dv, const double* nu_fp, int model, int scheme,
                                      void* stream);
 
+/* Sharded grid, first launch of a step: x-advection of this rank's nv_local velocity columns (SpaceExponential.push,
+ * pushers/vlasov.py:234-251) with the field solve of the WHOLE grid in the tail of the same launch -- what the
+ * reference's shard_map'ed compute_charge_density + SpectralPoissonSolver + LongitudinalElectricFieldDriver do with an
+ * implicit all-reduce (field.py:21-33, 197-224).  Every persistent CTA pushes its slice of the rank's share of the
+ * charge density (ion_share + charge dv sum over the local columns) into all ranks' inboxes over NVLink peer memory,
+ * the rank raises its flag in every inbox, waits for the P flags of its own inbox, adds the P shares in rank order
+ * (bit-identical rho on all ranks) and solves E = green (*) rho redundantly.  No collective library call, no second
+ * launch; flags carry the monotonic step count `epoch` (>= 1, the same on every rank), inboxes are double-buffered by
+ * its parity, so the only other ordering a step needs is one barrier after the v-row kernel.  The launch is
+ * cooperative; it needs nx in {1024, 2048, 4096}, nv_local % 4 == 0 and all CTAs resident. */
+typedef struct adept_b200_field_peers {
+  int n_peers, my_rank;
+  unsigned long long epoch;
+  double* share_in[8];             /* rank r's inbox [2][n_peers][nx], mapped into this process */
+  unsigned long long* flag_in[8];  /* rank r's flags [n_peers], zero before the first step */
+  unsigned int* sync_counter;      /* local zero-initialised word (device-wide barriers of the launch) */
+  const double* ion_share;         /* nullable [nx]: static ion background / n_peers */
+  double dv, charge, dx;
+  const double* green;             /* [nx] Re ifft(-i / kx) */
+  double* rho;                     /* [nx] out */
+  double* e;                       /* [nx] out */
+  double* dex;                     /* [nx] out, written when n_ex > 0 */
+  double* pond;                    /* [nx] out (zero: a_zero is) */
+  const double* a_zero;            /* [nx + 2] zeros: the sharded path carries no transverse wave */
+  int n_ex;
+  const double* ex_space;          /* [n_ex, nx] */
+  const double* ex_kx;             /* [n_ex, nx] */
+  double ex_w[8], ex_a0[8], ex_tenv[8], ex_wt[8];
+} adept_b200_field_peers;
+int adept_b200_vdfdx_field_peers_f64(const double* f_in, double* f_out, int nx, int nv_local, const double* v_local,
+                                     double dt, double k1x, double* parts, int nparts,
+                                     const adept_b200_field_peers* fp, void* stream);
+
 /* out[i] = sum_r peers[r][i], r = 0 .. n_peers-1 in that order (the nx-long all-reduce of the charge density of a
  * sharded grid without a collective library call: every rank reads every rank's share over NVLink peer memory and adds
  * them in rank order, so all ranks hold bit-identical sums).  peers_host: host array of device pointers mapped into

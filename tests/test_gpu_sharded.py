@@ -28,6 +28,8 @@ def _worker(rank, world, port, dk, nsteps, out_path, transpose="nccl"):
         sim.t, sim.step_index = 30.0, 300
         for _ in range(nsteps):
             sim.step()
+        if transpose == "p2p" and sim.nx in (1024, 2048, 4096):  # the two-launch step with the field solve in the tail
+            assert sim.p2p["tail"] is not None and sim.p2p["tail"]["epoch"] == nsteps
         full = sim.gather_full("electron").cpu().numpy()
         if rank == 0:
             np.savez(out_path, f=full, e=sim.state["e"].cpu().numpy())
