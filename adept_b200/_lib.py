@@ -92,6 +92,9 @@ SIGNATURES = {
                                      c_i, c_i, c_dp],
     "adept_b200_vpush_collide_p2p_f64": [C.POINTER(c_dp), C.POINTER(c_dp), c_i, c_ll, c_i, c_i, c_dp, c_dp, c_dp, c_d,
                                          c_d, c_d, c_d, c_dp, c_d, c_dp, c_i, c_i, c_dp],
+    "adept_b200_vpush_collide_p2p_staged_f64": [C.POINTER(c_dp), C.POINTER(c_dp), c_i, c_ll, c_i, c_i, c_dp, c_dp, c_dp,
+                                                c_d, c_d, c_d, c_d, c_dp, c_d, c_dp, c_i, c_i, c_dp, c_dp, c_i, c_ll, c_dp],
+    "adept_b200_copy2d_f64": [c_dp, c_ll, c_dp, c_ll, c_ll, c_ll, c_dp],
     "adept_b200_sum_peers_f64": [C.POINTER(c_dp), c_i, c_ll, c_dp, c_dp],
     "adept_b200_vdfdx_field_peers_f64": [c_dp, c_dp, c_i, c_i, c_dp, c_d, c_d, c_dp, c_i, C.POINTER(FieldPeers), c_dp],
     "adept_b200_save_moments_f64": [c_dp, c_dp, c_d, c_i, c_i, c_i, c_dp, c_d, c_dp, c_dp],

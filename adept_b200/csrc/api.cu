@@ -350,6 +350,41 @@ int adept_b200_vpush_collide_p2p_f64(const double* const* in_peers_host, double*
                            row0_global);
 }
 
+int adept_b200_vpush_collide_p2p_staged_f64(const double* const* in_peers_host, double* const* out_peers_host,
+                                            int n_peers, long long row0_global, int nx, int nv, const double* e,
+                                            const double* dex, const double* pond, double charge, double mass,
+                                            double dt, double k1v, const double* v, double dv, const double* nu_fp,
+                                            int model, int scheme, double* stage, unsigned int* round_counters,
+                                            int n_movers, long long nx_global, void* stream) {
+  ADEPT_REQUIRE(in_peers_host, "in_peers") ADEPT_REQUIRE(out_peers_host, "out_peers") ADEPT_REQUIRE(e, "e")
+  ADEPT_REQUIRE(v, "v") ADEPT_REQUIRE(nu_fp, "nu_fp") ADEPT_REQUIRE(stage, "stage")
+  if (n_movers != 0) ADEPT_REQUIRE(round_counters, "round_counters")
+  for (int j = 0; j < n_peers && j < 8; j++) {
+    ADEPT_REQUIRE(in_peers_host[j], "in_peers[j]") ADEPT_REQUIRE(out_peers_host[j], "out_peers[j]")
+  }
+  return vpush_collide_f64(in_peers_host[0], out_peers_host[0], 1, nx, nv, e, dex, pond, charge, mass, dt, k1v, v, dv,
+                           nu_fp, 1.0, model, scheme, (cudaStream_t)stream, in_peers_host, out_peers_host, n_peers,
+                           row0_global, 0.0, stage, round_counters, n_movers, nx_global);
+}
+
+int adept_b200_copy2d_f64(double* dst, long long dst_pitch, const double* src, long long src_pitch, long long width,
+                          long long height, void* stream) {
+  ADEPT_REQUIRE(dst, "dst") ADEPT_REQUIRE(src, "src")
+  if (width < 1 || height < 1 || dst_pitch < width || src_pitch < width) {
+    set_last_error("copy2d: width=%lld height=%lld dst_pitch=%lld src_pitch=%lld", width, height, dst_pitch, src_pitch);
+    return ADEPT_ERR_BAD_SHAPE;
+  }
+  cudaError_t err = cudaMemcpy2DAsync(dst, (size_t)dst_pitch * sizeof(double), src, (size_t)src_pitch * sizeof(double),
+                                      (size_t)width * sizeof(double), (size_t)height, cudaMemcpyDeviceToDevice,
+                                      (cudaStream_t)stream);
+  if (err != cudaSuccess) {
+    set_last_error("copy2d: cudaMemcpy2DAsync: %s", cudaGetErrorString(err));
+    (void)cudaGetLastError();
+    return ADEPT_ERR_CUDA;
+  }
+  return ADEPT_OK;
+}
+
 int adept_b200_interp2d_f64(const double* f0, const double* f1, double w, int nx, int nv, const double* x,
                             const double* v, const double* xq, const double* vq, int nxq, int nvq, double* out,
                             void* stream) {

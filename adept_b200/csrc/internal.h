@@ -82,7 +82,9 @@ int vpush_collide_f64(const double* fin, double* fout, int batch, int nx, int nv
                       const double* pond, double q, double m, double dt, double k1v, const double* v, double dv,
                       const double* nu_fp, double nu_fp_scale, int model, int scheme, cudaStream_t stream,
                       const double* const* in_peers = nullptr, double* const* out_peers = nullptr, int n_peers = 0,
-                      long long row0_global = 0, double dt_fp = 0.0 /* collision time step; 0: the same as dt */);
+                      long long row0_global = 0, double dt_fp = 0.0 /* collision time step; 0: the same as dt */,
+                      double* stage = nullptr, unsigned int* round_ctr = nullptr, int n_movers = 0,
+                      long long nx_global = 0);
 bool tma_available();
 int encode_map_2d(CUtensorMap* map, const double* base, unsigned long long dim0, unsigned long long dim1,
                   unsigned long long pitch_bytes, unsigned box0, unsigned box1, int swizzle128);

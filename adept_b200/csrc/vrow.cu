@@ -46,6 +46,14 @@ struct VrowArgs {
   int nvp_shift;
   long long row0_global;
   long long nx_global;  // rows of every rank's v-sharded buffer
+  // Staged peer input (PEER instantiation, stage != null): the first n_movers CTAs of the grid do no arithmetic; they
+  // gather the rank's rows from the owning ranks into stage[nx_local][nv] (bulk loads over NVLink into shared memory,
+  // one bulk store per row), row m + i n_movers by mover m in round i, and count themselves into round_ctr[i] when the
+  // row has landed.  The compute CTA of a row pair waits for its round and bulk-loads the pair from the stage -- the
+  // NVLink latency of a pair's input no longer sits between that CTA's launch and its arithmetic.
+  double* stage;
+  unsigned int* round_ctr;
+  int n_movers;
 };
 
 // Peer mode with bulk transfers (PEER instantiation): the tensor maps of the P output buffers, one per rank
@@ -77,7 +85,7 @@ struct VrowCfg {
 // rank and row from the solved dense row (out_maps[j] views rank j's buffer); the NVLink sees 4-16 KB requests instead
 // of a warp's 256-byte loads and stores, and the stores leave the load/store pipe.
 template <int LOGN, bool TMA_OUT, bool CC, int TW, bool PEER>
-__device__ __forceinline__ void vrow_body(const CUtensorMap* out_maps, const VrowArgs& p) {
+__device__ __forceinline__ void vrow_body(const CUtensorMap* out_maps, const VrowArgs& p, const long long pair) {
   using K = VrowCfg<LOGN>;
   using C = FftCfg<LOGN>;
   using PC = PhaseCfg<LOGN>;
@@ -92,7 +100,7 @@ __device__ __forceinline__ void vrow_body(const CUtensorMap* out_maps, const Vro
 
   const int t = threadIdx.x < T ? threadIdx.x : 0;  // spare threads (T < 32) shadow thread 0 and never store
   const bool live = threadIdx.x < T;
-  const long long row0 = 2 * (long long)blockIdx.x;
+  const long long row0 = 2 * pair;
   const double* a_in = p.fin + row0 * N;
   const double* b_in = a_in + N;
 
@@ -116,17 +124,32 @@ __device__ __forceinline__ void vrow_body(const CUtensorMap* out_maps, const Vro
       mbar_init(ld_bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       mbar_expect_tx(ld_bar, (uint32_t)(2 * N * sizeof(double)));
-      const int np = N >> p.nvp_shift;
+      if (p.stage) {  // both rows are adjacent in the stage: one bulk load, once the movers have landed their round
+        if (p.n_movers > 0) {  // (n_movers == 0: the caller filled the stage before the launch, e.g. by copy engines)
+          const unsigned int* ctr = p.round_ctr + row0 / p.n_movers;
+          unsigned int seen;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+          } while (seen < (unsigned int)p.n_movers);
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(in_rows)),
+                     "l"(p.stage + (size_t)row0 * N), "r"((uint32_t)(2 * N * sizeof(double))), "r"(smem_u32(ld_bar))
+                     : "memory");
+      } else {
+        const int np = N >> p.nvp_shift;
 #pragma unroll 1
-      for (int j = 0; j < np; j++) {
-        const double* src = p.in_peer[j] + (size_t)(p.row0_global + row0) * nvp;
+        for (int j = 0; j < np; j++) {
+          const double* src = p.in_peer[j] + (size_t)(p.row0_global + row0) * nvp;
 #pragma unroll
-        for (int s2 = 0; s2 < 2; s2++)
-          asm volatile(
-              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                  smem_u32(in_rows + (size_t)s2 * N + j * nvp)),
-              "l"(src + s2 * nvp), "r"((uint32_t)(nvp * sizeof(double))), "r"(smem_u32(ld_bar))
-              : "memory");
+          for (int s2 = 0; s2 < 2; s2++)
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                    smem_u32(in_rows + (size_t)s2 * N + j * nvp)),
+                "l"(src + s2 * nvp), "r"((uint32_t)(nvp * sizeof(double))), "r"(smem_u32(ld_bar))
+                : "memory");
+        }
       }
     }
     __syncthreads();  // the barrier is initialised before anybody polls it
@@ -219,13 +242,68 @@ __device__ __forceinline__ void vrow_body(const CUtensorMap* out_maps, const Vro
 template <int LOGN, bool TMA_OUT, bool CC, int TW = 0>
 __global__ void __launch_bounds__(VrowCfg<LOGN>::THREADS, (VrowCfg<LOGN>::THREADS <= 256 ? 2 : 1))
     vpush_collide_kernel(const __grid_constant__ CUtensorMap out_map, VrowArgs p) {
-  vrow_body<LOGN, TMA_OUT, CC, TW, false>(&out_map, p);
+  vrow_body<LOGN, TMA_OUT, CC, TW, false>(&out_map, p, (long long)blockIdx.x);
+}
+
+// Mover CTA of the staged peer mode (VrowArgs::stage): one thread drives a two-slot pipeline of whole rows,
+// L(i) = P bulk loads of row m + i n_movers from the owning ranks into slot i & 1, S(i) = one bulk store of the slot
+// into the stage; round_ctr[i] is raised when S(i) has completed.
+template <int LOGN>
+__device__ __forceinline__ void vrow_mover(const VrowArgs& p) {
+  constexpr int N = 1 << LOGN;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  if (threadIdx.x != 0) return;
+  double* slots = reinterpret_cast<double*>(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)2 * N * sizeof(double));
+  mbar_init(&bars[0], 1);
+  mbar_init(&bars[1], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  const size_t nvp = (size_t)1 << p.nvp_shift;
+  const int np = N >> p.nvp_shift, nm = p.n_movers, m = blockIdx.x;
+  const int rounds = (int)(2 * p.npairs / nm);
+  for (int i = 0; i <= rounds + 1; i++) {
+    if (i < rounds) {  // L(i): the slot's previous row (i - 2) must have been read out by its store
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      const int sl = i & 1;
+      const long long row = m + (long long)i * nm;
+      mbar_expect_tx(&bars[sl], (uint32_t)(N * sizeof(double)));
+#pragma unroll 1
+      for (int j = 0; j < np; j++)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(slots + (size_t)sl * N + j * nvp)),
+                     "l"(p.in_peer[j] + (size_t)(p.row0_global + row) * nvp), "r"((uint32_t)(nvp * sizeof(double))),
+                     "r"(smem_u32(&bars[sl]))
+                     : "memory");
+    }
+    if (i >= 1 && i - 1 < rounds) {  // S(i - 1)
+      const int sl = (i - 1) & 1;
+      mbar_wait(&bars[sl], (uint32_t)(((i - 1) >> 1) & 1));
+      const long long row = m + (long long)(i - 1) * nm;
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.stage + (size_t)row * N),
+                   "r"(smem_u32(slots + (size_t)sl * N)), "r"((uint32_t)(N * sizeof(double)))
+                   : "memory");
+      tma_commit_group();
+    }
+    if (i >= 2) {  // S(i - 2) has completed (at most S(i - 1) may still be pending): its round may start
+      if (i - 1 < rounds)
+        asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+      else
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      asm volatile("fence.proxy.async;" ::: "memory");
+      __threadfence();
+      atomicAdd(p.round_ctr + (i - 2), 1u);
+    }
+  }
 }
 
 template <int LOGN, bool CC>
 __global__ void __launch_bounds__(VrowCfg<LOGN>::THREADS, (VrowCfg<LOGN>::THREADS <= 256 ? 2 : 1))
     vpush_collide_peer_kernel(const __grid_constant__ PeerMaps maps, VrowArgs p) {
-  vrow_body<LOGN, true, CC, 0, true>(maps.m, p);
+  if (p.stage && p.n_movers > 0 && (int)blockIdx.x < p.n_movers) {  // the lowest block indices are dispatched first: movers are resident
+    vrow_mover<LOGN>(p);                          // before any compute CTA can wait for them
+    return;
+  }
+  vrow_body<LOGN, true, CC, 0, true>(maps.m, p, (long long)blockIdx.x - ((p.stage && p.n_movers > 0) ? p.n_movers : 0));
 }
 
 template <int LOGN, bool TMA_OUT, bool CC, int TW = 0>
@@ -276,8 +354,18 @@ static int launch_vrow_peer(const VrowArgs& p, cudaStream_t stream) {
                                  nvp / 16, 1);
     if (rc != ADEPT_OK) return rc;
   }
+  unsigned grid = (unsigned)p.npairs;
+  if (p.stage && p.n_movers > 0) {
+    const int rounds = (int)(2 * p.npairs / p.n_movers);
+    cudaError_t err = cudaMemsetAsync(p.round_ctr, 0, (size_t)rounds * sizeof(unsigned int), stream);
+    if (err != cudaSuccess) {
+      set_last_error("vpush_collide(peer, staged): cudaMemsetAsync: %s", cudaGetErrorString(err));
+      return ADEPT_ERR_CUDA;
+    }
+    grid += (unsigned)p.n_movers;
+  }
   ProfileScope prof("vpush_collide", stream);
-  kern<<<(unsigned)p.npairs, K::THREADS, K::SMEM, stream>>>(maps, p);
+  kern<<<grid, K::THREADS, K::SMEM, stream>>>(maps, p);
   return check_launch("vpush_collide_peer_kernel");
 }
 
@@ -333,7 +421,7 @@ int vpush_collide_f64(const double* fin, double* fout, int batch, int nx, int nv
                       const double* pond, double q, double m, double dt, double k1v, const double* v, double dv,
                       const double* nu_fp, double nu_fp_scale, int model, int scheme, cudaStream_t stream,
                       const double* const* in_peers, double* const* out_peers, int n_peers, long long row0_global,
-                      double dt_fp) {
+                      double dt_fp, double* stage, unsigned int* round_ctr, int n_movers, long long nx_global) {
   if (batch < 1 || !vpush_collide_supported(nx, nv, model, scheme, 0)) {
     set_last_error("vpush_collide: unsupported shape batch=%d nx=%d nv=%d / model=%d scheme=%d", batch, nx, nv, model,
                    scheme);
@@ -359,7 +447,21 @@ int vpush_collide_f64(const double* fin, double* fout, int batch, int nx, int nv
     }
     int sh = 0;
     while ((nv / n_peers) >> (sh + 1)) sh++;
-    p.nvp_shift = sh, p.row0_global = row0_global, p.nx_global = (long long)nx * n_peers;
+    p.nvp_shift = sh, p.row0_global = row0_global, p.nx_global = nx_global > 0 ? nx_global : (long long)nx * n_peers;
+    if (row0_global < 0 || row0_global + nx > p.nx_global) {
+      set_last_error("vpush_collide(peer mode): rows [%lld, %lld) outside the %lld rows of the grid", row0_global,
+                     row0_global + nx, p.nx_global);
+      return ADEPT_ERR_BAD_ARG;
+    }
+    if (stage) {
+      const bool movers_ok = n_movers == 0 || (round_ctr && n_movers >= 2 && !(n_movers & 1) && nx % n_movers == 0);
+      if (!movers_ok || nv < 2048 || !tma_available() || !peer_tma_enabled() || sh < 7) {
+        set_last_error("vpush_collide(peer, staged): needs round counters, an even number of movers dividing the %d "
+                       "local rows (got %d), nv >= 2048 and the bulk-transfer peer path", nx, n_movers);
+        return ADEPT_ERR_UNSUPPORTED;
+      }
+      p.stage = stage, p.round_ctr = round_ctr, p.n_movers = n_movers;
+    }
     for (int j = 0; j < n_peers; j++) p.in_peer[j] = in_peers[j], p.out_peer[j] = out_peers[j];
   }
   switch (logn) {

@@ -122,10 +122,22 @@ def _peer_array(ptrs):
 
 
 def vpush_collide_p2p(in_ptrs, out_ptrs, row0_global, nx_local, nv, e, pond, q, m, dt, k1v, v, dv, nu_fp, model=1,
-                      dex=None, scheme=0):
+                      dex=None, scheme=0, stage=None, round_counters=None, n_movers=0, nx_global=0):
     """Fused v-advection + Fokker-Planck step of this rank's ``nx_local`` rows of a grid whose buffers are all
     v-sharded ``[nx, nv / P]``: cells are read from and written to the owning ranks' buffers over peer memory
-    (``in_ptrs`` / ``out_ptrs``: one device pointer per rank)."""
+    (``in_ptrs`` / ``out_ptrs``: one device pointer per rank).  With ``stage`` ([nx_local, nv] scratch) and
+    ``round_counters`` (int32 [nx_local / n_movers]) the input rows are gathered by ``n_movers`` mover CTAs of the same
+    launch (``adept_b200_vpush_collide_p2p_staged_f64``)."""
+    if stage is not None:
+        rc = _lib.load().adept_b200_vpush_collide_p2p_staged_f64(
+            _peer_array(in_ptrs), _peer_array(out_ptrs), len(out_ptrs), int(row0_global), int(nx_local), int(nv),
+            _ptr(e, "e"), _ptr(dex, "dex", True), _ptr(pond, "pond", True), float(q), float(m), float(dt), float(k1v),
+            _ptr(v, "v"), float(dv), _ptr(nu_fp, "nu_fp"), int(model), int(scheme), _ptr(stage, "stage"),
+            None if round_counters is None else C.c_void_p(round_counters.data_ptr()), int(n_movers), int(nx_global),
+            _stream())
+        _lib.check(rc, "vpush_collide_p2p_staged")
+        _count()
+        return
     rc = _lib.load().adept_b200_vpush_collide_p2p_f64(
         _peer_array(in_ptrs), _peer_array(out_ptrs), len(out_ptrs), int(row0_global), int(nx_local), int(nv),
         _ptr(e, "e"), _ptr(dex, "dex", True), _ptr(pond, "pond", True), float(q), float(m), float(dt), float(k1v),
@@ -343,6 +355,14 @@ def vdfdx_rho(f, v, dt, k1x, parts, out=None, k1x_batch=None):
     _lib.check(rc, "vdfdx_rho")
     _count(2)
     return out
+
+
+def copy2d(dst_ptr, dst_pitch, src_ptr, src_pitch, width, height):
+    """``height`` rows of ``width`` doubles from ``src_ptr`` to ``dst_ptr`` (raw device addresses, pitches in doubles) as
+    one copy-engine transfer on the current stream; ``src_ptr`` may be a peer-mapped buffer."""
+    rc = _lib.load().adept_b200_copy2d_f64(C.c_void_p(int(dst_ptr)), int(dst_pitch), C.c_void_p(int(src_ptr)),
+                                           int(src_pitch), int(width), int(height), _stream())
+    _lib.check(rc, "copy2d")
 
 
 def sum_peers(ptrs, n, out):

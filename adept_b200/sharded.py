@@ -215,6 +215,33 @@ class ShardedVlasov1D:
             "parts": torch.zeros((nparts, self.nx), dtype=torch.float64, device=self.device),
             "token": torch.zeros(1, dtype=torch.float64, device=self.device),
         }
+        # ADEPT_B200_SHARDED_CE=c (chunks; default 0 = off): copy engines gather the rank's rows from the owning ranks into
+        # an x-sharded stage chunk by chunk on a second stream while the v-row kernel works on the previous chunk.
+        # Measured on 2 GPUs (r02n): 290 us per step with 4 chunks, 459 us with 8, against 218 us with the peer transfers
+        # inside the kernel -- a chunk of 512 rows is less than one wave of CTAs, and each chunk costs P copy calls.
+        ce = int(os.environ.get("ADEPT_B200_SHARDED_CE", "0"))
+        while ce > 1 and (self.nxp % ce or (self.nxp // ce) & 1):
+            ce //= 2
+        self.p2p["ce_chunks"] = ce if (ce >= 1 and nv >= 2048 and self.nxp % 2 == 0) else 0
+        if self.p2p["ce_chunks"]:
+            self.p2p["copy_stream"] = torch.cuda.Stream(device=self.device)
+            self.p2p["ev_start"] = torch.cuda.Event()
+            self.p2p["ev_in"] = [torch.cuda.Event() for _ in range(ce)]
+        # ADEPT_B200_SHARDED_MOVERS=n (default 0 = off; measured slower: 32 movers 203 us against 120 us for the v-row
+        # kernel on 2 GPUs -- the two-slot pipelines hold too few bytes in flight): mover CTAs of the v-row kernel gather
+        nm = int(os.environ.get("ADEPT_B200_SHARDED_MOVERS", "0"))
+        while nm > 0 and (self.nxp % nm or nm & 1):
+            nm //= 2
+        if self.p2p["ce_chunks"]:
+            nm = 0
+            self.p2p["stage"] = torch.empty((self.nxp, nv), dtype=torch.float64, device=self.device)
+            self.p2p["round_ctr"], self.p2p["n_movers"] = None, 0
+        elif nm >= 2 and nv >= 2048:
+            self.p2p["stage"] = torch.empty((self.nxp, nv), dtype=torch.float64, device=self.device)
+            self.p2p["round_ctr"] = torch.zeros(self.nxp // nm, dtype=torch.int32, device=self.device)
+            self.p2p["n_movers"] = nm
+        else:
+            self.p2p["stage"], self.p2p["round_ctr"], self.p2p["n_movers"] = None, None, 0
         # ADEPT_B200_SHARDED_TAIL=0 keeps the separate reduce / exchange / Poisson launches (A/B timing)
         tail_ok = (self.nx in (1024, 2048, 4096) and self.p2p["symm_sync"]
                    and os.environ.get("ADEPT_B200_SHARDED_TAIL", "1") != "0" and nvp % 4 == 0)
@@ -272,7 +299,9 @@ class ShardedVlasov1D:
         nu_fp = float(self.nu_fp_prof.time_envelope(t)) * pp["nu_fp_space"]
         ops.vpush_collide_p2p(pp["st_ptrs"], pp["vs_ptrs"], self.rank * self.nxp, self.nxp, pp["nv"], e_loc, None,
                               float(sp["charge"]), float(sp["mass"]), dt, float(sg["kvr"][1]), self.v_full[n],
-                              float(sg["dv"]), nu_fp, model=self.coll.model, dex=dex_loc, scheme=self.coll.scheme)
+                              float(sg["dv"]), nu_fp, model=self.coll.model, dex=dex_loc, scheme=self.coll.scheme,
+                              stage=pp["stage"] if pp["n_movers"] else None, round_counters=pp["round_ctr"],
+                              n_movers=pp["n_movers"])
         if pp["symm_sync"]:
             pp["handles"][2].barrier(channel=1)  # every rank's stores into my columns (and its reads of the shares) are done
         else:
@@ -296,14 +325,47 @@ class ShardedVlasov1D:
         ops.vdfdx_field_peers(pp["f_vs"], self.v_loc[n], dt, self.k1x, pp["parts"], pp["f_st"], tl)
         e, dex = tl["e"], tl["dex"]
         nu_fp = float(self.nu_fp_prof.time_envelope(t)) * pp["nu_fp_space"]
-        ops.vpush_collide_p2p(pp["st_ptrs"], pp["vs_ptrs"], self.rank * self.nxp, self.nxp, pp["nv"], e[self.rows], None,
-                              float(sp["charge"]), float(sp["mass"]), dt, float(sg["kvr"][1]), self.v_full[n],
-                              float(sg["dv"]), nu_fp, model=self.coll.model, dex=dex[self.rows], scheme=self.coll.scheme)
+        if pp["ce_chunks"]:
+            self._vpush_ce(e[self.rows], dex[self.rows], nu_fp)
+        else:
+            ops.vpush_collide_p2p(pp["st_ptrs"], pp["vs_ptrs"], self.rank * self.nxp, self.nxp, pp["nv"], e[self.rows],
+                                  None, float(sp["charge"]), float(sp["mass"]), dt, float(sg["kvr"][1]), self.v_full[n],
+                                  float(sg["dv"]), nu_fp, model=self.coll.model, dex=dex[self.rows],
+                                  scheme=self.coll.scheme, stage=pp["stage"], round_counters=pp["round_ctr"],
+                                  n_movers=pp["n_movers"])
         pp["handles"][2].barrier(channel=1)  # every rank's stores into my columns are done
         self.state["e"], self.state["de"] = e, dex
         self.step_index += 1
         self.t = self.step_index * dt
         return self.state
+
+    def _vpush_ce(self, e_loc, dex_loc, nu_fp):
+        """v-row kernel over my rows in chunks; the copy engines gather chunk c + 1 (one strided copy per owning rank, over
+        NVLink for the others) while the SMs work on chunk c.  Results leave the kernel as TMA stores to the owners."""
+        g, dt = self.cfg["grid"], float(self.grid.dt)
+        ops, pp, n = self.lops.ops, self.p2p, self.names[0]
+        sg, sp = g["species_grids"][n], g["species_params"][n]
+        C_, nv, nvp = pp["ce_chunks"], pp["nv"], self.nvp[n]
+        nc = self.nxp // C_
+        main, cs = torch.cuda.current_stream(), pp["copy_stream"]
+        pp["ev_start"].record(main)  # the x-push of every rank has completed (flag exchange in its tail)
+        cs.wait_event(pp["ev_start"])
+        stage = pp["stage"]
+        with torch.cuda.stream(cs):
+            for c in range(C_):
+                r0 = self.rank * self.nxp + c * nc
+                for dj in range(self.P):  # start with the next rank: the ranks' reads spread over the links
+                    j = (self.rank + 1 + dj) % self.P
+                    ops.copy2d(stage.data_ptr() + (c * nc * nv + j * nvp) * 8, nv, int(pp["st_ptrs"][j]) + r0 * nvp * 8,
+                               nvp, nvp, nc)
+                pp["ev_in"][c].record(cs)
+        for c in range(C_):
+            main.wait_event(pp["ev_in"][c])
+            rows = slice(c * nc, (c + 1) * nc)
+            ops.vpush_collide_p2p(pp["st_ptrs"], pp["vs_ptrs"], self.rank * self.nxp + c * nc, nc, nv, e_loc[rows], None,
+                                  float(sp["charge"]), float(sp["mass"]), dt, float(sg["kvr"][1]), self.v_full[n],
+                                  float(sg["dv"]), nu_fp[rows], model=self.coll.model, dex=dex_loc[rows],
+                                  scheme=self.coll.scheme, stage=stage[rows], n_movers=0, nx_global=self.nx)
 
     # ---- layout changes -------------------------------------------------------------------------------------------
     def to_x_sharded(self, f_vs):

@@ -113,6 +113,27 @@ int adept_b200_vpush_collide_p2p_f64(const double* const* in_peers_host, double*
                                      const double* v, double dv, const double* nu_fp, int model, int scheme,
                                      void* stream);
 
+/* The same with the rank's input rows gathered by dedicated mover CTAs of the same launch: the first n_movers CTAs
+ * (even, dividing nx) bulk-load whole rows from the owning ranks through shared memory into stage[nx, nv] (local
+ * scratch) and raise round_counters[i] (nx / n_movers unsigned ints, zeroed by the call) when round i has landed; the
+ * compute CTA of a row pair waits for its round and bulk-loads the pair from the stage, so a pair's NVLink latency no
+ * longer sits between its CTA's start and its arithmetic (2 CTAs per SM cannot hide it otherwise).  Results still leave
+ * as one TMA tensor store per rank and row.  Needs nv >= 2048.  n_movers = 0: the caller has filled the stage before
+ * the launch (adept_b200_copy2d_f64 on a copy stream, chunk by chunk, while earlier chunks compute).  nx = rows of this
+ * call, nx_global = rows of the ranks' buffers (0: nx * n_peers). */
+int adept_b200_vpush_collide_p2p_staged_f64(const double* const* in_peers_host, double* const* out_peers_host,
+                                            int n_peers, long long row0_global, int nx, int nv, const double* e,
+                                            const double* dex, const double* pond, double charge, double mass,
+                                            double dt, double k1v, const double* v, double dv, const double* nu_fp,
+                                            int model, int scheme, double* stage, unsigned int* round_counters,
+                                            int n_movers, long long nx_global, void* stream);
+
+/* Strided device-to-device copy of `height` rows of `width` doubles (pitches in doubles), enqueued on `stream` as one
+ * cudaMemcpy2DAsync: it runs on a copy engine, over NVLink when src is a peer-mapped buffer, and takes no SM.  The
+ * sharded grid gathers the v-sharded row blocks of the other ranks into its x-sharded stage with it. */
+int adept_b200_copy2d_f64(double* dst, long long dst_pitch, const double* src, long long src_pitch, long long width,
+                          long long height, void* stream);
+
 /* Sharded grid, first launch of a step: x-advection of this rank's nv_local velocity columns (SpaceExponential.push,
  * pushers/vlasov.py:234-251) with the field solve of the WHOLE grid in the tail of the same launch -- what the
  * reference's shard_map'ed compute_charge_density + SpectralPoissonSolver + LongitudinalElectricFieldDriver do with an
