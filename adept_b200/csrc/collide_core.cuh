@@ -107,26 +107,41 @@ __device__ __forceinline__ void row_reduce(double (&val)[NVAL], double* red, int
 // chunk c at j ^ (c & 7)): the layout a TMA tensor store with CU_TENSOR_MAP_SWIZZLE_128B reads, conflict-free for the
 // 16-byte stores of a warp; rowbuf must then be 1024-byte aligned.  Each thread fences its stores for the async proxy.
 // CC: Chang-Cooper weighting of the drag term instead of central differencing.
-template <int E, bool DENSE_OUT = false, bool CC = false>
-__device__ __forceinline__ void fp_row_fast(double* rowbuf, double* red, double* pcr, int& parity, int tt,
-                                            int T, int nv, double vc, double dv, double dt, double nu, int model) {
-  const bool warp_mode = (T & 31) == 0;
-  const int i0 = E * tt;
-  const double* chunk = rowbuf + i0 + tt;
-  double mom[3] = {0.0, 0.0, 0.0};
+// Velocity moments of the calling thread's chunk of a chunk-padded row: {sum f, sum f v, sum f v^2} with v = vc + l dv
+// (index-space sums, shifted once).  Callers reduce them over the row with row_reduce.
+template <int E>
+__device__ __forceinline__ void fp_chunk_moments(const double* rowbuf, int tt, double vc, double dv, double* mom) {
+  const double* chunk = rowbuf + E * tt + tt;
+  double m0 = 0.0, m1 = 0.0, m2 = 0.0;
 #pragma unroll
   for (int l = 0; l < E; l++) {
     const double fl = chunk[l];
-    mom[0] += fl;
-    mom[1] = fma(fl, (double)l, mom[1]);
-    mom[2] = fma(fl, (double)(l * l), mom[2]);
+    m0 += fl;
+    m1 = fma(fl, (double)l, m1);
+    m2 = fma(fl, (double)(l * l), m2);
   }
-  {
-    const double m0 = mom[0], m1 = mom[1] * dv, m2 = mom[2] * (dv * dv);
-    mom[1] = fma(vc, m0, m1);
-    mom[2] = fma(vc * vc, m0, fma(2.0 * vc, m1, m2));
+  m1 *= dv, m2 *= dv * dv;
+  mom[0] = m0;
+  mom[1] = fma(vc, m0, m1);
+  mom[2] = fma(vc * vc, m0, fma(2.0 * vc, m1, m2));
+}
+
+// `sums` (nullable): the row's three moments, already reduced over the row by the caller (the fused v-row kernel
+// reduces both rows of its pair behind one barrier).
+template <int E, bool DENSE_OUT = false, bool CC = false>
+__device__ __forceinline__ void fp_row_fast(double* rowbuf, double* red, double* pcr, int& parity, int tt,
+                                            int T, int nv, double vc, double dv, double dt, double nu, int model,
+                                            const double* sums = nullptr) {
+  const bool warp_mode = (T & 31) == 0;
+  const int i0 = E * tt;
+  const double* chunk = rowbuf + i0 + tt;
+  double mom[3];
+  if (sums) {
+    mom[0] = sums[0], mom[1] = sums[1], mom[2] = sums[2];
+  } else {
+    fp_chunk_moments<E>(rowbuf, tt, vc, dv, mom);
+    row_reduce<3>(mom, red, parity, 0, tt, T, T, warp_mode, true);
   }
-  row_reduce<3>(mom, red, parity, 0, tt, T, T, warp_mode, true);
   const double s0 = mom[0], s1 = mom[1], s2 = mom[2];
   const double vbar = (model == FP_LB) ? 0.0 : s1 / s0;
   const double Temp = (s2 - 2.0 * vbar * s1 + vbar * vbar * s0) / s0;

@@ -10,6 +10,8 @@
 // phase factors (Im of DC/Nyquist dropped exactly like irfft does), recombined, and transformed back with the
 // same forward kernel (swap trick).  Phase factors exp(-i m alpha) are built from two small per-sequence tables
 // (m = 64*hi + lo) so no sincos is evaluated per element.
+#include <stdlib.h>
+
 #include "internal.h"
 #include "push_core.cuh"
 
@@ -49,7 +51,7 @@ struct PushArgs {
   const double* filt;  // nullable [N/2+1]: real multiplier per mode (Hou-Li filter)
 };
 
-template <int LOGN, int AXIS>
+template <int LOGN, int AXIS, int TW = 0>
 __global__ void __launch_bounds__(PushCfg<LOGN, AXIS>::THREADS, (PushCfg<LOGN, AXIS>::THREADS <= 256 ? 2 : 1))
     spectral_push_kernel(PushArgs p) {
   using C = FftCfg<LOGN>;
@@ -129,11 +131,11 @@ __global__ void __launch_bounds__(PushCfg<LOGN, AXIS>::THREADS, (PushCfg<LOGN, A
   // after the loads are in flight: the sincos latency of the filling warps hides behind the HBM latency of the loads
   phase_table_fill<LOGN>(ph, alpha_a, alpha_b, t, T);
 
-  fft_forward<LOGN>(x, buf, p.tw, t, p.zero);
+  fft_forward<LOGN, 1, TW>(x, buf, p.tw, t, p.zero);
 
   half_spectrum_update<LOGN, 1>(x, buf, ph, t, p.filt);
 
-  fft_forward<LOGN>(x, buf, p.tw + p.zero, t, p.zero);  // opaque offset: no CSE of twiddle loads with the first FFT
+  fft_forward<LOGN, 1, TW>(x, buf, p.tw + p.zero, t, p.zero);  // opaque offset: no CSE of twiddle loads with the first FFT
 
   // ---- store: a'[e] = Im, b'[e] = Re of the swapped result ---------------------------------------------
   if (active) {
@@ -156,13 +158,13 @@ __global__ void __launch_bounds__(PushCfg<LOGN, AXIS>::THREADS, (PushCfg<LOGN, A
   }
 }
 
-template <int LOGN, int AXIS>
+template <int LOGN, int AXIS, int TW = 0>
 static int launch_push(const PushArgs& p, cudaStream_t stream) {
   using K = PushCfg<LOGN, AXIS>;
   static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
-  auto kern = spectral_push_kernel<LOGN, AXIS>;
+  auto kern = spectral_push_kernel<LOGN, AXIS, TW>;
   if (dev < 64 && !configured[dev]) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
     if (err != cudaSuccess) {
@@ -177,8 +179,20 @@ static int launch_push(const PushArgs& p, cudaStream_t stream) {
   return check_launch("spectral_push_kernel");
 }
 
+// The nv = 4096 v-advection runs with two twiddle loads per pass (fft_core.cuh TW = 1): 98.3 -> 96.3 us (r02s);
+// ADEPT_B200_PTW=0 selects the six-load passes for A/B timing
+static bool push_tw1() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("ADEPT_B200_PTW");
+    mode = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return mode == 1;
+}
+
 template <int AXIS>
 static int dispatch_push(int logn, const PushArgs& p, cudaStream_t stream) {
+  if (AXIS == AXIS_V && logn == 12 && push_tw1()) return launch_push<12, AXIS, 1>(p, stream);
   switch (logn) {
 #define ADEPT_CASE(L) \
   case L:             \

@@ -279,12 +279,14 @@ int reduce_parts_f64(const double* parts, int nparts, long long n, double scale_
 // log1p(r) is its Taylor polynomial through r^8 (next term < 1.2e-20).  Zero, subnormals, inf and NaN take the library
 // path (log(0) = -inf must survive: -|f| log|f| is NaN at f = 0 in the reference too).
 __device__ __noinline__ double slow_log(double ax) { return log(ax); }  // out of line: keeps the streaming loop small
-__device__ __forceinline__ double fast_log_pos(double ax, const double2* __restrict__ tab) {
-  const long long bits = __double_as_longlong(ax);
-  const int hi = (int)(bits >> 32);
-  if ((unsigned)(hi - 0x00100000) >= (unsigned)(0x7ff00000 - 0x00100000)) return slow_log(ax);
+// true for zero, subnormals, inf and NaN (ax >= 0): everything the table path does not cover
+__device__ __forceinline__ bool log_needs_library(double ax) {
+  return (unsigned)(__double2hiint(ax) - 0x00100000) >= (unsigned)(0x7ff00000 - 0x00100000);
+}
+__device__ __forceinline__ double fast_log_normal(double ax, const double2* __restrict__ tab) {  // normal range only
+  const int hi = __double2hiint(ax);
   const double2 tb = tab[(hi >> 13) & 127];
-  const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(ax));
   const double r = fma(m, tb.x, -1.0);
   double q = fma(r, -1.0 / 8.0, 1.0 / 7.0);
   q = fma(r, q, -1.0 / 6.0);
@@ -295,9 +297,35 @@ __device__ __forceinline__ double fast_log_pos(double ax, const double2* __restr
   const double p1 = fma(r * r, q, r);
   return fma((double)((hi >> 20) - 1023), 0.693147180559945309417232, tb.y + p1);
 }
+__device__ __forceinline__ double fast_log_pos(double ax, const double2* __restrict__ tab) {
+  return log_needs_library(ax) ? slow_log(ax) : fast_log_normal(ax, tab);
+}
+// The same with a 32-entry table held one entry per LANE (inv32 = 1/c rounded, l32 = -log(inv32), c = 1 + lane/32) and
+// served by warp shuffles: the data-dependent shared-memory lookups of the 128-entry table conflict (11.6 wavefronts
+// per warp instead of 4: the load/store pipe was 71 % busy and the pass took 51 us); a shuffle has no banks.
+// r = m/c - 1 <= 2^-5, polynomial through r^12 (next term < 2e-21).  All 32 lanes must call it together.
+__device__ __forceinline__ double fast_log_normal_shfl(double ax, double inv32, double l32) {
+  const int hi = __double2hiint(ax);
+  const int idx = (hi >> 15) & 31;
+  const double inv = __shfl_sync(0xffffffffu, inv32, idx), lc = __shfl_sync(0xffffffffu, l32, idx);
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(ax));
+  const double r = fma(m, inv, -1.0);
+  double q = fma(r, -1.0 / 12.0, 1.0 / 11.0);
+  q = fma(r, q, -1.0 / 10.0);
+  q = fma(r, q, 1.0 / 9.0);
+  q = fma(r, q, -1.0 / 8.0);
+  q = fma(r, q, 1.0 / 7.0);
+  q = fma(r, q, -1.0 / 6.0);
+  q = fma(r, q, 1.0 / 5.0);
+  q = fma(r, q, -1.0 / 4.0);
+  q = fma(r, q, 1.0 / 3.0);
+  q = fma(r, q, -0.5);
+  const double p1 = fma(r * r, q, r);
+  return fma((double)((hi >> 20) - 1023), 0.693147180559945309417232, lc + p1);
+}
 
 template <int SPLIT>
-__global__ void __launch_bounds__(256, 3) save_moments_kernel(const double* __restrict__ f0, const double* __restrict__ f1,
+__global__ void __launch_bounds__(256, 2) save_moments_kernel(const double* __restrict__ f0, const double* __restrict__ f1,
                                                            double w, const double* __restrict__ v, long long rows,
                                                            int nv, double dv, double* __restrict__ out) {
   __shared__ double part[8][6];
@@ -308,6 +336,7 @@ __global__ void __launch_bounds__(256, 3) save_moments_kernel(const double* __re
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const double inv32 = 1.0 / (1.0 + (double)lane * (1.0 / 32.0)), l32 = -log(inv32);  // this lane's entry of the 32-table
   const long long row = (long long)blockIdx.x * (8 / SPLIT) + wid / SPLIT;
   const int q = wid % SPLIT;
   const bool live = row < rows;
@@ -347,10 +376,33 @@ __global__ void __launch_bounds__(256, 3) save_moments_kernel(const double* __re
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) va[u] = __ldg(v2 + i + 32 * u);
+        // the eight cells of a batch share ONE range test for the logarithm (a branch per cell cost more instructions
+        // than the arithmetic: 70 per cell)
+        double xs[8], lg[8];
+        bool special = false;
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-          add(xa[u].x, ya[u].x, va[u].x, s);
-          add(xa[u].y, ya[u].y, va[u].y, s1);
+          xs[2 * u] = b ? xa[u].x + w * (ya[u].x - xa[u].x) : xa[u].x;  // diffrax's linear dense output (adept/_base_.py:40)
+          xs[2 * u + 1] = b ? xa[u].y + w * (ya[u].y - xa[u].y) : xa[u].y;
+          special = special || log_needs_library(fabs(xs[2 * u])) || log_needs_library(fabs(xs[2 * u + 1]));
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) lg[u] = fast_log_normal_shfl(fabs(xs[u]), inv32, l32);  // every lane: shuffles inside
+        if (special) {  // zero / subnormal / inf / NaN somewhere in this lane's batch: the library redoes those cells
+#pragma unroll
+          for (int u = 0; u < 8; u++)
+            if (log_needs_library(fabs(xs[u]))) lg[u] = slow_log(fabs(xs[u]));
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const double x = xs[u], vv = (u & 1) ? va[u >> 1].y : va[u >> 1].x;
+          double(&acc)[6] = (u & 1) ? s1 : s;
+          acc[0] += x;
+          acc[1] += x * vv;
+          acc[2] += x * (vv * vv);
+          acc[3] += x * (vv * vv * vv);
+          acc[4] = fma(-lg[u], fabs(x), acc[4]);
+          acc[5] += x * x;
         }
       }
       for (; i < n2; i += 32) {

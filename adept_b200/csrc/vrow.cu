@@ -54,6 +54,10 @@ struct VrowArgs {
   double* stage;
   unsigned int* round_ctr;
   int n_movers;
+  // Peer mode: the CTAs of the first wave start their loads spread over `stagger_cycles` SM clocks (CTA b waits
+  // b / first_wave of it).  All CTAs of a wave otherwise load at the same time (the link is the bottleneck, no SM
+  // computes), then all compute (the link idles): with one or two waves per launch nothing ever interleaves.
+  int stagger_cycles, first_wave;
 };
 
 // Peer mode with bulk transfers (PEER instantiation): the tensor maps of the P output buffers, one per rank
@@ -71,7 +75,7 @@ struct VrowCfg {
   static constexpr bool WARP_MODE = (T % 32) == 0;
   static constexpr size_t BUF_BYTES = (size_t)C::BUF * sizeof(cplx);            // == 2 rows x (N + T) doubles
   static constexpr size_t PH_BYTES = ((size_t)2 * PC::PER_SEQ * sizeof(cplx) + 127) / 128 * 128;  // phase tables
-  static constexpr size_t RED_BYTES = (size_t)2 * (WARP_MODE ? T / 32 : (T > 32 ? T : 32)) * 3 * sizeof(double);
+  static constexpr size_t RED_BYTES = (size_t)2 * (WARP_MODE ? T / 32 : (T > 32 ? T : 32)) * 6 * sizeof(double);  // 6 sums
   static constexpr size_t PCR_BYTES = (size_t)6 * T * sizeof(double);
   // ~84 KB at nv = 4096: two CTAs per SM leave ~60 KB of the 228 KB array to L1, enough for the twiddle rows in use
   static constexpr size_t SMEM = BUF_BYTES + PH_BYTES + RED_BYTES + PCR_BYTES + 16;  // + one mbarrier (peer bulk loads)
@@ -116,6 +120,12 @@ __device__ __forceinline__ void vrow_body(const CUtensorMap* out_maps, const Vro
     }
   }
 
+  if (p.nvp_shift >= 0 && p.stagger_cycles > 0 && (int)blockIdx.x < p.first_wave) {
+    const long long wait = (long long)p.stagger_cycles * (long long)blockIdx.x / p.first_wave;
+    const long long t0 = clock64();
+    while (clock64() - t0 < wait) {
+    }
+  }
   cplx x[E];
   if constexpr (PEER) {
     const size_t nvp = (size_t)1 << p.nvp_shift;
@@ -198,11 +208,13 @@ __device__ __forceinline__ void vrow_body(const CUtensorMap* out_maps, const Vro
   int parity = 0;
   const double vc = __ldg(p.v + 16 * t);
   // NOTE: spare threads (T < 32) would corrupt shared state in fp_row_fast; the launcher only uses this kernel for T >= 32
+  // (the moments of both rows behind one barrier + the collision frequencies fetched at kernel start were measured:
+  // 141.8 -> 144.3 us, the longer live ranges spill; reverted)
 #pragma unroll 1
   for (int s = 0; s < 2; s++) {
     double* row = rowA + s * ROW_STRIDE;
     fp_row_fast<16, TMA_OUT, CC>(row, red, pcr, parity, t, T, N, vc, p.dv, p.dt_fp,
-                             __dmul_rn(p.trow ? p.trow[TROW_NU_FP] : p.nu_fp_scale, p.nu_fp[row0 + s]), p.model);
+                                 __dmul_rn(p.trow ? p.trow[TROW_NU_FP] : p.nu_fp_scale, p.nu_fp[row0 + s]), p.model);
     if (TMA_OUT && threadIdx.x == 0) {  // the barrier that ends fp_row_fast ordered every thread's fenced stores
       if constexpr (PEER) {  // one box {16, nvp/16} per owning rank
         const int nvp = 1 << p.nvp_shift, np = N >> p.nvp_shift;
@@ -369,14 +381,16 @@ static int launch_vrow_peer(const VrowArgs& p, cudaStream_t stream) {
   return check_launch("vpush_collide_peer_kernel");
 }
 
-// ADEPT_B200_PEER_TMA=0 keeps the per-thread peer loads and stores (A/B timing of the sharded grid)
-static bool peer_tma_enabled() {
-  static int mode = -1;
-  if (mode < 0) {
+// Bulk transfers or per-thread peer loads / stores?  Measured on the 4096^2 grid (r02j, r02q): 2 ranks 237 us per step
+// with bulk transfers against 244 us, 4 ranks 178 us against 164 us (three 8 KB segments per row and peer do not make
+// up for the single issuing thread).  Default: bulk transfers for two ranks only; ADEPT_B200_PEER_TMA=0 / 1 forces one.
+static bool peer_tma_enabled(int n_peers = 2) {
+  static int mode = -2;
+  if (mode == -2) {
     const char* e = getenv("ADEPT_B200_PEER_TMA");
-    mode = (e && atoi(e) == 0) ? 0 : 1;
+    mode = e ? (atoi(e) != 0 ? 1 : 0) : -1;
   }
-  return mode == 1;
+  return mode == -1 ? n_peers == 2 : mode == 1;
 }
 
 // TMA output needs 1024-byte aligned row buffers ((nv + nv/16) * 8 bytes apart: nv >= 2048), 16-byte aligned f_out
@@ -388,7 +402,7 @@ static int launch_vrow_auto(const VrowArgs& p, cudaStream_t stream) {
                       (unsigned long long)p.npairs * 2 * (K::N / 16) < (1ull << 31);
   const bool cc = p.scheme == FP_CHANG_COOPER;
   if constexpr (LOGN >= 11) {  // peer mode with bulk transfers: whole 1 KB-multiple row segments of at most 256 chunks
-    if (p.nvp_shift >= 7 && p.nvp_shift <= 12 && tma_available() && peer_tma_enabled() &&
+    if (p.nvp_shift >= 7 && p.nvp_shift <= 12 && tma_available() && (p.stage || peer_tma_enabled(K::N >> p.nvp_shift)) &&
         (unsigned long long)p.nx_global * ((1ull << p.nvp_shift) / 16) < (1ull << 31)) {
       bool aligned = true;
       for (int j = 0; j < (K::N >> p.nvp_shift); j++)
@@ -448,6 +462,20 @@ int vpush_collide_f64(const double* fin, double* fout, int batch, int nx, int nv
     int sh = 0;
     while ((nv / n_peers) >> (sh + 1)) sh++;
     p.nvp_shift = sh, p.row0_global = row0_global, p.nx_global = nx_global > 0 ? nx_global : (long long)nx * n_peers;
+    {  // ADEPT_B200_PEER_STAGGER_US: ramp of the first wave's start times in microseconds (0 = off)
+      static int stagger_us = -1;
+      if (stagger_us < 0) {
+        const char* ev = getenv("ADEPT_B200_PEER_STAGGER_US");
+        stagger_us = ev ? atoi(ev) : 0;
+        if (stagger_us < 0 || stagger_us > 1000) stagger_us = 0;
+      }
+      int dev = 0, sms = 148, khz = 1900000;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
+      p.first_wave = 2 * sms;
+      p.stagger_cycles = (int)((long long)stagger_us * khz / 1000);
+    }
     if (row0_global < 0 || row0_global + nx > p.nx_global) {
       set_last_error("vpush_collide(peer mode): rows [%lld, %lld) outside the %lld rows of the grid", row0_global,
                      row0_global + nx, p.nx_global);
@@ -455,7 +483,7 @@ int vpush_collide_f64(const double* fin, double* fout, int batch, int nx, int nv
     }
     if (stage) {
       const bool movers_ok = n_movers == 0 || (round_ctr && n_movers >= 2 && !(n_movers & 1) && nx % n_movers == 0);
-      if (!movers_ok || nv < 2048 || !tma_available() || !peer_tma_enabled() || sh < 7) {
+      if (!movers_ok || nv < 2048 || !tma_available() || sh < 7) {
         set_last_error("vpush_collide(peer, staged): needs round counters, an even number of movers dividing the %d "
                        "local rows (got %d), nv >= 2048 and the bulk-transfer peer path", nx, n_movers);
         return ADEPT_ERR_UNSUPPORTED;

@@ -455,6 +455,27 @@ def test_save_moments_fused_pass(ops, nx, nv, interp):
         np.testing.assert_allclose(got[k], ref[k], rtol=1e-12, atol=1e-13 * np.max(np.abs(ref[k])))
 
 
+def test_save_moments_log_special_values(ops):
+    """The entropy moment uses a table-based logarithm on the normal range and the library on the rest: negative f (the
+    reference takes |f|), subnormals, huge values, and f = 0, where -|f| log|f| is NaN in the reference too."""
+    nx, nv = 8, 4096
+    f, x, v, dx, dv = make_f(nx, nv, seed=3, noise=0.0)
+    f[1, 100:200] *= -1.0
+    f[2, 7] = 5e-324
+    f[2, 9] = 1e-310
+    f[3, 11] = 1e300
+    f[4, 13] = 1.0
+    f[4, 14] = np.nextafter(1.0, 0.0)
+    f[5, 2048] = 0.0
+    got = host(ops.save_moments(dev(f), dev(v), dv)).reshape(6, nx)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ref = np.sum(-np.log(np.abs(f)) * np.abs(f), axis=1) * dv
+    assert np.isnan(ref[5]) and np.isnan(got[4][5])
+    ok = ~np.isnan(ref)
+    np.testing.assert_allclose(got[4][ok], ref[ok], rtol=1e-12)
+    np.testing.assert_allclose(got[0], np.sum(f, axis=1) * dv, rtol=1e-12)
+
+
 def test_field_moments_match_oracle():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
