@@ -300,32 +300,8 @@ __device__ __forceinline__ double fast_log_normal(double ax, const double2* __re
 __device__ __forceinline__ double fast_log_pos(double ax, const double2* __restrict__ tab) {
   return log_needs_library(ax) ? slow_log(ax) : fast_log_normal(ax, tab);
 }
-// The same with a 32-entry table held one entry per LANE (inv32 = 1/c rounded, l32 = -log(inv32), c = 1 + lane/32) and
-// served by warp shuffles: the data-dependent shared-memory lookups of the 128-entry table conflict (11.6 wavefronts
-// per warp instead of 4: the load/store pipe was 71 % busy and the pass took 51 us); a shuffle has no banks.
-// r = m/c - 1 <= 2^-5, polynomial through r^12 (next term < 2e-21).  All 32 lanes must call it together.
-__device__ __forceinline__ double fast_log_normal_shfl(double ax, double inv32, double l32) {
-  const int hi = __double2hiint(ax);
-  const int idx = (hi >> 15) & 31;
-  const double inv = __shfl_sync(0xffffffffu, inv32, idx), lc = __shfl_sync(0xffffffffu, l32, idx);
-  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(ax));
-  const double r = fma(m, inv, -1.0);
-  double q = fma(r, -1.0 / 12.0, 1.0 / 11.0);
-  q = fma(r, q, -1.0 / 10.0);
-  q = fma(r, q, 1.0 / 9.0);
-  q = fma(r, q, -1.0 / 8.0);
-  q = fma(r, q, 1.0 / 7.0);
-  q = fma(r, q, -1.0 / 6.0);
-  q = fma(r, q, 1.0 / 5.0);
-  q = fma(r, q, -1.0 / 4.0);
-  q = fma(r, q, 1.0 / 3.0);
-  q = fma(r, q, -0.5);
-  const double p1 = fma(r * r, q, r);
-  return fma((double)((hi >> 20) - 1023), 0.693147180559945309417232, lc + p1);
-}
-
 template <int SPLIT>
-__global__ void __launch_bounds__(256, 2) save_moments_kernel(const double* __restrict__ f0, const double* __restrict__ f1,
+__global__ void __launch_bounds__(256, 3) save_moments_kernel(const double* __restrict__ f0, const double* __restrict__ f1,
                                                            double w, const double* __restrict__ v, long long rows,
                                                            int nv, double dv, double* __restrict__ out) {
   __shared__ double part[8][6];
@@ -336,7 +312,6 @@ __global__ void __launch_bounds__(256, 2) save_moments_kernel(const double* __re
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const double inv32 = 1.0 / (1.0 + (double)lane * (1.0 / 32.0)), l32 = -log(inv32);  // this lane's entry of the 32-table
   const long long row = (long long)blockIdx.x * (8 / SPLIT) + wid / SPLIT;
   const int q = wid % SPLIT;
   const bool live = row < rows;
@@ -386,12 +361,13 @@ __global__ void __launch_bounds__(256, 2) save_moments_kernel(const double* __re
           xs[2 * u + 1] = b ? xa[u].y + w * (ya[u].y - xa[u].y) : xa[u].y;
           special = special || log_needs_library(fabs(xs[2 * u])) || log_needs_library(fabs(xs[2 * u + 1]));
         }
+        // (a 32-entry table served by warp shuffles instead of the shared-memory lookups was measured: 52 -> 68 us)
+        if (special) {
 #pragma unroll
-        for (int u = 0; u < 8; u++) lg[u] = fast_log_normal_shfl(fabs(xs[u]), inv32, l32);  // every lane: shuffles inside
-        if (special) {  // zero / subnormal / inf / NaN somewhere in this lane's batch: the library redoes those cells
+          for (int u = 0; u < 8; u++) lg[u] = fast_log_pos(fabs(xs[u]), logtab);
+        } else {
 #pragma unroll
-          for (int u = 0; u < 8; u++)
-            if (log_needs_library(fabs(xs[u]))) lg[u] = slow_log(fabs(xs[u]));
+          for (int u = 0; u < 8; u++) lg[u] = fast_log_normal(fabs(xs[u]), logtab);
         }
 #pragma unroll
         for (int u = 0; u < 8; u++) {

@@ -54,10 +54,6 @@ struct VrowArgs {
   double* stage;
   unsigned int* round_ctr;
   int n_movers;
-  // Peer mode: the CTAs of the first wave start their loads spread over `stagger_cycles` SM clocks (CTA b waits
-  // b / first_wave of it).  All CTAs of a wave otherwise load at the same time (the link is the bottleneck, no SM
-  // computes), then all compute (the link idles): with one or two waves per launch nothing ever interleaves.
-  int stagger_cycles, first_wave;
 };
 
 // Peer mode with bulk transfers (PEER instantiation): the tensor maps of the P output buffers, one per rank
@@ -120,12 +116,6 @@ __device__ __forceinline__ void vrow_body(const CUtensorMap* out_maps, const Vro
     }
   }
 
-  if (p.nvp_shift >= 0 && p.stagger_cycles > 0 && (int)blockIdx.x < p.first_wave) {
-    const long long wait = (long long)p.stagger_cycles * (long long)blockIdx.x / p.first_wave;
-    const long long t0 = clock64();
-    while (clock64() - t0 < wait) {
-    }
-  }
   cplx x[E];
   if constexpr (PEER) {
     const size_t nvp = (size_t)1 << p.nvp_shift;
@@ -462,20 +452,6 @@ int vpush_collide_f64(const double* fin, double* fout, int batch, int nx, int nv
     int sh = 0;
     while ((nv / n_peers) >> (sh + 1)) sh++;
     p.nvp_shift = sh, p.row0_global = row0_global, p.nx_global = nx_global > 0 ? nx_global : (long long)nx * n_peers;
-    {  // ADEPT_B200_PEER_STAGGER_US: ramp of the first wave's start times in microseconds (0 = off)
-      static int stagger_us = -1;
-      if (stagger_us < 0) {
-        const char* ev = getenv("ADEPT_B200_PEER_STAGGER_US");
-        stagger_us = ev ? atoi(ev) : 0;
-        if (stagger_us < 0 || stagger_us > 1000) stagger_us = 0;
-      }
-      int dev = 0, sms = 148, khz = 1900000;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
-      p.first_wave = 2 * sms;
-      p.stagger_cycles = (int)((long long)stagger_us * khz / 1000);
-    }
     if (row0_global < 0 || row0_global + nx > p.nx_global) {
       set_last_error("vpush_collide(peer mode): rows [%lld, %lld) outside the %lld rows of the grid", row0_global,
                      row0_global + nx, p.nx_global);
