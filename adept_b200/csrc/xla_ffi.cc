@@ -1,3 +1,4 @@
+// EXPERIMENTAL -- never compiled or run (no XLA FFI headers in the build image); excluded from the default build.
 // Layer 2 of the drop-in boundary: XLA FFI handlers that unwrap XLA buffers + the CUDA stream and forward
 // to the C ABI of include/adept_b200.h.  This is what jax.ffi.ffi_call binds inside the reference's jitted
 // diffrax loop (adept/_vlasov1d/modules.py:343-356); adept_b200/jax_ffi.py registers the symbols and pairs forward and

@@ -1,4 +1,4 @@
-"""JAX host side of the drop-in: ``jax.ffi`` custom calls into ``libadept_b200_xla.so`` (csrc/xla_ffi.cc) paired with
+"""EXPERIMENTAL (never imported here: no jax in the build image).  JAX host side of the drop-in: ``jax.ffi`` custom calls into ``libadept_b200_xla.so`` (csrc/xla_ffi.cc) paired with
 their adjoints in ``jax.custom_vjp``, and pusher classes with the constructor and call signatures of the reference
 (adept/_vlasov1d/solvers/pushers/vlasov.py:63-251, fokker_planck.py:272-443) that ``B200Vlasov1D`` installs into
 ``VlasovMaxwell``.
