@@ -117,6 +117,7 @@ SIGNATURES = {
     "adept_b200_poisson_f64": [c_dp, c_dp, c_ll, c_dp, c_i, c_i, c_i, c_d, c_d, c_dp],
     "adept_b200_axpy_f64": [c_dp, c_dp, c_d, c_dp, c_ll, c_dp],
     "adept_b200_poisson_green_f64": [c_dp, c_dp, c_ll, c_dp, c_i, c_i, c_dp],
+    "adept_b200_row_means_f64": [c_dp, c_i, c_ll, c_dp, c_dp],
     "adept_b200_field_energy_f64": [c_dp, c_dp, c_dp, c_dp, c_d, c_i, c_i, c_dp, c_dp],
     "adept_b200_ponderomotive_f64": [c_dp, c_dp, c_i, c_i, c_d, c_dp],
     "adept_b200_wave_step_f64": [c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_i, c_i, c_d, c_d, c_d, c_dp],

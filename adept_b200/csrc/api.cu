@@ -532,6 +532,11 @@ int adept_b200_poisson_green_f64(const double* rho, const double* green, long lo
   return poisson_green_f64(rho, green, green_stride, e, batch, nx, (cudaStream_t)stream);
 }
 
+int adept_b200_row_means_f64(const double* a, int rows, long long n, double* out, void* stream) {
+  ADEPT_REQUIRE(a, "a") ADEPT_REQUIRE(out, "out")
+  return row_means_f64(a, rows, n, out, (cudaStream_t)stream);
+}
+
 int adept_b200_field_energy_f64(const double* e0, const double* de0, const double* e1, const double* de1, double w,
                                 int batch, int nx, double* out, void* stream) {
   ADEPT_REQUIRE(e0, "e0") ADEPT_REQUIRE(de0, "de0") ADEPT_REQUIRE(out, "out")

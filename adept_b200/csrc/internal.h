@@ -46,6 +46,7 @@ int collide_f64(const double* fin, double* fout, int batch, int nx, int nv, cons
                 cudaStream_t stream, int sc_steps = 0, double sc_rtol = 1e-8, double sc_atol = 1e-12,
                 const double* coef_in = nullptr, double* coef_out = nullptr, int coef_div = 1);
 int diff_over_dt_f64(const double* a, const double* b, double dt, double* out, long long n, cudaStream_t stream);
+int row_means_f64(const double* a, int rows, long long n, double* out, cudaStream_t stream);
 int field_energy_f64(const double* e0, const double* de0, const double* e1, const double* de1, double w, int batch,
                      int nx, double* out, cudaStream_t stream);
 int reduce_parts_f64(const double* parts, int nparts, long long n, double scale_a, double scale_b, const double* base,

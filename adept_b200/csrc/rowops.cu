@@ -222,6 +222,41 @@ int field_energy_f64(const double* e0, const double* de0, const double* e1, cons
   return check_launch("field_energy_kernel");
 }
 
+// ---- space averages of saved moments: out[r] = mean_i a[r, i]  (the jnp.mean over x of get_default_save_func,
+// storage.py:306-323).  One CTA per row, fixed summation order; `out` may be pinned host memory (mapped): the scalars
+// of a save point then reach the host without a reduction kernel of the host framework and a separate copy.
+__global__ void __launch_bounds__(1024) row_means_kernel(const double* __restrict__ a, long long n,
+                                                        double* __restrict__ out) {
+  __shared__ double red[32];
+  const double* row = a + (long long)blockIdx.x * n;
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  for (long long i0 = threadIdx.x; i0 < n; i0 += 4 * 1024) {
+    double x[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) x[u] = (i0 + u * 1024 < n) ? row[i0 + u * 1024] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; u++) s[u] += x[u];
+  }
+  const double t = warp_sum((s[0] + s[1]) + (s[2] + s[3]));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int k = 0; k < 32; k++) tot += red[k];
+    out[blockIdx.x] = tot / (double)n;
+  }
+}
+
+int row_means_f64(const double* a, int rows, long long n, double* out, cudaStream_t stream) {
+  if (rows < 1 || n < 1) {
+    set_last_error("row_means: bad shape rows=%d n=%lld", rows, n);
+    return ADEPT_ERR_BAD_SHAPE;
+  }
+  ProfileScope prof("row_means", stream);
+  row_means_kernel<<<rows, 1024, 0, stream>>>(a, n, out);
+  return check_launch("row_means_kernel");
+}
+
 // ---- second stage of the fused x-push charge density: out[i] = base[i] + scale_b * ((sum_p parts[p, i]) * scale_a) ----
 // 64 rows per CTA; the parts are dealt to 4 thread groups (p = g, g+4, ...), each with two running sums, and combined
 // in a fixed order: deterministic, and short dependent-load chains (nparts/8 per thread).

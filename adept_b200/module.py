@@ -40,17 +40,17 @@ _V_CACHE = {}
 def default_scalars(cfg, y0, y1=None, w=0.0):
     """Scalar time series saved at every step by the reference (storage.py:286-327) for the state interpolated
     linearly between y0 and y1 (weight w); device tensors."""
+    from . import ops
+
     g = cfg["grid"]
     s = {}
     ke = 0.0
     for name, m in _species_moments(cfg, y0, y1, w, _V_CACHE).items():
         mass = g["species_params"][name]["mass"]
-        mean = torch.mean(m.reshape(6, -1), dim=1)
+        mean = ops.row_means(m.reshape(6, -1))  # the jnp.mean over x of storage.py:306-323, one launch
         s[f"mean_n_{name}"], s[f"mean_j_{name}"], s[f"mean_P_{name}"] = mean[0], mean[1], mean[2]
         s[f"mean_q_{name}"], s[f"mean_-flogf_{name}"], s[f"mean_f2_{name}"] = mean[3], mean[4], mean[5]
         ke = ke + 0.5 * mass * mean[2]
-    from . import ops
-
     e2 = ops.field_energy(y0["e"], y0["de"], None if y1 is None else y1["e"], None if y1 is None else y1["de"], w)
     s["mean_e2"], s["mean_de2"] = e2[..., 0], e2[..., 1]
     a2 = _lerp(y0, y1, w, "a") ** 2.0

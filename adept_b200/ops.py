@@ -503,6 +503,24 @@ def poisson_green(rho, green, out=None):
     return out
 
 
+def row_means(a, out=None):
+    """out[r] = mean(a[r, :]) for a 2-D tensor, one launch (the space average of the saved moments, storage.py:306-323).
+    ``out`` may be a PINNED host tensor like :func:`field_energy`'s: valid after the stream has been synchronised."""
+    if a.dim() != 2:
+        raise AdeptB200Error("row_means: expected a 2-D tensor")
+    rows, n = a.shape
+    if out is None:
+        out = torch.empty(rows, dtype=torch.float64, device=a.device)
+    if not out.is_cuda and out.is_pinned() and out.dtype == torch.float64 and out.is_contiguous():
+        out_ptr = C.c_void_p(out.data_ptr())
+    else:
+        out_ptr = _ptr(out, "out")
+    rc = _lib.load().adept_b200_row_means_f64(_ptr(a, "a"), int(rows), int(n), out_ptr, _stream())
+    _lib.check(rc, "row_means")
+    _count()
+    return out
+
+
 def field_energy(e, de, e1=None, de1=None, w=0.0, out=None):
     """{mean(e^2), mean(de^2)} per member in one launch (storage.py:316-317), optionally of the state interpolated
     towards (e1, de1) with weight w.  Returns a [batch, 2] (or [2]) tensor.  ``out`` may be a PINNED host tensor

@@ -636,7 +636,7 @@ def run_b200(args):
                 # the reference's always-on default save (storage.py:282, 306-323): mean_x sum_v {f, f v, f v^2, f v^3,
                 # -|f| log|f|, f^2} dv of the new state, one more pass over f every step, read back per step
                 ops.save_moments(st[name], v_dev, float(sgrid["dv"]), out=mom_dev)
-                mom_host[i].copy_(mom_dev.mean(dim=1), non_blocking=True)
+                ops.row_means(mom_dev, out=mom_host[i])  # mean over x, written straight into the pinned host ring
         f_back.copy_(sim.state[name], non_blocking=True)
         torch.cuda.synchronize()
         return float(diag_host[nsteps - 1, 0])

@@ -235,6 +235,11 @@ int adept_b200_axpy_f64(const double* a, const double* b, double s, double* out,
 int adept_b200_poisson_green_f64(const double* rho, const double* green, long long green_stride, double* e, int batch,
                                  int nx, void* stream);
 
+/* out[r] = mean_i a[r, i], r < rows: the average over x that get_default_save_func takes of every velocity moment
+ * (adept/_vlasov1d/storage.py:306-323), one CTA per row, fixed summation order.  `out` may be a pinned (mapped) host
+ * buffer like adept_b200_field_energy_f64's: the six scalars of a save point then travel to the host with the launch. */
+int adept_b200_row_means_f64(const double* a, int rows, long long n, double* out, void* stream);
+
 /* Field-energy scalars of the default save function (mean_e2, mean_de2; adept/_vlasov1d/storage.py:316-317), one
  * launch: out[b] = {mean(e_b^2), mean(de_b^2)} of (e0, de0)[batch, nx], or of the state interpolated linearly towards
  * (e1, de1) with weight w when those are given (both or neither). */

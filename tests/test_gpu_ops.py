@@ -455,6 +455,21 @@ def test_save_moments_fused_pass(ops, nx, nv, interp):
         np.testing.assert_allclose(got[k], ref[k], rtol=1e-12, atol=1e-13 * np.max(np.abs(ref[k])))
 
 
+@pytest.mark.parametrize("rows,n", [(6, 4096), (1, 1), (3, 5000), (6, 17280)])
+def test_row_means_device_and_pinned_out(ops, rows, n):
+    """Space average of the saved moments (storage.py:306-323): one launch, into device memory or a pinned host ring."""
+    rng = np.random.default_rng(7)
+    a = rng.standard_normal((rows, n)) + 1.0
+    ref = a.mean(axis=1)
+    got = host(ops.row_means(dev(a)))
+    np.testing.assert_allclose(got, ref, rtol=1e-13, atol=1e-15)
+    ring = torch.zeros((4, rows), dtype=torch.float64).pin_memory()
+    ops.row_means(dev(a), out=ring[2])
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(ring[2].numpy(), ref, rtol=1e-13, atol=1e-15)
+    assert float(ring[0].abs().sum() + ring[1].abs().sum() + ring[3].abs().sum()) == 0.0
+
+
 def test_save_moments_log_special_values(ops):
     """The entropy moment uses a table-based logarithm on the normal range and the library on the rest: negative f (the
     reference takes |f|), subnormals, huge values, and f = 0, where -|f| log|f| is NaN in the reference too."""
