@@ -335,16 +335,42 @@ __device__ __forceinline__ double fast_log_normal(double ax, const double2* __re
 __device__ __forceinline__ double fast_log_pos(double ax, const double2* __restrict__ tab) {
   return log_needs_library(ax) ? slow_log(ax) : fast_log_normal(ax, tab);
 }
-template <int SPLIT>
+// Variant with half the table traffic (LOGV = 1): the multiplier is not looked up but taken from the hardware reciprocal
+// seed of m (MUFU.RCP64H, about 20 bits) truncated to 7 mantissa bits, 1/2 <= q <= 1, so only -log(q) comes from a table
+// (129 eight-byte entries indexed by q's own bits: whatever the seed returns, multiplier and table entry belong together).
+// r = m q - 1 lies in (-2^-7 - 2^-20, 2^-20]; same polynomial.
+__device__ __forceinline__ double fast_log_normal_rcp(double ax, const double* __restrict__ ltab) {
+  const int hi = __double2hiint(ax);
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(ax));
+  double r0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(m));
+  int rh = __double2hiint(r0) & 0xffffe000;
+  rh = min(max(rh, 0x3fe00000), 0x3ff00000);  // q in [1/2, 1] whatever the seed's last bits are
+  const double qm = __hiloint2double(rh, 0);
+  const int j = (rh - 0x3fe00000) >> 13;      // 0 .. 128
+  const double r = fma(m, qm, -1.0);
+  double q = fma(r, -1.0 / 8.0, 1.0 / 7.0);
+  q = fma(r, q, -1.0 / 6.0);
+  q = fma(r, q, 1.0 / 5.0);
+  q = fma(r, q, -1.0 / 4.0);
+  q = fma(r, q, 1.0 / 3.0);
+  q = fma(r, q, -0.5);
+  const double p1 = fma(r * r, q, r);
+  return fma((double)((hi >> 20) - 1023), 0.693147180559945309417232, ltab[j] + p1);
+}
+template <int SPLIT, int LOGV = 0>
 __global__ void __launch_bounds__(256, 3) save_moments_kernel(const double* __restrict__ f0, const double* __restrict__ f1,
                                                            double w, const double* __restrict__ v, long long rows,
                                                            int nv, double dv, double* __restrict__ out) {
   __shared__ double part[8][6];
   __shared__ double2 logtab[128];
+  __shared__ double ltab[LOGV == 1 ? 129 : 1];
   if (threadIdx.x < 128) {
     const double inv = 1.0 / (1.0 + (double)threadIdx.x * (1.0 / 128.0));
     logtab[threadIdx.x] = make_double2(inv, -log(inv));
   }
+  if (LOGV == 1 && threadIdx.x < 129)  // q = (1 + j/128) / 2 for j < 128, q = 1 for j = 128
+    ltab[threadIdx.x] = threadIdx.x == 128 ? 0.0 : -log(0.5 * (1.0 + (double)threadIdx.x * (1.0 / 128.0)));
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const long long row = (long long)blockIdx.x * (8 / SPLIT) + wid / SPLIT;
@@ -400,6 +426,9 @@ __global__ void __launch_bounds__(256, 3) save_moments_kernel(const double* __re
         if (special) {
 #pragma unroll
           for (int u = 0; u < 8; u++) lg[u] = fast_log_pos(fabs(xs[u]), logtab);
+        } else if (LOGV == 1) {
+#pragma unroll
+          for (int u = 0; u < 8; u++) lg[u] = fast_log_normal_rcp(fabs(xs[u]), ltab);
         } else {
 #pragma unroll
           for (int u = 0; u < 8; u++) lg[u] = fast_log_normal(fabs(xs[u]), logtab);
@@ -450,7 +479,14 @@ int save_moments_f64(const double* f0, const double* f1, double w, int batch, in
   }
   const long long rows = (long long)batch * nx;
   ProfileScope prof("save_moments", stream);
-  if (nv % 16 == 0 && nv >= 2048)
+  static int logv = -1;  // ADEPT_B200_LOGVAR=1: the reciprocal-seed logarithm (fast_log_normal_rcp), A/B timing
+  if (logv < 0) {
+    const char* e = getenv("ADEPT_B200_LOGVAR");
+    logv = (e && atoi(e) == 1) ? 1 : 0;
+  }
+  if (nv % 16 == 0 && nv >= 2048 && logv == 1)
+    save_moments_kernel<4, 1><<<(unsigned)((rows + 1) / 2), 256, 0, stream>>>(f0, f1, w, v, rows, nv, dv, out);
+  else if (nv % 16 == 0 && nv >= 2048)
     save_moments_kernel<4><<<(unsigned)((rows + 1) / 2), 256, 0, stream>>>(f0, f1, w, v, rows, nv, dv, out);
   else
     save_moments_kernel<1><<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(f0, f1, w, v, rows, nv, dv, out);
