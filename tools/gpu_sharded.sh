@@ -1,11 +1,19 @@
 #!/bin/bash
-# Sharded-grid session on N GPUs: parity tests, then the strong-scaling timing of the 4096^2 grid with the peer
-# transfers as bulk copies / TMA stores (default) and as per-thread loads and stores (ADEPT_B200_PEER_TMA=0).
-R=${1:-r02j}; N=${2:-2}
+# Sharded-grid session on N GPUs: parity tests, then bench.py under torchrun (its extras carry the sharded grid's parity
+# against the oracle and its strong-scaling time).
+R=${1:-rXX}; N=${2:-2}
 O=gpurun_out
 mkdir -p $O
-timeout 600 python -m pytest tests/test_gpu_sharded.py -m gpu -q -x --timeout 240 > $O/${R}_pytest_sharded.log 2>&1; echo "pytest exit $?"; tail -3 $O/${R}_pytest_sharded.log
-for mode in ${3:-4 8 0}; do
-  ADEPT_B200_SHARDED_CE=$mode timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
-    tools/bench_sharded.py 4096 4096 100 p2p > $O/${R}_sharded_${N}gpu_ce$mode.txt 2>&1; echo "CE=$mode:"; tail -2 $O/${R}_sharded_${N}gpu_ce$mode.txt | cut -c1-600
-done
+timeout 900 python -m pytest tests/test_gpu_sharded.py -m gpu -q --timeout 600 > $O/${R}_pytest_sharded.log 2>&1; echo "pytest exit $?"; tail -3 $O/${R}_pytest_sharded.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
+    bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline > $O/${R}_bench_${N}gpu.json 2> $O/${R}_bench_${N}gpu.err
+python - <<PY
+import json
+try:
+    d = json.loads(open("$O/${R}_bench_${N}gpu.json").read().strip().splitlines()[-1])
+    print(d["n_gpus"], d["ms_per_step"], d["value"], "e2e", d["e2e"]["value"])
+    print(json.dumps(d["extra"].get("sharded"))[:1200])
+    print(json.dumps(d["extra"].get("ensemble_c4"))[:500])
+except Exception as e:
+    print("bench failed", e); print(open("$O/${R}_bench_${N}gpu.err").read()[-3000:])
+PY
