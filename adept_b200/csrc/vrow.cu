@@ -71,7 +71,7 @@ struct VrowCfg {
   static constexpr bool WARP_MODE = (T % 32) == 0;
   static constexpr size_t BUF_BYTES = (size_t)C::BUF * sizeof(cplx);            // == 2 rows x (N + T) doubles
   static constexpr size_t PH_BYTES = ((size_t)2 * PC::PER_SEQ * sizeof(cplx) + 127) / 128 * 128;  // phase tables
-  static constexpr size_t RED_BYTES = (size_t)2 * (WARP_MODE ? T / 32 : (T > 32 ? T : 32)) * 6 * sizeof(double);  // 6 sums
+  static constexpr size_t RED_BYTES = (size_t)2 * (WARP_MODE ? T / 32 : (T > 32 ? T : 32)) * 6 * sizeof(double);  // room for the three moments of both rows (row_reduce<6>; fp_row_fast uses half)
   static constexpr size_t PCR_BYTES = (size_t)6 * T * sizeof(double);
   // ~84 KB at nv = 4096: two CTAs per SM leave ~60 KB of the 228 KB array to L1, enough for the twiddle rows in use
   static constexpr size_t SMEM = BUF_BYTES + PH_BYTES + RED_BYTES + PCR_BYTES + 16;  // + one mbarrier (peer bulk loads)
